@@ -1,0 +1,94 @@
+"""Deterministic synthetic scenes (BASELINE.json configs).
+
+Each generator returns a float32 array of rows ``(x, y, angle, half_w, half_h, is_static)`` in body
+creation order; body 0 is always the static ground.  No RNG.  The scene shapes follow the
+reference demo's box stacks (reference src/main.cpp:82-230: ground + rows of (10,5) half-size
+boxes), scaled to the BASELINE sizes.
+"""
+import numpy as np
+
+BOX = (10.0, 5.0)
+GRAVITY = -200.0
+DT = 1.0 / 60.0
+
+
+def _ground(half_width):
+    return [(0.0, 0.0, 0.0, float(half_width), 10.0, 1.0)]
+
+
+def pyramid(rows, pitch=21.0, x0=0.0, ground=True, ground_half_width=1e7):
+    """Brick pyramid: row r has rows-r boxes at x=(i-(rows-r)*0.5)*pitch, y=15+10r."""
+    out = _ground(ground_half_width) if ground else []
+    for r in range(rows):
+        n = rows - r
+        i = np.arange(n, dtype=np.float64)
+        xs = x0 + (i - n * 0.5) * pitch
+        for x in xs:
+            out.append((float(x), 15.0 + 10.0 * r, 0.0, BOX[0], BOX[1], 0.0))
+    return np.asarray(out, dtype=np.float32)
+
+
+def pyramid_fast(rows, pitch=21.0, x0=0.0, ground_half_width=1e7):
+    """Vectorised pyramid() for the 1 M-box scene (rows=1414)."""
+    r = np.repeat(np.arange(rows), rows - np.arange(rows))
+    n = rows - r
+    starts = np.concatenate([[0], np.cumsum(rows - np.arange(rows))[:-1]])
+    i = np.arange(r.size) - starts[r]
+    xs = x0 + (i - n * 0.5) * pitch
+    ys = 15.0 + 10.0 * r
+    body = np.zeros((r.size + 1, 6), dtype=np.float32)
+    body[0] = (0.0, 0.0, 0.0, ground_half_width, 10.0, 1.0)
+    body[1:, 0] = xs
+    body[1:, 1] = ys
+    body[1:, 3] = BOX[0]
+    body[1:, 4] = BOX[1]
+    return body
+
+
+def stack(columns, height, pitch=30.0, ground_half_width=1e7):
+    """Horizontal row of box columns: x=(c-columns/2)*pitch, y=15+10h, column-major order."""
+    c = np.repeat(np.arange(columns), height)
+    h = np.tile(np.arange(height), columns)
+    body = np.zeros((columns * height + 1, 6), dtype=np.float32)
+    body[0] = (0.0, 0.0, 0.0, ground_half_width, 10.0, 1.0)
+    body[1:, 0] = (c - columns / 2) * pitch
+    body[1:, 1] = 15.0 + 10.0 * h
+    body[1:, 3] = BOX[0]
+    body[1:, 4] = BOX[1]
+    return body
+
+
+def multi_island(count, rows, pitch=21.0, ground_half_width=1e7):
+    """`count` separate pyramids of `rows` rows side by side (independent islands: the ground is
+    static and does not merge islands, reference src/Solver.cpp:304,316-317)."""
+    one = pyramid_fast(rows, pitch)[1:]
+    span = rows * pitch + 2 * pitch
+    body = np.zeros((count * one.shape[0] + 1, 6), dtype=np.float32)
+    body[0] = (0.0, 0.0, 0.0, ground_half_width, 10.0, 1.0)
+    for k in range(count):
+        blk = one.copy()
+        blk[:, 0] = (one[:, 0].astype(np.float64) + (k - count / 2) * span).astype(np.float32)
+        body[1 + k * one.shape[0] : 1 + (k + 1) * one.shape[0]] = blk
+    return body
+
+
+SCENES = {
+    # BASELINE.json configs[0..4]
+    "pyramid_1k": lambda: pyramid_fast(45),
+    "stack_100k": lambda: stack(10000, 10),
+    "pyramid_1m": lambda: pyramid_fast(1414),
+    "islands_1m": lambda: multi_island(1024, 44),
+    "stack_10m": lambda: stack(100000, 100, pitch=21.0),
+    # smaller relatives used by tests
+    "pyramid_10": lambda: pyramid_fast(10),
+    "pyramid_10k": lambda: pyramid_fast(141),
+    "pyramid_100k": lambda: pyramid_fast(447),
+    "stack_1k": lambda: stack(100, 10),
+    "stack_10k": lambda: stack(1000, 10),
+    "islands_8x10": lambda: multi_island(8, 10),
+    "islands_64x20": lambda: multi_island(64, 20),
+}
+
+
+def make(name):
+    return SCENES[name]()
