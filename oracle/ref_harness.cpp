@@ -164,7 +164,18 @@ void ref_step_staged(void* h, float dt, int solveMode, int islandMode, int conta
     }
     STAGE(0, w.IntegrateVelocity(*r->queue, dt));
     STAGE(1, w.collider.UpdateBroadphase(w.bodies.data, w.bodies.size));
-    STAGE(2, w.collider.UpdatePairs(*r->queue, w.bodies.data, w.bodies.size));
+    // bit 8 of stage_mask: take UpdatePairsParallel even with 0 workers.  With WorkQueue(0) its
+    // parallelFor runs inline on the caller, so the pair order is the serial sweep order, but it
+    // goes through contains()+insert() and so avoids the DenseHash tombstone corruption that
+    // UpdatePairsSerial trips on scenes with manifold churn.
+    if (stage_mask & 0x100)
+    {
+        STAGE(2, w.collider.UpdatePairsParallel(*r->queue, w.bodies.data, w.bodies.size));
+    }
+    else
+    {
+        STAGE(2, w.collider.UpdatePairs(*r->queue, w.bodies.data, w.bodies.size));
+    }
     STAGE(3, w.collider.UpdateManifolds(*r->queue, w.bodies.data));
     STAGE(4, w.collider.PackManifolds(w.bodies.data));
     STAGE(5, w.RefreshContactJoints());
@@ -229,14 +240,16 @@ int ref_prepare_indices(void* h, int groupSize, int* out_index)
 void ref_solve_joints(void* bodies, int bodiesCount, void* joints, int jointCount, const void* contactPoints,
     int contactPointCount, int solveMode, int islandMode, int contactIters, int penetrationIters, int workers, int* out_index)
 {
-    (void)contactPointCount;
+    // the SIMD gathers use aligned 32-byte loads on ContactPoint rows: keep them in an AlignedArray
+    AlignedArray<ContactPoint> cps;
+    cps.resize(contactPointCount);
+    memcpy(cps.data, contactPoints, size_t(contactPointCount) * sizeof(ContactPoint));
     WorkQueue queue(workers);
     Solver solver;
     solver.contactJoints.resize(jointCount);
     memcpy(solver.contactJoints.data, joints, size_t(jointCount) * sizeof(ContactJoint));
     Configuration c = make_config(solveMode, islandMode, contactIters, penetrationIters);
-    solver.SolveJoints(queue, static_cast<RigidBody*>(bodies), bodiesCount,
-        const_cast<ContactPoint*>(static_cast<const ContactPoint*>(contactPoints)), c);
+    solver.SolveJoints(queue, static_cast<RigidBody*>(bodies), bodiesCount, cps.data, c);
     memcpy(joints, solver.contactJoints.data, size_t(jointCount) * sizeof(ContactJoint));
     if (out_index) memcpy(out_index, solver.joint_index.data, size_t(jointCount) * sizeof(int));
 }

@@ -82,6 +82,7 @@ STAGES = (
     "PrepareIndices",
 )
 ALL_STAGES = 0xFF
+SAFE_PAIRS = 0x100  # route UpdatePairs through UpdatePairsParallel (see ref_harness.cpp)
 
 
 class RefWorld:
@@ -107,8 +108,14 @@ class RefWorld:
         for x, y, a, sx, sy, st in np.asarray(scene, dtype=np.float32).tolist():
             add(self.h, x, y, a, sx, sy, int(st))
 
-    def step(self, dt=1.0 / 60.0, solve=T.SOLVE_AVX2, island=T.ISLAND_SINGLE, iters=(20, 20)):
-        self.l.ref_step(self.h, dt, solve, island, iters[0], iters[1])
+    def step(self, dt=1.0 / 60.0, solve=T.SOLVE_AVX2, island=T.ISLAND_SINGLE, iters=(20, 20), safe_pairs=True):
+        """One World::Update.  safe_pairs=True runs the same eight stages through the public stage
+        functions but takes UpdatePairsParallel (identical pair order with 0 workers, immune to the
+        reference's DenseHash tombstone bug); safe_pairs=False calls World::Update itself."""
+        if safe_pairs:
+            self.l.ref_step_staged(self.h, dt, solve, island, iters[0], iters[1], ALL_STAGES | SAFE_PAIRS)
+        else:
+            self.l.ref_step(self.h, dt, solve, island, iters[0], iters[1])
 
     def step_staged(self, dt=1.0 / 60.0, solve=T.SOLVE_AVX2, island=T.ISLAND_SINGLE, iters=(20, 20), mask=ALL_STAGES):
         self.l.ref_step_staged(self.h, dt, solve, island, iters[0], iters[1], mask)
