@@ -1,0 +1,187 @@
+/* phyx_b200 — C ABI of the B200 (sm_100a) hot path behind World::Update().
+ *
+ * The reference (zeux/phyx @ 327b6c96) has no plugin/FFI layer: its "operator API" is the C++
+ * member surface World / Collider / Solver.  This header is the boundary a
+ * drop-in replacement binds instead: every entry point replaces one reference stage and takes
+ * the reference's own POD records (plain pointers and sizes, no C++ or torch types), so the host
+ * mirror in phyx_b200/host/ (same class and member names as the reference) — or a patched copy
+ * of the reference itself, see INTEGRATION.md — forwards its stage calls here.
+ *
+ * All functions return 0 on success, a non-zero phyx_b200_status otherwise; the message is
+ * available from phyx_b200_last_error().  Nothing here falls back to the CPU: if no CUDA device
+ * is present phyx_b200_create fails.
+ *
+ * One context = one World on one device.  A context is driven by one host thread at a time
+ * (the reference's Update is not re-entrant either, World.cpp:19-37).
+ */
+#ifndef PHYX_B200_H
+#define PHYX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PHYX_B200_API __declspec(dllexport)
+#else
+#define PHYX_B200_API __attribute__((visibility("default")))
+#endif
+
+/* ---- records: the reference's own layouts, sizes pinned by static_assert in the library ------ */
+
+typedef struct { float x, y; } phyx_vec2;
+
+/* RigidBody, reference src/RigidBody.h:12-58 (128 B) */
+typedef struct {
+    uint32_t index;
+    phyx_vec2 geom_size;
+    phyx_vec2 geom_xVector, geom_yVector, geom_pos;
+    phyx_vec2 aabb_min, aabb_max;
+    phyx_vec2 velocity, acceleration, displacingVelocity;
+    float angularVelocity, angularAcceleration, displacingAngularVelocity;
+    float invMass, invInertia;
+    phyx_vec2 xVector, yVector, pos;
+    int32_t lastIteration, lastDisplacementIteration;
+} phyx_rigid_body;
+
+/* ContactJoint, reference src/Joints.h:6-23 (20 B) */
+typedef struct {
+    int32_t contactPointIndex, body1Index, body2Index;
+    float normalLimiter_accumulatedImpulse, frictionLimiter_accumulatedImpulse;
+} phyx_contact_joint;
+
+/* ContactPoint, reference src/Manifold.h:12-43 (32 B) */
+typedef struct {
+    phyx_vec2 delta1, delta2, normal;
+    uint8_t isMerged, isNewlyCreated, pad_[2];
+    int32_t solverIndex;
+} phyx_contact_point;
+
+/* Manifold, reference src/Manifold.h:45-68 (16 B) */
+typedef struct { int32_t body1Index, body2Index, pointCount, pointIndex; } phyx_manifold;
+
+/* Collider::BroadphaseEntry, reference src/Collider.h:45-50 (20 B) */
+typedef struct { float minx, maxx, centery, extenty; uint32_t index; } phyx_broadphase_entry;
+
+typedef struct { int32_t body1Index, body2Index; } phyx_pair;
+
+typedef enum {
+    PHYX_B200_OK = 0,
+    PHYX_B200_ERR_CUDA = 1,        /* a CUDA runtime call failed (message has the cudaError) */
+    PHYX_B200_ERR_ARGUMENT = 2,    /* null pointer, negative size, index out of range */
+    PHYX_B200_ERR_NO_DEVICE = 3,   /* no CUDA device / device is not sm_100 */
+    PHYX_B200_ERR_CAPACITY = 4,    /* caller buffer too small (required size is reported) */
+    PHYX_B200_ERR_STATE = 5        /* call order violated (e.g. sweep before update_broadphase) */
+} phyx_b200_status;
+
+/* How the joints are ordered for the sequential-impulse sweeps. */
+typedef enum {
+    /* Graph colouring on the device (the reference's independent-joint grouping, Solver.cpp:217-273,
+     * widened from SIMD-8 groups to whole colours); per-joint skip rule.  Throughput mode. */
+    PHYX_B200_SCHEDULE_COLOUR = 0,
+    /* Replay of the reference's AVX2 order: PrepareIndices(N=8) groups + scalar tail, executed as
+     * dependency levels, with the AVX2 8-lane skip rule.  Dependency-equivalent to
+     * Solve_AVX2 / Island_Single, hence bit-comparable with it.  Parity mode. */
+    PHYX_B200_SCHEDULE_REPLAY_AVX2 = 1,
+    /* As above for Solve_SSE2 (N=4) and Solve_Scalar (N=1). */
+    PHYX_B200_SCHEDULE_REPLAY_SSE2 = 2,
+    PHYX_B200_SCHEDULE_REPLAY_SCALAR = 3
+} phyx_b200_schedule;
+
+typedef struct {
+    int32_t contactIterationsCount;       /* Configuration.h:21 */
+    int32_t penetrationIterationsCount;   /* Configuration.h:22 */
+    int32_t schedule;                     /* phyx_b200_schedule */
+    int32_t flags;                        /* PHYX_B200_SOLVE_* */
+} phyx_b200_solve_config;
+
+#define PHYX_B200_SOLVE_STATIC_DEPS 1     /* replay: also order joints that share a STATIC body (exact
+                                             lastIteration visibility; serialises ground contacts) */
+#define PHYX_B200_SOLVE_KEEP_SCHEDULE 2   /* reuse the schedule built by the previous solve call if the
+                                             joint (body1,body2) list is unchanged */
+
+typedef struct {
+    int32_t joints, slots, levels;             /* schedule shape: slots >= joints (padding), levels = colours */
+    int32_t contactIterationsRun, penetrationIterationsRun;  /* with the productive early-out */
+    int32_t staticHazards;                     /* see DESIGN.md "static bodies"; 0 => replay is exact */
+    float ms_schedule, ms_refresh, ms_iterations, ms_finish, ms_total;   /* CUDA-event times */
+    float ms_h2d, ms_d2h;
+} phyx_b200_solve_stats;
+
+typedef struct {
+    int64_t tests;     /* sweep tests: j visited before the x-break (Collider.cpp:303-307) */
+    int64_t pairs;     /* pairs that also pass the y test (hash lookups in the reference) */
+    float ms_sort, ms_sweep, ms_total;
+} phyx_b200_broadphase_stats;
+
+typedef struct phyx_b200_ctx phyx_b200_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+PHYX_B200_API int phyx_b200_create(int device, phyx_b200_ctx** out);
+PHYX_B200_API void phyx_b200_destroy(phyx_b200_ctx* ctx);
+PHYX_B200_API const char* phyx_b200_last_error(void);
+PHYX_B200_API const char* phyx_b200_version(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+PHYX_B200_API int64_t phyx_b200_launch_count(const phyx_b200_ctx* ctx);
+/* CUDA stream all work of this context is issued on (cudaStream_t as void*), for event timing */
+PHYX_B200_API void* phyx_b200_stream(const phyx_b200_ctx* ctx);
+PHYX_B200_API int phyx_b200_synchronize(phyx_b200_ctx* ctx);
+
+/* ---- bodies: World::bodies (AlignedArray<RigidBody>, World.h:32) <-> SoA in HBM ---------------- */
+/* Replaces nothing in the reference (there is no device boundary there); it is the H2D/D2H hop of
+ * the drop-in.  upload converts the AoS records to the device SoA, download converts back and
+ * fills every field the reference's stages write (velocity .. coords, geom.coords, geom.aabb). */
+PHYX_B200_API int phyx_b200_upload_bodies(phyx_b200_ctx* ctx, const phyx_rigid_body* bodies, int count);
+PHYX_B200_API int phyx_b200_download_bodies(phyx_b200_ctx* ctx, phyx_rigid_body* bodies, int count);
+PHYX_B200_API int phyx_b200_body_count(const phyx_b200_ctx* ctx);
+
+/* ---- World::IntegrateVelocity / IntegratePosition, reference src/World.cpp:39-70 -------------- */
+PHYX_B200_API int phyx_b200_integrate_velocity(phyx_b200_ctx* ctx, float dt, float gravity);
+PHYX_B200_API int phyx_b200_integrate_position(phyx_b200_ctx* ctx, float dt);
+
+/* ---- Collider::UpdateBroadphase, reference src/Collider.cpp:251-284 --------------------------- */
+/* key = radixFloat(aabb.min.x), stable 3-pass (11/11/10 bit) LSD radix sort, gather entries. */
+PHYX_B200_API int phyx_b200_update_broadphase(phyx_b200_ctx* ctx);
+/* Collider::broadphase (Collider.h:65) for host readers */
+PHYX_B200_API int phyx_b200_download_broadphase(phyx_b200_ctx* ctx, phyx_broadphase_entry* entries, int capacity);
+
+/* ---- the sweep of Collider::UpdatePairs*, reference src/Collider.cpp:296-366 ------------------- */
+/* Every (index_i, index_j) that passes the x-break and the y test, in the reference's emission
+ * order (i ascending, then j ascending in sorted order).  The manifold-map filter stays with the
+ * caller (Collider.cpp:311,358).  If the list is longer than `capacity` nothing is written,
+ * *count receives the required size and PHYX_B200_ERR_CAPACITY is returned. */
+PHYX_B200_API int phyx_b200_sweep_pairs(phyx_b200_ctx* ctx, phyx_pair* pairs, int64_t capacity, int64_t* count,
+    phyx_b200_broadphase_stats* stats);
+
+/* ---- Solver::SolveJoints, reference src/Solver.cpp:17-119 ------------------------------------- */
+/* Runs PrepareBodies .. FinishBodies on the bodies resident in the context: velocities and
+ * displacing velocities are updated on the device, the cached impulses are written back into
+ * `joints` (Solver::contactJoints, Solver.h:108). */
+PHYX_B200_API int phyx_b200_solve_joints(phyx_b200_ctx* ctx, phyx_contact_joint* joints, int jointCount,
+    const phyx_contact_point* contactPoints, int contactPointCount, const phyx_b200_solve_config* config,
+    phyx_b200_solve_stats* stats);
+
+/* The schedule the last solve used: slots[k] = joint index or -1, levels[l] = {start, grouped_end,
+ * end} (same meaning as oracle/phyx_oracle.h).  Pass NULL to query sizes. */
+PHYX_B200_API int phyx_b200_get_schedule(phyx_b200_ctx* ctx, int32_t* slots, int32_t slotCapacity,
+    int32_t* levels3, int32_t levelCapacity, int32_t* slotCount, int32_t* levelCount);
+
+/* ---- device-resident variants (inputs already in HBM; used for kernel-only timing) ------------ */
+/* Stage joints + contact points in HBM once ... */
+PHYX_B200_API int phyx_b200_stage_joints(phyx_b200_ctx* ctx, const phyx_contact_joint* joints, int jointCount,
+    const phyx_contact_point* contactPoints, int contactPointCount);
+/* ... then solve them in place (cached impulses stay on the device; read with fetch_joints). */
+PHYX_B200_API int phyx_b200_solve_staged(phyx_b200_ctx* ctx, const phyx_b200_solve_config* config, phyx_b200_solve_stats* stats);
+PHYX_B200_API int phyx_b200_fetch_joints(phyx_b200_ctx* ctx, phyx_contact_joint* joints, int jointCount);
+/* snapshot / restore of the resident body state (so every timed step does identical work) */
+PHYX_B200_API int phyx_b200_snapshot_bodies(phyx_b200_ctx* ctx);
+PHYX_B200_API int phyx_b200_restore_bodies(phyx_b200_ctx* ctx);
+/* sweep without the D2H copy: counts only */
+PHYX_B200_API int phyx_b200_sweep_pairs_resident(phyx_b200_ctx* ctx, phyx_b200_broadphase_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

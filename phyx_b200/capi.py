@@ -1,0 +1,252 @@
+"""ctypes binding of the C ABI in include/phyx_b200.h (phyx_b200/libphyx_b200.so).
+
+This is the only way Python reaches the hot path: there is no Python or CPU implementation behind
+it.  If the shared library has not been built, or no B200 is present, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import types as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libphyx_b200.so")
+
+SCHEDULE_COLOUR, SCHEDULE_REPLAY_AVX2, SCHEDULE_REPLAY_SSE2, SCHEDULE_REPLAY_SCALAR = 0, 1, 2, 3
+SOLVE_STATIC_DEPS, SOLVE_KEEP_SCHEDULE = 1, 2
+
+LEVEL = np.dtype([("start", np.int32), ("grouped_end", np.int32), ("end", np.int32)])
+
+# every symbol include/phyx_b200.h declares (tests/test_abi.py checks the header against this list
+# and the built library against both)
+EXPORTS = (
+    "phyx_b200_create",
+    "phyx_b200_destroy",
+    "phyx_b200_last_error",
+    "phyx_b200_version",
+    "phyx_b200_launch_count",
+    "phyx_b200_stream",
+    "phyx_b200_synchronize",
+    "phyx_b200_upload_bodies",
+    "phyx_b200_download_bodies",
+    "phyx_b200_body_count",
+    "phyx_b200_integrate_velocity",
+    "phyx_b200_integrate_position",
+    "phyx_b200_update_broadphase",
+    "phyx_b200_download_broadphase",
+    "phyx_b200_sweep_pairs",
+    "phyx_b200_solve_joints",
+    "phyx_b200_get_schedule",
+    "phyx_b200_stage_joints",
+    "phyx_b200_solve_staged",
+    "phyx_b200_fetch_joints",
+    "phyx_b200_snapshot_bodies",
+    "phyx_b200_restore_bodies",
+    "phyx_b200_sweep_pairs_resident",
+)
+
+
+class SolveConfig(C.Structure):
+    _fields_ = [
+        ("contactIterationsCount", C.c_int32),
+        ("penetrationIterationsCount", C.c_int32),
+        ("schedule", C.c_int32),
+        ("flags", C.c_int32),
+    ]
+
+
+class SolveStats(C.Structure):
+    _fields_ = [
+        ("joints", C.c_int32),
+        ("slots", C.c_int32),
+        ("levels", C.c_int32),
+        ("contactIterationsRun", C.c_int32),
+        ("penetrationIterationsRun", C.c_int32),
+        ("staticHazards", C.c_int32),
+        ("ms_schedule", C.c_float),
+        ("ms_refresh", C.c_float),
+        ("ms_iterations", C.c_float),
+        ("ms_finish", C.c_float),
+        ("ms_total", C.c_float),
+        ("ms_h2d", C.c_float),
+        ("ms_d2h", C.c_float),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class BroadphaseStats(C.Structure):
+    _fields_ = [("tests", C.c_int64), ("pairs", C.c_int64), ("ms_sort", C.c_float), ("ms_sweep", C.c_float), ("ms_total", C.c_float)]
+
+
+class PhyxError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def load():
+    """Load libphyx_b200.so.  Raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise PhyxError(f"{LIB_PATH} is missing: build it with `make -C phyx_b200/csrc` (there is no CPU fallback)")
+    l = C.CDLL(LIB_PATH)
+    vp, i32, f32, i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+    l.phyx_b200_last_error.restype = C.c_char_p
+    l.phyx_b200_version.restype = C.c_char_p
+    l.phyx_b200_create.argtypes = [i32, C.POINTER(vp)]
+    l.phyx_b200_destroy.argtypes = [vp]
+    l.phyx_b200_destroy.restype = None
+    l.phyx_b200_launch_count.argtypes = [vp]
+    l.phyx_b200_launch_count.restype = i64
+    l.phyx_b200_stream.argtypes = [vp]
+    l.phyx_b200_stream.restype = vp
+    l.phyx_b200_synchronize.argtypes = [vp]
+    l.phyx_b200_upload_bodies.argtypes = [vp, vp, i32]
+    l.phyx_b200_download_bodies.argtypes = [vp, vp, i32]
+    l.phyx_b200_body_count.argtypes = [vp]
+    l.phyx_b200_integrate_velocity.argtypes = [vp, f32, f32]
+    l.phyx_b200_integrate_position.argtypes = [vp, f32]
+    l.phyx_b200_update_broadphase.argtypes = [vp]
+    l.phyx_b200_download_broadphase.argtypes = [vp, vp, i32]
+    l.phyx_b200_sweep_pairs.argtypes = [vp, vp, i64, C.POINTER(i64), C.POINTER(BroadphaseStats)]
+    l.phyx_b200_sweep_pairs_resident.argtypes = [vp, C.POINTER(BroadphaseStats)]
+    l.phyx_b200_solve_joints.argtypes = [vp, vp, i32, vp, i32, C.POINTER(SolveConfig), C.POINTER(SolveStats)]
+    l.phyx_b200_get_schedule.argtypes = [vp, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    l.phyx_b200_stage_joints.argtypes = [vp, vp, i32, vp, i32]
+    l.phyx_b200_solve_staged.argtypes = [vp, C.POINTER(SolveConfig), C.POINTER(SolveStats)]
+    l.phyx_b200_fetch_joints.argtypes = [vp, vp, i32]
+    l.phyx_b200_snapshot_bodies.argtypes = [vp]
+    l.phyx_b200_restore_bodies.argtypes = [vp]
+    _LIB = l
+    return l
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One device context = one World's state in HBM (phyx_b200_ctx)."""
+
+    def __init__(self, device=0):
+        self.l = load()
+        h = C.c_void_p()
+        self._check(self.l.phyx_b200_create(device, C.byref(h)))
+        self.h = h
+
+    def _check(self, status):
+        if status != 0:
+            raise PhyxError(f"phyx_b200 status {status}: {self.l.phyx_b200_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.l.phyx_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- bodies ----
+    def upload_bodies(self, bodies):
+        b = np.ascontiguousarray(bodies, dtype=T.RIGID_BODY)
+        self._check(self.l.phyx_b200_upload_bodies(self.h, _p(b), b.shape[0]))
+
+    def download_bodies(self, out=None):
+        n = self.l.phyx_b200_body_count(self.h)
+        out = np.zeros(n, dtype=T.RIGID_BODY) if out is None else out
+        self._check(self.l.phyx_b200_download_bodies(self.h, _p(out), n))
+        return out
+
+    def integrate_velocity(self, dt, gravity):
+        self._check(self.l.phyx_b200_integrate_velocity(self.h, dt, gravity))
+
+    def integrate_position(self, dt):
+        self._check(self.l.phyx_b200_integrate_position(self.h, dt))
+
+    def snapshot_bodies(self):
+        self._check(self.l.phyx_b200_snapshot_bodies(self.h))
+
+    def restore_bodies(self):
+        self._check(self.l.phyx_b200_restore_bodies(self.h))
+
+    # ---- broadphase ----
+    def update_broadphase(self):
+        self._check(self.l.phyx_b200_update_broadphase(self.h))
+
+    def download_broadphase(self):
+        n = self.l.phyx_b200_body_count(self.h)
+        out = np.zeros(n, dtype=T.BROADPHASE_ENTRY)
+        self._check(self.l.phyx_b200_download_broadphase(self.h, _p(out), n))
+        return out
+
+    def sweep_pairs(self, capacity=None):
+        n = self.l.phyx_b200_body_count(self.h)
+        cap = capacity if capacity is not None else 8 * n + 1024
+        stats = BroadphaseStats()
+        while True:
+            out = np.zeros((cap, 2), dtype=np.int32)
+            cnt = C.c_int64(0)
+            st = self.l.phyx_b200_sweep_pairs(self.h, _p(out), cap, C.byref(cnt), C.byref(stats))
+            if st == 4 and capacity is None:  # PHYX_B200_ERR_CAPACITY: retry with the reported size
+                cap = int(cnt.value)
+                continue
+            self._check(st)
+            return out[: cnt.value], stats
+
+    def sweep_pairs_resident(self):
+        stats = BroadphaseStats()
+        self._check(self.l.phyx_b200_sweep_pairs_resident(self.h, C.byref(stats)))
+        return stats
+
+    # ---- solve ----
+    def solve_joints(self, joints, contact_points, iters=(20, 20), schedule=SCHEDULE_COLOUR, flags=0):
+        """Solver::SolveJoints on the resident bodies.  Returns (joints_out, stats)."""
+        j = np.array(joints, dtype=T.CONTACT_JOINT, copy=True)
+        cp = np.ascontiguousarray(contact_points, dtype=T.CONTACT_POINT)
+        cfg = SolveConfig(iters[0], iters[1], schedule, flags)
+        stats = SolveStats()
+        self._check(self.l.phyx_b200_solve_joints(self.h, _p(j), j.shape[0], _p(cp), cp.shape[0], C.byref(cfg), C.byref(stats)))
+        return j, stats
+
+    def stage_joints(self, joints, contact_points):
+        j = np.ascontiguousarray(joints, dtype=T.CONTACT_JOINT)
+        cp = np.ascontiguousarray(contact_points, dtype=T.CONTACT_POINT)
+        self._check(self.l.phyx_b200_stage_joints(self.h, _p(j), j.shape[0], _p(cp), cp.shape[0]))
+        self._staged = j.shape[0]
+
+    def solve_staged(self, iters=(20, 20), schedule=SCHEDULE_COLOUR, flags=0):
+        cfg = SolveConfig(iters[0], iters[1], schedule, flags)
+        stats = SolveStats()
+        self._check(self.l.phyx_b200_solve_staged(self.h, C.byref(cfg), C.byref(stats)))
+        return stats
+
+    def fetch_joints(self):
+        out = np.zeros(self._staged, dtype=T.CONTACT_JOINT)
+        self._check(self.l.phyx_b200_fetch_joints(self.h, _p(out), out.shape[0]))
+        return out
+
+    def get_schedule(self):
+        ns, nl = C.c_int32(0), C.c_int32(0)
+        self._check(self.l.phyx_b200_get_schedule(self.h, None, 0, None, 0, C.byref(ns), C.byref(nl)))
+        slots = np.zeros(ns.value, dtype=np.int32)
+        levels = np.zeros(nl.value, dtype=LEVEL)
+        self._check(self.l.phyx_b200_get_schedule(self.h, _p(slots), ns.value, _p(levels), nl.value, C.byref(ns), C.byref(nl)))
+        return slots, levels
+
+    def launch_count(self):
+        return int(self.l.phyx_b200_launch_count(self.h))
+
+    def stream(self):
+        return int(self.l.phyx_b200_stream(self.h) or 0)
+
+    def synchronize(self):
+        self._check(self.l.phyx_b200_synchronize(self.h))

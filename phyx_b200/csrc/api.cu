@@ -1,0 +1,403 @@
+// phyx_b200 — the C ABI (include/phyx_b200.h): context lifetime, host<->device staging, stage calls.
+#include "common.cuh"
+
+#include <stdarg.h>
+
+#include <algorithm>
+
+static_assert(sizeof(phyx_rigid_body) == 128, "RigidBody must keep the reference layout (128 B)");
+static_assert(sizeof(phyx_contact_joint) == 20, "ContactJoint must keep the reference layout (20 B)");
+static_assert(sizeof(phyx_contact_point) == 32, "ContactPoint must keep the reference layout (32 B)");
+static_assert(sizeof(phyx_manifold) == 16, "Manifold must keep the reference layout (16 B)");
+static_assert(sizeof(phyx_broadphase_entry) == 20, "BroadphaseEntry must keep the reference layout (20 B)");
+static_assert(sizeof(phyx::Level) == 12, "Level is three ints");
+
+namespace phyx
+{
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int DevBuf::reserve(size_t bytes)
+{
+    if (bytes <= cap) return PHYX_B200_OK;
+    size_t want = std::max(bytes, cap + cap / 2);
+    want = (want + 255) & ~size_t(255);
+    void* p = nullptr;
+    PHYX_CUDA(cudaMalloc(&p, want));
+    if (ptr) cudaFree(ptr);   // contents are scratch or re-filled by the caller: no copy
+    ptr = p;
+    cap = want;
+    return PHYX_B200_OK;
+}
+
+void DevBuf::release()
+{
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+int HostBuf::reserve(size_t bytes)
+{
+    if (bytes <= cap) return PHYX_B200_OK;
+    size_t want = std::max(bytes, cap + cap / 2);
+    void* p = nullptr;
+    PHYX_CUDA(cudaMallocHost(&p, want));
+    if (ptr) cudaFreeHost(ptr);
+    ptr = p;
+    cap = want;
+    return PHYX_B200_OK;
+}
+
+void HostBuf::release()
+{
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+static int check(phyx_b200_ctx* c)
+{
+    if (!c)
+    {
+        set_error("null context");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    PHYX_CUDA(cudaSetDevice(c->device));
+    return PHYX_B200_OK;
+}
+
+static float elapsed_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+// H2D of joints + contact points into the resident buffers
+static int stage_joints(phyx_b200_ctx* c, const phyx_contact_joint* joints, int nj, const phyx_contact_point* cps, int ncp)
+{
+    if (nj < 0 || ncp < 0 || (nj > 0 && (!joints || !cps)))
+    {
+        set_error("solve: bad joint / contact point arrays");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    for (int j = 0; j < nj; ++j)
+    {
+        if (joints[j].contactPointIndex < 0 || joints[j].contactPointIndex >= ncp)
+        {
+            set_error("solve: joint %d references contact point %d outside [0,%d)", j, joints[j].contactPointIndex, ncp);
+            return PHYX_B200_ERR_ARGUMENT;
+        }
+    }
+    PHYX_TRY(c->joints.reserve(size_t(std::max(nj, 1)) * sizeof(phyx_contact_joint)));
+    PHYX_TRY(c->contactPoints.reserve(size_t(std::max(ncp, 1)) * sizeof(phyx_contact_point)));
+    if (nj > 0) PHYX_CUDA(cudaMemcpyAsync(c->joints.ptr, joints, size_t(nj) * sizeof(phyx_contact_joint), cudaMemcpyHostToDevice, c->stream));
+    if (ncp > 0)
+        PHYX_CUDA(cudaMemcpyAsync(c->contactPoints.ptr, cps, size_t(ncp) * sizeof(phyx_contact_point), cudaMemcpyHostToDevice, c->stream));
+    c->jointCount = nj;
+    c->contactPointCount = ncp;
+    return PHYX_B200_OK;
+}
+
+} // namespace phyx
+
+using namespace phyx;
+
+extern "C" {
+
+const char* phyx_b200_last_error(void) { return g_error; }
+const char* phyx_b200_version(void) { return "phyx_b200 0.1 (sm_100a)"; }
+
+int phyx_b200_create(int device, phyx_b200_ctx** out)
+{
+    if (!out)
+    {
+        set_error("create: null out pointer");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+    {
+        set_error("no CUDA device available (%s); phyx_b200 has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return PHYX_B200_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count)
+    {
+        set_error("create: device %d outside [0,%d)", device, count);
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    PHYX_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PHYX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+    {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return PHYX_B200_ERR_NO_DEVICE;
+    }
+    phyx_b200_ctx* c = new phyx_b200_ctx();
+    c->device = device;
+    c->numSMs = prop.multiProcessorCount;
+    PHYX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) PHYX_CUDA(cudaEventCreate(&ev));
+    *out = c;
+    return PHYX_B200_OK;
+}
+
+void phyx_b200_destroy(phyx_b200_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->sortA, &c->sortB, &c->hist,
+        &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
+        &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags,
+        &c->colourTmp };
+    for (DevBuf* b : bufs) b->release();
+    c->pinned.release();
+    for (auto& ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int64_t phyx_b200_launch_count(const phyx_b200_ctx* c) { return c ? c->launches : 0; }
+void* phyx_b200_stream(const phyx_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int phyx_b200_synchronize(phyx_b200_ctx* c)
+{
+    PHYX_TRY(check(c));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_body_count(const phyx_b200_ctx* c) { return c ? c->bodyCount : 0; }
+
+int phyx_b200_upload_bodies(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int count)
+{
+    PHYX_TRY(check(c));
+    if (count < 0 || (count > 0 && !bodies))
+    {
+        set_error("upload_bodies: bad arguments");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    return bodies_upload(c, bodies, count);
+}
+
+int phyx_b200_download_bodies(phyx_b200_ctx* c, phyx_rigid_body* bodies, int count)
+{
+    PHYX_TRY(check(c));
+    if (count != c->bodyCount || (count > 0 && !bodies))
+    {
+        set_error("download_bodies: count %d does not match the %d resident bodies", count, c->bodyCount);
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    return bodies_download(c, bodies, count);
+}
+
+int phyx_b200_integrate_velocity(phyx_b200_ctx* c, float dt, float gravity)
+{
+    PHYX_TRY(check(c));
+    return bodies_integrate_velocity(c, dt, gravity);
+}
+
+int phyx_b200_integrate_position(phyx_b200_ctx* c, float dt)
+{
+    PHYX_TRY(check(c));
+    return bodies_integrate_position(c, dt);
+}
+
+int phyx_b200_snapshot_bodies(phyx_b200_ctx* c)
+{
+    PHYX_TRY(check(c));
+    return bodies_snapshot(c, false);
+}
+
+int phyx_b200_restore_bodies(phyx_b200_ctx* c)
+{
+    PHYX_TRY(check(c));
+    return bodies_snapshot(c, true);
+}
+
+int phyx_b200_update_broadphase(phyx_b200_ctx* c)
+{
+    PHYX_TRY(check(c));
+    return broadphase_update(c);
+}
+
+int phyx_b200_download_broadphase(phyx_b200_ctx* c, phyx_broadphase_entry* entries, int capacity)
+{
+    PHYX_TRY(check(c));
+    int n = c->bodyCount;
+    if (!c->broadphaseValid)
+    {
+        set_error("download_broadphase: call update_broadphase first");
+        return PHYX_B200_ERR_STATE;
+    }
+    if (capacity < n || (n > 0 && !entries))
+    {
+        set_error("download_broadphase: capacity %d < %d entries", capacity, n);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    if (n == 0) return PHYX_B200_OK;
+    std::vector<float2> x(n), y(n);
+    std::vector<unsigned> idx(n);
+    const float2* ex = c->entry.as<float2>();
+    PHYX_CUDA(cudaMemcpyAsync(x.data(), ex, size_t(n) * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaMemcpyAsync(y.data(), ex + n, size_t(n) * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaMemcpyAsync(idx.data(), c->entryIndex.ptr, size_t(n) * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i)
+    {
+        entries[i].minx = x[i].x;
+        entries[i].maxx = x[i].y;
+        entries[i].centery = y[i].x;
+        entries[i].extenty = y[i].y;
+        entries[i].index = idx[i];
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_sweep_pairs_resident(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
+{
+    PHYX_TRY(check(c));
+    return broadphase_sweep(c, stats);
+}
+
+int phyx_b200_sweep_pairs(phyx_b200_ctx* c, phyx_pair* pairs, int64_t capacity, int64_t* count, phyx_b200_broadphase_stats* stats)
+{
+    PHYX_TRY(check(c));
+    if (!count || capacity < 0 || (capacity > 0 && !pairs))
+    {
+        set_error("sweep_pairs: bad arguments");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    PHYX_TRY(broadphase_sweep(c, stats));
+    *count = c->lastPairs;
+    if (c->lastPairs > capacity)
+    {
+        set_error("sweep_pairs: %lld pairs do not fit capacity %lld", (long long)c->lastPairs, (long long)capacity);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    if (c->lastPairs > 0)
+    {
+        PHYX_CUDA(cudaMemcpyAsync(pairs, c->pairs.ptr, size_t(c->lastPairs) * sizeof(phyx_pair), cudaMemcpyDeviceToHost, c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_stage_joints(phyx_b200_ctx* c, const phyx_contact_joint* joints, int jointCount, const phyx_contact_point* contactPoints,
+    int contactPointCount)
+{
+    PHYX_TRY(check(c));
+    PHYX_TRY(stage_joints(c, joints, jointCount, contactPoints, contactPointCount));
+    c->hostJoints.assign(joints, joints + jointCount);
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_solve_staged(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats)
+{
+    PHYX_TRY(check(c));
+    if (!cfg)
+    {
+        set_error("solve: null config");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    cudaEvent_t t0 = c->ev[4], t1 = c->ev[5], t2 = c->ev[6];
+    PHYX_CUDA(cudaEventRecord(t0, c->stream));
+    PHYX_TRY(schedule_build(c, c->hostJoints.data(), c->jointCount, cfg->schedule, cfg->flags));
+    PHYX_CUDA(cudaEventRecord(t1, c->stream));
+    PHYX_TRY(solve_run(c, cfg, stats));
+    PHYX_CUDA(cudaEventRecord(t2, c->stream));
+    PHYX_CUDA(cudaEventSynchronize(t2));
+    if (stats)
+    {
+        stats->ms_schedule = elapsed_ms(t0, t1);
+        stats->ms_total = elapsed_ms(t0, t2);
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_fetch_joints(phyx_b200_ctx* c, phyx_contact_joint* joints, int jointCount)
+{
+    PHYX_TRY(check(c));
+    if (jointCount != c->jointCount || (jointCount > 0 && !joints))
+    {
+        set_error("fetch_joints: count %d does not match the %d resident joints", jointCount, c->jointCount);
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    if (jointCount > 0)
+    {
+        PHYX_CUDA(cudaMemcpyAsync(joints, c->joints.ptr, size_t(jointCount) * sizeof(phyx_contact_joint), cudaMemcpyDeviceToHost, c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_solve_joints(phyx_b200_ctx* c, phyx_contact_joint* joints, int jointCount, const phyx_contact_point* contactPoints,
+    int contactPointCount, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats)
+{
+    PHYX_TRY(check(c));
+    if (!cfg)
+    {
+        set_error("solve: null config");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    cudaEvent_t t0 = c->ev[4], t1 = c->ev[5], t2 = c->ev[6], t3 = c->ev[7];
+    PHYX_CUDA(cudaEventRecord(t0, c->stream));
+    PHYX_TRY(stage_joints(c, joints, jointCount, contactPoints, contactPointCount));
+    PHYX_CUDA(cudaEventRecord(t1, c->stream));
+    PHYX_TRY(schedule_build(c, joints, jointCount, cfg->schedule, cfg->flags));
+    PHYX_CUDA(cudaEventRecord(t2, c->stream));
+    PHYX_TRY(solve_run(c, cfg, stats));
+    PHYX_CUDA(cudaEventRecord(t3, c->stream));
+    float h2d = 0.f, sched = 0.f;
+    if (jointCount > 0)
+        PHYX_CUDA(cudaMemcpyAsync(joints, c->joints.ptr, size_t(jointCount) * sizeof(phyx_contact_joint), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    PHYX_CUDA(cudaEventSynchronize(c->ev[0]));
+    h2d = elapsed_ms(t0, t1);
+    sched = elapsed_ms(t1, t2);
+    if (stats)
+    {
+        stats->ms_h2d = h2d;
+        stats->ms_schedule = sched;
+        stats->ms_d2h = elapsed_ms(t3, c->ev[0]);
+        stats->ms_total = elapsed_ms(t0, c->ev[0]);
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_get_schedule(phyx_b200_ctx* c, int32_t* slots, int32_t slotCapacity, int32_t* levels3, int32_t levelCapacity, int32_t* slotCount,
+    int32_t* levelCount)
+{
+    PHYX_TRY(check(c));
+    int ns = int(c->hostSlots.size()), nl = int(c->hostLevels.size());
+    if (slotCount) *slotCount = ns;
+    if (levelCount) *levelCount = nl;
+    if (!slots && !levels3) return PHYX_B200_OK;
+    if (slotCapacity < ns || levelCapacity < nl)
+    {
+        set_error("get_schedule: need %d slots and %d levels", ns, nl);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    if (slots && ns) memcpy(slots, c->hostSlots.data(), size_t(ns) * sizeof(int));
+    if (levels3 && nl) memcpy(levels3, c->hostLevels.data(), size_t(nl) * sizeof(Level));
+    return PHYX_B200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,320 @@
+// phyx_b200 — single-axis sweep & prune broadphase on the device.
+//
+// Reference stages replaced here:
+//   Collider::UpdateBroadphase   src/Collider.cpp:251-284   key build, radixSort3, entry gather
+//   radixFloat / radixSort3      src/base/RadixSort.h:19-95 order-preserving float key, stable LSD
+//                                                            sort, digits of 11/11/10 bits
+//   Collider::UpdatePairs* sweep src/Collider.cpp:296-366   for i: for j>i while minx[j]<=maxx[i]:
+//                                                            y-interval test -> candidate pair
+//
+// The sort is a stable LSD radix sort with the reference's own three digits, so the permutation
+// (including the order of ties: equal keys keep body-index order) is identical to radixSort3's.
+// The sweep emits pairs in exactly the reference's order (i ascending, j ascending) by
+// count -> exclusive scan -> emit over fixed-size work items, so long scans (the ground body's
+// covers every entry) are split over many warps instead of serialising one thread.
+#include "common.cuh"
+
+namespace phyx
+{
+
+constexpr int kBlock = 256;
+
+// ---- keys -------------------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned radix_float(float v)   // RadixSort.h:19-26
+{
+    int f = __float_as_int(v);
+    unsigned mask = unsigned(f >> 31) | 0x80000000u;
+    return unsigned(f) ^ mask;
+}
+
+__global__ void k_make_keys(int n, const float4* __restrict__ aabb, uint2* __restrict__ kv)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    kv[i] = make_uint2(radix_float(aabb[i].x), unsigned(i));
+}
+
+// ---- radix sort pass ----------------------------------------------------------------------------
+// tile = 256 threads x 16 keys; warp w owns 512 consecutive keys, read as 16 coalesced chunks of 32.
+
+constexpr int kSortItems = 16;
+constexpr int kSortWarps = kBlock / 32;
+constexpr int kSortTile = kBlock * kSortItems;
+constexpr int kMaxDigits = 2048;
+
+__global__ void __launch_bounds__(kBlock) k_radix_hist(const uint2* __restrict__ src, int n, int shift, int digits, int numBlocks,
+    int* __restrict__ table)
+{
+    __shared__ int h[kMaxDigits];
+    for (int d = threadIdx.x; d < digits; d += kBlock) h[d] = 0;
+    __syncthreads();
+    int base = blockIdx.x * kSortTile;
+    unsigned mask = unsigned(digits - 1);
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k)
+    {
+        int i = base + k * kBlock + threadIdx.x;
+        if (i < n) atomicAdd(&h[(src[i].x >> shift) & mask], 1);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < digits; d += kBlock) table[size_t(d) * numBlocks + blockIdx.x] = h[d];
+}
+
+__global__ void __launch_bounds__(kBlock) k_radix_scatter(const uint2* __restrict__ src, uint2* __restrict__ dst, int n, int shift,
+    int digits, int numBlocks, const int* __restrict__ tableScanned)
+{
+    __shared__ unsigned short cnt[kSortWarps][kMaxDigits];   // per-warp digit counts, then prefixes
+    __shared__ int gOff[kMaxDigits];                         // global offset of (digit, this block)
+
+    unsigned short* flat = &cnt[0][0];
+    for (int k = threadIdx.x; k < kSortWarps * kMaxDigits; k += kBlock) flat[k] = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned mask = unsigned(digits - 1);
+    const int base = blockIdx.x * kSortTile + warp * (32 * kSortItems);
+
+    uint2 kv[kSortItems];
+    unsigned packed[kSortItems];   // digit | rank-within-warp << 11
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k)
+    {
+        int i = base + k * 32 + lane;
+        bool valid = i < n;
+        kv[k] = valid ? src[i] : make_uint2(0, 0);
+        unsigned d = (kv[k].x >> shift) & mask;
+        unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (0x10000u | unsigned(lane)));
+        int leader = __ffs(peers) - 1;
+        unsigned before = __popc(peers & ((1u << lane) - 1u));
+        unsigned old = 0;
+        if (lane == leader && valid)
+        {
+            old = cnt[warp][d];
+            cnt[warp][d] = (unsigned short)(old + __popc(peers));
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        packed[k] = d | ((old + before) << 11);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < digits; d += kBlock)
+    {
+        gOff[d] = tableScanned[size_t(d) * numBlocks + blockIdx.x];
+        unsigned run = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w)
+        {
+            unsigned t = cnt[w][d];
+            cnt[w][d] = (unsigned short)run;
+            run += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k)
+    {
+        int i = base + k * 32 + lane;
+        if (i < n)
+        {
+            unsigned d = packed[k] & 2047u;
+            int pos = gOff[d] + int(cnt[warp][d]) + int(packed[k] >> 11);
+            dst[pos] = kv[k];
+        }
+    }
+}
+
+// ---- entries ----------------------------------------------------------------------------------
+
+__global__ void k_gather_entries(int n, const uint2* __restrict__ sorted, const float4* __restrict__ aabb, float2* __restrict__ entryX,
+    float2* __restrict__ entryY, unsigned* __restrict__ entryIndex)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned b = sorted[i].y;
+    float4 bb = aabb[b];
+    entryX[i] = make_float2(bb.x, bb.z);
+    entryY[i] = make_float2((bb.y + bb.w) * 0.5f, (bb.w - bb.y) * 0.5f);   // Collider.cpp:276-279
+    entryIndex[i] = b;
+}
+
+// ---- sweep ------------------------------------------------------------------------------------
+
+constexpr int kChunk = 1024;   // sweep tests per work item (one warp, 32 rounds)
+
+// end_i = first j > i with minx[j] > maxx[i] (the x-break, Collider.cpp:306); minx is sorted.
+__global__ void k_sweep_end(int n, const float2* __restrict__ entryX, int* __restrict__ end, int* __restrict__ itemsOf)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float maxx = entryX[i].y;
+    int lo = i + 1, hi = n;
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (entryX[mid].x > maxx) hi = mid; else lo = mid + 1;
+    }
+    end[i] = lo;
+    itemsOf[i] = (lo - i - 1 + kChunk - 1) / kChunk;
+}
+
+__global__ void k_sweep_items(int n, const int* __restrict__ itemStart, const int* __restrict__ end, int2* __restrict__ items)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cnt = (end[i] - i - 1 + kChunk - 1) / kChunk;
+    int s = itemStart[i];
+    for (int k = 0; k < cnt; ++k) items[s + k] = make_int2(i, k);
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numItemsPtr, const int2* __restrict__ items,
+    const int* __restrict__ end, const float2* __restrict__ entryY, const unsigned* __restrict__ entryIndex, int* __restrict__ itemCount,
+    const int* __restrict__ itemOffset, int2* __restrict__ pairs, unsigned long long* __restrict__ tests)
+{
+    const int lane = threadIdx.x & 31;
+    const int warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    const int numItems = *numItemsPtr;
+    unsigned long long localTests = 0;
+    for (int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < numItems; it += warpsPerGrid)
+    {
+        int2 item = items[it];
+        int i = item.x;
+        int j0 = i + 1 + item.y * kChunk;
+        int j1 = min(j0 + kChunk, end[i]);
+        float2 yi = entryY[i];
+        unsigned bi = EMIT ? entryIndex[i] : 0u;
+        int out = EMIT ? itemOffset[it] : 0;
+        int count = 0;
+        for (int jb = j0; jb < j1; jb += 32)
+        {
+            int j = jb + lane;
+            bool hit = false;
+            if (j < j1)
+            {
+                float2 yj = entryY[j];
+                hit = fabsf(yj.x - yi.x) <= yi.y + yj.y;   // Collider.cpp:309
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (EMIT)
+            {
+                if (hit) pairs[out + __popc(m & ((1u << lane) - 1u))] = make_int2(int(bi), int(entryIndex[j]));
+                out += __popc(m);
+            }
+            else
+                count += __popc(m);
+        }
+        if (!EMIT && lane == 0)
+        {
+            itemCount[it] = count;
+            localTests += (unsigned long long)(j1 - j0);
+        }
+    }
+    if (!EMIT && lane == 0 && localTests) atomicAdd(tests, localTests);
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+
+static int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift, int digits)
+{
+    int blocks = (n + kSortTile - 1) / kSortTile;
+    size_t tableInts = size_t(digits) * blocks;
+    PHYX_TRY(c->hist.reserve(tableInts * sizeof(int)));
+    k_radix_hist<<<blocks, kBlock, 0, c->stream>>>(src, n, shift, digits, blocks, c->hist.as<int>());
+    c->launches++;
+    PHYX_TRY(exclusive_scan_i32(c, c->hist.as<int>(), c->hist.as<int>(), int(tableInts), nullptr));
+    k_radix_scatter<<<blocks, kBlock, 0, c->stream>>>(src, dst, n, shift, digits, blocks, c->hist.as<int>());
+    c->launches++;
+    PHYX_CUDA(cudaGetLastError());
+    return PHYX_B200_OK;
+}
+
+int broadphase_update(phyx_b200_ctx* c)
+{
+    int n = c->bodyCount;
+    size_t n1 = size_t(n > 0 ? n : 1);
+    PHYX_TRY(c->sortA.reserve(n1 * sizeof(uint2)));
+    PHYX_TRY(c->sortB.reserve(n1 * sizeof(uint2)));
+    PHYX_TRY(c->entry.reserve(n1 * 2 * sizeof(float2)));
+    PHYX_TRY(c->entryIndex.reserve(n1 * sizeof(unsigned)));
+    c->broadphaseValid = true;
+    if (n == 0) return PHYX_B200_OK;
+    int grid = (n + kBlock - 1) / kBlock;
+    k_make_keys<<<grid, kBlock, 0, c->stream>>>(n, c->aabb.as<float4>(), c->sortA.as<uint2>());
+    c->launches++;
+    // radixSort3: digits 0-10, 11-21, 22-31; A -> B -> A -> B (RadixSort.h:74-88)
+    PHYX_TRY(radix_pass(c, c->sortA.as<uint2>(), c->sortB.as<uint2>(), n, 0, 2048));
+    PHYX_TRY(radix_pass(c, c->sortB.as<uint2>(), c->sortA.as<uint2>(), n, 11, 2048));
+    PHYX_TRY(radix_pass(c, c->sortA.as<uint2>(), c->sortB.as<uint2>(), n, 22, 1024));
+    float2* entryX = c->entry.as<float2>();
+    float2* entryY = entryX + n1;
+    k_gather_entries<<<grid, kBlock, 0, c->stream>>>(n, c->sortB.as<uint2>(), c->aabb.as<float4>(), entryX, entryY, c->entryIndex.as<unsigned>());
+    c->launches++;
+    PHYX_CUDA(cudaGetLastError());
+    return PHYX_B200_OK;
+}
+
+// Runs count + scan (+ emit into c->pairs).  Leaves the pair list on the device; c->lastPairs /
+// c->lastTests hold the totals.
+int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
+{
+    if (!c->broadphaseValid)
+    {
+        set_error("sweep_pairs: call update_broadphase first (bodies moved since the last sort)");
+        return PHYX_B200_ERR_STATE;
+    }
+    int n = c->bodyCount;
+    c->lastPairs = c->lastTests = 0;
+    if (n < 2) return PHYX_B200_OK;
+    size_t n1 = size_t(n);
+    float2* entryX = c->entry.as<float2>();
+    float2* entryY = entryX + n1;
+    PHYX_TRY(c->sweepEnd.reserve(n1 * sizeof(int)));
+    PHYX_TRY(c->itemStart.reserve((n1 + 1) * sizeof(int)));
+    PHYX_TRY(c->counters.reserve(64));
+    int* d_numItems = c->counters.as<int>();
+    int* d_numPairs = d_numItems + 1;
+    unsigned long long* d_tests = reinterpret_cast<unsigned long long*>(c->counters.as<char>() + 16);
+    PHYX_CUDA(cudaMemsetAsync(c->counters.ptr, 0, 64, c->stream));
+
+    int grid = (n + kBlock - 1) / kBlock;
+    k_sweep_end<<<grid, kBlock, 0, c->stream>>>(n, entryX, c->sweepEnd.as<int>(), c->itemStart.as<int>());
+    c->launches++;
+    PHYX_TRY(exclusive_scan_i32(c, c->itemStart.as<int>(), c->itemStart.as<int>(), n, d_numItems));
+    int numItems = 0;
+    PHYX_CUDA(cudaMemcpyAsync(&numItems, d_numItems, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    if (numItems == 0) return PHYX_B200_OK;
+
+    PHYX_TRY(c->items.reserve(size_t(numItems) * sizeof(int2)));
+    PHYX_TRY(c->itemCount.reserve(size_t(numItems) * sizeof(int)));
+    k_sweep_items<<<grid, kBlock, 0, c->stream>>>(n, c->itemStart.as<int>(), c->sweepEnd.as<int>(), c->items.as<int2>());
+    c->launches++;
+
+    int warpsPerBlock = kBlock / 32;
+    int sweepGrid = min((numItems + warpsPerBlock - 1) / warpsPerBlock, c->numSMs * 8);
+    k_sweep<false><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
+        c->entryIndex.as<unsigned>(), c->itemCount.as<int>(), nullptr, nullptr, d_tests);
+    c->launches++;
+    PHYX_TRY(exclusive_scan_i32(c, c->itemCount.as<int>(), c->itemCount.as<int>(), numItems, d_numPairs));
+    struct { int items, pairs; long long pad; unsigned long long tests; } host;
+    PHYX_CUDA(cudaMemcpyAsync(&host, c->counters.ptr, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    c->lastPairs = host.pairs;
+    c->lastTests = (long long)host.tests;
+    if (host.pairs > 0)
+    {
+        PHYX_TRY(c->pairs.reserve(size_t(host.pairs) * sizeof(int2)));
+        k_sweep<true><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
+            c->entryIndex.as<unsigned>(), nullptr, c->itemCount.as<int>(), c->pairs.as<int2>(), nullptr);
+        c->launches++;
+    }
+    PHYX_CUDA(cudaGetLastError());
+    if (stats)
+    {
+        stats->pairs = c->lastPairs;
+        stats->tests = c->lastTests;
+    }
+    return PHYX_B200_OK;
+}
+
+} // namespace phyx

@@ -1,0 +1,157 @@
+// phyx_b200 — shared declarations of the sm_100a hot path (context, buffers, error plumbing).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "phyx_b200.h"
+
+namespace phyx
+{
+
+void set_error(const char* fmt, ...);
+
+#define PHYX_CUDA(call)                                                                          \
+    do                                                                                           \
+    {                                                                                            \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+        {                                                                                        \
+            phyx::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return PHYX_B200_ERR_CUDA;                                                           \
+        }                                                                                        \
+    } while (0)
+
+#define PHYX_TRY(call)              \
+    do                              \
+    {                               \
+        int s_ = (call);            \
+        if (s_ != PHYX_B200_OK)     \
+            return s_;              \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf
+{
+    void* ptr = nullptr;
+    size_t cap = 0;
+
+    template <typename T> T* as() const { return static_cast<T*>(ptr); }
+    int reserve(size_t bytes);
+    void release();
+};
+
+// grow-only pinned host staging buffer
+struct HostBuf
+{
+    void* ptr = nullptr;
+    size_t cap = 0;
+    template <typename T> T* as() const { return static_cast<T*>(ptr); }
+    int reserve(size_t bytes);
+    void release();
+};
+
+// One level of the solve schedule: slots [start, grouped_end) are 8-wide units (AVX2 skip rule),
+// slots [grouped_end, end) are 1-wide units.  start % 8 == 0.
+struct Level
+{
+    int start, grouped_end, end;
+};
+
+constexpr int kStaticBit = 1 << 30;       // body reference flag in the packed joint: body is static
+constexpr int kBodyMask = kStaticBit - 1;
+
+struct TimerPair
+{
+    cudaEvent_t a = nullptr, b = nullptr;
+};
+
+} // namespace phyx
+
+struct phyx_b200_ctx
+{
+    int device = 0;
+    int numSMs = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+
+    // ---- bodies (SoA in HBM) --------------------------------------------------------------
+    int bodyCount = 0;
+    phyx::DevBuf vel;      // float4 {vx, vy, w, lastIteration}       = reference SolveBody (impulse)
+    phyx::DevBuf disp;     // float4 {dvx, dvy, dw, lastIteration}    = reference SolveBody (displacement)
+    phyx::DevBuf acc;      // float4 {ax, ay, alpha, 0}
+    phyx::DevBuf params;   // float4 {invMass, invInertia, pos.x, pos.y}
+    phyx::DevBuf rot;      // float4 {xVector.x, xVector.y, yVector.x, yVector.y}
+    phyx::DevBuf aabb;     // float4 {min.x, min.y, max.x, max.y}
+    phyx::DevBuf size;     // float2 half extents
+    phyx::DevBuf aos;      // staging for the 128-byte AoS records
+    phyx::DevBuf snap;     // snapshot of vel/disp/acc/params/rot/aabb
+    bool hasSnapshot = false;
+
+    // ---- broadphase -----------------------------------------------------------------------
+    phyx::DevBuf sortA, sortB;   // uint2 {key, index}
+    phyx::DevBuf hist;           // per-block digit counts / offsets
+    phyx::DevBuf scanTmp;
+    phyx::DevBuf entry;          // float4 {minx, maxx, centery, extenty}, sorted order
+    phyx::DevBuf entryIndex;     // uint32 body index, sorted order
+    phyx::DevBuf sweepEnd;       // int: end_i
+    phyx::DevBuf itemStart;      // int: first work item of body i (exclusive scan)
+    phyx::DevBuf items;          // int2 {i, chunk}
+    phyx::DevBuf itemCount;      // int per item -> exclusive scan = output offset
+    phyx::DevBuf pairs;          // int2 output
+    phyx::DevBuf counters;       // misc device scalars
+    bool broadphaseValid = false;
+    int64_t lastPairs = 0, lastTests = 0;
+
+    // ---- solve ----------------------------------------------------------------------------
+    int jointCount = 0, contactPointCount = 0;
+    phyx::DevBuf joints;         // phyx_contact_joint AoS (device copy)
+    phyx::DevBuf contactPoints;  // phyx_contact_point AoS (device copy)
+    int slotCount = 0, levelCount = 0;
+    phyx::DevBuf slotJoint;      // int: joint index of slot (or -1)
+    phyx::DevBuf levels;         // Level[levelCount]
+    phyx::DevBuf q0, q1, q2, q3; // float4 per slot (see solve.cu)
+    phyx::DevBuf accNF;          // float2 per slot
+    phyx::DevBuf accD;           // float per slot
+    phyx::DevBuf stamps;         // 2 x u64 per body (impulse / displacement static-body stamps)
+    phyx::DevBuf solveFlags;     // productive flags + result words
+    phyx::DevBuf colourTmp;      // colouring scratch
+    std::vector<int> hostSlots;  // last schedule (host copy, for get_schedule / KEEP_SCHEDULE)
+    std::vector<phyx::Level> hostLevels;
+    std::vector<int> hostPairKey; // (b1,b2) list the schedule was built for
+    int scheduleMode = -1, scheduleFlags = 0;
+    std::vector<phyx_contact_joint> hostJoints; // host copy of staged joints (replay schedule needs it)
+
+    phyx::HostBuf pinned;        // pinned staging for H2D/D2H
+    cudaEvent_t ev[8] = {};
+    int solveBlocksPerSM = 0;
+};
+
+namespace phyx
+{
+// bodies.cu
+int bodies_upload(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int n);
+int bodies_download(phyx_b200_ctx* c, phyx_rigid_body* bodies, int n);
+int bodies_integrate_velocity(phyx_b200_ctx* c, float dt, float gravity);
+int bodies_integrate_position(phyx_b200_ctx* c, float dt);
+int bodies_snapshot(phyx_b200_ctx* c, bool restore);
+
+// broadphase.cu
+int broadphase_update(phyx_b200_ctx* c);
+int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats);
+
+// schedule.cu
+int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int nj, int mode, int flags);
+
+// solve.cu
+int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats);
+
+// scan.cu
+int exclusive_scan_i32(phyx_b200_ctx* c, const int* in, int* out, int n, int* totalDevice /* may be null */);
+int exclusive_scan_i64(phyx_b200_ctx* c, const int* in, long long* out, int n, long long* totalDevice);
+} // namespace phyx

@@ -1,0 +1,246 @@
+// phyx_b200 — solve schedules: which joints may run together, in which order.
+//
+// Reference stage replaced here:
+//   Solver::PrepareIndices   src/Solver.cpp:217-273   greedy grouping of joints into SIMD-wide
+//                                                      sets with pairwise distinct bodies
+//
+// Two schedule families (phyx_b200_schedule):
+//   COLOUR      the grouping idea widened from 8 lanes to the whole device: joints are coloured so
+//               that no two joints of a colour share a dynamic body; one colour = one level.
+//   REPLAY_*    the reference's exact order (PrepareIndices with N = 8 / 4 / 1: groups first, then
+//               the scalar tail) turned into dependency levels: a unit (group or single joint) is
+//               placed one level after the latest earlier unit that shares a dynamic body with it.
+//               Executing levels in order, units of a level in parallel, applies impulses to every
+//               body in the same order as the reference's sequential loop.
+//
+// A level lists its 8-wide units first (each occupying 8 aligned slots, padded with -1 when N = 4)
+// and its 1-wide units after them (see Level in common.cuh).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace phyx
+{
+
+namespace
+{
+
+inline bool is_static(const float4& p) { return p.x == 0.0f && p.y == 0.0f; }   // Solver.cpp:304
+
+// The reference's greedy grouper, restated (Solver.cpp:217-273): repeatedly sweep the remaining
+// joints, taking the first N whose bodies are untouched in this round; taken joints are replaced
+// by the last remaining one.  Returns groupOffset (multiple of N).
+int reference_order(const phyx_contact_joint* joints, int nj, int nb, int N, std::vector<int>& order)
+{
+    order.resize(nj);
+    for (int i = 0; i < nj; ++i) order[i] = i;
+    if (N == 1) return 0;
+    std::vector<int> pool(order);
+    std::vector<int> bodyRound(nb, 0);
+    int round = 0, remaining = nj, offset = 0;
+    while (remaining >= N)
+    {
+        int taken = 0;
+        ++round;
+        for (int i = 0; i < remaining && taken < N;)
+        {
+            int j = pool[i];
+            int b1 = joints[j].body1Index, b2 = joints[j].body2Index;
+            if (bodyRound[b1] < round && bodyRound[b2] < round)
+            {
+                bodyRound[b1] = bodyRound[b2] = round;
+                order[offset + taken++] = j;
+                pool[i] = pool[--remaining];
+            }
+            else
+                ++i;
+        }
+        offset += taken;
+        if (taken < N) break;
+    }
+    for (int i = 0; i < remaining; ++i) order[offset + i] = pool[i];
+    return offset & ~(N - 1);
+}
+
+struct Unit
+{
+    int first, width, level;   // order[first .. first+width)
+};
+
+void build_replay(const phyx_contact_joint* joints, int nj, int nb, const std::vector<unsigned char>& statics, int N, bool staticDeps,
+    std::vector<int>& slots, std::vector<Level>& levels)
+{
+    std::vector<int> order;
+    int groupOffset = reference_order(joints, nj, nb, N, order);
+    std::vector<Unit> units;
+    units.reserve(size_t(groupOffset / std::max(N, 1)) + size_t(nj - groupOffset));
+    for (int g = 0; N > 1 && g < groupOffset; g += N) units.push_back({ g, N, 0 });
+    for (int i = groupOffset; i < nj; ++i) units.push_back({ i, 1, 0 });
+
+    std::vector<int> bodyLevel(nb, 0);
+    int maxLevel = 0;
+    for (Unit& u : units)
+    {
+        int lvl = 0;
+        for (int k = 0; k < u.width; ++k)
+        {
+            const phyx_contact_joint& j = joints[order[u.first + k]];
+            if (staticDeps || !statics[j.body1Index]) lvl = std::max(lvl, bodyLevel[j.body1Index]);
+            if (staticDeps || !statics[j.body2Index]) lvl = std::max(lvl, bodyLevel[j.body2Index]);
+        }
+        u.level = lvl;   // 0-based level of this unit
+        for (int k = 0; k < u.width; ++k)
+        {
+            const phyx_contact_joint& j = joints[order[u.first + k]];
+            if (staticDeps || !statics[j.body1Index]) bodyLevel[j.body1Index] = lvl + 1;
+            if (staticDeps || !statics[j.body2Index]) bodyLevel[j.body2Index] = lvl + 1;
+        }
+        maxLevel = std::max(maxLevel, lvl + 1);
+    }
+    // bucket by level: wide units first, singles after (stable in unit order)
+    std::vector<int> wideCount(maxLevel, 0), singleCount(maxLevel, 0);
+    for (const Unit& u : units) (u.width > 1 ? wideCount : singleCount)[u.level]++;
+    levels.resize(maxLevel);
+    int cursor = 0;
+    for (int l = 0; l < maxLevel; ++l)
+    {
+        levels[l].start = cursor;
+        levels[l].grouped_end = cursor + wideCount[l] * 8;
+        levels[l].end = levels[l].grouped_end + singleCount[l];
+        cursor = (levels[l].end + 7) & ~7;
+    }
+    slots.assign(cursor, -1);
+    std::vector<int> wideAt(maxLevel), singleAt(maxLevel);
+    for (int l = 0; l < maxLevel; ++l)
+    {
+        wideAt[l] = levels[l].start;
+        singleAt[l] = levels[l].grouped_end;
+    }
+    for (const Unit& u : units)
+    {
+        if (u.width > 1)
+        {
+            for (int k = 0; k < u.width; ++k) slots[wideAt[u.level] + k] = order[u.first + k];
+            wideAt[u.level] += 8;
+        }
+        else
+            slots[singleAt[u.level]++] = order[u.first];
+    }
+}
+
+// Greedy colouring in joint order: smallest colour not yet used on either dynamic body.
+void build_colours(const phyx_contact_joint* joints, int nj, int nb, const std::vector<unsigned char>& statics, std::vector<int>& slots,
+    std::vector<Level>& levels)
+{
+    int words = 1;
+    std::vector<int> colour(nj);
+    int numColours = 0;
+    for (;;)
+    {
+        std::vector<uint64_t> used(size_t(nb) * words, 0);
+        bool overflow = false;
+        numColours = 0;
+        for (int j = 0; j < nj && !overflow; ++j)
+        {
+            int b1 = joints[j].body1Index, b2 = joints[j].body2Index;
+            const bool d1 = !statics[b1], d2 = !statics[b2];
+            int c = -1;
+            for (int w = 0; w < words; ++w)
+            {
+                uint64_t m = (d1 ? used[size_t(b1) * words + w] : 0) | (d2 ? used[size_t(b2) * words + w] : 0);
+                if (~m)
+                {
+                    c = w * 64 + __builtin_ctzll(~m);
+                    break;
+                }
+            }
+            if (c < 0)
+            {
+                overflow = true;
+                break;
+            }
+            colour[j] = c;
+            numColours = std::max(numColours, c + 1);
+            if (d1) used[size_t(b1) * words + (c >> 6)] |= uint64_t(1) << (c & 63);
+            if (d2) used[size_t(b2) * words + (c >> 6)] |= uint64_t(1) << (c & 63);
+        }
+        if (!overflow) break;
+        words *= 2;
+    }
+    std::vector<int> count(numColours, 0);
+    for (int j = 0; j < nj; ++j) count[colour[j]]++;
+    levels.resize(numColours);
+    int cursor = 0;
+    std::vector<int> at(numColours);
+    for (int c = 0; c < numColours; ++c)
+    {
+        levels[c].start = cursor;
+        levels[c].grouped_end = cursor;
+        levels[c].end = cursor + count[c];
+        at[c] = cursor;
+        cursor = (levels[c].end + 31) & ~31;
+    }
+    slots.assign(cursor, -1);
+    for (int j = 0; j < nj; ++j) slots[at[colour[j]]++] = j;
+}
+
+} // namespace
+
+int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int nj, int mode, int flags)
+{
+    const int nb = c->bodyCount;
+    // (body1, body2) list: validates indices and detects an unchanged joint graph
+    std::vector<int> key(size_t(nj) * 2);
+    for (int j = 0; j < nj; ++j)
+    {
+        int b1 = hostJoints[j].body1Index, b2 = hostJoints[j].body2Index;
+        if (b1 < 0 || b1 >= nb || b2 < 0 || b2 >= nb)
+        {
+            set_error("solve: joint %d references body (%d,%d) outside [0,%d)", j, b1, b2, nb);
+            return PHYX_B200_ERR_ARGUMENT;
+        }
+        key[2 * j] = b1;
+        key[2 * j + 1] = b2;
+    }
+    const bool keep = (flags & PHYX_B200_SOLVE_KEEP_SCHEDULE) && c->scheduleMode == mode &&
+                      c->scheduleFlags == (flags & PHYX_B200_SOLVE_STATIC_DEPS) && key == c->hostPairKey;
+    if (keep) return PHYX_B200_OK;
+
+    // static flags from the resident body parameters
+    std::vector<float4> params(size_t(nb > 0 ? nb : 1));
+    if (nb > 0)
+    {
+        PHYX_CUDA(cudaMemcpyAsync(params.data(), c->params.ptr, size_t(nb) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    std::vector<unsigned char> statics(size_t(nb > 0 ? nb : 1));
+    for (int i = 0; i < nb; ++i) statics[i] = is_static(params[i]);
+
+    std::vector<int>& slots = c->hostSlots;
+    std::vector<Level>& levels = c->hostLevels;
+    slots.clear();
+    levels.clear();
+    switch (mode)
+    {
+    case PHYX_B200_SCHEDULE_COLOUR: build_colours(hostJoints, nj, nb, statics, slots, levels); break;
+    case PHYX_B200_SCHEDULE_REPLAY_AVX2: build_replay(hostJoints, nj, nb, statics, 8, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, levels); break;
+    case PHYX_B200_SCHEDULE_REPLAY_SSE2: build_replay(hostJoints, nj, nb, statics, 4, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, levels); break;
+    case PHYX_B200_SCHEDULE_REPLAY_SCALAR: build_replay(hostJoints, nj, nb, statics, 1, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, levels); break;
+    default: set_error("solve: unknown schedule %d", mode); return PHYX_B200_ERR_ARGUMENT;
+    }
+    c->slotCount = int(slots.size());
+    c->levelCount = int(levels.size());
+    PHYX_TRY(c->slotJoint.reserve(std::max<size_t>(slots.size(), 1) * sizeof(int)));
+    PHYX_TRY(c->levels.reserve(std::max<size_t>(levels.size(), 1) * sizeof(Level)));
+    if (!slots.empty())
+        PHYX_CUDA(cudaMemcpyAsync(c->slotJoint.ptr, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (!levels.empty())
+        PHYX_CUDA(cudaMemcpyAsync(c->levels.ptr, levels.data(), levels.size() * sizeof(Level), cudaMemcpyHostToDevice, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    c->hostPairKey.swap(key);
+    c->scheduleMode = mode;
+    c->scheduleFlags = flags & PHYX_B200_SOLVE_STATIC_DEPS;
+    return PHYX_B200_OK;
+}
+
+} // namespace phyx
