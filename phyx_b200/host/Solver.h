@@ -1,0 +1,3 @@
+// Source compatibility with the reference include layout: everything lives in phyx_host.h.
+#pragma once
+#include "phyx_host.h"
