@@ -97,15 +97,15 @@ typedef struct {
     int32_t flags;                        /* PHYX_B200_SOLVE_* */
 } phyx_b200_solve_config;
 
-#define PHYX_B200_SOLVE_STATIC_DEPS 1     /* replay: also order joints that share a STATIC body (exact
-                                             lastIteration visibility; serialises ground contacts) */
+#define PHYX_B200_SOLVE_STATIC_DEPS 1     /* replay: also put joints that share a STATIC body on strictly increasing levels
+                                             (serialises ground contacts; only useful to cross-check the wake passes) */
 #define PHYX_B200_SOLVE_KEEP_SCHEDULE 2   /* reuse the schedule built by the previous solve call if the
                                              joint (body1,body2) list is unchanged */
 
 typedef struct {
     int32_t joints, slots, levels;             /* schedule shape: slots >= joints (padding), levels = colours */
     int32_t contactIterationsRun, penetrationIterationsRun;  /* with the productive early-out */
-    int32_t staticHazards;                     /* see DESIGN.md "static bodies"; 0 => replay is exact */
+    int32_t wakePasses;                        /* extra level passes run for static-body wake-ups (DESIGN.md "static bodies") */
     float ms_schedule, ms_refresh, ms_iterations, ms_finish, ms_total;   /* CUDA-event times */
     float ms_h2d, ms_d2h;
 } phyx_b200_solve_stats;

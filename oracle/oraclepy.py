@@ -40,7 +40,7 @@ def lib():
     l.pxo_prepare_indices.argtypes = [vp, i32, i32, i32, vp]
     l.pxo_prepare_indices.restype = i32
     l.pxo_solve_joints.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, vp, vp]
-    l.pxo_solve_scheduled.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, vp, vp]
+    l.pxo_solve_scheduled.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, vp]
     _LIB = l
     return l
 
@@ -110,13 +110,12 @@ def solve_joints(bodies, joints, contact_points, group=8, iters=(20, 20)):
 
 
 def solve_scheduled(bodies, joints, contact_points, slots, levels, iters=(20, 20)):
-    """Solve under an explicit schedule. Returns (bodies, joints, iters_run, hazards)."""
+    """Sequential solve in slot order. Returns (bodies, joints, iters_run)."""
     b = np.array(bodies, dtype=T.RIGID_BODY, copy=True)
     j = np.array(joints, dtype=T.CONTACT_JOINT, copy=True)
     cp = np.ascontiguousarray(contact_points, dtype=T.CONTACT_POINT)
     s = np.ascontiguousarray(slots, dtype=np.int32)
     lv = np.ascontiguousarray(levels, dtype=LEVEL)
     ran = np.zeros(2, dtype=np.int32)
-    hz = C.c_int(0)
-    lib().pxo_solve_scheduled(_p(b), b.shape[0], _p(j), j.shape[0], _p(cp), _p(s), _p(lv), lv.shape[0], iters[0], iters[1], _p(ran), C.byref(hz))
-    return b, j, (int(ran[0]), int(ran[1])), int(hz.value)
+    lib().pxo_solve_scheduled(_p(b), b.shape[0], _p(j), j.shape[0], _p(cp), _p(s), _p(lv), lv.shape[0], iters[0], iters[1], _p(ran))
+    return b, j, (int(ran[0]), int(ran[1]))

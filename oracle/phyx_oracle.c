@@ -407,18 +407,10 @@ static int displacement_joint(packed_joint* j, solve_body* v1, solve_body* v2)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-typedef struct {
-    solve_body* rows;       /* impulse or displacement SolveBody rows */
-    const uint8_t* is_static;
-    int* pending;           /* static bodies written during the current level */
-    int npending;
-    int* pending_flag;
-} phase_state;
-
-/* One pass (phase 0 = impulses, 1 = displacement) of iteration `it` over the whole schedule.
- * Returns any-productive (Solver.cpp:189,210). */
-static int run_iteration(packed_joint* P, const int* slots, const pxo_level* levels, int nlevels, phase_state* S,
-    int phase, int it, int* hazards)
+/* One pass (phase 0 = impulses, 1 = displacement) of iteration `it` over the whole schedule, strictly
+ * sequentially: level by level, slot by slot, every write visible to the next unit at once - the
+ * reference's own loop (Solver.cpp:774-911 / 929-1015).  Returns any-productive (:189,:210). */
+static int run_iteration(packed_joint* P, const int* slots, const pxo_level* levels, int nlevels, solve_body* rows, int phase, int it)
 {
     int any = 0;
     for (int l = 0; l < nlevels; ++l)
@@ -434,7 +426,7 @@ static int run_iteration(packed_joint* P, const int* slots, const pxo_level* lev
             {
                 int s = slots[k + u];
                 if (s < 0) continue;
-                if (S->rows[P[s].b1].last > it - 2 || S->rows[P[s].b2].last > it - 2) active = 1;
+                if (rows[P[s].b1].last > it - 2 || rows[P[s].b2].last > it - 2) active = 1;
             }
             if (active)
             {
@@ -443,58 +435,29 @@ static int run_iteration(packed_joint* P, const int* slots, const pxo_level* lev
                     int s = slots[k + u];
                     if (s < 0) continue;
                     packed_joint* j = &P[s];
-                    solve_body v1 = S->rows[j->b1], v2 = S->rows[j->b2];
+                    solve_body v1 = rows[j->b1], v2 = rows[j->b2];
                     int productive = phase == 0 ? impulse_joint(j, &v1, &v2, width == 8) : displacement_joint(j, &v1, &v2);
                     any |= productive;
-                    int bs[2] = { j->b1, j->b2 };
-                    solve_body* vs[2] = { &v1, &v2 };
-                    for (int e = 0; e < 2; ++e)
-                    {
-                        int b = bs[e];
-                        if (S->is_static[b])
-                        {
-                            /* velocity write-back is exact (v + 0*d); lastIteration is deferred to
-                             * the end of the level (see phyx_oracle.h) */
-                            S->rows[b].vx = vs[e]->vx; S->rows[b].vy = vs[e]->vy; S->rows[b].w = vs[e]->w;
-                            if (productive)
-                            {
-                                if (S->rows[b].last <= it - 2 && hazards) (*hazards)++;
-                                if (!S->pending_flag[b]) { S->pending_flag[b] = 1; S->pending[S->npending++] = b; }
-                            }
-                        }
-                        else
-                        {
-                            if (productive) vs[e]->last = it;
-                            S->rows[b] = *vs[e];
-                        }
-                    }
+                    if (productive) { v1.last = it; v2.last = it; }      /* Solver.cpp:903-904 */
+                    rows[j->b1] = v1;
+                    rows[j->b2] = v2;
                 }
             }
             k += width;
         }
-        for (int q = 0; q < S->npending; ++q)
-        {
-            S->rows[S->pending[q]].last = it;
-            S->pending_flag[S->pending[q]] = 0;
-        }
-        S->npending = 0;
     }
     return any;
 }
 
 void pxo_solve_scheduled(pxo_body* bodies, int nb, pxo_joint* joints, int nj, const pxo_contact_point* cps,
     const int* slots, const pxo_level* levels, int nlevels, int contact_iters, int penetration_iters,
-    int* iters_out, int* hazards_out)
+    int* iters_out)
 {
     size_t nbs = (size_t)(nb > 0 ? nb : 1), njs = (size_t)(nj > 0 ? nj : 1);
     solve_params* par = (solve_params*)malloc(nbs * sizeof(solve_params));
     solve_body* imp = (solve_body*)malloc(nbs * sizeof(solve_body));
     solve_body* dis = (solve_body*)malloc(nbs * sizeof(solve_body));
-    uint8_t* is_static = (uint8_t*)malloc(nbs);
-    int* pending = (int*)malloc(nbs * sizeof(int));
-    int* pending_flag = (int*)calloc(nbs, sizeof(int));
     packed_joint* P = (packed_joint*)malloc(njs * sizeof(packed_joint));
-    int hazards = 0;
 
     /* PrepareBodies, src/Solver.cpp:456-480 */
     for (int i = 0; i < nb; ++i)
@@ -504,7 +467,6 @@ void pxo_solve_scheduled(pxo_body* bodies, int nb, pxo_joint* joints, int nj, co
         imp[i].vx = bodies[i].velocity.x; imp[i].vy = bodies[i].velocity.y; imp[i].w = bodies[i].angularVelocity; imp[i].last = -1;
         dis[i].vx = bodies[i].displacingVelocity.x; dis[i].vy = bodies[i].displacingVelocity.y;
         dis[i].w = bodies[i].displacingAngularVelocity; dis[i].last = -1;
-        is_static[i] = (bodies[i].invMass == 0.0f && bodies[i].invInertia == 0.0f);   /* Solver.cpp:304 */
     }
     /* PrepareJoints copy, src/Solver.cpp:509-521 (packed storage is addressed by joint id here;
      * the processing ORDER is what the schedule fixes) */
@@ -519,18 +481,16 @@ void pxo_solve_scheduled(pxo_body* bodies, int nb, pxo_joint* joints, int nj, co
         for (int k = levels[l].start; k < levels[l].end; ++k)
             if (slots[k] >= 0) prestep_joint(&P[slots[k]], imp);
 
-    phase_state S = { imp, is_static, pending, 0, pending_flag };
     int ran0 = 0, ran1 = 0;
     for (int it = 0; it < contact_iters; ++it)                 /* Solver.cpp:175-190 */
     {
         ran0++;
-        if (!run_iteration(P, slots, levels, nlevels, &S, 0, it, &hazards)) break;
+        if (!run_iteration(P, slots, levels, nlevels, imp, 0, it)) break;
     }
-    S.rows = dis;
     for (int it = 0; it < penetration_iters; ++it)             /* Solver.cpp:196-211 */
     {
         ran1++;
-        if (!run_iteration(P, slots, levels, nlevels, &S, 1, it, &hazards)) break;
+        if (!run_iteration(P, slots, levels, nlevels, dis, 1, it)) break;
     }
     /* FinishJoints / FinishBodies, src/Solver.cpp:482-494, 537-545 */
     for (int i = 0; i < nj; ++i)
@@ -545,14 +505,12 @@ void pxo_solve_scheduled(pxo_body* bodies, int nb, pxo_joint* joints, int nj, co
         bodies[i].displacingAngularVelocity = dis[i].w;
     }
     if (iters_out) { iters_out[0] = ran0; iters_out[1] = ran1; }
-    if (hazards_out) *hazards_out = hazards;
-    free(P); free(pending_flag); free(pending); free(is_static); free(dis); free(imp); free(par);
+    free(P); free(dis); free(imp); free(par);
 }
 
 /* SolveJoints<N>, Island_Single: the reference order is "groups of N from PrepareIndices, then the
  * tail one by one"; expressed as a schedule in which every unit is its own level, the scheduled
- * solve above IS the sequential reference loop (the static-body rule degenerates to immediate
- * visibility). */
+ * solve above IS the sequential reference loop. */
 void pxo_solve_joints(pxo_body* bodies, int nb, pxo_joint* joints, int nj, const pxo_contact_point* cps,
     int group, int contact_iters, int penetration_iters, int* joint_index_out, int* iters_out)
 {
@@ -579,7 +537,7 @@ void pxo_solve_joints(pxo_body* bodies, int nb, pxo_joint* joints, int nj, const
         levels[l].start = k; levels[l].grouped_end = k; levels[l].end = k + 1;
         k += 8; l++;
     }
-    pxo_solve_scheduled(bodies, nb, joints, nj, cps, slots, levels, nunits, contact_iters, penetration_iters, iters_out, 0);
+    pxo_solve_scheduled(bodies, nb, joints, nj, cps, slots, levels, nunits, contact_iters, penetration_iters, iters_out);
     if (joint_index_out) memcpy(joint_index_out, order, (size_t)nj * sizeof(int));
     free(levels); free(slots); free(order);
 }

@@ -63,7 +63,7 @@ class SolveStats(C.Structure):
         ("levels", C.c_int32),
         ("contactIterationsRun", C.c_int32),
         ("penetrationIterationsRun", C.c_int32),
-        ("staticHazards", C.c_int32),
+        ("wakePasses", C.c_int32),
         ("ms_schedule", C.c_float),
         ("ms_refresh", C.c_float),
         ("ms_iterations", C.c_float),

@@ -118,9 +118,13 @@ struct phyx_b200_ctx
     phyx::DevBuf q0, q1, q2, q3; // float4 per slot (see solve.cu)
     phyx::DevBuf accNF;          // float2 per slot
     phyx::DevBuf accD;           // float per slot
-    phyx::DevBuf stamps;         // 2 x u64 per body (impulse / displacement static-body stamps)
+    phyx::DevBuf stamps;         // 2 x u64 per body (impulse / displacement static-body words)
+    phyx::DevBuf slotPos;        // int per slot: sequential position of the slot's unit (replay schedules)
+    bool slotPosValid = false;
+    phyx::DevBuf processed;      // int per slot: tick of the pass that ran it
     phyx::DevBuf solveFlags;     // productive flags + result words
     phyx::DevBuf colourTmp;      // colouring scratch
+    std::vector<int> hostSlotPos;
     std::vector<int> hostSlots;  // last schedule (host copy, for get_schedule / KEEP_SCHEDULE)
     std::vector<phyx::Level> hostLevels;
     std::vector<int> hostPairKey; // (b1,b2) list the schedule was built for

@@ -68,7 +68,7 @@ struct Unit
 };
 
 void build_replay(const phyx_contact_joint* joints, int nj, int nb, const std::vector<unsigned char>& statics, int N, bool staticDeps,
-    std::vector<int>& slots, std::vector<Level>& levels)
+    std::vector<int>& slots, std::vector<int>& slotPos, std::vector<Level>& levels)
 {
     std::vector<int> order;
     int groupOffset = reference_order(joints, nj, nb, N, order);
@@ -77,6 +77,10 @@ void build_replay(const phyx_contact_joint* joints, int nj, int nb, const std::v
     for (int g = 0; N > 1 && g < groupOffset; g += N) units.push_back({ g, N, 0 });
     for (int i = groupOffset; i < nj; ++i) units.push_back({ i, 1, 0 });
 
+    // bodyLevel[b]: earliest level the next unit on body b may take.  A dynamic body forces a
+    // strictly later level (its velocity row is read-modify-written); a static body only forces a
+    // level that is not earlier (its joints may share a level, but must not overtake each other:
+    // see "static bodies" in solve.cu), unless staticDeps asks for the strict order there too.
     std::vector<int> bodyLevel(nb, 0);
     int maxLevel = 0;
     for (Unit& u : units)
@@ -85,15 +89,14 @@ void build_replay(const phyx_contact_joint* joints, int nj, int nb, const std::v
         for (int k = 0; k < u.width; ++k)
         {
             const phyx_contact_joint& j = joints[order[u.first + k]];
-            if (staticDeps || !statics[j.body1Index]) lvl = std::max(lvl, bodyLevel[j.body1Index]);
-            if (staticDeps || !statics[j.body2Index]) lvl = std::max(lvl, bodyLevel[j.body2Index]);
+            lvl = std::max(lvl, std::max(bodyLevel[j.body1Index], bodyLevel[j.body2Index]));
         }
         u.level = lvl;   // 0-based level of this unit
         for (int k = 0; k < u.width; ++k)
         {
             const phyx_contact_joint& j = joints[order[u.first + k]];
-            if (staticDeps || !statics[j.body1Index]) bodyLevel[j.body1Index] = lvl + 1;
-            if (staticDeps || !statics[j.body2Index]) bodyLevel[j.body2Index] = lvl + 1;
+            bodyLevel[j.body1Index] = lvl + ((staticDeps || !statics[j.body1Index]) ? 1 : 0);
+            bodyLevel[j.body2Index] = lvl + ((staticDeps || !statics[j.body2Index]) ? 1 : 0);
         }
         maxLevel = std::max(maxLevel, lvl + 1);
     }
@@ -110,21 +113,30 @@ void build_replay(const phyx_contact_joint* joints, int nj, int nb, const std::v
         cursor = (levels[l].end + 7) & ~7;
     }
     slots.assign(cursor, -1);
+    slotPos.assign(cursor, 0);   // sequential position of a slot = index of its unit in the reference order
     std::vector<int> wideAt(maxLevel), singleAt(maxLevel);
     for (int l = 0; l < maxLevel; ++l)
     {
         wideAt[l] = levels[l].start;
         singleAt[l] = levels[l].grouped_end;
     }
-    for (const Unit& u : units)
+    for (size_t ui = 0; ui < units.size(); ++ui)
     {
+        const Unit& u = units[ui];
         if (u.width > 1)
         {
-            for (int k = 0; k < u.width; ++k) slots[wideAt[u.level] + k] = order[u.first + k];
+            for (int k = 0; k < u.width; ++k)
+            {
+                slots[wideAt[u.level] + k] = order[u.first + k];
+                slotPos[wideAt[u.level] + k] = int(ui);
+            }
             wideAt[u.level] += 8;
         }
         else
+        {
+            slotPos[singleAt[u.level]] = int(ui);
             slots[singleAt[u.level]++] = order[u.first];
+        }
     }
 }
 
@@ -217,15 +229,17 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
     for (int i = 0; i < nb; ++i) statics[i] = is_static(params[i]);
 
     std::vector<int>& slots = c->hostSlots;
+    std::vector<int>& slotPos = c->hostSlotPos;
     std::vector<Level>& levels = c->hostLevels;
     slots.clear();
+    slotPos.clear();
     levels.clear();
     switch (mode)
     {
     case PHYX_B200_SCHEDULE_COLOUR: build_colours(hostJoints, nj, nb, statics, slots, levels); break;
-    case PHYX_B200_SCHEDULE_REPLAY_AVX2: build_replay(hostJoints, nj, nb, statics, 8, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, levels); break;
-    case PHYX_B200_SCHEDULE_REPLAY_SSE2: build_replay(hostJoints, nj, nb, statics, 4, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, levels); break;
-    case PHYX_B200_SCHEDULE_REPLAY_SCALAR: build_replay(hostJoints, nj, nb, statics, 1, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, levels); break;
+    case PHYX_B200_SCHEDULE_REPLAY_AVX2: build_replay(hostJoints, nj, nb, statics, 8, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, slotPos, levels); break;
+    case PHYX_B200_SCHEDULE_REPLAY_SSE2: build_replay(hostJoints, nj, nb, statics, 4, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, slotPos, levels); break;
+    case PHYX_B200_SCHEDULE_REPLAY_SCALAR: build_replay(hostJoints, nj, nb, statics, 1, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, slotPos, levels); break;
     default: set_error("solve: unknown schedule %d", mode); return PHYX_B200_ERR_ARGUMENT;
     }
     c->slotCount = int(slots.size());
@@ -236,6 +250,13 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
         PHYX_CUDA(cudaMemcpyAsync(c->slotJoint.ptr, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (!levels.empty())
         PHYX_CUDA(cudaMemcpyAsync(c->levels.ptr, levels.data(), levels.size() * sizeof(Level), cudaMemcpyHostToDevice, c->stream));
+    // colour schedules run in slot order, so a slot's sequential position is its own index
+    c->slotPosValid = !slotPos.empty();
+    if (c->slotPosValid)
+    {
+        PHYX_TRY(c->slotPos.reserve(slotPos.size() * sizeof(int)));
+        PHYX_CUDA(cudaMemcpyAsync(c->slotPos.ptr, slotPos.data(), slotPos.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
     PHYX_CUDA(cudaStreamSynchronize(c->stream));
     c->hostPairKey.swap(key);
     c->scheduleMode = mode;

@@ -30,10 +30,6 @@
 // Compiled with --fmad=false: every float operation is the reference's, in the reference's order.
 #include "common.cuh"
 
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
-
 namespace phyx
 {
 
@@ -53,11 +49,13 @@ struct SolveParams
     float* accD;
     const Level* levels;
     int numLevels;
-    unsigned long long* stampImp;
-    unsigned long long* stampDisp;
+    const int* slotPos;                // position of the slot's unit in the sequential order (null: the slot index)
+    int* processed;                    // per slot: tick of the last pass that ran it (units with a static body only)
+    unsigned long long* staticImp;     // per body: static-body lastIteration word, impulse phase
+    unsigned long long* staticDisp;    //           ... displacement phase
     int contactIters, penetrationIters;
-    unsigned* flags;   // [0, I) impulse productive words, [I, I+D) displacement
-    int* result;       // [0] impulse iterations run, [1] displacement iterations run, [2] static hazards
+    unsigned long long* barrier;       // ring of 4 grid-barrier words
+    int* result;                       // [0] impulse iterations run, [1] displacement iterations run, [2] extra wake passes
 };
 
 __device__ __forceinline__ float vmax(float l, float r) { return l > r ? l : r; }   // SIMD max: l>r?l:r
@@ -139,30 +137,90 @@ __global__ void __launch_bounds__(kBlock) k_finish(int numSlots, const int* __re
     joints[j].frictionLimiter_accumulatedImpulse = a.y;
 }
 
-// ---- static-body lastIteration stamps ----------------------------------------------------------------
-// A static body can sit in many joints of one level, so its lastIteration cannot live in a row
-// that those joints race on.  Per static body one 64-bit word {hi = tick of the latest productive
-// level, lo = tick of the one before}; tick = iteration*numLevels + level + 1.  A reader in tick t
-// sees hi if hi < t, else lo: writes of the CURRENT level are invisible, whatever the timing, so
-// the result is deterministic ("visible to later levels only").
-__device__ __forceinline__ int stamp_visible_last(const unsigned long long* p, unsigned tick, int numLevels)
+// ---- static bodies -----------------------------------------------------------------------------------
+// A static body (invMass = invInertia = 0) never changes velocity, so joints that share one do not
+// conflict and may sit in the same level; thousands of ground contacts would otherwise serialise.
+// What they DO share is the body's lastIteration, which the reference updates joint by joint
+// (Solver.cpp:903-910) and reads in the skip test (:790-798).  To reproduce the sequential
+// semantics exactly, each static body has one 64-bit word per phase:
+//     [63:48] latest iteration in which a joint on it was productive, +1 (0 = never)
+//     [47:32] the productive iteration before that, +1
+//     [31:0]  smallest sequential position among the productive joints of the latest iteration
+// A joint at position p in iteration it therefore sees lastIteration = it exactly when an EARLIER
+// joint (position < p) on that body was productive in this iteration, else the value carried over
+// from previous iterations.  Schedules keep the joints of one static body in non-decreasing level
+// order, so every earlier joint is in the same or an earlier level; if a joint of the same level
+// becomes productive on a body whose carried-over value is stale ("cold"), the level is re-scanned
+// for joints that this wakes up (k_solve, wake passes) until nothing changes.
+__device__ __forceinline__ int static_visible_last(const unsigned long long* p, int it, unsigned pos)
 {
     unsigned long long w = __ldcg(p);
-    unsigned hi = unsigned(w >> 32), lo = unsigned(w);
-    unsigned t = hi < tick ? hi : lo;
-    return t == 0 ? -1 : int((t - 1) / unsigned(numLevels));
+    unsigned latest = unsigned(w >> 48), prev = unsigned(w >> 32) & 0xffffu, minPos = unsigned(w);
+    if (latest == unsigned(it + 1)) return (minPos < pos) ? it : int(prev) - 1;
+    return int(latest) - 1;
 }
 
-__device__ __forceinline__ void stamp_write(unsigned long long* p, unsigned tick)
+// Record "productive at (it, pos)".  Returns true if this changed the word while the body was cold
+// (its carried-over lastIteration <= it-2), i.e. if it can wake up later joints of the same level.
+__device__ __forceinline__ bool static_mark(unsigned long long* p, int it, unsigned pos)
 {
     unsigned long long old = __ldcg(p);
-    while (unsigned(old >> 32) != tick)
+    for (;;)
     {
-        unsigned long long nw = (static_cast<unsigned long long>(tick) << 32) | (old >> 32);
-        unsigned long long prev = atomicCAS(p, old, nw);
-        if (prev == old) break;
-        old = prev;
+        unsigned latest = unsigned(old >> 48), prev = unsigned(old >> 32) & 0xffffu, minPos = unsigned(old);
+        unsigned long long nw;
+        int carried;
+        if (latest == unsigned(it + 1))
+        {
+            if (pos >= minPos) return false;
+            nw = (old & 0xffffffff00000000ull) | pos;
+            carried = int(prev) - 1;
+        }
+        else
+        {
+            nw = (static_cast<unsigned long long>(it + 1) << 48) | (static_cast<unsigned long long>(latest) << 32) | pos;
+            carried = int(latest) - 1;
+        }
+        unsigned long long seen = atomicCAS(p, old, nw);
+        if (seen == old) return carried <= it - 2;
+        old = seen;
     }
+}
+
+// ---- grid barrier -------------------------------------------------------------------------------------
+// One barrier per level.  Besides synchronising, it ORs two flags over the whole grid at no extra
+// latency by packing them into the arrival count: [19:0] arrivals, [39:20] CTAs asking for a wake
+// pass, [59:40] CTAs that saw a productive joint in this iteration.  A ring of four words avoids
+// sense reversal: word e+1 is cleared by CTA 0 before it arrives at barrier e.
+struct BarrierResult
+{
+    bool wake, productive;
+};
+
+__device__ __forceinline__ BarrierResult grid_barrier(unsigned long long* ring, unsigned& epoch, bool wake, bool productive)
+{
+    __shared__ unsigned long long s_value;
+    const int w = __syncthreads_or(wake ? 1 : 0);
+    const int pr = __syncthreads_or(productive ? 1 : 0);
+    if (threadIdx.x == 0)
+    {
+        unsigned long long* word = ring + (epoch & 3u);
+        if (blockIdx.x == 0) ring[(epoch + 1u) & 3u] = 0ull;
+        const unsigned long long add = 1ull | (w ? (1ull << 20) : 0ull) | (pr ? (1ull << 40) : 0ull);
+        __threadfence();
+        unsigned long long v = atomicAdd(word, add) + add;
+        while ((v & 0xfffffull) != gridDim.x)
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word) : "memory");
+        __threadfence();
+        s_value = v;
+    }
+    __syncthreads();
+    const unsigned long long v = s_value;
+    epoch++;
+    BarrierResult r;
+    r.wake = ((v >> 20) & 0xfffffull) != 0;
+    r.productive = ((v >> 40) & 0xfffffull) != 0;
+    return r;
 }
 
 __device__ __forceinline__ float flipsign_bits(float x, float y)   // SIMD_AVX2.h:272-275
@@ -203,14 +261,18 @@ __device__ __forceinline__ void prestep_slot(const SolveParams& P, int s)
     if (!st2) __stcg(&P.vel[b2], v2);
 }
 
-// ---- one level of one iteration ------------------------------------------------------------------------
-// PHASE 0: SolveJointsImpulses (Solver.cpp:781-910); PHASE 1: SolveJointsDisplacement (:937-1014)
+// ---- one pass over one level of one iteration -----------------------------------------------------------
+// PHASE 0: SolveJointsImpulses (Solver.cpp:781-910); PHASE 1: SolveJointsDisplacement (:937-1014).
+// firstPass = false is a wake pass: only units that contain a static body and have not run yet in
+// this (iteration, level) are reconsidered.  Returns productive; sets `wake` if a joint of this
+// pass turned a cold static body productive.
 template <int PHASE>
-__device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L, int it, unsigned tick, int tid, int nthreads)
+__device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L, int it, int tick, bool firstPass, int tid, int nthreads, bool& wake)
 {
     float4* rows = PHASE == 0 ? P.vel : P.disp;
-    unsigned long long* stamps = PHASE == 0 ? P.stampImp : P.stampDisp;
+    unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
     const int lane = threadIdx.x & 31;
+    const unsigned seg = 0xffu << (lane & ~7);   // the 8-lane unit this lane belongs to
     bool anyProductive = false;
 
     for (int s0 = L.start + (tid & ~31); s0 < L.end; s0 += nthreads)   // warp-uniform trip count
@@ -222,22 +284,33 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
         const int r1 = __float_as_int(c3.x), r2 = __float_as_int(c3.y);
         valid = valid && r1 >= 0;
         const int b1 = r1 & kBodyMask, b2 = r2 & kBodyMask;
-        const bool st1 = r1 & kStaticBit, st2 = r2 & kStaticBit;
+        const bool st1 = valid && (r1 & kStaticBit), st2 = valid && (r2 & kStaticBit);
+        const bool wide = s < L.grouped_end;
+
+        // units with a static body are the only ones a wake pass can affect
+        const unsigned mStatic = __ballot_sync(0xffffffffu, st1 || st2);
+        const bool unitHasStatic = wide ? (mStatic & seg) != 0 : (st1 || st2);
+        if (!firstPass)
+        {
+            valid = valid && unitHasStatic;
+            if (valid) valid = __ldcg(&P.processed[s]) != tick;
+        }
 
         float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1;
         int last1 = -1, last2 = -1;
+        unsigned pos = 0;
         bool active = false;
         if (valid)
         {
             v1 = __ldcg(&rows[b1]);
             v2 = __ldcg(&rows[b2]);
-            last1 = st1 ? stamp_visible_last(&stamps[b1], tick, P.numLevels) : __float_as_int(v1.w);
-            last2 = st2 ? stamp_visible_last(&stamps[b2], tick, P.numLevels) : __float_as_int(v2.w);
+            if (st1 || st2) pos = P.slotPos ? unsigned(P.slotPos[s]) : unsigned(s);
+            last1 = st1 ? static_visible_last(&statics[b1], it, pos) : __float_as_int(v1.w);
+            last2 = st2 ? static_visible_last(&statics[b2], it, pos) : __float_as_int(v2.w);
             active = (last1 > it - 2) || (last2 > it - 2);   // Solver.cpp:790-792
         }
-        const bool wide = s < L.grouped_end;
-        unsigned m = __ballot_sync(0xffffffffu, active);
-        if (wide) active = valid && ((m >> (lane & ~7)) & 0xffu);   // AVX2: skip only if none of the 8 lanes (:797)
+        const unsigned mActive = __ballot_sync(0xffffffffu, active);
+        if (wide) active = valid && (mActive & seg) != 0;   // AVX2: skip only if none of the 8 lanes is active (:797)
 
         bool productive = false;
         if (active)
@@ -322,27 +395,22 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
                 productive = fabsf(d) > kProductiveImpulse;
             }
 
-            // lastIteration = it where productive (Solver.cpp:903-910); static bodies via stamps
+            // lastIteration = it where productive (Solver.cpp:903-910)
             if (!st1)
             {
                 v1.w = __int_as_float(productive ? it : last1);
                 __stcg(&rows[b1], v1);
             }
             else if (productive)
-            {
-                if (last1 <= it - 2) atomicAdd(&P.result[2], 1);
-                stamp_write(&stamps[b1], tick);
-            }
+                wake |= static_mark(&statics[b1], it, pos);
             if (!st2)
             {
                 v2.w = __int_as_float(productive ? it : last2);
                 __stcg(&rows[b2], v2);
             }
             else if (productive)
-            {
-                if (last2 <= it - 2) atomicAdd(&P.result[2], 1);
-                stamp_write(&stamps[b2], tick);
-            }
+                wake |= static_mark(&statics[b2], it, pos);
+            if (unitHasStatic) __stcg(&P.processed[s], tick);
         }
         anyProductive |= productive;
     }
@@ -350,54 +418,56 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
 }
 
 // Persistent cooperative kernel: the whole SolveJointIsland loop nest (Solver.cpp:159-211) in one
-// launch, one grid-wide barrier per level.
+// launch, one grid-wide barrier per level (plus one per wake pass, which is rare).
 __global__ void __launch_bounds__(kBlock) k_solve(SolveParams P)
 {
-    cg::grid_group grid = cg::this_grid();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
+    unsigned epoch = 0;
+    int wakePasses = 0;
 
     for (int l = 0; l < P.numLevels; ++l)
     {
         const Level L = P.levels[l];
         for (int s = L.start + tid; s < L.end; s += nthreads) prestep_slot(P, s);
-        grid.sync();
+        grid_barrier(P.barrier, epoch, false, false);
     }
 
-    int ranImpulse = 0;
-    for (int it = 0; it < P.contactIters; ++it)
+    int ran[2] = { 0, 0 };
+    int tick = 0;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase)
     {
-        bool any = false;
-        for (int l = 0; l < P.numLevels; ++l)
+        const int iters = phase == 0 ? P.contactIters : P.penetrationIters;
+        for (int it = 0; it < iters; ++it)
         {
-            any |= solve_level<0>(P, P.levels[l], it, unsigned(it) * unsigned(P.numLevels) + unsigned(l) + 1u, tid, nthreads);
-            if (l + 1 < P.numLevels) grid.sync();
+            bool any = false, productiveAnywhere = false;
+            for (int l = 0; l < P.numLevels; ++l)
+            {
+                const Level L = P.levels[l];
+                ++tick;
+                bool firstPass = true;
+                for (;;)
+                {
+                    bool wake = false;
+                    any |= (phase == 0) ? solve_level<0>(P, L, it, tick, firstPass, tid, nthreads, wake)
+                                        : solve_level<1>(P, L, it, tick, firstPass, tid, nthreads, wake);
+                    BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
+                    productiveAnywhere = r.productive;
+                    if (!r.wake) break;
+                    firstPass = false;
+                    ++wakePasses;
+                }
+            }
+            ran[phase]++;
+            if (!productiveAnywhere) break;   // Solver.cpp:189 / :210
         }
-        if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(&P.flags[it], 1u);
-        grid.sync();
-        ranImpulse++;
-        if (__ldcg(&P.flags[it]) == 0u) break;   // Solver.cpp:189
-    }
-
-    int ranDisp = 0;
-    for (int it = 0; it < P.penetrationIters; ++it)
-    {
-        bool any = false;
-        for (int l = 0; l < P.numLevels; ++l)
-        {
-            any |= solve_level<1>(P, P.levels[l], it, unsigned(it) * unsigned(P.numLevels) + unsigned(l) + 1u, tid, nthreads);
-            if (l + 1 < P.numLevels) grid.sync();
-        }
-        if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(&P.flags[P.contactIters + it], 1u);
-        grid.sync();
-        ranDisp++;
-        if (__ldcg(&P.flags[P.contactIters + it]) == 0u) break;   // Solver.cpp:210
     }
     if (tid == 0)
     {
-        P.result[0] = ranImpulse;
-        P.result[1] = ranDisp;
+        P.result[0] = ran[0];
+        P.result[1] = ran[1];
+        P.result[2] = wakePasses;
     }
 }
 
@@ -427,17 +497,23 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
     PHYX_TRY(c->q3.reserve(ns1 * sizeof(float4)));
     PHYX_TRY(c->accNF.reserve(ns1 * sizeof(float2)));
     PHYX_TRY(c->accD.reserve(ns1 * sizeof(float)));
+    if (I > 60000 || D > 60000)
+    {
+        set_error("solve: at most 60000 iterations per phase");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
     PHYX_TRY(c->stamps.reserve(size_t(nb > 0 ? nb : 1) * 2 * sizeof(unsigned long long)));
-    size_t flagWords = size_t(I + D) + 8;
-    PHYX_TRY(c->solveFlags.reserve(flagWords * sizeof(unsigned)));
+    PHYX_TRY(c->processed.reserve(ns1 * sizeof(int)));
+    PHYX_TRY(c->solveFlags.reserve(64));
 
     cudaEvent_t e0 = c->ev[0], e1 = c->ev[1], e2 = c->ev[2], e3 = c->ev[3];
     PHYX_CUDA(cudaEventRecord(e0, c->stream));
-    int ranI = I > 0 ? 1 : 0, ranD = D > 0 ? 1 : 0, hazards = 0;
+    int ranI = I > 0 ? 1 : 0, ranD = D > 0 ? 1 : 0, wakePasses = 0;
     if (ns > 0 && nl > 0)
     {
         PHYX_CUDA(cudaMemsetAsync(c->stamps.ptr, 0, size_t(nb) * 2 * sizeof(unsigned long long), c->stream));
-        PHYX_CUDA(cudaMemsetAsync(c->solveFlags.ptr, 0, flagWords * sizeof(unsigned), c->stream));
+        PHYX_CUDA(cudaMemsetAsync(c->solveFlags.ptr, 0, 64, c->stream));
+        PHYX_CUDA(cudaMemsetAsync(c->processed.ptr, 0, size_t(ns) * sizeof(int), c->stream));
         int grid = (ns + kBlock - 1) / kBlock;
         k_refresh<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
             c->params.as<float4>(), c->q0.as<float4>(), c->q1.as<float4>(), c->q2.as<float4>(), c->q3.as<float4>(), c->accNF.as<float2>(),
@@ -456,12 +532,14 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         P.accD = c->accD.as<float>();
         P.levels = c->levels.as<Level>();
         P.numLevels = nl;
-        P.stampImp = c->stamps.as<unsigned long long>();
-        P.stampDisp = P.stampImp + nb;
+        P.slotPos = c->slotPosValid ? c->slotPos.as<int>() : nullptr;
+        P.processed = c->processed.as<int>();
+        P.staticImp = c->stamps.as<unsigned long long>();
+        P.staticDisp = P.staticImp + nb;
         P.contactIters = I;
         P.penetrationIters = D;
-        P.flags = c->solveFlags.as<unsigned>();
-        P.result = reinterpret_cast<int*>(P.flags + (I + D));
+        P.barrier = c->solveFlags.as<unsigned long long>();          // 4 words
+        P.result = reinterpret_cast<int*>(c->solveFlags.as<char>() + 32);
         if (c->solveBlocksPerSM == 0)
         {
             int per = 0;
@@ -490,7 +568,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         PHYX_CUDA(cudaStreamSynchronize(c->stream));
         ranI = host[0];
         ranD = host[1];
-        hazards = host[2];
+        wakePasses = host[2];
         if (stats)
         {
             stats->ms_refresh = elapsed(e0, e1);
@@ -507,7 +585,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         stats->levels = nl;
         stats->contactIterationsRun = ranI;
         stats->penetrationIterationsRun = ranD;
-        stats->staticHazards = hazards;
+        stats->wakePasses = wakePasses;
     }
     return PHYX_B200_OK;
 }

@@ -36,24 +36,23 @@ def test_world_update_tracks_reference(ref, scene, steps, mode, flags):
     sc = scenes.make(scene)
     r = ref.RefWorld(sc, "strict")
     w = world.World(sc, solve_flags=flags)
-    hazards = 0
+    wakes = 0
     first_diff = None
     for step in range(steps):
         r.step(solve=mode)
         w.step(solve=mode)
-        hazards += w.solve_stats().staticHazards
+        wakes += w.solve_stats().wakePasses
         if first_diff is None and not np.array_equal(r.bodies()["pos"].view(np.uint32), w.bodies()["pos"].view(np.uint32)):
             first_diff = step
     rb, wb = r.bodies(), w.bodies()
     dpos, dvel = rel_dev(wb, rb)
     print(f"\n{scene} mode={mode} flags={flags}: {steps} steps, joints {len(w.joints())}/{len(r.joints())}, "
-          f"rel dpos {dpos:.3e} dvel {dvel:.3e}, hazards {hazards}, first bit difference at step {first_diff}")
+          f"rel dpos {dpos:.3e} dvel {dvel:.3e}, wake passes {wakes}, first bit difference at step {first_diff}")
     assert len(w.joints()) == len(r.joints()) and len(w.manifolds()) == len(r.manifolds())
     assert dpos <= 1e-4 and dvel <= 1e-4  # north-star tolerance
-    if hazards == 0:
-        assert_records_equal(wb, rb, STATE, what="bodies after N steps")
-        assert_records_equal(w.joints(), r.joints(), what="joint cache")
-        assert_records_equal(w.manifolds(), r.manifolds(), what="manifolds")
+    assert_records_equal(wb, rb, STATE, what="bodies after N steps")
+    assert_records_equal(w.joints(), r.joints(), what="joint cache")
+    assert_records_equal(w.manifolds(), r.manifolds(), what="manifolds")
 
 
 def test_public_stage_functions_are_drop_in(ref):
