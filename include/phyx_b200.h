@@ -175,7 +175,8 @@ PHYX_B200_API int phyx_b200_stage_joints(phyx_b200_ctx* ctx, const phyx_contact_
 /* ... then solve them in place (cached impulses stay on the device; read with fetch_joints). */
 PHYX_B200_API int phyx_b200_solve_staged(phyx_b200_ctx* ctx, const phyx_b200_solve_config* config, phyx_b200_solve_stats* stats);
 PHYX_B200_API int phyx_b200_fetch_joints(phyx_b200_ctx* ctx, phyx_contact_joint* joints, int jointCount);
-/* snapshot / restore of the resident body state (so every timed step does identical work) */
+/* snapshot / restore of the resident body state and of the staged joints' cached impulses (so every
+ * timed step does identical work) */
 PHYX_B200_API int phyx_b200_snapshot_bodies(phyx_b200_ctx* ctx);
 PHYX_B200_API int phyx_b200_restore_bodies(phyx_b200_ctx* ctx);
 /* sweep without the D2H copy: counts only */

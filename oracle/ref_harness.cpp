@@ -93,6 +93,12 @@ int ref_add_body(void* h, float x, float y, float angle, float sx, float sy, int
     return int(b->index);
 }
 
+void ref_add_bodies(void* h, const float* rows6, int count)
+{
+    for (int i = 0; i < count; ++i)
+        ref_add_body(h, rows6[6 * i], rows6[6 * i + 1], rows6[6 * i + 2], rows6[6 * i + 3], rows6[6 * i + 4], rows6[6 * i + 5] != 0.f);
+}
+
 int ref_body_count(void* h) { return static_cast<RefWorld*>(h)->world.bodies.size; }
 int ref_joint_count(void* h) { return static_cast<RefWorld*>(h)->world.solver.contactJoints.size; }
 int ref_manifold_count(void* h) { return static_cast<RefWorld*>(h)->world.collider.manifolds.size; }

@@ -36,6 +36,7 @@ def lib(flavour="strict"):
     l.ref_set_gravity.argtypes = [vp, f32]
     l.ref_add_body.argtypes = [vp, f32, f32, f32, f32, f32, i32]
     l.ref_add_body.restype = i32
+    l.ref_add_bodies.argtypes = [vp, vp, i32]
     for name in ("ref_body_count", "ref_joint_count", "ref_manifold_count", "ref_contact_point_count"):
         getattr(l, name).argtypes = [vp]
         getattr(l, name).restype = i32
@@ -104,9 +105,8 @@ class RefWorld:
             pass
 
     def add_scene(self, scene):
-        add = self.l.ref_add_body
-        for x, y, a, sx, sy, st in np.asarray(scene, dtype=np.float32).tolist():
-            add(self.h, x, y, a, sx, sy, int(st))
+        rows = np.ascontiguousarray(scene, dtype=np.float32)
+        self.l.ref_add_bodies(self.h, _p(rows), rows.shape[0])
 
     def step(self, dt=1.0 / 60.0, solve=T.SOLVE_AVX2, island=T.ISLAND_SINGLE, iters=(20, 20), safe_pairs=True):
         """One World::Update.  safe_pairs=True runs the same eight stages through the public stage

@@ -203,6 +203,19 @@ int bodies_snapshot(phyx_b200_ctx* c, bool restore)
         else
             PHYX_CUDA(cudaMemcpyAsync(s, bufs[k]->ptr, n4, cudaMemcpyDeviceToDevice, c->stream));
     }
+    // staged joints (cached impulses are updated in place by solve_staged) travel with the snapshot
+    size_t jb = size_t(c->jointCount) * sizeof(phyx_contact_joint);
+    if (!restore)
+    {
+        c->snapJointCount = c->jointCount;
+        if (jb)
+        {
+            PHYX_TRY(c->snapJoints.reserve(jb));
+            PHYX_CUDA(cudaMemcpyAsync(c->snapJoints.ptr, c->joints.ptr, jb, cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
+    else if (jb && c->snapJointCount == c->jointCount)
+        PHYX_CUDA(cudaMemcpyAsync(c->joints.ptr, c->snapJoints.ptr, jb, cudaMemcpyDeviceToDevice, c->stream));
     if (restore) c->broadphaseValid = false;
     return PHYX_B200_OK;
 }

@@ -91,6 +91,8 @@ struct phyx_b200_ctx
     phyx::DevBuf size;     // float2 half extents
     phyx::DevBuf aos;      // staging for the 128-byte AoS records
     phyx::DevBuf snap;     // snapshot of vel/disp/acc/params/rot/aabb
+    phyx::DevBuf snapJoints;   // ... and of the staged joints (cached impulses)
+    int snapJointCount = -1;
     bool hasSnapshot = false;
 
     // ---- broadphase -----------------------------------------------------------------------

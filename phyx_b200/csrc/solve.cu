@@ -75,6 +75,15 @@ __device__ __forceinline__ void refresh_limiter(float n1x, float n1y, float w1x,
     cinv = (fabsf(c) > 0.0f) ? __fdiv_rn(1.0f, c) : 0.0f;
 }
 
+// ---- PrepareBodies, Solver.cpp:456-480: the only work left is lastIteration = -1 in both row sets ----
+__global__ void __launch_bounds__(kBlock) k_prepare_bodies(int n, float4* __restrict__ vel, float4* __restrict__ disp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    reinterpret_cast<int*>(vel + i)[3] = -1;
+    reinterpret_cast<int*>(disp + i)[3] = -1;
+}
+
 // ---- PrepareJoints copy + RefreshJoints ----------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __restrict__ slotJoint, const phyx_contact_joint* __restrict__ joints,
     const float4* __restrict__ contactPoints, const float4* __restrict__ params, float4* __restrict__ q0, float4* __restrict__ q1,
@@ -514,6 +523,8 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         PHYX_CUDA(cudaMemsetAsync(c->stamps.ptr, 0, size_t(nb) * 2 * sizeof(unsigned long long), c->stream));
         PHYX_CUDA(cudaMemsetAsync(c->solveFlags.ptr, 0, 64, c->stream));
         PHYX_CUDA(cudaMemsetAsync(c->processed.ptr, 0, size_t(ns) * sizeof(int), c->stream));
+        k_prepare_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, c->vel.as<float4>(), c->disp.as<float4>());
+        c->launches++;
         int grid = (ns + kBlock - 1) / kBlock;
         k_refresh<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
             c->params.as<float4>(), c->q0.as<float4>(), c->q1.as<float4>(), c->q2.as<float4>(), c->q3.as<float4>(), c->accNF.as<float2>(),
