@@ -101,6 +101,8 @@ typedef struct {
                                              (serialises ground contacts; only useful to cross-check the wake passes) */
 #define PHYX_B200_SOLVE_KEEP_SCHEDULE 2   /* reuse the schedule built by the previous solve call if the
                                              joint (body1,body2) list is unchanged */
+#define PHYX_B200_SOLVE_HOST_COLOURING 4  /* COLOUR schedule: build it with the serial host greedy instead of
+                                             the device kernel (cross-check only) */
 
 typedef struct {
     int32_t joints, slots, levels;             /* schedule shape: slots >= joints (padding), levels = colours */

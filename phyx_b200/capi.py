@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libphyx_b200.so")
 
 SCHEDULE_COLOUR, SCHEDULE_REPLAY_AVX2, SCHEDULE_REPLAY_SSE2, SCHEDULE_REPLAY_SCALAR = 0, 1, 2, 3
-SOLVE_STATIC_DEPS, SOLVE_KEEP_SCHEDULE = 1, 2
+SOLVE_STATIC_DEPS, SOLVE_KEEP_SCHEDULE, SOLVE_HOST_COLOURING = 1, 2, 4
 
 LEVEL = np.dtype([("start", np.int32), ("grouped_end", np.int32), ("end", np.int32)])
 

@@ -162,7 +162,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
-        &c->colourTmp };
+        &c->colourTmp, &c->colourKeys, &c->colourSorted };
     for (DevBuf* b : bufs) b->release();
     c->pinned.release();
     for (auto& ev : c->ev)
@@ -386,6 +386,17 @@ int phyx_b200_get_schedule(phyx_b200_ctx* c, int32_t* slots, int32_t slotCapacit
     int32_t* levelCount)
 {
     PHYX_TRY(check(c));
+    if (c->hostSlotsStale)
+    {
+        // device-built schedule: fetch the slot -> joint table on demand
+        c->hostSlots.resize(size_t(c->slotCount));
+        if (c->slotCount)
+        {
+            PHYX_CUDA(cudaMemcpyAsync(c->hostSlots.data(), c->slotJoint.ptr, size_t(c->slotCount) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            PHYX_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        c->hostSlotsStale = false;
+    }
     int ns = int(c->hostSlots.size()), nl = int(c->hostLevels.size());
     if (slotCount) *slotCount = ns;
     if (levelCount) *levelCount = nl;

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numIte
 
 // ---- host side ----------------------------------------------------------------------------------
 
-static int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift, int digits)
+int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift, int digits)
 {
     int blocks = (n + kSortTile - 1) / kSortTile;
     size_t tableInts = size_t(digits) * blocks;

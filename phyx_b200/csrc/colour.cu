@@ -1,0 +1,264 @@
+// phyx_b200 — graph colouring of the joints on the device (PHYX_B200_SCHEDULE_COLOUR).
+//
+// Reference stage replaced here:
+//   Solver::PrepareIndices   src/Solver.cpp:217-273   serial greedy grouping into SIMD-8 sets of
+//                                                      joints with pairwise distinct bodies
+//
+// The same idea at device width: a colour is a set of joints no two of which share a DYNAMIC body
+// (static bodies never change velocity, see solve.cu), so a whole colour can be relaxed in
+// parallel.  The colouring is the Jones-Plassmann parallel form of first-fit greedy: every joint
+// has a fixed pseudo-random priority; in each round a joint whose priority is the smallest among
+// the still uncoloured joints on BOTH of its bodies takes the smallest colour not yet used on
+// either body.  The result is exactly what sequential first-fit produces when it visits the joints
+// in priority order, so it is deterministic (no dependence on thread timing) and checkable on the
+// host; the number of rounds is the longest priority-monotone chain, O(log J) in practice.
+//
+// One persistent cooperative kernel runs all rounds (two grid barriers per round); the joints are
+// then laid out colour-major by one stable counting-sort pass (the broadphase's radix pass on the
+// colour as a 6-bit digit), each colour padded to a multiple of 32 slots.
+#include "common.cuh"
+#include "barrier.cuh"
+
+namespace phyx
+{
+
+constexpr int kBlock = 256;
+constexpr int kMaxColours = 64;
+constexpr unsigned long long kNoClaim = ~0ull;
+
+__device__ __forceinline__ unsigned mix32(unsigned x)   // murmur3 finaliser: the joint's priority
+{
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
+}
+
+// jb[j] = {body1 or -1 if static, body2 or -1 if static}; joints with no dynamic body get colour 0
+__global__ void __launch_bounds__(kBlock) k_colour_init(int nj, const phyx_contact_joint* __restrict__ joints, const float4* __restrict__ params,
+    int2* __restrict__ jb, int* __restrict__ colour)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nj) return;
+    int b1 = joints[j].body1Index, b2 = joints[j].body2Index;
+    float4 p1 = params[b1], p2 = params[b2];
+    if (p1.x == 0.0f && p1.y == 0.0f) b1 = -1;
+    if (p2.x == 0.0f && p2.y == 0.0f) b2 = -1;
+    jb[j] = make_int2(b1, b2);
+    colour[j] = (b1 < 0 && b2 < 0) ? 0 : -1;
+}
+
+struct ColourParams
+{
+    int nj;
+    const int2* jb;
+    int* colour;
+    unsigned long long* claim;   // per body: smallest (priority, joint) among its uncoloured joints
+    unsigned long long* used;    // per body: colours taken
+    unsigned long long* barrier;
+    int* result;                 // [0] rounds, [1] overflow (a joint needed a colour >= 64)
+};
+
+__global__ void __launch_bounds__(kBlock) k_colour_rounds(ColourParams P)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    unsigned epoch = 0;
+    int rounds = 0;
+    bool overflow = false;
+    for (;;)
+    {
+        // claim: every uncoloured joint bids on its dynamic bodies
+        for (int j = tid; j < P.nj; j += nthreads)
+        {
+            if (__ldcg(&P.colour[j]) >= 0) continue;
+            const int2 b = P.jb[j];
+            const unsigned long long key = (static_cast<unsigned long long>(mix32(unsigned(j))) << 32) | unsigned(j);
+            if (b.x >= 0) atomicMin(&P.claim[b.x], key);
+            if (b.y >= 0) atomicMin(&P.claim[b.y], key);
+        }
+        grid_barrier(P.barrier, epoch, false, false);
+        // commit: winners of both bids take the first colour free on both bodies
+        bool left = false;
+        for (int j = tid; j < P.nj; j += nthreads)
+        {
+            if (__ldcg(&P.colour[j]) >= 0) continue;
+            const int2 b = P.jb[j];
+            const unsigned long long key = (static_cast<unsigned long long>(mix32(unsigned(j))) << 32) | unsigned(j);
+            const bool win1 = b.x < 0 || __ldcg(&P.claim[b.x]) == key;
+            const bool win2 = b.y < 0 || __ldcg(&P.claim[b.y]) == key;
+            if (win1 && win2)
+            {
+                unsigned long long m = (b.x >= 0 ? __ldcg(&P.used[b.x]) : 0ull) | (b.y >= 0 ? __ldcg(&P.used[b.y]) : 0ull);
+                int c = __ffsll(~m) - 1;
+                if (c < 0)
+                {
+                    c = kMaxColours - 1;   // keep going so the kernel terminates; the host falls back
+                    overflow = true;
+                }
+                const unsigned long long bit = 1ull << c;
+                if (b.x >= 0)
+                {
+                    __stcg(&P.used[b.x], __ldcg(&P.used[b.x]) | bit);
+                    __stcg(&P.claim[b.x], kNoClaim);
+                }
+                if (b.y >= 0)
+                {
+                    __stcg(&P.used[b.y], __ldcg(&P.used[b.y]) | bit);
+                    __stcg(&P.claim[b.y], kNoClaim);
+                }
+                __stcg(&P.colour[j], c);
+            }
+            else
+                left = true;
+        }
+        ++rounds;
+        BarrierResult r = grid_barrier(P.barrier, epoch, left, overflow);
+        overflow = r.productive;
+        if (!r.wake) break;
+    }
+    if (tid == 0)
+    {
+        P.result[0] = rounds;
+        P.result[1] = overflow ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_colour_keys(int nj, const int* __restrict__ colour, uint2* __restrict__ keys, int* __restrict__ counts)
+{
+    __shared__ int h[kMaxColours];
+    if (threadIdx.x < kMaxColours) h[threadIdx.x] = 0;
+    __syncthreads();
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nj)
+    {
+        int c = colour[j];
+        keys[j] = make_uint2(unsigned(c), unsigned(j));
+        atomicAdd(&h[c], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < kMaxColours && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+
+// counts[64] -> level table (colour c = level c, start aligned to 32), firstPos[c] (rank base in the
+// sorted run), header {numLevels, numSlots, widestLevel}
+__global__ void k_colour_levels(const int* __restrict__ counts, Level* __restrict__ levels, int* __restrict__ firstPos, int* __restrict__ header)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int numLevels = 0;
+    for (int c = 0; c < kMaxColours; ++c)
+        if (counts[c] > 0) numLevels = c + 1;
+    int cursor = 0, run = 0, widest = 0;
+    for (int c = 0; c < numLevels; ++c)
+    {
+        levels[c].start = cursor;
+        levels[c].grouped_end = cursor;
+        levels[c].end = cursor + counts[c];
+        firstPos[c] = run;
+        run += counts[c];
+        widest = max(widest, counts[c]);
+        cursor = (levels[c].end + 31) & ~31;
+    }
+    header[0] = numLevels;
+    header[1] = cursor;
+    header[2] = widest;
+}
+
+__global__ void __launch_bounds__(kBlock) k_colour_place(int nj, const uint2* __restrict__ sorted, const Level* __restrict__ levels,
+    const int* __restrict__ firstPos, int* __restrict__ slotJoint)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nj) return;
+    uint2 e = sorted[p];
+    slotJoint[levels[e.x].start + (p - firstPos[e.x])] = int(e.y);
+}
+
+// Build the colour schedule for the resident joints.  Returns PHYX_B200_ERR_CAPACITY if more than
+// 64 colours are needed (a dynamic body with dozens of joints); the caller then uses the host builder.
+int colour_schedule_build(phyx_b200_ctx* c)
+{
+    const int nj = c->jointCount, nb = c->bodyCount;
+    c->hostSlots.clear();
+    c->hostSlotPos.clear();
+    c->hostLevels.clear();
+    c->slotPosValid = false;
+    c->slotCount = c->levelCount = 0;
+    if (nj == 0) return PHYX_B200_OK;
+
+    const size_t nb1 = size_t(nb > 0 ? nb : 1);
+    // scratch: jb[nj] int2 | colour[nj] int | claim[nb] u64 | used[nb] u64 | counts[64] | firstPos[64] | header[4] | result[4] | barrier[4] u64
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    const size_t oJb = take(size_t(nj) * sizeof(int2)), oColour = take(size_t(nj) * sizeof(int)), oClaim = take(nb1 * 8), oUsed = take(nb1 * 8),
+                 oCounts = take(kMaxColours * sizeof(int)), oFirst = take(kMaxColours * sizeof(int)), oHeader = take(16), oResult = take(16),
+                 oBarrier = take(32);
+    PHYX_TRY(c->colourTmp.reserve(off));
+    char* base = c->colourTmp.as<char>();
+    int2* jb = reinterpret_cast<int2*>(base + oJb);
+    int* colour = reinterpret_cast<int*>(base + oColour);
+    unsigned long long* claim = reinterpret_cast<unsigned long long*>(base + oClaim);
+    unsigned long long* used = reinterpret_cast<unsigned long long*>(base + oUsed);
+    int* counts = reinterpret_cast<int*>(base + oCounts);
+    int* firstPos = reinterpret_cast<int*>(base + oFirst);
+    int* header = reinterpret_cast<int*>(base + oHeader);
+    int* result = reinterpret_cast<int*>(base + oResult);
+    unsigned long long* barrier = reinterpret_cast<unsigned long long*>(base + oBarrier);
+
+    PHYX_CUDA(cudaMemsetAsync(claim, 0xff, nb1 * 8, c->stream));
+    PHYX_CUDA(cudaMemsetAsync(used, 0, nb1 * 8, c->stream));
+    PHYX_CUDA(cudaMemsetAsync(base + oCounts, 0, off - oCounts, c->stream));   // counts .. barrier
+
+    const int grid = (nj + kBlock - 1) / kBlock;
+    k_colour_init<<<grid, kBlock, 0, c->stream>>>(nj, c->joints.as<phyx_contact_joint>(), c->params.as<float4>(), jb, colour);
+    c->launches++;
+
+    if (c->colourBlocksPerSM == 0)
+    {
+        int per = 0;
+        PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_colour_rounds, kBlock, 0));
+        c->colourBlocksPerSM = per > 0 ? per : 1;
+    }
+    ColourParams P = { nj, jb, colour, claim, used, barrier, result };
+    int cgrid = std::max(1, std::min(grid, c->numSMs * c->colourBlocksPerSM));
+    void* args[] = { &P };
+    PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_colour_rounds, dim3(cgrid), dim3(kBlock), args, 0, c->stream));
+    c->launches++;
+
+    // colour-major layout: stable counting sort of {colour, joint} on a 6-bit digit
+    PHYX_TRY(c->colourKeys.reserve(size_t(nj) * sizeof(uint2)));
+    PHYX_TRY(c->colourSorted.reserve(size_t(nj) * sizeof(uint2)));
+    k_colour_keys<<<grid, kBlock, 0, c->stream>>>(nj, colour, c->colourKeys.as<uint2>(), counts);
+    c->launches++;
+    PHYX_TRY(radix_pass(c, c->colourKeys.as<uint2>(), c->colourSorted.as<uint2>(), nj, 0, kMaxColours));
+    PHYX_TRY(c->levels.reserve(kMaxColours * sizeof(Level)));
+    k_colour_levels<<<1, 32, 0, c->stream>>>(counts, c->levels.as<Level>(), firstPos, header);
+    c->launches++;
+    const size_t maxSlots = size_t(nj) + 32 * kMaxColours;
+    PHYX_TRY(c->slotJoint.reserve(maxSlots * sizeof(int)));
+    PHYX_CUDA(cudaMemsetAsync(c->slotJoint.ptr, 0xff, maxSlots * sizeof(int), c->stream));
+    k_colour_place<<<grid, kBlock, 0, c->stream>>>(nj, c->colourSorted.as<uint2>(), c->levels.as<Level>(), firstPos, c->slotJoint.as<int>());
+    c->launches++;
+    PHYX_CUDA(cudaGetLastError());
+
+    struct { int header[4]; int result[4]; } host;
+    PHYX_CUDA(cudaMemcpyAsync(host.header, header, 16, cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaMemcpyAsync(host.result, result, 16, cudaMemcpyDeviceToHost, c->stream));
+    Level lv[kMaxColours];
+    PHYX_CUDA(cudaMemcpyAsync(lv, c->levels.ptr, sizeof(lv), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    if (host.result[1])
+    {
+        set_error("colouring needs more than %d colours", kMaxColours);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    c->levelCount = host.header[0];
+    c->slotCount = host.header[1];
+    c->colourRounds = host.result[0];
+    c->hostLevels.assign(lv, lv + c->levelCount);
+    c->hostSlotsStale = true;
+    return PHYX_B200_OK;
+}
+
+} // namespace phyx

@@ -126,6 +126,8 @@ struct phyx_b200_ctx
     phyx::DevBuf processed;      // int per slot: tick of the pass that ran it
     phyx::DevBuf solveFlags;     // productive flags + result words
     phyx::DevBuf colourTmp;      // colouring scratch
+    phyx::DevBuf colourKeys, colourSorted;   // uint2 {colour, joint} before / after the counting sort
+    bool hostSlotsStale = false; // schedule lives on the device only; get_schedule fetches it on demand
     std::vector<int> hostSlotPos;
     std::vector<int> hostSlots;  // last schedule (host copy, for get_schedule / KEEP_SCHEDULE)
     std::vector<phyx::Level> hostLevels;
@@ -135,7 +137,7 @@ struct phyx_b200_ctx
 
     phyx::HostBuf pinned;        // pinned staging for H2D/D2H
     cudaEvent_t ev[8] = {};
-    int solveBlocksPerSM = 0;
+    int solveBlocksPerSM = 0, colourBlocksPerSM = 0, colourRounds = 0;
 };
 
 namespace phyx
@@ -150,6 +152,11 @@ int bodies_snapshot(phyx_b200_ctx* c, bool restore);
 // broadphase.cu
 int broadphase_update(phyx_b200_ctx* c);
 int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats);
+// one stable LSD pass over {key, value} pairs on `digits` (power of two <= 2048) bins of key >> shift
+int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift, int digits);
+
+// colour.cu
+int colour_schedule_build(phyx_b200_ctx* c);
 
 // schedule.cu
 int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int nj, int mode, int flags);

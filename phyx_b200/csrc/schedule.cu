@@ -201,8 +201,9 @@ void build_colours(const phyx_contact_joint* joints, int nj, int nb, const std::
 int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int nj, int mode, int flags)
 {
     const int nb = c->bodyCount;
-    // (body1, body2) list: validates indices and detects an unchanged joint graph
-    std::vector<int> key(size_t(nj) * 2);
+    // (body1, body2) list: validates indices and (on request) detects an unchanged joint graph
+    const bool wantKey = (flags & PHYX_B200_SOLVE_KEEP_SCHEDULE) != 0;
+    std::vector<int> key(wantKey ? size_t(nj) * 2 : 0);
     for (int j = 0; j < nj; ++j)
     {
         int b1 = hostJoints[j].body1Index, b2 = hostJoints[j].body2Index;
@@ -211,12 +212,26 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
             set_error("solve: joint %d references body (%d,%d) outside [0,%d)", j, b1, b2, nb);
             return PHYX_B200_ERR_ARGUMENT;
         }
-        key[2 * j] = b1;
-        key[2 * j + 1] = b2;
+        if (wantKey)
+        {
+            key[2 * j] = b1;
+            key[2 * j + 1] = b2;
+        }
     }
-    const bool keep = (flags & PHYX_B200_SOLVE_KEEP_SCHEDULE) && c->scheduleMode == mode &&
-                      c->scheduleFlags == (flags & PHYX_B200_SOLVE_STATIC_DEPS) && key == c->hostPairKey;
+    const bool keep = wantKey && c->scheduleMode == mode && c->scheduleFlags == (flags & PHYX_B200_SOLVE_STATIC_DEPS) && key == c->hostPairKey;
     if (keep) return PHYX_B200_OK;
+    c->hostPairKey.swap(key);
+    c->scheduleMode = mode;
+    c->scheduleFlags = flags & PHYX_B200_SOLVE_STATIC_DEPS;
+
+    // throughput schedule: colour on the device (the joints are already resident)
+    if (mode == PHYX_B200_SCHEDULE_COLOUR && !(flags & PHYX_B200_SOLVE_HOST_COLOURING))
+    {
+        int st = colour_schedule_build(c);
+        if (st != PHYX_B200_ERR_CAPACITY) return st;
+        // more than 64 colours (a dynamic body with dozens of joints): the host builder has no limit
+    }
+    c->hostSlotsStale = false;
 
     // static flags from the resident body parameters
     std::vector<float4> params(size_t(nb > 0 ? nb : 1));
@@ -258,9 +273,6 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
         PHYX_CUDA(cudaMemcpyAsync(c->slotPos.ptr, slotPos.data(), slotPos.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     }
     PHYX_CUDA(cudaStreamSynchronize(c->stream));
-    c->hostPairKey.swap(key);
-    c->scheduleMode = mode;
-    c->scheduleFlags = flags & PHYX_B200_SOLVE_STATIC_DEPS;
     return PHYX_B200_OK;
 }
 

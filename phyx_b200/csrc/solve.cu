@@ -29,6 +29,7 @@
 //
 // Compiled with --fmad=false: every float operation is the reference's, in the reference's order.
 #include "common.cuh"
+#include "barrier.cuh"
 
 namespace phyx
 {
@@ -194,42 +195,6 @@ __device__ __forceinline__ bool static_mark(unsigned long long* p, int it, unsig
         if (seen == old) return carried <= it - 2;
         old = seen;
     }
-}
-
-// ---- grid barrier -------------------------------------------------------------------------------------
-// One barrier per level.  Besides synchronising, it ORs two flags over the whole grid at no extra
-// latency by packing them into the arrival count: [19:0] arrivals, [39:20] CTAs asking for a wake
-// pass, [59:40] CTAs that saw a productive joint in this iteration.  A ring of four words avoids
-// sense reversal: word e+1 is cleared by CTA 0 before it arrives at barrier e.
-struct BarrierResult
-{
-    bool wake, productive;
-};
-
-__device__ __forceinline__ BarrierResult grid_barrier(unsigned long long* ring, unsigned& epoch, bool wake, bool productive)
-{
-    __shared__ unsigned long long s_value;
-    const int w = __syncthreads_or(wake ? 1 : 0);
-    const int pr = __syncthreads_or(productive ? 1 : 0);
-    if (threadIdx.x == 0)
-    {
-        unsigned long long* word = ring + (epoch & 3u);
-        if (blockIdx.x == 0) ring[(epoch + 1u) & 3u] = 0ull;
-        const unsigned long long add = 1ull | (w ? (1ull << 20) : 0ull) | (pr ? (1ull << 40) : 0ull);
-        __threadfence();
-        unsigned long long v = atomicAdd(word, add) + add;
-        while ((v & 0xfffffull) != gridDim.x)
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word) : "memory");
-        __threadfence();
-        s_value = v;
-    }
-    __syncthreads();
-    const unsigned long long v = s_value;
-    epoch++;
-    BarrierResult r;
-    r.wake = ((v >> 20) & 0xfffffull) != 0;
-    r.productive = ((v >> 40) & 0xfffffull) != 0;
-    return r;
 }
 
 __device__ __forceinline__ float flipsign_bits(float x, float y)   // SIMD_AVX2.h:272-275

@@ -158,3 +158,55 @@ def test_radix_sort_is_stable_on_ties_and_ragged_sizes(ctx, oracle):
         pairs, stats = ctx.sweep_pairs()
         want, tests = oracle.sweep_pairs(oracle.update_broadphase(b))
         assert np.array_equal(pairs, want) and stats.tests == tests
+
+
+def _mix32(x):
+    x = np.uint32(x)
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint32(16)
+        x *= np.uint32(0x85EBCA6B)
+        x ^= x >> np.uint32(13)
+        x *= np.uint32(0xC2B2AE35)
+        x ^= x >> np.uint32(16)
+    return int(x)
+
+
+@pytest.mark.parametrize("name", ["solve_pyramid_1k_s30.npz", "solve_stack_1k_s40.npz"])
+def test_device_colouring_is_priority_first_fit(ctx, name):
+    """The device colouring (Jones-Plassmann rounds) must equal sequential first-fit over the joints
+    visited in priority order: deterministic, independent of thread timing."""
+    g = golden(name)
+    joints, bodies = g["joints"], g["bodies"]
+    ctx.upload_bodies(bodies)
+    ctx.solve_joints(joints, g["contact_points"], schedule=capi.SCHEDULE_COLOUR)
+    slots, levels = ctx.get_schedule()
+    check_schedule(slots, levels, joints, bodies)
+    got = np.full(joints.shape[0], -1)
+    for c, lv in enumerate(levels):
+        s = slots[lv["start"]:lv["end"]]
+        assert np.all(s >= 0) and np.all(np.diff(s) > 0)  # colour-major, joint order inside a colour
+        got[s] = c
+    static = (bodies["invMass"] == 0) & (bodies["invInertia"] == 0)
+    used = {}
+    want = np.zeros(joints.shape[0], dtype=int)
+    for j in sorted(range(joints.shape[0]), key=lambda j: (_mix32(j), j)):
+        bs = [b for b in (int(joints["body1Index"][j]), int(joints["body2Index"][j])) if not static[b]]
+        taken = set().union(*[used.get(b, set()) for b in bs]) if bs else set()
+        c = 0
+        while c in taken:
+            c += 1
+        want[j] = c
+        for b in bs:
+            used.setdefault(b, set()).add(c)
+    assert np.array_equal(got, want)
+
+
+def test_host_colouring_cross_check(ctx, oracle):
+    g = golden("solve_pyramid_1k_s30.npz")
+    ctx.upload_bodies(g["bodies"])
+    j, stats = ctx.solve_joints(g["joints"], g["contact_points"], schedule=capi.SCHEDULE_COLOUR, flags=capi.SOLVE_HOST_COLOURING)
+    slots, levels = ctx.get_schedule()
+    check_schedule(slots, levels, g["joints"], g["bodies"])
+    ob, oj, ran = oracle.solve_scheduled(g["bodies"], g["joints"], g["contact_points"], slots, levels)
+    assert_records_equal(j, oj, what="joints")
+    assert_records_equal(ctx.download_bodies(), ob, VEL_FIELDS, what="bodies")
