@@ -108,6 +108,10 @@ typedef struct {
     int32_t joints, slots, levels;             /* schedule shape: slots >= joints (padding), levels = colours */
     int32_t contactIterationsRun, penetrationIterationsRun;  /* with the productive early-out */
     int32_t wakePasses;                        /* extra level passes run for static-body wake-ups (DESIGN.md "static bodies") */
+    int32_t colourRounds;                      /* rounds the device colouring needed (0: host-built schedule) */
+    int32_t reserved_;
+    int64_t activeJointIterations[2];          /* joint-iterations actually relaxed (not skipped by the lastIteration
+                                                  test) in the impulse / displacement loops */
     float ms_schedule, ms_refresh, ms_iterations, ms_finish, ms_total;   /* CUDA-event times */
     float ms_h2d, ms_d2h;
 } phyx_b200_solve_stats;

@@ -64,6 +64,9 @@ class SolveStats(C.Structure):
         ("contactIterationsRun", C.c_int32),
         ("penetrationIterationsRun", C.c_int32),
         ("wakePasses", C.c_int32),
+        ("colourRounds", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("activeJointIterations", C.c_int64 * 2),
         ("ms_schedule", C.c_float),
         ("ms_refresh", C.c_float),
         ("ms_iterations", C.c_float),
@@ -74,7 +77,7 @@ class SolveStats(C.Structure):
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k == "activeJointIterations" else getattr(self, k)) for k, _ in self._fields_}
 
 
 class BroadphaseStats(C.Structure):

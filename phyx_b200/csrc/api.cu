@@ -90,14 +90,7 @@ static int stage_joints(phyx_b200_ctx* c, const phyx_contact_joint* joints, int 
         set_error("solve: bad joint / contact point arrays");
         return PHYX_B200_ERR_ARGUMENT;
     }
-    for (int j = 0; j < nj; ++j)
-    {
-        if (joints[j].contactPointIndex < 0 || joints[j].contactPointIndex >= ncp)
-        {
-            set_error("solve: joint %d references contact point %d outside [0,%d)", j, joints[j].contactPointIndex, ncp);
-            return PHYX_B200_ERR_ARGUMENT;
-        }
-    }
+    // index validation happens where the schedule is built (on the device for the colour schedule)
     PHYX_TRY(c->joints.reserve(size_t(std::max(nj, 1)) * sizeof(phyx_contact_joint)));
     PHYX_TRY(c->contactPoints.reserve(size_t(std::max(ncp, 1)) * sizeof(phyx_contact_point)));
     if (nj > 0) PHYX_CUDA(cudaMemcpyAsync(c->joints.ptr, joints, size_t(nj) * sizeof(phyx_contact_joint), cudaMemcpyHostToDevice, c->stream));

@@ -37,12 +37,21 @@ __device__ __forceinline__ unsigned mix32(unsigned x)   // murmur3 finaliser: th
 }
 
 // jb[j] = {body1 or -1 if static, body2 or -1 if static}; joints with no dynamic body get colour 0
-__global__ void __launch_bounds__(kBlock) k_colour_init(int nj, const phyx_contact_joint* __restrict__ joints, const float4* __restrict__ params,
-    int2* __restrict__ jb, int* __restrict__ colour)
+// Also validates the joint's indices (result[2] = 1 + first bad joint seen): nothing on the host
+// has to walk the joint array.
+__global__ void __launch_bounds__(kBlock) k_colour_init(int nj, int nb, int ncp, const phyx_contact_joint* __restrict__ joints,
+    const float4* __restrict__ params, int2* __restrict__ jb, int* __restrict__ colour, int* __restrict__ result)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nj) return;
-    int b1 = joints[j].body1Index, b2 = joints[j].body2Index;
+    int b1 = joints[j].body1Index, b2 = joints[j].body2Index, cp = joints[j].contactPointIndex;
+    if (b1 < 0 || b1 >= nb || b2 < 0 || b2 >= nb || cp < 0 || cp >= ncp)
+    {
+        atomicMax(&result[2], j + 1);
+        jb[j] = make_int2(-1, -1);
+        colour[j] = 0;
+        return;
+    }
     float4 p1 = params[b1], p2 = params[b2];
     if (p1.x == 0.0f && p1.y == 0.0f) b1 = -1;
     if (p2.x == 0.0f && p2.y == 0.0f) b2 = -1;
@@ -211,7 +220,8 @@ int colour_schedule_build(phyx_b200_ctx* c)
     PHYX_CUDA(cudaMemsetAsync(base + oCounts, 0, off - oCounts, c->stream));   // counts .. barrier
 
     const int grid = (nj + kBlock - 1) / kBlock;
-    k_colour_init<<<grid, kBlock, 0, c->stream>>>(nj, c->joints.as<phyx_contact_joint>(), c->params.as<float4>(), jb, colour);
+    k_colour_init<<<grid, kBlock, 0, c->stream>>>(nj, nb, c->contactPointCount, c->joints.as<phyx_contact_joint>(), c->params.as<float4>(), jb, colour,
+        result);
     c->launches++;
 
     if (c->colourBlocksPerSM == 0)
@@ -248,6 +258,11 @@ int colour_schedule_build(phyx_b200_ctx* c)
     Level lv[kMaxColours];
     PHYX_CUDA(cudaMemcpyAsync(lv, c->levels.ptr, sizeof(lv), cudaMemcpyDeviceToHost, c->stream));
     PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    if (host.result[2])
+    {
+        set_error("solve: joint %d references a body outside [0,%d) or a contact point outside [0,%d)", host.result[2] - 1, nb, c->contactPointCount);
+        return PHYX_B200_ERR_ARGUMENT;
+    }
     if (host.result[1])
     {
         set_error("colouring needs more than %d colours", kMaxColours);

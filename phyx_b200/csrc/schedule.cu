@@ -200,16 +200,19 @@ void build_colours(const phyx_contact_joint* joints, int nj, int nb, const std::
 
 int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int nj, int mode, int flags)
 {
-    const int nb = c->bodyCount;
-    // (body1, body2) list: validates indices and (on request) detects an unchanged joint graph
+    const int nb = c->bodyCount, ncp = c->contactPointCount;
+    const bool deviceColouring = mode == PHYX_B200_SCHEDULE_COLOUR && !(flags & PHYX_B200_SOLVE_HOST_COLOURING);
+    // (body1, body2) list: validates indices and (on request) detects an unchanged joint graph.
+    // The device colouring validates in its own first kernel, so the host walks the joints only
+    // for host-built schedules or when asked to compare with the previous call.
     const bool wantKey = (flags & PHYX_B200_SOLVE_KEEP_SCHEDULE) != 0;
     std::vector<int> key(wantKey ? size_t(nj) * 2 : 0);
-    for (int j = 0; j < nj; ++j)
+    for (int j = 0; j < nj && (wantKey || !deviceColouring); ++j)
     {
-        int b1 = hostJoints[j].body1Index, b2 = hostJoints[j].body2Index;
-        if (b1 < 0 || b1 >= nb || b2 < 0 || b2 >= nb)
+        int b1 = hostJoints[j].body1Index, b2 = hostJoints[j].body2Index, cp = hostJoints[j].contactPointIndex;
+        if (b1 < 0 || b1 >= nb || b2 < 0 || b2 >= nb || cp < 0 || cp >= ncp)
         {
-            set_error("solve: joint %d references body (%d,%d) outside [0,%d)", j, b1, b2, nb);
+            set_error("solve: joint %d references a body outside [0,%d) or a contact point outside [0,%d)", j, nb, ncp);
             return PHYX_B200_ERR_ARGUMENT;
         }
         if (wantKey)
@@ -225,13 +228,14 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
     c->scheduleFlags = flags & PHYX_B200_SOLVE_STATIC_DEPS;
 
     // throughput schedule: colour on the device (the joints are already resident)
-    if (mode == PHYX_B200_SCHEDULE_COLOUR && !(flags & PHYX_B200_SOLVE_HOST_COLOURING))
+    if (deviceColouring)
     {
         int st = colour_schedule_build(c);
         if (st != PHYX_B200_ERR_CAPACITY) return st;
         // more than 64 colours (a dynamic body with dozens of joints): the host builder has no limit
     }
     c->hostSlotsStale = false;
+    c->colourRounds = 0;
 
     // static flags from the resident body parameters
     std::vector<float4> params(size_t(nb > 0 ? nb : 1));

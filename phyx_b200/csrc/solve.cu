@@ -57,6 +57,7 @@ struct SolveParams
     int contactIters, penetrationIters;
     unsigned long long* barrier;       // ring of 4 grid-barrier words
     int* result;                       // [0] impulse iterations run, [1] displacement iterations run, [2] extra wake passes
+    unsigned long long* activeTotal;   // [2] joint-iterations relaxed (not skipped) per phase
 };
 
 __device__ __forceinline__ float vmax(float l, float r) { return l > r ? l : r; }   // SIMD max: l>r?l:r
@@ -241,7 +242,8 @@ __device__ __forceinline__ void prestep_slot(const SolveParams& P, int s)
 // this (iteration, level) are reconsidered.  Returns productive; sets `wake` if a joint of this
 // pass turned a cold static body productive.
 template <int PHASE>
-__device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L, int it, int tick, bool firstPass, int tid, int nthreads, bool& wake)
+__device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L, int it, int tick, bool firstPass, int tid, int nthreads, bool& wake,
+    unsigned& activeCount)
 {
     float4* rows = PHASE == 0 ? P.vel : P.disp;
     unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
@@ -289,6 +291,7 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
         bool productive = false;
         if (active)
         {
+            ++activeCount;
             const float4 c0 = __ldcs(&P.q0[s]);
             const float4 c2 = __ldcs(&P.q2[s]);
             const float nx = c0.x, ny = c0.y, aN1 = c0.z, aN2 = c0.w;
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(kBlock) k_solve(SolveParams P)
     }
 
     int ran[2] = { 0, 0 };
+    unsigned active[2] = { 0u, 0u };
     int tick = 0;
 #pragma unroll 1
     for (int phase = 0; phase < 2; ++phase)
@@ -424,8 +428,8 @@ __global__ void __launch_bounds__(kBlock) k_solve(SolveParams P)
                 for (;;)
                 {
                     bool wake = false;
-                    any |= (phase == 0) ? solve_level<0>(P, L, it, tick, firstPass, tid, nthreads, wake)
-                                        : solve_level<1>(P, L, it, tick, firstPass, tid, nthreads, wake);
+                    any |= (phase == 0) ? solve_level<0>(P, L, it, tick, firstPass, tid, nthreads, wake, active[0])
+                                        : solve_level<1>(P, L, it, tick, firstPass, tid, nthreads, wake, active[1]);
                     BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
                     productiveAnywhere = r.productive;
                     if (!r.wake) break;
@@ -436,6 +440,12 @@ __global__ void __launch_bounds__(kBlock) k_solve(SolveParams P)
             ran[phase]++;
             if (!productiveAnywhere) break;   // Solver.cpp:189 / :210
         }
+    }
+    for (int phase = 0; phase < 2; ++phase)
+    {
+        unsigned v = active[phase];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.activeTotal[phase], static_cast<unsigned long long>(v));
     }
     if (tid == 0)
     {
@@ -516,6 +526,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         P.penetrationIters = D;
         P.barrier = c->solveFlags.as<unsigned long long>();          // 4 words
         P.result = reinterpret_cast<int*>(c->solveFlags.as<char>() + 32);
+        P.activeTotal = reinterpret_cast<unsigned long long*>(c->solveFlags.as<char>() + 48);
         if (c->solveBlocksPerSM == 0)
         {
             int per = 0;
@@ -539,12 +550,17 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         k_finish<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->accNF.as<float2>(), c->joints.as<phyx_contact_joint>());
         c->launches++;
         PHYX_CUDA(cudaEventRecord(e3, c->stream));
-        int host[3];
+        int host[8];   // result[0..2], pad, activeTotal[2] as two 64-bit words
         PHYX_CUDA(cudaMemcpyAsync(host, P.result, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
         PHYX_CUDA(cudaStreamSynchronize(c->stream));
         ranI = host[0];
         ranD = host[1];
         wakePasses = host[2];
+        if (stats)
+        {
+            memcpy(&stats->activeJointIterations[0], &host[4], 8);
+            memcpy(&stats->activeJointIterations[1], &host[6], 8);
+        }
         if (stats)
         {
             stats->ms_refresh = elapsed(e0, e1);
@@ -562,6 +578,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         stats->contactIterationsRun = ranI;
         stats->penetrationIterationsRun = ranD;
         stats->wakePasses = wakePasses;
+        stats->colourRounds = c->colourRounds;
     }
     return PHYX_B200_OK;
 }

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_sizes_match_header():
     assert C.sizeof(capi.SolveConfig) == 16
-    assert C.sizeof(capi.SolveStats) == 6 * 4 + 7 * 4
+    assert C.sizeof(capi.SolveStats) == 8 * 4 + 2 * 8 + 7 * 4 + 4  # 4 B tail padding (int64 alignment)
     assert C.sizeof(capi.BroadphaseStats) == 8 + 8 + 12 + 4  # 3 floats + tail padding
 
 
