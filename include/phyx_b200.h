@@ -174,6 +174,36 @@ PHYX_B200_API int phyx_b200_solve_joints(phyx_b200_ctx* ctx, phyx_contact_joint*
 PHYX_B200_API int phyx_b200_get_schedule(phyx_b200_ctx* ctx, int32_t* slots, int32_t slotCapacity,
     int32_t* levels3, int32_t levelCapacity, int32_t* slotCount, int32_t* levelCount);
 
+/* ---- resident collider stages: a whole World::Update without leaving HBM ------------------------ */
+/* The manifold cache (Collider::manifolds / contactPoints / manifoldMap, Collider.h:58-61) and the joint
+ * cache (Solver::contactJoints, Solver.h:108) live in the context; every stage below works on them in
+ * place and reproduces the reference's ordering rules (sweep-order append, swap-with-last removal),
+ * so the arrays read back with the download calls are bit-identical to the reference's. */
+
+/* Collider::UpdatePairs, reference src/Collider.cpp:286-366: sweep + "not in the cache yet" filter; new
+ * manifolds are appended in sweep order.  stats->pairs counts every overlapping pair (cache lookups). */
+PHYX_B200_API int phyx_b200_update_pairs(phyx_b200_ctx* ctx, phyx_b200_broadphase_stats* stats);
+/* Collider::UpdateManifolds, reference src/Collider.cpp:8-245,368-377: box-box SAT + clipping, <= 2 points */
+PHYX_B200_API int phyx_b200_update_manifolds(phyx_b200_ctx* ctx);
+/* Collider::PackManifolds, reference src/Collider.cpp:379-416 */
+PHYX_B200_API int phyx_b200_pack_manifolds(phyx_b200_ctx* ctx);
+/* World::RefreshContactJoints, reference src/World.cpp:72-149; the three counters are the reference's
+ * Matched / Created / Deleted meta counters (World.cpp:146-148); any of them may be NULL */
+PHYX_B200_API int phyx_b200_refresh_contact_joints(phyx_b200_ctx* ctx, int32_t* matched, int32_t* created, int32_t* deleted);
+/* Solver::SolveJoints on the resident joint cache (same as solve_joints without the host arrays) */
+PHYX_B200_API int phyx_b200_solve_resident(phyx_b200_ctx* ctx, const phyx_b200_solve_config* config, phyx_b200_solve_stats* stats);
+/* resetWorld() clears manifolds, manifoldMap and contactJoints (reference src/main.cpp:86-89) */
+PHYX_B200_API int phyx_b200_reset_collider(phyx_b200_ctx* ctx);
+/* sizes of Collider::manifolds, Collider::contactPoints, Solver::contactJoints */
+PHYX_B200_API int phyx_b200_collider_counts(phyx_b200_ctx* ctx, int32_t* manifolds, int32_t* contactPoints, int32_t* joints);
+/* host mirrors of the three arrays (the demo reads them for rendering and the HUD, main.cpp:357-413) */
+PHYX_B200_API int phyx_b200_download_manifolds(phyx_b200_ctx* ctx, phyx_manifold* out, int capacity);
+PHYX_B200_API int phyx_b200_download_contact_points(phyx_b200_ctx* ctx, phyx_contact_point* out, int capacity);
+PHYX_B200_API int phyx_b200_download_joints(phyx_b200_ctx* ctx, phyx_contact_joint* out, int capacity);
+/* push a complete collider state built elsewhere (contactPoints holds 2*manifoldCount records) */
+PHYX_B200_API int phyx_b200_upload_collider(phyx_b200_ctx* ctx, const phyx_manifold* manifolds, int manifoldCount,
+    const phyx_contact_point* contactPoints, const phyx_contact_joint* joints, int jointCount);
+
 /* ---- device-resident variants (inputs already in HBM; used for kernel-only timing) ------------ */
 /* Stage joints + contact points in HBM once ... */
 PHYX_B200_API int phyx_b200_stage_joints(phyx_b200_ctx* ctx, const phyx_contact_joint* joints, int jointCount,

@@ -44,6 +44,17 @@ EXPORTS = (
     "phyx_b200_snapshot_bodies",
     "phyx_b200_restore_bodies",
     "phyx_b200_sweep_pairs_resident",
+    "phyx_b200_update_pairs",
+    "phyx_b200_update_manifolds",
+    "phyx_b200_pack_manifolds",
+    "phyx_b200_refresh_contact_joints",
+    "phyx_b200_solve_resident",
+    "phyx_b200_reset_collider",
+    "phyx_b200_collider_counts",
+    "phyx_b200_download_manifolds",
+    "phyx_b200_download_contact_points",
+    "phyx_b200_download_joints",
+    "phyx_b200_upload_collider",
 )
 
 
@@ -126,6 +137,17 @@ def load():
     l.phyx_b200_fetch_joints.argtypes = [vp, vp, i32]
     l.phyx_b200_snapshot_bodies.argtypes = [vp]
     l.phyx_b200_restore_bodies.argtypes = [vp]
+    l.phyx_b200_update_pairs.argtypes = [vp, C.POINTER(BroadphaseStats)]
+    l.phyx_b200_update_manifolds.argtypes = [vp]
+    l.phyx_b200_pack_manifolds.argtypes = [vp]
+    l.phyx_b200_refresh_contact_joints.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    l.phyx_b200_solve_resident.argtypes = [vp, C.POINTER(SolveConfig), C.POINTER(SolveStats)]
+    l.phyx_b200_reset_collider.argtypes = [vp]
+    l.phyx_b200_collider_counts.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    l.phyx_b200_download_manifolds.argtypes = [vp, vp, i32]
+    l.phyx_b200_download_contact_points.argtypes = [vp, vp, i32]
+    l.phyx_b200_download_joints.argtypes = [vp, vp, i32]
+    l.phyx_b200_upload_collider.argtypes = [vp, vp, i32, vp, vp, i32]
     _LIB = l
     return l
 
@@ -236,6 +258,59 @@ class Context:
         out = np.zeros(self._staged, dtype=T.CONTACT_JOINT)
         self._check(self.l.phyx_b200_fetch_joints(self.h, _p(out), out.shape[0]))
         return out
+
+    # ---- resident collider stages ----
+    def update_pairs(self):
+        stats = BroadphaseStats()
+        self._check(self.l.phyx_b200_update_pairs(self.h, C.byref(stats)))
+        return stats
+
+    def update_manifolds(self):
+        self._check(self.l.phyx_b200_update_manifolds(self.h))
+
+    def pack_manifolds(self):
+        self._check(self.l.phyx_b200_pack_manifolds(self.h))
+
+    def refresh_contact_joints(self):
+        m, cr, d = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._check(self.l.phyx_b200_refresh_contact_joints(self.h, C.byref(m), C.byref(cr), C.byref(d)))
+        return m.value, cr.value, d.value
+
+    def solve_resident(self, iters=(20, 20), schedule=SCHEDULE_COLOUR, flags=0):
+        cfg = SolveConfig(iters[0], iters[1], schedule, flags)
+        stats = SolveStats()
+        self._check(self.l.phyx_b200_solve_resident(self.h, C.byref(cfg), C.byref(stats)))
+        return stats
+
+    def reset_collider(self):
+        self._check(self.l.phyx_b200_reset_collider(self.h))
+
+    def collider_counts(self):
+        m, p, j = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._check(self.l.phyx_b200_collider_counts(self.h, C.byref(m), C.byref(p), C.byref(j)))
+        return m.value, p.value, j.value
+
+    def download_manifolds(self):
+        out = np.zeros(self.collider_counts()[0], dtype=T.MANIFOLD)
+        self._check(self.l.phyx_b200_download_manifolds(self.h, _p(out), out.shape[0]))
+        return out
+
+    def download_contact_points(self):
+        out = np.zeros(self.collider_counts()[1], dtype=T.CONTACT_POINT)
+        self._check(self.l.phyx_b200_download_contact_points(self.h, _p(out), out.shape[0]))
+        return out
+
+    def download_joints(self):
+        out = np.zeros(self.collider_counts()[2], dtype=T.CONTACT_JOINT)
+        self._check(self.l.phyx_b200_download_joints(self.h, _p(out), out.shape[0]))
+        return out
+
+    def upload_collider(self, manifolds, contact_points, joints):
+        m = np.ascontiguousarray(manifolds, dtype=T.MANIFOLD)
+        cp = np.ascontiguousarray(contact_points, dtype=T.CONTACT_POINT)
+        j = np.ascontiguousarray(joints, dtype=T.CONTACT_JOINT)
+        assert cp.shape[0] == 2 * m.shape[0]
+        self._check(self.l.phyx_b200_upload_collider(self.h, _p(m), m.shape[0], _p(cp), _p(j), j.shape[0]))
 
     def get_schedule(self):
         ns, nl = C.c_int32(0), C.c_int32(0)

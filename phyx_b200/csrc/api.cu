@@ -38,6 +38,25 @@ int DevBuf::reserve(size_t bytes)
     return PHYX_B200_OK;
 }
 
+// grow, preserving the first keepBytes (persistent arrays: manifolds, contact points, joints)
+int DevBuf::reserve_keep(size_t bytes, size_t keepBytes, cudaStream_t stream)
+{
+    if (bytes <= cap) return PHYX_B200_OK;
+    size_t want = std::max(bytes, cap + cap / 2);
+    want = (want + 255) & ~size_t(255);
+    void* p = nullptr;
+    PHYX_CUDA(cudaMalloc(&p, want));
+    if (ptr)
+    {
+        if (keepBytes) PHYX_CUDA(cudaMemcpyAsync(p, ptr, std::min(keepBytes, cap), cudaMemcpyDeviceToDevice, stream));
+        PHYX_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(ptr);
+    }
+    ptr = p;
+    cap = want;
+    return PHYX_B200_OK;
+}
+
 void DevBuf::release()
 {
     if (ptr) cudaFree(ptr);
@@ -98,6 +117,10 @@ static int stage_joints(phyx_b200_ctx* c, const phyx_contact_joint* joints, int 
         PHYX_CUDA(cudaMemcpyAsync(c->contactPoints.ptr, cps, size_t(ncp) * sizeof(phyx_contact_point), cudaMemcpyHostToDevice, c->stream));
     c->jointCount = nj;
     c->contactPointCount = ncp;
+    // joints / contact points now come from the caller: the resident manifold cache no longer describes them
+    c->manifoldCount = 0;
+    c->pairTableSlots = 0;
+    c->hostJointsValid = false;
     return PHYX_B200_OK;
 }
 
@@ -155,7 +178,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
-        &c->colourTmp, &c->colourKeys, &c->colourSorted };
+        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp };
     for (DevBuf* b : bufs) b->release();
     c->pinned.release();
     for (auto& ev : c->ev)
@@ -264,7 +287,7 @@ int phyx_b200_download_broadphase(phyx_b200_ctx* c, phyx_broadphase_entry* entri
 int phyx_b200_sweep_pairs_resident(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
 {
     PHYX_TRY(check(c));
-    return broadphase_sweep(c, stats);
+    return broadphase_sweep(c, stats, false);
 }
 
 int phyx_b200_sweep_pairs(phyx_b200_ctx* c, phyx_pair* pairs, int64_t capacity, int64_t* count, phyx_b200_broadphase_stats* stats)
@@ -275,7 +298,7 @@ int phyx_b200_sweep_pairs(phyx_b200_ctx* c, phyx_pair* pairs, int64_t capacity, 
         set_error("sweep_pairs: bad arguments");
         return PHYX_B200_ERR_ARGUMENT;
     }
-    PHYX_TRY(broadphase_sweep(c, stats));
+    PHYX_TRY(broadphase_sweep(c, stats, false));
     *count = c->lastPairs;
     if (c->lastPairs > capacity)
     {
@@ -296,6 +319,7 @@ int phyx_b200_stage_joints(phyx_b200_ctx* c, const phyx_contact_joint* joints, i
     PHYX_TRY(check(c));
     PHYX_TRY(stage_joints(c, joints, jointCount, contactPoints, contactPointCount));
     c->hostJoints.assign(joints, joints + jointCount);
+    c->hostJointsValid = true;
     PHYX_CUDA(cudaStreamSynchronize(c->stream));
     return PHYX_B200_OK;
 }
@@ -311,6 +335,18 @@ int phyx_b200_solve_staged(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, 
     if (stats) memset(stats, 0, sizeof(*stats));
     cudaEvent_t t0 = c->ev[4], t1 = c->ev[5], t2 = c->ev[6];
     PHYX_CUDA(cudaEventRecord(t0, c->stream));
+    // host-built schedules (reference-order replay, cross-check colouring) and KEEP_SCHEDULE read the
+    // joint list on the host: fetch it if the joints were produced on the device
+    const bool hostNeedsJoints = cfg->schedule != PHYX_B200_SCHEDULE_COLOUR || (cfg->flags & (PHYX_B200_SOLVE_HOST_COLOURING | PHYX_B200_SOLVE_KEEP_SCHEDULE));
+    if (hostNeedsJoints && !c->hostJointsValid)
+    {
+        c->hostJoints.resize(size_t(c->jointCount));
+        if (c->jointCount)
+        {
+            PHYX_CUDA(cudaMemcpyAsync(c->hostJoints.data(), c->joints.ptr, size_t(c->jointCount) * sizeof(phyx_contact_joint), cudaMemcpyDeviceToHost, c->stream));
+            PHYX_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    }
     PHYX_TRY(schedule_build(c, c->hostJoints.data(), c->jointCount, cfg->schedule, cfg->flags));
     PHYX_CUDA(cudaEventRecord(t1, c->stream));
     PHYX_TRY(solve_run(c, cfg, stats));
@@ -322,6 +358,159 @@ int phyx_b200_solve_staged(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, 
         stats->ms_total = elapsed_ms(t0, t2);
     }
     return PHYX_B200_OK;
+}
+
+// ---- resident collider stages -----------------------------------------------------------------------
+
+int phyx_b200_update_pairs(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
+{
+    PHYX_TRY(check(c));
+    c->hostJointsValid = false;
+    return collide_update_pairs(c, stats);
+}
+
+int phyx_b200_update_manifolds(phyx_b200_ctx* c)
+{
+    PHYX_TRY(check(c));
+    return collide_update_manifolds(c);
+}
+
+int phyx_b200_pack_manifolds(phyx_b200_ctx* c)
+{
+    PHYX_TRY(check(c));
+    return collide_pack_manifolds(c);
+}
+
+int phyx_b200_refresh_contact_joints(phyx_b200_ctx* c, int32_t* matched, int32_t* created, int32_t* deleted)
+{
+    PHYX_TRY(check(c));
+    c->hostJointsValid = false;
+    return collide_refresh_joints(c, matched, created, deleted);
+}
+
+int phyx_b200_solve_resident(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats)
+{
+    return phyx_b200_solve_staged(c, cfg, stats);
+}
+
+int phyx_b200_reset_collider(phyx_b200_ctx* c)
+{
+    PHYX_TRY(check(c));
+    c->hostJointsValid = false;
+    return collide_reset(c);
+}
+
+int phyx_b200_collider_counts(phyx_b200_ctx* c, int32_t* manifolds, int32_t* contactPoints, int32_t* joints)
+{
+    PHYX_TRY(check(c));
+    if (manifolds) *manifolds = c->manifoldCount;
+    if (contactPoints) *contactPoints = c->contactPointCount;
+    if (joints) *joints = c->jointCount;
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_download_manifolds(phyx_b200_ctx* c, phyx_manifold* out, int capacity)
+{
+    PHYX_TRY(check(c));
+    const int M = c->manifoldCount;
+    if (capacity < M || (M > 0 && !out))
+    {
+        set_error("download_manifolds: capacity %d < %d", capacity, M);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    if (M == 0) return PHYX_B200_OK;
+    std::vector<int2> body(M);
+    std::vector<int> count(M);
+    PHYX_CUDA(cudaMemcpyAsync(body.data(), c->manBody.ptr, size_t(M) * sizeof(int2), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaMemcpyAsync(count.data(), c->manCount.ptr, size_t(M) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    for (int m = 0; m < M; ++m)
+    {
+        out[m].body1Index = body[m].x;
+        out[m].body2Index = body[m].y;
+        out[m].pointCount = count[m];
+        out[m].pointIndex = 2 * m;   // invariant of the reference's bookkeeping (Collider.cpp:315,405)
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_download_contact_points(phyx_b200_ctx* c, phyx_contact_point* out, int capacity)
+{
+    PHYX_TRY(check(c));
+    const int n = c->contactPointCount;
+    if (capacity < n || (n > 0 && !out))
+    {
+        set_error("download_contact_points: capacity %d < %d", capacity, n);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    if (n > 0)
+    {
+        PHYX_CUDA(cudaMemcpyAsync(out, c->contactPoints.ptr, size_t(n) * sizeof(phyx_contact_point), cudaMemcpyDeviceToHost, c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_download_joints(phyx_b200_ctx* c, phyx_contact_joint* out, int capacity)
+{
+    PHYX_TRY(check(c));
+    const int n = c->jointCount;
+    if (capacity < n || (n > 0 && !out))
+    {
+        set_error("download_joints: capacity %d < %d", capacity, n);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    if (n > 0)
+    {
+        PHYX_CUDA(cudaMemcpyAsync(out, c->joints.ptr, size_t(n) * sizeof(phyx_contact_joint), cudaMemcpyDeviceToHost, c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return PHYX_B200_OK;
+}
+
+// Push a complete collider state (e.g. one produced by the reference, or edited by the caller).
+int phyx_b200_upload_collider(phyx_b200_ctx* c, const phyx_manifold* manifolds, int manifoldCount, const phyx_contact_point* contactPoints,
+    const phyx_contact_joint* joints, int jointCount)
+{
+    PHYX_TRY(check(c));
+    if (manifoldCount < 0 || jointCount < 0 || (manifoldCount > 0 && (!manifolds || !contactPoints)) || (jointCount > 0 && !joints))
+    {
+        set_error("upload_collider: bad arguments");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    const int M = manifoldCount;
+    std::vector<int2> body(size_t(M > 0 ? M : 1));
+    std::vector<int> count(size_t(M > 0 ? M : 1));
+    for (int m = 0; m < M; ++m)
+    {
+        if (manifolds[m].pointIndex != 2 * m || manifolds[m].pointCount < 0 || manifolds[m].pointCount > 2)
+        {
+            set_error("upload_collider: manifold %d breaks the pointIndex = 2*index / pointCount <= 2 invariant", m);
+            return PHYX_B200_ERR_ARGUMENT;
+        }
+        body[m] = make_int2(manifolds[m].body1Index, manifolds[m].body2Index);
+        count[m] = manifolds[m].pointCount;
+    }
+    c->manifoldCount = 0;
+    c->jointCount = 0;
+    PHYX_TRY(c->manBody.reserve(body.size() * sizeof(int2)));
+    PHYX_TRY(c->manCount.reserve(count.size() * sizeof(int)));
+    PHYX_TRY(c->contactPoints.reserve(size_t(M > 0 ? M : 1) * 2 * sizeof(phyx_contact_point)));
+    PHYX_TRY(c->joints.reserve(size_t(jointCount > 0 ? jointCount : 1) * sizeof(phyx_contact_joint)));
+    if (M > 0)
+    {
+        PHYX_CUDA(cudaMemcpyAsync(c->manBody.ptr, body.data(), size_t(M) * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+        PHYX_CUDA(cudaMemcpyAsync(c->manCount.ptr, count.data(), size_t(M) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        PHYX_CUDA(cudaMemcpyAsync(c->contactPoints.ptr, contactPoints, size_t(M) * 2 * sizeof(phyx_contact_point), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (jointCount > 0)
+        PHYX_CUDA(cudaMemcpyAsync(c->joints.ptr, joints, size_t(jointCount) * sizeof(phyx_contact_joint), cudaMemcpyHostToDevice, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    c->manifoldCount = M;
+    c->contactPointCount = 2 * M;
+    c->jointCount = jointCount;
+    c->hostJointsValid = false;
+    return collide_rebuild_pair_table(c);
 }
 
 int phyx_b200_fetch_joints(phyx_b200_ctx* c, phyx_contact_joint* joints, int jointCount)

@@ -13,6 +13,7 @@
 // count -> exclusive scan -> emit over fixed-size work items, so long scans (the ground body's
 // covers every entry) are split over many warps instead of serialising one thread.
 #include "common.cuh"
+#include "pairset.cuh"
 
 namespace phyx
 {
@@ -166,15 +167,19 @@ __global__ void k_sweep_items(int n, const int* __restrict__ itemStart, const in
     for (int k = 0; k < cnt; ++k) items[s + k] = make_int2(i, k);
 }
 
-template <bool EMIT>
+// One warp per work item.  FILTER: a hit only counts / is emitted if its (index_i, index_j) key is
+// not in the manifold cache (Collider.cpp:358-362: contains() before push); the unfiltered hit
+// total is still accumulated for the statistics.
+template <bool EMIT, bool FILTER>
 __global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numItemsPtr, const int2* __restrict__ items,
     const int* __restrict__ end, const float2* __restrict__ entryY, const unsigned* __restrict__ entryIndex, int* __restrict__ itemCount,
-    const int* __restrict__ itemOffset, int2* __restrict__ pairs, unsigned long long* __restrict__ tests)
+    const int* __restrict__ itemOffset, int2* __restrict__ pairs, unsigned long long* __restrict__ totals,
+    const unsigned long long* __restrict__ table, size_t tableMask)
 {
     const int lane = threadIdx.x & 31;
     const int warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
     const int numItems = *numItemsPtr;
-    unsigned long long localTests = 0;
+    unsigned long long localTests = 0, localHits = 0;
     for (int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < numItems; it += warpsPerGrid)
     {
         int2 item = items[it];
@@ -182,22 +187,34 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numIte
         int j0 = i + 1 + item.y * kChunk;
         int j1 = min(j0 + kChunk, end[i]);
         float2 yi = entryY[i];
-        unsigned bi = EMIT ? entryIndex[i] : 0u;
+        unsigned bi = (EMIT || FILTER) ? entryIndex[i] : 0u;
         int out = EMIT ? itemOffset[it] : 0;
         int count = 0;
         for (int jb = j0; jb < j1; jb += 32)
         {
             int j = jb + lane;
             bool hit = false;
+            unsigned bj = 0;
             if (j < j1)
             {
                 float2 yj = entryY[j];
                 hit = fabsf(yj.x - yi.x) <= yi.y + yj.y;   // Collider.cpp:309
             }
+            if (FILTER)
+            {
+                if (!EMIT) localHits += __popc(__ballot_sync(0xffffffffu, hit));
+                if (hit)
+                {
+                    bj = entryIndex[j];
+                    hit = !pair_contains(table, tableMask, pair_key(bi, bj));
+                }
+            }
+            else if (EMIT && hit)
+                bj = entryIndex[j];
             unsigned m = __ballot_sync(0xffffffffu, hit);
             if (EMIT)
             {
-                if (hit) pairs[out + __popc(m & ((1u << lane) - 1u))] = make_int2(int(bi), int(entryIndex[j]));
+                if (hit) pairs[out + __popc(m & ((1u << lane) - 1u))] = make_int2(int(bi), int(bj));
                 out += __popc(m);
             }
             else
@@ -209,7 +226,11 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numIte
             localTests += (unsigned long long)(j1 - j0);
         }
     }
-    if (!EMIT && lane == 0 && localTests) atomicAdd(tests, localTests);
+    if (!EMIT && lane == 0)
+    {
+        if (localTests) atomicAdd(&totals[0], localTests);
+        if (FILTER && localHits) atomicAdd(&totals[1], localHits);
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -255,7 +276,10 @@ int broadphase_update(phyx_b200_ctx* c)
 
 // Runs count + scan (+ emit into c->pairs).  Leaves the pair list on the device; c->lastPairs /
 // c->lastTests hold the totals.
-int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
+// filter = false: every overlapping pair (lastPairs of them) ends up in c->pairs.
+// filter = true : only pairs whose key is not in c->pairTable are emitted (lastNewPairs of them);
+//                 lastPairs still counts every overlapping pair.
+int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats, bool filter)
 {
     if (!c->broadphaseValid)
     {
@@ -263,8 +287,10 @@ int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
         return PHYX_B200_ERR_STATE;
     }
     int n = c->bodyCount;
-    c->lastPairs = c->lastTests = 0;
+    c->lastPairs = c->lastTests = c->lastNewPairs = 0;
+    if (stats) stats->pairs = stats->tests = 0;
     if (n < 2) return PHYX_B200_OK;
+    if (filter && c->pairTableSlots == 0) PHYX_TRY(collide_rebuild_pair_table(c));
     size_t n1 = size_t(n);
     float2* entryX = c->entry.as<float2>();
     float2* entryY = entryX + n1;
@@ -273,7 +299,7 @@ int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
     PHYX_TRY(c->counters.reserve(64));
     int* d_numItems = c->counters.as<int>();
     int* d_numPairs = d_numItems + 1;
-    unsigned long long* d_tests = reinterpret_cast<unsigned long long*>(c->counters.as<char>() + 16);
+    unsigned long long* d_totals = reinterpret_cast<unsigned long long*>(c->counters.as<char>() + 16);   // tests, unfiltered hits
     PHYX_CUDA(cudaMemsetAsync(c->counters.ptr, 0, 64, c->stream));
 
     int grid = (n + kBlock - 1) / kBlock;
@@ -290,22 +316,33 @@ int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
     k_sweep_items<<<grid, kBlock, 0, c->stream>>>(n, c->itemStart.as<int>(), c->sweepEnd.as<int>(), c->items.as<int2>());
     c->launches++;
 
+    const unsigned long long* table = c->pairTable.as<unsigned long long>();
+    const size_t mask = c->pairTableSlots ? c->pairTableSlots - 1 : 0;
     int warpsPerBlock = kBlock / 32;
     int sweepGrid = min((numItems + warpsPerBlock - 1) / warpsPerBlock, c->numSMs * 8);
-    k_sweep<false><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
-        c->entryIndex.as<unsigned>(), c->itemCount.as<int>(), nullptr, nullptr, d_tests);
+    if (filter)
+        k_sweep<false, true><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
+            c->entryIndex.as<unsigned>(), c->itemCount.as<int>(), nullptr, nullptr, d_totals, table, mask);
+    else
+        k_sweep<false, false><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
+            c->entryIndex.as<unsigned>(), c->itemCount.as<int>(), nullptr, nullptr, d_totals, nullptr, 0);
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, c->itemCount.as<int>(), c->itemCount.as<int>(), numItems, d_numPairs));
-    struct { int items, pairs; long long pad; unsigned long long tests; } host;
+    struct { int items, pairs; long long pad; unsigned long long tests, hits; } host;
     PHYX_CUDA(cudaMemcpyAsync(&host, c->counters.ptr, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
     PHYX_CUDA(cudaStreamSynchronize(c->stream));
-    c->lastPairs = host.pairs;
     c->lastTests = (long long)host.tests;
+    c->lastPairs = filter ? (long long)host.hits : host.pairs;
+    c->lastNewPairs = filter ? host.pairs : 0;
     if (host.pairs > 0)
     {
         PHYX_TRY(c->pairs.reserve(size_t(host.pairs) * sizeof(int2)));
-        k_sweep<true><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
-            c->entryIndex.as<unsigned>(), nullptr, c->itemCount.as<int>(), c->pairs.as<int2>(), nullptr);
+        if (filter)
+            k_sweep<true, true><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
+                c->entryIndex.as<unsigned>(), nullptr, c->itemCount.as<int>(), c->pairs.as<int2>(), nullptr, table, mask);
+        else
+            k_sweep<true, false><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
+                c->entryIndex.as<unsigned>(), nullptr, c->itemCount.as<int>(), c->pairs.as<int2>(), nullptr, nullptr, 0);
         c->launches++;
     }
     PHYX_CUDA(cudaGetLastError());

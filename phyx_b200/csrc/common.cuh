@@ -43,6 +43,7 @@ struct DevBuf
 
     template <typename T> T* as() const { return static_cast<T*>(ptr); }
     int reserve(size_t bytes);
+    int reserve_keep(size_t bytes, size_t keepBytes, cudaStream_t stream);
     void release();
 };
 
@@ -110,6 +111,15 @@ struct phyx_b200_ctx
     bool broadphaseValid = false;
     int64_t lastPairs = 0, lastTests = 0;
 
+    // ---- collider state (persistent across steps) ---------------------------------------------
+    int manifoldCount = 0;
+    phyx::DevBuf manBody;        // int2 {body1, body2} per manifold (sweep order at creation: NOT canonical)
+    phyx::DevBuf manCount;       // int pointCount per manifold; pointIndex is always 2*m
+    phyx::DevBuf pairTable;      // open-addressing set of (body1<<32 | body2) keys of the live manifolds
+    size_t pairTableSlots = 0;
+    phyx::DevBuf collideTmp;     // flags / prefix sums / mover tables
+    int64_t lastNewPairs = 0;
+
     // ---- solve ----------------------------------------------------------------------------
     int jointCount = 0, contactPointCount = 0;
     phyx::DevBuf joints;         // phyx_contact_joint AoS (device copy)
@@ -133,7 +143,8 @@ struct phyx_b200_ctx
     std::vector<phyx::Level> hostLevels;
     std::vector<int> hostPairKey; // (b1,b2) list the schedule was built for
     int scheduleMode = -1, scheduleFlags = 0;
-    std::vector<phyx_contact_joint> hostJoints; // host copy of staged joints (replay schedule needs it)
+    std::vector<phyx_contact_joint> hostJoints; // host copy of the resident joints (host-built schedules need it)
+    bool hostJointsValid = false;
 
     phyx::HostBuf pinned;        // pinned staging for H2D/D2H
     cudaEvent_t ev[8] = {};
@@ -151,7 +162,7 @@ int bodies_snapshot(phyx_b200_ctx* c, bool restore);
 
 // broadphase.cu
 int broadphase_update(phyx_b200_ctx* c);
-int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats);
+int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats, bool filter);
 // one stable LSD pass over {key, value} pairs on `digits` (power of two <= 2048) bins of key >> shift
 int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift, int digits);
 
@@ -163,6 +174,14 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
 
 // solve.cu
 int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats);
+
+// collide.cu
+int collide_update_pairs(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats);
+int collide_update_manifolds(phyx_b200_ctx* c);
+int collide_pack_manifolds(phyx_b200_ctx* c);
+int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* deleted);
+int collide_reset(phyx_b200_ctx* c);
+int collide_rebuild_pair_table(phyx_b200_ctx* c);
 
 // scan.cu
 int exclusive_scan_i32(phyx_b200_ctx* c, const int* in, int* out, int n, int* totalDevice /* may be null */);

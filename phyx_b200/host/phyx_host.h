@@ -5,10 +5,9 @@
 // A program written against the reference's headers (reference src/main.cpp is the model:
 // world.AddBody(...), world.gravity, world.Update(queue, dt, config), world.bodies[i].coords,
 // world.collider.manifolds, world.solver.contactJoints ...) compiles against these headers
-// unchanged and gets the three hot loops — integration, sweep & prune broadphase, contact solve —
-// executed by the sm_100a kernels.  The stages that are not on the hot path yet (narrowphase,
-// manifold and joint caches) run here on the host, written to perform the
-// reference's float operations in the reference's order so whole-step results stay bit-comparable.
+// unchanged and gets every stage of the step — integration, sweep & prune broadphase, narrowphase,
+// manifold and joint caches, contact solve — executed by the sm_100a kernels.  Nothing is computed
+// on the host: the classes below only keep the caller-visible arrays in step with the device.
 //
 // Records keep the reference's exact memory layout (static_asserts below): they are handed to the
 // C ABI as they are.
@@ -324,6 +323,9 @@ struct Configuration
 
 // ---- device binding shared by World, Collider and Solver --------------------------------------------
 
+struct Collider;
+struct Solver;
+
 namespace phyx_host
 {
 struct Device
@@ -334,12 +336,16 @@ struct Device
     bool inUpdate = false;     // World::Update is driving: stage functions skip their own sync
     int residentCount = 0;
     double stageMs[8] = {};    // wall time per stage (reference scope taxonomy)
+    double syncMs = 0;         // wall time of the end-of-Update download + mirrors
+    int mirroredManifolds = 0, mirroredJoints = 0;   // sizes last written into the host mirrors
     phyx_b200_solve_stats lastSolve = {};
     phyx_b200_broadphase_stats lastBroadphase = {};
 
     void ensure();                                   // create the context (aborts with a message on failure)
     void upload(RigidBody* bodies, int count);       // AoS -> HBM
     void download(RigidBody* bodies, int count);     // HBM -> AoS
+    void mirror(Collider& collider, Solver& solver, bool contents);   // device caches -> host arrays
+    void followReset(Collider& collider, Solver& solver);             // host arrays cleared -> clear device caches
     ~Device();
 };
 [[noreturn]] void fail(const char* what, int status);
@@ -368,8 +374,8 @@ struct Collider
         unsigned int index;
     };
 
-    // pair cache: same observable behaviour as the reference's DenseHashSet of (body1, body2) keys
-    // in sweep order (NOT canonical: SURVEY App. B3), without its tombstone bug (App. B2)
+    // The pair cache itself lives on the device (pairset.cuh).  This member only exists because
+    // callers clear it when they reset the world (reference src/main.cpp:88).
     struct PairSet
     {
         std::unordered_set<uint64_t> keys;
@@ -388,8 +394,10 @@ struct Collider
     AlignedArray<BroadphaseSortEntry> broadphaseSort[2];
 
     phyx_host::Device* device = nullptr;
+    Solver* solver = nullptr;
     bool mirrorBroadphase = false;   // also copy the sorted entries back into `broadphase` every step
-    std::vector<phyx_pair> pairBuffer;
+    bool mirrorContents = true;      // refresh manifolds / contactPoints / contactJoints contents after every step
+                                     // (sizes are always current); switch off when nothing on the host reads them
 };
 
 // ---- Solver (reference src/Solver.h) -------------------------------------------------------------------
@@ -405,8 +413,8 @@ struct Solver
     AlignedArray<ContactJoint> contactJoints;
 
     phyx_host::Device* device = nullptr;
-    int contactPointCount = 0;       // set by World before SolveJoints (the reference passes a bare pointer)
-    int solveFlags = 0;              // PHYX_B200_SOLVE_* (e.g. STATIC_DEPS for exact replay)
+    Collider* collider = nullptr;
+    int solveFlags = 0;              // PHYX_B200_SOLVE_*
 };
 
 // ---- World (reference src/World.h) ---------------------------------------------------------------------
@@ -435,5 +443,6 @@ struct World
     float gravity;
 
     // --- additions (not in the reference) ---
-    phyx_host::Device device;        // the HBM-resident copy of `bodies`; select the GPU with device.deviceIndex before the first Update
+    phyx_host::Device device;        // the HBM-resident state; select the GPU with device.deviceIndex before the first Update
+    int matchedJoints = 0, createdJoints = 0, deletedJoints = 0;   // the reference's Matched/Created/Deleted counters (World.cpp:146-148)
 };

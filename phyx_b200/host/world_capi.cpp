@@ -30,6 +30,17 @@ API void* phyxw_create(int device) { return new Handle(device, 0); }
 API void phyxw_destroy(void* h) { delete static_cast<Handle*>(h); }
 API void phyxw_set_gravity(void* h, float g) { static_cast<Handle*>(h)->world.gravity = g; }
 API void phyxw_set_solve_flags(void* h, int flags) { static_cast<Handle*>(h)->world.solver.solveFlags = flags; }
+API void phyxw_set_mirror_contents(void* h, int on) { static_cast<Handle*>(h)->world.collider.mirrorContents = on != 0; }
+API double phyxw_get_sync_ms(void* h) { return static_cast<Handle*>(h)->world.device.syncMs; }
+API void phyxw_reset_world(void* h)
+{
+    // what the demo's resetWorld does (reference src/main.cpp:86-89)
+    World& w = static_cast<Handle*>(h)->world;
+    w.bodies.clear();
+    w.collider.manifolds.clear();
+    w.collider.manifoldMap.clear();
+    w.solver.contactJoints.clear();
+}
 
 API int phyxw_add_body(void* h, float x, float y, float angle, float sx, float sy, int is_static)
 {
@@ -67,11 +78,7 @@ API void phyxw_step_staged(void* h, float dt, int solveMode, int islandMode, int
     if (mask & 8) w.collider.UpdateManifolds(s->queue, w.bodies.data);
     if (mask & 16) w.collider.PackManifolds(w.bodies.data);
     if (mask & 32) w.RefreshContactJoints();
-    if (mask & 64)
-    {
-        w.solver.contactPointCount = w.collider.contactPoints.size;
-        w.solver.SolveJoints(s->queue, w.bodies.data, w.bodies.size, w.collider.contactPoints.data, c);
-    }
+    if (mask & 64) w.solver.SolveJoints(s->queue, w.bodies.data, w.bodies.size, w.collider.contactPoints.data, c);
     if (mask & 128) w.IntegratePosition(s->queue, dt);
 }
 
@@ -113,7 +120,11 @@ API void phyxw_get_broadphase(void* h, void* out)
     memcpy(out, c.broadphase.data, size_t(c.broadphase.size) * sizeof(Collider::BroadphaseEntry));
 }
 API void phyxw_get_stage_ms(void* h, double* out8) { memcpy(out8, static_cast<Handle*>(h)->world.device.stageMs, sizeof(double) * 8); }
-API void phyxw_reset_stage_ms(void* h) { memset(static_cast<Handle*>(h)->world.device.stageMs, 0, sizeof(double) * 8); }
+API void phyxw_reset_stage_ms(void* h)
+{
+    memset(static_cast<Handle*>(h)->world.device.stageMs, 0, sizeof(double) * 8);
+    static_cast<Handle*>(h)->world.device.syncMs = 0;
+}
 API void phyxw_get_solve_stats(void* h, phyx_b200_solve_stats* out) { *out = static_cast<Handle*>(h)->world.device.lastSolve; }
 API void phyxw_get_broadphase_stats(void* h, phyx_b200_broadphase_stats* out) { *out = static_cast<Handle*>(h)->world.device.lastBroadphase; }
 API void* phyxw_context(void* h)

@@ -47,6 +47,10 @@ def load():
         getattr(l, f"phyxw_get_{n}").argtypes = [vp, vp]
     l.phyxw_set_bodies.argtypes = [vp, vp, i32]
     l.phyxw_reset_stage_ms.argtypes = [vp]
+    l.phyxw_set_mirror_contents.argtypes = [vp, i32]
+    l.phyxw_get_sync_ms.argtypes = [vp]
+    l.phyxw_get_sync_ms.restype = C.c_double
+    l.phyxw_reset_world.argtypes = [vp]
     l.phyxw_context.argtypes = [vp]
     l.phyxw_context.restype = vp
     _LIB = l
@@ -58,11 +62,12 @@ def _p(a):
 
 
 class World:
-    def __init__(self, scene=None, device=0, gravity=-200.0, solve_flags=0):
+    def __init__(self, scene=None, device=0, gravity=-200.0, solve_flags=0, mirror_contents=True):
         self.l = load()
         self.h = self.l.phyxw_create(device)
         self.l.phyxw_set_gravity(self.h, gravity)
         self.l.phyxw_set_solve_flags(self.h, solve_flags)
+        self.l.phyxw_set_mirror_contents(self.h, int(mirror_contents))
         if scene is not None:
             self.add_scene(scene)
 
@@ -116,7 +121,20 @@ class World:
     def stage_ms(self):
         out = np.zeros(8, dtype=np.float64)
         self.l.phyxw_get_stage_ms(self.h, _p(out))
-        return dict(zip(STAGES, out.tolist()))
+        d = dict(zip(STAGES, out.tolist()))
+        d["sync"] = float(self.l.phyxw_get_sync_ms(self.h))
+        return d
+
+    def reset_world(self):
+        self.l.phyxw_reset_world(self.h)
+
+    def context(self):
+        """A capi.Context view of this world's device context (not owned)."""
+        ctx = capi.Context.__new__(capi.Context)
+        ctx.l = capi.load()
+        ctx.h = C.c_void_p(self.l.phyxw_context(self.h))
+        ctx.close = lambda: None  # borrowed: the World owns the context
+        return ctx
 
     def reset_stage_ms(self):
         self.l.phyxw_reset_stage_ms(self.h)

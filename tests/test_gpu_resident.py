@@ -1,0 +1,120 @@
+"""The resident collider stages (UpdatePairs, UpdateManifolds, PackManifolds, RefreshContactJoints on
+the device) against the reference, stage by stage: the reference's state before a stage is pushed
+to the device, the stage runs there, and the arrays read back must be bit-identical to what the
+reference's own stage function leaves behind (order included)."""
+import numpy as np
+import pytest
+
+from conftest import assert_records_equal
+from phyx_b200 import capi, scenes, types as T, world
+
+pytestmark = pytest.mark.gpu
+
+CP_FIELDS = ("delta1", "delta2", "normal", "isMerged", "isNewlyCreated", "solverIndex")
+
+
+def live_points(manifolds, cps):
+    idx = np.concatenate([np.arange(2 * m, 2 * m + c) for m, c in enumerate(manifolds["pointCount"])]) if manifolds.shape[0] else np.zeros(0, dtype=int)
+    return cps[idx.astype(int)]
+
+
+def compare_collider(ctx, r, what):
+    m = ctx.download_manifolds()
+    assert_records_equal(m, r.manifolds(), what=f"{what}: manifolds")
+    assert_records_equal(live_points(m, ctx.download_contact_points()), live_points(r.manifolds(), r.contact_points()), CP_FIELDS, what=f"{what}: contact points")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("scene,steps", [("pyramid_10", (0, 1, 2, 7, 30)), ("pyramid_1k", (0, 1, 3, 25)), ("stack_1k", (0, 2, 40, 41)), ("islands_8x10", (0, 5))])
+def test_each_resident_stage_matches_reference(ctx, ref, scene, steps):
+    r = ref.RefWorld(scenes.make(scene), "strict")
+    for step in range(max(steps) + 1):
+        if step not in steps:
+            r.step()
+            continue
+        # state before the step -> device
+        ctx.upload_bodies(r.bodies())
+        ctx.upload_collider(r.manifolds(), r.contact_points() if len(r.contact_points()) == 2 * len(r.manifolds()) else np.zeros(2 * len(r.manifolds()), dtype=T.CONTACT_POINT), r.joints())
+        r.step_staged(mask=0x01)
+        ctx.integrate_velocity(scenes.DT, scenes.GRAVITY)
+        r.step_staged(mask=0x02)
+        ctx.update_broadphase()
+        r.step_staged(mask=0x04 | ref.SAFE_PAIRS)
+        bp = ctx.update_pairs()
+        m = ctx.download_manifolds()
+        assert_records_equal(m, r.manifolds(), what=f"step {step} UpdatePairs")
+        tests, pairs = r.count_sweep()
+        assert (bp.tests, bp.pairs) == (tests, pairs)
+        r.step_staged(mask=0x08)
+        ctx.update_manifolds()
+        compare_collider(ctx, r, f"step {step} UpdateManifolds")
+        r.step_staged(mask=0x10)
+        ctx.pack_manifolds()
+        compare_collider(ctx, r, f"step {step} PackManifolds")
+        r.step_staged(mask=0x20)
+        ctx.refresh_contact_joints()
+        compare_collider(ctx, r, f"step {step} RefreshContactJoints")
+        assert_records_equal(ctx.download_joints(), r.joints(), what=f"step {step} joints after refresh")
+        r.step_staged(mask=0x40)
+        ctx.solve_resident(schedule=capi.SCHEDULE_REPLAY_AVX2)
+        assert_records_equal(ctx.download_joints(), r.joints(), what=f"step {step} joints after solve")
+        r.step_staged(mask=0x80)
+        ctx.integrate_position(scenes.DT)
+        assert_records_equal(ctx.download_bodies(), r.bodies(), ("pos", "xVector", "yVector", "velocity", "angularVelocity", "aabb_min", "aabb_max"), what=f"step {step} bodies")
+
+
+def test_resident_stepping_without_host_round_trips(ref):
+    """100 steps driven only by the resident stage calls (nothing uploaded after step 0) end in the
+    reference's state, bit for bit."""
+    sc = scenes.make("pyramid_1k")
+    r = ref.RefWorld(sc, "strict")
+    w = world.World(sc)
+    w.step_staged(mask=0)  # no-op; creates nothing yet
+    ctx = w.context()
+    ctx.upload_bodies(w.bodies())
+    for _ in range(100):
+        r.step()
+        ctx.integrate_velocity(scenes.DT, scenes.GRAVITY)
+        ctx.update_broadphase()
+        ctx.update_pairs()
+        ctx.update_manifolds()
+        ctx.pack_manifolds()
+        ctx.refresh_contact_joints()
+        ctx.solve_resident(schedule=capi.SCHEDULE_REPLAY_AVX2)
+        ctx.integrate_position(scenes.DT)
+    assert_records_equal(ctx.download_bodies(), r.bodies(), ("pos", "xVector", "yVector", "velocity", "angularVelocity"), what="bodies")
+    assert_records_equal(ctx.download_joints(), r.joints(), what="joints")
+    assert_records_equal(ctx.download_manifolds(), r.manifolds(), what="manifolds")
+
+
+def test_reset_world_clears_device_caches(ref):
+    sc = scenes.make("pyramid_10")
+    w = world.World(sc)
+    for _ in range(5):
+        w.step()
+    assert len(w.joints()) > 0
+    w.reset_world()
+    w.add_scene(sc)
+    r = ref.RefWorld(sc, "strict")
+    for _ in range(5):
+        w.step()
+        r.step()
+    assert_records_equal(w.joints(), r.joints(), what="joints after reset")
+    assert_records_equal(w.bodies(), r.bodies(), ("pos", "velocity"), what="bodies after reset")
+
+
+def test_mirrors_can_be_switched_off(ref):
+    sc = scenes.make("pyramid_10")
+    w = world.World(sc, mirror_contents=False)
+    r = ref.RefWorld(sc, "strict")
+    for _ in range(10):
+        w.step()
+        r.step()
+    assert len(w.joints()) == len(r.joints()) and len(w.manifolds()) == len(r.manifolds())   # sizes stay current
+    assert_records_equal(w.bodies(), r.bodies(), ("pos", "velocity"), what="bodies")
