@@ -17,6 +17,7 @@
 #ifndef PHYX_B200_H
 #define PHYX_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -142,6 +143,10 @@ PHYX_B200_API int phyx_b200_synchronize(phyx_b200_ctx* ctx);
 PHYX_B200_API int phyx_b200_upload_bodies(phyx_b200_ctx* ctx, const phyx_rigid_body* bodies, int count);
 PHYX_B200_API int phyx_b200_download_bodies(phyx_b200_ctx* ctx, phyx_rigid_body* bodies, int count);
 PHYX_B200_API int phyx_b200_body_count(const phyx_b200_ctx* ctx);
+/* page-lock / release a caller buffer in place (e.g. World::bodies.data) so the copies above run at
+ * full PCIe rate; optional */
+PHYX_B200_API int phyx_b200_host_register(phyx_b200_ctx* ctx, void* ptr, size_t bytes);
+PHYX_B200_API int phyx_b200_host_unregister(phyx_b200_ctx* ctx, void* ptr);
 
 /* ---- World::IntegrateVelocity / IntegratePosition, reference src/World.cpp:39-70 -------------- */
 PHYX_B200_API int phyx_b200_integrate_velocity(phyx_b200_ctx* ctx, float dt, float gravity);

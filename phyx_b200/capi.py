@@ -31,6 +31,8 @@ EXPORTS = (
     "phyx_b200_upload_bodies",
     "phyx_b200_download_bodies",
     "phyx_b200_body_count",
+    "phyx_b200_host_register",
+    "phyx_b200_host_unregister",
     "phyx_b200_integrate_velocity",
     "phyx_b200_integrate_position",
     "phyx_b200_update_broadphase",
@@ -124,6 +126,8 @@ def load():
     l.phyx_b200_upload_bodies.argtypes = [vp, vp, i32]
     l.phyx_b200_download_bodies.argtypes = [vp, vp, i32]
     l.phyx_b200_body_count.argtypes = [vp]
+    l.phyx_b200_host_register.argtypes = [vp, vp, C.c_size_t]
+    l.phyx_b200_host_unregister.argtypes = [vp, vp]
     l.phyx_b200_integrate_velocity.argtypes = [vp, f32, f32]
     l.phyx_b200_integrate_position.argtypes = [vp, f32]
     l.phyx_b200_update_broadphase.argtypes = [vp]

@@ -199,6 +199,36 @@ int phyx_b200_synchronize(phyx_b200_ctx* c)
 
 int phyx_b200_body_count(const phyx_b200_ctx* c) { return c ? c->bodyCount : 0; }
 
+// Page-lock a caller buffer in place (cudaHostRegister) so uploads / downloads of World::bodies run at
+// full PCIe rate without a staging copy.  Returns OK also when the range is already registered.
+int phyx_b200_host_register(phyx_b200_ctx* c, void* ptr, size_t bytes)
+{
+    PHYX_TRY(check(c));
+    if (!ptr || bytes == 0) return PHYX_B200_OK;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered)
+    {
+        cudaGetLastError();
+        return PHYX_B200_OK;
+    }
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        set_error("host_register(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return PHYX_B200_ERR_CUDA;
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_host_unregister(phyx_b200_ctx* c, void* ptr)
+{
+    PHYX_TRY(check(c));
+    if (!ptr) return PHYX_B200_OK;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) cudaGetLastError();   // not registered: nothing to undo
+    return PHYX_B200_OK;
+}
+
 int phyx_b200_upload_bodies(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int count)
 {
     PHYX_TRY(check(c));

@@ -72,6 +72,18 @@ void Device::ensure()
 void Device::upload(RigidBody* bodies, int count)
 {
     ensure();
+    // keep World::bodies page-locked (it is copied both ways every Update); re-pin when it was reallocated
+    if (pinBodies && (bodies != pinnedPtr || size_t(count) * sizeof(RigidBody) > pinnedBytes))
+    {
+        if (pinnedPtr) phyx_b200_host_unregister(ctx, pinnedPtr);
+        pinnedPtr = nullptr;
+        pinnedBytes = 0;
+        if (count > 0 && phyx_b200_host_register(ctx, bodies, size_t(count) * sizeof(RigidBody)) == 0)
+        {
+            pinnedPtr = bodies;
+            pinnedBytes = size_t(count) * sizeof(RigidBody);
+        }
+    }
     PHYX_CALL(phyx_b200_upload_bodies(ctx, reinterpret_cast<const phyx_rigid_body*>(bodies), count));
     resident = true;
     residentCount = count;
@@ -84,6 +96,7 @@ void Device::download(RigidBody* bodies, int count)
 
 Device::~Device()
 {
+    if (ctx && pinnedPtr) phyx_b200_host_unregister(ctx, pinnedPtr);
     if (ctx) phyx_b200_destroy(ctx);
 }
 

@@ -337,6 +337,9 @@ struct Device
     int residentCount = 0;
     double stageMs[8] = {};    // wall time per stage (reference scope taxonomy)
     double syncMs = 0;         // wall time of the end-of-Update download + mirrors
+    bool pinBodies = true;     // page-lock World::bodies in place for full-rate PCIe copies
+    void* pinnedPtr = nullptr;
+    size_t pinnedBytes = 0;
     int mirroredManifolds = 0, mirroredJoints = 0;   // sizes last written into the host mirrors
     phyx_b200_solve_stats lastSolve = {};
     phyx_b200_broadphase_stats lastBroadphase = {};
