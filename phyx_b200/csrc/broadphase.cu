@@ -174,7 +174,7 @@ template <bool EMIT, bool FILTER>
 __global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numItemsPtr, const int2* __restrict__ items,
     const int* __restrict__ end, const float2* __restrict__ entryY, const unsigned* __restrict__ entryIndex, int* __restrict__ itemCount,
     const int* __restrict__ itemOffset, int2* __restrict__ pairs, unsigned long long* __restrict__ totals,
-    const unsigned long long* __restrict__ table, size_t tableMask)
+    const unsigned long long* __restrict__ table, size_t tableMask, const int* __restrict__ totalOutPtr)
 {
     const int lane = threadIdx.x & 31;
     const int warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
@@ -182,6 +182,13 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numIte
     unsigned long long localTests = 0, localHits = 0;
     for (int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < numItems; it += warpsPerGrid)
     {
+        if (EMIT)
+        {
+            // the count pass already knows which items produce output: skip the rest (with the cache
+            // filter almost every item of a settled scene is empty)
+            const int next = (it + 1 < numItems) ? itemOffset[it + 1] : *totalOutPtr;
+            if (next == itemOffset[it]) continue;
+        }
         int2 item = items[it];
         int i = item.x;
         int j0 = i + 1 + item.y * kChunk;
@@ -322,10 +329,10 @@ int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats, bool f
     int sweepGrid = min((numItems + warpsPerBlock - 1) / warpsPerBlock, c->numSMs * 8);
     if (filter)
         k_sweep<false, true><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
-            c->entryIndex.as<unsigned>(), c->itemCount.as<int>(), nullptr, nullptr, d_totals, table, mask);
+            c->entryIndex.as<unsigned>(), c->itemCount.as<int>(), nullptr, nullptr, d_totals, table, mask, nullptr);
     else
         k_sweep<false, false><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
-            c->entryIndex.as<unsigned>(), c->itemCount.as<int>(), nullptr, nullptr, d_totals, nullptr, 0);
+            c->entryIndex.as<unsigned>(), c->itemCount.as<int>(), nullptr, nullptr, d_totals, nullptr, 0, nullptr);
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, c->itemCount.as<int>(), c->itemCount.as<int>(), numItems, d_numPairs));
     struct { int items, pairs; long long pad; unsigned long long tests, hits; } host;
@@ -339,10 +346,10 @@ int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats, bool f
         PHYX_TRY(c->pairs.reserve(size_t(host.pairs) * sizeof(int2)));
         if (filter)
             k_sweep<true, true><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
-                c->entryIndex.as<unsigned>(), nullptr, c->itemCount.as<int>(), c->pairs.as<int2>(), nullptr, table, mask);
+                c->entryIndex.as<unsigned>(), nullptr, c->itemCount.as<int>(), c->pairs.as<int2>(), nullptr, table, mask, d_numPairs);
         else
             k_sweep<true, false><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
-                c->entryIndex.as<unsigned>(), nullptr, c->itemCount.as<int>(), c->pairs.as<int2>(), nullptr, nullptr, 0);
+                c->entryIndex.as<unsigned>(), nullptr, c->itemCount.as<int>(), c->pairs.as<int2>(), nullptr, nullptr, 0, d_numPairs);
         c->launches++;
     }
     PHYX_CUDA(cudaGetLastError());

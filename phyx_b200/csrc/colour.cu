@@ -66,62 +66,92 @@ struct ColourParams
     int* colour;
     unsigned long long* claim;   // per body: smallest (priority, joint) among its uncoloured joints
     unsigned long long* used;    // per body: colours taken
+    int* list[2];                // worklists of still uncoloured joints (ping-pong); round 0 walks all joints
+    int* listCount;              // ring of 4 counters: listCount[r & 3] = length of the list round r reads
     unsigned long long* barrier;
     int* result;                 // [0] rounds, [1] overflow (a joint needed a colour >= 64)
 };
+
+__device__ __forceinline__ unsigned long long colour_key(int j) { return (static_cast<unsigned long long>(mix32(unsigned(j))) << 32) | unsigned(j); }
 
 __global__ void __launch_bounds__(kBlock) k_colour_rounds(ColourParams P)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
     unsigned epoch = 0;
     int rounds = 0;
     bool overflow = false;
     for (;;)
     {
+        const int n = rounds == 0 ? P.nj : __ldcg(&P.listCount[rounds & 3]);
+        const int* cur = P.list[rounds & 1];
+        int* next = P.list[(rounds + 1) & 1];
+        int* nextCount = &P.listCount[(rounds + 1) & 3];
+        if (tid == 0) *nextCount = 0;   // last read three rounds ago
         // claim: every uncoloured joint bids on its dynamic bodies
-        for (int j = tid; j < P.nj; j += nthreads)
+        for (int i = tid; i < n; i += nthreads)
         {
-            if (__ldcg(&P.colour[j]) >= 0) continue;
+            const int j = rounds == 0 ? i : cur[i];
+            if (rounds == 0 && __ldcg(&P.colour[j]) >= 0) continue;
             const int2 b = P.jb[j];
-            const unsigned long long key = (static_cast<unsigned long long>(mix32(unsigned(j))) << 32) | unsigned(j);
+            const unsigned long long key = colour_key(j);
             if (b.x >= 0) atomicMin(&P.claim[b.x], key);
             if (b.y >= 0) atomicMin(&P.claim[b.y], key);
         }
         grid_barrier(P.barrier, epoch, false, false);
-        // commit: winners of both bids take the first colour free on both bodies
+        // commit: winners of both bids take the first colour free on both bodies; the rest queue up
         bool left = false;
-        for (int j = tid; j < P.nj; j += nthreads)
+        for (int i0 = tid & ~31; i0 < n; i0 += nthreads)   // warp-uniform trip count
         {
-            if (__ldcg(&P.colour[j]) >= 0) continue;
-            const int2 b = P.jb[j];
-            const unsigned long long key = (static_cast<unsigned long long>(mix32(unsigned(j))) << 32) | unsigned(j);
-            const bool win1 = b.x < 0 || __ldcg(&P.claim[b.x]) == key;
-            const bool win2 = b.y < 0 || __ldcg(&P.claim[b.y]) == key;
-            if (win1 && win2)
+            const int i = i0 + lane;
+            bool lose = false;
+            int j = -1;
+            if (i < n)
             {
-                unsigned long long m = (b.x >= 0 ? __ldcg(&P.used[b.x]) : 0ull) | (b.y >= 0 ? __ldcg(&P.used[b.y]) : 0ull);
-                int c = __ffsll(~m) - 1;
-                if (c < 0)
+                j = rounds == 0 ? i : cur[i];
+                if (!(rounds == 0 && __ldcg(&P.colour[j]) >= 0))
                 {
-                    c = kMaxColours - 1;   // keep going so the kernel terminates; the host falls back
-                    overflow = true;
+                    const int2 b = P.jb[j];
+                    const unsigned long long key = colour_key(j);
+                    const bool win1 = b.x < 0 || __ldcg(&P.claim[b.x]) == key;
+                    const bool win2 = b.y < 0 || __ldcg(&P.claim[b.y]) == key;
+                    if (win1 && win2)
+                    {
+                        unsigned long long m = (b.x >= 0 ? __ldcg(&P.used[b.x]) : 0ull) | (b.y >= 0 ? __ldcg(&P.used[b.y]) : 0ull);
+                        int c = __ffsll(~m) - 1;
+                        if (c < 0)
+                        {
+                            c = kMaxColours - 1;   // keep going so the kernel terminates; the host falls back
+                            overflow = true;
+                        }
+                        const unsigned long long bit = 1ull << c;
+                        if (b.x >= 0)
+                        {
+                            __stcg(&P.used[b.x], __ldcg(&P.used[b.x]) | bit);
+                            __stcg(&P.claim[b.x], kNoClaim);
+                        }
+                        if (b.y >= 0)
+                        {
+                            __stcg(&P.used[b.y], __ldcg(&P.used[b.y]) | bit);
+                            __stcg(&P.claim[b.y], kNoClaim);
+                        }
+                        __stcg(&P.colour[j], c);
+                    }
+                    else
+                        lose = true;
                 }
-                const unsigned long long bit = 1ull << c;
-                if (b.x >= 0)
-                {
-                    __stcg(&P.used[b.x], __ldcg(&P.used[b.x]) | bit);
-                    __stcg(&P.claim[b.x], kNoClaim);
-                }
-                if (b.y >= 0)
-                {
-                    __stcg(&P.used[b.y], __ldcg(&P.used[b.y]) | bit);
-                    __stcg(&P.claim[b.y], kNoClaim);
-                }
-                __stcg(&P.colour[j], c);
             }
-            else
+            // losers go to the next round's worklist (its order does not influence the result)
+            const unsigned m = __ballot_sync(0xffffffffu, lose);
+            if (m)
+            {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(nextCount, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (lose) next[base + __popc(m & ((1u << lane) - 1u))] = j;
                 left = true;
+            }
         }
         ++rounds;
         BarrierResult r = grid_barrier(P.barrier, epoch, left, overflow);
@@ -201,8 +231,9 @@ int colour_schedule_build(phyx_b200_ctx* c)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
     const size_t oJb = take(size_t(nj) * sizeof(int2)), oColour = take(size_t(nj) * sizeof(int)), oClaim = take(nb1 * 8), oUsed = take(nb1 * 8),
+                 oList0 = take(size_t(nj) * sizeof(int)), oList1 = take(size_t(nj) * sizeof(int)),
                  oCounts = take(kMaxColours * sizeof(int)), oFirst = take(kMaxColours * sizeof(int)), oHeader = take(16), oResult = take(16),
-                 oBarrier = take(32);
+                 oBarrier = take(32), oListCount = take(16);
     PHYX_TRY(c->colourTmp.reserve(off));
     char* base = c->colourTmp.as<char>();
     int2* jb = reinterpret_cast<int2*>(base + oJb);
@@ -230,7 +261,8 @@ int colour_schedule_build(phyx_b200_ctx* c)
         PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_colour_rounds, kBlock, 0));
         c->colourBlocksPerSM = per > 0 ? per : 1;
     }
-    ColourParams P = { nj, jb, colour, claim, used, barrier, result };
+    ColourParams P = { nj, jb, colour, claim, used, { reinterpret_cast<int*>(base + oList0), reinterpret_cast<int*>(base + oList1) },
+        reinterpret_cast<int*>(base + oListCount), barrier, result };
     int cgrid = std::max(1, std::min(grid, c->numSMs * c->colourBlocksPerSM));
     void* args[] = { &P };
     PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_colour_rounds, dim3(cgrid), dim3(kBlock), args, 0, c->stream));

@@ -237,13 +237,45 @@ __device__ __forceinline__ void prestep_slot(const SolveParams& P, int s)
 }
 
 // ---- one pass over one level of one iteration -----------------------------------------------------------
+// The read-only joint streams of a slot (and its accumulators, which only this thread ever writes)
+// do not depend on what other CTAs do, so they are loaded AHEAD of the grid barrier that opens the
+// level; after the barrier only the two body rows (L2) stand between a thread and its arithmetic.
+// All streams are fetched speculatively, before the skip test: the kernel is latency-bound, not
+// bandwidth-bound (ncu: DRAM ~10 % busy), so spending bytes to shorten the dependent chain wins.
+template <int PHASE>
+struct SlotData
+{
+    float4 c0, c1, c2, c3;   // c1: impulse phase only
+    float2 acc;              // impulse: {accN, accF}; displacement: {accD, -}
+};
+
+template <int PHASE>
+__device__ __forceinline__ void load_slot(const SolveParams& P, int s, bool inRange, SlotData<PHASE>& d)
+{
+    d.c3 = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
+    if (inRange)
+    {
+        d.c3 = __ldcs(&P.q3[s]);
+        d.c0 = __ldcs(&P.q0[s]);
+        d.c2 = __ldcs(&P.q2[s]);
+        if (PHASE == 0)
+        {
+            d.c1 = __ldcs(&P.q1[s]);
+            d.acc = __ldcs(&P.accNF[s]);
+        }
+        else
+            d.acc.x = __ldcs(&P.accD[s]);
+    }
+}
+
 // PHASE 0: SolveJointsImpulses (Solver.cpp:781-910); PHASE 1: SolveJointsDisplacement (:937-1014).
 // firstPass = false is a wake pass: only units that contain a static body and have not run yet in
 // this (iteration, level) are reconsidered.  Returns productive; sets `wake` if a joint of this
-// pass turned a cold static body productive.
+// pass turned a cold static body productive.  `pre` holds the streams of this thread's first slot
+// when havePre is set.
 template <int PHASE>
 __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L, int it, int tick, bool firstPass, int tid, int nthreads, bool& wake,
-    unsigned& activeCount)
+    unsigned& activeCount, SlotData<PHASE>& pre, bool havePre)
 {
     float4* rows = PHASE == 0 ? P.vel : P.disp;
     unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
@@ -255,8 +287,9 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
     {
         const int s = s0 + lane;
         bool valid = s < L.end;
-        float4 c3 = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
-        if (valid) c3 = __ldcs(&P.q3[s]);
+        if (!havePre) load_slot<PHASE>(P, s, valid, pre);
+        havePre = false;
+        const float4 c3 = pre.c3;
         const int r1 = __float_as_int(c3.x), r2 = __float_as_int(c3.y);
         valid = valid && r1 >= 0;
         const int b1 = r1 & kBodyMask, b2 = r2 & kBodyMask;
@@ -292,8 +325,8 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
         if (active)
         {
             ++activeCount;
-            const float4 c0 = __ldcs(&P.q0[s]);
-            const float4 c2 = __ldcs(&P.q2[s]);
+            const float4 c0 = pre.c0;
+            const float4 c2 = pre.c2;
             const float nx = c0.x, ny = c0.y, aN1 = c0.z, aN2 = c0.w;
             const float im1 = c2.x, ii1 = c2.y, im2 = c2.z, ii2 = c2.w;
             const float cinvN = c3.z;
@@ -304,8 +337,8 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
 
             if (PHASE == 0)
             {
-                const float4 c1 = __ldcs(&P.q1[s]);
-                float2 acc = __ldcs(&P.accNF[s]);
+                const float4 c1 = pre.c1;
+                float2 acc = pre.acc;
                 const float aF1 = c1.x, aF2 = c1.y, cinvF = c1.z, dstVel = c1.w;
 
                 float dV = dstVel;
@@ -351,7 +384,7 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
             }
             else
             {
-                float accD = __ldcs(&P.accD[s]);
+                float accD = pre.acc.x;
                 float dV = c3.w;   // dstDisplacingVelocity
                 dV -= nx * v1.x;
                 dV -= ny * v1.y;
@@ -394,14 +427,60 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
     return anyProductive;
 }
 
-// Persistent cooperative kernel: the whole SolveJointIsland loop nest (Solver.cpp:159-211) in one
-// launch, one grid-wide barrier per level (plus one per wake pass, which is rare).
-__global__ void __launch_bounds__(kBlock) k_solve(SolveParams P)
+// All iterations of one phase (Solver.cpp:175-190 / :196-211), one grid barrier per level plus one per
+// wake pass (rare).  Returns the number of iterations run.
+template <int PHASE>
+__device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int tid, int nthreads, unsigned& epoch, int& tick, int& wakePasses,
+    unsigned& activeCount)
+{
+    SlotData<PHASE> pre;
+    bool havePre = false;
+    int ran = 0;
+    for (int it = 0; it < iters; ++it)
+    {
+        bool any = false, productiveAnywhere = false;
+        for (int l = 0; l < P.numLevels; ++l)
+        {
+            const Level L = P.levels[l];
+            ++tick;
+            bool wake = false;
+            any |= solve_level<PHASE>(P, L, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre);
+            // streams of this thread's first slot in the level that follows (next level, or level 0 of
+            // the next iteration), fetched while the grid drains into the barrier
+            {
+                const Level N = P.levels[l + 1 < P.numLevels ? l + 1 : 0];
+                const int sN = N.start + tid;
+                load_slot<PHASE>(P, sN, sN < N.end, pre);
+                havePre = true;
+            }
+            BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
+            while (r.wake)
+            {
+                SlotData<PHASE> scratch;
+                wake = false;
+                any |= solve_level<PHASE>(P, L, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
+                ++wakePasses;
+                r = grid_barrier(P.barrier, epoch, wake, any);
+            }
+            productiveAnywhere = r.productive;
+        }
+        ++ran;
+        if (!productiveAnywhere) break;   // Solver.cpp:189 / :210
+    }
+    return ran;
+}
+
+// Persistent cooperative kernel: the whole SolveJointIsland loop nest (Solver.cpp:159-211) in one launch.
+#ifndef PHYX_SOLVE_MIN_BLOCKS
+#define PHYX_SOLVE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kBlock, PHYX_SOLVE_MIN_BLOCKS) k_solve(SolveParams P)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     unsigned epoch = 0;
-    int wakePasses = 0;
+    int wakePasses = 0, tick = 0;
+    unsigned active[2] = { 0u, 0u };
 
     for (int l = 0; l < P.numLevels; ++l)
     {
@@ -410,37 +489,9 @@ __global__ void __launch_bounds__(kBlock) k_solve(SolveParams P)
         grid_barrier(P.barrier, epoch, false, false);
     }
 
-    int ran[2] = { 0, 0 };
-    unsigned active[2] = { 0u, 0u };
-    int tick = 0;
-#pragma unroll 1
-    for (int phase = 0; phase < 2; ++phase)
-    {
-        const int iters = phase == 0 ? P.contactIters : P.penetrationIters;
-        for (int it = 0; it < iters; ++it)
-        {
-            bool any = false, productiveAnywhere = false;
-            for (int l = 0; l < P.numLevels; ++l)
-            {
-                const Level L = P.levels[l];
-                ++tick;
-                bool firstPass = true;
-                for (;;)
-                {
-                    bool wake = false;
-                    any |= (phase == 0) ? solve_level<0>(P, L, it, tick, firstPass, tid, nthreads, wake, active[0])
-                                        : solve_level<1>(P, L, it, tick, firstPass, tid, nthreads, wake, active[1]);
-                    BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
-                    productiveAnywhere = r.productive;
-                    if (!r.wake) break;
-                    firstPass = false;
-                    ++wakePasses;
-                }
-            }
-            ran[phase]++;
-            if (!productiveAnywhere) break;   // Solver.cpp:189 / :210
-        }
-    }
+    const int ranImpulse = run_phase<0>(P, P.contactIters, tid, nthreads, epoch, tick, wakePasses, active[0]);
+    const int ranDisplacement = run_phase<1>(P, P.penetrationIters, tid, nthreads, epoch, tick, wakePasses, active[1]);
+
     for (int phase = 0; phase < 2; ++phase)
     {
         unsigned v = active[phase];
@@ -449,8 +500,8 @@ __global__ void __launch_bounds__(kBlock) k_solve(SolveParams P)
     }
     if (tid == 0)
     {
-        P.result[0] = ran[0];
-        P.result[1] = ran[1];
+        P.result[0] = ranImpulse;
+        P.result[1] = ranDisplacement;
         P.result[2] = wakePasses;
     }
 }
