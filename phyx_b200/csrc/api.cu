@@ -121,6 +121,7 @@ static int stage_joints(phyx_b200_ctx* c, const phyx_contact_joint* joints, int 
     c->manifoldCount = 0;
     c->pairTableSlots = 0;
     c->hostJointsValid = false;
+    c->colourStateValid = false;
     return PHYX_B200_OK;
 }
 
@@ -178,7 +179,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
-        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp };
+        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->jointColour, &c->bodyUsed, &c->bodyStatic };
     for (DevBuf* b : bufs) b->release();
     c->pinned.release();
     for (auto& ev : c->ev)
@@ -540,6 +541,7 @@ int phyx_b200_upload_collider(phyx_b200_ctx* c, const phyx_manifold* manifolds, 
     c->contactPointCount = 2 * M;
     c->jointCount = jointCount;
     c->hostJointsValid = false;
+    c->colourStateValid = false;
     return collide_rebuild_pair_table(c);
 }
 

@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(kBlock) k_point_new_flags(int numPoints, const
 
 // World.cpp:91-124: new points get a joint appended in (manifold, point) order, known points re-attach
 __global__ void __launch_bounds__(kBlock) k_joint_match(int numPoints, int oldJoints, const int2* __restrict__ manBody, const int* __restrict__ manCount,
-    float4* __restrict__ contactPoints, const int* __restrict__ isNew, const int* __restrict__ newRank, phyx_contact_joint* __restrict__ joints)
+    float4* __restrict__ contactPoints, const int* __restrict__ isNew, const int* __restrict__ newRank, phyx_contact_joint* __restrict__ joints,
+    int* __restrict__ jointColour)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= numPoints) return;
@@ -481,6 +482,7 @@ __global__ void __launch_bounds__(kBlock) k_joint_match(int numPoints, int oldJo
         jt.normalLimiter_accumulatedImpulse = 0.f;
         jt.frictionLimiter_accumulatedImpulse = 0.f;
         joints[j] = jt;
+        jointColour[j] = -1;   // to be coloured by the next schedule build
         reinterpret_cast<int*>(contactPoints + size_t(p) * 2 + 1)[3] = j;
     }
     else
@@ -490,19 +492,36 @@ __global__ void __launch_bounds__(kBlock) k_joint_match(int numPoints, int oldJo
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_joint_alive(int nj, const phyx_contact_joint* __restrict__ joints, int* __restrict__ alive)
+// dead joints also give their colour back to their (dynamic) bodies
+__global__ void __launch_bounds__(kBlock) k_joint_alive(int nj, const phyx_contact_joint* __restrict__ joints, int* __restrict__ alive,
+    const int* __restrict__ jointColour, unsigned long long* __restrict__ bodyUsed, const unsigned char* __restrict__ bodyStatic)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nj) alive[j] = joints[j].contactPointIndex >= 0;
+    if (j >= nj) return;
+    const phyx_contact_joint jt = joints[j];
+    const bool live = jt.contactPointIndex >= 0;
+    alive[j] = live;
+    if (!live && bodyUsed)
+    {
+        const int c = jointColour[j];
+        if (c >= 0)
+        {
+            const unsigned long long keep = ~(1ull << c);
+            if (!bodyStatic[jt.body1Index]) atomicAnd(&bodyUsed[jt.body1Index], keep);
+            if (!bodyStatic[jt.body2Index]) atomicAnd(&bodyUsed[jt.body2Index], keep);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kBlock) k_joint_fill(int n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
-    const int* __restrict__ moverIndex, phyx_contact_joint* __restrict__ joints)
+    const int* __restrict__ moverIndex, phyx_contact_joint* __restrict__ joints, int* __restrict__ jointColour)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int K = *totalPtr;
     if (j >= n || j >= K || alive[j]) return;
-    joints[j] = joints[moverIndex[j - prefix[j]]];   // World.cpp:131-134
+    const int src = moverIndex[j - prefix[j]];
+    joints[j] = joints[src];   // World.cpp:131-134
+    jointColour[j] = jointColour[src];
 }
 
 __global__ void __launch_bounds__(kBlock) k_joint_backlink(const int* __restrict__ totalPtr, const phyx_contact_joint* __restrict__ joints,
@@ -536,8 +555,9 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         PHYX_CUDA(cudaMemcpyAsync(&fresh, total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         PHYX_CUDA(cudaStreamSynchronize(c->stream));
         PHYX_TRY(c->joints.reserve_keep(size_t(J0 + fresh > 0 ? J0 + fresh : 1) * sizeof(phyx_contact_joint), size_t(J0) * sizeof(phyx_contact_joint), c->stream));
+        PHYX_TRY(c->jointColour.reserve_keep(size_t(J0 + fresh > 0 ? J0 + fresh : 1) * sizeof(int), c->colourStateValid ? size_t(J0) * sizeof(int) : 0, c->stream));
         k_joint_match<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(P, J0, c->manBody.as<int2>(), c->manCount.as<int>(),
-            c->contactPoints.as<float4>(), isNew, newRank, c->joints.as<phyx_contact_joint>());
+            c->contactPoints.as<float4>(), isNew, newRank, c->joints.as<phyx_contact_joint>(), c->jointColour.as<int>());
         c->launches++;
     }
     const int J1 = J0 + fresh;
@@ -551,10 +571,13 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         int* movers = prefix + J1;
         int* total = movers + J1;
         const int grid = (J1 + kBlock - 1) / kBlock;
-        k_joint_alive<<<grid, kBlock, 0, c->stream>>>(J1, c->joints.as<phyx_contact_joint>(), alive);
+        PHYX_TRY(c->jointColour.reserve_keep(size_t(J1) * sizeof(int), c->colourStateValid ? size_t(J0) * sizeof(int) : 0, c->stream));
+        const bool track = c->colourStateValid && c->colourStateBodies == c->bodyCount;
+        k_joint_alive<<<grid, kBlock, 0, c->stream>>>(J1, c->joints.as<phyx_contact_joint>(), alive, c->jointColour.as<int>(),
+            track ? c->bodyUsed.as<unsigned long long>() : nullptr, c->bodyStatic.as<unsigned char>());
         PHYX_TRY(exclusive_scan_i32(c, alive, prefix, J1, total));
         k_list_movers<<<grid, kBlock, 0, c->stream>>>(J1, alive, prefix, total, movers);
-        k_joint_fill<<<grid, kBlock, 0, c->stream>>>(J1, alive, prefix, total, movers, c->joints.as<phyx_contact_joint>());
+        k_joint_fill<<<grid, kBlock, 0, c->stream>>>(J1, alive, prefix, total, movers, c->joints.as<phyx_contact_joint>(), c->jointColour.as<int>());
         k_joint_backlink<<<grid, kBlock, 0, c->stream>>>(total, c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>());
         c->launches += 4;
         PHYX_CUDA(cudaMemcpyAsync(&K, total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -570,6 +593,7 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
 
 int collide_reset(phyx_b200_ctx* c)
 {
+    c->colourStateValid = false;
     c->manifoldCount = 0;
     c->contactPointCount = 0;
     c->jointCount = 0;

@@ -39,8 +39,10 @@ __device__ __forceinline__ unsigned mix32(unsigned x)   // murmur3 finaliser: th
 // jb[j] = {body1 or -1 if static, body2 or -1 if static}; joints with no dynamic body get colour 0
 // Also validates the joint's indices (result[2] = 1 + first bad joint seen): nothing on the host
 // has to walk the joint array.
+// keepColours: the joint cache carried last step's colours along (incremental build); only joints
+// with colour -1 (new this step) still need one.
 __global__ void __launch_bounds__(kBlock) k_colour_init(int nj, int nb, int ncp, const phyx_contact_joint* __restrict__ joints,
-    const float4* __restrict__ params, int2* __restrict__ jb, int* __restrict__ colour, int* __restrict__ result)
+    const float4* __restrict__ params, int2* __restrict__ jb, int* __restrict__ colour, int* __restrict__ result, bool keepColours)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nj) return;
@@ -56,7 +58,26 @@ __global__ void __launch_bounds__(kBlock) k_colour_init(int nj, int nb, int ncp,
     if (p1.x == 0.0f && p1.y == 0.0f) b1 = -1;
     if (p2.x == 0.0f && p2.y == 0.0f) b2 = -1;
     jb[j] = make_int2(b1, b2);
-    colour[j] = (b1 < 0 && b2 < 0) ? 0 : -1;
+    if (b1 < 0 && b2 < 0)
+        colour[j] = 0;
+    else if (!keepColours)
+        colour[j] = -1;
+}
+
+// static flags the colouring is built with; mismatch = 1 if a body changed class since the last full build
+__global__ void __launch_bounds__(kBlock) k_colour_body_flags(int nb, const float4* __restrict__ params, unsigned char* __restrict__ bodyStatic, bool compare,
+    int* __restrict__ result)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    float4 p = params[b];
+    unsigned char st = (p.x == 0.0f && p.y == 0.0f) ? 1 : 0;
+    if (compare)
+    {
+        if (bodyStatic[b] != st) result[3] = 1;
+    }
+    else
+        bodyStatic[b] = st;
 }
 
 struct ColourParams
@@ -216,7 +237,24 @@ __global__ void __launch_bounds__(kBlock) k_colour_place(int nj, const uint2* __
 
 // Build the colour schedule for the resident joints.  Returns PHYX_B200_ERR_CAPACITY if more than
 // 64 colours are needed (a dynamic body with dozens of joints); the caller then uses the host builder.
+static int colour_schedule_build_once(phyx_b200_ctx* c, bool incremental, bool* staticsChanged);
+
+// Incremental by default: joints keep the colour they had last step (the joint cache carries it
+// through its compaction), the per-body colour masks persist, and only joints created this step go
+// through the colouring rounds.  A full rebuild happens on the first call, after the caller replaced
+// the joints, when a body changed between static and dynamic, or when incremental additions have
+// let the number of colours drift upwards.
 int colour_schedule_build(phyx_b200_ctx* c)
+{
+    bool incremental = c->colourStateValid && c->colourStateBodies == c->bodyCount && c->jointColour.ptr && c->bodyUsed.ptr;
+    bool changed = false;
+    int st = colour_schedule_build_once(c, incremental, &changed);
+    if (st == PHYX_B200_OK && incremental && (changed || c->levelCount > c->coloursAtFullBuild + 6))
+        st = colour_schedule_build_once(c, false, &changed);
+    return st;
+}
+
+static int colour_schedule_build_once(phyx_b200_ctx* c, bool incremental, bool* staticsChanged)
 {
     const int nj = c->jointCount, nb = c->bodyCount;
     c->hostSlots.clear();
@@ -230,16 +268,19 @@ int colour_schedule_build(phyx_b200_ctx* c)
     // scratch: jb[nj] int2 | colour[nj] int | claim[nb] u64 | used[nb] u64 | counts[64] | firstPos[64] | header[4] | result[4] | barrier[4] u64
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-    const size_t oJb = take(size_t(nj) * sizeof(int2)), oColour = take(size_t(nj) * sizeof(int)), oClaim = take(nb1 * 8), oUsed = take(nb1 * 8),
+    const size_t oJb = take(size_t(nj) * sizeof(int2)), oClaim = take(nb1 * 8),
                  oList0 = take(size_t(nj) * sizeof(int)), oList1 = take(size_t(nj) * sizeof(int)),
                  oCounts = take(kMaxColours * sizeof(int)), oFirst = take(kMaxColours * sizeof(int)), oHeader = take(16), oResult = take(16),
                  oBarrier = take(32), oListCount = take(16);
     PHYX_TRY(c->colourTmp.reserve(off));
     char* base = c->colourTmp.as<char>();
     int2* jb = reinterpret_cast<int2*>(base + oJb);
-    int* colour = reinterpret_cast<int*>(base + oColour);
+    PHYX_TRY(c->jointColour.reserve_keep(size_t(nj) * sizeof(int), incremental ? size_t(nj) * sizeof(int) : 0, c->stream));
+    PHYX_TRY(c->bodyUsed.reserve_keep(nb1 * 8, incremental ? nb1 * 8 : 0, c->stream));
+    PHYX_TRY(c->bodyStatic.reserve_keep(nb1, incremental ? nb1 : 0, c->stream));
+    int* colour = c->jointColour.as<int>();
     unsigned long long* claim = reinterpret_cast<unsigned long long*>(base + oClaim);
-    unsigned long long* used = reinterpret_cast<unsigned long long*>(base + oUsed);
+    unsigned long long* used = c->bodyUsed.as<unsigned long long>();
     int* counts = reinterpret_cast<int*>(base + oCounts);
     int* firstPos = reinterpret_cast<int*>(base + oFirst);
     int* header = reinterpret_cast<int*>(base + oHeader);
@@ -247,12 +288,17 @@ int colour_schedule_build(phyx_b200_ctx* c)
     unsigned long long* barrier = reinterpret_cast<unsigned long long*>(base + oBarrier);
 
     PHYX_CUDA(cudaMemsetAsync(claim, 0xff, nb1 * 8, c->stream));
-    PHYX_CUDA(cudaMemsetAsync(used, 0, nb1 * 8, c->stream));
+    if (!incremental) PHYX_CUDA(cudaMemsetAsync(used, 0, nb1 * 8, c->stream));
     PHYX_CUDA(cudaMemsetAsync(base + oCounts, 0, off - oCounts, c->stream));   // counts .. barrier
 
     const int grid = (nj + kBlock - 1) / kBlock;
+    if (nb > 0)
+    {
+        k_colour_body_flags<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, c->params.as<float4>(), c->bodyStatic.as<unsigned char>(), incremental, result);
+        c->launches++;
+    }
     k_colour_init<<<grid, kBlock, 0, c->stream>>>(nj, nb, c->contactPointCount, c->joints.as<phyx_contact_joint>(), c->params.as<float4>(), jb, colour,
-        result);
+        result, incremental);
     c->launches++;
 
     if (c->colourBlocksPerSM == 0)
@@ -303,6 +349,10 @@ int colour_schedule_build(phyx_b200_ctx* c)
     c->levelCount = host.header[0];
     c->slotCount = host.header[1];
     c->colourRounds = host.result[0];
+    *staticsChanged = host.result[3] != 0;
+    c->colourStateValid = true;
+    c->colourStateBodies = nb;
+    if (!incremental) c->coloursAtFullBuild = c->levelCount;
     c->hostLevels.assign(lv, lv + c->levelCount);
     c->hostSlotsStale = true;
     return PHYX_B200_OK;

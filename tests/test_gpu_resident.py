@@ -118,3 +118,36 @@ def test_mirrors_can_be_switched_off(ref):
         r.step()
     assert len(w.joints()) == len(r.joints()) and len(w.manifolds()) == len(r.manifolds())   # sizes stay current
     assert_records_equal(w.bodies(), r.bodies(), ("pos", "velocity"), what="bodies")
+
+
+@pytest.mark.parametrize("scene,steps", [("stack_1k", 60), ("pyramid_1k", 25)])
+def test_incremental_colouring_stays_valid_and_exact(oracle, scene, steps):
+    """Colour mode over many resident steps: the joint cache carries colours from step to step and only
+    new joints are coloured.  Every step the schedule must still be a proper colouring, and the solve
+    must equal the oracle's sequential sweep in slot order, bit for bit."""
+    from test_gpu_hotpath import check_schedule, VEL_FIELDS
+
+    w = world.World(scenes.make(scene))
+    ctx = w.context()
+    ctx.upload_bodies(w.bodies())
+    rounds = []
+    for step in range(steps):
+        ctx.integrate_velocity(scenes.DT, scenes.GRAVITY)
+        ctx.update_broadphase()
+        ctx.update_pairs()
+        ctx.update_manifolds()
+        ctx.pack_manifolds()
+        ctx.refresh_contact_joints()
+        b0, j0, cp = ctx.download_bodies(), ctx.download_joints(), ctx.download_contact_points()
+        st = ctx.solve_resident(schedule=capi.SCHEDULE_COLOUR)
+        rounds.append(st.colourRounds)
+        slots, levels = ctx.get_schedule()
+        check_schedule(slots, levels, j0, b0)
+        if step % 7 == 0 or step == steps - 1:
+            ob, oj, ran = oracle.solve_scheduled(b0, j0, cp, slots, levels)
+            assert (st.contactIterationsRun, st.penetrationIterationsRun) == ran
+            assert_records_equal(ctx.download_joints(), oj, what=f"step {step} joints")
+            assert_records_equal(ctx.download_bodies(), ob, VEL_FIELDS, what=f"step {step} bodies")
+        ctx.integrate_position(scenes.DT)
+    # after the first (full) build, later steps only colour the few new joints
+    assert min(rounds[1:]) < rounds[0]
