@@ -31,6 +31,8 @@
 #include "common.cuh"
 #include "barrier.cuh"
 
+#include <stdlib.h>
+
 namespace phyx
 {
 
@@ -236,6 +238,89 @@ __device__ __forceinline__ void prestep_slot(const SolveParams& P, int s)
     if (!st2) __stcg(&P.vel[b2], v2);
 }
 
+// ---- the arithmetic of one joint --------------------------------------------------------------------
+// PHASE 0: SolveJointsImpulses (Solver.cpp:833-901): normal impulse clamped to >= -accumulated, then
+// friction clamped to the Coulomb cone of the updated normal impulse.  PHASE 1:
+// SolveJointsDisplacement (:971-1003).  v1 / v2 are the two body rows; acc = {accN, accF} resp. {accD, -}.
+// `wide` selects the SIMD (xor) form of flipsign over the scalar one (SIMD_AVX2.h:272 / SIMD_Scalar.h:265).
+template <int PHASE>
+__device__ __forceinline__ bool relax(const float4 c0, const float4 c1, const float4 c2, const float4 c3, float2& acc, float4& v1, float4& v2, bool wide)
+{
+    const float nx = c0.x, ny = c0.y, aN1 = c0.z, aN2 = c0.w;
+    const float im1 = c2.x, ii1 = c2.y, im2 = c2.z, ii2 = c2.w;
+    const float cinvN = c3.z;
+    // normal limiter: projectors (n, -n), compMass = projector * invMass
+    const float n2x = -nx, n2y = -ny;
+    const float cm1x = nx * im1, cm1y = ny * im1, cm1a = aN1 * ii1;
+    const float cm2x = n2x * im2, cm2y = n2y * im2, cm2a = aN2 * ii2;
+
+    if (PHASE == 0)
+    {
+        const float aF1 = c1.x, aF2 = c1.y, cinvF = c1.z, dstVel = c1.w;
+
+        float dV = dstVel;
+        dV -= nx * v1.x;
+        dV -= ny * v1.y;
+        dV -= aN1 * v1.z;
+        dV -= n2x * v2.x;
+        dV -= n2y * v2.y;
+        dV -= aN2 * v2.z;
+        float dN = dV * cinvN;
+        dN = vmax(dN, -acc.x);
+        v1.x += cm1x * dN;
+        v1.y += cm1y * dN;
+        v1.z += cm1a * dN;
+        v2.x += cm2x * dN;
+        v2.y += cm2y * dN;
+        v2.z += cm2a * dN;
+        acc.x += dN;
+
+        const float tx = -ny, ty = nx, t2x = -tx, t2y = -ty;
+        float fV = 0.0f;
+        fV -= tx * v1.x;
+        fV -= ty * v1.y;
+        fV -= aF1 * v1.z;
+        fV -= t2x * v2.x;
+        fV -= t2y * v2.y;
+        fV -= aF2 * v2.z;
+        float dF = fV * cinvF;
+        const float force = acc.y + dF;
+        const float limit = acc.x * kFrictionCoefficient;
+        const float limitSigned = wide ? flipsign_bits(limit, force) : (force < 0.0f ? -limit : limit);
+        const float adjusted = limitSigned - acc.y;
+        dF = (fabsf(force) > limit) ? adjusted : dF;
+        acc.y += dF;
+        v1.x += (tx * im1) * dF;
+        v1.y += (ty * im1) * dF;
+        v1.z += (aF1 * ii1) * dF;
+        v2.x += (t2x * im2) * dF;
+        v2.y += (t2y * im2) * dF;
+        v2.z += (aF2 * ii2) * dF;
+        return vmax(fabsf(dN), fabsf(dF)) > kProductiveImpulse;
+    }
+    else
+    {
+        float accD = acc.x;
+        float dV = c3.w;   // dstDisplacingVelocity
+        dV -= nx * v1.x;
+        dV -= ny * v1.y;
+        dV -= aN1 * v1.z;
+        dV -= n2x * v2.x;
+        dV -= n2y * v2.y;
+        dV -= aN2 * v2.z;
+        float d = dV * cinvN;
+        d = vmax(d, -accD);
+        v1.x += cm1x * d;
+        v1.y += cm1y * d;
+        v1.z += cm1a * d;
+        v2.x += cm2x * d;
+        v2.y += cm2y * d;
+        v2.z += cm2a * d;
+        acc.x = accD + d;
+        return fabsf(d) > kProductiveImpulse;
+    }
+}
+
 // ---- one pass over one level of one iteration -----------------------------------------------------------
 // The read-only joint streams of a slot (and its accumulators, which only this thread ever writes)
 // do not depend on what other CTAs do, so they are loaded AHEAD of the grid barrier that opens the
@@ -325,85 +410,12 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
         if (active)
         {
             ++activeCount;
-            const float4 c0 = pre.c0;
-            const float4 c2 = pre.c2;
-            const float nx = c0.x, ny = c0.y, aN1 = c0.z, aN2 = c0.w;
-            const float im1 = c2.x, ii1 = c2.y, im2 = c2.z, ii2 = c2.w;
-            const float cinvN = c3.z;
-            // normal limiter: projectors (n, -n), compMass = projector * invMass
-            const float n2x = -nx, n2y = -ny;
-            const float cm1x = nx * im1, cm1y = ny * im1, cm1a = aN1 * ii1;
-            const float cm2x = n2x * im2, cm2y = n2y * im2, cm2a = aN2 * ii2;
-
+            float2 acc = pre.acc;
+            productive = relax<PHASE>(pre.c0, pre.c1, pre.c2, c3, acc, v1, v2, wide);
             if (PHASE == 0)
-            {
-                const float4 c1 = pre.c1;
-                float2 acc = pre.acc;
-                const float aF1 = c1.x, aF2 = c1.y, cinvF = c1.z, dstVel = c1.w;
-
-                float dV = dstVel;
-                dV -= nx * v1.x;
-                dV -= ny * v1.y;
-                dV -= aN1 * v1.z;
-                dV -= n2x * v2.x;
-                dV -= n2y * v2.y;
-                dV -= aN2 * v2.z;
-                float dN = dV * cinvN;
-                dN = vmax(dN, -acc.x);
-                v1.x += cm1x * dN;
-                v1.y += cm1y * dN;
-                v1.z += cm1a * dN;
-                v2.x += cm2x * dN;
-                v2.y += cm2y * dN;
-                v2.z += cm2a * dN;
-                acc.x += dN;
-
-                const float tx = -ny, ty = nx, t2x = -tx, t2y = -ty;
-                float fV = 0.0f;
-                fV -= tx * v1.x;
-                fV -= ty * v1.y;
-                fV -= aF1 * v1.z;
-                fV -= t2x * v2.x;
-                fV -= t2y * v2.y;
-                fV -= aF2 * v2.z;
-                float dF = fV * cinvF;
-                const float force = acc.y + dF;
-                const float limit = acc.x * kFrictionCoefficient;
-                const float limitSigned = wide ? flipsign_bits(limit, force) : (force < 0.0f ? -limit : limit);
-                const float adjusted = limitSigned - acc.y;
-                dF = (fabsf(force) > limit) ? adjusted : dF;
-                acc.y += dF;
-                v1.x += (tx * im1) * dF;
-                v1.y += (ty * im1) * dF;
-                v1.z += (aF1 * ii1) * dF;
-                v2.x += (t2x * im2) * dF;
-                v2.y += (t2y * im2) * dF;
-                v2.z += (aF2 * ii2) * dF;
                 __stcs(&P.accNF[s], acc);
-                productive = vmax(fabsf(dN), fabsf(dF)) > kProductiveImpulse;
-            }
             else
-            {
-                float accD = pre.acc.x;
-                float dV = c3.w;   // dstDisplacingVelocity
-                dV -= nx * v1.x;
-                dV -= ny * v1.y;
-                dV -= aN1 * v1.z;
-                dV -= n2x * v2.x;
-                dV -= n2y * v2.y;
-                dV -= aN2 * v2.z;
-                float d = dV * cinvN;
-                d = vmax(d, -accD);
-                v1.x += cm1x * d;
-                v1.y += cm1y * d;
-                v1.z += cm1a * d;
-                v2.x += cm2x * d;
-                v2.y += cm2y * d;
-                v2.z += cm2a * d;
-                accD += d;
-                __stcs(&P.accD[s], accD);
-                productive = fabsf(d) > kProductiveImpulse;
-            }
+                __stcs(&P.accD[s], acc.x);
 
             // lastIteration = it where productive (Solver.cpp:903-910)
             if (!st1)
@@ -506,6 +518,316 @@ __global__ void __launch_bounds__(kBlock, PHYX_SOLVE_MIN_BLOCKS) k_solve(SolvePa
     }
 }
 
+// =====================================================================================================
+// TMA-staged variant of the solve kernel
+// =====================================================================================================
+// Same algorithm, different data movement.  Each CTA owns every gridDim.x-th chunk of kU*256 slots of
+// every level.  The four read-only joint streams of a chunk (Q0..Q3, 64 B per slot) are brought into a
+// shared-memory ring by 1-D bulk TMA copies (cp.async.bulk, SASS UBLKCP) that complete on an mbarrier;
+// one elected thread issues them kStages-1 chunks ahead.  Because the streams never change during a
+// solve, the producer runs ahead of the grid barriers too: when a level opens, its first chunks are
+// already in shared memory, and what remains on the critical path of a slot is the gather of its two
+// body rows from L2, of which every thread keeps kU slots' worth in flight.
+constexpr int kPipeThreads = kBlock;
+
+template <int U>
+struct PipeStage
+{
+    float4 q0[U * kPipeThreads], q1[U * kPipeThreads], q2[U * kPipeThreads], q3[U * kPipeThreads];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned done;
+    do
+    {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// the chunks this CTA owns, in execution order
+struct ChunkCursor
+{
+    int it, l, k;
+};
+
+template <int U>
+__device__ __forceinline__ bool cursor_next(const SolveParams& P, int iters, ChunkCursor& c, int& base, int& count)
+{
+    while (c.it < iters)
+    {
+        const Level L = P.levels[c.l];
+        const long long b = L.start + static_cast<long long>(blockIdx.x + c.k * gridDim.x) * (U * kPipeThreads);
+        if (b < L.end)
+        {
+            base = int(b);
+            count = min(U * kPipeThreads, L.end - int(b));
+            ++c.k;
+            return true;
+        }
+        c.k = 0;
+        if (++c.l == P.numLevels)
+        {
+            c.l = 0;
+            ++c.it;
+        }
+    }
+    return false;
+}
+
+struct SlotWork
+{
+    float4 c3, v1, v2;
+    float2 acc;
+    int s, b1, b2, last1, last2;
+    unsigned pos;
+    bool valid, wide, st1, st2, unitHasStatic, active;
+};
+
+template <int PHASE, int U, int S>
+__device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, PipeStage<U>* stages, unsigned long long* full, int* sharedWord,
+    unsigned& consumed, unsigned& epoch, int& tick, int& wakePasses, unsigned& activeCount)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned seg = 0xffu << (lane & ~7);
+    float4* rows = PHASE == 0 ? P.vel : P.disp;
+    unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
+    const bool producer = threadIdx.x == 0;
+
+    ChunkCursor prod = { 0, 0, 0 };
+    unsigned issued = consumed;   // producer-only bookkeeping (thread 0)
+    auto produce = [&]() {
+        int base, count;
+        if (!cursor_next<U>(P, iters, prod, base, count)) return;
+        const unsigned st = issued % S;
+        PipeStage<U>& dst = stages[st];
+        const unsigned bytes = unsigned(count) * 16u;
+        mbar_expect_tx(&full[st], 4u * bytes);
+        bulk_g2s(dst.q0, P.q0 + base, bytes, &full[st]);
+        bulk_g2s(dst.q1, P.q1 + base, bytes, &full[st]);
+        bulk_g2s(dst.q2, P.q2 + base, bytes, &full[st]);
+        bulk_g2s(dst.q3, P.q3 + base, bytes, &full[st]);
+        ++issued;
+    };
+    if (producer)
+        for (int k = 0; k < S - 1; ++k) produce();
+
+    int ran = 0;
+    for (int it = 0; it < iters; ++it)
+    {
+        bool any = false, productiveAnywhere = false;
+        for (int l = 0; l < P.numLevels; ++l)
+        {
+            const Level L = P.levels[l];
+            ++tick;
+            bool wake = false;
+            for (int k = 0;; ++k)
+            {
+                const long long cb = L.start + static_cast<long long>(blockIdx.x + k * gridDim.x) * (U * kPipeThreads);
+                if (cb >= L.end) break;
+                const int base = int(cb);
+                const int count = min(U * kPipeThreads, L.end - base);
+                const unsigned st = consumed % S;
+                if (producer) produce();   // refills the stage released by the previous chunk's __syncthreads
+                mbar_wait(&full[st], (consumed / S) & 1u);
+                const PipeStage<U>& in = stages[st];
+
+                SlotWork w[U];
+                // 1. decode, issue every global load of the chunk's slots
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    const int idx = u * kPipeThreads + threadIdx.x;
+                    SlotWork& x = w[u];
+                    x.s = base + idx;
+                    x.valid = idx < count;
+                    x.c3 = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
+                    if (x.valid) x.c3 = in.q3[idx];
+                    const int r1 = __float_as_int(x.c3.x), r2 = __float_as_int(x.c3.y);
+                    x.valid = x.valid && r1 >= 0;
+                    x.b1 = r1 & kBodyMask;
+                    x.b2 = r2 & kBodyMask;
+                    x.st1 = x.valid && (r1 & kStaticBit);
+                    x.st2 = x.valid && (r2 & kStaticBit);
+                    x.wide = x.s < L.grouped_end;
+                    x.v1 = x.v2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    x.acc = make_float2(0.f, 0.f);
+                    x.pos = 0;
+                    if (x.valid)
+                    {
+                        x.v1 = __ldcg(&rows[x.b1]);
+                        x.v2 = __ldcg(&rows[x.b2]);
+                        if (PHASE == 0)
+                            x.acc = __ldcs(&P.accNF[x.s]);
+                        else
+                            x.acc.x = __ldcs(&P.accD[x.s]);
+                        if (x.st1 || x.st2) x.pos = P.slotPos ? unsigned(P.slotPos[x.s]) : unsigned(x.s);
+                    }
+                }
+                // 2. skip test (Solver.cpp:790-798)
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    SlotWork& x = w[u];
+                    const unsigned mStatic = __ballot_sync(0xffffffffu, x.st1 || x.st2);
+                    x.unitHasStatic = x.wide ? (mStatic & seg) != 0 : (x.st1 || x.st2);
+                    x.last1 = x.last2 = -1;
+                    x.active = false;
+                    if (x.valid)
+                    {
+                        x.last1 = x.st1 ? static_visible_last(&statics[x.b1], it, x.pos) : __float_as_int(x.v1.w);
+                        x.last2 = x.st2 ? static_visible_last(&statics[x.b2], it, x.pos) : __float_as_int(x.v2.w);
+                        x.active = (x.last1 > it - 2) || (x.last2 > it - 2);
+                    }
+                    const unsigned mActive = __ballot_sync(0xffffffffu, x.active);
+                    if (x.wide) x.active = x.valid && (mActive & seg) != 0;
+                }
+                // 3. relax, write back
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    SlotWork& x = w[u];
+                    if (!x.active) continue;
+                    const int idx = u * kPipeThreads + threadIdx.x;
+                    ++activeCount;
+                    const bool productive = relax<PHASE>(in.q0[idx], in.q1[idx], in.q2[idx], x.c3, x.acc, x.v1, x.v2, x.wide);
+                    if (PHASE == 0)
+                        __stcs(&P.accNF[x.s], x.acc);
+                    else
+                        __stcs(&P.accD[x.s], x.acc.x);
+                    if (!x.st1)
+                    {
+                        x.v1.w = __int_as_float(productive ? it : x.last1);
+                        __stcg(&rows[x.b1], x.v1);
+                    }
+                    else if (productive)
+                        wake |= static_mark(&statics[x.b1], it, x.pos);
+                    if (!x.st2)
+                    {
+                        x.v2.w = __int_as_float(productive ? it : x.last2);
+                        __stcg(&rows[x.b2], x.v2);
+                    }
+                    else if (productive)
+                        wake |= static_mark(&statics[x.b2], it, x.pos);
+                    if (x.unitHasStatic) __stcg(&P.processed[x.s], tick);
+                    any |= productive;
+                }
+                __syncthreads();   // every thread is done with this stage: it may be refilled
+                ++consumed;
+            }
+            BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
+            while (r.wake)
+            {
+                SlotData<PHASE> scratch;
+                wake = false;
+                any |= solve_level<PHASE>(P, L, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
+                ++wakePasses;
+                r = grid_barrier(P.barrier, epoch, wake, any);
+            }
+            productiveAnywhere = r.productive;
+        }
+        ++ran;
+        if (!productiveAnywhere) break;   // Solver.cpp:189 / :210
+    }
+    // drain: chunks fetched speculatively for iterations that will not run must land before the ring
+    // is reused or the CTA exits
+    if (producer)
+    {
+        for (unsigned n = consumed; n != issued; ++n) mbar_wait(&full[n % S], (n / S) & 1u);
+        *sharedWord = int(issued);
+    }
+    __syncthreads();
+    consumed = unsigned(*sharedWord);
+    __syncthreads();
+    return ran;
+}
+
+template <int U, int S>
+__global__ void __launch_bounds__(kPipeThreads) k_solve_pipe(SolveParams P)
+{
+    extern __shared__ __align__(128) unsigned char pipeSmem[];
+    PipeStage<U>* stages = reinterpret_cast<PipeStage<U>*>(pipeSmem);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(pipeSmem + sizeof(PipeStage<U>) * S);
+    int* sharedWord = reinterpret_cast<int*>(full + S);
+
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    if (threadIdx.x == 0)
+    {
+        for (int k = 0; k < S; ++k) mbar_init(&full[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    unsigned epoch = 0, consumed = 0;
+    int wakePasses = 0, tick = 0;
+    unsigned active[2] = { 0u, 0u };
+
+    for (int l = 0; l < P.numLevels; ++l)
+    {
+        const Level L = P.levels[l];
+        for (int s = L.start + tid; s < L.end; s += nthreads) prestep_slot(P, s);
+        grid_barrier(P.barrier, epoch, false, false);
+    }
+    const int ranImpulse = run_phase_pipe<0, U, S>(P, P.contactIters, stages, full, sharedWord, consumed, epoch, tick, wakePasses, active[0]);
+    const int ranDisplacement = run_phase_pipe<1, U, S>(P, P.penetrationIters, stages, full, sharedWord, consumed, epoch, tick, wakePasses, active[1]);
+
+    for (int phase = 0; phase < 2; ++phase)
+    {
+        unsigned v = active[phase];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.activeTotal[phase], static_cast<unsigned long long>(v));
+    }
+    if (tid == 0)
+    {
+        P.result[0] = ranImpulse;
+        P.result[1] = ranDisplacement;
+        P.result[2] = wakePasses;
+    }
+}
+
+template <int U, int S>
+static int launch_solve_pipe(phyx_b200_ctx* c, SolveParams& P, int widestLevel)
+{
+    const size_t smem = sizeof(PipeStage<U>) * S + sizeof(unsigned long long) * S + 16;
+    static int perSM = 0;
+    if (perSM == 0)
+    {
+        PHYX_CUDA(cudaFuncSetAttribute(k_solve_pipe<U, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_solve_pipe<U, S>, kPipeThreads, smem));
+        if (perSM < 1)
+        {
+            set_error("pipelined solve kernel does not fit on an SM");
+            return PHYX_B200_ERR_CUDA;
+        }
+    }
+    const int want = (widestLevel + U * kPipeThreads - 1) / (U * kPipeThreads);
+    const int grid = max(1, min(want, c->numSMs * perSM));
+    void* args[] = { &P };
+    PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_pipe<U, S>, dim3(grid), dim3(kPipeThreads), args, smem, c->stream));
+    return PHYX_B200_OK;
+}
+
 // ---- host orchestration -----------------------------------------------------------------------------
 
 static float elapsed(cudaEvent_t a, cudaEvent_t b)
@@ -594,8 +916,29 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         for (const Level& L : c->hostLevels) maxLevel = max(maxLevel, L.end - L.start);
         int want = (maxLevel + kBlock - 1) / kBlock;
         int sgrid = max(1, min(want, c->numSMs * c->solveBlocksPerSM));
-        void* args[] = { &P };
-        PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3(sgrid), dim3(kBlock), args, 0, c->stream));
+        // PHYX_SOLVE_KERNEL=direct selects the register-prefetch kernel; default is the TMA-staged one
+        // (PHYX_SOLVE_PIPE="<slots per thread><stages>", e.g. 23)
+        static const char* kernelEnv = getenv("PHYX_SOLVE_KERNEL");
+        static const char* pipeEnv = getenv("PHYX_SOLVE_PIPE");
+        if (kernelEnv && !strcmp(kernelEnv, "direct"))
+        {
+            void* args[] = { &P };
+            PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3(sgrid), dim3(kBlock), args, 0, c->stream));
+        }
+        else
+        {
+            const int variant = pipeEnv ? atoi(pipeEnv) : 23;
+            switch (variant)
+            {
+            case 12: PHYX_TRY((launch_solve_pipe<1, 2>(c, P, maxLevel))); break;
+            case 13: PHYX_TRY((launch_solve_pipe<1, 3>(c, P, maxLevel))); break;
+            case 14: PHYX_TRY((launch_solve_pipe<1, 4>(c, P, maxLevel))); break;
+            case 22: PHYX_TRY((launch_solve_pipe<2, 2>(c, P, maxLevel))); break;
+            case 32: PHYX_TRY((launch_solve_pipe<3, 2>(c, P, maxLevel))); break;
+            case 42: PHYX_TRY((launch_solve_pipe<4, 2>(c, P, maxLevel))); break;
+            default: PHYX_TRY((launch_solve_pipe<2, 3>(c, P, maxLevel))); break;
+            }
+        }
         c->launches++;
         PHYX_CUDA(cudaEventRecord(e2, c->stream));
         k_finish<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->accNF.as<float2>(), c->joints.as<phyx_contact_joint>());
