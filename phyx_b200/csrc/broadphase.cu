@@ -127,11 +127,12 @@ __global__ void __launch_bounds__(kBlock) k_radix_scatter(const uint2* __restric
 // ---- entries ----------------------------------------------------------------------------------
 
 __global__ void k_gather_entries(int n, const uint2* __restrict__ sorted, const float4* __restrict__ aabb, float2* __restrict__ entryX,
-    float2* __restrict__ entryY, unsigned* __restrict__ entryIndex)
+    float2* __restrict__ entryY, unsigned* __restrict__ entryIndex, int* __restrict__ rowOf)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned b = sorted[i].y;
+    rowOf[b] = i;   // inverse permutation: the solver stores body rows in this order (solve.cu)
     float4 bb = aabb[b];
     entryX[i] = make_float2(bb.x, bb.z);
     entryY[i] = make_float2((bb.y + bb.w) * 0.5f, (bb.w - bb.y) * 0.5f);   // Collider.cpp:276-279
@@ -275,8 +276,12 @@ int broadphase_update(phyx_b200_ctx* c)
     PHYX_TRY(radix_pass(c, c->sortA.as<uint2>(), c->sortB.as<uint2>(), n, 22, 1024));
     float2* entryX = c->entry.as<float2>();
     float2* entryY = entryX + n1;
-    k_gather_entries<<<grid, kBlock, 0, c->stream>>>(n, c->sortB.as<uint2>(), c->aabb.as<float4>(), entryX, entryY, c->entryIndex.as<unsigned>());
+    PHYX_TRY(c->rowOf.reserve(n1 * sizeof(int)));
+    k_gather_entries<<<grid, kBlock, 0, c->stream>>>(n, c->sortB.as<uint2>(), c->aabb.as<float4>(), entryX, entryY, c->entryIndex.as<unsigned>(),
+        c->rowOf.as<int>());
     c->launches++;
+    c->rowOrderValid = true;
+    c->rowOrderBodies = n;
     PHYX_CUDA(cudaGetLastError());
     return PHYX_B200_OK;
 }

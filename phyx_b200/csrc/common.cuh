@@ -135,6 +135,11 @@ struct phyx_b200_ctx
     bool slotPosValid = false;
     phyx::DevBuf processed;      // int per slot: tick of the pass that ran it
     phyx::DevBuf solveFlags;     // productive flags + result words
+    phyx::DevBuf timeline;       // developer aid (PHYX_SOLVE_TIMELINE)
+    phyx::DevBuf solveRows;      // 2 x float4 per body: the solver's packed copy of the velocity / displacement rows
+    phyx::DevBuf rowOf;          // int per body: its row in the sorted-x order of the last broadphase
+    bool rowOrderValid = false;
+    int rowOrderBodies = 0;
     phyx::DevBuf colourTmp;      // colouring scratch
     phyx::DevBuf colourKeys, colourSorted;   // uint2 {colour, joint} before / after the counting sort
     bool hostSlotsStale = false; // schedule lives on the device only; get_schedule fetches it on demand

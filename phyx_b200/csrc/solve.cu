@@ -60,7 +60,18 @@ struct SolveParams
     unsigned long long* barrier;       // ring of 4 grid-barrier words
     int* result;                       // [0] impulse iterations run, [1] displacement iterations run, [2] extra wake passes
     unsigned long long* activeTotal;   // [2] joint-iterations relaxed (not skipped) per phase
+    unsigned long long* timeline;      // optional (PHYX_SOLVE_TIMELINE=1): globaltimer after every level barrier, CTA 0
 };
+
+__device__ __forceinline__ void timeline_mark(const SolveParams& P, int tick)
+{
+    if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0 && tick < 4096)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        P.timeline[tick] = t;
+    }
+}
 
 __device__ __forceinline__ float vmax(float l, float r) { return l > r ? l : r; }   // SIMD max: l>r?l:r
 
@@ -79,19 +90,39 @@ __device__ __forceinline__ void refresh_limiter(float n1x, float n1y, float w1x,
     cinv = (fabsf(c) > 0.0f) ? __fdiv_rn(1.0f, c) : 0.0f;
 }
 
-// ---- PrepareBodies, Solver.cpp:456-480: the only work left is lastIteration = -1 in both row sets ----
-__global__ void __launch_bounds__(kBlock) k_prepare_bodies(int n, float4* __restrict__ vel, float4* __restrict__ disp)
+// ---- PrepareBodies / FinishBodies, Solver.cpp:456-494 ---------------------------------------------------
+// Like the reference, the solve works on its own packed copy of the body rows {v, w, lastIteration}.
+// Here the copy is also the place to fix memory locality: rows are stored in the broadphase's
+// sorted-x order (order[i] = body at sorted position i), so joints that are neighbours in the slot
+// order (sweep order) gather neighbouring rows: the gather / scatter of body rows through L1 is what
+// bounds the iterations (one 32-byte sector per lane when the rows are scattered).
+__global__ void __launch_bounds__(kBlock) k_prepare_bodies(int n, const unsigned* __restrict__ order, const float4* __restrict__ vel,
+    const float4* __restrict__ disp, float4* __restrict__ rowsVel, float4* __restrict__ rowsDisp)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    reinterpret_cast<int*>(vel + i)[3] = -1;
-    reinterpret_cast<int*>(disp + i)[3] = -1;
+    const unsigned b = order ? order[i] : unsigned(i);
+    float4 v = vel[b], d = disp[b];
+    v.w = __int_as_float(-1);
+    d.w = __int_as_float(-1);
+    rowsVel[i] = v;
+    rowsDisp[i] = d;
+}
+
+__global__ void __launch_bounds__(kBlock) k_finish_bodies(int n, const unsigned* __restrict__ order, const float4* __restrict__ rowsVel,
+    const float4* __restrict__ rowsDisp, float4* __restrict__ vel, float4* __restrict__ disp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned b = order ? order[i] : unsigned(i);
+    vel[b] = rowsVel[i];
+    disp[b] = rowsDisp[i];
 }
 
 // ---- PrepareJoints copy + RefreshJoints ----------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __restrict__ slotJoint, const phyx_contact_joint* __restrict__ joints,
-    const float4* __restrict__ contactPoints, const float4* __restrict__ params, float4* __restrict__ q0, float4* __restrict__ q1,
-    float4* __restrict__ q2, float4* __restrict__ q3, float2* __restrict__ accNF, float* __restrict__ accD)
+    const float4* __restrict__ contactPoints, const float4* __restrict__ params, const int* __restrict__ rowOf, float4* __restrict__ q0,
+    float4* __restrict__ q1, float4* __restrict__ q2, float4* __restrict__ q3, float2* __restrict__ accNF, float* __restrict__ accD)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= numSlots) return;
@@ -126,8 +157,9 @@ __global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __r
     float tx = -ny, ty = nx;
     refresh_limiter(tx, ty, w1x, w1y, w2x, w2y, p1.x, p1.y, p2.x, p2.y, aF1, aF2, cinvF);
 
-    int b1 = jt.body1Index | ((p1.x == 0.0f && p1.y == 0.0f) ? kStaticBit : 0);
-    int b2 = jt.body2Index | ((p2.x == 0.0f && p2.y == 0.0f) ? kStaticBit : 0);
+    // the packed joint addresses the solver's row copy (rowOf: body -> row, see k_prepare_bodies)
+    int b1 = (rowOf ? rowOf[jt.body1Index] : jt.body1Index) | ((p1.x == 0.0f && p1.y == 0.0f) ? kStaticBit : 0);
+    int b2 = (rowOf ? rowOf[jt.body2Index] : jt.body2Index) | ((p2.x == 0.0f && p2.y == 0.0f) ? kStaticBit : 0);
 
     q0[s] = make_float4(nx, ny, aN1, aN2);
     q1[s] = make_float4(aF1, aF2, cinvF, dstVel);
@@ -466,6 +498,7 @@ __device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int ti
                 havePre = true;
             }
             BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
+            timeline_mark(P, tick);
             while (r.wake)
             {
                 SlotData<PHASE> scratch;
@@ -736,6 +769,7 @@ __device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, P
                 ++consumed;
             }
             BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
+            timeline_mark(P, tick);
             while (r.wake)
             {
                 SlotData<PHASE> scratch;
@@ -871,18 +905,25 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         PHYX_CUDA(cudaMemsetAsync(c->stamps.ptr, 0, size_t(nb) * 2 * sizeof(unsigned long long), c->stream));
         PHYX_CUDA(cudaMemsetAsync(c->solveFlags.ptr, 0, 64, c->stream));
         PHYX_CUDA(cudaMemsetAsync(c->processed.ptr, 0, size_t(ns) * sizeof(int), c->stream));
-        k_prepare_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, c->vel.as<float4>(), c->disp.as<float4>());
+        // solver rows in sorted-x order when this step's broadphase is available, else in body order
+        const bool sorted = c->rowOrderValid && c->rowOrderBodies == nb;
+        const unsigned* order = sorted ? c->entryIndex.as<unsigned>() : nullptr;
+        const int* rowOf = sorted ? c->rowOf.as<int>() : nullptr;
+        PHYX_TRY(c->solveRows.reserve(size_t(nb) * 2 * sizeof(float4)));
+        float4* rowsVel = c->solveRows.as<float4>();
+        float4* rowsDisp = rowsVel + nb;
+        k_prepare_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, c->vel.as<float4>(), c->disp.as<float4>(), rowsVel, rowsDisp);
         c->launches++;
         int grid = (ns + kBlock - 1) / kBlock;
         k_refresh<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
-            c->params.as<float4>(), c->q0.as<float4>(), c->q1.as<float4>(), c->q2.as<float4>(), c->q3.as<float4>(), c->accNF.as<float2>(),
+            c->params.as<float4>(), rowOf, c->q0.as<float4>(), c->q1.as<float4>(), c->q2.as<float4>(), c->q3.as<float4>(), c->accNF.as<float2>(),
             c->accD.as<float>());
         c->launches++;
         PHYX_CUDA(cudaEventRecord(e1, c->stream));
 
         SolveParams P;
-        P.vel = c->vel.as<float4>();
-        P.disp = c->disp.as<float4>();
+        P.vel = rowsVel;
+        P.disp = rowsDisp;
         P.q0 = c->q0.as<float4>();
         P.q1 = c->q1.as<float4>();
         P.q2 = c->q2.as<float4>();
@@ -900,6 +941,14 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         P.barrier = c->solveFlags.as<unsigned long long>();          // 4 words
         P.result = reinterpret_cast<int*>(c->solveFlags.as<char>() + 32);
         P.activeTotal = reinterpret_cast<unsigned long long*>(c->solveFlags.as<char>() + 48);
+        static const bool wantTimeline = getenv("PHYX_SOLVE_TIMELINE") != nullptr;
+        P.timeline = nullptr;
+        if (wantTimeline)
+        {
+            PHYX_TRY(c->timeline.reserve(4096 * 8));
+            PHYX_CUDA(cudaMemsetAsync(c->timeline.ptr, 0, 4096 * 8, c->stream));
+            P.timeline = c->timeline.as<unsigned long long>();
+        }
         if (c->solveBlocksPerSM == 0)
         {
             int per = 0;
@@ -942,13 +991,25 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         c->launches++;
         PHYX_CUDA(cudaEventRecord(e2, c->stream));
         k_finish<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->accNF.as<float2>(), c->joints.as<phyx_contact_joint>());
-        c->launches++;
+        k_finish_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, rowsVel, rowsDisp, c->vel.as<float4>(), c->disp.as<float4>());
+        c->launches += 2;
         PHYX_CUDA(cudaEventRecord(e3, c->stream));
         int host[8];   // result[0..2], pad, activeTotal[2] as two 64-bit words
         PHYX_CUDA(cudaMemcpyAsync(host, P.result, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
         PHYX_CUDA(cudaStreamSynchronize(c->stream));
         ranI = host[0];
         ranD = host[1];
+        if (wantTimeline)
+        {
+            // developer aid: per-level durations of the last solve on stderr
+            std::vector<unsigned long long> t(4096);
+            cudaMemcpy(t.data(), c->timeline.ptr, 4096 * 8, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[timeline] levels=%d:", nl);
+            for (int l = 0; l < nl; ++l) fprintf(stderr, " %d", c->hostLevels[l].end - c->hostLevels[l].start);
+            fprintf(stderr, "\n");
+            for (int k = 2; k < 4096 && t[k]; ++k)
+                if (k <= 3 * nl + 1 || k % (nl * 5) < nl) fprintf(stderr, "[timeline] tick %d (level %d): %.2f us\n", k, (k - 1) % nl, (t[k] - t[k - 1]) * 1e-3);
+        }
         wakePasses = host[2];
         if (stats)
         {
