@@ -965,18 +965,18 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         for (const Level& L : c->hostLevels) maxLevel = max(maxLevel, L.end - L.start);
         int want = (maxLevel + kBlock - 1) / kBlock;
         int sgrid = max(1, min(want, c->numSMs * c->solveBlocksPerSM));
-        // PHYX_SOLVE_KERNEL=direct selects the register-prefetch kernel; default is the TMA-staged one
-        // (PHYX_SOLVE_PIPE="<slots per thread><stages>", e.g. 23)
+        // Default: the register-prefetch kernel (fastest measured).  PHYX_SOLVE_KERNEL=pipe
+        // selects the TMA-staged one; PHYX_SOLVE_PIPE="<slots per thread><stages>" (e.g. 12, 23) its shape.
         static const char* kernelEnv = getenv("PHYX_SOLVE_KERNEL");
         static const char* pipeEnv = getenv("PHYX_SOLVE_PIPE");
-        if (kernelEnv && !strcmp(kernelEnv, "direct"))
+        if (!(kernelEnv && !strcmp(kernelEnv, "pipe")))
         {
             void* args[] = { &P };
             PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3(sgrid), dim3(kBlock), args, 0, c->stream));
         }
         else
         {
-            const int variant = pipeEnv ? atoi(pipeEnv) : 23;
+            const int variant = pipeEnv ? atoi(pipeEnv) : 12;
             switch (variant)
             {
             case 12: PHYX_TRY((launch_solve_pipe<1, 2>(c, P, maxLevel))); break;

@@ -103,3 +103,38 @@ def test_throughput_mode_stays_physical(ref):
     print(f"\ncolour-vs-AVX2 rel dpos {ours:.3e}; reference Scalar-vs-AVX2 {own_spread:.3e}")
     assert ours < max(3 * own_spread, 1e-2)
     assert abs(len(w.joints()) - len(r.joints())) < 0.02 * len(r.joints())
+
+
+@pytest.mark.parametrize("scene,steps", [("stack_100k", 12), ("pyramid_100k", 12)])
+def test_replay_parity_at_100k(ref, scene, steps):
+    """BASELINE configs[1] scale: the replay of the reference's AVX2 order stays bit-identical to the
+    reference on 100 k bodies (300-400 k joints), collider arrays included."""
+    sc = scenes.make(scene)
+    r = ref.RefWorld(sc, "strict")
+    w = world.World(sc)
+    levels = 0
+    for _ in range(steps):
+        r.step(solve=T.SOLVE_AVX2)
+        w.step(solve=T.SOLVE_AVX2)
+        levels = max(levels, w.solve_stats().levels)
+    rb, wb = r.bodies(), w.bodies()
+    dpos, dvel = rel_dev(wb, rb)
+    print(f"\n{scene}: {steps} steps, {len(w.joints())} joints, {levels} dependency levels, rel dpos {dpos:.3e} dvel {dvel:.3e}")
+    assert_records_equal(wb, rb, STATE, what="bodies")
+    assert_records_equal(w.joints(), r.joints(), what="joints")
+    assert_records_equal(w.manifolds(), r.manifolds(), what="manifolds")
+
+
+def test_full_pipeline_at_1m_matches_reference_for_three_steps(ref):
+    """BASELINE configs[2] scale (1 M-box pyramid, ~4 M joints): three replay steps, bit-identical."""
+    sc = scenes.make("pyramid_1m")
+    r = ref.RefWorld(sc, "strict")
+    w = world.World(sc, mirror_contents=False)
+    for _ in range(3):
+        r.step(solve=T.SOLVE_AVX2)
+        w.step(solve=T.SOLVE_AVX2)
+    rb, wb = r.bodies(), w.bodies()
+    assert len(w.joints()) == len(r.joints()) and len(w.manifolds()) == len(r.manifolds())
+    assert_records_equal(wb, rb, STATE, what="bodies")
+    ctx = w.context()
+    assert_records_equal(ctx.download_joints(), r.joints(), what="joints")
