@@ -106,6 +106,7 @@ struct phyx_b200_ctx
     phyx::DevBuf itemStart;      // int: first work item of body i (exclusive scan)
     phyx::DevBuf items;          // int2 {i, chunk}
     phyx::DevBuf itemCount;      // int per item -> exclusive scan = output offset
+    phyx::DevBuf tileLong;       // u8 per sweep tile: 1 = left to the item kernel
     phyx::DevBuf pairs;          // int2 output
     phyx::DevBuf counters;       // misc device scalars
     bool broadphaseValid = false;
