@@ -289,27 +289,38 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(int n, const int* 
         for (int j0 = i + 1; j0 < e; j0 += kChunk, ++item)
         {
             const int j1 = min(j0 + kChunk, e);
-            int count = 0;
-            for (int jb = j0; jb < j1; jb += 32)
+            // y test for the whole chunk first (bit t of `hits` = this lane's test in round t) ...
+            unsigned hits = 0;
+            for (int jb = j0, t = 0; jb < j1; jb += 32, ++t)
             {
                 const int j = jb + lane;
-                bool hit = false;
                 if (j < j1)
                 {
                     const float2 yj = tileY[j - first];
-                    hit = fabsf(yj.x - yi.x) <= yi.y + yj.y;   // Collider.cpp:309
+                    if (fabsf(yj.x - yi.x) <= yi.y + yj.y) hits |= 1u << t;   // Collider.cpp:309
                 }
-                if (FILTER)
-                {
-                    localHits += __popc(__ballot_sync(0xffffffffu, hit));
-                    if (hit) hit = !pair_contains(table, tableMask, pair_key(bi, entryIndex[j]));
-                }
-                count += __popc(__ballot_sync(0xffffffffu, hit));
             }
+            // ... then the cache lookups of the hits, all lanes' probes in flight together instead of
+            // stalling the scan once per hit
+            int count = __popc(hits);
+            if (FILTER)
+            {
+                localHits += count;
+                count = 0;
+                while (hits)
+                {
+                    const int t = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const int j = j0 + t * 32 + lane;
+                    if (!pair_contains(table, tableMask, pair_key(bi, entryIndex[j]))) ++count;
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
             if (lane == 0) itemCount[item] = count;
             localTests += (unsigned long long)(j1 - j0);
         }
     }
+    for (int o = 16; o > 0; o >>= 1) localHits += __shfl_xor_sync(0xffffffffu, localHits, o);
     if (lane == 0)
     {
         if (localTests) atomicAdd(&totals[0], localTests);
