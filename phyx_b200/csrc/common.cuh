@@ -141,6 +141,10 @@ struct phyx_b200_ctx
     phyx::DevBuf rowOf;          // int per body: its row in the sorted-x order of the last broadphase
     bool rowOrderValid = false;
     int rowOrderBodies = 0;
+    // strip order of the solver rows (locality.cu)
+    phyx::DevBuf locKeysA, locKeysB, locOrder, locRowOf, locStats;
+    bool locValid = false;
+    int locBodies = 0, locAge = 0;
     phyx::DevBuf colourTmp;      // colouring scratch
     phyx::DevBuf colourKeys, colourSorted;   // uint2 {colour, joint} before / after the counting sort
     bool hostSlotsStale = false; // schedule lives on the device only; get_schedule fetches it on demand
@@ -180,6 +184,9 @@ int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift,
 
 // colour.cu
 int colour_schedule_build(phyx_b200_ctx* c);
+
+// locality.cu
+int locality_order_update(phyx_b200_ctx* c);
 
 // schedule.cu
 int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int nj, int mode, int flags);

@@ -905,10 +905,15 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         PHYX_CUDA(cudaMemsetAsync(c->stamps.ptr, 0, size_t(nb) * 2 * sizeof(unsigned long long), c->stream));
         PHYX_CUDA(cudaMemsetAsync(c->solveFlags.ptr, 0, 64, c->stream));
         PHYX_CUDA(cudaMemsetAsync(c->processed.ptr, 0, size_t(ns) * sizeof(int), c->stream));
-        // solver rows in sorted-x order when this step's broadphase is available, else in body order
-        const bool sorted = c->rowOrderValid && c->rowOrderBodies == nb;
-        const unsigned* order = sorted ? c->entryIndex.as<unsigned>() : nullptr;
-        const int* rowOf = sorted ? c->rowOf.as<int>() : nullptr;
+        // memory order of the solver rows: strips (locality.cu), else the broadphase's sorted-x order,
+        // else body order.  PHYX_ROW_ORDER=sweep|body overrides (for A/B measurements).
+        static const char* orderEnv = getenv("PHYX_ROW_ORDER");
+        const bool wantStrips = !orderEnv, wantSweep = !orderEnv || !strcmp(orderEnv, "sweep");
+        if (wantStrips) PHYX_TRY(locality_order_update(c));
+        const bool strips = wantStrips && c->locValid && c->locBodies == nb;
+        const bool sorted = !strips && wantSweep && c->rowOrderValid && c->rowOrderBodies == nb;
+        const unsigned* order = strips ? c->locOrder.as<unsigned>() : sorted ? c->entryIndex.as<unsigned>() : nullptr;
+        const int* rowOf = strips ? c->locRowOf.as<int>() : sorted ? c->rowOf.as<int>() : nullptr;
         PHYX_TRY(c->solveRows.reserve(size_t(nb) * 2 * sizeof(float4)));
         float4* rowsVel = c->solveRows.as<float4>();
         float4* rowsDisp = rowsVel + nb;
