@@ -246,6 +246,9 @@ def run_ours(args, rank, world_size, local_rank):
         w.step(solve=world.SOLVE_B200, iters=ITERS)
         stage_ms_e2e = {k: round(v, 3) for k, v in w.stage_ms().items()}
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (k_solve: warm start + all iterations, one launch per step)
