@@ -516,10 +516,10 @@ __device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int ti
 }
 
 // Persistent cooperative kernel: the whole SolveJointIsland loop nest (Solver.cpp:159-211) in one launch.
-#ifndef PHYX_SOLVE_MIN_BLOCKS
-#define PHYX_SOLVE_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(kBlock, PHYX_SOLVE_MIN_BLOCKS) k_solve(SolveParams P)
+// THREADS x MIN_BLOCKS is the register budget: 256x4, 512x2 and 1024x1 all give 64 registers and
+// 1024 threads per SM; fewer, larger CTAs make the grid barrier cheaper (148 arrivals instead of 592).
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve(SolveParams P)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
@@ -955,10 +955,16 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
             PHYX_CUDA(cudaMemsetAsync(c->timeline.ptr, 0, 4096 * 8, c->stream));
             P.timeline = c->timeline.as<unsigned long long>();
         }
+        // CTA shape of the direct kernel: PHYX_SOLVE_BLOCK = 256 | 512 | 1024 (default 1024, one CTA per SM)
+        static const int blockEnv = getenv("PHYX_SOLVE_BLOCK") ? atoi(getenv("PHYX_SOLVE_BLOCK")) : 1024;
+        const int sblock = blockEnv == 256 ? 256 : blockEnv == 512 ? 512 : 1024;
+        void* solveKernel = sblock == 256 ? (void*)k_solve<256, 4> : sblock == 512 ? (void*)k_solve<512, 2> : (void*)k_solve<1024, 1>;
         if (c->solveBlocksPerSM == 0)
         {
             int per = 0;
-            PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_solve, kBlock, 0));
+            if (sblock == 256) PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_solve<256, 4>, 256, 0));
+            else if (sblock == 512) PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_solve<512, 2>, 512, 0));
+            else PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_solve<1024, 1>, 1024, 0));
             if (per < 1)
             {
                 set_error("solve kernel does not fit on an SM");
@@ -969,7 +975,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         // persistent grid: every SM full, but no more CTAs than the widest level can use
         int maxLevel = 0;
         for (const Level& L : c->hostLevels) maxLevel = max(maxLevel, L.end - L.start);
-        int want = (maxLevel + kBlock - 1) / kBlock;
+        int want = (maxLevel + sblock - 1) / sblock;
         int sgrid = max(1, min(want, c->numSMs * c->solveBlocksPerSM));
         // Default: the register-prefetch kernel (fastest measured).  PHYX_SOLVE_KERNEL=pipe
         // selects the TMA-staged one; PHYX_SOLVE_PIPE="<slots per thread><stages>" (e.g. 12, 23) its shape.
@@ -978,7 +984,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         if (!(kernelEnv && !strcmp(kernelEnv, "pipe")))
         {
             void* args[] = { &P };
-            PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3(sgrid), dim3(kBlock), args, 0, c->stream));
+            PHYX_CUDA(cudaLaunchCooperativeKernel(solveKernel, dim3(sgrid), dim3(sblock), args, 0, c->stream));
         }
         else
         {
