@@ -955,8 +955,8 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
             PHYX_CUDA(cudaMemsetAsync(c->timeline.ptr, 0, 4096 * 8, c->stream));
             P.timeline = c->timeline.as<unsigned long long>();
         }
-        // CTA shape of the direct kernel: PHYX_SOLVE_BLOCK = 256 | 512 | 1024 (default 1024, one CTA per SM)
-        static const int blockEnv = getenv("PHYX_SOLVE_BLOCK") ? atoi(getenv("PHYX_SOLVE_BLOCK")) : 1024;
+        // CTA shape of the direct kernel: PHYX_SOLVE_BLOCK = 256 | 512 | 1024 (default 512: measured 2.37 ms vs 2.40 / 2.44 ms)
+        static const int blockEnv = getenv("PHYX_SOLVE_BLOCK") ? atoi(getenv("PHYX_SOLVE_BLOCK")) : 512;
         const int sblock = blockEnv == 256 ? 256 : blockEnv == 512 ? 512 : 1024;
         void* solveKernel = sblock == 256 ? (void*)k_solve<256, 4> : sblock == 512 ? (void*)k_solve<512, 2> : (void*)k_solve<1024, 1>;
         if (c->solveBlocksPerSM == 0)
