@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(kBlock) k_radix_scatter(const uint2* __restric
         }
         old = __shfl_sync(0xffffffffu, old, leader);
         packed[k] = d | ((old + before) << 11);
+        __syncwarp();   // the next chunk's leaders read counters other lanes just wrote
     }
     __syncthreads();
     for (int d = threadIdx.x; d < digits; d += kBlock)
