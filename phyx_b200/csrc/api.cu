@@ -179,7 +179,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
-        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->jointColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->timeline, &c->tileLong, &c->locKeysA, &c->locKeysB, &c->locOrder, &c->locRowOf, &c->locStats };
+        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->jointColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->timeline, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->locKeysA, &c->locKeysB, &c->locOrder, &c->locRowOf, &c->locStats };
     for (DevBuf* b : bufs) b->release();
     c->pinned.release();
     for (auto& ev : c->ev)

@@ -262,6 +262,7 @@ static int colour_schedule_build_once(phyx_b200_ctx* c, bool incremental, bool* 
     c->hostLevels.clear();
     c->slotPosValid = false;
     c->slotCount = c->levelCount = 0;
+    c->strictLevelCount = c->numMultiStatics = 0;
     if (nj == 0) return PHYX_B200_OK;
 
     const size_t nb1 = size_t(nb > 0 ? nb : 1);

@@ -135,6 +135,10 @@ struct phyx_b200_ctx
     phyx::DevBuf slotPos;        // int per slot: sequential position of the slot's unit (replay schedules)
     bool slotPosValid = false;
     phyx::DevBuf processed;      // int per slot: tick of the pass that ran it
+    // strict companion of a replay schedule (schedule.cu StaticRule): used for iterations in which a static
+    // body with several joints starts "cold"
+    phyx::DevBuf strictLevels, strictMap, staticMulti, rowsMulti;
+    int strictLevelCount = 0, numMultiStatics = 0;
     phyx::DevBuf solveFlags;     // productive flags + result words
     phyx::DevBuf timeline;       // developer aid (PHYX_SOLVE_TIMELINE)
     phyx::DevBuf solveRows;      // 2 x float4 per body: the solver's packed copy of the velocity / displacement rows

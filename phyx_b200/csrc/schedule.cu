@@ -67,20 +67,31 @@ struct Unit
     int first, width, level;   // order[first .. first+width)
 };
 
-void build_replay(const phyx_contact_joint* joints, int nj, int nb, const std::vector<unsigned char>& statics, int N, bool staticDeps,
-    std::vector<int>& slots, std::vector<int>& slotPos, std::vector<Level>& levels)
+// How static bodies enter the level assignment of a replay schedule.
+enum StaticRule
 {
-    std::vector<int> order;
+    kStaticsFree = 0,       // ignored: joints on a static body are unordered among themselves (fast schedule)
+    kStaticsOrdered = 1,    // joints of one static body sit on non-decreasing levels in sequential order (strict
+                            // schedule: exact under every lastIteration state, but levels ratchet along e.g. the
+                            // ground's contacts)
+    kStaticsSerial = 2      // strictly increasing levels (PHYX_B200_SOLVE_STATIC_DEPS; cross-check only)
+};
+
+// reference order -> units (SIMD groups first, then the scalar tail)
+void reference_units(const phyx_contact_joint* joints, int nj, int nb, int N, std::vector<int>& order, std::vector<Unit>& units)
+{
     int groupOffset = reference_order(joints, nj, nb, N, order);
-    std::vector<Unit> units;
+    units.clear();
     units.reserve(size_t(groupOffset / std::max(N, 1)) + size_t(nj - groupOffset));
     for (int g = 0; N > 1 && g < groupOffset; g += N) units.push_back({ g, N, 0 });
     for (int i = groupOffset; i < nj; ++i) units.push_back({ i, 1, 0 });
+}
 
-    // bodyLevel[b]: earliest level the next unit on body b may take.  A dynamic body forces a
-    // strictly later level (its velocity row is read-modify-written); a static body only forces a
-    // level that is not earlier (its joints may share a level, but must not overtake each other:
-    // see "static bodies" in solve.cu), unless staticDeps asks for the strict order there too.
+// Dependency levels + slot layout.  bodyLevel[b] is the earliest level the next unit on body b may take:
+// a dynamic body forces a strictly later level (its velocity row is read-modify-written).
+void layout_replay(const phyx_contact_joint* joints, int nb, const std::vector<unsigned char>& statics, const std::vector<int>& order,
+    std::vector<Unit>& units, StaticRule rule, std::vector<int>& slots, std::vector<int>& slotPos, std::vector<Level>& levels)
+{
     std::vector<int> bodyLevel(nb, 0);
     int maxLevel = 0;
     for (Unit& u : units)
@@ -89,14 +100,15 @@ void build_replay(const phyx_contact_joint* joints, int nj, int nb, const std::v
         for (int k = 0; k < u.width; ++k)
         {
             const phyx_contact_joint& j = joints[order[u.first + k]];
-            lvl = std::max(lvl, std::max(bodyLevel[j.body1Index], bodyLevel[j.body2Index]));
+            if (rule != kStaticsFree || !statics[j.body1Index]) lvl = std::max(lvl, bodyLevel[j.body1Index]);
+            if (rule != kStaticsFree || !statics[j.body2Index]) lvl = std::max(lvl, bodyLevel[j.body2Index]);
         }
         u.level = lvl;   // 0-based level of this unit
         for (int k = 0; k < u.width; ++k)
         {
             const phyx_contact_joint& j = joints[order[u.first + k]];
-            bodyLevel[j.body1Index] = lvl + ((staticDeps || !statics[j.body1Index]) ? 1 : 0);
-            bodyLevel[j.body2Index] = lvl + ((staticDeps || !statics[j.body2Index]) ? 1 : 0);
+            bodyLevel[j.body1Index] = lvl + ((rule == kStaticsSerial || !statics[j.body1Index]) ? 1 : 0);
+            bodyLevel[j.body2Index] = lvl + ((rule == kStaticsSerial || !statics[j.body2Index]) ? 1 : 0);
         }
         maxLevel = std::max(maxLevel, lvl + 1);
     }
@@ -253,13 +265,68 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
     slots.clear();
     slotPos.clear();
     levels.clear();
+    // strict companion of a replay schedule (see StaticRule): S position -> slot of the fast schedule
+    std::vector<int> strictMap;
+    std::vector<Level> strictLevels;
+    std::vector<unsigned char> multi;
+    int numMulti = 0;
+    const int N = mode == PHYX_B200_SCHEDULE_REPLAY_AVX2 ? 8 : mode == PHYX_B200_SCHEDULE_REPLAY_SSE2 ? 4 : 1;
     switch (mode)
     {
     case PHYX_B200_SCHEDULE_COLOUR: build_colours(hostJoints, nj, nb, statics, slots, levels); break;
-    case PHYX_B200_SCHEDULE_REPLAY_AVX2: build_replay(hostJoints, nj, nb, statics, 8, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, slotPos, levels); break;
-    case PHYX_B200_SCHEDULE_REPLAY_SSE2: build_replay(hostJoints, nj, nb, statics, 4, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, slotPos, levels); break;
-    case PHYX_B200_SCHEDULE_REPLAY_SCALAR: build_replay(hostJoints, nj, nb, statics, 1, flags & PHYX_B200_SOLVE_STATIC_DEPS, slots, slotPos, levels); break;
+    case PHYX_B200_SCHEDULE_REPLAY_AVX2:
+    case PHYX_B200_SCHEDULE_REPLAY_SSE2:
+    case PHYX_B200_SCHEDULE_REPLAY_SCALAR:
+    {
+        std::vector<int> order;
+        std::vector<Unit> units;
+        reference_units(hostJoints, nj, nb, N, order, units);
+        if (flags & PHYX_B200_SOLVE_STATIC_DEPS)
+        {
+            layout_replay(hostJoints, nb, statics, order, units, kStaticsSerial, slots, slotPos, levels);
+            break;
+        }
+        // static bodies with at least two units: the only ones whose lastIteration couples joints
+        std::vector<int> unitsOn(size_t(nb > 0 ? nb : 1), 0);
+        for (const Unit& u : units)
+            for (int k = 0; k < u.width; ++k)
+            {
+                const phyx_contact_joint& j = hostJoints[order[u.first + k]];
+                if (statics[j.body1Index]) unitsOn[j.body1Index]++;
+                if (statics[j.body2Index]) unitsOn[j.body2Index]++;
+            }
+        multi.assign(size_t(nb > 0 ? nb : 1), 0);
+        for (int b = 0; b < nb; ++b)
+            if (unitsOn[b] >= 2)
+            {
+                multi[b] = 1;
+                ++numMulti;
+            }
+        layout_replay(hostJoints, nb, statics, order, units, kStaticsFree, slots, slotPos, levels);
+        if (numMulti > 0)
+        {
+            std::vector<int> strictSlots, strictPos;
+            layout_replay(hostJoints, nb, statics, order, units, kStaticsOrdered, strictSlots, strictPos, strictLevels);
+            std::vector<int> slotOfJoint(size_t(nj > 0 ? nj : 1), -1);
+            for (size_t k = 0; k < slots.size(); ++k)
+                if (slots[k] >= 0) slotOfJoint[slots[k]] = int(k);
+            strictMap.resize(strictSlots.size());
+            for (size_t k = 0; k < strictSlots.size(); ++k) strictMap[k] = strictSlots[k] >= 0 ? slotOfJoint[strictSlots[k]] : -1;
+        }
+        break;
+    }
     default: set_error("solve: unknown schedule %d", mode); return PHYX_B200_ERR_ARGUMENT;
+    }
+    c->strictLevelCount = int(strictLevels.size());
+    c->numMultiStatics = numMulti;
+    if (!strictLevels.empty())
+    {
+        PHYX_TRY(c->strictLevels.reserve(strictLevels.size() * sizeof(Level)));
+        PHYX_TRY(c->strictMap.reserve(strictMap.size() * sizeof(int)));
+        PHYX_TRY(c->staticMulti.reserve(multi.size()));
+        PHYX_CUDA(cudaMemcpyAsync(c->strictLevels.ptr, strictLevels.data(), strictLevels.size() * sizeof(Level), cudaMemcpyHostToDevice, c->stream));
+        PHYX_CUDA(cudaMemcpyAsync(c->strictMap.ptr, strictMap.data(), strictMap.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        PHYX_CUDA(cudaMemcpyAsync(c->staticMulti.ptr, multi.data(), multi.size(), cudaMemcpyHostToDevice, c->stream));
     }
     c->slotCount = int(slots.size());
     c->levelCount = int(levels.size());

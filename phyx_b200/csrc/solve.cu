@@ -61,6 +61,13 @@ struct SolveParams
     int* result;                       // [0] impulse iterations run, [1] displacement iterations run, [2] extra wake passes
     unsigned long long* activeTotal;   // [2] joint-iterations relaxed (not skipped) per phase
     unsigned long long* timeline;      // optional (PHYX_SOLVE_TIMELINE=1): globaltimer after every level barrier, CTA 0
+    // strict companion schedule of a replay (schedule.cu StaticRule); numStrictLevels == 0: single schedule
+    const Level* strictLevels;
+    int numStrictLevels;
+    const int* strictMap;              // strict position -> slot (or -1)
+    const unsigned char* rowsMulti;    // per body row: static body with at least two units
+    int numMultiStatics;
+    int* hotCount;                     // [2 phases][4]: multi-unit static bodies productive in iteration it, at [it % 3]
 };
 
 __device__ __forceinline__ void timeline_mark(const SolveParams& P, int tick)
@@ -97,11 +104,13 @@ __device__ __forceinline__ void refresh_limiter(float n1x, float n1y, float w1x,
 // order (sweep order) gather neighbouring rows: the gather / scatter of body rows through L1 is what
 // bounds the iterations (one 32-byte sector per lane when the rows are scattered).
 __global__ void __launch_bounds__(kBlock) k_prepare_bodies(int n, const unsigned* __restrict__ order, const float4* __restrict__ vel,
-    const float4* __restrict__ disp, float4* __restrict__ rowsVel, float4* __restrict__ rowsDisp)
+    const float4* __restrict__ disp, float4* __restrict__ rowsVel, float4* __restrict__ rowsDisp, const unsigned char* __restrict__ multi,
+    unsigned char* __restrict__ rowsMulti)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned b = order ? order[i] : unsigned(i);
+    if (multi) rowsMulti[i] = multi[b];
     float4 v = vel[b], d = disp[b];
     v.w = __int_as_float(-1);
     d.w = __int_as_float(-1);
@@ -207,7 +216,7 @@ __device__ __forceinline__ int static_visible_last(const unsigned long long* p, 
 
 // Record "productive at (it, pos)".  Returns true if this changed the word while the body was cold
 // (its carried-over lastIteration <= it-2), i.e. if it can wake up later joints of the same level.
-__device__ __forceinline__ bool static_mark(unsigned long long* p, int it, unsigned pos)
+__device__ __forceinline__ bool static_mark(unsigned long long* p, int it, unsigned pos, int* hotCounter)
 {
     unsigned long long old = __ldcg(p);
     for (;;)
@@ -227,7 +236,12 @@ __device__ __forceinline__ bool static_mark(unsigned long long* p, int it, unsig
             carried = int(latest) - 1;
         }
         unsigned long long seen = atomicCAS(p, old, nw);
-        if (seen == old) return carried <= it - 2;
+        if (seen == old)
+        {
+            // first productive joint on this body in this iteration: it will be "hot" in the next one
+            if (hotCounter && latest != unsigned(it + 1)) atomicAdd(hotCounter, 1);
+            return carried <= it - 2;
+        }
         old = seen;
     }
 }
@@ -391,19 +405,26 @@ __device__ __forceinline__ void load_slot(const SolveParams& P, int s, bool inRa
 // pass turned a cold static body productive.  `pre` holds the streams of this thread's first slot
 // when havePre is set.
 template <int PHASE>
-__device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L, int it, int tick, bool firstPass, int tid, int nthreads, bool& wake,
-    unsigned& activeCount, SlotData<PHASE>& pre, bool havePre)
+__device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L, const int* __restrict__ slotMap, int it, int tick, bool firstPass, int tid,
+    int nthreads, bool& wake, unsigned& activeCount, SlotData<PHASE>& pre, bool havePre)
 {
     float4* rows = PHASE == 0 ? P.vel : P.disp;
     unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
+    int* hotCounter = P.hotCount ? P.hotCount + PHASE * 4 + (it % 3) : nullptr;
     const int lane = threadIdx.x & 31;
     const unsigned seg = 0xffu << (lane & ~7);   // the 8-lane unit this lane belongs to
     bool anyProductive = false;
 
     for (int s0 = L.start + (tid & ~31); s0 < L.end; s0 += nthreads)   // warp-uniform trip count
     {
-        const int s = s0 + lane;
-        bool valid = s < L.end;
+        const int k = s0 + lane;   // position in the level; the slot it names goes through slotMap if there is one
+        bool valid = k < L.end;
+        int s = k;
+        if (slotMap && valid)
+        {
+            s = slotMap[k];
+            valid = s >= 0;
+        }
         if (!havePre) load_slot<PHASE>(P, s, valid, pre);
         havePre = false;
         const float4 c3 = pre.c3;
@@ -411,7 +432,7 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
         valid = valid && r1 >= 0;
         const int b1 = r1 & kBodyMask, b2 = r2 & kBodyMask;
         const bool st1 = valid && (r1 & kStaticBit), st2 = valid && (r2 & kStaticBit);
-        const bool wide = s < L.grouped_end;
+        const bool wide = k < L.grouped_end;
 
         // units with a static body are the only ones a wake pass can affect
         const unsigned mStatic = __ballot_sync(0xffffffffu, st1 || st2);
@@ -456,14 +477,14 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
                 __stcg(&rows[b1], v1);
             }
             else if (productive)
-                wake |= static_mark(&statics[b1], it, pos);
+                wake |= static_mark(&statics[b1], it, pos, (P.rowsMulti && P.rowsMulti[b1]) ? hotCounter : nullptr);
             if (!st2)
             {
                 v2.w = __int_as_float(productive ? it : last2);
                 __stcg(&rows[b2], v2);
             }
             else if (productive)
-                wake |= static_mark(&statics[b2], it, pos);
+                wake |= static_mark(&statics[b2], it, pos, (P.rowsMulti && P.rowsMulti[b2]) ? hotCounter : nullptr);
             if (unitHasStatic) __stcg(&P.processed[s], tick);
         }
         anyProductive |= productive;
@@ -480,21 +501,47 @@ __device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int ti
     SlotData<PHASE> pre;
     bool havePre = false;
     int ran = 0;
+    const bool dual = P.numStrictLevels > 0;
+    int* hot = P.hotCount ? P.hotCount + PHASE * 4 : nullptr;
     for (int it = 0; it < iters; ++it)
     {
-        bool any = false, productiveAnywhere = false;
-        for (int l = 0; l < P.numLevels; ++l)
+        // Replay schedules come in two forms (schedule.cu StaticRule).  The fast one ignores static bodies
+        // and is exact whenever every static body with several joints is "hot" (was productive in the
+        // previous iteration: then all its joints are active whatever their order; iteration 0 is always
+        // hot).  Otherwise this iteration runs on the strict form.
+        bool strict = false;
+        if (dual)
         {
-            const Level L = P.levels[l];
+            if (it > 0) strict = __ldcg(&hot[(it - 1) % 3]) < P.numMultiStatics;
+            if (tid == 0) hot[(it + 1) % 3] = 0;
+            havePre = false;   // the slot prefetched across the iteration boundary may belong to the other form
+        }
+        const Level* levels = strict ? P.strictLevels : P.levels;
+        const int numLevels = strict ? P.numStrictLevels : P.numLevels;
+        const int* slotMap = strict ? P.strictMap : nullptr;
+
+        bool any = false, productiveAnywhere = false;
+        for (int l = 0; l < numLevels; ++l)
+        {
+            const Level L = levels[l];
             ++tick;
             bool wake = false;
-            any |= solve_level<PHASE>(P, L, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre);
+            any |= solve_level<PHASE>(P, L, slotMap, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre);
             // streams of this thread's first slot in the level that follows (next level, or level 0 of
             // the next iteration), fetched while the grid drains into the barrier
+            havePre = false;
+            if (l + 1 < numLevels || !dual)
             {
-                const Level N = P.levels[l + 1 < P.numLevels ? l + 1 : 0];
-                const int sN = N.start + tid;
-                load_slot<PHASE>(P, sN, sN < N.end, pre);
+                const Level N = levels[l + 1 < numLevels ? l + 1 : 0];
+                const int kN = N.start + tid;
+                bool inRange = kN < N.end;
+                int sN = kN;
+                if (slotMap && inRange)
+                {
+                    sN = slotMap[kN];
+                    inRange = sN >= 0;
+                }
+                load_slot<PHASE>(P, sN, inRange, pre);
                 havePre = true;
             }
             BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
@@ -503,13 +550,14 @@ __device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int ti
             {
                 SlotData<PHASE> scratch;
                 wake = false;
-                any |= solve_level<PHASE>(P, L, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
+                any |= solve_level<PHASE>(P, L, slotMap, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
                 ++wakePasses;
                 r = grid_barrier(P.barrier, epoch, wake, any);
             }
             productiveAnywhere = r.productive;
         }
         ++ran;
+        if (strict) ++wakePasses;   // reported together: iterations that needed the strict form
         if (!productiveAnywhere) break;   // Solver.cpp:189 / :210
     }
     return ran;
@@ -754,14 +802,14 @@ __device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, P
                         __stcg(&rows[x.b1], x.v1);
                     }
                     else if (productive)
-                        wake |= static_mark(&statics[x.b1], it, x.pos);
+                        wake |= static_mark(&statics[x.b1], it, x.pos, nullptr);
                     if (!x.st2)
                     {
                         x.v2.w = __int_as_float(productive ? it : x.last2);
                         __stcg(&rows[x.b2], x.v2);
                     }
                     else if (productive)
-                        wake |= static_mark(&statics[x.b2], it, x.pos);
+                        wake |= static_mark(&statics[x.b2], it, x.pos, nullptr);
                     if (x.unitHasStatic) __stcg(&P.processed[x.s], tick);
                     any |= productive;
                 }
@@ -774,7 +822,7 @@ __device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, P
             {
                 SlotData<PHASE> scratch;
                 wake = false;
-                any |= solve_level<PHASE>(P, L, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
+                any |= solve_level<PHASE>(P, L, nullptr, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
                 ++wakePasses;
                 r = grid_barrier(P.barrier, epoch, wake, any);
             }
@@ -895,7 +943,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
     }
     PHYX_TRY(c->stamps.reserve(size_t(nb > 0 ? nb : 1) * 2 * sizeof(unsigned long long)));
     PHYX_TRY(c->processed.reserve(ns1 * sizeof(int)));
-    PHYX_TRY(c->solveFlags.reserve(64));
+    PHYX_TRY(c->solveFlags.reserve(128));
 
     cudaEvent_t e0 = c->ev[0], e1 = c->ev[1], e2 = c->ev[2], e3 = c->ev[3];
     PHYX_CUDA(cudaEventRecord(e0, c->stream));
@@ -903,7 +951,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
     if (ns > 0 && nl > 0)
     {
         PHYX_CUDA(cudaMemsetAsync(c->stamps.ptr, 0, size_t(nb) * 2 * sizeof(unsigned long long), c->stream));
-        PHYX_CUDA(cudaMemsetAsync(c->solveFlags.ptr, 0, 64, c->stream));
+        PHYX_CUDA(cudaMemsetAsync(c->solveFlags.ptr, 0, 128, c->stream));
         PHYX_CUDA(cudaMemsetAsync(c->processed.ptr, 0, size_t(ns) * sizeof(int), c->stream));
         // memory order of the solver rows: the broadphase's sorted-x order (default; measured best:
         // k_solve 2.40 ms vs 2.71 ms for strips and 3.08 ms for body order on the 1 M pyramid), else body
@@ -918,7 +966,10 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         PHYX_TRY(c->solveRows.reserve(size_t(nb) * 2 * sizeof(float4)));
         float4* rowsVel = c->solveRows.as<float4>();
         float4* rowsDisp = rowsVel + nb;
-        k_prepare_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, c->vel.as<float4>(), c->disp.as<float4>(), rowsVel, rowsDisp);
+        const bool dual = c->strictLevelCount > 0 && c->slotPosValid;
+        if (dual) PHYX_TRY(c->rowsMulti.reserve(size_t(nb)));
+        k_prepare_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, c->vel.as<float4>(), c->disp.as<float4>(), rowsVel, rowsDisp,
+            dual ? c->staticMulti.as<unsigned char>() : nullptr, dual ? c->rowsMulti.as<unsigned char>() : nullptr);
         c->launches++;
         int grid = (ns + kBlock - 1) / kBlock;
         k_refresh<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
@@ -947,6 +998,12 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         P.barrier = c->solveFlags.as<unsigned long long>();          // 4 words
         P.result = reinterpret_cast<int*>(c->solveFlags.as<char>() + 32);
         P.activeTotal = reinterpret_cast<unsigned long long*>(c->solveFlags.as<char>() + 48);
+        P.strictLevels = dual ? c->strictLevels.as<Level>() : nullptr;
+        P.numStrictLevels = dual ? c->strictLevelCount : 0;
+        P.strictMap = dual ? c->strictMap.as<int>() : nullptr;
+        P.rowsMulti = dual ? c->rowsMulti.as<unsigned char>() : nullptr;
+        P.numMultiStatics = dual ? c->numMultiStatics : 0;
+        P.hotCount = dual ? reinterpret_cast<int*>(c->solveFlags.as<char>() + 64) : nullptr;
         static const bool wantTimeline = getenv("PHYX_SOLVE_TIMELINE") != nullptr;
         P.timeline = nullptr;
         if (wantTimeline)
@@ -981,7 +1038,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         // selects the TMA-staged one; PHYX_SOLVE_PIPE="<slots per thread><stages>" (e.g. 12, 23) its shape.
         static const char* kernelEnv = getenv("PHYX_SOLVE_KERNEL");
         static const char* pipeEnv = getenv("PHYX_SOLVE_PIPE");
-        if (!(kernelEnv && !strcmp(kernelEnv, "pipe")))
+        if (dual || !(kernelEnv && !strcmp(kernelEnv, "pipe")))   // the strict companion schedule is a direct-kernel feature
         {
             void* args[] = { &P };
             PHYX_CUDA(cudaLaunchCooperativeKernel(solveKernel, dim3(sgrid), dim3(sblock), args, 0, c->stream));
