@@ -72,6 +72,25 @@ def multi_island(count, rows, pitch=21.0, ground_half_width=1e7):
     return body
 
 
+def tumble(count, seed=12345, ground_half_width=1e7):
+    """Boxes of mixed sizes dropped at mixed angles in a loose pile (deterministic LCG, no RNG module):
+    exercises the vertex-face / vertex-vertex branches of the narrowphase that axis-aligned stacks never
+    reach (reference src/Collider.cpp:122-160), plus manifold churn (pairs appear and disappear)."""
+    body = np.zeros((count + 1, 6), dtype=np.float32)
+    body[0] = (0.0, 0.0, 0.0, ground_half_width, 10.0, 1.0)
+    s = seed
+    cols = max(int(np.sqrt(count)), 1)
+    for i in range(count):
+        vals = []
+        for _ in range(4):
+            s = (s * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+            vals.append(((s >> 33) & 0xFFFFFF) / float(1 << 24))
+        cx, cy = i % cols, i // cols
+        body[i + 1] = ((cx - cols / 2) * 26.0 + (vals[0] - 0.5) * 8.0, 30.0 + cy * 24.0 + vals[1] * 6.0, (vals[2] - 0.5) * 2.4,
+                       6.0 + 6.0 * vals[3], 4.0 + 3.0 * vals[0], 0.0)
+    return body
+
+
 SCENES = {
     # BASELINE.json configs[0..4]
     "pyramid_1k": lambda: pyramid_fast(45),
@@ -87,6 +106,8 @@ SCENES = {
     "stack_10k": lambda: stack(1000, 10),
     "islands_8x10": lambda: multi_island(8, 10),
     "islands_64x20": lambda: multi_island(64, 20),
+    "tumble_300": lambda: tumble(300),
+    "tumble_3k": lambda: tumble(3000),
 }
 
 

@@ -31,7 +31,8 @@ def ctx():
     c.close()
 
 
-@pytest.mark.parametrize("scene,steps", [("pyramid_10", (0, 1, 2, 7, 30)), ("pyramid_1k", (0, 1, 3, 25)), ("stack_1k", (0, 2, 40, 41)), ("islands_8x10", (0, 5))])
+@pytest.mark.parametrize("scene,steps", [("pyramid_10", (0, 1, 2, 7, 30)), ("pyramid_1k", (0, 1, 3, 25)), ("stack_1k", (0, 2, 40, 41)), ("islands_8x10", (0, 5)),
+                                          ("tumble_300", (0, 10, 35, 36, 80))])
 def test_each_resident_stage_matches_reference(ctx, ref, scene, steps):
     r = ref.RefWorld(scenes.make(scene), "strict")
     for step in range(max(steps) + 1):

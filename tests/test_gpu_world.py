@@ -31,6 +31,9 @@ def rel_dev(a, b):
     ("pyramid_1k", 40, T.SOLVE_SCALAR, 0),
     ("stack_1k", 100, T.SOLVE_AVX2, 0),
     ("islands_8x10", 100, T.SOLVE_AVX2, 0),
+    ("tumble_300", 150, T.SOLVE_AVX2, 0),      # rotated boxes: every narrowphase branch, manifold churn
+    ("tumble_300", 60, T.SOLVE_SCALAR, 0),
+    ("tumble_3k", 80, T.SOLVE_AVX2, 0),
 ])
 def test_world_update_tracks_reference(ref, scene, steps, mode, flags):
     sc = scenes.make(scene)
