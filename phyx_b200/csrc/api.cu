@@ -64,25 +64,6 @@ void DevBuf::release()
     cap = 0;
 }
 
-int HostBuf::reserve(size_t bytes)
-{
-    if (bytes <= cap) return PHYX_B200_OK;
-    size_t want = std::max(bytes, cap + cap / 2);
-    void* p = nullptr;
-    PHYX_CUDA(cudaMallocHost(&p, want));
-    if (ptr) cudaFreeHost(ptr);
-    ptr = p;
-    cap = want;
-    return PHYX_B200_OK;
-}
-
-void HostBuf::release()
-{
-    if (ptr) cudaFreeHost(ptr);
-    ptr = nullptr;
-    cap = 0;
-}
-
 static int check(phyx_b200_ctx* c)
 {
     if (!c)
@@ -181,7 +162,6 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
         &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->jointColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->timeline, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->locKeysA, &c->locKeysB, &c->locOrder, &c->locRowOf, &c->locStats };
     for (DevBuf* b : bufs) b->release();
-    c->pinned.release();
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kBlock) k_append_manifolds(int count, const in
     int2 p = pairs[k];
     manBody[first + k] = p;        // Manifold(index_i, index_j, size*2): pointIndex is implicit (2*m)
     manCount[first + k] = 0;
-    pair_insert(table, mask, pair_key(unsigned(p.x), unsigned(p.y)));
+    if (table) pair_insert(table, mask, pair_key(unsigned(p.x), unsigned(p.y)));
 }
 
 __global__ void __launch_bounds__(kBlock) k_table_insert(int count, const int2* __restrict__ manBody, unsigned long long* __restrict__ table, size_t mask)
@@ -82,26 +82,19 @@ int collide_rebuild_pair_table(phyx_b200_ctx* c)
 int collide_update_pairs(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
 {
     PHYX_TRY(broadphase_sweep(c, stats, true));
-    int fresh = int(c->lastNewPairs);
+    const int fresh = int(c->lastNewPairs);
     if (fresh == 0) return PHYX_B200_OK;
-    // keep the table sparse enough for the additions
-    if (size_t(c->manifoldCount + fresh) * 2 > c->pairTableSlots)
-    {
-        PHYX_TRY(reserve_manifolds(c, c->manifoldCount + fresh));
-        k_append_manifolds<<<(fresh + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(fresh, c->pairs.as<int2>(), c->manifoldCount, c->manBody.as<int2>(),
-            c->manCount.as<int>(), c->pairTable.as<unsigned long long>(), c->pairTableSlots - 1);
-        c->launches++;
-        c->manifoldCount += fresh;
-        c->contactPointCount = 2 * c->manifoldCount;
-        return collide_rebuild_pair_table(c);
-    }
     PHYX_TRY(reserve_manifolds(c, c->manifoldCount + fresh));
+    // the table must stay sparse (linear probing never terminates on a full table): if the additions
+    // would push it past half full, append without inserting and rebuild it at the right size
+    const bool rebuild = size_t(c->manifoldCount + fresh) * 2 > c->pairTableSlots;
     k_append_manifolds<<<(fresh + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(fresh, c->pairs.as<int2>(), c->manifoldCount, c->manBody.as<int2>(),
-        c->manCount.as<int>(), c->pairTable.as<unsigned long long>(), c->pairTableSlots - 1);
+        c->manCount.as<int>(), rebuild ? nullptr : c->pairTable.as<unsigned long long>(), c->pairTableSlots - 1);
     c->launches++;
     c->manifoldCount += fresh;
     c->contactPointCount = 2 * c->manifoldCount;
     PHYX_CUDA(cudaGetLastError());
+    if (rebuild) PHYX_TRY(collide_rebuild_pair_table(c));
     return PHYX_B200_OK;
 }
 

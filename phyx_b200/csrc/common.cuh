@@ -47,16 +47,6 @@ struct DevBuf
     void release();
 };
 
-// grow-only pinned host staging buffer
-struct HostBuf
-{
-    void* ptr = nullptr;
-    size_t cap = 0;
-    template <typename T> T* as() const { return static_cast<T*>(ptr); }
-    int reserve(size_t bytes);
-    void release();
-};
-
 // One level of the solve schedule: slots [start, grouped_end) are 8-wide units (AVX2 skip rule),
 // slots [grouped_end, end) are 1-wide units.  start % 8 == 0.
 struct Level
@@ -66,11 +56,6 @@ struct Level
 
 constexpr int kStaticBit = 1 << 30;       // body reference flag in the packed joint: body is static
 constexpr int kBodyMask = kStaticBit - 1;
-
-struct TimerPair
-{
-    cudaEvent_t a = nullptr, b = nullptr;
-};
 
 } // namespace phyx
 
@@ -166,7 +151,6 @@ struct phyx_b200_ctx
     std::vector<phyx_contact_joint> hostJoints; // host copy of the resident joints (host-built schedules need it)
     bool hostJointsValid = false;
 
-    phyx::HostBuf pinned;        // pinned staging for H2D/D2H
     cudaEvent_t ev[8] = {};
     int solveBlocksPerSM = 0, colourBlocksPerSM = 0, colourRounds = 0;
 };
@@ -208,5 +192,4 @@ int collide_rebuild_pair_table(phyx_b200_ctx* c);
 
 // scan.cu
 int exclusive_scan_i32(phyx_b200_ctx* c, const int* in, int* out, int n, int* totalDevice /* may be null */);
-int exclusive_scan_i64(phyx_b200_ctx* c, const int* in, long long* out, int n, long long* totalDevice);
 } // namespace phyx
