@@ -91,6 +91,21 @@ def tumble(count, seed=12345, ground_half_width=1e7):
     return body
 
 
+def clump(count, ground_half_width=1e7):
+    """Every box overlaps every other one: ~count^2/2 pairs out of `count` bodies and hundreds of joints per
+    body.  Not physical; it drives the pair table through a rebuild, the pair buffer through a regrow and
+    the device colouring past its 64-colour limit (host fallback)."""
+    body = np.zeros((count + 1, 6), dtype=np.float32)
+    body[0] = (0.0, 0.0, 0.0, ground_half_width, 10.0, 1.0)
+    i = np.arange(count)
+    body[1:, 0] = (i % 17) * 0.37 - 3.0
+    body[1:, 1] = 60.0 + (i // 17) * 0.29
+    body[1:, 2] = (i % 5) * 0.11
+    body[1:, 3] = BOX[0]
+    body[1:, 4] = BOX[1]
+    return body
+
+
 SCENES = {
     # BASELINE.json configs[0..4]
     "pyramid_1k": lambda: pyramid_fast(45),
@@ -106,6 +121,7 @@ SCENES = {
     "stack_10k": lambda: stack(1000, 10),
     "islands_8x10": lambda: multi_island(8, 10),
     "islands_64x20": lambda: multi_island(64, 20),
+    "clump_300": lambda: clump(300),
     "tumble_300": lambda: tumble(300),
     "tumble_3k": lambda: tumble(3000),
 }

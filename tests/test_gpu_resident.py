@@ -32,7 +32,7 @@ def ctx():
 
 
 @pytest.mark.parametrize("scene,steps", [("pyramid_10", (0, 1, 2, 7, 30)), ("pyramid_1k", (0, 1, 3, 25)), ("stack_1k", (0, 2, 40, 41)), ("islands_8x10", (0, 5)),
-                                          ("tumble_300", (0, 10, 35, 36, 80))])
+                                          ("tumble_300", (0, 10, 35, 36, 80)), ("clump_300", (0, 1))])
 def test_each_resident_stage_matches_reference(ctx, ref, scene, steps):
     r = ref.RefWorld(scenes.make(scene), "strict")
     for step in range(max(steps) + 1):
@@ -152,3 +152,27 @@ def test_incremental_colouring_stays_valid_and_exact(oracle, scene, steps):
         ctx.integrate_position(scenes.DT)
     # after the first (full) build, later steps only colour the few new joints
     assert min(rounds[1:]) < rounds[0]
+
+
+def test_more_than_64_colours_falls_back_to_the_host_builder(oracle):
+    """clump_300: hundreds of joints per body, far beyond the device colouring's 64 colours."""
+    from test_gpu_hotpath import check_schedule, VEL_FIELDS
+
+    w = world.World(scenes.make("clump_300"))
+    ctx = w.context()
+    ctx.upload_bodies(w.bodies())
+    ctx.integrate_velocity(scenes.DT, scenes.GRAVITY)
+    ctx.update_broadphase()
+    bp = ctx.update_pairs()
+    assert bp.pairs > 40000
+    ctx.update_manifolds()
+    ctx.pack_manifolds()
+    ctx.refresh_contact_joints()
+    b0, j0, cp = ctx.download_bodies(), ctx.download_joints(), ctx.download_contact_points()
+    st = ctx.solve_resident(schedule=capi.SCHEDULE_COLOUR, iters=(4, 2))
+    assert st.levels > 64 and st.colourRounds == 0
+    slots, levels = ctx.get_schedule()
+    check_schedule(slots, levels, j0, b0)
+    ob, oj, ran = oracle.solve_scheduled(b0, j0, cp, slots, levels, iters=(4, 2))
+    assert_records_equal(ctx.download_joints(), oj, what="joints")
+    assert_records_equal(ctx.download_bodies(), ob, VEL_FIELDS, what="bodies")
