@@ -346,19 +346,7 @@ int phyx_b200_solve_staged(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, 
     if (stats) memset(stats, 0, sizeof(*stats));
     cudaEvent_t t0 = c->ev[4], t1 = c->ev[5], t2 = c->ev[6];
     PHYX_CUDA(cudaEventRecord(t0, c->stream));
-    // host-built schedules (reference-order replay, cross-check colouring) and KEEP_SCHEDULE read the
-    // joint list on the host: fetch it if the joints were produced on the device
-    const bool hostNeedsJoints = cfg->schedule != PHYX_B200_SCHEDULE_COLOUR || (cfg->flags & (PHYX_B200_SOLVE_HOST_COLOURING | PHYX_B200_SOLVE_KEEP_SCHEDULE));
-    if (hostNeedsJoints && !c->hostJointsValid)
-    {
-        c->hostJoints.resize(size_t(c->jointCount));
-        if (c->jointCount)
-        {
-            PHYX_CUDA(cudaMemcpyAsync(c->hostJoints.data(), c->joints.ptr, size_t(c->jointCount) * sizeof(phyx_contact_joint), cudaMemcpyDeviceToHost, c->stream));
-            PHYX_CUDA(cudaStreamSynchronize(c->stream));
-        }
-    }
-    PHYX_TRY(schedule_build(c, c->hostJoints.data(), c->jointCount, cfg->schedule, cfg->flags));
+    PHYX_TRY(schedule_build(c, c->hostJointsValid ? c->hostJoints.data() : nullptr, c->jointCount, cfg->schedule, cfg->flags));
     PHYX_CUDA(cudaEventRecord(t1, c->stream));
     PHYX_TRY(solve_run(c, cfg, stats));
     PHYX_CUDA(cudaEventRecord(t2, c->stream));

@@ -218,6 +218,21 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
     // The device colouring validates in its own first kernel, so the host walks the joints only
     // for host-built schedules or when asked to compare with the previous call.
     const bool wantKey = (flags & PHYX_B200_SOLVE_KEEP_SCHEDULE) != 0;
+    // Host-built schedules (reference-order replay, cross-check or fallback colouring) and KEEP_SCHEDULE read
+    // the joint list on the host: fetch it if the joints were produced on the device.
+    auto fetch_joints = [&]() -> int {
+        if (hostJoints) return PHYX_B200_OK;
+        c->hostJoints.resize(size_t(nj));
+        if (nj)
+        {
+            PHYX_CUDA(cudaMemcpyAsync(c->hostJoints.data(), c->joints.ptr, size_t(nj) * sizeof(phyx_contact_joint), cudaMemcpyDeviceToHost, c->stream));
+            PHYX_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        c->hostJointsValid = true;
+        hostJoints = c->hostJoints.data();
+        return PHYX_B200_OK;
+    };
+    if (wantKey || !deviceColouring) PHYX_TRY(fetch_joints());
     std::vector<int> key(wantKey ? size_t(nj) * 2 : 0);
     for (int j = 0; j < nj && (wantKey || !deviceColouring); ++j)
     {
@@ -245,6 +260,8 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
         int st = colour_schedule_build(c);
         if (st != PHYX_B200_ERR_CAPACITY) return st;
         // more than 64 colours (a dynamic body with dozens of joints): the host builder has no limit
+        PHYX_TRY(fetch_joints());
+        c->colourStateValid = false;
     }
     c->hostSlotsStale = false;
     c->colourRounds = 0;
