@@ -609,12 +609,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve(SolveParams P)
 // solve, the producer runs ahead of the grid barriers too: when a level opens, its first chunks are
 // already in shared memory, and what remains on the critical path of a slot is the gather of its two
 // body rows from L2, of which every thread keeps kU slots' worth in flight.
-constexpr int kPipeThreads = kBlock;
 
-template <int U>
+template <int U, int T>
 struct PipeStage
 {
-    float4 q0[U * kPipeThreads], q1[U * kPipeThreads], q2[U * kPipeThreads], q3[U * kPipeThreads];
+    float4 q0[U * T], q1[U * T], q2[U * T], q3[U * T];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -650,17 +649,17 @@ struct ChunkCursor
     int it, l, k;
 };
 
-template <int U>
+template <int U, int T>
 __device__ __forceinline__ bool cursor_next(const SolveParams& P, int iters, ChunkCursor& c, int& base, int& count)
 {
     while (c.it < iters)
     {
         const Level L = P.levels[c.l];
-        const long long b = L.start + static_cast<long long>(blockIdx.x + c.k * gridDim.x) * (U * kPipeThreads);
+        const long long b = L.start + static_cast<long long>(blockIdx.x + c.k * gridDim.x) * (U * T);
         if (b < L.end)
         {
             base = int(b);
-            count = min(U * kPipeThreads, L.end - int(b));
+            count = min(U * T, L.end - int(b));
             ++c.k;
             return true;
         }
@@ -683,8 +682,8 @@ struct SlotWork
     bool valid, wide, st1, st2, unitHasStatic, active;
 };
 
-template <int PHASE, int U, int S>
-__device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, PipeStage<U>* stages, unsigned long long* full, int* sharedWord,
+template <int PHASE, int U, int S, int T>
+__device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, PipeStage<U, T>* stages, unsigned long long* full, int* sharedWord,
     unsigned& consumed, unsigned& epoch, int& tick, int& wakePasses, unsigned& activeCount)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -699,9 +698,9 @@ __device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, P
     unsigned issued = consumed;   // producer-only bookkeeping (thread 0)
     auto produce = [&]() {
         int base, count;
-        if (!cursor_next<U>(P, iters, prod, base, count)) return;
+        if (!cursor_next<U, T>(P, iters, prod, base, count)) return;
         const unsigned st = issued % S;
-        PipeStage<U>& dst = stages[st];
+        PipeStage<U, T>& dst = stages[st];
         const unsigned bytes = unsigned(count) * 16u;
         mbar_expect_tx(&full[st], 4u * bytes);
         bulk_g2s(dst.q0, P.q0 + base, bytes, &full[st]);
@@ -724,21 +723,21 @@ __device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, P
             bool wake = false;
             for (int k = 0;; ++k)
             {
-                const long long cb = L.start + static_cast<long long>(blockIdx.x + k * gridDim.x) * (U * kPipeThreads);
+                const long long cb = L.start + static_cast<long long>(blockIdx.x + k * gridDim.x) * (U * T);
                 if (cb >= L.end) break;
                 const int base = int(cb);
-                const int count = min(U * kPipeThreads, L.end - base);
+                const int count = min(U * T, L.end - base);
                 const unsigned st = consumed % S;
                 if (producer) produce();   // refills the stage released by the previous chunk's __syncthreads
                 mbar_wait(&full[st], (consumed / S) & 1u);
-                const PipeStage<U>& in = stages[st];
+                const PipeStage<U, T>& in = stages[st];
 
                 SlotWork w[U];
                 // 1. decode, issue every global load of the chunk's slots
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                 {
-                    const int idx = u * kPipeThreads + threadIdx.x;
+                    const int idx = u * T + threadIdx.x;
                     SlotWork& x = w[u];
                     x.s = base + idx;
                     x.valid = idx < count;
@@ -789,7 +788,7 @@ __device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, P
                 {
                     SlotWork& x = w[u];
                     if (!x.active) continue;
-                    const int idx = u * kPipeThreads + threadIdx.x;
+                    const int idx = u * T + threadIdx.x;
                     ++activeCount;
                     const bool productive = relax<PHASE>(in.q0[idx], in.q1[idx], in.q2[idx], x.c3, x.acc, x.v1, x.v2, x.wide);
                     if (PHASE == 0)
@@ -844,12 +843,12 @@ __device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, P
     return ran;
 }
 
-template <int U, int S>
-__global__ void __launch_bounds__(kPipeThreads) k_solve_pipe(SolveParams P)
+template <int U, int S, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_solve_pipe(SolveParams P)
 {
     extern __shared__ __align__(128) unsigned char pipeSmem[];
-    PipeStage<U>* stages = reinterpret_cast<PipeStage<U>*>(pipeSmem);
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(pipeSmem + sizeof(PipeStage<U>) * S);
+    PipeStage<U, T>* stages = reinterpret_cast<PipeStage<U, T>*>(pipeSmem);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(pipeSmem + sizeof(PipeStage<U, T>) * S);
     int* sharedWord = reinterpret_cast<int*>(full + S);
 
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -871,8 +870,8 @@ __global__ void __launch_bounds__(kPipeThreads) k_solve_pipe(SolveParams P)
         for (int s = L.start + tid; s < L.end; s += nthreads) prestep_slot(P, s);
         grid_barrier(P.barrier, epoch, false, false);
     }
-    const int ranImpulse = run_phase_pipe<0, U, S>(P, P.contactIters, stages, full, sharedWord, consumed, epoch, tick, wakePasses, active[0]);
-    const int ranDisplacement = run_phase_pipe<1, U, S>(P, P.penetrationIters, stages, full, sharedWord, consumed, epoch, tick, wakePasses, active[1]);
+    const int ranImpulse = run_phase_pipe<0, U, S, T>(P, P.contactIters, stages, full, sharedWord, consumed, epoch, tick, wakePasses, active[0]);
+    const int ranDisplacement = run_phase_pipe<1, U, S, T>(P, P.penetrationIters, stages, full, sharedWord, consumed, epoch, tick, wakePasses, active[1]);
 
     for (int phase = 0; phase < 2; ++phase)
     {
@@ -888,25 +887,25 @@ __global__ void __launch_bounds__(kPipeThreads) k_solve_pipe(SolveParams P)
     }
 }
 
-template <int U, int S>
+template <int U, int S, int T, int MINB>
 static int launch_solve_pipe(phyx_b200_ctx* c, SolveParams& P, int widestLevel)
 {
-    const size_t smem = sizeof(PipeStage<U>) * S + sizeof(unsigned long long) * S + 16;
+    const size_t smem = sizeof(PipeStage<U, T>) * S + sizeof(unsigned long long) * S + 16;
     static int perSM = 0;
     if (perSM == 0)
     {
-        PHYX_CUDA(cudaFuncSetAttribute(k_solve_pipe<U, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_solve_pipe<U, S>, kPipeThreads, smem));
+        PHYX_CUDA(cudaFuncSetAttribute(k_solve_pipe<U, S, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_solve_pipe<U, S, T, MINB>, T, smem));
         if (perSM < 1)
         {
             set_error("pipelined solve kernel does not fit on an SM");
             return PHYX_B200_ERR_CUDA;
         }
     }
-    const int want = (widestLevel + U * kPipeThreads - 1) / (U * kPipeThreads);
+    const int want = (widestLevel + U * T - 1) / (U * T);
     const int grid = max(1, min(want, c->numSMs * perSM));
     void* args[] = { &P };
-    PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_pipe<U, S>, dim3(grid), dim3(kPipeThreads), args, smem, c->stream));
+    PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_pipe<U, S, T, MINB>, dim3(grid), dim3(T), args, smem, c->stream));
     return PHYX_B200_OK;
 }
 
@@ -1046,15 +1045,15 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         else
         {
             const int variant = pipeEnv ? atoi(pipeEnv) : 12;
-            switch (variant)
+            switch (variant)   // <slots per thread, stages, threads, min CTAs per SM>
             {
-            case 12: PHYX_TRY((launch_solve_pipe<1, 2>(c, P, maxLevel))); break;
-            case 13: PHYX_TRY((launch_solve_pipe<1, 3>(c, P, maxLevel))); break;
-            case 14: PHYX_TRY((launch_solve_pipe<1, 4>(c, P, maxLevel))); break;
-            case 22: PHYX_TRY((launch_solve_pipe<2, 2>(c, P, maxLevel))); break;
-            case 32: PHYX_TRY((launch_solve_pipe<3, 2>(c, P, maxLevel))); break;
-            case 42: PHYX_TRY((launch_solve_pipe<4, 2>(c, P, maxLevel))); break;
-            default: PHYX_TRY((launch_solve_pipe<2, 3>(c, P, maxLevel))); break;
+            case 13: PHYX_TRY((launch_solve_pipe<1, 3, 256, 3>(c, P, maxLevel))); break;
+            case 22: PHYX_TRY((launch_solve_pipe<2, 2, 256, 2>(c, P, maxLevel))); break;
+            case 23: PHYX_TRY((launch_solve_pipe<2, 3, 256, 2>(c, P, maxLevel))); break;
+            case 124: PHYX_TRY((launch_solve_pipe<1, 2, 256, 4>(c, P, maxLevel))); break;
+            case 512: PHYX_TRY((launch_solve_pipe<1, 2, 512, 2>(c, P, maxLevel))); break;
+            case 1024: PHYX_TRY((launch_solve_pipe<1, 2, 1024, 1>(c, P, maxLevel))); break;
+            default: PHYX_TRY((launch_solve_pipe<1, 2, 256, 3>(c, P, maxLevel))); break;
             }
         }
         c->launches++;
