@@ -404,13 +404,14 @@ __device__ __forceinline__ void load_slot(const SolveParams& P, int s, bool inRa
 // this (iteration, level) are reconsidered.  Returns productive; sets `wake` if a joint of this
 // pass turned a cold static body productive.  `pre` holds the streams of this thread's first slot
 // when havePre is set.
-template <int PHASE>
-__device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L, const int* __restrict__ slotMap, int it, int tick, bool firstPass, int tid,
+template <int PHASE, bool DUAL>
+__device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L, const int* __restrict__ slotMapArg, int it, int tick, bool firstPass, int tid,
     int nthreads, bool& wake, unsigned& activeCount, SlotData<PHASE>& pre, bool havePre)
 {
+    const int* __restrict__ slotMap = DUAL ? slotMapArg : nullptr;   // compile-time null for single-schedule kernels
     float4* rows = PHASE == 0 ? P.vel : P.disp;
     unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
-    int* hotCounter = P.hotCount ? P.hotCount + PHASE * 4 + (it % 3) : nullptr;
+    int* hotCounter = (DUAL && P.hotCount) ? P.hotCount + PHASE * 4 + (it % 3) : nullptr;
     const int lane = threadIdx.x & 31;
     const unsigned seg = 0xffu << (lane & ~7);   // the 8-lane unit this lane belongs to
     bool anyProductive = false;
@@ -477,14 +478,14 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
                 __stcg(&rows[b1], v1);
             }
             else if (productive)
-                wake |= static_mark(&statics[b1], it, pos, (P.rowsMulti && P.rowsMulti[b1]) ? hotCounter : nullptr);
+                wake |= static_mark(&statics[b1], it, pos, (DUAL && P.rowsMulti && P.rowsMulti[b1]) ? hotCounter : nullptr);
             if (!st2)
             {
                 v2.w = __int_as_float(productive ? it : last2);
                 __stcg(&rows[b2], v2);
             }
             else if (productive)
-                wake |= static_mark(&statics[b2], it, pos, (P.rowsMulti && P.rowsMulti[b2]) ? hotCounter : nullptr);
+                wake |= static_mark(&statics[b2], it, pos, (DUAL && P.rowsMulti && P.rowsMulti[b2]) ? hotCounter : nullptr);
             if (unitHasStatic) __stcg(&P.processed[s], tick);
         }
         anyProductive |= productive;
@@ -494,14 +495,14 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
 
 // All iterations of one phase (Solver.cpp:175-190 / :196-211), one grid barrier per level plus one per
 // wake pass (rare).  Returns the number of iterations run.
-template <int PHASE>
+template <int PHASE, bool DUAL>
 __device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int tid, int nthreads, unsigned& epoch, int& tick, int& wakePasses,
     unsigned& activeCount)
 {
     SlotData<PHASE> pre;
     bool havePre = false;
     int ran = 0;
-    const bool dual = P.numStrictLevels > 0;
+    const bool dual = DUAL && P.numStrictLevels > 0;
     int* hot = P.hotCount ? P.hotCount + PHASE * 4 : nullptr;
     for (int it = 0; it < iters; ++it)
     {
@@ -526,7 +527,7 @@ __device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int ti
             const Level L = levels[l];
             ++tick;
             bool wake = false;
-            any |= solve_level<PHASE>(P, L, slotMap, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre);
+            any |= solve_level<PHASE, DUAL>(P, L, slotMap, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre);
             // streams of this thread's first slot in the level that follows (next level, or level 0 of
             // the next iteration), fetched while the grid drains into the barrier
             havePre = false;
@@ -536,7 +537,7 @@ __device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int ti
                 const int kN = N.start + tid;
                 bool inRange = kN < N.end;
                 int sN = kN;
-                if (slotMap && inRange)
+                if (DUAL && slotMap && inRange)
                 {
                     sN = slotMap[kN];
                     inRange = sN >= 0;
@@ -550,7 +551,7 @@ __device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int ti
             {
                 SlotData<PHASE> scratch;
                 wake = false;
-                any |= solve_level<PHASE>(P, L, slotMap, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
+                any |= solve_level<PHASE, DUAL>(P, L, slotMap, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
                 ++wakePasses;
                 r = grid_barrier(P.barrier, epoch, wake, any);
             }
@@ -566,7 +567,7 @@ __device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int ti
 // Persistent cooperative kernel: the whole SolveJointIsland loop nest (Solver.cpp:159-211) in one launch.
 // THREADS x MIN_BLOCKS is the register budget: 256x4, 512x2 and 1024x1 all give 64 registers and
 // 1024 threads per SM; fewer, larger CTAs make the grid barrier cheaper (148 arrivals instead of 592).
-template <int THREADS, int MIN_BLOCKS>
+template <int THREADS, int MIN_BLOCKS, bool DUAL>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve(SolveParams P)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -582,8 +583,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve(SolveParams P)
         grid_barrier(P.barrier, epoch, false, false);
     }
 
-    const int ranImpulse = run_phase<0>(P, P.contactIters, tid, nthreads, epoch, tick, wakePasses, active[0]);
-    const int ranDisplacement = run_phase<1>(P, P.penetrationIters, tid, nthreads, epoch, tick, wakePasses, active[1]);
+    const int ranImpulse = run_phase<0, DUAL>(P, P.contactIters, tid, nthreads, epoch, tick, wakePasses, active[0]);
+    const int ranDisplacement = run_phase<1, DUAL>(P, P.penetrationIters, tid, nthreads, epoch, tick, wakePasses, active[1]);
 
     for (int phase = 0; phase < 2; ++phase)
     {
@@ -821,7 +822,7 @@ __device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, P
             {
                 SlotData<PHASE> scratch;
                 wake = false;
-                any |= solve_level<PHASE>(P, L, nullptr, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
+                any |= solve_level<PHASE, false>(P, L, nullptr, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
                 ++wakePasses;
                 r = grid_barrier(P.barrier, epoch, wake, any);
             }
@@ -1014,13 +1015,13 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         // CTA shape of the direct kernel: PHYX_SOLVE_BLOCK = 256 | 512 | 1024 (default 512: measured 2.37 ms vs 2.40 / 2.44 ms)
         static const int blockEnv = getenv("PHYX_SOLVE_BLOCK") ? atoi(getenv("PHYX_SOLVE_BLOCK")) : 512;
         const int sblock = blockEnv == 256 ? 256 : blockEnv == 512 ? 512 : 1024;
-        void* solveKernel = sblock == 256 ? (void*)k_solve<256, 4> : sblock == 512 ? (void*)k_solve<512, 2> : (void*)k_solve<1024, 1>;
-        if (c->solveBlocksPerSM == 0)
+        // the dual-schedule (replay) instantiation carries the strict companion's bookkeeping; the
+        // single-schedule one compiles it away
+        void* solveKernel = dual ? (sblock == 256 ? (void*)k_solve<256, 4, true> : sblock == 512 ? (void*)k_solve<512, 2, true> : (void*)k_solve<1024, 1, true>)
+                                 : (sblock == 256 ? (void*)k_solve<256, 4, false> : sblock == 512 ? (void*)k_solve<512, 2, false> : (void*)k_solve<1024, 1, false>);
         {
             int per = 0;
-            if (sblock == 256) PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_solve<256, 4>, 256, 0));
-            else if (sblock == 512) PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_solve<512, 2>, 512, 0));
-            else PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_solve<1024, 1>, 1024, 0));
+            PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, solveKernel, sblock, 0));
             if (per < 1)
             {
                 set_error("solve kernel does not fit on an SM");
