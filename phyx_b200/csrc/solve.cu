@@ -381,21 +381,32 @@ struct SlotData
 };
 
 template <int PHASE>
+#ifndef PHYX_SOLVE_SPECULATIVE
+#define PHYX_SOLVE_SPECULATIVE 1   // 1: fetch every stream before the skip test; 0: only Q3, the rest once the joint is known to be active
+#endif
+
+template <int PHASE>
+__device__ __forceinline__ void load_rest(const SolveParams& P, int s, SlotData<PHASE>& d)
+{
+    d.c0 = __ldcs(&P.q0[s]);
+    d.c2 = __ldcs(&P.q2[s]);
+    if (PHASE == 0)
+    {
+        d.c1 = __ldcs(&P.q1[s]);
+        d.acc = __ldcs(&P.accNF[s]);
+    }
+    else
+        d.acc.x = __ldcs(&P.accD[s]);
+}
+
+template <int PHASE>
 __device__ __forceinline__ void load_slot(const SolveParams& P, int s, bool inRange, SlotData<PHASE>& d)
 {
     d.c3 = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
     if (inRange)
     {
         d.c3 = __ldcs(&P.q3[s]);
-        d.c0 = __ldcs(&P.q0[s]);
-        d.c2 = __ldcs(&P.q2[s]);
-        if (PHASE == 0)
-        {
-            d.c1 = __ldcs(&P.q1[s]);
-            d.acc = __ldcs(&P.accNF[s]);
-        }
-        else
-            d.acc.x = __ldcs(&P.accD[s]);
+        if (PHYX_SOLVE_SPECULATIVE) load_rest<PHASE>(P, s, d);
     }
 }
 
@@ -464,6 +475,7 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
         if (active)
         {
             ++activeCount;
+            if (!PHYX_SOLVE_SPECULATIVE) load_rest<PHASE>(P, s, pre);
             float2 acc = pre.acc;
             productive = relax<PHASE>(pre.c0, pre.c1, pre.c2, c3, acc, v1, v2, wide);
             if (PHASE == 0)
