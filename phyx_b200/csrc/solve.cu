@@ -380,7 +380,6 @@ struct SlotData
     float2 acc;              // impulse: {accN, accF}; displacement: {accD, -}
 };
 
-template <int PHASE>
 #ifndef PHYX_SOLVE_SPECULATIVE
 #define PHYX_SOLVE_SPECULATIVE 1   // 1: fetch every stream before the skip test; 0: only Q3, the rest once the joint is known to be active
 #endif
