@@ -437,8 +437,24 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
             valid = s >= 0;
         }
         if (!havePre) load_slot<PHASE>(P, s, valid, pre);
+        // software pipeline inside the level as well: this trip works on a copy while the streams of the
+        // thread's next slot (one grid-stride further) are already on their way
+        const SlotData<PHASE> cur = pre;
         havePre = false;
-        const float4 c3 = pre.c3;
+        if (s0 + nthreads < L.end)
+        {
+            const int kN = k + nthreads;
+            bool inRange = kN < L.end;
+            int sN = kN;
+            if (slotMap && inRange)
+            {
+                sN = slotMap[kN];
+                inRange = sN >= 0;
+            }
+            load_slot<PHASE>(P, sN, inRange, pre);
+            havePre = true;
+        }
+        const float4 c3 = cur.c3;
         const int r1 = __float_as_int(c3.x), r2 = __float_as_int(c3.y);
         valid = valid && r1 >= 0;
         const int b1 = r1 & kBodyMask, b2 = r2 & kBodyMask;
@@ -474,9 +490,10 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
         if (active)
         {
             ++activeCount;
-            if (!PHYX_SOLVE_SPECULATIVE) load_rest<PHASE>(P, s, pre);
-            float2 acc = pre.acc;
-            productive = relax<PHASE>(pre.c0, pre.c1, pre.c2, c3, acc, v1, v2, wide);
+            SlotData<PHASE> rest = cur;
+            if (!PHYX_SOLVE_SPECULATIVE) load_rest<PHASE>(P, s, rest);
+            float2 acc = rest.acc;
+            productive = relax<PHASE>(rest.c0, rest.c1, rest.c2, c3, acc, v1, v2, wide);
             if (PHASE == 0)
                 __stcs(&P.accNF[s], acc);
             else
@@ -1023,13 +1040,20 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
             PHYX_CUDA(cudaMemsetAsync(c->timeline.ptr, 0, 4096 * 8, c->stream));
             P.timeline = c->timeline.as<unsigned long long>();
         }
-        // CTA shape of the direct kernel: PHYX_SOLVE_BLOCK = 256 | 512 | 1024 (default 512: measured 2.37 ms vs 2.40 / 2.44 ms)
-        static const int blockEnv = getenv("PHYX_SOLVE_BLOCK") ? atoi(getenv("PHYX_SOLVE_BLOCK")) : 512;
-        const int sblock = blockEnv == 256 ? 256 : blockEnv == 512 ? 512 : 1024;
-        // the dual-schedule (replay) instantiation carries the strict companion's bookkeeping; the
-        // single-schedule one compiles it away
-        void* solveKernel = dual ? (sblock == 256 ? (void*)k_solve<256, 4, true> : sblock == 512 ? (void*)k_solve<512, 2, true> : (void*)k_solve<1024, 1, true>)
-                                 : (sblock == 256 ? (void*)k_solve<256, 4, false> : sblock == 512 ? (void*)k_solve<512, 2, false> : (void*)k_solve<1024, 1, false>);
+        // CTA shape of the direct kernel: PHYX_SOLVE_SHAPE = <threads><min CTAs per SM> (2564, 2563, 5122, 5121, 10241)
+        static const int shapeEnv = getenv("PHYX_SOLVE_SHAPE") ? atoi(getenv("PHYX_SOLVE_SHAPE")) : 5122;
+        int sblock = 512;
+        void* solveKernel = nullptr;
+#define PHYX_PICK(T, B) (dual ? (void*)k_solve<T, B, true> : (void*)k_solve<T, B, false>)
+        switch (shapeEnv)
+        {
+        case 2564: sblock = 256; solveKernel = PHYX_PICK(256, 4); break;
+        case 2563: sblock = 256; solveKernel = PHYX_PICK(256, 3); break;
+        case 5121: sblock = 512; solveKernel = PHYX_PICK(512, 1); break;
+        case 10241: sblock = 1024; solveKernel = PHYX_PICK(1024, 1); break;
+        default: sblock = 512; solveKernel = PHYX_PICK(512, 2); break;
+        }
+#undef PHYX_PICK
         {
             int per = 0;
             PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, solveKernel, sblock, 0));
