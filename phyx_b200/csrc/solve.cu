@@ -437,24 +437,8 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
             valid = s >= 0;
         }
         if (!havePre) load_slot<PHASE>(P, s, valid, pre);
-        // software pipeline inside the level as well: this trip works on a copy while the streams of the
-        // thread's next slot (one grid-stride further) are already on their way
-        const SlotData<PHASE> cur = pre;
         havePre = false;
-        if (s0 + nthreads < L.end)
-        {
-            const int kN = k + nthreads;
-            bool inRange = kN < L.end;
-            int sN = kN;
-            if (slotMap && inRange)
-            {
-                sN = slotMap[kN];
-                inRange = sN >= 0;
-            }
-            load_slot<PHASE>(P, sN, inRange, pre);
-            havePre = true;
-        }
-        const float4 c3 = cur.c3;
+        const float4 c3 = pre.c3;
         const int r1 = __float_as_int(c3.x), r2 = __float_as_int(c3.y);
         valid = valid && r1 >= 0;
         const int b1 = r1 & kBodyMask, b2 = r2 & kBodyMask;
@@ -490,10 +474,9 @@ __device__ __forceinline__ bool solve_level(const SolveParams& P, const Level L,
         if (active)
         {
             ++activeCount;
-            SlotData<PHASE> rest = cur;
-            if (!PHYX_SOLVE_SPECULATIVE) load_rest<PHASE>(P, s, rest);
-            float2 acc = rest.acc;
-            productive = relax<PHASE>(rest.c0, rest.c1, rest.c2, c3, acc, v1, v2, wide);
+            if (!PHYX_SOLVE_SPECULATIVE) load_rest<PHASE>(P, s, pre);
+            float2 acc = pre.acc;
+            productive = relax<PHASE>(pre.c0, pre.c1, pre.c2, c3, acc, v1, v2, wide);
             if (PHASE == 0)
                 __stcs(&P.accNF[s], acc);
             else
