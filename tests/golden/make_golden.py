@@ -125,3 +125,9 @@ if __name__ == "__main__":
     trajectories()
     radix()
     print("golden fixtures written to", OUT)
+
+# host_api_demo_12_40.txt: tests/cpp/host_api_demo.cpp compiled against the REFERENCE's headers and sources
+# (same flags as the strict oracle build) and run as `demo 12 40`:
+#   REF=/root/reference/src; g++ -O2 -ffp-contract=off -std=c++11 -mavx2 -mfma -include cstdio -include cstring \
+#     -include cassert -DMICROPROFILE_ENABLED=0 '-DMicroProfileOnThreadExit()=do{}while(0)' -I$REF -I$REF/microprofile \
+#     tests/cpp/host_api_demo.cpp $REF/World.cpp $REF/Solver.cpp $REF/Collider.cpp $REF/base/WorkQueue.cpp -lpthread -o demo_ref
