@@ -85,7 +85,9 @@ int ref_add_body(void* h, float x, float y, float angle, float sx, float sy, int
 {
     World& w = static_cast<RefWorld*>(h)->world;
     RigidBody* b = w.AddBody(Coords2f(Vector2f(x, y), angle), Vector2f(sx, sy));
-    if (is_static)
+    if (is_static == 2)
+        b->invMass = 0.f;   // the demo's platforms (src/main.cpp:172-173): immovable but free to rotate
+    else if (is_static)
     {
         b->invMass = 0.f;
         b->invInertia = 0.f;
@@ -96,7 +98,7 @@ int ref_add_body(void* h, float x, float y, float angle, float sx, float sy, int
 void ref_add_bodies(void* h, const float* rows6, int count)
 {
     for (int i = 0; i < count; ++i)
-        ref_add_body(h, rows6[6 * i], rows6[6 * i + 1], rows6[6 * i + 2], rows6[6 * i + 3], rows6[6 * i + 4], rows6[6 * i + 5] != 0.f);
+        ref_add_body(h, rows6[6 * i], rows6[6 * i + 1], rows6[6 * i + 2], rows6[6 * i + 3], rows6[6 * i + 4], int(rows6[6 * i + 5]));
 }
 
 int ref_body_count(void* h) { return static_cast<RefWorld*>(h)->world.bodies.size; }

@@ -46,7 +46,9 @@ API int phyxw_add_body(void* h, float x, float y, float angle, float sx, float s
 {
     World& w = static_cast<Handle*>(h)->world;
     RigidBody* b = w.AddBody(Coords2f(Vector2f(x, y), angle), Vector2f(sx, sy));
-    if (is_static)
+    if (is_static == 2)
+        b->invMass = 0.f;   // the demo's platforms (reference src/main.cpp:172-173): immovable but free to rotate
+    else if (is_static)
     {
         b->invMass = 0.f;
         b->invInertia = 0.f;
@@ -57,7 +59,7 @@ API int phyxw_add_body(void* h, float x, float y, float angle, float sx, float s
 API void phyxw_add_bodies(void* h, const float* rows6, int count)
 {
     for (int i = 0; i < count; ++i)
-        phyxw_add_body(h, rows6[6 * i], rows6[6 * i + 1], rows6[6 * i + 2], rows6[6 * i + 3], rows6[6 * i + 4], rows6[6 * i + 5] != 0.f);
+        phyxw_add_body(h, rows6[6 * i], rows6[6 * i + 1], rows6[6 * i + 2], rows6[6 * i + 3], rows6[6 * i + 4], int(rows6[6 * i + 5]));
 }
 
 API void phyxw_step(void* h, float dt, int solveMode, int islandMode, int contactIters, int penetrationIters)

@@ -106,6 +106,25 @@ def clump(count, ground_half_width=1e7):
     return body
 
 
+def platforms(count=400, seed=777):
+    """The demo's "Stacks" layout in small (reference src/main.cpp:170-186): two platforms with
+    invMass = 0 only (row flag 2: immovable but free to rotate, so NOT static for the solver: every
+    joint on them conflicts) and boxes raining on them.  Platforms collect dozens of joints on one
+    dynamic body: deep dependency chains in replay, more than 64 colours in colour mode."""
+    body = np.zeros((count + 3, 6), dtype=np.float32)
+    body[0] = (0.0, 0.0, 0.0, 1e7, 10.0, 1.0)
+    body[1] = (0.0, 120.0, 0.0, 300.0, 10.0, 2.0)
+    body[2] = (420.0, 60.0, 0.0, 200.0, 10.0, 2.0)
+    s = seed
+    for i in range(count):
+        vals = []
+        for _ in range(3):
+            s = (s * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+            vals.append(((s >> 33) & 0xFFFFFF) / float(1 << 24))
+        body[i + 3] = (vals[0] * 500.0 - 100.0, 160.0 + vals[1] * 900.0, vals[2] * 0.8, 4.0, 4.0, 0.0)
+    return body
+
+
 SCENES = {
     # BASELINE.json configs[0..4]
     "pyramid_1k": lambda: pyramid_fast(45),
@@ -122,6 +141,7 @@ SCENES = {
     "islands_8x10": lambda: multi_island(8, 10),
     "islands_64x20": lambda: multi_island(64, 20),
     "clump_300": lambda: clump(300),
+    "platforms_400": lambda: platforms(400),
     "tumble_300": lambda: tumble(300),
     "tumble_3k": lambda: tumble(3000),
 }

@@ -34,6 +34,7 @@ def rel_dev(a, b):
     ("tumble_300", 150, T.SOLVE_AVX2, 0),      # rotated boxes: every narrowphase branch, manifold churn
     ("tumble_300", 60, T.SOLVE_SCALAR, 0),
     ("tumble_3k", 80, T.SOLVE_AVX2, 0),
+    ("platforms_400", 200, T.SOLVE_AVX2, 0),   # bodies with invMass = 0 only (not static): many joints on one dynamic body
 ])
 def test_world_update_tracks_reference(ref, scene, steps, mode, flags):
     sc = scenes.make(scene)
