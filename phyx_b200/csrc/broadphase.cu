@@ -29,6 +29,12 @@ __device__ __forceinline__ unsigned radix_float(float v)   // RadixSort.h:19-26
     return unsigned(f) ^ mask;
 }
 
+__device__ __forceinline__ float radix_unfloat(unsigned u)   // inverse of radix_float
+{
+    unsigned mask = (u & 0x80000000u) ? 0x80000000u : 0xffffffffu;
+    return __int_as_float(int(u ^ mask));
+}
+
 __global__ void k_make_keys(int n, const float4* __restrict__ aabb, uint2* __restrict__ kv)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,7 +150,8 @@ __global__ void k_gather_entries(int n, const uint2* __restrict__ sorted, const 
 
 constexpr int kChunk = 1024;   // sweep tests per work item (one warp, 32 rounds)
 constexpr int kTile = 256;     // sorted bodies per tile of the shared-memory count pass
-constexpr int kTileCap = 5120; // entries of {centery, extenty} a tile may hold (40 KB)
+constexpr int kTileCap = 4096; // entries of {centery, extenty} a tile may hold (32 KB)
+constexpr int kCells = 256;    // height cells a tile's entries are bucketed into
 
 // end_i = first j > i with minx[j] > maxx[i] (the x-break, Collider.cpp:306); minx is sorted.
 __global__ void k_sweep_end(int n, const float2* __restrict__ entryX, int* __restrict__ end, int* __restrict__ itemsOf)
@@ -258,10 +265,20 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(int n, const int* 
     unsigned long long* __restrict__ totals, const unsigned long long* __restrict__ table, size_t tableMask)
 {
     __shared__ float2 tileY[kTileCap];
+    __shared__ unsigned short byCell[kTileCap];     // tile entries (relative index) bucketed by y cell
+    __shared__ int cellStart[kCells + 1], cellFill[kCells];
     __shared__ int sMaxEnd;
+    __shared__ unsigned sYmin, sYmax, sEymax;        // order-preserving float bits
     const int i0 = blockIdx.x * kTile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) sMaxEnd = 0;
+    if (threadIdx.x == 0)
+    {
+        sMaxEnd = 0;
+        sYmin = 0xffffffffu;
+        sYmax = 0u;
+        sEymax = 0u;
+    }
+    for (int k = threadIdx.x; k < kCells; k += kBlock) cellFill[k] = 0;
     __syncthreads();
     {
         const int i = i0 + threadIdx.x;
@@ -277,49 +294,128 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(int n, const int* 
         return;
     }
     if (threadIdx.x == 0) tileLong[blockIdx.x] = 0;
-    for (int k = threadIdx.x; k < span; k += kBlock) tileY[k] = entryY[first + k];
+    // load the tile, find its y range and largest half extent
+    {
+        unsigned lo = 0xffffffffu, hi = 0u, ex = 0u;
+        for (int k = threadIdx.x; k < span; k += kBlock)
+        {
+            const float2 y = entryY[first + k];
+            tileY[k] = y;
+            lo = min(lo, radix_float(y.x));
+            hi = max(hi, radix_float(y.x));
+            ex = max(ex, radix_float(y.y));
+        }
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            ex = max(ex, __shfl_xor_sync(0xffffffffu, ex, o));
+        }
+        if (lane == 0)
+        {
+            atomicMin(&sYmin, lo);
+            atomicMax(&sYmax, hi);
+            atomicMax(&sEymax, ex);
+        }
+    }
+    __syncthreads();
+    // Bucket the tile's entries by height.  A body can only touch entries whose centre lies within
+    // (its own half extent + the tile's largest half extent) of its own, i.e. in a few neighbouring
+    // cells, so the scan of a body visits a handful of candidates instead of its whole x range
+    // (~R/2 entries on an R-row pyramid).  The counts are those of the full scan.
+    const float ymin = radix_unfloat(sYmin), ymax = radix_unfloat(sYmax), eymax = radix_unfloat(sEymax);
+    const float cellH = fmaxf((ymax - ymin) / float(kCells), 1e-6f);
+    const float invCellH = 1.0f / cellH;
+    for (int k = threadIdx.x; k < span; k += kBlock) atomicAdd(&cellFill[min(kCells - 1, max(0, int((tileY[k].x - ymin) * invCellH)))], 1);
+    __syncthreads();
+    if (warp == 0)
+    {
+        int run = 0;
+        for (int c0 = 0; c0 < kCells; c0 += 32)
+        {
+            const int v = cellFill[c0 + lane];
+            int inc = v;
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            cellStart[c0 + lane] = run + inc - v;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) cellStart[kCells] = run;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kCells; k += kBlock) cellFill[k] = cellStart[k];
+    __syncthreads();
+    for (int k = threadIdx.x; k < span; k += kBlock)
+    {
+        const int cell = min(kCells - 1, max(0, int((tileY[k].x - ymin) * invCellH)));
+        byCell[atomicAdd(&cellFill[cell], 1)] = (unsigned short)k;
+    }
     __syncthreads();
 
     unsigned long long localTests = 0, localHits = 0;
     for (int i = i0 + warp; i < min(i0 + kTile, n); i += kBlock / 32)
     {
         const int e = end[i];
+        const int len = e - i - 1;
+        if (len <= 0) continue;
         const float2 yi = (i == i0) ? entryY[i] : tileY[i - first];
         const unsigned bi = FILTER ? entryIndex[i] : 0u;
-        int item = itemStart[i];
-        for (int j0 = i + 1; j0 < e; j0 += kChunk, ++item)
+        const int item = itemStart[i];
+        const int numItems = (len + kChunk - 1) / kChunk;
+        // candidates: the cells within reach of this body's y interval
+        const float reach = yi.y + eymax;
+        const int cLo = min(kCells - 1, max(0, int((yi.x - reach - ymin) * invCellH) - 1));
+        const int cHi = min(kCells - 1, max(0, int((yi.x + reach - ymin) * invCellH) + 1));
+        const int kBegin = cellStart[cLo], kEnd = cellStart[cHi + 1];
+        // per work item (chunk of kChunk tests) counts; a tile-able body has at most kTileCap / kChunk items
+        int counts[kTileCap / kChunk + 1];
+#pragma unroll
+        for (int c = 0; c <= kTileCap / kChunk; ++c) counts[c] = 0;
+        for (int kb = kBegin; kb < kEnd; kb += 32 * 32)
         {
-            const int j1 = min(j0 + kChunk, e);
-            // y test for the whole chunk first (bit t of `hits` = this lane's test in round t) ...
+            // y test for up to 32 rounds of candidates (bit t = this lane's test in round t) ...
             unsigned hits = 0;
-            for (int jb = j0, t = 0; jb < j1; jb += 32, ++t)
+            for (int t = 0; t < 32 && kb + t * 32 < kEnd; ++t)
             {
-                const int j = jb + lane;
-                if (j < j1)
+                const int k = kb + t * 32 + lane;
+                if (k < kEnd)
                 {
-                    const float2 yj = tileY[j - first];
-                    if (fabsf(yj.x - yi.x) <= yi.y + yj.y) hits |= 1u << t;   // Collider.cpp:309
+                    const int rel = byCell[k];
+                    const int j = first + rel;
+                    const float2 yj = tileY[rel];
+                    if (j > i && j < e && fabsf(yj.x - yi.x) <= yi.y + yj.y) hits |= 1u << t;   // Collider.cpp:306,309
                 }
             }
-            // ... then the cache lookups of the hits, all lanes' probes in flight together instead of
-            // stalling the scan once per hit
-            int count = __popc(hits);
-            if (FILTER)
+            // ... then the cache lookups of the hits, all lanes' probes in flight together
+            if (FILTER) localHits += __popc(hits);
+            while (hits)
             {
-                localHits += count;
-                count = 0;
-                while (hits)
+                const int t = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const int j = first + byCell[kb + t * 32 + lane];
+                if (!FILTER || !pair_contains(table, tableMask, pair_key(bi, entryIndex[j])))
                 {
-                    const int t = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    const int j = j0 + t * 32 + lane;
-                    if (!pair_contains(table, tableMask, pair_key(bi, entryIndex[j]))) ++count;
+                    const int chunk = (j - i - 1) / kChunk;
+#pragma unroll
+                    for (int c = 0; c <= kTileCap / kChunk; ++c)
+                        if (c == chunk) ++counts[c];
                 }
             }
-            for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
-            if (lane == 0) itemCount[item] = count;
-            localTests += (unsigned long long)(j1 - j0);
         }
+#pragma unroll
+        for (int c = 0; c <= kTileCap / kChunk; ++c)
+        {
+            if (c < numItems)
+            {
+                int v = counts[c];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) itemCount[item + c] = v;
+            }
+        }
+        localTests += (unsigned long long)len;   // what the reference's scan would have tested
     }
     for (int o = 16; o > 0; o >>= 1) localHits += __shfl_xor_sync(0xffffffffu, localHits, o);
     if (lane == 0)
