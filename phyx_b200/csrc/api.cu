@@ -103,6 +103,7 @@ static int stage_joints(phyx_b200_ctx* c, const phyx_contact_joint* joints, int 
     c->pairTableSlots = 0;
     c->hostJointsValid = false;
     c->colourStateValid = false;
+    c->jointUnitsValid = false;
     return PHYX_B200_OK;
 }
 
@@ -160,7 +161,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
-        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->jointColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->timeline, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->locKeysA, &c->locKeysB, &c->locOrder, &c->locRowOf, &c->locStats };
+        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->timeline, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->locKeysA, &c->locKeysB, &c->locOrder, &c->locRowOf, &c->locStats };
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -494,6 +495,7 @@ int phyx_b200_upload_collider(phyx_b200_ctx* c, const phyx_manifold* manifolds, 
     c->jointCount = 0;
     PHYX_TRY(c->manBody.reserve(body.size() * sizeof(int2)));
     PHYX_TRY(c->manCount.reserve(count.size() * sizeof(int)));
+    PHYX_TRY(c->manColour.reserve(count.size() * sizeof(int)));
     PHYX_TRY(c->contactPoints.reserve(size_t(M > 0 ? M : 1) * 2 * sizeof(phyx_contact_point)));
     PHYX_TRY(c->joints.reserve(size_t(jointCount > 0 ? jointCount : 1) * sizeof(phyx_contact_joint)));
     if (M > 0)
@@ -510,6 +512,7 @@ int phyx_b200_upload_collider(phyx_b200_ctx* c, const phyx_manifold* manifolds, 
     c->jointCount = jointCount;
     c->hostJointsValid = false;
     c->colourStateValid = false;
+    c->jointUnitsValid = false;
     return collide_rebuild_pair_table(c);
 }
 

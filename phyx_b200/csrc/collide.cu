@@ -30,13 +30,14 @@ constexpr int kBlock = 256;
 // ================================================================================================
 
 __global__ void __launch_bounds__(kBlock) k_append_manifolds(int count, const int2* __restrict__ pairs, int first, int2* __restrict__ manBody,
-    int* __restrict__ manCount, unsigned long long* __restrict__ table, size_t mask)
+    int* __restrict__ manCount, int* __restrict__ manColour, unsigned long long* __restrict__ table, size_t mask)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     int2 p = pairs[k];
     manBody[first + k] = p;        // Manifold(index_i, index_j, size*2): pointIndex is implicit (2*m)
     manCount[first + k] = 0;
+    manColour[first + k] = -1;     // coloured when it gets its first contact point (colour.cu)
     if (table) pair_insert(table, mask, pair_key(unsigned(p.x), unsigned(p.y)));
 }
 
@@ -54,6 +55,7 @@ static int reserve_manifolds(phyx_b200_ctx* c, int count)
     size_t have = size_t(c->manifoldCount);
     PHYX_TRY(c->manBody.reserve_keep(n * sizeof(int2), have * sizeof(int2), c->stream));
     PHYX_TRY(c->manCount.reserve_keep(n * sizeof(int), have * sizeof(int), c->stream));
+    PHYX_TRY(c->manColour.reserve_keep(n * sizeof(int), have * sizeof(int), c->stream));
     PHYX_TRY(c->contactPoints.reserve_keep(n * 2 * sizeof(phyx_contact_point), have * 2 * sizeof(phyx_contact_point), c->stream));
     return PHYX_B200_OK;
 }
@@ -89,7 +91,7 @@ int collide_update_pairs(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
     // would push it past half full, append without inserting and rebuild it at the right size
     const bool rebuild = size_t(c->manifoldCount + fresh) * 2 > c->pairTableSlots;
     k_append_manifolds<<<(fresh + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(fresh, c->pairs.as<int2>(), c->manifoldCount, c->manBody.as<int2>(),
-        c->manCount.as<int>(), rebuild ? nullptr : c->pairTable.as<unsigned long long>(), c->pairTableSlots - 1);
+        c->manCount.as<int>(), c->manColour.as<int>(), rebuild ? nullptr : c->pairTable.as<unsigned long long>(), c->pairTableSlots - 1);
     c->launches++;
     c->manifoldCount += fresh;
     c->contactPointCount = 2 * c->manifoldCount;
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(kBlock) k_update_manifolds(int count, const in
 int collide_update_manifolds(phyx_b200_ctx* c)
 {
     int M = c->manifoldCount;
+    c->jointUnitsValid = false;   // new contact points have no joint until RefreshContactJoints
     if (M == 0) return PHYX_B200_OK;
     k_update_manifolds<<<(M + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(),
         c->contactPoints.as<float4>(), c->params.as<float4>(), c->rot.as<float4>(), c->size.as<float2>());
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(kBlock) k_list_movers(int n, const int* __rest
 // ================================================================================================
 
 __global__ void __launch_bounds__(kBlock) k_manifold_alive(int count, const int2* __restrict__ manBody, const int* __restrict__ manCount,
-    const float4* __restrict__ aabb, int* __restrict__ alive)
+    const float4* __restrict__ aabb, int* __restrict__ alive, const int* __restrict__ manColour, unsigned long long* __restrict__ bodyUsed)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= count) return;
@@ -387,11 +390,20 @@ __global__ void __launch_bounds__(kBlock) k_manifold_alive(int count, const int2
     float4 a1 = aabb[b.x], a2 = aabb[b.y];
     // AABB2::Intersects, src/AABB2.h:18-23
     bool apart = (a1.x > a2.z) || (a2.x > a1.z) || (a1.y > a2.w) || (a2.y > a1.w);
-    alive[m] = !(manCount[m] == 0 && apart);   // Collider.cpp:390
+    const bool keep = !(manCount[m] == 0 && apart);   // Collider.cpp:390
+    alive[m] = keep;
+    // a removed manifold hands its solver colour back to its bodies (colour.cu; the masks of static bodies are never read)
+    if (!keep && bodyUsed && manColour[m] >= 0)
+    {
+        const unsigned long long mask = ~(1ull << manColour[m]);
+        atomicAnd(&bodyUsed[b.x], mask);
+        atomicAnd(&bodyUsed[b.y], mask);
+    }
 }
 
 __global__ void __launch_bounds__(kBlock) k_manifold_fill(int n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
-    const int* __restrict__ moverIndex, int2* __restrict__ manBody, int* __restrict__ manCount, float4* __restrict__ contactPoints)
+    const int* __restrict__ moverIndex, int2* __restrict__ manBody, int* __restrict__ manCount, int* __restrict__ manColour,
+    float4* __restrict__ contactPoints)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     const int K = *totalPtr;
@@ -400,6 +412,7 @@ __global__ void __launch_bounds__(kBlock) k_manifold_fill(int n, const int* __re
     const int cnt = manCount[src];
     manBody[m] = manBody[src];
     manCount[m] = cnt;
+    manColour[m] = manColour[src];
     for (int k = 0; k < cnt; ++k)   // Collider.cpp:400-401: only the live points travel
     {
         contactPoints[size_t(2 * m + k) * 2] = contactPoints[size_t(2 * src + k) * 2];
@@ -410,6 +423,7 @@ __global__ void __launch_bounds__(kBlock) k_manifold_fill(int n, const int* __re
 int collide_pack_manifolds(phyx_b200_ctx* c)
 {
     const int M = c->manifoldCount;
+    c->jointUnitsValid = false;   // contact points move; RefreshContactJoints re-links the joints
     if (M == 0) return PHYX_B200_OK;
     // scratch: alive[M] | prefix[M] | movers[M] | total
     PHYX_TRY(c->collideTmp.reserve((size_t(M) * 3 + 4) * sizeof(int)));
@@ -418,12 +432,14 @@ int collide_pack_manifolds(phyx_b200_ctx* c)
     int* movers = prefix + M;
     int* total = movers + M;
     const int grid = (M + kBlock - 1) / kBlock;
-    k_manifold_alive<<<grid, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(), c->aabb.as<float4>(), alive);
+    const bool track = c->colourStateValid && c->colourStateBodies == c->bodyCount && c->bodyUsed.ptr;
+    k_manifold_alive<<<grid, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(), c->aabb.as<float4>(), alive, c->manColour.as<int>(),
+        track ? c->bodyUsed.as<unsigned long long>() : nullptr);
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, alive, prefix, M, total));
     k_list_movers<<<grid, kBlock, 0, c->stream>>>(M, alive, prefix, total, movers);
     k_manifold_fill<<<grid, kBlock, 0, c->stream>>>(M, alive, prefix, total, movers, c->manBody.as<int2>(), c->manCount.as<int>(),
-        c->contactPoints.as<float4>());
+        c->manColour.as<int>(), c->contactPoints.as<float4>());
     c->launches += 2;
     int K = 0;
     PHYX_CUDA(cudaMemcpyAsync(&K, total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -458,8 +474,7 @@ __global__ void __launch_bounds__(kBlock) k_point_new_flags(int numPoints, const
 
 // World.cpp:91-124: new points get a joint appended in (manifold, point) order, known points re-attach
 __global__ void __launch_bounds__(kBlock) k_joint_match(int numPoints, int oldJoints, const int2* __restrict__ manBody, const int* __restrict__ manCount,
-    float4* __restrict__ contactPoints, const int* __restrict__ isNew, const int* __restrict__ newRank, phyx_contact_joint* __restrict__ joints,
-    int* __restrict__ jointColour)
+    float4* __restrict__ contactPoints, const int* __restrict__ isNew, const int* __restrict__ newRank, phyx_contact_joint* __restrict__ joints)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= numPoints) return;
@@ -475,7 +490,6 @@ __global__ void __launch_bounds__(kBlock) k_joint_match(int numPoints, int oldJo
         jt.normalLimiter_accumulatedImpulse = 0.f;
         jt.frictionLimiter_accumulatedImpulse = 0.f;
         joints[j] = jt;
-        jointColour[j] = -1;   // to be coloured by the next schedule build
         reinterpret_cast<int*>(contactPoints + size_t(p) * 2 + 1)[3] = j;
     }
     else
@@ -485,36 +499,19 @@ __global__ void __launch_bounds__(kBlock) k_joint_match(int numPoints, int oldJo
     }
 }
 
-// dead joints also give their colour back to their (dynamic) bodies
-__global__ void __launch_bounds__(kBlock) k_joint_alive(int nj, const phyx_contact_joint* __restrict__ joints, int* __restrict__ alive,
-    const int* __restrict__ jointColour, unsigned long long* __restrict__ bodyUsed, const unsigned char* __restrict__ bodyStatic)
+__global__ void __launch_bounds__(kBlock) k_joint_alive(int nj, const phyx_contact_joint* __restrict__ joints, int* __restrict__ alive)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nj) return;
-    const phyx_contact_joint jt = joints[j];
-    const bool live = jt.contactPointIndex >= 0;
-    alive[j] = live;
-    if (!live && bodyUsed)
-    {
-        const int c = jointColour[j];
-        if (c >= 0)
-        {
-            const unsigned long long keep = ~(1ull << c);
-            if (!bodyStatic[jt.body1Index]) atomicAnd(&bodyUsed[jt.body1Index], keep);
-            if (!bodyStatic[jt.body2Index]) atomicAnd(&bodyUsed[jt.body2Index], keep);
-        }
-    }
+    if (j < nj) alive[j] = joints[j].contactPointIndex >= 0;
 }
 
 __global__ void __launch_bounds__(kBlock) k_joint_fill(int n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
-    const int* __restrict__ moverIndex, phyx_contact_joint* __restrict__ joints, int* __restrict__ jointColour)
+    const int* __restrict__ moverIndex, phyx_contact_joint* __restrict__ joints)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int K = *totalPtr;
     if (j >= n || j >= K || alive[j]) return;
-    const int src = moverIndex[j - prefix[j]];
-    joints[j] = joints[src];   // World.cpp:131-134
-    jointColour[j] = jointColour[src];
+    joints[j] = joints[moverIndex[j - prefix[j]]];   // World.cpp:131-134
 }
 
 __global__ void __launch_bounds__(kBlock) k_joint_backlink(const int* __restrict__ totalPtr, const phyx_contact_joint* __restrict__ joints,
@@ -548,9 +545,8 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         PHYX_CUDA(cudaMemcpyAsync(&fresh, total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         PHYX_CUDA(cudaStreamSynchronize(c->stream));
         PHYX_TRY(c->joints.reserve_keep(size_t(J0 + fresh > 0 ? J0 + fresh : 1) * sizeof(phyx_contact_joint), size_t(J0) * sizeof(phyx_contact_joint), c->stream));
-        PHYX_TRY(c->jointColour.reserve_keep(size_t(J0 + fresh > 0 ? J0 + fresh : 1) * sizeof(int), c->colourStateValid ? size_t(J0) * sizeof(int) : 0, c->stream));
         k_joint_match<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(P, J0, c->manBody.as<int2>(), c->manCount.as<int>(),
-            c->contactPoints.as<float4>(), isNew, newRank, c->joints.as<phyx_contact_joint>(), c->jointColour.as<int>());
+            c->contactPoints.as<float4>(), isNew, newRank, c->joints.as<phyx_contact_joint>());
         c->launches++;
     }
     const int J1 = J0 + fresh;
@@ -564,13 +560,10 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         int* movers = prefix + J1;
         int* total = movers + J1;
         const int grid = (J1 + kBlock - 1) / kBlock;
-        PHYX_TRY(c->jointColour.reserve_keep(size_t(J1) * sizeof(int), c->colourStateValid ? size_t(J0) * sizeof(int) : 0, c->stream));
-        const bool track = c->colourStateValid && c->colourStateBodies == c->bodyCount;
-        k_joint_alive<<<grid, kBlock, 0, c->stream>>>(J1, c->joints.as<phyx_contact_joint>(), alive, c->jointColour.as<int>(),
-            track ? c->bodyUsed.as<unsigned long long>() : nullptr, c->bodyStatic.as<unsigned char>());
+        k_joint_alive<<<grid, kBlock, 0, c->stream>>>(J1, c->joints.as<phyx_contact_joint>(), alive);
         PHYX_TRY(exclusive_scan_i32(c, alive, prefix, J1, total));
         k_list_movers<<<grid, kBlock, 0, c->stream>>>(J1, alive, prefix, total, movers);
-        k_joint_fill<<<grid, kBlock, 0, c->stream>>>(J1, alive, prefix, total, movers, c->joints.as<phyx_contact_joint>(), c->jointColour.as<int>());
+        k_joint_fill<<<grid, kBlock, 0, c->stream>>>(J1, alive, prefix, total, movers, c->joints.as<phyx_contact_joint>());
         k_joint_backlink<<<grid, kBlock, 0, c->stream>>>(total, c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>());
         c->launches += 4;
         PHYX_CUDA(cudaMemcpyAsync(&K, total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -578,6 +571,7 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
     }
     PHYX_CUDA(cudaGetLastError());
     c->jointCount = K;
+    c->jointUnitsValid = true;   // every live contact point now names its joint (solverIndex) and vice versa
     if (created) *created = fresh;
     if (deleted) *deleted = J1 - K;
     if (matched) *matched = K - fresh > 0 ? K - fresh : 0;
@@ -587,6 +581,7 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
 int collide_reset(phyx_b200_ctx* c)
 {
     c->colourStateValid = false;
+    c->jointUnitsValid = false;
     c->manifoldCount = 0;
     c->contactPointCount = 0;
     c->jointCount = 0;

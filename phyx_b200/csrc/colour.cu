@@ -237,25 +237,36 @@ __global__ void __launch_bounds__(kBlock) k_colour_place(int nj, const uint2* __
 
 // Build the colour schedule for the resident joints.  Returns PHYX_B200_ERR_CAPACITY if more than
 // 64 colours are needed (a dynamic body with dozens of joints); the caller then uses the host builder.
-static int colour_schedule_build_once(phyx_b200_ctx* c, bool incremental, bool* staticsChanged);
+static int colour_joints_build(phyx_b200_ctx* c, bool* staticsChanged);
+static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsChanged);
 
-// Incremental by default: joints keep the colour they had last step (the joint cache carries it
-// through its compaction), the per-body colour masks persist, and only joints created this step go
-// through the colouring rounds.  A full rebuild happens on the first call, after the caller replaced
-// the joints, when a body changed between static and dynamic, or when incremental additions have
-// let the number of colours drift upwards.
+// Two colourings.
+//  * Units (resident pipeline): the unit is a MANIFOLD, i.e. the (up to two) joints of one body pair.
+//    Colouring manifolds needs about half the colours of colouring joints (a body has half as many
+//    manifolds as joints), and the two joints of a manifold go to the two halves of one FUSED level: the
+//    same thread relaxes joint A then joint B with no barrier in between (B's bodies are touched by no
+//    other joint of that level, so this equals the colour-major sequential order).  The colouring is
+//    incremental: manifolds keep their colour from step to step (the manifold cache carries it through
+//    PackManifolds, which also hands the colours of removed manifolds back to their bodies), the per-body
+//    colour masks persist, and only manifolds without a colour go through the rounds.  A full rebuild
+//    happens on first use, when a body changes between static and dynamic, or when the colour count has
+//    drifted upwards.
+//  * Joints (host-array API, no manifold information): every joint is a unit; always a full build.
 int colour_schedule_build(phyx_b200_ctx* c)
 {
-    bool incremental = c->colourStateValid && c->colourStateBodies == c->bodyCount && c->jointColour.ptr && c->bodyUsed.ptr;
     bool changed = false;
-    int st = colour_schedule_build_once(c, incremental, &changed);
-    if (st == PHYX_B200_OK && incremental && (changed || c->levelCount > c->coloursAtFullBuild + 6))
-        st = colour_schedule_build_once(c, false, &changed);
+    if (!c->jointUnitsValid || c->manifoldCount == 0) return colour_joints_build(c, &changed);
+    bool incremental = c->colourStateValid && c->colourStateBodies == c->bodyCount && c->manColour.ptr && c->bodyUsed.ptr;
+    int st = colour_units_build(c, incremental, &changed);
+    if (st == PHYX_B200_OK && incremental && (changed || c->levelCount > c->coloursAtFullBuild + 4))
+        st = colour_units_build(c, false, &changed);
     return st;
 }
 
-static int colour_schedule_build_once(phyx_b200_ctx* c, bool incremental, bool* staticsChanged)
+static int colour_joints_build(phyx_b200_ctx* c, bool* staticsChanged)
 {
+    const bool incremental = false;
+
     const int nj = c->jointCount, nb = c->bodyCount;
     c->hostSlots.clear();
     c->hostSlotPos.clear();
@@ -269,17 +280,16 @@ static int colour_schedule_build_once(phyx_b200_ctx* c, bool incremental, bool* 
     // scratch: jb[nj] int2 | colour[nj] int | claim[nb] u64 | used[nb] u64 | counts[64] | firstPos[64] | header[4] | result[4] | barrier[4] u64
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-    const size_t oJb = take(size_t(nj) * sizeof(int2)), oClaim = take(nb1 * 8),
+    const size_t oJb = take(size_t(nj) * sizeof(int2)), oColour = take(size_t(nj) * sizeof(int)), oClaim = take(nb1 * 8),
                  oList0 = take(size_t(nj) * sizeof(int)), oList1 = take(size_t(nj) * sizeof(int)),
                  oCounts = take(kMaxColours * sizeof(int)), oFirst = take(kMaxColours * sizeof(int)), oHeader = take(16), oResult = take(16),
                  oBarrier = take(32), oListCount = take(16);
     PHYX_TRY(c->colourTmp.reserve(off));
     char* base = c->colourTmp.as<char>();
     int2* jb = reinterpret_cast<int2*>(base + oJb);
-    PHYX_TRY(c->jointColour.reserve_keep(size_t(nj) * sizeof(int), incremental ? size_t(nj) * sizeof(int) : 0, c->stream));
-    PHYX_TRY(c->bodyUsed.reserve_keep(nb1 * 8, incremental ? nb1 * 8 : 0, c->stream));
-    PHYX_TRY(c->bodyStatic.reserve_keep(nb1, incremental ? nb1 : 0, c->stream));
-    int* colour = c->jointColour.as<int>();
+    PHYX_TRY(c->bodyUsed.reserve(nb1 * 8));
+    PHYX_TRY(c->bodyStatic.reserve(nb1));
+    int* colour = reinterpret_cast<int*>(base + oColour);
     unsigned long long* claim = reinterpret_cast<unsigned long long*>(base + oClaim);
     unsigned long long* used = c->bodyUsed.as<unsigned long long>();
     int* counts = reinterpret_cast<int*>(base + oCounts);
@@ -351,10 +361,203 @@ static int colour_schedule_build_once(phyx_b200_ctx* c, bool incremental, bool* 
     c->slotCount = host.header[1];
     c->colourRounds = host.result[0];
     *staticsChanged = host.result[3] != 0;
+    c->colourStateValid = false;   // per-joint colours are not carried from step to step
+    c->hostLevels.assign(lv, lv + c->levelCount);
+    c->hostSlotsStale = true;
+    return PHYX_B200_OK;
+}
+
+// ---- manifold units -----------------------------------------------------------------------------------
+
+constexpr int kSkipUnit = kMaxColours;   // working colour of a manifold without contact points
+
+__global__ void __launch_bounds__(kBlock) k_unit_init(int M, const int2* __restrict__ manBody, const int* __restrict__ manCount,
+    const float4* __restrict__ params, int* __restrict__ manColour, int2* __restrict__ jb, int* __restrict__ work, unsigned long long* __restrict__ bodyUsed,
+    bool keepColours)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    int2 b = manBody[m];
+    const float4 p1 = params[b.x], p2 = params[b.y];
+    if (p1.x == 0.0f && p1.y == 0.0f) b.x = -1;
+    if (p2.x == 0.0f && p2.y == 0.0f) b.y = -1;
+    jb[m] = b;
+    const int had = keepColours ? manColour[m] : -1;
+    if (manCount[m] == 0)
+    {
+        // lost its last contact: give the colour back to the bodies
+        if (had >= 0)
+        {
+            const unsigned long long keep = ~(1ull << had);
+            if (b.x >= 0) atomicAnd(&bodyUsed[b.x], keep);
+            if (b.y >= 0) atomicAnd(&bodyUsed[b.y], keep);
+        }
+        manColour[m] = -1;
+        work[m] = kSkipUnit;
+    }
+    else if (b.x < 0 && b.y < 0)
+        work[m] = 0;   // no dynamic body: conflicts with nothing
+    else
+        work[m] = had;
+}
+
+// persist the colours, emit {colour, manifold} sort keys and the per-colour histogram (bin 64 = skipped)
+__global__ void __launch_bounds__(kBlock) k_unit_keys(int M, const int* __restrict__ work, int* __restrict__ manColour, uint2* __restrict__ keys,
+    int* __restrict__ counts)
+{
+    __shared__ int h[kMaxColours + 1];
+    if (threadIdx.x <= kMaxColours) h[threadIdx.x] = 0;
+    __syncthreads();
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < M)
+    {
+        const int c = work[m];
+        manColour[m] = (c == kSkipUnit) ? -1 : c;
+        keys[m] = make_uint2(unsigned(c), unsigned(m));
+        atomicAdd(&h[c], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x <= kMaxColours && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+
+// counts[64] -> paired level table: level k = {start, -1, start + 2*count}, start a multiple of 64; slots
+// 2r and 2r+1 of a level are the first and second joint of its r-th manifold (solve.cu, paired levels)
+__global__ void k_unit_levels(const int* __restrict__ counts, Level* __restrict__ levels, int* __restrict__ firstPos, int* __restrict__ header)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int numLevels = 0;
+    for (int c = 0; c < kMaxColours; ++c)
+        if (counts[c] > 0) numLevels = c + 1;
+    int cursor = 0, run = 0, widest = 0;
+    for (int c = 0; c < numLevels; ++c)
+    {
+        levels[c].start = cursor;
+        levels[c].grouped_end = -1;
+        levels[c].end = cursor + 2 * counts[c];
+        firstPos[c] = run;
+        run += counts[c];
+        widest = max(widest, 2 * counts[c]);
+        cursor = (levels[c].end + 63) & ~63;
+    }
+    header[0] = numLevels;
+    header[1] = cursor;
+    header[2] = widest;
+}
+
+__global__ void __launch_bounds__(kBlock) k_unit_place(int M, const uint2* __restrict__ sorted, const Level* __restrict__ levels,
+    const int* __restrict__ firstPos, const int* __restrict__ manCount, const float4* __restrict__ contactPoints, int* __restrict__ slotJoint)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= M) return;
+    const uint2 e = sorted[p];
+    if (e.x >= unsigned(kMaxColours)) return;   // manifold without contact points
+    const int m = int(e.y);
+    const int slot = levels[e.x].start + 2 * (p - firstPos[e.x]);
+    // the joints of a manifold are the solverIndex of its contact points (World.cpp:100-103,140)
+    slotJoint[slot] = __float_as_int(contactPoints[size_t(2 * m) * 2 + 1].w);
+    slotJoint[slot + 1] = manCount[m] > 1 ? __float_as_int(contactPoints[size_t(2 * m + 1) * 2 + 1].w) : -1;
+}
+
+static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsChanged)
+{
+    const int M = c->manifoldCount, nb = c->bodyCount, nj = c->jointCount;
+    c->hostSlots.clear();
+    c->hostSlotPos.clear();
+    c->hostLevels.clear();
+    c->slotPosValid = false;
+    c->slotCount = c->levelCount = 0;
+    c->strictLevelCount = c->numMultiStatics = 0;
+    if (nj == 0 || M == 0) return PHYX_B200_OK;
+
+    const size_t nb1 = size_t(nb > 0 ? nb : 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    const size_t oJb = take(size_t(M) * sizeof(int2)), oWork = take(size_t(M) * sizeof(int)), oClaim = take(nb1 * 8),
+                 oList0 = take(size_t(M) * sizeof(int)), oList1 = take(size_t(M) * sizeof(int)),
+                 oCounts = take((kMaxColours + 1) * sizeof(int)), oFirst = take(kMaxColours * sizeof(int)), oHeader = take(16), oResult = take(16),
+                 oBarrier = take(32), oListCount = take(16);
+    PHYX_TRY(c->colourTmp.reserve(off));
+    char* base = c->colourTmp.as<char>();
+    int2* jb = reinterpret_cast<int2*>(base + oJb);
+    int* work = reinterpret_cast<int*>(base + oWork);
+    PHYX_TRY(c->manColour.reserve_keep(size_t(M) * sizeof(int), incremental ? size_t(M) * sizeof(int) : 0, c->stream));
+    PHYX_TRY(c->bodyUsed.reserve_keep(nb1 * 8, incremental ? nb1 * 8 : 0, c->stream));
+    PHYX_TRY(c->bodyStatic.reserve_keep(nb1, incremental ? nb1 : 0, c->stream));
+    unsigned long long* claim = reinterpret_cast<unsigned long long*>(base + oClaim);
+    unsigned long long* used = c->bodyUsed.as<unsigned long long>();
+    int* counts = reinterpret_cast<int*>(base + oCounts);
+    int* firstPos = reinterpret_cast<int*>(base + oFirst);
+    int* header = reinterpret_cast<int*>(base + oHeader);
+    int* result = reinterpret_cast<int*>(base + oResult);
+    unsigned long long* barrier = reinterpret_cast<unsigned long long*>(base + oBarrier);
+
+    PHYX_CUDA(cudaMemsetAsync(claim, 0xff, nb1 * 8, c->stream));
+    if (!incremental) PHYX_CUDA(cudaMemsetAsync(used, 0, nb1 * 8, c->stream));
+    PHYX_CUDA(cudaMemsetAsync(base + oCounts, 0, off - oCounts, c->stream));   // counts .. list counters
+
+    const int grid = (M + kBlock - 1) / kBlock;
+    if (nb > 0)
+    {
+        k_colour_body_flags<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, c->params.as<float4>(), c->bodyStatic.as<unsigned char>(), incremental, result);
+        c->launches++;
+    }
+    k_unit_init<<<grid, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(), c->params.as<float4>(), c->manColour.as<int>(), jb, work,
+        used, incremental);
+    c->launches++;
+
+    if (c->colourBlocksPerSM == 0)
+    {
+        int per = 0;
+        PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_colour_rounds, kBlock, 0));
+        c->colourBlocksPerSM = per > 0 ? per : 1;
+    }
+    ColourParams P = { M, jb, work, claim, used, { reinterpret_cast<int*>(base + oList0), reinterpret_cast<int*>(base + oList1) },
+        reinterpret_cast<int*>(base + oListCount), barrier, result };
+    int cgrid = std::max(1, std::min(grid, c->numSMs * c->colourBlocksPerSM));
+    void* args[] = { &P };
+    PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_colour_rounds, dim3(cgrid), dim3(kBlock), args, 0, c->stream));
+    c->launches++;
+
+    // colour-major layout of the manifolds: stable counting sort on a 7-bit digit (bin 64 = skipped)
+    PHYX_TRY(c->colourKeys.reserve(size_t(M) * sizeof(uint2)));
+    PHYX_TRY(c->colourSorted.reserve(size_t(M) * sizeof(uint2)));
+    k_unit_keys<<<grid, kBlock, 0, c->stream>>>(M, work, c->manColour.as<int>(), c->colourKeys.as<uint2>(), counts);
+    c->launches++;
+    PHYX_TRY(radix_pass(c, c->colourKeys.as<uint2>(), c->colourSorted.as<uint2>(), M, 0, 2 * kMaxColours));
+    PHYX_TRY(c->levels.reserve(kMaxColours * sizeof(Level)));
+    k_unit_levels<<<1, 32, 0, c->stream>>>(counts, c->levels.as<Level>(), firstPos, header);
+    c->launches++;
+    const size_t maxSlots = 2 * size_t(M) + 64 * kMaxColours;
+    PHYX_TRY(c->slotJoint.reserve(maxSlots * sizeof(int)));
+    PHYX_CUDA(cudaMemsetAsync(c->slotJoint.ptr, 0xff, maxSlots * sizeof(int), c->stream));
+    k_unit_place<<<grid, kBlock, 0, c->stream>>>(M, c->colourSorted.as<uint2>(), c->levels.as<Level>(), firstPos, c->manCount.as<int>(),
+        c->contactPoints.as<float4>(), c->slotJoint.as<int>());
+    c->launches++;
+    PHYX_CUDA(cudaGetLastError());
+
+    struct { int header[4]; int result[4]; int counts[kMaxColours + 1]; } host;
+    PHYX_CUDA(cudaMemcpyAsync(host.header, header, 16, cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaMemcpyAsync(host.result, result, 16, cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaMemcpyAsync(host.counts, counts, sizeof(host.counts), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    if (host.result[1])
+    {
+        set_error("colouring needs more than %d colours", kMaxColours);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    c->levelCount = host.header[0];
+    c->slotCount = host.header[1];
+    c->colourRounds = host.result[0];
+    *staticsChanged = host.result[3] != 0;
     c->colourStateValid = true;
     c->colourStateBodies = nb;
     if (!incremental) c->coloursAtFullBuild = c->levelCount;
-    c->hostLevels.assign(lv, lv + c->levelCount);
+    int cursor = 0;
+    for (int k = 0; k < c->levelCount; ++k)
+    {
+        c->hostLevels.push_back({ cursor, -1, cursor + 2 * host.counts[k] });
+        cursor = (cursor + 2 * host.counts[k] + 63) & ~63;
+    }
     c->hostSlotsStale = true;
     return PHYX_B200_OK;
 }

@@ -138,10 +138,11 @@ struct phyx_b200_ctx
     phyx::DevBuf colourKeys, colourSorted;   // uint2 {colour, joint} before / after the counting sort
     bool hostSlotsStale = false; // schedule lives on the device only; get_schedule fetches it on demand
     // persistent colouring state (incremental recolouring of the joint cache)
-    phyx::DevBuf jointColour;    // int per joint, moves with the joint through the cache compaction; -1 = not coloured yet
-    phyx::DevBuf bodyUsed;       // u64 per body: colours taken by its joints
+    phyx::DevBuf manColour;      // int per manifold, moves with it through PackManifolds; -1 = none (no contact points yet)
+    phyx::DevBuf bodyUsed;       // u64 per body: colours taken by its manifolds
     phyx::DevBuf bodyStatic;     // u8 per body: static flag the colouring was built with
     bool colourStateValid = false;
+    bool jointUnitsValid = false;   // joints are exactly the contact points of the resident manifolds (set by RefreshContactJoints)
     int colourStateBodies = 0, coloursAtFullBuild = 0;
     std::vector<int> hostSlotPos;
     std::vector<int> hostSlots;  // last schedule (host copy, for get_schedule / KEEP_SCHEDULE)

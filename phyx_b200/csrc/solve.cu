@@ -612,6 +612,216 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve(SolveParams P)
 }
 
 // =====================================================================================================
+// Paired levels (manifold-unit colouring, colour.cu)
+// =====================================================================================================
+// A paired level holds whole manifolds: slots 2u and 2u+1 are the two joints of one body pair (2u+1 is
+// empty when the manifold has one contact point).  No other unit of the level touches these two bodies,
+// so ONE thread relaxes both joints back to back on the same two body rows held in registers: half the
+// levels (grid barriers) per iteration, and half the row gathers / scatters per joint.  The result is
+// that of the sequential sweep in slot order: joint 2u+1 follows 2u directly, it sees exactly the rows
+// 2u left, and since both joints have the same bodies the skip test (Solver.cpp:790-798) gives the
+// same answer for both: if 2u runs, lastIteration of its bodies can only have grown, so 2u+1 runs;
+// if 2u is skipped nothing changed, so 2u+1 is skipped.
+template <int PHASE>
+struct PairData
+{
+    float4 a0, a1, a2, a3;   // streams of slot 2u
+    float4 b0, b1, b2, b3;   // streams of slot 2u+1
+    float4 acc;              // impulse: {accN, accF} of 2u, {accN, accF} of 2u+1; displacement: {accD 2u, accD 2u+1, -, -}
+};
+
+template <int PHASE>
+__device__ __forceinline__ void load_pair(const SolveParams& P, int s, bool inRange, PairData<PHASE>& d)
+{
+    d.a3 = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
+    if (inRange)
+    {
+        d.a3 = __ldcs(&P.q3[s]);
+        d.b3 = __ldcs(&P.q3[s + 1]);
+        d.a0 = __ldcs(&P.q0[s]);
+        d.b0 = __ldcs(&P.q0[s + 1]);
+        d.a2 = __ldcs(&P.q2[s]);
+        d.b2 = __ldcs(&P.q2[s + 1]);
+        if (PHASE == 0)
+        {
+            d.a1 = __ldcs(&P.q1[s]);
+            d.b1 = __ldcs(&P.q1[s + 1]);
+            d.acc = __ldcs(reinterpret_cast<const float4*>(&P.accNF[s]));   // s is even: 16-byte aligned
+        }
+        else
+        {
+            const float2 a = __ldcs(reinterpret_cast<const float2*>(&P.accD[s]));
+            d.acc = make_float4(a.x, a.y, 0.f, 0.f);
+        }
+    }
+}
+
+__device__ __forceinline__ void prestep_pair(const SolveParams& P, int s)
+{
+    const float4 c3 = __ldcs(&P.q3[s]);
+    const int r1 = __float_as_int(c3.x), r2 = __float_as_int(c3.y);
+    if (r1 < 0) return;
+    const int b1 = r1 & kBodyMask, b2 = r2 & kBodyMask;
+    float4 v1 = __ldcg(&P.vel[b1]), v2 = __ldcg(&P.vel[b2]);
+    const float4 accs = __ldcs(reinterpret_cast<const float4*>(&P.accNF[s]));
+    const bool haveB = __float_as_int(__ldcs(&P.q3[s + 1]).x) >= 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+    {
+        if (h == 1 && !haveB) break;
+        const float4 c0 = __ldcs(&P.q0[s + h]), c1 = __ldcs(&P.q1[s + h]), c2 = __ldcs(&P.q2[s + h]);
+        const float nx = c0.x, ny = c0.y;
+        const float accN = h ? accs.z : accs.x, accF = h ? accs.w : accs.y;
+        v1.x += (nx * c2.x) * accN;
+        v1.y += (ny * c2.x) * accN;
+        v1.z += (c0.z * c2.y) * accN;
+        v2.x += ((-nx) * c2.z) * accN;
+        v2.y += ((-ny) * c2.z) * accN;
+        v2.z += (c0.w * c2.w) * accN;
+        const float tx = -ny, ty = nx;
+        v1.x += (tx * c2.x) * accF;
+        v1.y += (ty * c2.x) * accF;
+        v1.z += (c1.x * c2.y) * accF;
+        v2.x += ((-tx) * c2.z) * accF;
+        v2.y += ((-ty) * c2.z) * accF;
+        v2.z += (c1.y * c2.w) * accF;
+    }
+    if (!(r1 & kStaticBit)) __stcg(&P.vel[b1], v1);
+    if (!(r2 & kStaticBit)) __stcg(&P.vel[b2], v2);
+}
+
+template <int PHASE>
+__device__ __forceinline__ bool solve_pairs(const SolveParams& P, const Level L, int it, int tick, bool firstPass, int tid, int nthreads, bool& wake,
+    unsigned& activeCount, PairData<PHASE>& pre, bool havePre)
+{
+    float4* rows = PHASE == 0 ? P.vel : P.disp;
+    unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
+    bool anyProductive = false;
+    for (int s = L.start + 2 * tid; s < L.end; s += 2 * nthreads)
+    {
+        if (!havePre) load_pair<PHASE>(P, s, true, pre);
+        havePre = false;
+        const int r1 = __float_as_int(pre.a3.x), r2 = __float_as_int(pre.a3.y);
+        if (r1 < 0) continue;
+        const int b1 = r1 & kBodyMask, b2 = r2 & kBodyMask;
+        const bool st1 = r1 & kStaticBit, st2 = r2 & kStaticBit;
+        if (!firstPass && (!(st1 || st2) || __ldcg(&P.processed[s]) == tick)) continue;   // wake pass: only pairs a static body can wake
+
+        float4 v1 = __ldcg(&rows[b1]), v2 = __ldcg(&rows[b2]);
+        const unsigned pos = unsigned(s);
+        const int last1 = st1 ? static_visible_last(&statics[b1], it, pos) : __float_as_int(v1.w);
+        const int last2 = st2 ? static_visible_last(&statics[b2], it, pos) : __float_as_int(v2.w);
+        if (!((last1 > it - 2) || (last2 > it - 2))) continue;   // Solver.cpp:790-792, for both joints (see above)
+
+        const bool haveB = __float_as_int(pre.b3.x) >= 0;
+        activeCount += haveB ? 2u : 1u;
+        float2 accA = make_float2(pre.acc.x, PHASE == 0 ? pre.acc.y : 0.f);
+        float2 accB = PHASE == 0 ? make_float2(pre.acc.z, pre.acc.w) : make_float2(pre.acc.y, 0.f);
+        const bool productiveA = relax<PHASE>(pre.a0, pre.a1, pre.a2, pre.a3, accA, v1, v2, false);
+        bool productiveB = false;
+        if (haveB) productiveB = relax<PHASE>(pre.b0, pre.b1, pre.b2, pre.b3, accB, v1, v2, false);
+        if (PHASE == 0)
+            __stcs(reinterpret_cast<float4*>(&P.accNF[s]), make_float4(accA.x, accA.y, accB.x, accB.y));
+        else
+            __stcs(reinterpret_cast<float2*>(&P.accD[s]), make_float2(accA.x, accB.x));
+
+        // lastIteration = it where productive (Solver.cpp:903-910); a static body is marked at the position
+        // of the first productive joint
+        const bool productive = productiveA || productiveB;
+        const unsigned markPos = productiveA ? pos : pos + 1;
+        if (!st1)
+        {
+            v1.w = __int_as_float(productive ? it : last1);
+            __stcg(&rows[b1], v1);
+        }
+        else if (productive)
+            wake |= static_mark(&statics[b1], it, markPos, nullptr);
+        if (!st2)
+        {
+            v2.w = __int_as_float(productive ? it : last2);
+            __stcg(&rows[b2], v2);
+        }
+        else if (productive)
+            wake |= static_mark(&statics[b2], it, markPos, nullptr);
+        if (st1 || st2) __stcg(&P.processed[s], tick);
+        anyProductive |= productive;
+    }
+    return anyProductive;
+}
+
+template <int PHASE>
+__device__ __forceinline__ int run_phase_pairs(const SolveParams& P, int iters, int tid, int nthreads, unsigned& epoch, int& tick, int& wakePasses,
+    unsigned& activeCount)
+{
+    PairData<PHASE> pre;
+    bool havePre = false;
+    int ran = 0;
+    for (int it = 0; it < iters; ++it)
+    {
+        bool any = false, productiveAnywhere = false;
+        for (int l = 0; l < P.numLevels; ++l)
+        {
+            const Level L = P.levels[l];
+            ++tick;
+            bool wake = false;
+            any |= solve_pairs<PHASE>(P, L, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre);
+            // streams of this thread's first pair of the level that follows, fetched while the grid drains into the barrier
+            const Level N = P.levels[l + 1 < P.numLevels ? l + 1 : 0];
+            const int sN = N.start + 2 * tid;
+            havePre = sN < N.end;
+            if (havePre) load_pair<PHASE>(P, sN, true, pre);
+            BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
+            timeline_mark(P, tick);
+            while (r.wake)
+            {
+                PairData<PHASE> scratch;
+                wake = false;
+                any |= solve_pairs<PHASE>(P, L, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
+                ++wakePasses;
+                r = grid_barrier(P.barrier, epoch, wake, any);
+            }
+            productiveAnywhere = r.productive;
+        }
+        ++ran;
+        if (!productiveAnywhere) break;   // Solver.cpp:189 / :210
+    }
+    return ran;
+}
+
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve_pairs(SolveParams P)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    unsigned epoch = 0;
+    int wakePasses = 0, tick = 0;
+    unsigned active[2] = { 0u, 0u };
+
+    for (int l = 0; l < P.numLevels; ++l)
+    {
+        const Level L = P.levels[l];
+        for (int s = L.start + 2 * tid; s < L.end; s += 2 * nthreads) prestep_pair(P, s);
+        grid_barrier(P.barrier, epoch, false, false);
+    }
+
+    const int ranImpulse = run_phase_pairs<0>(P, P.contactIters, tid, nthreads, epoch, tick, wakePasses, active[0]);
+    const int ranDisplacement = run_phase_pairs<1>(P, P.penetrationIters, tid, nthreads, epoch, tick, wakePasses, active[1]);
+
+    for (int phase = 0; phase < 2; ++phase)
+    {
+        unsigned v = active[phase];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.activeTotal[phase], static_cast<unsigned long long>(v));
+    }
+    if (tid == 0)
+    {
+        P.result[0] = ranImpulse;
+        P.result[1] = ranDisplacement;
+        P.result[2] = wakePasses;
+    }
+}
+
+// =====================================================================================================
 // TMA-staged variant of the solve kernel
 // =====================================================================================================
 // Same algorithm, different data movement.  Each CTA owns every gridDim.x-th chunk of kU*256 slots of
@@ -1027,9 +1237,11 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         static const int shapeEnv = getenv("PHYX_SOLVE_SHAPE") ? atoi(getenv("PHYX_SOLVE_SHAPE")) : 5122;
         int sblock = 512;
         void* solveKernel = nullptr;
-#define PHYX_PICK(T, B) (dual ? (void*)k_solve<T, B, true> : (void*)k_solve<T, B, false>)
-        switch (shapeEnv)
+        const bool paired = !c->hostLevels.empty() && c->hostLevels[0].grouped_end < 0;   // manifold units: all levels are paired
+#define PHYX_PICK(T, B) (paired ? (void*)k_solve_pairs<T, B> : dual ? (void*)k_solve<T, B, true> : (void*)k_solve<T, B, false>)
+        switch (paired && !getenv("PHYX_SOLVE_SHAPE") ? 2562 : shapeEnv)
         {
+        case 2562: sblock = 256; solveKernel = PHYX_PICK(256, 2); break;
         case 2564: sblock = 256; solveKernel = PHYX_PICK(256, 4); break;
         case 2563: sblock = 256; solveKernel = PHYX_PICK(256, 3); break;
         case 5121: sblock = 512; solveKernel = PHYX_PICK(512, 1); break;
@@ -1050,13 +1262,14 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         // persistent grid: every SM full, but no more CTAs than the widest level can use
         int maxLevel = 0;
         for (const Level& L : c->hostLevels) maxLevel = max(maxLevel, L.end - L.start);
+        if (paired) maxLevel = (maxLevel + 1) / 2;   // one thread per pair
         int want = (maxLevel + sblock - 1) / sblock;
         int sgrid = max(1, min(want, c->numSMs * c->solveBlocksPerSM));
         // Default: the register-prefetch kernel (fastest measured).  PHYX_SOLVE_KERNEL=pipe
         // selects the TMA-staged one; PHYX_SOLVE_PIPE="<slots per thread><stages>" (e.g. 12, 23) its shape.
         static const char* kernelEnv = getenv("PHYX_SOLVE_KERNEL");
         static const char* pipeEnv = getenv("PHYX_SOLVE_PIPE");
-        if (dual || !(kernelEnv && !strcmp(kernelEnv, "pipe")))   // the strict companion schedule is a direct-kernel feature
+        if (dual || paired || !(kernelEnv && !strcmp(kernelEnv, "pipe")))   // strict companions and paired levels are direct-kernel features
         {
             void* args[] = { &P };
             PHYX_CUDA(cudaLaunchCooperativeKernel(solveKernel, dim3(sgrid), dim3(sblock), args, 0, c->stream));

@@ -72,12 +72,22 @@ def test_colour_solve_is_bit_equal_to_oracle_on_same_schedule(ctx, oracle, name)
 
 
 def check_schedule(slots, levels, joints, bodies):
-    """Every joint exactly once; inside a level no dynamic body appears twice."""
+    """Every joint exactly once; inside a level no dynamic body appears twice.  A paired level
+    (grouped_end < 0, manifold units) holds the two joints of one body pair in slots 2u, 2u+1: the pair
+    counts as one unit."""
     used = slots[slots >= 0]
     assert sorted(used.tolist()) == list(range(joints.shape[0]))
     static = (bodies["invMass"] == 0) & (bodies["invInertia"] == 0)
     for lv in levels:
         s = slots[lv["start"]:lv["end"]]
+        if lv["grouped_end"] < 0:
+            assert lv["start"] % 2 == 0 and s.size % 2 == 0
+            a, b = s[0::2], s[1::2]
+            assert np.all(a >= 0)
+            two = b >= 0
+            assert np.array_equal(joints["body1Index"][a[two]], joints["body1Index"][b[two]])
+            assert np.array_equal(joints["body2Index"][a[two]], joints["body2Index"][b[two]])
+            s = a
         s = s[s >= 0]
         bs = np.concatenate([joints["body1Index"][s], joints["body2Index"][s]])
         bs = bs[~static[bs]]

@@ -123,8 +123,8 @@ def test_mirrors_can_be_switched_off(ref):
 
 @pytest.mark.parametrize("scene,steps", [("stack_1k", 60), ("pyramid_1k", 25)])
 def test_incremental_colouring_stays_valid_and_exact(oracle, scene, steps):
-    """Colour mode over many resident steps: the joint cache carries colours from step to step and only
-    new joints are coloured.  Every step the schedule must still be a proper colouring, and the solve
+    """Colour mode over many resident steps: the manifold cache carries colours from step to step and only
+    manifolds without one are coloured.  Every step the schedule must still be a proper colouring, and the solve
     must equal the oracle's sequential sweep in slot order, bit for bit."""
     from test_gpu_hotpath import check_schedule, VEL_FIELDS
 
@@ -152,6 +152,52 @@ def test_incremental_colouring_stays_valid_and_exact(oracle, scene, steps):
         ctx.integrate_position(scenes.DT)
     # after the first (full) build, later steps only colour the few new joints
     assert min(rounds[1:]) < rounds[0]
+
+
+def test_unit_colouring_is_priority_first_fit_over_manifolds():
+    """Resident colour schedule: the unit is the manifold.  A full build must equal sequential first-fit over
+    the manifolds in priority order (deterministic), and lay the joints of a manifold out as slot pairs."""
+    from test_gpu_hotpath import check_schedule, _mix32
+
+    w = world.World(scenes.make("pyramid_1k"))
+    ctx = w.context()
+    ctx.upload_bodies(w.bodies())
+    ctx.integrate_velocity(scenes.DT, scenes.GRAVITY)
+    ctx.update_broadphase()
+    ctx.update_pairs()
+    ctx.update_manifolds()
+    ctx.pack_manifolds()
+    ctx.refresh_contact_joints()
+    bodies, joints, man = ctx.download_bodies(), ctx.download_joints(), ctx.download_manifolds()
+    ctx.solve_resident(schedule=capi.SCHEDULE_COLOUR)
+    slots, levels = ctx.get_schedule()
+    check_schedule(slots, levels, joints, bodies)
+    assert np.all(levels["grouped_end"] < 0)
+    got = np.full(man.shape[0], -1)
+    for c, lv in enumerate(levels):
+        a = slots[lv["start"]:lv["end"]:2]
+        b = slots[lv["start"] + 1:lv["end"]:2]
+        m = joints["contactPointIndex"][a] // 2
+        assert np.all(np.diff(m) > 0)                                  # manifold order inside a colour
+        assert np.array_equal(joints["contactPointIndex"][a], 2 * m)   # first point, then second
+        assert np.array_equal(joints["contactPointIndex"][b[b >= 0]], 2 * m[b >= 0] + 1)
+        assert np.array_equal(b >= 0, man["pointCount"][m] > 1)
+        got[m] = c
+    static = (bodies["invMass"] == 0) & (bodies["invInertia"] == 0)
+    used = {}
+    want = np.full(man.shape[0], -1)
+    for m in sorted(range(man.shape[0]), key=lambda m: (_mix32(m), m)):
+        if man["pointCount"][m] == 0:
+            continue
+        bs = [b for b in (int(man["body1Index"][m]), int(man["body2Index"][m])) if not static[b]]
+        taken = set().union(*[used.get(b, set()) for b in bs]) if bs else set()
+        c = 0
+        while c in taken:
+            c += 1
+        want[m] = c
+        for b in bs:
+            used.setdefault(b, set()).add(c)
+    assert np.array_equal(got, want)
 
 
 def test_more_than_64_colours_falls_back_to_the_host_builder(oracle):
