@@ -42,7 +42,7 @@ BYTES_IMPULSE, BYTES_DISPLACEMENT, BYTES_PRESTEP, BYTES_SKIP = 196, 136, 128, 40
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="pyramid_1m")
@@ -53,45 +53,97 @@ def parse():
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region: the counters of the B200_PROFILING.md
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.*` line, read through
+    NVML (the library nvidia-smi itself prints from) by a thread of this process every 20 ms.  Spawning
+    nvidia-smi next to the timed loop was measured to stall the step's host<->driver round trips (its start-up
+    enumerates every GPU of the box under the driver lock: 11.4 ms per step instead of 3.5 ms), so the
+    subprocess form is only the fallback when pynvml is missing, and it is started BEFORE the warm-up steps."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def __enter__(self):
+        self.index, self.rows, self.proc, self.nvml, self.handle = index, [], None, None, None
+        self.recording, self.stop = False, False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.source = "NVML (pynvml), 20 ms period"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+        except Exception:
+            self.nvml = None
+            self.source = "nvidia-smi -lms 100"
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except OSError:
+                self.proc = None
             self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
-        return self
+        self.thread.start()
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop:
+            if self.recording:
+                try:
+                    sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.rows.append((sm, self.mx, mask))
+                except Exception:
+                    pass
+            time.sleep(0.02)
 
     def _read(self):
+        if not self.proc:
+            return
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.12)
-            self.proc.terminate()
-            self.thread.join(timeout=2)
-
-    def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+            if not self.recording:
+                continue
+            r = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
+                mask = 0
+                for (name, bit), v in zip(self.REASONS, r[3:7]):
+                    if v.lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((float(r[0]), float(r[1]), mask))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def __enter__(self):
+        self.rows.clear()
+        self.recording = True
+        return self
+
+    def __exit__(self, *a):
+        if len(self.rows) < 2:
+            time.sleep(0.05)   # a very short timed region: take the samples right behind it (clocks do not drop within 50 ms)
+        self.recording = False
+
+    def close(self):
+        self.stop = True
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm = [r[0] for r in self.rows]
+        mx = max([r[1] for r in self.rows], default=0.0)
+        reasons = sorted({name for r in self.rows for name, bit in self.REASONS if r[2] & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def measured_peak():
@@ -208,18 +260,20 @@ def run_ours(args, rank, world_size, local_rank):
         ctx.integrate_position(scenes.DT)
         return bp, st
 
+    clocks = ClockSampler(local_rank)   # started before the warm-up so that its start-up cost is not in the timed region
     for _ in range(max(args.warmup, 3)):
         resident_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.launch_count()
     stats = []
-    with ClockSampler(local_rank) as clocks:
+    with clocks:
         e0.record(stream)
         for _ in range(args.steps):
             stats.append(resident_step())
         e1.record(stream)
         barrier()
+    clocks.close()
     launches = ctx.launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps

@@ -209,6 +209,35 @@ PHYX_B200_API int phyx_b200_download_joints(phyx_b200_ctx* ctx, phyx_contact_joi
 PHYX_B200_API int phyx_b200_upload_collider(phyx_b200_ctx* ctx, const phyx_manifold* manifolds, int manifoldCount,
     const phyx_contact_point* contactPoints, const phyx_contact_joint* joints, int jointCount);
 
+/* ---- one world over several devices (an island that spans devices) ------------------------ */
+/* The reference has no counterpart (one process, one address space); in its terms this is Solver::SolveJoints
+ * (src/Solver.cpp:68-215) of ONE island executed by `ranks` devices.  Every rank holds the whole world and
+ * runs the other stages redundantly (deterministic, so the replicas stay bit-identical); the solve is split by
+ * solver row (sorted-x order): a rank relaxes the manifolds whose dynamic bodies lie in its row range, all
+ * ranks relax the few manifolds that straddle a cut, and the rows those touch ("ghost bodies") travel between
+ * the devices once per pass (warm start, every impulse iteration, every displacement iteration) over NVLink
+ * peer memory.  Results equal the one-device sweep over the same slot order (phyx_b200_get_schedule), with
+ * static bodies' lastIteration tracked per rank.
+ *
+ * partition_create allocates this rank's exchange buffer (boundaryCapacity rows per peer and pass, bulkBytes
+ * per peer for the end-of-solve exchange: 32 B per body + 8 B per schedule slot of the largest rank) and
+ * returns its CUDA IPC handle (64 bytes) and/or its device pointer; partition_attach receives the handles of
+ * all ranks (ranks x 64 bytes, other processes) or their pointers (same process; peerDevices may name the
+ * devices so that peer access gets enabled). */
+PHYX_B200_API int phyx_b200_partition_create(phyx_b200_ctx* ctx, int rank, int ranks, int boundaryCapacity, size_t bulkBytes,
+    void* ipcHandleOut, void** localPointerOut);
+PHYX_B200_API int phyx_b200_partition_attach(phyx_b200_ctx* ctx, const void* ipcHandles, void* const* localPointers, const int* peerDevices);
+PHYX_B200_API int phyx_b200_partition_destroy(phyx_b200_ctx* ctx);
+/* the plan of the last partitioned schedule: row cuts [ranks+1], first boundary row of each rank in the boundary
+ * list [ranks+1], first slot of each class [ranks+2] (class `ranks` = the cut manifolds); any may be NULL */
+PHYX_B200_API int phyx_b200_partition_plan(phyx_b200_ctx* ctx, int32_t* cuts, int32_t* boundaryStart, int32_t* classSlotStart);
+/* Solver::SolveJoints on the resident joint cache, this rank's share; collective: every rank's process calls
+ * it for the same step.  A rank whose peers do not show up gives up after 4 s with PHYX_B200_ERR_STATE. */
+PHYX_B200_API int phyx_b200_solve_partitioned(phyx_b200_ctx* ctx, const phyx_b200_solve_config* config, phyx_b200_solve_stats* stats);
+/* the same for all ranks living in ONE process (group[k] is rank k; stats has `count` entries or is NULL) */
+PHYX_B200_API int phyx_b200_solve_partitioned_group(phyx_b200_ctx* const* group, int count, const phyx_b200_solve_config* config,
+    phyx_b200_solve_stats* stats);
+
 /* ---- device-resident variants (inputs already in HBM; used for kernel-only timing) ------------ */
 /* Stage joints + contact points in HBM once ... */
 PHYX_B200_API int phyx_b200_stage_joints(phyx_b200_ctx* ctx, const phyx_contact_joint* joints, int jointCount,

@@ -57,6 +57,12 @@ EXPORTS = (
     "phyx_b200_download_contact_points",
     "phyx_b200_download_joints",
     "phyx_b200_upload_collider",
+    "phyx_b200_partition_create",
+    "phyx_b200_partition_attach",
+    "phyx_b200_partition_destroy",
+    "phyx_b200_partition_plan",
+    "phyx_b200_solve_partitioned",
+    "phyx_b200_solve_partitioned_group",
 )
 
 
@@ -152,6 +158,12 @@ def load():
     l.phyx_b200_download_contact_points.argtypes = [vp, vp, i32]
     l.phyx_b200_download_joints.argtypes = [vp, vp, i32]
     l.phyx_b200_upload_collider.argtypes = [vp, vp, i32, vp, vp, i32]
+    l.phyx_b200_partition_create.argtypes = [vp, i32, i32, i32, C.c_size_t, vp, C.POINTER(vp)]
+    l.phyx_b200_partition_attach.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(i32)]
+    l.phyx_b200_partition_destroy.argtypes = [vp]
+    l.phyx_b200_partition_plan.argtypes = [vp, vp, vp, vp]
+    l.phyx_b200_solve_partitioned.argtypes = [vp, C.POINTER(SolveConfig), C.POINTER(SolveStats)]
+    l.phyx_b200_solve_partitioned_group.argtypes = [C.POINTER(vp), i32, C.POINTER(SolveConfig), C.POINTER(SolveStats)]
     _LIB = l
     return l
 
@@ -323,6 +335,34 @@ class Context:
         levels = np.zeros(nl.value, dtype=LEVEL)
         self._check(self.l.phyx_b200_get_schedule(self.h, _p(slots), ns.value, _p(levels), nl.value, C.byref(ns), C.byref(nl)))
         return slots, levels
+
+    # ---- one world over several devices (phyx_b200/partition.py drives these) ----
+    def partition_create(self, rank, ranks, boundary_capacity, bulk_bytes):
+        """Returns (ipc_handle: 64 bytes, device pointer of this rank's exchange buffer)."""
+        handle = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        self._check(self.l.phyx_b200_partition_create(self.h, rank, ranks, boundary_capacity, bulk_bytes, handle, C.byref(ptr)))
+        return handle.raw, int(ptr.value or 0)
+
+    def partition_attach(self, ranks, ipc_handles=None, local_pointers=None, peer_devices=None):
+        hbuf = C.create_string_buffer(b"".join(ipc_handles), 64 * ranks) if ipc_handles is not None else None
+        ptrs = (C.c_void_p * ranks)(*local_pointers) if local_pointers is not None else None
+        devs = (C.c_int * ranks)(*peer_devices) if peer_devices is not None else None
+        self._check(self.l.phyx_b200_partition_attach(self.h, hbuf, ptrs, devs))
+
+    def partition_destroy(self):
+        self._check(self.l.phyx_b200_partition_destroy(self.h))
+
+    def partition_plan(self, ranks):
+        cuts, bstart, cls = np.zeros(ranks + 1, np.int32), np.zeros(ranks + 1, np.int32), np.zeros(ranks + 2, np.int32)
+        self._check(self.l.phyx_b200_partition_plan(self.h, _p(cuts), _p(bstart), _p(cls)))
+        return cuts, bstart, cls
+
+    def solve_partitioned(self, iters=(20, 20)):
+        cfg = SolveConfig(iters[0], iters[1], SCHEDULE_COLOUR, 0)
+        stats = SolveStats()
+        self._check(self.l.phyx_b200_solve_partitioned(self.h, C.byref(cfg), C.byref(stats)))
+        return stats
 
     def launch_count(self):
         return int(self.l.phyx_b200_launch_count(self.h))

@@ -158,10 +158,11 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    part_destroy(c);
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
-        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->timeline, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->locKeysA, &c->locKeysB, &c->locOrder, &c->locRowOf, &c->locStats };
+        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->timeline, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->locKeysA, &c->locKeysB, &c->locOrder, &c->locRowOf, &c->locStats, &c->pairQ, &c->pairIdx };
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -358,6 +359,163 @@ int phyx_b200_solve_staged(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, 
         stats->ms_total = elapsed_ms(t0, t2);
     }
     return PHYX_B200_OK;
+}
+
+// ---- one world over several devices ---------------------------------------------------------------------
+
+int phyx_b200_partition_create(phyx_b200_ctx* c, int rank, int ranks, int boundaryCapacity, size_t bulkBytes, void* ipcHandleOut, void** localPointerOut)
+{
+    PHYX_TRY(check(c));
+    return part_create(c, rank, ranks, boundaryCapacity, bulkBytes, ipcHandleOut, localPointerOut);
+}
+
+int phyx_b200_partition_attach(phyx_b200_ctx* c, const void* ipcHandles, void* const* localPointers, const int* peerDevices)
+{
+    PHYX_TRY(check(c));
+    return part_attach(c, ipcHandles, localPointers, peerDevices);
+}
+
+int phyx_b200_partition_destroy(phyx_b200_ctx* c)
+{
+    PHYX_TRY(check(c));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    part_destroy(c);
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_partition_plan(phyx_b200_ctx* c, int32_t* cuts, int32_t* boundaryStart, int32_t* classSlotStart)
+{
+    PHYX_TRY(check(c));
+    const Partition& pt = c->part;
+    if (pt.ranks < 2 || !pt.planValid)
+    {
+        set_error("partition_plan: no partitioned schedule has been built yet");
+        return PHYX_B200_ERR_STATE;
+    }
+    for (int q = 0; q <= pt.ranks; ++q)
+    {
+        if (cuts) cuts[q] = pt.cuts[q];
+        if (boundaryStart) boundaryStart[q] = pt.bStart[q];
+    }
+    if (classSlotStart)
+        for (int q = 0; q <= pt.ranks + 1; ++q) classSlotStart[q] = pt.classSlotStart[q];
+    return PHYX_B200_OK;
+}
+
+// The passes of one partitioned solve over a set of contexts.  One context per process: `count` is 1 and the
+// kernels themselves wait for the peers' flags.  Several contexts in ONE process (tests, or one host process
+// driving several devices): every pass is issued on all of them before the next one, and an event of each
+// context orders "has sent" before the others' "takes over" (two cooperative kernels of one device cannot
+// wait for each other inside the kernel).
+static int solve_partitioned_passes(phyx_b200_ctx* const* group, int count, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats)
+{
+    auto all = [&](auto&& fn) -> int {
+        for (int k = 0; k < count; ++k)
+        {
+            PHYX_TRY(check(group[k]));
+            PHYX_TRY(fn(group[k]));
+        }
+        return PHYX_B200_OK;
+    };
+    auto sent = [&]() -> int {
+        if (count < 2) return PHYX_B200_OK;
+        for (int k = 0; k < count; ++k)
+        {
+            PHYX_TRY(check(group[k]));
+            PHYX_CUDA(cudaEventRecord(group[k]->part.evReady, group[k]->stream));
+        }
+        for (int k = 0; k < count; ++k)
+        {
+            PHYX_TRY(check(group[k]));
+            for (int j = 0; j < count; ++j)
+                if (j != k) PHYX_CUDA(cudaStreamWaitEvent(group[k]->stream, group[j]->part.evReady, 0));
+        }
+        return PHYX_B200_OK;
+    };
+    auto pass = [&](int phase, int it) -> int {
+        PHYX_TRY(all([&](phyx_b200_ctx* c) -> int { return part_launch(c, phase, it, 0); }));
+        PHYX_TRY(sent());
+        return all([&](phyx_b200_ctx* c) -> int { return part_launch(c, phase, it, 1); });
+    };
+    for (int k = 0; k < count; ++k)
+    {
+        phyx_b200_ctx* c = group[k];
+        PHYX_TRY(check(c));
+        if (stats) memset(&stats[k], 0, sizeof(stats[k]));
+        PHYX_CUDA(cudaEventRecord(c->ev[4], c->stream));
+        PHYX_TRY(schedule_build(c, nullptr, c->jointCount, PHYX_B200_SCHEDULE_COLOUR, 0));
+        PHYX_CUDA(cudaEventRecord(c->ev[5], c->stream));
+        PHYX_TRY(part_begin(c, cfg));
+        PHYX_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    }
+    PHYX_TRY(pass(-1, 0));
+    for (int it = 0; it < cfg->contactIterationsCount; ++it) PHYX_TRY(pass(0, it));
+    for (int it = 0; it < cfg->penetrationIterationsCount; ++it) PHYX_TRY(pass(1, it));
+    PHYX_TRY(all([&](phyx_b200_ctx* c) -> int {
+        PHYX_CUDA(cudaEventRecord(c->ev[1], c->stream));
+        return part_bulk_push(c);
+    }));
+    PHYX_TRY(sent());
+    PHYX_TRY(all([&](phyx_b200_ctx* c) -> int { return part_bulk_pull(c); }));
+    for (int k = 0; k < count; ++k)
+    {
+        phyx_b200_ctx* c = group[k];
+        PHYX_TRY(check(c));
+        PHYX_CUDA(cudaEventRecord(c->ev[2], c->stream));
+        PHYX_TRY(part_end(c, stats ? &stats[k] : nullptr));
+        PHYX_CUDA(cudaEventRecord(c->ev[6], c->stream));
+        PHYX_CUDA(cudaEventSynchronize(c->ev[6]));
+        if (stats)
+        {
+            stats[k].ms_schedule = elapsed_ms(c->ev[4], c->ev[5]);
+            stats[k].ms_refresh = elapsed_ms(c->ev[5], c->ev[0]);
+            stats[k].ms_iterations = elapsed_ms(c->ev[0], c->ev[1]);
+            stats[k].ms_finish = elapsed_ms(c->ev[1], c->ev[6]);   // end-of-solve exchange + FinishJoints + FinishBodies
+            stats[k].ms_total = elapsed_ms(c->ev[4], c->ev[6]);
+        }
+    }
+    return PHYX_B200_OK;
+}
+
+static int check_partitioned(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg)
+{
+    PHYX_TRY(check(c));
+    if (!cfg || cfg->schedule != PHYX_B200_SCHEDULE_COLOUR)
+    {
+        set_error("solve_partitioned: needs a config with schedule = PHYX_B200_SCHEDULE_COLOUR");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    if (c->part.ranks < 2)
+    {
+        set_error("solve_partitioned: the context is not partitioned (partition_create)");
+        return PHYX_B200_ERR_STATE;
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_solve_partitioned(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats)
+{
+    PHYX_TRY(check_partitioned(c, cfg));
+    return solve_partitioned_passes(&c, 1, cfg, stats);
+}
+
+int phyx_b200_solve_partitioned_group(phyx_b200_ctx* const* group, int count, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats)
+{
+    if (!group || count < 2 || count > kMaxRanks)
+    {
+        set_error("solve_partitioned_group: need 2..%d contexts", kMaxRanks);
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    for (int k = 0; k < count; ++k)
+    {
+        PHYX_TRY(check_partitioned(group[k], cfg));
+        if (group[k]->part.ranks != count || group[k]->part.rank != k)
+        {
+            set_error("solve_partitioned_group: context %d is rank %d of %d", k, group[k]->part.rank, group[k]->part.ranks);
+            return PHYX_B200_ERR_ARGUMENT;
+        }
+    }
+    return solve_partitioned_passes(group, count, cfg, stats);
 }
 
 // ---- resident collider stages -----------------------------------------------------------------------

@@ -24,11 +24,15 @@ __device__ __forceinline__ BarrierResult grid_barrier(unsigned long long* ring, 
         unsigned long long* word = ring + (epoch & 3u);
         if (blockIdx.x == 0) ring[(epoch + 1u) & 3u] = 0ull;
         const unsigned long long add = 1ull | (w ? (1ull << 20) : 0ull) | (pr ? (1ull << 40) : 0ull);
-        __threadfence();
+        // release: the CTA's writes (ordered before this point by the __syncthreads above) become visible before
+        // the arrival; acq_rel is enough for the fence-atomic-fence pattern and cheaper than __threadfence's MEMBAR.SC
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
         unsigned long long v = atomicAdd(word, add) + add;
+        // poll with relaxed loads and acquire once at the end: an acquire load per poll costs an L1
+        // invalidation of the whole SM (SASS CCTL.IVALL, ~75 polls per barrier in the ncu capture of r1g)
         while ((v & 0xfffffull) != gridDim.x)
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word) : "memory");
-        __threadfence();
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word) : "memory");
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
         s_value = v;
     }
     __syncthreads();

@@ -23,7 +23,6 @@ namespace phyx
 {
 
 constexpr int kBlock = 256;
-constexpr int kMaxColours = 64;
 constexpr unsigned long long kNoClaim = ~0ull;
 
 __device__ __forceinline__ unsigned mix32(unsigned x)   // murmur3 finaliser: the joint's priority
@@ -258,7 +257,8 @@ int colour_schedule_build(phyx_b200_ctx* c)
     if (!c->jointUnitsValid || c->manifoldCount == 0) return colour_joints_build(c, &changed);
     bool incremental = c->colourStateValid && c->colourStateBodies == c->bodyCount && c->manColour.ptr && c->bodyUsed.ptr;
     int st = colour_units_build(c, incremental, &changed);
-    if (st == PHYX_B200_OK && incremental && (changed || c->levelCount > c->coloursAtFullBuild + 4))
+    const int colours = c->part.ranks > 1 ? c->partColours : c->levelCount;   // partitioned layouts have one level per (class, colour)
+    if (st == PHYX_B200_OK && incremental && (changed || colours > c->coloursAtFullBuild + 4))
         st = colour_units_build(c, false, &changed);
     return st;
 }
@@ -445,17 +445,267 @@ __global__ void k_unit_levels(const int* __restrict__ counts, Level* __restrict_
 }
 
 __global__ void __launch_bounds__(kBlock) k_unit_place(int M, const uint2* __restrict__ sorted, const Level* __restrict__ levels,
-    const int* __restrict__ firstPos, const int* __restrict__ manCount, const float4* __restrict__ contactPoints, int* __restrict__ slotJoint)
+    const int* __restrict__ firstPos, const int* __restrict__ manCount, const float4* __restrict__ contactPoints, int* __restrict__ slotJoint, unsigned skipBin)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= M) return;
     const uint2 e = sorted[p];
-    if (e.x >= unsigned(kMaxColours)) return;   // manifold without contact points
+    if (e.x >= skipBin) return;   // manifold without contact points
     const int m = int(e.y);
     const int slot = levels[e.x].start + 2 * (p - firstPos[e.x]);
     // the joints of a manifold are the solverIndex of its contact points (World.cpp:100-103,140)
     slotJoint[slot] = __float_as_int(contactPoints[size_t(2 * m) * 2 + 1].w);
     slotJoint[slot + 1] = manCount[m] > 1 ? __float_as_int(contactPoints[size_t(2 * m + 1) * 2 + 1].w) : -1;
+}
+
+
+// ---- partitioned layout (one world over several devices, partition.cu) -----------------------------------
+// The solver rows are in sorted-x order, so a contiguous row range is a vertical strip of the world.  Rank q
+// owns the rows [cuts[q], cuts[q+1]); the cuts balance the number of manifolds per rank (a manifold counts
+// for its lower dynamic row).  A manifold whose dynamic bodies all belong to rank q is INTERIOR to q
+// (class q); one whose two bodies belong to different ranks is CUT (class `ranks`).  Slots are laid out
+// class-major, colour-minor: each rank's interior manifolds are one contiguous slot range holding its colour
+// levels, the cut manifolds follow with theirs.  Read as ONE sequential order this is a valid Gauss-Seidel
+// sweep (interior classes are mutually independent), which is what the oracle checks the devices against.
+
+__device__ __forceinline__ int part_rank_of(const int* __restrict__ cuts, int ranks, int row)
+{
+    int k = 0;
+    for (int q = 1; q < ranks; ++q) k += (cuts[q] <= row) ? 1 : 0;
+    return k;
+}
+
+// hist[row] = manifolds (with a colour) whose lower dynamic row it is
+__global__ void __launch_bounds__(kBlock) k_part_hist(int M, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
+    int* __restrict__ hist)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    if (work[m] >= kMaxColours) return;
+    const int2 b = jb[m];
+    int r1 = b.x < 0 ? -1 : (rowOf ? rowOf[b.x] : b.x), r2 = b.y < 0 ? -1 : (rowOf ? rowOf[b.y] : b.y);
+    int home = r1 < 0 ? r2 : (r2 < 0 ? r1 : min(r1, r2));
+    if (home >= 0) atomicAdd(&hist[home], 1);
+}
+
+// cuts[q] = first row with at least q/ranks of the manifolds before it; plan[0..ranks] = cuts
+__global__ void k_part_cuts(int nb, int ranks, const int* __restrict__ prefix, const int* __restrict__ total, int* __restrict__ cuts)
+{
+    const int q = threadIdx.x;
+    if (q > ranks) return;
+    if (q == 0) { cuts[0] = 0; return; }
+    if (q == ranks) { cuts[q] = nb; return; }
+    const long long target = (static_cast<long long>(*total) * q + ranks - 1) / ranks;
+    int lo = 0, hi = nb;   // smallest row r in [0, nb] with prefix[r] >= target (prefix[nb] := total)
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    cuts[q] = lo;
+}
+
+// persist the colours, classify, emit {class * 64 + colour, manifold} sort keys and the histogram over bins,
+// flag the rows cut manifolds touch (the boundary rows exchanged between the ranks)
+__global__ void __launch_bounds__(kBlock) k_part_keys(int M, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
+    const int* __restrict__ cuts, int ranks, int* __restrict__ manColour, uint2* __restrict__ keys, int* __restrict__ counts, int* __restrict__ rowFlag)
+{
+    __shared__ int h[(kMaxRanks + 1) * kMaxColours + 1];
+    const int bins1 = (ranks + 1) * kMaxColours + 1;
+    for (int b = threadIdx.x; b < bins1; b += blockDim.x) h[b] = 0;
+    __syncthreads();
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = m < M ? work[m] : kMaxColours;
+    if (m < M) manColour[m] = (c >= kMaxColours) ? -1 : c;
+    int bin = (ranks + 1) * kMaxColours;   // skipped
+    if (m < M && c < kMaxColours)
+    {
+        const int2 b = jb[m];
+        const int r1 = b.x < 0 ? -1 : (rowOf ? rowOf[b.x] : b.x), r2 = b.y < 0 ? -1 : (rowOf ? rowOf[b.y] : b.y);
+        int cls = 0;
+        if (r1 >= 0 && r2 >= 0)
+        {
+            const int k1 = part_rank_of(cuts, ranks, r1), k2 = part_rank_of(cuts, ranks, r2);
+            if (k1 == k2)
+                cls = k1;
+            else
+            {
+                cls = ranks;
+                rowFlag[r1] = 1;
+                rowFlag[r2] = 1;
+            }
+        }
+        else if (r1 >= 0 || r2 >= 0)
+            cls = part_rank_of(cuts, ranks, r1 >= 0 ? r1 : r2);
+        bin = cls * kMaxColours + c;
+    }
+    if (m < M)
+    {
+        keys[m] = make_uint2(unsigned(bin), unsigned(m));
+        atomicAdd(&h[bin], 1);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins1; b += blockDim.x)
+        if (h[b]) atomicAdd(&counts[b], h[b]);
+}
+
+// counts[bins] -> paired level table over ALL bins (empty bins are empty levels), firstPos, header {bins, numSlots, widest}
+__global__ void k_part_levels(int bins, const int* __restrict__ counts, Level* __restrict__ levels, int* __restrict__ firstPos, int* __restrict__ header)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int cursor = 0, run = 0, widest = 0;
+    for (int b = 0; b < bins; ++b)
+    {
+        levels[b].start = cursor;
+        levels[b].grouped_end = -1;
+        levels[b].end = cursor + 2 * counts[b];
+        firstPos[b] = run;
+        run += counts[b];
+        widest = max(widest, 2 * counts[b]);
+        if (counts[b] > 0) cursor = (levels[b].end + 63) & ~63;
+    }
+    header[0] = bins;
+    header[1] = cursor;
+    header[2] = widest;
+}
+
+__global__ void __launch_bounds__(kBlock) k_part_blist(int nb, const int* __restrict__ rowFlag, const int* __restrict__ rowPrefix, int* __restrict__ bRows)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nb) return;
+    if (rowFlag[r]) bRows[rowPrefix[r]] = r;
+}
+
+// plan words: [0..ranks] cuts, [16..16+ranks] first boundary row of each rank in bRows, [16+ranks] = total
+__global__ void k_part_bstart(int nb, int ranks, const int* __restrict__ rowPrefix, const int* __restrict__ total, int* __restrict__ plan)
+{
+    const int q = threadIdx.x;
+    if (q > ranks) return;
+    const int row = plan[q];
+    plan[16 + q] = row >= nb ? *total : rowPrefix[row];
+}
+
+// Layout of the coloured manifolds for a partitioned solve; `work` holds the colours.  Fills the context's
+// schedule (slots, level table over all bins) and the partition plan.
+static int part_layout(phyx_b200_ctx* c, const int2* jb, const int* work, int* result, bool incremental, bool* staticsChanged, int* coloursOut)
+{
+    Partition& pt = c->part;
+    const int M = c->manifoldCount, nb = c->bodyCount, R = pt.ranks;
+    const int bins = (R + 1) * kMaxColours;
+    const int grid = (M + kBlock - 1) / kBlock;
+    const int* rowOf = (c->rowOrderValid && c->rowOrderBodies == nb) ? c->rowOf.as<int>() : nullptr;
+    pt.planValid = false;
+
+    PHYX_TRY(pt.rowFlag.reserve(size_t(nb + 1) * sizeof(int)));
+    PHYX_TRY(pt.rowPrefix.reserve(size_t(nb + 1) * sizeof(int)));
+    PHYX_TRY(pt.bRows.reserve(size_t(nb + 1) * sizeof(int)));
+    PHYX_TRY(pt.planWords.reserve((64 + size_t(bins) + 1 + bins) * sizeof(int)));
+    int* plan = pt.planWords.as<int>();        // [0..15] cuts, [16..31] bStart, [32..35] header, [36] scan total, [64..] counts[bins + 1], then firstPos[bins]
+    int* header = plan + 32;
+    int* total = plan + 36;
+    int* counts = plan + 64;
+    int* firstPos = counts + bins + 1;
+    PHYX_CUDA(cudaMemsetAsync(plan, 0, (64 + size_t(bins) + 1 + bins) * sizeof(int), c->stream));
+
+    // cuts that balance the manifold count
+    PHYX_CUDA(cudaMemsetAsync(pt.rowFlag.ptr, 0, size_t(nb + 1) * sizeof(int), c->stream));
+    k_part_hist<<<grid, kBlock, 0, c->stream>>>(M, jb, work, rowOf, pt.rowFlag.as<int>());
+    PHYX_TRY(exclusive_scan_i32(c, pt.rowFlag.as<int>(), pt.rowPrefix.as<int>(), nb, total));
+    k_part_cuts<<<1, 32, 0, c->stream>>>(nb, R, pt.rowPrefix.as<int>(), total, plan);
+    c->launches += 2;
+
+    // classes, sort keys, boundary flags
+    PHYX_CUDA(cudaMemsetAsync(pt.rowFlag.ptr, 0, size_t(nb + 1) * sizeof(int), c->stream));
+    PHYX_TRY(c->colourKeys.reserve(size_t(M) * sizeof(uint2)));
+    PHYX_TRY(c->colourSorted.reserve(size_t(M) * sizeof(uint2)));
+    k_part_keys<<<grid, kBlock, 0, c->stream>>>(M, jb, work, rowOf, plan, R, c->manColour.as<int>(), c->colourKeys.as<uint2>(), counts, pt.rowFlag.as<int>());
+    c->launches++;
+    int digits = 1;
+    while (digits < bins + 1) digits <<= 1;
+    PHYX_TRY(radix_pass(c, c->colourKeys.as<uint2>(), c->colourSorted.as<uint2>(), M, 0, digits));
+    PHYX_TRY(pt.binLevels.reserve(size_t(bins) * sizeof(Level)));
+    k_part_levels<<<1, 32, 0, c->stream>>>(bins, counts, pt.binLevels.as<Level>(), firstPos, header);
+    c->launches++;
+    const size_t maxSlots = 2 * size_t(M) + 64 * size_t(bins);
+    PHYX_TRY(c->slotJoint.reserve(maxSlots * sizeof(int)));
+    PHYX_CUDA(cudaMemsetAsync(c->slotJoint.ptr, 0xff, maxSlots * sizeof(int), c->stream));
+    k_unit_place<<<grid, kBlock, 0, c->stream>>>(M, c->colourSorted.as<uint2>(), pt.binLevels.as<Level>(), firstPos, c->manCount.as<int>(),
+        c->contactPoints.as<float4>(), c->slotJoint.as<int>(), unsigned(bins));
+    c->launches++;
+
+    // boundary rows, in row order: each rank's own ones are one contiguous run
+    PHYX_TRY(exclusive_scan_i32(c, pt.rowFlag.as<int>(), pt.rowPrefix.as<int>(), nb, total));
+    k_part_blist<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, pt.rowFlag.as<int>(), pt.rowPrefix.as<int>(), pt.bRows.as<int>());
+    k_part_bstart<<<1, 32, 0, c->stream>>>(nb, R, pt.rowPrefix.as<int>(), total, plan);
+    c->launches += 2;
+    PHYX_CUDA(cudaGetLastError());
+
+    std::vector<int> host(64 + size_t(bins) + 1);
+    int res[4];
+    PHYX_CUDA(cudaMemcpyAsync(host.data(), plan, host.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaMemcpyAsync(res, result, 16, cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    if (res[1])
+    {
+        set_error("colouring needs more than %d colours", kMaxColours);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    c->colourRounds = res[0];
+    *staticsChanged = res[3] != 0;
+    c->colourStateValid = true;
+    c->colourStateBodies = nb;
+
+    // host copies: global level list (non-empty bins, in slot order), this rank's level table, slot ranges per class
+    const int* hc = host.data() + 64;
+    std::vector<Level> mine, cutLevels;
+    int cursor = 0, colours = 0;
+    pt.widestInterior = pt.widestCut = 0;
+    for (int q = 0; q <= R; ++q)
+    {
+        pt.classSlotStart[q] = cursor;
+        for (int k = 0; k < kMaxColours; ++k)
+        {
+            const int n = hc[q * kMaxColours + k];
+            if (n == 0) continue;
+            const Level L = { cursor, -1, cursor + 2 * n };
+            c->hostLevels.push_back(L);
+            if (q == pt.rank)
+            {
+                mine.push_back(L);
+                pt.widestInterior = std::max(pt.widestInterior, 2 * n);
+            }
+            if (q == R)
+            {
+                cutLevels.push_back(L);
+                pt.widestCut = std::max(pt.widestCut, 2 * n);
+            }
+            colours = std::max(colours, k + 1);
+            cursor = (cursor + 2 * n + 63) & ~63;
+        }
+    }
+    pt.classSlotStart[R + 1] = cursor;
+    c->slotCount = cursor;
+    c->levelCount = int(c->hostLevels.size());
+    if (!incremental) c->coloursAtFullBuild = colours;
+    pt.numInterior = int(mine.size());
+    pt.numCut = int(cutLevels.size());
+    mine.insert(mine.end(), cutLevels.begin(), cutLevels.end());
+    PHYX_TRY(pt.partLevels.reserve((mine.size() + 1) * sizeof(Level)));
+    if (!mine.empty()) PHYX_CUDA(cudaMemcpyAsync(pt.partLevels.ptr, mine.data(), mine.size() * sizeof(Level), cudaMemcpyHostToDevice, c->stream));
+    // the whole order as one level table: what a single device executes when it runs this schedule alone
+    PHYX_TRY(c->levels.reserve((c->hostLevels.size() + 1) * sizeof(Level)));
+    if (!c->hostLevels.empty())
+        PHYX_CUDA(cudaMemcpyAsync(c->levels.ptr, c->hostLevels.data(), c->hostLevels.size() * sizeof(Level), cudaMemcpyHostToDevice, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));   // `mine` is pageable stack memory
+    for (int q = 0; q <= R; ++q)
+    {
+        pt.cuts[q] = host[q];
+        pt.bStart[q] = host[16 + q];
+    }
+    pt.planValid = true;
+    c->hostSlotsStale = true;
+    *coloursOut = colours;
+    return PHYX_B200_OK;
 }
 
 static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsChanged)
@@ -518,6 +768,11 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
     PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_colour_rounds, dim3(cgrid), dim3(kBlock), args, 0, c->stream));
     c->launches++;
 
+    if (c->part.ranks > 1)
+    {
+        return part_layout(c, jb, work, result, incremental, staticsChanged, &c->partColours);
+    }
+
     // colour-major layout of the manifolds: stable counting sort on a 7-bit digit (bin 64 = skipped)
     PHYX_TRY(c->colourKeys.reserve(size_t(M) * sizeof(uint2)));
     PHYX_TRY(c->colourSorted.reserve(size_t(M) * sizeof(uint2)));
@@ -531,7 +786,7 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
     PHYX_TRY(c->slotJoint.reserve(maxSlots * sizeof(int)));
     PHYX_CUDA(cudaMemsetAsync(c->slotJoint.ptr, 0xff, maxSlots * sizeof(int), c->stream));
     k_unit_place<<<grid, kBlock, 0, c->stream>>>(M, c->colourSorted.as<uint2>(), c->levels.as<Level>(), firstPos, c->manCount.as<int>(),
-        c->contactPoints.as<float4>(), c->slotJoint.as<int>());
+        c->contactPoints.as<float4>(), c->slotJoint.as<int>(), unsigned(kMaxColours));
     c->launches++;
     PHYX_CUDA(cudaGetLastError());
 

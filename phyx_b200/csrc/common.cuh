@@ -57,6 +57,37 @@ struct Level
 constexpr int kStaticBit = 1 << 30;       // body reference flag in the packed joint: body is static
 constexpr int kBodyMask = kStaticBit - 1;
 
+constexpr int kMaxRanks = 8;              // devices one world can be partitioned over
+constexpr int kMaxColours = 64;           // colours per class of the schedule
+
+// Partition of one world's solve over `ranks` devices (partition.cu).  Every rank holds the whole world and runs
+// the collider stages redundantly (they are deterministic, so the replicas stay bit-identical); the solve is
+// split by solver row (sorted-x order): rank q owns the rows [cuts[q], cuts[q+1]) and the manifolds whose
+// dynamic bodies all lie in them ("interior"); manifolds whose two bodies belong to different ranks are "cut".
+struct Partition
+{
+    int rank = 0, ranks = 1;
+    // exchange buffer of this rank (one cudaMalloc, exported with CUDA IPC) and the peers' views of theirs
+    char* xbuf = nullptr;
+    size_t xbytes = 0;
+    char* peer[kMaxRanks] = {};
+    bool peerOpened[kMaxRanks] = {};   // opened with cudaIpcOpenMemHandle (else: same process, not ours to close)
+    int boundaryCapacity = 0;          // rows per sender and slot of the boundary exchange
+    size_t bulkCapacity = 0;           // bytes per sender of the end-of-solve exchange
+    unsigned long long bulkSeq = 0;
+    // plan of the current schedule (host copies; built by colour.cu with the schedule)
+    int cuts[kMaxRanks + 1] = {};      // row cuts
+    int bStart[kMaxRanks + 1] = {};    // boundary rows owned by rank q: bRows[bStart[q] .. bStart[q+1])
+    int classSlotStart[kMaxRanks + 2] = {};   // slots of class q (q = ranks: the cut class): [classSlotStart[q], classSlotStart[q+1])
+    int numInterior = 0, numCut = 0;   // levels of this rank in partLevels: interior first, then cut
+    bool planValid = false;
+    DevBuf rowFlag, rowPrefix, bRows, planWords, binLevels, partLevels, state;
+    int widestInterior = 0, widestCut = 0;   // slots of the widest level of each kind (grid sizing)
+    void* params = nullptr;            // SolveParams of the solve in flight (solve.cu)
+    cudaEvent_t evReady = nullptr;     // group driver: "this rank has sent"
+    int launchIndex = 0;
+};
+
 } // namespace phyx
 
 struct phyx_b200_ctx
@@ -114,6 +145,7 @@ struct phyx_b200_ctx
     phyx::DevBuf slotJoint;      // int: joint index of slot (or -1)
     phyx::DevBuf levels;         // Level[levelCount]
     phyx::DevBuf q0, q1, q2, q3; // float4 per slot (see solve.cu)
+    phyx::DevBuf pairQ, pairIdx; // paired levels, record form: 128-byte record + int2 index words per manifold (solve.cu)
     phyx::DevBuf accNF;          // float2 per slot
     phyx::DevBuf accD;           // float per slot
     phyx::DevBuf stamps;         // 2 x u64 per body (impulse / displacement static-body words)
@@ -143,7 +175,7 @@ struct phyx_b200_ctx
     phyx::DevBuf bodyStatic;     // u8 per body: static flag the colouring was built with
     bool colourStateValid = false;
     bool jointUnitsValid = false;   // joints are exactly the contact points of the resident manifolds (set by RefreshContactJoints)
-    int colourStateBodies = 0, coloursAtFullBuild = 0;
+    int colourStateBodies = 0, coloursAtFullBuild = 0, partColours = 0;
     std::vector<int> hostSlotPos;
     std::vector<int> hostSlots;  // last schedule (host copy, for get_schedule / KEEP_SCHEDULE)
     std::vector<phyx::Level> hostLevels;
@@ -154,6 +186,9 @@ struct phyx_b200_ctx
 
     cudaEvent_t ev[8] = {};
     int solveBlocksPerSM = 0, colourBlocksPerSM = 0, colourRounds = 0;
+
+    // ---- one world over several devices (partition.cu; SURVEY.md §8e: an island that spans devices) -----
+    phyx::Partition part;
 };
 
 namespace phyx
@@ -182,6 +217,16 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
 
 // solve.cu
 int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats);
+
+// solve.cu, partitioned solve (one world over several devices)
+int part_create(phyx_b200_ctx* c, int rank, int ranks, int boundaryCapacity, size_t bulkBytes, void* ipcHandleOut, void** localOut);
+int part_attach(phyx_b200_ctx* c, const void* ipcHandles, void* const* localPointers, const int* peerDevices);
+void part_destroy(phyx_b200_ctx* c);
+int part_begin(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg);
+int part_launch(phyx_b200_ctx* c, int phase, int it, int mode);
+int part_bulk_push(phyx_b200_ctx* c);
+int part_bulk_pull(phyx_b200_ctx* c);
+int part_end(phyx_b200_ctx* c, phyx_b200_solve_stats* stats);
 
 // collide.cu
 int collide_update_pairs(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats);

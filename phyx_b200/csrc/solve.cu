@@ -39,6 +39,7 @@ namespace phyx
 constexpr int kBlock = 256;
 constexpr float kProductiveImpulse = 1e-4f;    // Solver.cpp:8
 constexpr float kFrictionCoefficient = 0.3f;   // Solver.cpp:9
+constexpr int kPairHasB = int(0x80000000u);    // pairIdx.y: the manifold has a second joint
 
 struct SolveParams
 {
@@ -64,6 +65,11 @@ struct SolveParams
     // strict companion schedule of a replay (schedule.cu StaticRule); numStrictLevels == 0: single schedule
     const Level* strictLevels;
     int numStrictLevels;
+    // paired levels, record form (k_solve_pairs2): one 128-byte record and one index word pair per manifold
+    const float4* pairQ;
+    const int2* pairIdx;
+    int experiment;                    // developer aid (PHYX_SOLVE_EXPERIMENT, timing only, results are wrong): 1 = no joint passes the skip
+                                       // test, 2 = no row gathers either, 3 = no L2 prefetch; 1 and 2 also disable the early-out
     const int* strictMap;              // strict position -> slot (or -1)
     const unsigned char* rowsMulti;    // per body row: static body with at least two units
     int numMultiStatics;
@@ -131,14 +137,18 @@ __global__ void __launch_bounds__(kBlock) k_finish_bodies(int n, const unsigned*
 // ---- PrepareJoints copy + RefreshJoints ----------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __restrict__ slotJoint, const phyx_contact_joint* __restrict__ joints,
     const float4* __restrict__ contactPoints, const float4* __restrict__ params, const int* __restrict__ rowOf, float4* __restrict__ q0,
-    float4* __restrict__ q1, float4* __restrict__ q2, float4* __restrict__ q3, float2* __restrict__ accNF, float* __restrict__ accD)
+    float4* __restrict__ q1, float4* __restrict__ q2, float4* __restrict__ q3, float2* __restrict__ accNF, float* __restrict__ accD,
+    float4* __restrict__ pairQ, int2* __restrict__ pairIdx, int firstSlot)
 {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = firstSlot + blockIdx.x * blockDim.x + threadIdx.x;   // slots [firstSlot, numSlots)
     if (s >= numSlots) return;
     int j = slotJoint[s];
     if (j < 0)
     {
-        q3[s] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
+        if (!pairQ)
+            q3[s] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
+        else if (!(s & 1))
+            pairIdx[s >> 1] = make_int2(-1, -1);
         return;
     }
     phyx_contact_joint jt = joints[j];
@@ -170,10 +180,24 @@ __global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __r
     int b1 = (rowOf ? rowOf[jt.body1Index] : jt.body1Index) | ((p1.x == 0.0f && p1.y == 0.0f) ? kStaticBit : 0);
     int b2 = (rowOf ? rowOf[jt.body2Index] : jt.body2Index) | ((p2.x == 0.0f && p2.y == 0.0f) ? kStaticBit : 0);
 
-    q0[s] = make_float4(nx, ny, aN1, aN2);
-    q1[s] = make_float4(aF1, aF2, cinvF, dstVel);
-    q2[s] = make_float4(p1.x, p1.y, p2.x, p2.y);
-    q3[s] = make_float4(__int_as_float(b1), __int_as_float(b2), cinvN, dstDisp);
+    if (pairQ)
+    {
+        // record form (PairRecord below): {a0, a2, a3, b0, b2, b3, a1, b1}, a = slot 2p, b = slot 2p+1
+        const int h = s & 1;
+        float4* rec = pairQ + size_t(s >> 1) * 8;
+        rec[h ? 3 : 0] = make_float4(nx, ny, aN1, aN2);
+        rec[h ? 4 : 1] = make_float4(p1.x, p1.y, p2.x, p2.y);
+        rec[h ? 5 : 2] = make_float4(__int_as_float(b1), __int_as_float(b2), cinvN, dstDisp);
+        rec[h ? 7 : 6] = make_float4(aF1, aF2, cinvF, dstVel);
+        if (!h) pairIdx[s >> 1] = make_int2(b1, b2 | (slotJoint[s + 1] >= 0 ? kPairHasB : 0));   // numSlots is a multiple of 64
+    }
+    else
+    {
+        q0[s] = make_float4(nx, ny, aN1, aN2);
+        q1[s] = make_float4(aF1, aF2, cinvF, dstVel);
+        q2[s] = make_float4(p1.x, p1.y, p2.x, p2.y);
+        q3[s] = make_float4(__int_as_float(b1), __int_as_float(b2), cinvN, dstDisp);
+    }
     accNF[s] = make_float2(jt.normalLimiter_accumulatedImpulse, jt.frictionLimiter_accumulatedImpulse);
     accD[s] = 0.0f;
 }
@@ -822,6 +846,316 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve_pairs(SolveParams
 }
 
 // =====================================================================================================
+// Paired levels, record form: activity prediction instead of speculative streaming
+// =====================================================================================================
+// Measured on the 1 M-box pyramid (profiles/k_solve_r1g_metrics.json): k_solve_pairs moves 6.2 GB per
+// launch at 61 % of the measured copy bandwidth, yet only ~30 % of the joint-iterations pass the
+// lastIteration test (Solver.cpp:790-798): most of the streamed bytes belong to joints that are
+// skipped.  This form reads, for every manifold, only an 8-byte index pair {row1, row2 | hasB} and the
+// two body rows (L2) to decide; the 128-byte record (one cache line: both joints of the manifold) is
+// fetched for active manifolds only.  Activity is strongly correlated between consecutive iterations, so
+// each thread keeps one bit per manifold it owns (a manifold is visited by the same thread in every
+// iteration) and, while the grid drains into the level barrier, prefetches into L2 the records of the
+// next level's manifolds that were active last time: the DRAM latency of the records overlaps the
+// barrier instead of sitting behind the skip test.  A thread handles its manifolds of a level in
+// batches of kPairU: all index words first, then all row gathers (2 * kPairU independent L2 loads in
+// flight), then the tests and the relaxations; no two manifolds of a level share a dynamic body, so
+// gathering the rows of a whole batch up front reads nothing stale.  The arithmetic and the order of
+// relaxations are those of solve_pairs, hence the same results bit for bit.
+struct PairRecord   // layout of pairQ: 8 float4 per manifold; the displacement phase needs the first three 32-byte sectors only
+{
+    float4 a0, a2, a3, b0, b2, b3, a1, b1;
+};
+
+constexpr int kPairU = 4;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p);
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+
+__device__ __forceinline__ void prestep_pair2(const SolveParams& P, int p)
+{
+    const int2 idx = __ldcs(&P.pairIdx[p]);
+    if (idx.x < 0) return;
+    const int b1 = idx.x & kBodyMask, b2 = idx.y & kBodyMask;
+    const bool haveB = idx.y < 0;
+    float4 v1 = __ldcg(&P.vel[b1]), v2 = __ldcg(&P.vel[b2]);
+    const float4 accs = __ldcs(reinterpret_cast<const float4*>(&P.accNF[2 * p]));
+    const float4* rec = P.pairQ + size_t(p) * 8;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+    {
+        if (h == 1 && !haveB) break;
+        const float4 c0 = __ldcs(rec + (h ? 3 : 0)), c2 = __ldcs(rec + (h ? 4 : 1)), c1 = __ldcs(rec + (h ? 7 : 6));
+        const float nx = c0.x, ny = c0.y;
+        const float accN = h ? accs.z : accs.x, accF = h ? accs.w : accs.y;
+        v1.x += (nx * c2.x) * accN;
+        v1.y += (ny * c2.x) * accN;
+        v1.z += (c0.z * c2.y) * accN;
+        v2.x += ((-nx) * c2.z) * accN;
+        v2.y += ((-ny) * c2.z) * accN;
+        v2.z += (c0.w * c2.w) * accN;
+        const float tx = -ny, ty = nx;
+        v1.x += (tx * c2.x) * accF;
+        v1.y += (ty * c2.x) * accF;
+        v1.z += (c1.x * c2.y) * accF;
+        v2.x += ((-tx) * c2.z) * accF;
+        v2.y += ((-ty) * c2.z) * accF;
+        v2.z += (c1.y * c2.w) * accF;
+    }
+    if (!(idx.x & kStaticBit)) __stcg(&P.vel[b1], v1);
+    if (!(idx.y & kStaticBit)) __stcg(&P.vel[b2], v2);
+}
+
+// One pass over one paired level.  `pre` holds the index words of this thread's first batch when havePre
+// is set.  First passes record which manifolds were active in `activity` (bit = bitCursor + position in
+// the thread's visiting order, first 64 only) and advance bitCursor; wake passes leave both alone.
+template <int PHASE>
+__device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L, int it, int tick, bool firstPass, int tid, int nthreads, bool& wake,
+    unsigned& activeCount, const int2 (&pre)[kPairU], bool havePre, unsigned& bitCursor, unsigned long long& activity, unsigned scratch)
+{
+    float4* rows = PHASE == 0 ? P.vel : P.disp;
+    unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
+    const int pairBase = L.start >> 1, numPairs = (L.end - L.start) >> 1;
+    bool anyProductive = false;
+    for (long long first = tid; first < numPairs; first += static_cast<long long>(kPairU) * nthreads)
+    {
+        int2 idx[kPairU];
+        float4 v1[kPairU], v2[kPairU];
+#pragma unroll
+        for (int u = 0; u < kPairU; ++u)
+        {
+            const long long p = first + static_cast<long long>(u) * nthreads;
+            if (havePre)
+                idx[u] = pre[u];
+            else
+                idx[u] = p < numPairs ? __ldcs(&P.pairIdx[pairBase + int(p)]) : make_int2(-1, -1);
+        }
+        havePre = false;
+#pragma unroll
+        for (int u = 0; u < kPairU; ++u)
+        {
+            bool valid = idx[u].x >= 0;
+            if (!firstPass && valid)   // wake pass: only manifolds a static body can wake, and only those that have not run yet
+            {
+                const int s = 2 * (pairBase + int(first) + u * nthreads);
+                valid = ((idx[u].x | idx[u].y) & kStaticBit) && __ldcg(&P.processed[s]) != tick;
+            }
+            if (!valid) idx[u].x = -1;
+            v1[u] = v2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && P.experiment != 2)
+            {
+                v1[u] = __ldcg(&rows[idx[u].x & kBodyMask]);
+                v2[u] = __ldcg(&rows[idx[u].y & kBodyMask]);
+            }
+        }
+        // skip test (Solver.cpp:790-792) for the whole batch, for both joints of a manifold at once (see
+        // solve_pairs).  Testing every manifold of the batch before relaxing any is exact: a manifold that
+        // an earlier one of this batch wakes up through a static body is caught by the wake pass, like one
+        // woken by another thread.  (Pulling the records of the active ones into L1 at this point with
+        // LDGSTS.ca was measured: 11.3 instead of 10.4 us per level pass, the L1 does not survive.)
+        int last1v[kPairU], last2v[kPairU];
+#pragma unroll
+        for (int u = 0; u < kPairU; ++u)
+        {
+            const int r1 = idx[u].x, r2 = idx[u].y;
+            if (r1 < 0) continue;
+            const int p = pairBase + int(first) + u * nthreads;
+            const unsigned pos = unsigned(2 * p);
+            last1v[u] = (r1 & kStaticBit) ? static_visible_last(&statics[r1 & kBodyMask], it, pos) : __float_as_int(v1[u].w);
+            last2v[u] = (r2 & kStaticBit) ? static_visible_last(&statics[r2 & kBodyMask], it, pos) : __float_as_int(v2[u].w);
+            const bool active = ((last1v[u] > it - 2) || (last2v[u] > it - 2)) && P.experiment != 1 && P.experiment != 2;
+            if (!active)
+            {
+                idx[u].x = -1;
+                continue;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kPairU; ++u)
+        {
+            const int r1 = idx[u].x, r2 = idx[u].y;
+            if (r1 < 0) continue;
+            const int p = pairBase + int(first) + u * nthreads, s = 2 * p;
+            const int b1 = r1 & kBodyMask, b2 = r2 & kBodyMask;
+            const bool st1 = r1 & kStaticBit, st2 = r2 & kStaticBit, haveB = r2 < 0;
+            const unsigned pos = unsigned(s);
+            const int last1 = last1v[u], last2 = last2v[u];
+
+            if (firstPass && bitCursor + u < 64u) activity |= 1ull << (bitCursor + u);
+            const float4* rec = P.pairQ + size_t(p) * 8;
+            const float4 a0 = __ldg(rec + 0), a2 = __ldg(rec + 1), a3 = __ldg(rec + 2);
+            const float4 b0 = __ldg(rec + 3), b2r = __ldg(rec + 4), b3 = __ldg(rec + 5);
+            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1r = a1;
+            float2 accA, accB;
+            if (PHASE == 0)
+            {
+                a1 = __ldg(rec + 6);
+                b1r = __ldg(rec + 7);
+                const float4 acc = __ldcs(reinterpret_cast<const float4*>(&P.accNF[s]));
+                accA = make_float2(acc.x, acc.y);
+                accB = make_float2(acc.z, acc.w);
+            }
+            else
+            {
+                const float2 acc = __ldcs(reinterpret_cast<const float2*>(&P.accD[s]));
+                accA = make_float2(acc.x, 0.f);
+                accB = make_float2(acc.y, 0.f);
+            }
+            activeCount += haveB ? 2u : 1u;
+            float4 w1 = v1[u], w2 = v2[u];
+            const bool productiveA = relax<PHASE>(a0, a1, a2, a3, accA, w1, w2, false);
+            bool productiveB = false;
+            if (haveB) productiveB = relax<PHASE>(b0, b1r, b2r, b3, accB, w1, w2, false);
+            if (PHASE == 0)
+                __stcs(reinterpret_cast<float4*>(&P.accNF[s]), make_float4(accA.x, accA.y, accB.x, accB.y));
+            else
+                __stcs(reinterpret_cast<float2*>(&P.accD[s]), make_float2(accA.x, accB.x));
+
+            // lastIteration = it where productive (Solver.cpp:903-910); a static body is marked at the position
+            // of the first productive joint
+            const bool productive = productiveA || productiveB;
+            const unsigned markPos = productiveA ? pos : pos + 1;
+            if (!st1)
+            {
+                w1.w = __int_as_float(productive ? it : last1);
+                __stcg(&rows[b1], w1);
+            }
+            else if (productive)
+                wake |= static_mark(&statics[b1], it, markPos, nullptr);
+            if (!st2)
+            {
+                w2.w = __int_as_float(productive ? it : last2);
+                __stcg(&rows[b2], w2);
+            }
+            else if (productive)
+                wake |= static_mark(&statics[b2], it, markPos, nullptr);
+            if (st1 || st2) __stcg(&P.processed[s], tick);
+            anyProductive |= productive;
+        }
+        if (firstPass) bitCursor += kPairU;
+    }
+    return anyProductive;
+}
+
+template <int PHASE>
+__device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Level* levels, unsigned scratch, int iters, int tid, int nthreads, unsigned& epoch,
+    int& tick, int& wakePasses, unsigned& activeCount)
+{
+    int2 pre[kPairU];
+    bool havePre = false;
+    int ran = 0;
+    unsigned long long predicted = ~0ull;   // iteration 0 relaxes every joint (lastIteration = -1 > -2)
+    for (int it = 0; it < iters; ++it)
+    {
+        bool any = false, productiveAnywhere = false;
+        unsigned long long activity = 0ull;
+        unsigned bitCursor = 0u;
+        for (int l = 0; l < P.numLevels; ++l)
+        {
+            const Level L = levels[l];
+            ++tick;
+            bool wake = false;
+            any |= solve_pairs2<PHASE>(P, L, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre, bitCursor, activity, scratch);
+            // While the grid drains into the barrier: index words of this thread's first batch of the level that
+            // follows, and an L2 prefetch of the records it is expected to need (this iteration's own activity
+            // bits when the next level is level 0 of the next iteration, else last iteration's).
+            {
+                const bool wrap = l + 1 == P.numLevels;
+                const Level N = levels[wrap ? 0 : l + 1];
+                const int pairBaseN = N.start >> 1, numPairsN = (N.end - N.start) >> 1;
+                const unsigned cursorN = wrap ? 0u : bitCursor;
+                const unsigned long long hint = wrap ? activity : predicted;
+#pragma unroll
+                for (int u = 0; u < kPairU; ++u)
+                {
+                    const long long pN = tid + static_cast<long long>(u) * nthreads;
+                    pre[u] = make_int2(-1, -1);
+                    if (pN < numPairsN)
+                    {
+                        const int p = pairBaseN + int(pN);
+                        pre[u] = __ldcs(&P.pairIdx[p]);
+                        const unsigned bit = cursorN + u;
+                        if ((bit >= 64u || ((hint >> bit) & 1ull)) && P.experiment != 3)
+                        {
+                            prefetch_l2(P.pairQ + size_t(p) * 8);
+                            if (PHASE == 0)
+                                prefetch_l2(&P.accNF[2 * p]);
+                            else
+                                prefetch_l2(&P.accD[2 * p]);
+                        }
+                    }
+                }
+                havePre = true;
+            }
+            BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
+            timeline_mark(P, tick);
+            while (r.wake)
+            {
+                int2 none[kPairU];
+                unsigned dummyCursor = 0u;
+                unsigned long long dummyActivity = 0ull;
+                wake = false;
+                any |= solve_pairs2<PHASE>(P, L, it, tick, false, tid, nthreads, wake, activeCount, none, false, dummyCursor, dummyActivity, scratch);
+                ++wakePasses;
+                r = grid_barrier(P.barrier, epoch, wake, any);
+            }
+            productiveAnywhere = r.productive;
+        }
+        ++ran;
+        predicted = activity;
+        if (P.experiment == 1 || P.experiment == 2) productiveAnywhere = true;
+        if (!productiveAnywhere) break;   // Solver.cpp:189 / :210
+    }
+    return ran;
+}
+
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve_pairs2(SolveParams P)
+{
+    // the level table is read once per level pass, right behind the grid barrier: keep it in shared memory
+    constexpr int kSmemLevels = 128;
+    __shared__ Level s_levels[kSmemLevels];
+    const bool tableFits = P.numLevels <= kSmemLevels;
+    if (tableFits)
+        for (int l = threadIdx.x; l < P.numLevels; l += THREADS) s_levels[l] = P.levels[l];
+    __syncthreads();
+    const Level* levels = tableFits ? s_levels : P.levels;
+    const unsigned scratch = 0u;
+
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    unsigned epoch = 0;
+    int wakePasses = 0, tick = 0;
+    unsigned active[2] = { 0u, 0u };
+
+    for (int l = 0; l < P.numLevels; ++l)
+    {
+        const Level L = levels[l];
+        const int pairBase = L.start >> 1, numPairs = (L.end - L.start) >> 1;
+        for (long long p = tid; p < numPairs; p += nthreads) prestep_pair2(P, pairBase + int(p));
+        grid_barrier(P.barrier, epoch, false, false);
+    }
+
+    const int ranImpulse = run_phase_pairs2<0>(P, levels, scratch, P.contactIters, tid, nthreads, epoch, tick, wakePasses, active[0]);
+    const int ranDisplacement = run_phase_pairs2<1>(P, levels, scratch, P.penetrationIters, tid, nthreads, epoch, tick, wakePasses, active[1]);
+
+    for (int phase = 0; phase < 2; ++phase)
+    {
+        unsigned v = active[phase];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.activeTotal[phase], static_cast<unsigned long long>(v));
+    }
+    if (tid == 0)
+    {
+        P.result[0] = ranImpulse;
+        P.result[1] = ranDisplacement;
+        P.result[2] = wakePasses;
+    }
+}
+
+// =====================================================================================================
 // TMA-staged variant of the solve kernel
 // =====================================================================================================
 // Same algorithm, different data movement.  Each CTA owns every gridDim.x-th chunk of kU*256 slots of
@@ -1193,9 +1527,19 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
             dual ? c->staticMulti.as<unsigned char>() : nullptr, dual ? c->rowsMulti.as<unsigned char>() : nullptr);
         c->launches++;
         int grid = (ns + kBlock - 1) / kBlock;
+        // manifold units (colour.cu): all levels are paired.  Default kernel for them: the record form with
+        // activity prediction (k_solve_pairs2); PHYX_SOLVE_PAIRS=1 selects the speculative streaming form.
+        const bool paired = !c->hostLevels.empty() && c->hostLevels[0].grouped_end < 0;
+        static const char* pairsEnv = getenv("PHYX_SOLVE_PAIRS");
+        const bool records = paired && !(pairsEnv && !strcmp(pairsEnv, "1"));
+        if (records)
+        {
+            PHYX_TRY(c->pairQ.reserve(ns1 / 2 * 128 + 128));
+            PHYX_TRY(c->pairIdx.reserve(ns1 / 2 * sizeof(int2) + 64));
+        }
         k_refresh<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
             c->params.as<float4>(), rowOf, c->q0.as<float4>(), c->q1.as<float4>(), c->q2.as<float4>(), c->q3.as<float4>(), c->accNF.as<float2>(),
-            c->accD.as<float>());
+            c->accD.as<float>(), records ? c->pairQ.as<float4>() : nullptr, records ? c->pairIdx.as<int2>() : nullptr, 0);
         c->launches++;
         PHYX_CUDA(cudaEventRecord(e1, c->stream));
 
@@ -1219,6 +1563,10 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         P.barrier = c->solveFlags.as<unsigned long long>();          // 4 words
         P.result = reinterpret_cast<int*>(c->solveFlags.as<char>() + 32);
         P.activeTotal = reinterpret_cast<unsigned long long*>(c->solveFlags.as<char>() + 48);
+        const char* experimentEnv = getenv("PHYX_SOLVE_EXPERIMENT");   // read per call: tools/solve_experiments.py switches it between solves
+        P.experiment = experimentEnv ? atoi(experimentEnv) : 0;
+        P.pairQ = records ? c->pairQ.as<float4>() : nullptr;
+        P.pairIdx = records ? c->pairIdx.as<int2>() : nullptr;
         P.strictLevels = dual ? c->strictLevels.as<Level>() : nullptr;
         P.numStrictLevels = dual ? c->strictLevelCount : 0;
         P.strictMap = dual ? c->strictMap.as<int>() : nullptr;
@@ -1237,8 +1585,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         static const int shapeEnv = getenv("PHYX_SOLVE_SHAPE") ? atoi(getenv("PHYX_SOLVE_SHAPE")) : 5122;
         int sblock = 512;
         void* solveKernel = nullptr;
-        const bool paired = !c->hostLevels.empty() && c->hostLevels[0].grouped_end < 0;   // manifold units: all levels are paired
-#define PHYX_PICK(T, B) (paired ? (void*)k_solve_pairs<T, B> : dual ? (void*)k_solve<T, B, true> : (void*)k_solve<T, B, false>)
+#define PHYX_PICK(T, B) (records ? (void*)k_solve_pairs2<T, B> : paired ? (void*)k_solve_pairs<T, B> : dual ? (void*)k_solve<T, B, true> : (void*)k_solve<T, B, false>)
         switch (paired && !getenv("PHYX_SOLVE_SHAPE") ? 2562 : shapeEnv)
         {
         case 2562: sblock = 256; solveKernel = PHYX_PICK(256, 2); break;
@@ -1334,6 +1681,585 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         stats->penetrationIterationsRun = ranD;
         stats->wakePasses = wakePasses;
         stats->colourRounds = c->colourRounds;
+    }
+    return PHYX_B200_OK;
+}
+
+
+// =====================================================================================================
+// One world over several devices: the partitioned solve (an island that spans devices)
+// =====================================================================================================
+// colour.cu (part_layout) lays the coloured manifolds out class-major: rank q's INTERIOR manifolds (all
+// dynamic bodies in q's row range), then the CUT manifolds (bodies of two ranks).  Every pass of the solve
+// (warm start, each impulse iteration, each displacement iteration) then runs as
+//     interior levels, every rank its own, in parallel              (kernel, mode 0)
+//     exchange of the boundary rows (rows that cut manifolds touch)  (fused into the two kernels, see below)
+//     cut levels, every rank all of them, redundantly                (kernel, mode 1)
+// which equals ONE sequential sweep over the slot order [rank 0 levels .. rank R-1 levels, cut levels]: the
+// interior classes touch disjoint dynamic rows, and when the cut levels start every rank holds the same
+// fresh boundary rows, so all ranks compute identical cut results and no second exchange is needed.  This is
+// the ghost-body exchange at iteration boundaries that BASELINE.json's north_star describes, done without a
+// collective call: the tail of the interior kernel STORES the rank's own boundary rows straight into every
+// peer's receive buffer over NVLink (peer pointers from CUDA IPC), fences, and releases a per-sender
+// sequence flag in the peer's memory; the head of the cut kernel acquires the flags of all peers and copies
+// the received rows into its row array.  Two receive slots alternate, which is enough because a rank can
+// be at most one exchange ahead of a peer that has not consumed the previous one.
+// The productive early-out (Solver.cpp:189,210) needs an OR over all ranks: the interior flag travels with
+// the boundary rows, the cut flag is computed identically everywhere, and the decision is left in device
+// memory (stop[phase]) where the kernels of the remaining iterations see it and return at once, so the
+// host never waits for it.  Static bodies (never written) keep their lastIteration words per rank: a rank
+// sees the productive ground contacts of its own manifolds only (documented deviation from the one-device
+// order; the oracle reproduces it by giving every rank its own copy of each static body).
+
+struct PartDevState
+{
+    unsigned long long xseq;       // boundary exchanges completed (persists across solves; identical on all ranks)
+    int stop[2];                   // phase ended early: no productive joint anywhere
+    int ran[2];                    // iterations run per phase
+    int interiorProductive;        // this rank's last interior launch saw a productive joint
+    int error;                     // 1: gave up waiting for a peer
+    unsigned long long active[2];  // joint-iterations relaxed by this rank (interior and cut)
+    int wakePasses, pad_;
+};
+
+constexpr size_t kPartFlagBytes = 1024;      // exchange buffer: [0,64) boundary flags, [64,128) bulk flags, then the areas
+constexpr unsigned long long kPartTimeoutNs = 4000000000ull;
+
+struct PartArgs
+{
+    int phase, it, levelBegin, levelEnd, tickBase, mode, ring, rank, ranks, bCap;
+    int bStart[kMaxRanks + 1];
+    const int* bRows;
+    PartDevState* st;
+    char* self;
+    char* peer[kMaxRanks];
+};
+
+__host__ __device__ __forceinline__ size_t part_boundary_bytes(int ranks, int bCap) { return size_t(2) * ranks * (size_t(bCap) + 1) * sizeof(float4); }
+
+__device__ __forceinline__ float4* part_recv(char* xbuf, int ranks, int bCap, int slot, int sender)
+{
+    return reinterpret_cast<float4*>(xbuf + kPartFlagBytes) + (size_t(slot) * ranks + sender) * (size_t(bCap) + 1);
+}
+
+__device__ __forceinline__ unsigned long long global_timer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// spin until *flag >= want (written by a peer device with st.release.sys); false after kPartTimeoutNs
+__device__ __forceinline__ bool part_wait(const unsigned long long* flag, unsigned long long want)
+{
+    const unsigned long long t0 = global_timer();
+    bool ok = true;
+    for (;;)
+    {
+        unsigned long long v;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= want) break;
+        if (global_timer() - t0 > kPartTimeoutNs)
+        {
+            ok = false;
+            break;
+        }
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    return ok;
+}
+
+__device__ __forceinline__ void part_signal(unsigned long long* flag, unsigned long long value)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+}
+
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_part_solve(SolveParams P, PartArgs A)
+{
+    PartDevState* st = A.st;
+    // stop[] is only written by the last thread standing of an earlier cut launch: the same answer for every thread
+    if (A.phase >= 0 && __ldcg(&st->stop[A.phase])) return;
+
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    unsigned long long* ring = P.barrier + 4 * A.ring;
+    if (tid == 0)   // the next launch uses the other ring
+    {
+        unsigned long long* other = P.barrier + 4 * (A.ring ^ 1);
+        other[0] = other[1] = other[2] = other[3] = 0ull;
+    }
+    unsigned epoch = 0;
+    const unsigned long long xseq = __ldcg(&st->xseq);
+    const int slot = int(xseq & 1ull);
+    float4* rows = A.phase == 1 ? P.disp : P.vel;
+    unsigned long long* selfFlags = reinterpret_cast<unsigned long long*>(A.self);
+    bool gathered = false;
+
+    if (A.mode == 1)
+    {
+        // head of the cut launch: take over the peers' boundary rows of exchange `xseq`
+        if (threadIdx.x == 0)
+        {
+            bool ok = true;
+            for (int q = 0; q < A.ranks; ++q)
+                if (q != A.rank) ok = part_wait(selfFlags + q, xseq + 1ull) && ok;
+            if (!ok) atomicExch(&st->error, 1);
+        }
+        __syncthreads();
+        for (int q = 0; q < A.ranks; ++q)
+        {
+            if (q == A.rank) continue;
+            const float4* src = part_recv(A.self, A.ranks, A.bCap, slot, q);
+            const int first = A.bStart[q], n = A.bStart[q + 1] - first;
+            for (int i = tid; i < n; i += nthreads) __stcg(&rows[A.bRows[first + i]], __ldcg(src + i));
+            gathered |= __ldcg(src + A.bCap).x != 0.0f;
+        }
+        gathered |= __ldcg(&st->interiorProductive) != 0;
+        grid_barrier(ring, epoch, false, false);
+    }
+
+    bool any = false, productive = false;
+    int wakePasses = 0;
+    unsigned active = 0u;
+    for (int l = A.levelBegin; l < A.levelEnd; ++l)
+    {
+        const Level L = P.levels[l];
+        const int tick = A.tickBase + (l - A.levelBegin) + 1;
+        if (A.phase < 0)
+        {
+            const int pairBase = L.start >> 1, numPairs = (L.end - L.start) >> 1;
+            for (long long p = tid; p < numPairs; p += nthreads) prestep_pair2(P, pairBase + int(p));
+            grid_barrier(ring, epoch, false, false);
+            continue;
+        }
+        int2 none[kPairU];
+        unsigned cursor = 0u;
+        unsigned long long activity = 0ull;
+        bool wake = false;
+        if (A.phase == 0)
+            any |= solve_pairs2<0>(P, L, A.it, tick, true, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+        else
+            any |= solve_pairs2<1>(P, L, A.it, tick, true, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+        BarrierResult r = grid_barrier(ring, epoch, wake, any);
+        while (r.wake)
+        {
+            wake = false;
+            if (A.phase == 0)
+                any |= solve_pairs2<0>(P, L, A.it, tick, false, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+            else
+                any |= solve_pairs2<1>(P, L, A.it, tick, false, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+            ++wakePasses;
+            r = grid_barrier(ring, epoch, wake, any);
+        }
+        productive = r.productive;
+    }
+
+    if (A.mode == 0)
+    {
+        // tail of the interior launch: this rank's own boundary rows (final: the last level barrier is behind
+        // us) go straight into every peer's receive slot, then the flag
+        const int first = A.bStart[A.rank], n = A.bStart[A.rank + 1] - first;
+        for (int q = 0; q < A.ranks; ++q)
+        {
+            if (q == A.rank) continue;
+            float4* dst = part_recv(A.peer[q], A.ranks, A.bCap, slot, A.rank);
+            for (int i = tid; i < n; i += nthreads) dst[i] = __ldcg(&rows[A.bRows[first + i]]);
+            if (tid == 0) dst[A.bCap] = make_float4(productive ? 1.0f : 0.0f, 0.f, 0.f, 0.f);
+        }
+        __threadfence_system();
+        grid_barrier(ring, epoch, false, false);
+        if (tid == 0)
+        {
+            st->interiorProductive = productive ? 1 : 0;
+            for (int q = 0; q < A.ranks; ++q)
+                if (q != A.rank) part_signal(reinterpret_cast<unsigned long long*>(A.peer[q]) + A.rank, xseq + 1ull);
+        }
+    }
+    else if (tid == 0)
+    {
+        if (A.phase >= 0)
+        {
+            st->ran[A.phase] = A.it + 1;
+            if (!(gathered || productive)) st->stop[A.phase] = 1;
+        }
+        st->xseq = xseq + 1ull;
+    }
+
+    if (A.phase >= 0)
+    {
+        unsigned v = active;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&st->active[A.phase], static_cast<unsigned long long>(v));
+        if (tid == 0 && wakePasses) atomicAdd(&st->wakePasses, wakePasses);
+    }
+}
+
+// end-of-solve exchange: flags around plain peer copies
+__global__ void k_part_bulk_signal(PartArgs A, unsigned long long seq)
+{
+    __threadfence_system();
+    for (int q = 0; q < A.ranks; ++q)
+        if (q != A.rank) part_signal(reinterpret_cast<unsigned long long*>(A.peer[q]) + 8 + A.rank, seq);
+}
+
+__global__ void k_part_bulk_wait(PartArgs A, unsigned long long seq)
+{
+    unsigned long long* flags = reinterpret_cast<unsigned long long*>(A.self) + 8;
+    bool ok = true;
+    for (int q = 0; q < A.ranks; ++q)
+        if (q != A.rank) ok = part_wait(flags + q, seq) && ok;
+    if (!ok) atomicExch(&A.st->error, 1);
+}
+
+static PartArgs part_args(phyx_b200_ctx* c)
+{
+    Partition& pt = c->part;
+    PartArgs A;
+    memset(&A, 0, sizeof(A));
+    A.rank = pt.rank;
+    A.ranks = pt.ranks;
+    A.bCap = pt.boundaryCapacity;
+    for (int q = 0; q <= pt.ranks; ++q) A.bStart[q] = pt.bStart[q];
+    A.bRows = pt.bRows.as<int>();
+    A.st = pt.state.as<PartDevState>();
+    A.self = pt.xbuf;
+    for (int q = 0; q < pt.ranks; ++q) A.peer[q] = pt.peer[q];
+    return A;
+}
+
+static size_t part_bulk_offset(const Partition& pt) { return (kPartFlagBytes + part_boundary_bytes(pt.ranks, pt.boundaryCapacity) + 255) & ~size_t(255); }
+
+int part_create(phyx_b200_ctx* c, int rank, int ranks, int boundaryCapacity, size_t bulkBytes, void* ipcHandleOut, void** localOut)
+{
+    Partition& pt = c->part;
+    if (ranks < 2 || ranks > kMaxRanks || rank < 0 || rank >= ranks || boundaryCapacity < 1)
+    {
+        set_error("partition_create: need 2 <= ranks <= %d, 0 <= rank < ranks, boundaryCapacity >= 1", kMaxRanks);
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    if (pt.xbuf)
+    {
+        set_error("partition_create: context is already partitioned");
+        return PHYX_B200_ERR_STATE;
+    }
+    pt.rank = rank;
+    pt.ranks = ranks;
+    pt.boundaryCapacity = boundaryCapacity;
+    pt.bulkCapacity = (bulkBytes + 255) & ~size_t(255);
+    pt.xbytes = part_bulk_offset(pt) + size_t(ranks) * pt.bulkCapacity;
+    PHYX_CUDA(cudaMalloc(reinterpret_cast<void**>(&pt.xbuf), pt.xbytes));
+    PHYX_CUDA(cudaMemset(pt.xbuf, 0, kPartFlagBytes));
+    PHYX_TRY(pt.state.reserve(sizeof(PartDevState)));
+    PHYX_CUDA(cudaMemset(pt.state.ptr, 0, sizeof(PartDevState)));
+    if (!pt.evReady) PHYX_CUDA(cudaEventCreateWithFlags(&pt.evReady, cudaEventDisableTiming));
+    pt.bulkSeq = 0;
+    pt.planValid = false;
+    for (int q = 0; q < kMaxRanks; ++q)
+    {
+        pt.peer[q] = nullptr;
+        pt.peerOpened[q] = false;
+    }
+    pt.peer[rank] = pt.xbuf;
+    if (ipcHandleOut)
+    {
+        cudaIpcMemHandle_t h;
+        PHYX_CUDA(cudaIpcGetMemHandle(&h, pt.xbuf));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(ipcHandleOut, &h, sizeof(h));
+    }
+    if (localOut) *localOut = pt.xbuf;
+    // a schedule built before this call has the one-device layout
+    c->scheduleMode = -1;
+    c->colourStateValid = false;
+    return PHYX_B200_OK;
+}
+
+int part_attach(phyx_b200_ctx* c, const void* ipcHandles, void* const* localPointers, const int* peerDevices)
+{
+    Partition& pt = c->part;
+    if (!pt.xbuf || (!ipcHandles && !localPointers))
+    {
+        set_error("partition_attach: call partition_create first and pass the peers' IPC handles or pointers");
+        return PHYX_B200_ERR_STATE;
+    }
+    for (int q = 0; q < pt.ranks; ++q)
+    {
+        if (q == pt.rank) continue;
+        if (localPointers)
+        {
+            pt.peer[q] = static_cast<char*>(localPointers[q]);
+            if (peerDevices && peerDevices[q] != c->device)
+            {
+                cudaError_t e = cudaDeviceEnablePeerAccess(peerDevices[q], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled)
+                    cudaGetLastError();
+                else if (e != cudaSuccess)
+                {
+                    set_error("cudaDeviceEnablePeerAccess(%d) from device %d failed: %s", peerDevices[q], c->device, cudaGetErrorString(e));
+                    return PHYX_B200_ERR_CUDA;
+                }
+            }
+        }
+        else
+        {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, static_cast<const char*>(ipcHandles) + size_t(q) * sizeof(h), sizeof(h));
+            void* p = nullptr;
+            PHYX_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            pt.peer[q] = static_cast<char*>(p);
+            pt.peerOpened[q] = true;
+        }
+        if (!pt.peer[q])
+        {
+            set_error("partition_attach: no buffer for rank %d", q);
+            return PHYX_B200_ERR_ARGUMENT;
+        }
+    }
+    return PHYX_B200_OK;
+}
+
+void part_destroy(phyx_b200_ctx* c)
+{
+    Partition& pt = c->part;
+    for (int q = 0; q < kMaxRanks; ++q)
+    {
+        if (pt.peerOpened[q] && pt.peer[q]) cudaIpcCloseMemHandle(pt.peer[q]);
+        pt.peer[q] = nullptr;
+        pt.peerOpened[q] = false;
+    }
+    if (pt.xbuf) cudaFree(pt.xbuf);
+    pt.xbuf = nullptr;
+    if (pt.evReady) cudaEventDestroy(pt.evReady);
+    pt.evReady = nullptr;
+    delete static_cast<SolveParams*>(pt.params);
+    pt.params = nullptr;
+    DevBuf* bufs[] = { &pt.rowFlag, &pt.rowPrefix, &pt.bRows, &pt.planWords, &pt.binLevels, &pt.partLevels, &pt.state };
+    for (DevBuf* b : bufs) b->release();
+    pt.ranks = 1;
+    pt.rank = 0;
+    pt.planValid = false;
+    c->scheduleMode = -1;
+    c->colourStateValid = false;
+}
+
+constexpr int kPartThreads = 256;
+
+// schedule is built (part_layout): pack the rows, refresh this rank's joints, reset the per-solve state
+int part_begin(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg)
+{
+    Partition& pt = c->part;
+    const int ns = c->slotCount, nb = c->bodyCount, R = pt.ranks;
+    if (!pt.xbuf)
+    {
+        set_error("solve_partitioned: partition_create / partition_attach first");
+        return PHYX_B200_ERR_STATE;
+    }
+    for (int q = 0; q < R; ++q)
+        if (!pt.peer[q])
+        {
+            set_error("solve_partitioned: rank %d is not attached", q);
+            return PHYX_B200_ERR_STATE;
+        }
+    if (cfg->contactIterationsCount < 0 || cfg->penetrationIterationsCount < 0 || cfg->contactIterationsCount > 60000 || cfg->penetrationIterationsCount > 60000)
+    {
+        set_error("solve: iteration counts must be in [0, 60000]");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    pt.launchIndex = 0;
+    if (c->jointCount == 0) return PHYX_B200_OK;
+    if (!pt.planValid)
+    {
+        set_error("solve_partitioned: needs the manifold-unit schedule of the resident pipeline (RefreshContactJoints before SolveJoints)");
+        return PHYX_B200_ERR_STATE;
+    }
+    for (int q = 0; q < R; ++q)
+    {
+        const size_t need = size_t(pt.cuts[q + 1] - pt.cuts[q]) * 2 * sizeof(float4) + size_t(pt.classSlotStart[q + 1] - pt.classSlotStart[q]) * sizeof(float2);
+        if (pt.bStart[q + 1] - pt.bStart[q] > pt.boundaryCapacity || need > pt.bulkCapacity)
+        {
+            set_error("solve_partitioned: rank %d has %d boundary rows / %zu bulk bytes, capacity is %d / %zu", q, pt.bStart[q + 1] - pt.bStart[q], need,
+                pt.boundaryCapacity, pt.bulkCapacity);
+            return PHYX_B200_ERR_CAPACITY;
+        }
+    }
+    const size_t ns1 = size_t(ns > 0 ? ns : 1);
+    PHYX_TRY(c->pairQ.reserve(ns1 / 2 * 128 + 128));
+    PHYX_TRY(c->pairIdx.reserve(ns1 / 2 * sizeof(int2) + 64));
+    PHYX_TRY(c->accNF.reserve(ns1 * sizeof(float2)));
+    PHYX_TRY(c->accD.reserve(ns1 * sizeof(float)));
+    PHYX_TRY(c->stamps.reserve(size_t(nb > 0 ? nb : 1) * 2 * sizeof(unsigned long long)));
+    PHYX_TRY(c->processed.reserve(ns1 * sizeof(int)));
+    PHYX_TRY(c->solveFlags.reserve(128));
+    PHYX_TRY(c->solveRows.reserve(size_t(nb) * 2 * sizeof(float4)));
+    PHYX_CUDA(cudaMemsetAsync(c->stamps.ptr, 0, size_t(nb) * 2 * sizeof(unsigned long long), c->stream));
+    PHYX_CUDA(cudaMemsetAsync(c->solveFlags.ptr, 0, 128, c->stream));
+    PHYX_CUDA(cudaMemsetAsync(c->processed.ptr, 0, size_t(ns) * sizeof(int), c->stream));
+    PHYX_CUDA(cudaMemsetAsync(pt.state.as<char>() + 8, 0, sizeof(PartDevState) - 8, c->stream));   // everything but xseq
+
+    // rows in the broadphase's sorted-x order when there is one (the layout was built on the same choice)
+    const bool sorted = c->rowOrderValid && c->rowOrderBodies == nb;
+    const unsigned* order = sorted ? c->entryIndex.as<unsigned>() : nullptr;
+    const int* rowOf = sorted ? c->rowOf.as<int>() : nullptr;
+    float4* rowsVel = c->solveRows.as<float4>();
+    float4* rowsDisp = rowsVel + nb;
+    k_prepare_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, c->vel.as<float4>(), c->disp.as<float4>(), rowsVel, rowsDisp, nullptr, nullptr);
+    c->launches++;
+    // RefreshJoints for the slots this rank relaxes: its own class and the cut class
+    const int ranges[2][2] = { { pt.classSlotStart[pt.rank], pt.classSlotStart[pt.rank + 1] }, { pt.classSlotStart[R], pt.classSlotStart[R + 1] } };
+    for (const auto& rg : ranges)
+    {
+        const int n = rg[1] - rg[0];
+        if (n <= 0) continue;
+        k_refresh<<<(n + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(rg[1], c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
+            c->params.as<float4>(), rowOf, nullptr, nullptr, nullptr, nullptr, c->accNF.as<float2>(), c->accD.as<float>(), c->pairQ.as<float4>(),
+            c->pairIdx.as<int2>(), rg[0]);
+        c->launches++;
+    }
+    if (!pt.params) pt.params = new SolveParams;
+    SolveParams& P = *static_cast<SolveParams*>(pt.params);
+    memset(&P, 0, sizeof(P));
+    P.vel = rowsVel;
+    P.disp = rowsDisp;
+    P.accNF = c->accNF.as<float2>();
+    P.accD = c->accD.as<float>();
+    P.levels = pt.partLevels.as<Level>();
+    P.numLevels = pt.numInterior + pt.numCut;
+    P.processed = c->processed.as<int>();
+    P.staticImp = c->stamps.as<unsigned long long>();
+    P.staticDisp = P.staticImp + nb;
+    P.contactIters = cfg->contactIterationsCount;
+    P.penetrationIters = cfg->penetrationIterationsCount;
+    P.barrier = c->solveFlags.as<unsigned long long>();   // two rings of 4 words
+    P.pairQ = c->pairQ.as<float4>();
+    P.pairIdx = c->pairIdx.as<int2>();
+    {
+        int per = 0;
+        PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_part_solve<kPartThreads, 2>, kPartThreads, 0));
+        if (per < 1)
+        {
+            set_error("partitioned solve kernel does not fit on an SM");
+            return PHYX_B200_ERR_CUDA;
+        }
+        c->solveBlocksPerSM = per;
+    }
+    PHYX_CUDA(cudaGetLastError());
+    return PHYX_B200_OK;
+}
+
+// one launch: phase -1 (warm start), 0 (impulse iteration `it`), 1 (displacement iteration `it`); mode 0 interior, 1 cut
+int part_launch(phyx_b200_ctx* c, int phase, int it, int mode)
+{
+    Partition& pt = c->part;
+    if (c->jointCount == 0) return PHYX_B200_OK;
+    PartArgs A = part_args(c);
+    A.phase = phase;
+    A.it = it;
+    A.mode = mode;
+    A.levelBegin = mode == 0 ? 0 : pt.numInterior;
+    A.levelEnd = mode == 0 ? pt.numInterior : pt.numInterior + pt.numCut;
+    A.ring = pt.launchIndex & 1;
+    A.tickBase = (pt.launchIndex + 1) * 128;
+    pt.launchIndex++;
+    const int widest = (mode == 0 ? pt.widestInterior : pt.widestCut) / 2;   // manifolds of the widest level
+    const int want = (widest + kPartThreads - 1) / kPartThreads;
+    const int grid = std::max(1, std::min(want, c->numSMs * c->solveBlocksPerSM));
+    SolveParams& P = *static_cast<SolveParams*>(pt.params);
+    void* args[] = { &P, &A };
+    PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_part_solve<kPartThreads, 2>, dim3(grid), dim3(kPartThreads), args, 0, c->stream));
+    c->launches++;
+    return PHYX_B200_OK;
+}
+
+// end of the solve: every rank hands its own rows (both arrays) and the accumulated impulses of its own slots
+// to all peers, so that the replicas are identical again for FinishJoints / FinishBodies and the next stages
+int part_bulk_push(phyx_b200_ctx* c)
+{
+    Partition& pt = c->part;
+    if (c->jointCount == 0) return PHYX_B200_OK;
+    const int nb = c->bodyCount, r = pt.rank;
+    const size_t rowsN = size_t(pt.cuts[r + 1] - pt.cuts[r]), slotsN = size_t(pt.classSlotStart[r + 1] - pt.classSlotStart[r]);
+    const float4* rowsVel = c->solveRows.as<float4>();
+    const float4* rowsDisp = rowsVel + nb;
+    const size_t base = part_bulk_offset(pt) + size_t(r) * pt.bulkCapacity;
+    for (int q = 0; q < pt.ranks; ++q)
+    {
+        if (q == r) continue;
+        char* dst = pt.peer[q] + base;
+        if (rowsN)
+        {
+            PHYX_CUDA(cudaMemcpyAsync(dst, rowsVel + pt.cuts[r], rowsN * sizeof(float4), cudaMemcpyDefault, c->stream));
+            PHYX_CUDA(cudaMemcpyAsync(dst + rowsN * sizeof(float4), rowsDisp + pt.cuts[r], rowsN * sizeof(float4), cudaMemcpyDefault, c->stream));
+        }
+        if (slotsN)
+            PHYX_CUDA(cudaMemcpyAsync(dst + 2 * rowsN * sizeof(float4), c->accNF.as<float2>() + pt.classSlotStart[r], slotsN * sizeof(float2), cudaMemcpyDefault, c->stream));
+    }
+    pt.bulkSeq++;
+    k_part_bulk_signal<<<1, 1, 0, c->stream>>>(part_args(c), pt.bulkSeq);
+    c->launches++;
+    PHYX_CUDA(cudaGetLastError());
+    return PHYX_B200_OK;
+}
+
+int part_bulk_pull(phyx_b200_ctx* c)
+{
+    Partition& pt = c->part;
+    if (c->jointCount == 0) return PHYX_B200_OK;
+    const int nb = c->bodyCount;
+    k_part_bulk_wait<<<1, 1, 0, c->stream>>>(part_args(c), pt.bulkSeq);
+    c->launches++;
+    float4* rowsVel = c->solveRows.as<float4>();
+    float4* rowsDisp = rowsVel + nb;
+    for (int q = 0; q < pt.ranks; ++q)
+    {
+        if (q == pt.rank) continue;
+        const size_t rowsN = size_t(pt.cuts[q + 1] - pt.cuts[q]), slotsN = size_t(pt.classSlotStart[q + 1] - pt.classSlotStart[q]);
+        const char* src = pt.xbuf + part_bulk_offset(pt) + size_t(q) * pt.bulkCapacity;
+        if (rowsN)
+        {
+            PHYX_CUDA(cudaMemcpyAsync(rowsVel + pt.cuts[q], src, rowsN * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+            PHYX_CUDA(cudaMemcpyAsync(rowsDisp + pt.cuts[q], src + rowsN * sizeof(float4), rowsN * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (slotsN)
+            PHYX_CUDA(cudaMemcpyAsync(c->accNF.as<float2>() + pt.classSlotStart[q], src + 2 * rowsN * sizeof(float4), slotsN * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return PHYX_B200_OK;
+}
+
+// FinishJoints / FinishBodies on the (again identical) replicas; results of this rank
+int part_end(phyx_b200_ctx* c, phyx_b200_solve_stats* stats)
+{
+    Partition& pt = c->part;
+    const int ns = c->slotCount, nb = c->bodyCount;
+    PartDevState host;
+    memset(&host, 0, sizeof(host));
+    if (c->jointCount > 0)
+    {
+        const bool sorted = c->rowOrderValid && c->rowOrderBodies == nb;
+        const unsigned* order = sorted ? c->entryIndex.as<unsigned>() : nullptr;
+        float4* rowsVel = c->solveRows.as<float4>();
+        k_finish<<<(ns + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->accNF.as<float2>(), c->joints.as<phyx_contact_joint>());
+        k_finish_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, rowsVel, rowsVel + nb, c->vel.as<float4>(), c->disp.as<float4>());
+        c->launches += 2;
+        PHYX_CUDA(cudaMemcpyAsync(&host, pt.state.ptr, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+        if (host.error)
+        {
+            set_error("solve_partitioned: rank %d gave up waiting for a peer's boundary rows (a peer failed or did not call the solve)", pt.rank);
+            return PHYX_B200_ERR_STATE;
+        }
+    }
+    if (stats)
+    {
+        stats->joints = c->jointCount;
+        stats->slots = ns;
+        stats->levels = c->levelCount;
+        stats->contactIterationsRun = c->jointCount ? host.ran[0] : 0;
+        stats->penetrationIterationsRun = c->jointCount ? host.ran[1] : 0;
+        stats->wakePasses = host.wakePasses;
+        stats->colourRounds = c->colourRounds;
+        stats->activeJointIterations[0] = (long long)host.active[0];
+        stats->activeJointIterations[1] = (long long)host.active[1];
     }
     return PHYX_B200_OK;
 }

@@ -1,0 +1,166 @@
+"""One world over several devices: host side of the partitioned solve (include/phyx_b200.h
+"one world over several devices"; SURVEY.md §8e "an island that spans devices").
+
+Every rank holds the whole world and runs the collider stages redundantly; Solver::SolveJoints is split
+by solver row.  This module holds
+
+* the plumbing that connects the ranks' exchange buffers: `LocalGroup` for ranks living in ONE process
+  (device pointers are handed over directly; what the single-GPU tests use, and what a single host
+  process driving several devices would use) and `attach_process_group` for one process per GPU
+  (CUDA IPC handles travel through torch.distributed; the data path itself never touches it);
+* `ReplicatedWorld`, the per-rank World::Update loop on top of it;
+* `plan_model`, a numpy statement of the partition plan the device builds (row cuts balanced by
+  manifold count, interior / cut classes, boundary rows), used to check the device's plan;
+* `sequential_equivalent`, the rewrite under which a plain sequential sweep over the partitioned slot
+  order reproduces the partitioned execution exactly (every rank its own copy of each static body).
+"""
+import numpy as np
+
+from . import capi, scenes
+from . import types as T
+
+
+# ---------------------------------------------------------------------------------------------------
+def plan_model(row1, row2, ranks):
+    """row1/row2: solver row of each coloured manifold's bodies, -1 for a static body.
+    Returns (cuts[ranks+1], cls[manifolds] with `ranks` = cut, boundary rows sorted)."""
+    row1, row2 = np.asarray(row1, np.int64), np.asarray(row2, np.int64)
+    nb = int(max(row1.max(initial=-1), row2.max(initial=-1)) + 1)
+    return plan_model_n(row1, row2, ranks, nb)
+
+
+def plan_model_n(row1, row2, ranks, nb):
+    row1, row2 = np.asarray(row1, np.int64), np.asarray(row2, np.int64)
+    both = (row1 >= 0) & (row2 >= 0)
+    home = np.where(row1 < 0, row2, np.where(row2 < 0, row1, np.minimum(row1, row2)))
+    hist = np.bincount(home[home >= 0], minlength=nb)
+    prefix = np.concatenate([[0], np.cumsum(hist)])          # prefix[r] = manifolds whose home row is < r
+    total = int(prefix[-1])
+    cuts = np.zeros(ranks + 1, np.int64)
+    cuts[ranks] = nb
+    for q in range(1, ranks):
+        target = (total * q + ranks - 1) // ranks
+        cuts[q] = int(np.searchsorted(prefix, target, side="left"))
+    inner = cuts[1:ranks]
+
+    def rank_of(rows):
+        return np.searchsorted(inner, rows, side="right")
+
+    k1, k2 = rank_of(row1), rank_of(row2)
+    cls = np.where(both, np.where(k1 == k2, k1, ranks), np.where(row1 >= 0, k1, np.where(row2 >= 0, k2, 0)))
+    cut = both & (k1 != k2)
+    boundary = np.unique(np.concatenate([row1[cut], row2[cut]]))
+    return cuts, cls, boundary
+
+
+def sequential_equivalent(bodies, joints, slots, class_slot_start, ranks):
+    """The partitioned solve equals ONE sequential sweep over the slot order, except that a static body's
+    lastIteration (Solver.cpp:790-798, 903-910) is tracked per rank.  Returns (bodies', joints') in which the
+    joints of rank q > 0 reference rank q's own copy of each static body (copies appended after the originals);
+    a plain sequential sweep of that problem in slot order is what the devices compute."""
+    bodies = np.asarray(bodies)
+    joints = np.array(joints, copy=True)
+    static = np.nonzero((bodies["invMass"] == 0) & (bodies["invInertia"] == 0))[0]
+    n, ns = bodies.shape[0], static.size
+    if ns == 0:
+        return bodies.copy(), joints
+    clone_of = np.full(n, -1, np.int64)
+    clone_of[static] = np.arange(ns)
+    out = np.concatenate([bodies] + [bodies[static]] * (ranks - 1))
+    slots = np.asarray(slots)
+    for q in range(1, ranks):
+        js = slots[class_slot_start[q]:class_slot_start[q + 1]]
+        js = js[js >= 0]
+        for f in ("body1Index", "body2Index"):
+            b = joints[f][js]
+            is_static = clone_of[b] >= 0
+            joints[f][js] = np.where(is_static, n + (q - 1) * ns + clone_of[b], b)
+    return out, joints
+
+
+# ---------------------------------------------------------------------------------------------------
+def default_capacities(bodies, ranks):
+    """Exchange buffer sizes for a world of `bodies` bodies: boundary rows per peer and pass, bulk bytes per peer
+    (32 B per body + 8 B per slot, slots <= ~6 per body incl. padding, if ONE rank owned everything)."""
+    boundary = max(4096, int(bodies) // 4)
+    bulk = int(bodies) * 32 + (6 * int(bodies) + 64 * 64 * (ranks + 1)) * 8
+    return boundary, bulk
+
+
+class LocalGroup:
+    """`ranks` contexts in this process forming one partition (all on `devices[k]`, default device 0)."""
+
+    def __init__(self, contexts, devices=None, capacities=None):
+        self.ctx = list(contexts)
+        self.ranks = len(self.ctx)
+        self.devices = list(devices) if devices is not None else [0] * self.ranks
+        n = max(c.l.phyx_b200_body_count(c.h) for c in self.ctx)
+        boundary, bulk = capacities or default_capacities(max(n, 1), self.ranks)
+        ptrs = []
+        for k, c in enumerate(self.ctx):
+            _, p = c.partition_create(k, self.ranks, boundary, bulk)
+            ptrs.append(p)
+        for c in self.ctx:
+            c.partition_attach(self.ranks, local_pointers=ptrs, peer_devices=self.devices)
+
+    def solve(self, iters=(20, 20)):
+        import ctypes as C
+
+        l = self.ctx[0].l
+        handles = (C.c_void_p * self.ranks)(*[c.h for c in self.ctx])
+        cfg = capi.SolveConfig(iters[0], iters[1], capi.SCHEDULE_COLOUR, 0)
+        stats = (capi.SolveStats * self.ranks)()
+        self.ctx[0]._check(l.phyx_b200_solve_partitioned_group(handles, self.ranks, C.byref(cfg), stats))
+        return list(stats)
+
+    def close(self):
+        for c in self.ctx:
+            c.partition_destroy()
+
+
+def attach_process_group(ctx, capacities, group=None):
+    """One process per GPU: create this rank's exchange buffer, swap CUDA IPC handles with the other ranks of the
+    torch.distributed group (object all-gather; bootstrap only) and open theirs.  Returns (rank, ranks)."""
+    import torch.distributed as dist
+
+    rank, ranks = dist.get_rank(group), dist.get_world_size(group)
+    handle, _ = ctx.partition_create(rank, ranks, capacities[0], capacities[1])
+    handles = [None] * ranks
+    dist.all_gather_object(handles, handle, group=group)
+    ctx.partition_attach(ranks, ipc_handles=handles)
+    dist.barrier(group=group)
+    return rank, ranks
+
+
+class ReplicatedWorld:
+    """World::Update with the solve shared between the ranks: every stage but SolveJoints runs redundantly on each
+    rank's replica (reference src/World.cpp:19-37), SolveJoints is `solve` (a callable returning solve stats)."""
+
+    def __init__(self, ctx, bodies):
+        self.ctx = ctx
+        ctx.upload_bodies(bodies)
+
+    def stages_before_solve(self):
+        c = self.ctx
+        c.integrate_velocity(scenes.DT, scenes.GRAVITY)
+        c.update_broadphase()
+        bp = c.update_pairs()
+        c.update_manifolds()
+        c.pack_manifolds()
+        c.refresh_contact_joints()
+        return bp
+
+    def step(self, iters=(20, 20)):
+        bp = self.stages_before_solve()
+        st = self.ctx.solve_partitioned(iters)
+        self.ctx.integrate_position(scenes.DT)
+        return bp, st
+
+
+def body_records(scene):
+    """RigidBody records (reference AddBody semantics) for a scene array, via the host mirror."""
+    from . import world
+
+    w = world.World(scene, mirror_contents=False)
+    b = np.array(w.bodies(), dtype=T.RIGID_BODY, copy=True)
+    return b
