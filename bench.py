@@ -249,15 +249,26 @@ def run_ours(args, rank, world_size, local_rank):
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
     nb = scene.shape[0]
 
+    stage_max = {}
+    stage_wall = {}   # host wall time per stage call of the timed resident loop (stages that read counts back wait for the GPU)
+
+    def timed(name, fn, *a, **k):
+        t = time.perf_counter()
+        r = fn(*a, **k)
+        ms = (time.perf_counter() - t) * 1e3
+        stage_wall[name] = stage_wall.get(name, 0.0) + ms
+        stage_max[name] = max(stage_max.get(name, 0.0), ms)
+        return r
+
     def resident_step():
-        ctx.integrate_velocity(scenes.DT, scenes.GRAVITY)
-        ctx.update_broadphase()
-        bp = ctx.update_pairs()
-        ctx.update_manifolds()
-        ctx.pack_manifolds()
-        ctx.refresh_contact_joints()
-        st = ctx.solve_resident(iters=ITERS, schedule=capi.SCHEDULE_COLOUR)
-        ctx.integrate_position(scenes.DT)
+        timed("IntegrateVelocity", ctx.integrate_velocity, scenes.DT, scenes.GRAVITY)
+        timed("UpdateBroadphase", ctx.update_broadphase)
+        bp = timed("UpdatePairs", ctx.update_pairs)
+        timed("UpdateManifolds", ctx.update_manifolds)
+        timed("PackManifolds", ctx.pack_manifolds)
+        timed("RefreshContactJoints", ctx.refresh_contact_joints)
+        st = timed("SolveJoints", ctx.solve_resident, iters=ITERS, schedule=capi.SCHEDULE_COLOUR)
+        timed("IntegratePosition", ctx.integrate_position, scenes.DT)
         return bp, st
 
     clocks = ClockSampler(local_rank)   # started before the warm-up so that its start-up cost is not in the timed region
@@ -267,6 +278,8 @@ def run_ours(args, rank, world_size, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.launch_count()
     stats = []
+    stage_wall.clear()
+    stage_max.clear()
     with clocks:
         e0.record(stream)
         for _ in range(args.steps):
@@ -358,6 +371,8 @@ def run_ours(args, rank, world_size, local_rank):
         "solve_ms_per_step": {"total": solve_ms, "schedule": float(np.mean([st.ms_schedule for _, st in stats])), "refresh": float(np.mean([st.ms_refresh for _, st in stats])),
                               "iterations_kernel": k_ms, "colour_rounds": int(stats[-1][1].colourRounds), "colours": int(stats[-1][1].levels)},
         "solve_only_constraint_iterations_per_sec": world_size * jm * sum(ITERS) / (solve_ms * 1e-3),
+        "resident_stage_wall_ms": {k: round(v / args.steps, 3) for k, v in stage_wall.items()},
+        "resident_stage_wall_ms_max": {k: round(v, 3) for k, v in stage_max.items()},
         "steps_per_sec": world_size * 1e3 / ms_step,
         "broadphase": {"pairs": int(bp_last.pairs), "tests": int(bp_last.tests)},
     }

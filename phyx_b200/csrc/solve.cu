@@ -1527,11 +1527,14 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
             dual ? c->staticMulti.as<unsigned char>() : nullptr, dual ? c->rowsMulti.as<unsigned char>() : nullptr);
         c->launches++;
         int grid = (ns + kBlock - 1) / kBlock;
-        // manifold units (colour.cu): all levels are paired.  Default kernel for them: the record form with
-        // activity prediction (k_solve_pairs2); PHYX_SOLVE_PAIRS=1 selects the speculative streaming form.
+        // manifold units (colour.cu): all levels are paired.  Default kernel for them: the speculative streaming
+        // form (k_solve_pairs; measured 1.71 ms against 1.77-1.83 ms for the record form on the 1 M pyramid, which
+        // moves 4.4x fewer DRAM bytes but is bound by the same per-level barrier and latency chain);
+        // PHYX_SOLVE_PAIRS=2 selects the record form with activity prediction (k_solve_pairs2), which is also what
+        // the partitioned solve runs on.
         const bool paired = !c->hostLevels.empty() && c->hostLevels[0].grouped_end < 0;
         static const char* pairsEnv = getenv("PHYX_SOLVE_PAIRS");
-        const bool records = paired && !(pairsEnv && !strcmp(pairsEnv, "1"));
+        const bool records = paired && pairsEnv && !strcmp(pairsEnv, "2");
         if (records)
         {
             PHYX_TRY(c->pairQ.reserve(ns1 / 2 * 128 + 128));

@@ -157,10 +157,11 @@ class ReplicatedWorld:
         return bp, st
 
 
-def body_records(scene):
+def body_records(scene, device=0):
     """RigidBody records (reference AddBody semantics) for a scene array, via the host mirror."""
     from . import world
 
-    w = world.World(scene, mirror_contents=False)
+    w = world.World(scene, device=device, mirror_contents=False)
     b = np.array(w.bodies(), dtype=T.RIGID_BODY, copy=True)
+    w.close()
     return b
