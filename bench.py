@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--scene", default="pyramid_1m")
     ap.add_argument("--settle", type=int, default=30, help="untimed World::Update steps that build the contact state")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spanning", action="store_true",
+                    help="with --gpus N > 1: additionally run ONE world of the scene over all N GPUs (partitioned solve, boundary rows over NVLink peer memory) and report it under \"spanning\"")
     return ap.parse_args()
 
 
@@ -55,10 +57,11 @@ def parse():
 class ClockSampler:
     """SM clocks / throttle reasons DURING the timed region: the counters of the B200_PROFILING.md
     `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.*` line, read through
-    NVML (the library nvidia-smi itself prints from) by a thread of this process every 20 ms.  Spawning
-    nvidia-smi next to the timed loop was measured to stall the step's host<->driver round trips (its start-up
-    enumerates every GPU of the box under the driver lock: 11.4 ms per step instead of 3.5 ms), so the
-    subprocess form is only the fallback when pynvml is missing, and it is started BEFORE the warm-up steps."""
+    NVML (the library nvidia-smi itself prints from) by a thread of this process every 20 ms, started BEFORE
+    the warm-up steps: the first query on a freshly started box (and the start-up of an nvidia-smi process)
+    holds the driver for ~0.16 s, which landed in the first timed step when the sampler was started with the
+    timed region (11.4 instead of 3.5 ms per step over 20 steps).  The subprocess form is the fallback when
+    pynvml is missing."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
@@ -98,14 +101,17 @@ class ClockSampler:
     def _poll(self):
         n = self.nvml
         while not self.stop:
-            if self.recording:
-                try:
-                    sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
-                        else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            # query all the time, keep the samples of the timed region only: the FIRST query of a process can
+            # block the driver for ~0.16 s on a freshly started box (seen as one 160 ms UpdatePairs call in the
+            # first timed step), so it has to happen during the warm-up steps
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                if self.recording:
                     self.rows.append((sm, self.mx, mask))
-                except Exception:
-                    pass
+            except Exception:
+                pass
             time.sleep(0.02)
 
     def _read(self):
@@ -280,6 +286,7 @@ def run_ours(args, rank, world_size, local_rank):
     stats = []
     stage_wall.clear()
     stage_max.clear()
+    allocs0 = ctx.alloc_stats()
     with clocks:
         e0.record(stream)
         for _ in range(args.steps):
@@ -287,6 +294,7 @@ def run_ours(args, rank, world_size, local_rank):
         e1.record(stream)
         barrier()
     clocks.close()
+    allocs1 = ctx.alloc_stats()
     launches = ctx.launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
@@ -312,6 +320,16 @@ def run_ours(args, rank, world_size, local_rank):
         w.reset_stage_ms()
         w.step(solve=world.SOLVE_B200, iters=ITERS)
         stage_ms_e2e = {k: round(v, 3) for k, v in w.stage_ms().items()}
+
+    # ---- optional: ONE world over all ranks (an island that spans devices), strong scaling of the solve
+    spanning = None
+    if args.spanning and dist is not None:
+        from phyx_b200 import partition
+
+        try:
+            spanning = partition.run_spanning(args.scene, args.settle, max(3, min(args.steps, 10)), local_rank, iters=ITERS)
+        except Exception as e:  # noqa: BLE001 - the main line must still be printed
+            spanning = {"error": str(e)}
 
     if dist is not None:
         dist.barrier()
@@ -371,8 +389,10 @@ def run_ours(args, rank, world_size, local_rank):
         "solve_ms_per_step": {"total": solve_ms, "schedule": float(np.mean([st.ms_schedule for _, st in stats])), "refresh": float(np.mean([st.ms_refresh for _, st in stats])),
                               "iterations_kernel": k_ms, "colour_rounds": int(stats[-1][1].colourRounds), "colours": int(stats[-1][1].levels)},
         "solve_only_constraint_iterations_per_sec": world_size * jm * sum(ITERS) / (solve_ms * 1e-3),
+        "spanning": spanning,
         "resident_stage_wall_ms": {k: round(v / args.steps, 3) for k, v in stage_wall.items()},
         "resident_stage_wall_ms_max": {k: round(v, 3) for k, v in stage_max.items()},
+        "device_allocations_in_timed_region": {"count": allocs1[0] - allocs0[0], "host_ms": round(allocs1[1] - allocs0[1], 3)},
         "steps_per_sec": world_size * 1e3 / ms_step,
         "broadphase": {"pairs": int(bp_last.pairs), "tests": int(bp_last.tests)},
     }

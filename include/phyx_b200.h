@@ -132,6 +132,9 @@ PHYX_B200_API const char* phyx_b200_last_error(void);
 PHYX_B200_API const char* phyx_b200_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 PHYX_B200_API int64_t phyx_b200_launch_count(const phyx_b200_ctx* ctx);
+/* device (re)allocations made by this process's contexts so far and the host time spent in them; a steady-state
+ * step makes none (buffers grow with 2x headroom), so a difference across a timed region flags an outlier */
+PHYX_B200_API void phyx_b200_alloc_stats(int64_t* count, double* hostMs);
 /* CUDA stream all work of this context is issued on (cudaStream_t as void*), for event timing */
 PHYX_B200_API void* phyx_b200_stream(const phyx_b200_ctx* ctx);
 PHYX_B200_API int phyx_b200_synchronize(phyx_b200_ctx* ctx);

@@ -26,6 +26,7 @@ EXPORTS = (
     "phyx_b200_last_error",
     "phyx_b200_version",
     "phyx_b200_launch_count",
+    "phyx_b200_alloc_stats",
     "phyx_b200_stream",
     "phyx_b200_synchronize",
     "phyx_b200_upload_bodies",
@@ -126,6 +127,8 @@ def load():
     l.phyx_b200_destroy.restype = None
     l.phyx_b200_launch_count.argtypes = [vp]
     l.phyx_b200_launch_count.restype = i64
+    l.phyx_b200_alloc_stats.argtypes = [C.POINTER(i64), C.POINTER(C.c_double)]
+    l.phyx_b200_alloc_stats.restype = None
     l.phyx_b200_stream.argtypes = [vp]
     l.phyx_b200_stream.restype = vp
     l.phyx_b200_synchronize.argtypes = [vp]
@@ -366,6 +369,12 @@ class Context:
 
     def launch_count(self):
         return int(self.l.phyx_b200_launch_count(self.h))
+
+    def alloc_stats(self):
+        """(device allocations made by this process so far, host milliseconds spent in them)"""
+        n, ms = C.c_int64(0), C.c_double(0.0)
+        self.l.phyx_b200_alloc_stats(C.byref(n), C.byref(ms))
+        return int(n.value), float(ms.value)
 
     def stream(self):
         return int(self.l.phyx_b200_stream(self.h) or 0)

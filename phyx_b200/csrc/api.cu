@@ -4,6 +4,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <chrono>
 
 static_assert(sizeof(phyx_rigid_body) == 128, "RigidBody must keep the reference layout (128 B)");
 static_assert(sizeof(phyx_contact_joint) == 20, "ContactJoint must keep the reference layout (20 B)");
@@ -25,11 +26,35 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 
+// Device allocations made so far and the host time they took (phyx_b200_alloc_stats).  cudaMalloc / cudaFree are
+// driver round trips that synchronise the device; on shared hosts a single one was seen to take 0.3 s, so buffers
+// grow with generous headroom (request + 25 %, at least 2x the old size and 1 MiB) and a steady-state step makes none.
+static double g_allocMs = 0.0;
+static long long g_allocCount = 0;
+
+static size_t grow_to(size_t bytes, size_t cap)
+{
+    // 25 % beyond the request even on the first allocation: the persistent arrays (manifolds, contact points,
+    // joints) creep upwards by a few hundred records per step
+    size_t want = std::max(std::max(bytes + bytes / 4, cap * 2), size_t(1) << 20);
+    return (want + 255) & ~size_t(255);
+}
+
+struct AllocTimer
+{
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~AllocTimer()
+    {
+        g_allocMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        g_allocCount++;
+    }
+};
+
 int DevBuf::reserve(size_t bytes)
 {
     if (bytes <= cap) return PHYX_B200_OK;
-    size_t want = std::max(bytes, cap + cap / 2);
-    want = (want + 255) & ~size_t(255);
+    AllocTimer timer;
+    const size_t want = grow_to(bytes, cap);
     void* p = nullptr;
     PHYX_CUDA(cudaMalloc(&p, want));
     if (ptr) cudaFree(ptr);   // contents are scratch or re-filled by the caller: no copy
@@ -42,8 +67,8 @@ int DevBuf::reserve(size_t bytes)
 int DevBuf::reserve_keep(size_t bytes, size_t keepBytes, cudaStream_t stream)
 {
     if (bytes <= cap) return PHYX_B200_OK;
-    size_t want = std::max(bytes, cap + cap / 2);
-    want = (want + 255) & ~size_t(255);
+    AllocTimer timer;
+    const size_t want = grow_to(bytes, cap);
     void* p = nullptr;
     PHYX_CUDA(cudaMalloc(&p, want));
     if (ptr)
@@ -171,6 +196,12 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
 }
 
 int64_t phyx_b200_launch_count(const phyx_b200_ctx* c) { return c ? c->launches : 0; }
+
+void phyx_b200_alloc_stats(int64_t* count, double* hostMs)
+{
+    if (count) *count = g_allocCount;
+    if (hostMs) *hostMs = g_allocMs;
+}
 void* phyx_b200_stream(const phyx_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int phyx_b200_synchronize(phyx_b200_ctx* c)

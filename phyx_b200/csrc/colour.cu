@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "barrier.cuh"
 
+#include <stdlib.h>
+
 namespace phyx
 {
 
@@ -258,7 +260,11 @@ int colour_schedule_build(phyx_b200_ctx* c)
     bool incremental = c->colourStateValid && c->colourStateBodies == c->bodyCount && c->manColour.ptr && c->bodyUsed.ptr;
     int st = colour_units_build(c, incremental, &changed);
     const int colours = c->part.ranks > 1 ? c->partColours : c->levelCount;   // partitioned layouts have one level per (class, colour)
-    if (st == PHYX_B200_OK && incremental && (changed || colours > c->coloursAtFullBuild + 4))
+    // every colour is a level = a grid barrier and a latency chain per pass (~8-10 us x 22 passes on the bench scene),
+    // a full rebuild costs about a millisecond once: rebuild as soon as the incremental colouring has drifted two
+    // colours above the last full build (PHYX_COLOUR_DRIFT overrides the slack)
+    static const int drift = getenv("PHYX_COLOUR_DRIFT") ? atoi(getenv("PHYX_COLOUR_DRIFT")) : 1;
+    if (st == PHYX_B200_OK && incremental && (changed || colours > c->coloursAtFullBuild + drift))
         st = colour_units_build(c, false, &changed);
     return st;
 }

@@ -867,7 +867,7 @@ struct PairRecord   // layout of pairQ: 8 float4 per manifold; the displacement 
     float4 a0, a2, a3, b0, b2, b3, a1, b1;
 };
 
-constexpr int kPairU = 4;
+constexpr int kPairU = 4;   // manifolds a thread handles together (default; the 1024-threads-per-SM shape uses 2)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p);
 
@@ -911,20 +911,20 @@ __device__ __forceinline__ void prestep_pair2(const SolveParams& P, int p)
 // One pass over one paired level.  `pre` holds the index words of this thread's first batch when havePre
 // is set.  First passes record which manifolds were active in `activity` (bit = bitCursor + position in
 // the thread's visiting order, first 64 only) and advance bitCursor; wake passes leave both alone.
-template <int PHASE>
+template <int PHASE, int U>
 __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L, int it, int tick, bool firstPass, int tid, int nthreads, bool& wake,
-    unsigned& activeCount, const int2 (&pre)[kPairU], bool havePre, unsigned& bitCursor, unsigned long long& activity, unsigned scratch)
+    unsigned& activeCount, const int2 (&pre)[U], bool havePre, unsigned& bitCursor, unsigned long long& activity, unsigned scratch)
 {
     float4* rows = PHASE == 0 ? P.vel : P.disp;
     unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
     const int pairBase = L.start >> 1, numPairs = (L.end - L.start) >> 1;
     bool anyProductive = false;
-    for (long long first = tid; first < numPairs; first += static_cast<long long>(kPairU) * nthreads)
+    for (long long first = tid; first < numPairs; first += static_cast<long long>(U) * nthreads)
     {
-        int2 idx[kPairU];
-        float4 v1[kPairU], v2[kPairU];
+        int2 idx[U];
+        float4 v1[U], v2[U];
 #pragma unroll
-        for (int u = 0; u < kPairU; ++u)
+        for (int u = 0; u < U; ++u)
         {
             const long long p = first + static_cast<long long>(u) * nthreads;
             if (havePre)
@@ -934,7 +934,7 @@ __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L
         }
         havePre = false;
 #pragma unroll
-        for (int u = 0; u < kPairU; ++u)
+        for (int u = 0; u < U; ++u)
         {
             bool valid = idx[u].x >= 0;
             if (!firstPass && valid)   // wake pass: only manifolds a static body can wake, and only those that have not run yet
@@ -955,9 +955,9 @@ __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L
         // an earlier one of this batch wakes up through a static body is caught by the wake pass, like one
         // woken by another thread.  (Pulling the records of the active ones into L1 at this point with
         // LDGSTS.ca was measured: 11.3 instead of 10.4 us per level pass, the L1 does not survive.)
-        int last1v[kPairU], last2v[kPairU];
+        int last1v[U], last2v[U];
 #pragma unroll
-        for (int u = 0; u < kPairU; ++u)
+        for (int u = 0; u < U; ++u)
         {
             const int r1 = idx[u].x, r2 = idx[u].y;
             if (r1 < 0) continue;
@@ -973,7 +973,7 @@ __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L
             }
         }
 #pragma unroll
-        for (int u = 0; u < kPairU; ++u)
+        for (int u = 0; u < U; ++u)
         {
             const int r1 = idx[u].x, r2 = idx[u].y;
             if (r1 < 0) continue;
@@ -1034,16 +1034,16 @@ __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L
             if (st1 || st2) __stcg(&P.processed[s], tick);
             anyProductive |= productive;
         }
-        if (firstPass) bitCursor += kPairU;
+        if (firstPass) bitCursor += U;
     }
     return anyProductive;
 }
 
-template <int PHASE>
+template <int PHASE, int U>
 __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Level* levels, unsigned scratch, int iters, int tid, int nthreads, unsigned& epoch,
     int& tick, int& wakePasses, unsigned& activeCount)
 {
-    int2 pre[kPairU];
+    int2 pre[U];
     bool havePre = false;
     int ran = 0;
     unsigned long long predicted = ~0ull;   // iteration 0 relaxes every joint (lastIteration = -1 > -2)
@@ -1057,7 +1057,7 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
             const Level L = levels[l];
             ++tick;
             bool wake = false;
-            any |= solve_pairs2<PHASE>(P, L, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre, bitCursor, activity, scratch);
+            any |= solve_pairs2<PHASE, U>(P, L, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre, bitCursor, activity, scratch);
             // While the grid drains into the barrier: index words of this thread's first batch of the level that
             // follows, and an L2 prefetch of the records it is expected to need (this iteration's own activity
             // bits when the next level is level 0 of the next iteration, else last iteration's).
@@ -1068,7 +1068,7 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
                 const unsigned cursorN = wrap ? 0u : bitCursor;
                 const unsigned long long hint = wrap ? activity : predicted;
 #pragma unroll
-                for (int u = 0; u < kPairU; ++u)
+                for (int u = 0; u < U; ++u)
                 {
                     const long long pN = tid + static_cast<long long>(u) * nthreads;
                     pre[u] = make_int2(-1, -1);
@@ -1093,11 +1093,11 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
             timeline_mark(P, tick);
             while (r.wake)
             {
-                int2 none[kPairU];
+                int2 none[U];
                 unsigned dummyCursor = 0u;
                 unsigned long long dummyActivity = 0ull;
                 wake = false;
-                any |= solve_pairs2<PHASE>(P, L, it, tick, false, tid, nthreads, wake, activeCount, none, false, dummyCursor, dummyActivity, scratch);
+                any |= solve_pairs2<PHASE, U>(P, L, it, tick, false, tid, nthreads, wake, activeCount, none, false, dummyCursor, dummyActivity, scratch);
                 ++wakePasses;
                 r = grid_barrier(P.barrier, epoch, wake, any);
             }
@@ -1111,7 +1111,7 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
     return ran;
 }
 
-template <int THREADS, int MIN_BLOCKS>
+template <int THREADS, int MIN_BLOCKS, int U>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve_pairs2(SolveParams P)
 {
     // the level table is read once per level pass, right behind the grid barrier: keep it in shared memory
@@ -1138,8 +1138,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve_pairs2(SolveParam
         grid_barrier(P.barrier, epoch, false, false);
     }
 
-    const int ranImpulse = run_phase_pairs2<0>(P, levels, scratch, P.contactIters, tid, nthreads, epoch, tick, wakePasses, active[0]);
-    const int ranDisplacement = run_phase_pairs2<1>(P, levels, scratch, P.penetrationIters, tid, nthreads, epoch, tick, wakePasses, active[1]);
+    const int ranImpulse = run_phase_pairs2<0, U>(P, levels, scratch, P.contactIters, tid, nthreads, epoch, tick, wakePasses, active[0]);
+    const int ranDisplacement = run_phase_pairs2<1, U>(P, levels, scratch, P.penetrationIters, tid, nthreads, epoch, tick, wakePasses, active[1]);
 
     for (int phase = 0; phase < 2; ++phase)
     {
@@ -1588,7 +1588,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         static const int shapeEnv = getenv("PHYX_SOLVE_SHAPE") ? atoi(getenv("PHYX_SOLVE_SHAPE")) : 5122;
         int sblock = 512;
         void* solveKernel = nullptr;
-#define PHYX_PICK(T, B) (records ? (void*)k_solve_pairs2<T, B> : paired ? (void*)k_solve_pairs<T, B> : dual ? (void*)k_solve<T, B, true> : (void*)k_solve<T, B, false>)
+#define PHYX_PICK(T, B) (records ? (void*)k_solve_pairs2<T, B, (T * B >= 1024 ? 2 : kPairU)> : paired ? (void*)k_solve_pairs<T, B> : dual ? (void*)k_solve<T, B, true> : (void*)k_solve<T, B, false>)
         switch (paired && !getenv("PHYX_SOLVE_SHAPE") ? 2562 : shapeEnv)
         {
         case 2562: sblock = 256; solveKernel = PHYX_PICK(256, 2); break;
@@ -1841,17 +1841,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_part_solve(SolveParams 
         unsigned long long activity = 0ull;
         bool wake = false;
         if (A.phase == 0)
-            any |= solve_pairs2<0>(P, L, A.it, tick, true, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+            any |= solve_pairs2<0, kPairU>(P, L, A.it, tick, true, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
         else
-            any |= solve_pairs2<1>(P, L, A.it, tick, true, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+            any |= solve_pairs2<1, kPairU>(P, L, A.it, tick, true, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
         BarrierResult r = grid_barrier(ring, epoch, wake, any);
         while (r.wake)
         {
             wake = false;
             if (A.phase == 0)
-                any |= solve_pairs2<0>(P, L, A.it, tick, false, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+                any |= solve_pairs2<0, kPairU>(P, L, A.it, tick, false, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
             else
-                any |= solve_pairs2<1>(P, L, A.it, tick, false, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+                any |= solve_pairs2<1, kPairU>(P, L, A.it, tick, false, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
             ++wakePasses;
             r = grid_barrier(ring, epoch, wake, any);
         }

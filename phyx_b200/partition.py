@@ -120,15 +120,30 @@ class LocalGroup:
 
 def attach_process_group(ctx, capacities, group=None):
     """One process per GPU: create this rank's exchange buffer, swap CUDA IPC handles with the other ranks of the
-    torch.distributed group (object all-gather; bootstrap only) and open theirs.  Returns (rank, ranks)."""
+    torch.distributed group (object all-gather; bootstrap only) and open theirs.  Returns (rank, ranks).
+    Every rank reaches the all-gather even if its own buffer could not be created, so a failure raises on all
+    ranks instead of leaving the others waiting."""
     import torch.distributed as dist
 
     rank, ranks = dist.get_rank(group), dist.get_world_size(group)
-    handle, _ = ctx.partition_create(rank, ranks, capacities[0], capacities[1])
+    handle, error = None, None
+    try:
+        handle, _ = ctx.partition_create(rank, ranks, capacities[0], capacities[1])
+    except Exception as e:  # noqa: BLE001 - reported to every rank below
+        error = f"rank {rank}: {e}"
     handles = [None] * ranks
-    dist.all_gather_object(handles, handle, group=group)
-    ctx.partition_attach(ranks, ipc_handles=handles)
-    dist.barrier(group=group)
+    dist.all_gather_object(handles, handle if error is None else {"error": error}, group=group)
+    bad = [h["error"] for h in handles if isinstance(h, dict)]
+    if not bad:
+        try:
+            ctx.partition_attach(ranks, ipc_handles=handles)
+        except Exception as e:  # noqa: BLE001
+            error = f"rank {rank}: {e}"
+    outcome = [None] * ranks
+    dist.all_gather_object(outcome, error, group=group)
+    bad += [o for o in outcome if o]
+    if bad:
+        raise capi.PhyxError("partition set-up failed: " + "; ".join(sorted(set(bad))))
     return rank, ranks
 
 
@@ -165,3 +180,82 @@ def body_records(scene, device=0):
     b = np.array(w.bodies(), dtype=T.RIGID_BODY, copy=True)
     w.close()
     return b
+
+
+def run_spanning(scene_name, settle, steps, device, iters=(20, 20), group=None, check=False):
+    """ONE world over all ranks of the torch.distributed group (one process per GPU): every rank steps its replica,
+    the solve is partitioned.  Returns a dict on every rank (timings are this rank's; `ms_per_step` is the max over
+    ranks of the CUDA-event time of the timed steps).  check: rank 0 repeats the run with all ranks as contexts on
+    its own device and requires bit-identical bodies; it also times the one-device solve on the same states."""
+    import hashlib
+
+    import torch
+    import torch.distributed as dist
+
+    def digest(b):
+        h = hashlib.sha256()
+        for f in ("pos", "xVector", "velocity", "angularVelocity"):
+            h.update(np.ascontiguousarray(b[f]).tobytes())
+        return h.hexdigest()
+
+    rank, ranks = dist.get_rank(group), dist.get_world_size(group)
+    bodies = body_records(scenes.make(scene_name), device=device)
+    n = bodies.shape[0]
+    ctx = capi.Context(device)
+    world = ReplicatedWorld(ctx, bodies)
+    attach_process_group(ctx, default_capacities(n, ranks), group=group)
+    for _ in range(settle):
+        world.step(iters)
+    ctx.synchronize()
+    dist.barrier(group=group)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    stats = [world.step(iters)[1] for _ in range(steps)]
+    e1.record(stream)
+    ctx.synchronize()
+    dist.barrier(group=group)
+    ms = torch.tensor([e0.elapsed_time(e1) / max(steps, 1)], dtype=torch.float64, device=f"cuda:{device}" if dist.get_backend(group) == "nccl" else "cpu")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=group)
+    digests = [None] * ranks
+    dist.all_gather_object(digests, digest(ctx.download_bodies()), group=group)
+    cuts, bstart, cls = ctx.partition_plan(ranks)
+    last = stats[-1]
+    out = {
+        "scene": scene_name, "bodies": int(n), "joints": int(last.joints), "ranks": ranks, "steps": steps, "settle": settle,
+        "ms_per_step": float(ms.item()),
+        "constraint_iterations_per_sec": float(np.mean([s.joints for s in stats])) * sum(iters) / (float(ms.item()) * 1e-3),
+        "replicas_identical": len(set(digests)) == 1,
+        "solve_ms": float(np.mean([s.ms_total for s in stats])), "passes_ms": float(np.mean([s.ms_iterations for s in stats])),
+        "schedule_ms": float(np.mean([s.ms_schedule for s in stats])), "end_exchange_and_finish_ms": float(np.mean([s.ms_finish for s in stats])),
+        "iterations_run": [int(last.contactIterationsRun), int(last.penetrationIterationsRun)],
+        "row_cuts": cuts.tolist(), "boundary_rows": int(bstart[-1]), "cut_manifolds": int(cls[-1] - cls[-2]) // 2, "slots": int(cls[-1]),
+        "exchange": "peer stores over CUDA IPC mapped buffers + sequence flags, once per pass (warm start, impulse and displacement iterations)",
+    }
+    if check and rank == 0:
+        ctxs = [capi.Context(device) for _ in range(ranks)]
+        worlds = [ReplicatedWorld(c, bodies) for c in ctxs]
+        grp = LocalGroup(ctxs, devices=[device] * ranks)
+        one = ReplicatedWorld(capi.Context(device), bodies)
+        one_ms = []
+        for step in range(settle + steps):
+            for w in worlds:
+                w.stages_before_solve()
+            grp.solve(iters)
+            for c in ctxs:
+                c.integrate_position(scenes.DT)
+            one.stages_before_solve()
+            st = one.ctx.solve_resident(iters=iters, schedule=capi.SCHEDULE_COLOUR)
+            one.ctx.integrate_position(scenes.DT)
+            if step >= settle:
+                one_ms.append(st.ms_total)
+        out["matches_in_process_group"] = digest(ctxs[0].download_bodies()) == digests[0]
+        out["one_device_solve_ms"] = float(np.mean(one_ms))
+        grp.close()
+        for c in ctxs:
+            c.close()
+        one.ctx.close()
+    dist.barrier(group=group)
+    ctx.partition_destroy()
+    ctx.close()
+    return out
