@@ -14,11 +14,15 @@ struct BarrierResult
     bool wake, productive;
 };
 
-__device__ __forceinline__ BarrierResult grid_barrier(unsigned long long* ring, unsigned& epoch, bool wake, bool productive)
+// Split form: arrive as soon as the CTA's last store of the level is issued, do independent work (prefetches for
+// the next level), then wait.  Thread 0's release fence waits for ITS outstanding memory operations, so loads
+// issued before the arrival would delay the whole CTA's arrival by their latency; issued between arrive and
+// wait they overlap the barrier instead.
+__device__ __forceinline__ void grid_arrive(unsigned long long* ring, unsigned epoch, bool wake, bool productive, unsigned long long& ticket)
 {
-    __shared__ unsigned long long s_value;
     const int w = __syncthreads_or(wake ? 1 : 0);
     const int pr = __syncthreads_or(productive ? 1 : 0);
+    ticket = 0ull;
     if (threadIdx.x == 0)
     {
         unsigned long long* word = ring + (epoch & 3u);
@@ -27,7 +31,17 @@ __device__ __forceinline__ BarrierResult grid_barrier(unsigned long long* ring, 
         // release: the CTA's writes (ordered before this point by the __syncthreads above) become visible before
         // the arrival; acq_rel is enough for the fence-atomic-fence pattern and cheaper than __threadfence's MEMBAR.SC
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        unsigned long long v = atomicAdd(word, add) + add;
+        ticket = atomicAdd(word, add) + add;
+    }
+}
+
+__device__ __forceinline__ BarrierResult grid_wait(unsigned long long* ring, unsigned& epoch, unsigned long long ticket)
+{
+    __shared__ unsigned long long s_value;
+    if (threadIdx.x == 0)
+    {
+        unsigned long long* word = ring + (epoch & 3u);
+        unsigned long long v = ticket;
         // poll with relaxed loads and acquire once at the end: an acquire load per poll costs an L1
         // invalidation of the whole SM (SASS CCTL.IVALL, ~75 polls per barrier in the ncu capture of r1g)
         while ((v & 0xfffffull) != gridDim.x)
@@ -42,6 +56,13 @@ __device__ __forceinline__ BarrierResult grid_barrier(unsigned long long* ring, 
     r.wake = ((v >> 20) & 0xfffffull) != 0;
     r.productive = ((v >> 40) & 0xfffffull) != 0;
     return r;
+}
+
+__device__ __forceinline__ BarrierResult grid_barrier(unsigned long long* ring, unsigned& epoch, bool wake, bool productive)
+{
+    unsigned long long ticket;
+    grid_arrive(ring, epoch, wake, productive, ticket);
+    return grid_wait(ring, epoch, ticket);
 }
 
 } // namespace phyx

@@ -40,6 +40,7 @@ constexpr int kBlock = 256;
 constexpr float kProductiveImpulse = 1e-4f;    // Solver.cpp:8
 constexpr float kFrictionCoefficient = 0.3f;   // Solver.cpp:9
 constexpr int kPairHasB = int(0x80000000u);    // pairIdx.y: the manifold has a second joint
+constexpr int kPairRecordWords = 6;            // float4 per manifold record (PairRecord below)
 
 struct SolveParams
 {
@@ -182,14 +183,17 @@ __global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __r
 
     if (pairQ)
     {
-        // record form (PairRecord below): {a0, a2, a3, b0, b2, b3, a1, b1}, a = slot 2p, b = slot 2p+1
+        // record form (PairRecord below): six float4 per manifold, a = slot 2p, b = slot 2p+1
         const int h = s & 1;
-        float4* rec = pairQ + size_t(s >> 1) * 8;
-        rec[h ? 3 : 0] = make_float4(nx, ny, aN1, aN2);
-        rec[h ? 4 : 1] = make_float4(p1.x, p1.y, p2.x, p2.y);
-        rec[h ? 5 : 2] = make_float4(__int_as_float(b1), __int_as_float(b2), cinvN, dstDisp);
-        rec[h ? 7 : 6] = make_float4(aF1, aF2, cinvF, dstVel);
-        if (!h) pairIdx[s >> 1] = make_int2(b1, b2 | (slotJoint[s + 1] >= 0 ? kPairHasB : 0));   // numSlots is a multiple of 64
+        float4* rec = pairQ + size_t(s >> 1) * kPairRecordWords;
+        rec[h ? 1 : 0] = make_float4(nx, ny, aN1, aN2);
+        rec[h ? 5 : 4] = make_float4(aF1, aF2, cinvF, dstVel);
+        reinterpret_cast<float2*>(rec + 3)[h] = make_float2(cinvN, dstDisp);
+        if (!h)
+        {
+            rec[2] = make_float4(p1.x, p1.y, p2.x, p2.y);   // both joints of a manifold have the same two bodies
+            pairIdx[s >> 1] = make_int2(b1, b2 | (slotJoint[s + 1] >= 0 ? kPairHasB : 0));   // numSlots is a multiple of 64
+        }
     }
     else
     {
@@ -789,12 +793,14 @@ __device__ __forceinline__ int run_phase_pairs(const SolveParams& P, int iters, 
             ++tick;
             bool wake = false;
             any |= solve_pairs<PHASE>(P, L, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre);
+            unsigned long long ticket;
+            grid_arrive(P.barrier, epoch, wake, any, ticket);
             // streams of this thread's first pair of the level that follows, fetched while the grid drains into the barrier
             const Level N = P.levels[l + 1 < P.numLevels ? l + 1 : 0];
             const int sN = N.start + 2 * tid;
             havePre = sN < N.end;
             if (havePre) load_pair<PHASE>(P, sN, true, pre);
-            BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
+            BarrierResult r = grid_wait(P.barrier, epoch, ticket);
             timeline_mark(P, tick);
             while (r.wake)
             {
@@ -862,10 +868,30 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve_pairs(SolveParams
 // flight), then the tests and the relaxations; no two manifolds of a level share a dynamic body, so
 // gathering the rows of a whole batch up front reads nothing stale.  The arithmetic and the order of
 // relaxations are those of solve_pairs, hence the same results bit for bit.
-struct PairRecord   // layout of pairQ: 8 float4 per manifold; the displacement phase needs the first three 32-byte sectors only
+struct PairRecord   // layout of pairQ: 6 float4 = 96 bytes per manifold; the displacement phase needs the first 64 bytes only
 {
-    float4 a0, a2, a3, b0, b2, b3, a1, b1;
+    float4 a0;   // joint a: {n.x, n.y, angN1, angN2}
+    float4 b0;   // joint b: the same
+    float4 m;    // {invMass1, invInertia1, invMass2, invInertia2}: shared, both joints have the same two bodies
+    float4 nd;   // {compInvMassN a, dstDisplacingVelocity a, compInvMassN b, dstDisplacingVelocity b}
+    float4 a1;   // joint a: {angF1, angF2, compInvMassF, dstVelocity}
+    float4 b1;   // joint b: the same
 };
+static_assert(sizeof(PairRecord) == kPairRecordWords * sizeof(float4), "record layout");
+
+// Records of the manifolds that pass the skip test are staged through shared memory with asynchronous copies
+// (LDGSTS): a thread issues the copies for ALL its active manifolds of a batch at once and waits once, instead
+// of paying one DRAM round trip per manifold in sequence (measured: the chain of the busiest thread, not
+// bandwidth, bounds a level pass).  Layout [manifold of the batch][float4 of the record][thread]: conflict-free.
+__device__ __forceinline__ void cp_async16(float4* smemDst, const float4* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smemDst))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 
 constexpr int kPairU = 4;   // manifolds a thread handles together (default; the 1024-threads-per-SM shape uses 2)
 
@@ -882,12 +908,13 @@ __device__ __forceinline__ void prestep_pair2(const SolveParams& P, int p)
     const bool haveB = idx.y < 0;
     float4 v1 = __ldcg(&P.vel[b1]), v2 = __ldcg(&P.vel[b2]);
     const float4 accs = __ldcs(reinterpret_cast<const float4*>(&P.accNF[2 * p]));
-    const float4* rec = P.pairQ + size_t(p) * 8;
+    const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
+    const float4 c2 = __ldcs(rec + 2);
 #pragma unroll
     for (int h = 0; h < 2; ++h)
     {
         if (h == 1 && !haveB) break;
-        const float4 c0 = __ldcs(rec + (h ? 3 : 0)), c2 = __ldcs(rec + (h ? 4 : 1)), c1 = __ldcs(rec + (h ? 7 : 6));
+        const float4 c0 = __ldcs(rec + (h ? 1 : 0)), c1 = __ldcs(rec + (h ? 5 : 4));
         const float nx = c0.x, ny = c0.y;
         const float accN = h ? accs.z : accs.x, accF = h ? accs.w : accs.y;
         v1.x += (nx * c2.x) * accN;
@@ -908,29 +935,48 @@ __device__ __forceinline__ void prestep_pair2(const SolveParams& P, int p)
     if (!(idx.y & kStaticBit)) __stcg(&P.vel[b2], v2);
 }
 
+// Which manifold of a level a thread handles as its k-th one.  Activity is clustered (a moving region of the pile is
+// a contiguous run of manifolds of a level), and a level pass takes as long as its busiest CTA: with a plain
+// "thread id + k * threads" mapping a CTA owns runs of 256 consecutive manifolds and some CTAs get three or four hot
+// runs while the average is one.  Here consecutive 32-manifold chunks go to consecutive CTAs, and a CTA's consecutive
+// chunks to its consecutive warps, so a hot run of any length is dealt evenly over all CTAs and over the warps of
+// each; a warp still reads 32 consecutive index words / records.
+__device__ __forceinline__ long long pair_of(int k)
+{
+    const long long chunk = static_cast<long long>(k * int(blockDim.x >> 5) + int(threadIdx.x >> 5)) * gridDim.x + blockIdx.x;
+    return chunk * 32 + (threadIdx.x & 31);
+}
+// true while some thread of the grid still has a k-th manifold in a level of numPairs
+__device__ __forceinline__ bool pairs_left(int k, int numPairs)
+{
+    return static_cast<long long>(k) * int(blockDim.x >> 5) * gridDim.x * 32 < numPairs;
+}
+
 // One pass over one paired level.  `pre` holds the index words of this thread's first batch when havePre
 // is set.  First passes record which manifolds were active in `activity` (bit = bitCursor + position in
 // the thread's visiting order, first 64 only) and advance bitCursor; wake passes leave both alone.
 template <int PHASE, int U>
 __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L, int it, int tick, bool firstPass, int tid, int nthreads, bool& wake,
-    unsigned& activeCount, const int2 (&pre)[U], bool havePre, unsigned& bitCursor, unsigned long long& activity, unsigned scratch)
+    unsigned& activeCount, const int2 (&pre)[U], bool havePre, unsigned& bitCursor, unsigned long long& activity, float4* stage)
 {
     float4* rows = PHASE == 0 ? P.vel : P.disp;
     unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
     const int pairBase = L.start >> 1, numPairs = (L.end - L.start) >> 1;
     bool anyProductive = false;
-    for (long long first = tid; first < numPairs; first += static_cast<long long>(U) * nthreads)
+    for (int k0 = 0; pairs_left(k0, numPairs); k0 += U)
     {
         int2 idx[U];
         float4 v1[U], v2[U];
+        int pv[U];   // global manifold index (pairBase + position in the level)
 #pragma unroll
         for (int u = 0; u < U; ++u)
         {
-            const long long p = first + static_cast<long long>(u) * nthreads;
+            const long long p = pair_of(k0 + u);
+            pv[u] = pairBase + int(p < numPairs ? p : 0);
             if (havePre)
                 idx[u] = pre[u];
             else
-                idx[u] = p < numPairs ? __ldcs(&P.pairIdx[pairBase + int(p)]) : make_int2(-1, -1);
+                idx[u] = p < numPairs ? __ldcs(&P.pairIdx[pv[u]]) : make_int2(-1, -1);
         }
         havePre = false;
 #pragma unroll
@@ -939,8 +985,7 @@ __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L
             bool valid = idx[u].x >= 0;
             if (!firstPass && valid)   // wake pass: only manifolds a static body can wake, and only those that have not run yet
             {
-                const int s = 2 * (pairBase + int(first) + u * nthreads);
-                valid = ((idx[u].x | idx[u].y) & kStaticBit) && __ldcg(&P.processed[s]) != tick;
+                valid = ((idx[u].x | idx[u].y) & kStaticBit) && __ldcg(&P.processed[2 * pv[u]]) != tick;
             }
             if (!valid) idx[u].x = -1;
             v1[u] = v2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -961,7 +1006,7 @@ __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L
         {
             const int r1 = idx[u].x, r2 = idx[u].y;
             if (r1 < 0) continue;
-            const int p = pairBase + int(first) + u * nthreads;
+            const int p = pv[u];
             const unsigned pos = unsigned(2 * p);
             last1v[u] = (r1 & kStaticBit) ? static_visible_last(&statics[r1 & kBodyMask], it, pos) : __float_as_int(v1[u].w);
             last2v[u] = (r2 & kStaticBit) ? static_visible_last(&statics[r2 & kBodyMask], it, pos) : __float_as_int(v2[u].w);
@@ -971,43 +1016,65 @@ __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L
                 idx[u].x = -1;
                 continue;
             }
+            // stage the record: [u][word][thread]
+            const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
+#pragma unroll
+            for (int f = 0; f < (PHASE == 0 ? kPairRecordWords : 4); ++f) cp_async16(stage + (u * kPairRecordWords + f) * blockDim.x, rec + f);
         }
+        // the accumulators go to registers while the copies are in flight
+        float4 accv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            accv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx[u].x < 0) continue;
+            const int s = 2 * pv[u];
+            if (PHASE == 0)
+                accv[u] = __ldcs(reinterpret_cast<const float4*>(&P.accNF[s]));
+            else
+            {
+                const float2 a = __ldcs(reinterpret_cast<const float2*>(&P.accD[s]));
+                accv[u] = make_float4(a.x, a.y, 0.f, 0.f);
+            }
+        }
+        cp_async_wait_all();
 #pragma unroll
         for (int u = 0; u < U; ++u)
         {
             const int r1 = idx[u].x, r2 = idx[u].y;
             if (r1 < 0) continue;
-            const int p = pairBase + int(first) + u * nthreads, s = 2 * p;
+            const int s = 2 * pv[u];
             const int b1 = r1 & kBodyMask, b2 = r2 & kBodyMask;
             const bool st1 = r1 & kStaticBit, st2 = r2 & kStaticBit, haveB = r2 < 0;
             const unsigned pos = unsigned(s);
             const int last1 = last1v[u], last2 = last2v[u];
 
             if (firstPass && bitCursor + u < 64u) activity |= 1ull << (bitCursor + u);
-            const float4* rec = P.pairQ + size_t(p) * 8;
-            const float4 a0 = __ldg(rec + 0), a2 = __ldg(rec + 1), a3 = __ldg(rec + 2);
-            const float4 b0 = __ldg(rec + 3), b2r = __ldg(rec + 4), b3 = __ldg(rec + 5);
+            const float4* mine = stage + u * kPairRecordWords * blockDim.x;
+            const float4 a0 = mine[0], b0 = mine[blockDim.x], a2 = mine[2 * blockDim.x], nd = mine[3 * blockDim.x];
             float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1r = a1;
+            if (PHASE == 0)
+            {
+                a1 = mine[4 * blockDim.x];
+                b1r = mine[5 * blockDim.x];
+            }
+            const float4 a3 = make_float4(0.f, 0.f, nd.x, nd.y), b3 = make_float4(0.f, 0.f, nd.z, nd.w);
             float2 accA, accB;
             if (PHASE == 0)
             {
-                a1 = __ldg(rec + 6);
-                b1r = __ldg(rec + 7);
-                const float4 acc = __ldcs(reinterpret_cast<const float4*>(&P.accNF[s]));
-                accA = make_float2(acc.x, acc.y);
-                accB = make_float2(acc.z, acc.w);
+                accA = make_float2(accv[u].x, accv[u].y);
+                accB = make_float2(accv[u].z, accv[u].w);
             }
             else
             {
-                const float2 acc = __ldcs(reinterpret_cast<const float2*>(&P.accD[s]));
-                accA = make_float2(acc.x, 0.f);
-                accB = make_float2(acc.y, 0.f);
+                accA = make_float2(accv[u].x, 0.f);
+                accB = make_float2(accv[u].y, 0.f);
             }
             activeCount += haveB ? 2u : 1u;
             float4 w1 = v1[u], w2 = v2[u];
             const bool productiveA = relax<PHASE>(a0, a1, a2, a3, accA, w1, w2, false);
             bool productiveB = false;
-            if (haveB) productiveB = relax<PHASE>(b0, b1r, b2r, b3, accB, w1, w2, false);
+            if (haveB) productiveB = relax<PHASE>(b0, b1r, a2, b3, accB, w1, w2, false);
             if (PHASE == 0)
                 __stcs(reinterpret_cast<float4*>(&P.accNF[s]), make_float4(accA.x, accA.y, accB.x, accB.y));
             else
@@ -1040,7 +1107,7 @@ __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L
 }
 
 template <int PHASE, int U>
-__device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Level* levels, unsigned scratch, int iters, int tid, int nthreads, unsigned& epoch,
+__device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Level* levels, float4* stage, int iters, int tid, int nthreads, unsigned& epoch,
     int& tick, int& wakePasses, unsigned& activeCount)
 {
     int2 pre[U];
@@ -1057,7 +1124,9 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
             const Level L = levels[l];
             ++tick;
             bool wake = false;
-            any |= solve_pairs2<PHASE, U>(P, L, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre, bitCursor, activity, scratch);
+            any |= solve_pairs2<PHASE, U>(P, L, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre, bitCursor, activity, stage);
+            unsigned long long ticket;
+            grid_arrive(P.barrier, epoch, wake, any, ticket);
             // While the grid drains into the barrier: index words of this thread's first batch of the level that
             // follows, and an L2 prefetch of the records it is expected to need (this iteration's own activity
             // bits when the next level is level 0 of the next iteration, else last iteration's).
@@ -1070,16 +1139,18 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                 {
-                    const long long pN = tid + static_cast<long long>(u) * nthreads;
+                    const long long pN = pair_of(u);
                     pre[u] = make_int2(-1, -1);
                     if (pN < numPairsN)
                     {
                         const int p = pairBaseN + int(pN);
                         pre[u] = __ldcs(&P.pairIdx[p]);
+                        // (an L2 prefetch of the records predicted active from the previous iteration's activity bits was
+                        // measured here: 10.08 us per level pass with it, 9.64 us without; PHYX_SOLVE_EXPERIMENT=5 turns it on)
                         const unsigned bit = cursorN + u;
-                        if ((bit >= 64u || ((hint >> bit) & 1ull)) && P.experiment != 3)
+                        if (P.experiment == 5 && (bit >= 64u || ((hint >> bit) & 1ull)))
                         {
-                            prefetch_l2(P.pairQ + size_t(p) * 8);
+                            prefetch_l2(P.pairQ + size_t(p) * kPairRecordWords);
                             if (PHASE == 0)
                                 prefetch_l2(&P.accNF[2 * p]);
                             else
@@ -1089,7 +1160,7 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
                 }
                 havePre = true;
             }
-            BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
+            BarrierResult r = grid_wait(P.barrier, epoch, ticket);
             timeline_mark(P, tick);
             while (r.wake)
             {
@@ -1097,7 +1168,7 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
                 unsigned dummyCursor = 0u;
                 unsigned long long dummyActivity = 0ull;
                 wake = false;
-                any |= solve_pairs2<PHASE, U>(P, L, it, tick, false, tid, nthreads, wake, activeCount, none, false, dummyCursor, dummyActivity, scratch);
+                any |= solve_pairs2<PHASE, U>(P, L, it, tick, false, tid, nthreads, wake, activeCount, none, false, dummyCursor, dummyActivity, stage);
                 ++wakePasses;
                 r = grid_barrier(P.barrier, epoch, wake, any);
             }
@@ -1122,7 +1193,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve_pairs2(SolveParam
         for (int l = threadIdx.x; l < P.numLevels; l += THREADS) s_levels[l] = P.levels[l];
     __syncthreads();
     const Level* levels = tableFits ? s_levels : P.levels;
-    const unsigned scratch = 0u;
+    extern __shared__ float4 s_stage[];   // U * kPairRecordWords * THREADS float4 (dynamic): staging of the active records
+    float4* stage = s_stage + threadIdx.x;
 
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
@@ -1138,8 +1210,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve_pairs2(SolveParam
         grid_barrier(P.barrier, epoch, false, false);
     }
 
-    const int ranImpulse = run_phase_pairs2<0, U>(P, levels, scratch, P.contactIters, tid, nthreads, epoch, tick, wakePasses, active[0]);
-    const int ranDisplacement = run_phase_pairs2<1, U>(P, levels, scratch, P.penetrationIters, tid, nthreads, epoch, tick, wakePasses, active[1]);
+    const int ranImpulse = run_phase_pairs2<0, U>(P, levels, stage, P.contactIters, tid, nthreads, epoch, tick, wakePasses, active[0]);
+    const int ranDisplacement = run_phase_pairs2<1, U>(P, levels, stage, P.penetrationIters, tid, nthreads, epoch, tick, wakePasses, active[1]);
 
     for (int phase = 0; phase < 2; ++phase)
     {
@@ -1537,7 +1609,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         const bool records = paired && pairsEnv && !strcmp(pairsEnv, "2");
         if (records)
         {
-            PHYX_TRY(c->pairQ.reserve(ns1 / 2 * 128 + 128));
+            PHYX_TRY(c->pairQ.reserve(ns1 / 2 * kPairRecordWords * sizeof(float4) + 128));
             PHYX_TRY(c->pairIdx.reserve(ns1 / 2 * sizeof(int2) + 64));
         }
         k_refresh<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
@@ -1599,9 +1671,19 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         default: sblock = 512; solveKernel = PHYX_PICK(512, 2); break;
         }
 #undef PHYX_PICK
+        // the record form stages the active records in dynamic shared memory: [U][6][threads] float4
+        size_t solveSmem = 0;
+        if (records)
+        {
+            const int shape = paired && !getenv("PHYX_SOLVE_SHAPE") ? 2562 : shapeEnv;
+            const int minBlocks = shape % 10 > 0 ? shape % 10 : 2;
+            const int batch = sblock * minBlocks >= 1024 ? 2 : kPairU;
+            solveSmem = size_t(batch) * kPairRecordWords * sblock * sizeof(float4);
+            PHYX_CUDA(cudaFuncSetAttribute(solveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(solveSmem)));
+        }
         {
             int per = 0;
-            PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, solveKernel, sblock, 0));
+            PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, solveKernel, sblock, solveSmem));
             if (per < 1)
             {
                 set_error("solve kernel does not fit on an SM");
@@ -1622,7 +1704,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         if (dual || paired || !(kernelEnv && !strcmp(kernelEnv, "pipe")))   // strict companions and paired levels are direct-kernel features
         {
             void* args[] = { &P };
-            PHYX_CUDA(cudaLaunchCooperativeKernel(solveKernel, dim3(sgrid), dim3(sblock), args, 0, c->stream));
+            PHYX_CUDA(cudaLaunchCooperativeKernel(solveKernel, dim3(sgrid), dim3(sblock), args, solveSmem, c->stream));
         }
         else
         {
@@ -1780,6 +1862,8 @@ __device__ __forceinline__ void part_signal(unsigned long long* flag, unsigned l
 template <int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_part_solve(SolveParams P, PartArgs A)
 {
+    extern __shared__ float4 s_stage[];   // kPairU * kPairRecordWords * THREADS float4 (dynamic)
+    float4* stage = s_stage + threadIdx.x;
     PartDevState* st = A.st;
     // stop[] is only written by the last thread standing of an earlier cut launch: the same answer for every thread
     if (A.phase >= 0 && __ldcg(&st->stop[A.phase])) return;
@@ -1841,17 +1925,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_part_solve(SolveParams 
         unsigned long long activity = 0ull;
         bool wake = false;
         if (A.phase == 0)
-            any |= solve_pairs2<0, kPairU>(P, L, A.it, tick, true, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+            any |= solve_pairs2<0, kPairU>(P, L, A.it, tick, true, tid, nthreads, wake, active, none, false, cursor, activity, stage);
         else
-            any |= solve_pairs2<1, kPairU>(P, L, A.it, tick, true, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+            any |= solve_pairs2<1, kPairU>(P, L, A.it, tick, true, tid, nthreads, wake, active, none, false, cursor, activity, stage);
         BarrierResult r = grid_barrier(ring, epoch, wake, any);
         while (r.wake)
         {
             wake = false;
             if (A.phase == 0)
-                any |= solve_pairs2<0, kPairU>(P, L, A.it, tick, false, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+                any |= solve_pairs2<0, kPairU>(P, L, A.it, tick, false, tid, nthreads, wake, active, none, false, cursor, activity, stage);
             else
-                any |= solve_pairs2<1, kPairU>(P, L, A.it, tick, false, tid, nthreads, wake, active, none, false, cursor, activity, 0u);
+                any |= solve_pairs2<1, kPairU>(P, L, A.it, tick, false, tid, nthreads, wake, active, none, false, cursor, activity, stage);
             ++wakePasses;
             r = grid_barrier(ring, epoch, wake, any);
         }
@@ -2047,6 +2131,7 @@ void part_destroy(phyx_b200_ctx* c)
 }
 
 constexpr int kPartThreads = 256;
+constexpr size_t kPartSmem = size_t(kPairU) * kPairRecordWords * kPartThreads * sizeof(float4);
 
 // schedule is built (part_layout): pack the rows, refresh this rank's joints, reset the per-solve state
 int part_begin(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg)
@@ -2087,7 +2172,7 @@ int part_begin(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg)
         }
     }
     const size_t ns1 = size_t(ns > 0 ? ns : 1);
-    PHYX_TRY(c->pairQ.reserve(ns1 / 2 * 128 + 128));
+    PHYX_TRY(c->pairQ.reserve(ns1 / 2 * kPairRecordWords * sizeof(float4) + 128));
     PHYX_TRY(c->pairIdx.reserve(ns1 / 2 * sizeof(int2) + 64));
     PHYX_TRY(c->accNF.reserve(ns1 * sizeof(float2)));
     PHYX_TRY(c->accD.reserve(ns1 * sizeof(float)));
@@ -2138,7 +2223,8 @@ int part_begin(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg)
     P.pairIdx = c->pairIdx.as<int2>();
     {
         int per = 0;
-        PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_part_solve<kPartThreads, 2>, kPartThreads, 0));
+        PHYX_CUDA(cudaFuncSetAttribute(k_part_solve<kPartThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPartSmem)));
+        PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_part_solve<kPartThreads, 2>, kPartThreads, kPartSmem));
         if (per < 1)
         {
             set_error("partitioned solve kernel does not fit on an SM");
@@ -2169,7 +2255,7 @@ int part_launch(phyx_b200_ctx* c, int phase, int it, int mode)
     const int grid = std::max(1, std::min(want, c->numSMs * c->solveBlocksPerSM));
     SolveParams& P = *static_cast<SolveParams*>(pt.params);
     void* args[] = { &P, &A };
-    PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_part_solve<kPartThreads, 2>, dim3(grid), dim3(kPartThreads), args, 0, c->stream));
+    PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_part_solve<kPartThreads, 2>, dim3(grid), dim3(kPartThreads), args, kPartSmem, c->stream));
     c->launches++;
     return PHYX_B200_OK;
 }
