@@ -170,3 +170,79 @@ def test_partition_errors_are_reported():
     w.stages_before_solve()
     st = c.solve_resident(schedule=capi.SCHEDULE_COLOUR)
     assert st.joints > 0
+
+
+def _run_group(scene, ranks, steps, iters=(20, 20)):
+    bodies = partition.body_records(scene)
+    ctxs = [capi.Context(0) for _ in range(ranks)]
+    worlds = [partition.ReplicatedWorld(c, bodies) for c in ctxs]
+    group = partition.LocalGroup(ctxs)
+    stats = None
+    for _ in range(steps):
+        for w in worlds:
+            w.stages_before_solve()
+        stats = group.solve(iters)
+        for c in ctxs:
+            c.integrate_position(scenes.DT)
+    out = [c.download_bodies() for c in ctxs]
+    joints = [c.download_joints() for c in ctxs]
+    group.close()
+    for c in ctxs:
+        c.close()
+    return out, joints, stats
+
+
+def test_more_ranks_than_work():
+    """8 ranks on a 55-box pyramid: several ranks own no manifold at all, some own no boundary row; the passes
+    and the exchanges must still line up (every rank sends, possibly nothing) and the replicas stay identical."""
+    bodies, joints, stats = _run_group(scenes.make("pyramid_10"), 8, 25)
+    assert stats[0].joints > 0
+    for k in range(1, 8):
+        assert_records_equal(bodies[k], bodies[0], ("pos", "velocity", "angularVelocity", "xVector"), what=f"rank {k}")
+        assert_records_equal(joints[k], joints[0], what=f"joints of rank {k}")
+        assert (stats[k].contactIterationsRun, stats[k].penetrationIterationsRun) == (stats[0].contactIterationsRun, stats[0].penetrationIterationsRun)
+
+
+def test_world_without_contacts_and_one_sided_world():
+    # free fall, no ground: no manifold ever, the partitioned solve is a no-op on every rank
+    free = np.array([[0, 100, 0, 10, 5, 0], [50, 100, 0.3, 10, 5, 0], [120, 140, 0, 10, 5, 0]], dtype=np.float32)
+    bodies, joints, stats = _run_group(free, 2, 5)
+    assert stats[0].joints == 0 and joints[0].shape[0] == 0
+    assert_records_equal(bodies[1], bodies[0], ("pos", "velocity"), what="free fall")
+    assert np.all(bodies[0]["velocity"][:, 1] < 0)
+    # all contacts on the far left, a lone falling box far right: every manifold is interior to rank 0 or touches
+    # only the ground, the cut class is empty
+    left = scenes.stack(3, 6)
+    lone = np.array([[5000, 400, 0, 10, 5, 0]], dtype=np.float32)
+    bodies, joints, stats = _run_group(np.concatenate([left, lone]), 3, 20)
+    assert stats[0].joints > 0
+    for k in (1, 2):
+        assert_records_equal(bodies[k], bodies[0], ("pos", "velocity", "angularVelocity"), what=f"rank {k}")
+
+
+def test_partitioned_solve_at_100k_keeps_replicas_identical_and_exact(oracle):
+    """configs[1] size: 100 001 bodies, 2 ranks, a few steps; last step against the oracle."""
+    bodies = partition.body_records(scenes.make("stack_100k"))
+    n = bodies.shape[0]
+    ctxs = [capi.Context(0) for _ in range(2)]
+    worlds = [partition.ReplicatedWorld(c, bodies) for c in ctxs]
+    group = partition.LocalGroup(ctxs)
+    for step in range(6):
+        for w in worlds:
+            w.stages_before_solve()
+        if step == 5:
+            b0, j0, cp = ctxs[0].download_bodies(), ctxs[0].download_joints(), ctxs[0].download_contact_points()
+        stats = group.solve()
+        if step < 5:
+            for c in ctxs:
+                c.integrate_position(scenes.DT)
+    slots, levels = ctxs[0].get_schedule()
+    _, _, cls_start = ctxs[0].partition_plan(2)
+    b = [c.download_bodies() for c in ctxs]
+    assert_records_equal(b[1], b[0], VEL_FIELDS, what="replicas")
+    ob, oj = partition.sequential_equivalent(b0, j0, slots, cls_start, 2)
+    ob, oj, ran = oracle.solve_scheduled(ob, oj, cp, slots, levels)
+    assert (stats[0].contactIterationsRun, stats[0].penetrationIterationsRun) == ran
+    assert_records_equal(ctxs[0].download_joints(), oj, ("normalImpulse", "frictionImpulse"), what="joints")
+    assert_records_equal(b[0], ob[:n], VEL_FIELDS, what="bodies")
+    group.close()
