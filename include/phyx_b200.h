@@ -110,7 +110,8 @@ typedef struct {
     int32_t contactIterationsRun, penetrationIterationsRun;  /* with the productive early-out */
     int32_t wakePasses;                        /* extra level passes run for static-body wake-ups (DESIGN.md "static bodies") */
     int32_t colourRounds;                      /* rounds the device colouring needed (0: host-built schedule) */
-    int32_t reserved_;
+    int32_t kernelForm;                        /* iteration kernel that ran: 0 joint units (k_solve), 1 manifold units streaming
+                                                  (k_solve_pairs), 2 manifold units record form (k_solve_pairs2 / partitioned) */
     int64_t activeJointIterations[2];          /* joint-iterations actually relaxed (not skipped by the lastIteration
                                                   test) in the impulse / displacement loops */
     float ms_schedule, ms_refresh, ms_iterations, ms_finish, ms_total;   /* CUDA-event times */

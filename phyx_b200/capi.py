@@ -85,7 +85,7 @@ class SolveStats(C.Structure):
         ("penetrationIterationsRun", C.c_int32),
         ("wakePasses", C.c_int32),
         ("colourRounds", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("kernelForm", C.c_int32),
         ("activeJointIterations", C.c_int64 * 2),
         ("ms_schedule", C.c_float),
         ("ms_refresh", C.c_float),

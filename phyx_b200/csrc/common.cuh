@@ -186,6 +186,8 @@ struct phyx_b200_ctx
 
     cudaEvent_t ev[8] = {};
     int solveBlocksPerSM = 0, colourBlocksPerSM = 0, colourRounds = 0;
+    int lastKernelForm = 0;
+    float lastActiveFraction = 1.0f;   // share of the impulse joint-iterations the previous solve relaxed (kernel choice, solve.cu)
 
     // ---- one world over several devices (partition.cu; SURVEY.md §8e: an island that spans devices) -----
     phyx::Partition part;

@@ -1599,14 +1599,16 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
             dual ? c->staticMulti.as<unsigned char>() : nullptr, dual ? c->rowsMulti.as<unsigned char>() : nullptr);
         c->launches++;
         int grid = (ns + kBlock - 1) / kBlock;
-        // manifold units (colour.cu): all levels are paired.  Default kernel for them: the speculative streaming
-        // form (k_solve_pairs; measured 1.71 ms against 1.77-1.83 ms for the record form on the 1 M pyramid, which
-        // moves 4.4x fewer DRAM bytes but is bound by the same per-level barrier and latency chain);
-        // PHYX_SOLVE_PAIRS=2 selects the record form with activity prediction (k_solve_pairs2), which is also what
-        // the partitioned solve runs on.
+        // manifold units (colour.cu): all levels are paired.  Two kernels, same results bit for bit: the streaming form
+        // (k_solve_pairs) fetches every manifold's streams whether or not it passes the skip test, the record form
+        // (k_solve_pairs2) fetches records of the manifolds that pass only, at the price of a longer dependent
+        // chain for those.  Measured on the 1 M pyramid: 1.65 against 1.78 ms with 38 % of the joint-iterations
+        // active, 1.64 against 1.50 ms with 27 %.  So the choice follows the activity of the previous solve of this
+        // world (the contact state changes slowly); PHYX_SOLVE_PAIRS=1 / 2 forces one form.
         const bool paired = !c->hostLevels.empty() && c->hostLevels[0].grouped_end < 0;
         static const char* pairsEnv = getenv("PHYX_SOLVE_PAIRS");
-        const bool records = paired && pairsEnv && !strcmp(pairsEnv, "2");
+        const bool records = paired && (pairsEnv ? !strcmp(pairsEnv, "2") : c->lastActiveFraction < 0.32f);
+        c->lastKernelForm = records ? 2 : paired ? 1 : 0;
         if (records)
         {
             PHYX_TRY(c->pairQ.reserve(ns1 / 2 * kPairRecordWords * sizeof(float4) + 128));
@@ -1743,6 +1745,12 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
                 if (k <= 3 * nl + 1 || k % (nl * 5) < nl) fprintf(stderr, "[timeline] tick %d (level %d): %.2f us\n", k, (k - 1) % nl, (t[k] - t[k - 1]) * 1e-3);
         }
         wakePasses = host[2];
+        {
+            long long act0 = 0;
+            memcpy(&act0, &host[4], 8);
+            const double nominal = double(c->jointCount) * double(ranI > 0 ? ranI : 1);
+            c->lastActiveFraction = nominal > 0.0 ? float(double(act0) / nominal) : 1.0f;
+        }
         if (stats)
         {
             memcpy(&stats->activeJointIterations[0], &host[4], 8);
@@ -1766,6 +1774,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         stats->penetrationIterationsRun = ranD;
         stats->wakePasses = wakePasses;
         stats->colourRounds = c->colourRounds;
+        stats->kernelForm = c->lastKernelForm;
     }
     return PHYX_B200_OK;
 }
@@ -2347,6 +2356,7 @@ int part_end(phyx_b200_ctx* c, phyx_b200_solve_stats* stats)
         stats->penetrationIterationsRun = c->jointCount ? host.ran[1] : 0;
         stats->wakePasses = host.wakePasses;
         stats->colourRounds = c->colourRounds;
+        stats->kernelForm = 2;
         stats->activeJointIterations[0] = (long long)host.active[0];
         stats->activeJointIterations[1] = (long long)host.active[1];
     }
