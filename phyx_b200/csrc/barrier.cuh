@@ -29,9 +29,10 @@ __device__ __forceinline__ void grid_arrive(unsigned long long* ring, unsigned e
         if (blockIdx.x == 0) ring[(epoch + 1u) & 3u] = 0ull;
         const unsigned long long add = 1ull | (w ? (1ull << 20) : 0ull) | (pr ? (1ull << 40) : 0ull);
         // release: the CTA's writes (ordered before this point by the __syncthreads above) become visible before
-        // the arrival; acq_rel is enough for the fence-atomic-fence pattern and cheaper than __threadfence's MEMBAR.SC
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        ticket = atomicAdd(word, add) + add;
+        // the arrival (a release atomic: MEMBAR + ATOM, without the L1 invalidation an acq_rel fence adds)
+        unsigned long long before;
+        asm volatile("atom.release.gpu.global.add.u64 %0, [%1], %2;" : "=l"(before) : "l"(word), "l"(add) : "memory");
+        ticket = before + add;
     }
 }
 
@@ -46,7 +47,9 @@ __device__ __forceinline__ BarrierResult grid_wait(unsigned long long* ring, uns
         // invalidation of the whole SM (SASS CCTL.IVALL, ~75 polls per barrier in the ncu capture of r1g)
         while ((v & 0xfffffull) != gridDim.x)
             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word) : "memory");
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        // one acquire load instead of a fence: a fence (MEMBAR) also waits for this thread's own outstanding loads,
+        // i.e. for the next level's prefetch it issued between arrive and wait
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word) : "memory");
         s_value = v;
     }
     __syncthreads();

@@ -92,6 +92,7 @@ struct ColourParams
     int* listCount;              // ring of 4 counters: listCount[r & 3] = length of the list round r reads
     unsigned long long* barrier;
     int* result;                 // [0] rounds, [1] overflow (a joint needed a colour >= 64)
+    const int* hint;             // optional: the colour a unit takes if it is free on both bodies (else first fit)
 };
 
 __device__ __forceinline__ unsigned long long colour_key(int j) { return (static_cast<unsigned long long>(mix32(unsigned(j))) << 32) | unsigned(j); }
@@ -142,6 +143,11 @@ __global__ void __launch_bounds__(kBlock) k_colour_rounds(ColourParams P)
                     {
                         unsigned long long m = (b.x >= 0 ? __ldcg(&P.used[b.x]) : 0ull) | (b.y >= 0 ? __ldcg(&P.used[b.y]) : 0ull);
                         int c = __ffsll(~m) - 1;
+                        if (P.hint)
+                        {
+                            const int h = P.hint[j];
+                            if (h >= 0 && !((m >> h) & 1ull)) c = h;
+                        }
                         if (c < 0)
                         {
                             c = kMaxColours - 1;   // keep going so the kernel terminates; the host falls back
@@ -325,7 +331,7 @@ static int colour_joints_build(phyx_b200_ctx* c, bool* staticsChanged)
         c->colourBlocksPerSM = per > 0 ? per : 1;
     }
     ColourParams P = { nj, jb, colour, claim, used, { reinterpret_cast<int*>(base + oList0), reinterpret_cast<int*>(base + oList1) },
-        reinterpret_cast<int*>(base + oListCount), barrier, result };
+        reinterpret_cast<int*>(base + oListCount), barrier, result, nullptr };
     int cgrid = std::max(1, std::min(grid, c->numSMs * c->colourBlocksPerSM));
     void* args[] = { &P };
     PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_colour_rounds, dim3(cgrid), dim3(kBlock), args, 0, c->stream));
@@ -377,14 +383,34 @@ static int colour_joints_build(phyx_b200_ctx* c, bool* staticsChanged)
 
 constexpr int kSkipUnit = kMaxColours;   // working colour of a manifold without contact points
 
+// Experimental (PHYX_COLOUR_HINTS=1): colour hint of a manifold from geometry: layer parity of the lower body and
+// the side the upper one sits on.  On a regular brick pile these four combinations never meet at a body.
+__device__ __forceinline__ int unit_hint(float4 p1, float2 s1, float4 p2, float2 s2)
+{
+    const bool static1 = p1.x == 0.0f && p1.y == 0.0f, static2 = p2.x == 0.0f && p2.y == 0.0f;
+    const bool swap = static2 ? !static1 : (!static1 && (p2.w < p1.w || (p2.w == p1.w && p2.z < p1.z)));
+    const float4 lo = swap ? p2 : p1, hi = swap ? p1 : p2;
+    const float2 slo = swap ? s2 : s1;
+    if (static1 || static2)
+    {
+        const float h = fmaxf(2.0f * (swap ? s1 : s2).y, 1e-3f);
+        const int layer = int(floorf(hi.w / h)) & 1;
+        return 2 * (1 - layer);
+    }
+    const float h = fmaxf(2.0f * slo.y, 1e-3f);
+    const int layer = int(floorf(lo.w / h)) & 1;
+    return 2 * layer + (hi.z > lo.z ? 1 : 0);
+}
+
 __global__ void __launch_bounds__(kBlock) k_unit_init(int M, const int2* __restrict__ manBody, const int* __restrict__ manCount,
-    const float4* __restrict__ params, int* __restrict__ manColour, int2* __restrict__ jb, int* __restrict__ work, unsigned long long* __restrict__ bodyUsed,
-    bool keepColours)
+    const float4* __restrict__ params, const float2* __restrict__ size, int* __restrict__ manColour, int2* __restrict__ jb, int* __restrict__ work,
+    int* __restrict__ hint, unsigned long long* __restrict__ bodyUsed, bool keepColours)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     int2 b = manBody[m];
     const float4 p1 = params[b.x], p2 = params[b.y];
+    if (hint) hint[m] = unit_hint(p1, size[b.x], p2, size[b.y]);
     if (p1.x == 0.0f && p1.y == 0.0f) b.x = -1;
     if (p2.x == 0.0f && p2.y == 0.0f) b.y = -1;
     jb[m] = b;
@@ -728,7 +754,7 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
     const size_t nb1 = size_t(nb > 0 ? nb : 1);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-    const size_t oJb = take(size_t(M) * sizeof(int2)), oWork = take(size_t(M) * sizeof(int)), oClaim = take(nb1 * 8),
+    const size_t oJb = take(size_t(M) * sizeof(int2)), oWork = take(size_t(M) * sizeof(int)), oHint = take(size_t(M) * sizeof(int)), oClaim = take(nb1 * 8),
                  oList0 = take(size_t(M) * sizeof(int)), oList1 = take(size_t(M) * sizeof(int)),
                  oCounts = take((kMaxColours + 1) * sizeof(int)), oFirst = take(kMaxColours * sizeof(int)), oHeader = take(16), oResult = take(16),
                  oBarrier = take(32), oListCount = take(16);
@@ -757,8 +783,10 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
         k_colour_body_flags<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, c->params.as<float4>(), c->bodyStatic.as<unsigned char>(), incremental, result);
         c->launches++;
     }
-    k_unit_init<<<grid, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(), c->params.as<float4>(), c->manColour.as<int>(), jb, work,
-        used, incremental);
+    static const bool useHints = getenv("PHYX_COLOUR_HINTS") && !strcmp(getenv("PHYX_COLOUR_HINTS"), "1");
+    int* hint = useHints ? reinterpret_cast<int*>(base + oHint) : nullptr;
+    k_unit_init<<<grid, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(), c->params.as<float4>(), c->size.as<float2>(),
+        c->manColour.as<int>(), jb, work, hint, used, incremental);
     c->launches++;
 
     if (c->colourBlocksPerSM == 0)
@@ -768,7 +796,7 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
         c->colourBlocksPerSM = per > 0 ? per : 1;
     }
     ColourParams P = { M, jb, work, claim, used, { reinterpret_cast<int*>(base + oList0), reinterpret_cast<int*>(base + oList1) },
-        reinterpret_cast<int*>(base + oListCount), barrier, result };
+        reinterpret_cast<int*>(base + oListCount), barrier, result, hint };
     int cgrid = std::max(1, std::min(grid, c->numSMs * c->colourBlocksPerSM));
     void* args[] = { &P };
     PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_colour_rounds, dim3(cgrid), dim3(kBlock), args, 0, c->stream));
@@ -785,13 +813,17 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
     k_unit_keys<<<grid, kBlock, 0, c->stream>>>(M, work, c->manColour.as<int>(), c->colourKeys.as<uint2>(), counts);
     c->launches++;
     PHYX_TRY(radix_pass(c, c->colourKeys.as<uint2>(), c->colourSorted.as<uint2>(), M, 0, 2 * kMaxColours));
+    // per-colour table for the placement (a colour nobody uses is an empty entry); the solve gets a compact copy
+    // without empty entries below: an empty level would still cost a grid barrier per pass
+    PHYX_TRY(c->part.binLevels.reserve(kMaxColours * sizeof(Level)));
     PHYX_TRY(c->levels.reserve(kMaxColours * sizeof(Level)));
-    k_unit_levels<<<1, 32, 0, c->stream>>>(counts, c->levels.as<Level>(), firstPos, header);
+    Level* colourTable = c->part.binLevels.as<Level>();
+    k_unit_levels<<<1, 32, 0, c->stream>>>(counts, colourTable, firstPos, header);
     c->launches++;
     const size_t maxSlots = 2 * size_t(M) + 64 * kMaxColours;
     PHYX_TRY(c->slotJoint.reserve(maxSlots * sizeof(int)));
     PHYX_CUDA(cudaMemsetAsync(c->slotJoint.ptr, 0xff, maxSlots * sizeof(int), c->stream));
-    k_unit_place<<<grid, kBlock, 0, c->stream>>>(M, c->colourSorted.as<uint2>(), c->levels.as<Level>(), firstPos, c->manCount.as<int>(),
+    k_unit_place<<<grid, kBlock, 0, c->stream>>>(M, c->colourSorted.as<uint2>(), colourTable, firstPos, c->manCount.as<int>(),
         c->contactPoints.as<float4>(), c->slotJoint.as<int>(), unsigned(kMaxColours));
     c->launches++;
     PHYX_CUDA(cudaGetLastError());
@@ -806,19 +838,21 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
         set_error("colouring needs more than %d colours", kMaxColours);
         return PHYX_B200_ERR_CAPACITY;
     }
-    c->levelCount = host.header[0];
     c->slotCount = host.header[1];
     c->colourRounds = host.result[0];
     *staticsChanged = host.result[3] != 0;
     c->colourStateValid = true;
     c->colourStateBodies = nb;
-    if (!incremental) c->coloursAtFullBuild = c->levelCount;
     int cursor = 0;
-    for (int k = 0; k < c->levelCount; ++k)
+    for (int k = 0; k < host.header[0]; ++k)
     {
-        c->hostLevels.push_back({ cursor, -1, cursor + 2 * host.counts[k] });
-        cursor = (cursor + 2 * host.counts[k] + 63) & ~63;
+        if (host.counts[k] > 0) c->hostLevels.push_back({ cursor, -1, cursor + 2 * host.counts[k] });
+        cursor = (cursor + 2 * host.counts[k] + 63) & ~63;   // as k_unit_levels: an empty colour takes no slots
     }
+    c->levelCount = int(c->hostLevels.size());
+    if (!incremental) c->coloursAtFullBuild = c->levelCount;
+    if (c->levelCount > 0)
+        PHYX_CUDA(cudaMemcpyAsync(c->levels.ptr, c->hostLevels.data(), size_t(c->levelCount) * sizeof(Level), cudaMemcpyHostToDevice, c->stream));
     c->hostSlotsStale = true;
     return PHYX_B200_OK;
 }

@@ -246,3 +246,34 @@ def test_partitioned_solve_at_100k_keeps_replicas_identical_and_exact(oracle):
     assert_records_equal(ctxs[0].download_joints(), oj, ("normalImpulse", "frictionImpulse"), what="joints")
     assert_records_equal(b[0], ob[:n], VEL_FIELDS, what="bodies")
     group.close()
+
+
+def test_partitioned_layout_runs_on_one_device_too(oracle):
+    """A partitioned context can still run the whole schedule alone (phyx_b200_solve_resident): the class-major
+    slot order is then one long level table on one device, and the result is the plain sequential sweep over it
+    (one device, one copy of every static body: no rewrite needed)."""
+    from test_gpu_hotpath import check_schedule
+
+    bodies = partition.body_records(scenes.make("pyramid_1k"))
+    ctxs = [capi.Context(0) for _ in range(2)]
+    worlds = [partition.ReplicatedWorld(c, bodies) for c in ctxs]
+    group = partition.LocalGroup(ctxs)
+    for step in range(6):
+        for w in worlds:
+            w.stages_before_solve()
+        if step < 5:
+            group.solve()
+            for c in ctxs:
+                c.integrate_position(scenes.DT)
+    c = ctxs[0]
+    b0, j0, cp = c.download_bodies(), c.download_joints(), c.download_contact_points()
+    st = c.solve_resident(schedule=capi.SCHEDULE_COLOUR)
+    slots, levels = c.get_schedule()
+    check_schedule(slots, levels, j0, b0)
+    _, _, cls_start = c.partition_plan(2)
+    assert cls_start[3] == slots.shape[0] and cls_start[2] > cls_start[1] > 0
+    ob, oj, ran = oracle.solve_scheduled(b0, j0, cp, slots, levels)
+    assert (st.contactIterationsRun, st.penetrationIterationsRun) == ran
+    assert_records_equal(c.download_joints(), oj, what="joints")
+    assert_records_equal(c.download_bodies(), ob, VEL_FIELDS, what="bodies")
+    group.close()
