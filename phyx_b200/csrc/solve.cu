@@ -69,8 +69,8 @@ struct SolveParams
     // paired levels, record form (k_solve_pairs2): one 128-byte record and one index word pair per manifold
     const float4* pairQ;
     const int2* pairIdx;
-    int experiment;                    // developer aid (PHYX_SOLVE_EXPERIMENT, timing only, results are wrong): 1 = no joint passes the skip
-                                       // test, 2 = no row gathers either, 3 = no L2 prefetch; 1 and 2 also disable the early-out
+    int experiment;                    // developer aid (PHYX_SOLVE_EXPERIMENT, record form, tools/solve_experiments.py): 1 = no joint passes the
+                                       // skip test, 2 = no row gathers either (both: wrong results, early-out disabled), 5 = L2 prefetch on
     const int* strictMap;              // strict position -> slot (or -1)
     const unsigned char* rowsMulti;    // per body row: static body with at least two units
     int numMultiStatics;

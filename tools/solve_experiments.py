@@ -1,10 +1,11 @@
-"""Developer aid (GPU box): where does a level of the paired solve kernel spend its time?
+"""Developer aid (GPU box): where does a level pass of the record-form solve kernel spend its time?
 
 Settles the bench scene, then runs the resident solve on ONE frozen state (snapshot / restore) under
-the timing-only switches of solve.cu (PHYX_SOLVE_EXPERIMENT): 0 = real kernel, 3 = without the L2
-prefetch, 4 = without the L1 touch of the active records, 1 = no joint passes the skip test (barriers + index words + row gathers), 2 = no row gathers
-either (barriers + index words).  Prints kernel ms and microseconds per level pass.
-usage: python tools/solve_experiments.py [scene] [settle]
+the timing-only switches of solve.cu (PHYX_SOLVE_EXPERIMENT; run with PHYX_SOLVE_PAIRS=2 so that the record
+form is the kernel): 0 = real kernel, 5 = with the L2 prefetch of the records predicted active, 1 = no joint
+passes the skip test (barriers + index words + row gathers), 2 = no row gathers either (barriers + index
+words).  1 and 2 compute wrong results by design.  Prints kernel ms and microseconds per level pass.
+usage: PHYX_SOLVE_PAIRS=2 python tools/solve_experiments.py [scene] [settle]
 """
 import os
 import sys
@@ -28,7 +29,7 @@ def main():
     ctx.pack_manifolds()
     ctx.refresh_contact_joints()
     ctx.snapshot_bodies()
-    for exp in (0, 0, 4, 3, 1, 2, 0):
+    for exp in (0, 0, 5, 1, 2, 0):
         os.environ["PHYX_SOLVE_EXPERIMENT"] = str(exp)
         ctx.restore_bodies()
         st = ctx.solve_resident(iters=(20, 20), schedule=capi.SCHEDULE_COLOUR)
