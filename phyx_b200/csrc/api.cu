@@ -4,6 +4,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 
 static_assert(sizeof(phyx_rigid_body) == 128, "RigidBody must keep the reference layout (128 B)");
@@ -29,8 +30,8 @@ void set_error(const char* fmt, ...)
 // Device allocations made so far and the host time they took (phyx_b200_alloc_stats).  cudaMalloc / cudaFree are
 // driver round trips that synchronise the device; on shared hosts a single one was seen to take 0.3 s, so buffers
 // grow with generous headroom (request + 25 %, at least 2x the old size and 1 MiB) and a steady-state step makes none.
-static double g_allocMs = 0.0;
-static long long g_allocCount = 0;
+static std::atomic<long long> g_allocNs{ 0 };   // contexts may live on different host threads
+static std::atomic<long long> g_allocCount{ 0 };
 
 static size_t grow_to(size_t bytes, size_t cap)
 {
@@ -45,7 +46,7 @@ struct AllocTimer
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     ~AllocTimer()
     {
-        g_allocMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        g_allocNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         g_allocCount++;
     }
 };
@@ -199,8 +200,8 @@ int64_t phyx_b200_launch_count(const phyx_b200_ctx* c) { return c ? c->launches 
 
 void phyx_b200_alloc_stats(int64_t* count, double* hostMs)
 {
-    if (count) *count = g_allocCount;
-    if (hostMs) *hostMs = g_allocMs;
+    if (count) *count = g_allocCount.load();
+    if (hostMs) *hostMs = double(g_allocNs.load()) * 1e-6;
 }
 void* phyx_b200_stream(const phyx_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
