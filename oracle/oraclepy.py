@@ -41,6 +41,20 @@ def lib():
     l.pxo_prepare_indices.restype = i32
     l.pxo_solve_joints.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, vp, vp]
     l.pxo_solve_scheduled.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, vp]
+    l.pxo_rank_create.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32]
+    l.pxo_rank_create.restype = vp
+    l.pxo_rank_destroy.argtypes = [vp]
+    l.pxo_rank_destroy.restype = None
+    l.pxo_rank_pass.argtypes = [vp, i32, i32, i32]
+    l.pxo_rank_pass.restype = i32
+    for name in ("pxo_rank_get_rows", "pxo_rank_set_rows"):
+        getattr(l, name).argtypes = [vp, i32, vp, i32, vp]
+        getattr(l, name).restype = None
+    for name in ("pxo_rank_get_acc", "pxo_rank_set_acc"):
+        getattr(l, name).argtypes = [vp, vp, i32, vp]
+        getattr(l, name).restype = None
+    l.pxo_rank_finish.argtypes = [vp, vp, vp]
+    l.pxo_rank_finish.restype = None
     _LIB = l
     return l
 
@@ -119,3 +133,52 @@ def solve_scheduled(bodies, joints, contact_points, slots, levels, iters=(20, 20
     ran = np.zeros(2, dtype=np.int32)
     lib().pxo_solve_scheduled(_p(b), b.shape[0], _p(j), j.shape[0], _p(cp), _p(s), _p(lv), lv.shape[0], iters[0], iters[1], _p(ran))
     return b, j, (int(ran[0]), int(ran[1]))
+
+
+class Rank:
+    """One rank of the partitioned solve, executed literally on the CPU (phyx_oracle.c pxo_rank_*): own copy of the
+    rows and accumulators, interior passes, boundary rows in and out, cut passes."""
+
+    def __init__(self, bodies, joints, contact_points, slots, levels, level_class, rank, ranks):
+        self.b = np.ascontiguousarray(bodies, dtype=T.RIGID_BODY)
+        self.j = np.ascontiguousarray(joints, dtype=T.CONTACT_JOINT)
+        cp = np.ascontiguousarray(contact_points, dtype=T.CONTACT_POINT)
+        s = np.ascontiguousarray(slots, dtype=np.int32)
+        lv = np.ascontiguousarray(levels, dtype=LEVEL)
+        lc = np.ascontiguousarray(level_class, dtype=np.int32)
+        self.h = lib().pxo_rank_create(_p(self.b), self.b.shape[0], _p(self.j), self.j.shape[0], _p(cp), _p(s), s.shape[0], _p(lv), _p(lc), lv.shape[0], rank, ranks)
+
+    def run(self, phase, it, cut):
+        return bool(lib().pxo_rank_pass(self.h, phase, it, 1 if cut else 0))
+
+    def get_rows(self, phase, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        out = np.zeros((ids.shape[0], 4), dtype=np.float32)
+        lib().pxo_rank_get_rows(self.h, phase, _p(ids), ids.shape[0], _p(out))
+        return out
+
+    def set_rows(self, phase, ids, rows):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        lib().pxo_rank_set_rows(self.h, phase, _p(ids), ids.shape[0], _p(rows))
+
+    def get_acc(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        out = np.zeros((ids.shape[0], 2), dtype=np.float32)
+        lib().pxo_rank_get_acc(self.h, _p(ids), ids.shape[0], _p(out))
+        return out
+
+    def set_acc(self, ids, acc):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        acc = np.ascontiguousarray(acc, dtype=np.float32)
+        lib().pxo_rank_set_acc(self.h, _p(ids), ids.shape[0], _p(acc))
+
+    def finish(self):
+        b, j = self.b.copy(), self.j.copy()
+        lib().pxo_rank_finish(self.h, _p(b), _p(j))
+        return b, j
+
+    def close(self):
+        if self.h:
+            lib().pxo_rank_destroy(self.h)
+            self.h = None

@@ -541,3 +541,119 @@ void pxo_solve_joints(pxo_body* bodies, int nb, pxo_joint* joints, int nj, const
     if (joint_index_out) memcpy(joint_index_out, order, (size_t)nj * sizeof(int));
     free(levels); free(slots); free(order);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* One rank of the PARTITIONED solve (one world over several devices), executed
+ * literally on the CPU so that the multi-rank protocol itself can be tested without a GPU: every
+ * rank holds its own copy of all body rows and accumulators, relaxes the levels of its own class
+ * ("interior"), receives the other ranks' boundary rows, and relaxes the levels of the cut class on
+ * top of them.  The arithmetic is the functions above; what is restated here is the order of
+ * operations of solve.cu's k_part_solve and its drivers.  level_class[l] = owning rank of level l,
+ * `ranks` for a cut level. */
+struct pxo_rank
+{
+    int nb, nj, nlevels, rank, ranks;
+    solve_params* par;
+    solve_body* rows[2];    /* impulse / displacement rows, this rank's copy */
+    packed_joint* P;        /* this rank's copy of the packed joints (accumulators) */
+    int* slots;
+    pxo_level* levels;
+    int* level_class;
+    pxo_level* scratch;
+};
+
+pxo_rank* pxo_rank_create(const pxo_body* bodies, int nb, const pxo_joint* joints, int nj, const pxo_contact_point* cps,
+    const int* slots, int nslots, const pxo_level* levels, const int* level_class, int nlevels, int rank, int ranks)
+{
+    pxo_rank* r = (pxo_rank*)calloc(1, sizeof(pxo_rank));
+    size_t nbs = (size_t)(nb > 0 ? nb : 1), njs = (size_t)(nj > 0 ? nj : 1), nls = (size_t)(nlevels > 0 ? nlevels : 1);
+    r->nb = nb; r->nj = nj; r->nlevels = nlevels; r->rank = rank; r->ranks = ranks;
+    r->par = (solve_params*)malloc(nbs * sizeof(solve_params));
+    r->rows[0] = (solve_body*)malloc(nbs * sizeof(solve_body));
+    r->rows[1] = (solve_body*)malloc(nbs * sizeof(solve_body));
+    r->P = (packed_joint*)malloc(njs * sizeof(packed_joint));
+    r->slots = (int*)malloc((size_t)(nslots > 0 ? nslots : 1) * sizeof(int));
+    r->levels = (pxo_level*)malloc(nls * sizeof(pxo_level));
+    r->scratch = (pxo_level*)malloc(nls * sizeof(pxo_level));
+    r->level_class = (int*)malloc(nls * sizeof(int));
+    memcpy(r->slots, slots, (size_t)nslots * sizeof(int));
+    memcpy(r->levels, levels, (size_t)nlevels * sizeof(pxo_level));
+    memcpy(r->level_class, level_class, (size_t)nlevels * sizeof(int));
+    for (int i = 0; i < nb; ++i)     /* PrepareBodies */
+    {
+        r->par[i].invMass = bodies[i].invMass; r->par[i].invInertia = bodies[i].invInertia;
+        r->par[i].px = bodies[i].pos.x; r->par[i].py = bodies[i].pos.y;
+        r->rows[0][i].vx = bodies[i].velocity.x; r->rows[0][i].vy = bodies[i].velocity.y; r->rows[0][i].w = bodies[i].angularVelocity;
+        r->rows[0][i].last = -1;
+        r->rows[1][i].vx = bodies[i].displacingVelocity.x; r->rows[1][i].vy = bodies[i].displacingVelocity.y;
+        r->rows[1][i].w = bodies[i].displacingAngularVelocity; r->rows[1][i].last = -1;
+    }
+    for (int i = 0; i < nj; ++i)     /* PrepareJoints copy + RefreshJoints */
+    {
+        r->P[i].b1 = joints[i].body1Index; r->P[i].b2 = joints[i].body2Index; r->P[i].cp = joints[i].contactPointIndex;
+        r->P[i].accN = joints[i].normalImpulse; r->P[i].accF = joints[i].frictionImpulse;
+        refresh_joint(&r->P[i], r->rows[0], r->par, cps);
+    }
+    return r;
+}
+
+void pxo_rank_destroy(pxo_rank* r)
+{
+    if (!r) return;
+    free(r->par); free(r->rows[0]); free(r->rows[1]); free(r->P); free(r->slots); free(r->levels); free(r->scratch); free(r->level_class);
+    free(r);
+}
+
+/* One launch of k_part_solve: phase -1 = warm start, 0 = impulse iteration `it`, 1 = displacement iteration `it`;
+ * cut = 0: the levels of this rank's own class, cut = 1: the levels of the cut class.  Returns any-productive. */
+int pxo_rank_pass(pxo_rank* r, int phase, int it, int cut)
+{
+    const int want = cut ? r->ranks : r->rank;
+    int n = 0;
+    for (int l = 0; l < r->nlevels; ++l)
+        if (r->level_class[l] == want) r->scratch[n++] = r->levels[l];
+    if (phase < 0)
+    {
+        for (int l = 0; l < n; ++l)
+            for (int k = r->scratch[l].start; k < r->scratch[l].end; ++k)
+                if (r->slots[k] >= 0) prestep_joint(&r->P[r->slots[k]], r->rows[0]);
+        return 0;
+    }
+    return run_iteration(r->P, r->slots, r->scratch, n, r->rows[phase], phase, it);
+}
+
+/* body rows {vx, vy, w, lastIteration} as 4 x 32 bit, the unit of the boundary exchange */
+void pxo_rank_get_rows(const pxo_rank* r, int phase, const int* ids, int n, float* out4)
+{
+    const solve_body* rows = r->rows[phase == 1 ? 1 : 0];
+    for (int i = 0; i < n; ++i) memcpy(out4 + 4 * (size_t)i, &rows[ids[i]], sizeof(solve_body));
+}
+
+void pxo_rank_set_rows(pxo_rank* r, int phase, const int* ids, int n, const float* in4)
+{
+    solve_body* rows = r->rows[phase == 1 ? 1 : 0];
+    for (int i = 0; i < n; ++i) memcpy(&rows[ids[i]], in4 + 4 * (size_t)i, sizeof(solve_body));
+}
+
+/* accumulated impulses {normal, friction} of joints, the second part of the end-of-solve exchange */
+void pxo_rank_get_acc(const pxo_rank* r, const int* ids, int n, float* out2)
+{
+    for (int i = 0; i < n; ++i) { out2[2 * (size_t)i] = r->P[ids[i]].accN; out2[2 * (size_t)i + 1] = r->P[ids[i]].accF; }
+}
+
+void pxo_rank_set_acc(pxo_rank* r, const int* ids, int n, const float* in2)
+{
+    for (int i = 0; i < n; ++i) { r->P[ids[i]].accN = in2[2 * (size_t)i]; r->P[ids[i]].accF = in2[2 * (size_t)i + 1]; }
+}
+
+/* FinishJoints / FinishBodies from this rank's copy (after the end-of-solve exchange it is the whole result) */
+void pxo_rank_finish(const pxo_rank* r, pxo_body* bodies, pxo_joint* joints)
+{
+    for (int i = 0; i < r->nj; ++i) { joints[i].normalImpulse = r->P[i].accN; joints[i].frictionImpulse = r->P[i].accF; }
+    for (int i = 0; i < r->nb; ++i)
+    {
+        bodies[i].velocity.x = r->rows[0][i].vx; bodies[i].velocity.y = r->rows[0][i].vy; bodies[i].angularVelocity = r->rows[0][i].w;
+        bodies[i].displacingVelocity.x = r->rows[1][i].vx; bodies[i].displacingVelocity.y = r->rows[1][i].vy;
+        bodies[i].displacingAngularVelocity = r->rows[1][i].w;
+    }
+}
