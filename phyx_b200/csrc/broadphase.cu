@@ -189,60 +189,78 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numIte
 {
     const int lane = threadIdx.x & 31;
     const int warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int numItems = *numItemsPtr;
     unsigned long long localTests = 0, localHits = 0;
-    for (int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < numItems; it += warpsPerGrid)
+    // Warp w owns the items w, w + W, w + 2W, ... (W warps in the grid; neighbouring items, e.g. the thousand
+    // chunks of the ground body's scan, go to different warps).  Almost all of them need no work here (the count
+    // pass leaves most tiles to the tiled kernel, the emit pass only visits items with output), so the 32 lanes
+    // look at 32 of the warp's items at once and the warp then walks the few that remain.
+    for (long long first = warp; first < numItems; first += 32ll * warpsPerGrid)
     {
-        if (EMIT)
+        const long long mine = first + static_cast<long long>(lane) * warpsPerGrid;
+        bool need = false;
+        if (mine < numItems)
         {
-            // the count pass already knows which items produce output: skip the rest (with the cache
-            // filter almost every item of a settled scene is empty)
-            const int next = (it + 1 < numItems) ? itemOffset[it + 1] : *totalOutPtr;
-            if (next == itemOffset[it]) continue;
-        }
-        int2 item = items[it];
-        int i = item.x;
-        if (!EMIT && tileLong && !tileLong[i / kTile]) continue;   // counted by the tiled kernel
-        int j0 = i + 1 + item.y * kChunk;
-        int j1 = min(j0 + kChunk, end[i]);
-        float2 yi = entryY[i];
-        unsigned bi = (EMIT || FILTER) ? entryIndex[i] : 0u;
-        int out = EMIT ? itemOffset[it] : 0;
-        int count = 0;
-        for (int jb = j0; jb < j1; jb += 32)
-        {
-            int j = jb + lane;
-            bool hit = false;
-            unsigned bj = 0;
-            if (j < j1)
-            {
-                float2 yj = entryY[j];
-                hit = fabsf(yj.x - yi.x) <= yi.y + yj.y;   // Collider.cpp:309
-            }
-            if (FILTER)
-            {
-                if (!EMIT) localHits += __popc(__ballot_sync(0xffffffffu, hit));
-                if (hit)
-                {
-                    bj = entryIndex[j];
-                    hit = !pair_contains(table, tableMask, pair_key(bi, bj));
-                }
-            }
-            else if (EMIT && hit)
-                bj = entryIndex[j];
-            unsigned m = __ballot_sync(0xffffffffu, hit);
             if (EMIT)
             {
-                if (hit) pairs[out + __popc(m & ((1u << lane) - 1u))] = make_int2(int(bi), int(bj));
-                out += __popc(m);
+                // the count pass already knows which items produce output (with the cache filter almost every
+                // item of a settled scene is empty)
+                const int next = (mine + 1 < numItems) ? itemOffset[mine + 1] : *totalOutPtr;
+                need = next != itemOffset[mine];
             }
             else
-                count += __popc(m);
+                need = !(tileLong && !tileLong[items[mine].x / kTile]);   // else: counted by the tiled kernel
         }
-        if (!EMIT && lane == 0)
+        unsigned todo = __ballot_sync(0xffffffffu, need);
+        while (todo)
         {
-            itemCount[it] = count;
-            localTests += (unsigned long long)(j1 - j0);
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int it = int(first + static_cast<long long>(src) * warpsPerGrid);
+            int2 item = items[it];
+            int i = item.x;
+            int j0 = i + 1 + item.y * kChunk;
+            int j1 = min(j0 + kChunk, end[i]);
+            float2 yi = entryY[i];
+            unsigned bi = (EMIT || FILTER) ? entryIndex[i] : 0u;
+            int out = EMIT ? itemOffset[it] : 0;
+            int count = 0;
+            for (int jb = j0; jb < j1; jb += 32)
+            {
+                int j = jb + lane;
+                bool hit = false;
+                unsigned bj = 0;
+                if (j < j1)
+                {
+                    float2 yj = entryY[j];
+                    hit = fabsf(yj.x - yi.x) <= yi.y + yj.y;   // Collider.cpp:309
+                }
+                if (FILTER)
+                {
+                    if (!EMIT) localHits += __popc(__ballot_sync(0xffffffffu, hit));
+                    if (hit)
+                    {
+                        bj = entryIndex[j];
+                        hit = !pair_contains(table, tableMask, pair_key(bi, bj));
+                    }
+                }
+                else if (EMIT && hit)
+                    bj = entryIndex[j];
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (EMIT)
+                {
+                    if (hit) pairs[out + __popc(m & ((1u << lane) - 1u))] = make_int2(int(bi), int(bj));
+                    out += __popc(m);
+                }
+                else
+                    count += __popc(m);
+            }
+            if (!EMIT && lane == 0)
+            {
+                itemCount[it] = count;
+                localTests += (unsigned long long)(j1 - j0);
+            }
         }
     }
     if (!EMIT && lane == 0)
