@@ -118,3 +118,40 @@ def test_ipc_handshake_over_gloo(tmp_path):
         assert p.exitcode == 0
     for r in range(2):
         assert int(np.load(out + f".{r}.npy")[0]) == 1
+
+
+def test_plan_model_properties_on_random_contact_graphs():
+    """Whatever the contact graph: cuts are monotone and cover all rows, an interior manifold's dynamic rows lie inside
+    its rank's range, a cut manifold's rows lie in two different ranges, the boundary is exactly the rows of the cut
+    manifolds, and no rank is home to more than its share (+ the manifolds of one row) of the manifolds."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(2, 8), st.integers(1, 300), st.integers(0, 900), st.integers(0, 2**31 - 1))
+    def check(ranks, nb, m, seed):
+        rng = np.random.default_rng(seed)
+        r1 = rng.integers(-1, nb, m)
+        near = np.clip(r1 + rng.integers(-3, 4, m), -1, nb - 1)            # contacts are local in sorted-x order
+        r2 = np.where(rng.random(m) < 0.8, near, rng.integers(-1, nb, m))
+        cuts, cls, boundary = partition.plan_model_n(r1, r2, ranks, nb)
+        assert cuts[0] == 0 and cuts[ranks] == nb and np.all(np.diff(cuts) >= 0)
+        rank_of = lambda r: np.searchsorted(cuts[1:ranks], r, side="right")
+        want_boundary = set()
+        for k in range(m):
+            rows = [int(r) for r in (r1[k], r2[k]) if r >= 0]
+            if cls[k] < ranks:
+                assert all(rank_of(r) == cls[k] for r in rows) or not rows
+            else:
+                assert len(rows) == 2 and rank_of(rows[0]) != rank_of(rows[1])
+                want_boundary.update(rows)
+        assert set(boundary.tolist()) == want_boundary
+        home = np.where(r1 < 0, r2, np.where(r2 < 0, r1, np.minimum(r1, r2)))
+        home = home[home >= 0]
+        if home.size:
+            per_row = np.bincount(home, minlength=nb).max()
+            share = -(-home.size // ranks)
+            for q in range(ranks):
+                assert ((home >= cuts[q]) & (home < cuts[q + 1])).sum() <= share + per_row
+
+    check()
