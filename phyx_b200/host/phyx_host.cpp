@@ -72,6 +72,7 @@ void Device::ensure()
 void Device::upload(RigidBody* bodies, int count)
 {
     ensure();
+    if (hostStale && resident && residentCount == count) download(bodies, count);   // never push a stale host copy over newer device state
     // keep World::bodies page-locked (it is copied both ways every Update); re-pin when it was reallocated
     if (pinBodies && (bodies != pinnedPtr || size_t(count) * sizeof(RigidBody) > pinnedBytes))
     {
@@ -92,6 +93,7 @@ void Device::upload(RigidBody* bodies, int count)
 void Device::download(RigidBody* bodies, int count)
 {
     PHYX_CALL(phyx_b200_download_bodies(ctx, reinterpret_cast<phyx_rigid_body*>(bodies), count));
+    hostStale = false;
 }
 
 Device::~Device()
@@ -219,18 +221,37 @@ World::~World() {}
 
 RigidBody* World::AddBody(Coords2f coords, Vector2f size)
 {
+    SyncBodies();
     RigidBody fresh(coords, size, 1e-5f);
     fresh.index = bodies.size;
     bodies.push_back(fresh);
     device.resident = false;
+    device.hostEdited = true;
     return &bodies.data[bodies.size - 1];
+}
+
+void World::SyncBodies()
+{
+    if (device.hostStale && device.ctx && device.resident && device.residentCount == int(bodies.size)) device.download(bodies.data, bodies.size);
+    device.hostStale = false;
+}
+
+RigidBody* World::EditBodies()
+{
+    SyncBodies();
+    device.hostEdited = true;
+    return bodies.data;
 }
 
 void World::Update(WorkQueue& queue, float dt, const Configuration& configuration)
 {
     collisionTime = mergeTime = solveTime = 0;
     device.followReset(collider, solver);
-    device.upload(bodies.data, bodies.size);
+    // the reference's semantics: World::bodies is the source of truth at entry.  With the opt-in lazyBodies contract
+    // it only is when the caller said so.
+    if (!device.lazyBodies || device.hostEdited || !device.resident || device.residentCount != int(bodies.size))
+        device.upload(bodies.data, bodies.size);
+    device.hostEdited = false;
     device.inUpdate = true;
 
     IntegrateVelocity(queue, dt);
@@ -249,7 +270,10 @@ void World::Update(WorkQueue& queue, float dt, const Configuration& configuratio
     device.inUpdate = false;
     {
         StageTimer t(&device.syncMs);
-        device.download(bodies.data, bodies.size);
+        if (device.lazyBodies)
+            device.hostStale = true;
+        else
+            device.download(bodies.data, bodies.size);
         device.mirror(collider, solver, collider.mirrorContents);
     }
 }

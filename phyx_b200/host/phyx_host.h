@@ -341,6 +341,13 @@ struct Device
     void* pinnedPtr = nullptr;
     size_t pinnedBytes = 0;
     int mirroredManifolds = 0, mirroredJoints = 0;   // sizes last written into the host mirrors
+    // Opt-in contract for World::bodies.  Off (default, the reference's semantics): the host array is
+    // the source of truth at every Update entry and current at its exit: 2 x 128 B per body over PCIe per Update.
+    // On: Update uploads only when the host copy was declared edited (World::EditBodies, AddBody) and never
+    // downloads; World::SyncBodies brings World::bodies up to date when the caller wants to look at it.
+    bool lazyBodies = false;
+    bool hostEdited = true;    // the host copy has changes the device has not seen
+    bool hostStale = false;    // the device is ahead of the host copy
     phyx_b200_solve_stats lastSolve = {};
     phyx_b200_broadphase_stats lastBroadphase = {};
 
@@ -434,6 +441,10 @@ struct World
     NOINLINE void IntegrateVelocity(WorkQueue& queue, float dt);
     NOINLINE void IntegratePosition(WorkQueue& queue, float dt);
     NOINLINE void RefreshContactJoints();
+
+    // --- additions (not in the reference), only meaningful with device.lazyBodies ---
+    RigidBody* EditBodies();   // call BEFORE changing World::bodies between Updates: syncs the host copy, marks it edited
+    void SyncBodies();         // bring World::bodies up to date with the device
 
     float collisionTime;
     float mergeTime;

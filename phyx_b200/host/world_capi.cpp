@@ -93,14 +93,19 @@ API int phyxw_broadphase_count(void* h) { return static_cast<Handle*>(h)->world.
 API void phyxw_get_bodies(void* h, void* out)
 {
     World& w = static_cast<Handle*>(h)->world;
+    w.SyncBodies();
     memcpy(out, w.bodies.data, size_t(w.bodies.size) * sizeof(RigidBody));
 }
 API void phyxw_set_bodies(void* h, const void* in, int count)
 {
     World& w = static_cast<Handle*>(h)->world;
     w.bodies.resize(count);
-    memcpy(w.bodies.data, in, size_t(count) * sizeof(RigidBody));
+    memcpy(w.bodies.data, in, size_t(count) * sizeof(RigidBody));   // the whole array is replaced: nothing to sync first
+    w.device.hostStale = false;
+    w.device.hostEdited = true;
 }
+API void phyxw_set_lazy_bodies(void* h, int on) { static_cast<Handle*>(h)->world.device.lazyBodies = on != 0; }
+API void phyxw_sync_bodies(void* h) { static_cast<Handle*>(h)->world.SyncBodies(); }
 API void phyxw_get_joints(void* h, void* out)
 {
     Solver& s = static_cast<Handle*>(h)->world.solver;

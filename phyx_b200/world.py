@@ -48,6 +48,8 @@ def load():
     l.phyxw_set_bodies.argtypes = [vp, vp, i32]
     l.phyxw_reset_stage_ms.argtypes = [vp]
     l.phyxw_set_mirror_contents.argtypes = [vp, i32]
+    l.phyxw_set_lazy_bodies.argtypes = [vp, i32]
+    l.phyxw_sync_bodies.argtypes = [vp]
     l.phyxw_get_sync_ms.argtypes = [vp]
     l.phyxw_get_sync_ms.restype = C.c_double
     l.phyxw_reset_world.argtypes = [vp]
@@ -62,12 +64,15 @@ def _p(a):
 
 
 class World:
-    def __init__(self, scene=None, device=0, gravity=-200.0, solve_flags=0, mirror_contents=True):
+    def __init__(self, scene=None, device=0, gravity=-200.0, solve_flags=0, mirror_contents=True, lazy_bodies=False):
+        """lazy_bodies: the opt-in World::bodies contract of the host mirror (upload only what set_bodies / AddBody
+        changed, download only when bodies() is read); default off = the reference's semantics."""
         self.l = load()
         self.h = self.l.phyxw_create(device)
         self.l.phyxw_set_gravity(self.h, gravity)
         self.l.phyxw_set_solve_flags(self.h, solve_flags)
         self.l.phyxw_set_mirror_contents(self.h, int(mirror_contents))
+        self.l.phyxw_set_lazy_bodies(self.h, int(lazy_bodies))
         if scene is not None:
             self.add_scene(scene)
 

@@ -142,3 +142,24 @@ def test_full_pipeline_at_1m_matches_reference_for_three_steps(ref):
     assert_records_equal(wb, rb, STATE, what="bodies")
     ctx = w.context()
     assert_records_equal(ctx.download_joints(), r.joints(), what="joints")
+
+
+def test_lazy_bodies_contract_gives_the_same_trajectory():
+    """The host mirror's opt-in World::bodies contract (upload only declared edits, download only on demand) must not
+    change a single bit of the simulation, including an edit made between two Updates, and must stop moving the body
+    array over PCIe on every Update."""
+    sc = scenes.make("pyramid_1k")
+    a, b = world.World(sc), world.World(sc, lazy_bodies=True)
+    for step in range(30):
+        if step == 10:
+            for w in (a, b):
+                bodies = w.bodies()
+                bodies["acceleration"][5] = (3000.0, 500.0)
+                w.set_bodies(bodies)
+        if step == 20:
+            assert_records_equal(b.bodies(), a.bodies(), STATE, what="bodies at step 20")   # a read in the middle syncs
+        a.step(solve=world.SOLVE_B200)
+        b.step(solve=world.SOLVE_B200)
+    assert_records_equal(b.bodies(), a.bodies(), STATE, what="bodies")
+    assert_records_equal(b.joints(), a.joints(), what="joints")
+    assert a.bodies()["velocity"][5][0] != 0
