@@ -111,7 +111,8 @@ typedef struct {
     int32_t wakePasses;                        /* extra level passes run for static-body wake-ups (DESIGN.md "static bodies") */
     int32_t colourRounds;                      /* rounds the device colouring needed (0: host-built schedule) */
     int32_t kernelForm;                        /* iteration kernel that ran: 0 joint units (k_solve), 1 manifold units streaming
-                                                  (k_solve_pairs), 2 manifold units record form (k_solve_pairs2 / partitioned) */
+                                                  (k_solve_pairs), 2 manifold units record form (k_solve_pairs2 / partitioned),
+                                                  3 strip-local (k_solve_strips, the default of the resident pipeline) */
     int64_t activeJointIterations[2];          /* joint-iterations actually relaxed (not skipped by the lastIteration
                                                   test) in the impulse / displacement loops */
     float ms_schedule, ms_refresh, ms_iterations, ms_finish, ms_total;   /* CUDA-event times */
@@ -182,6 +183,25 @@ PHYX_B200_API int phyx_b200_solve_joints(phyx_b200_ctx* ctx, phyx_contact_joint*
  * end} (same meaning as oracle/phyx_oracle.h).  Pass NULL to query sizes. */
 PHYX_B200_API int phyx_b200_get_schedule(phyx_b200_ctx* ctx, int32_t* slots, int32_t slotCapacity,
     int32_t* levels3, int32_t levelCapacity, int32_t* slotCount, int32_t* levelCount);
+
+/* Tuning of Solver::SolveJoints on the resident joint cache (the reference's counterpart is the choice of SIMD width and
+ * island mode in Configuration, src/Configuration.h:3-23).  kernelForm: 0 = choose (strip-local whenever its layout is
+ * usable, else streaming / record form by the previous step's activity), 1 / 2 = force the streaming / record form on the
+ * colour-major layout, 3 = require the strip-local form (the solve fails with PHYX_B200_ERR_STATE if the layout is
+ * rejected).  strips: 0 = choose, -1 = never, n = cut the solver rows into n strips (<= number of SMs).  All forms
+ * relax the same joints; 1 and 2 give identical results, 3 uses the slot order phyx_b200_get_schedule reports. */
+PHYX_B200_API int phyx_b200_solve_tuning(phyx_b200_ctx* ctx, int kernelForm, int strips);
+/* The strip layout of the last solve: *strips = S (0: the last solve did not use strips), cuts[S+1] = row cuts,
+ * classSlotStart[2S+1] = first slot of each class (class k < S: interior of strip k, class S+k: cut set between strips
+ * k and k+1), info[8] = {usable, reject mask, rows of the largest strip, rows of the largest cut set, largest bin,
+ * static bodies, colours, cut manifolds}.  capacity = entries available in cuts / classSlotStart; any pointer may be NULL. */
+PHYX_B200_API int phyx_b200_strip_plan(phyx_b200_ctx* ctx, int32_t* strips, int32_t* cuts, int32_t* classSlotStart, int32_t capacity, int32_t* info);
+
+/* Developer aid (no reference counterpart; the reference instruments its solve with microprofile scopes, Solver.cpp:132):
+ * time stamps of the strip-local kernel.  passes >= 0: the following solves record, per CTA and pass (warm start = 0),
+ * 8 words of %globaltimer: [0] pass start, [1] interior done, [2] neighbour's rows arrived, [3] cut set done, [4] pass end.
+ * out != NULL: copy the stamps of the last solve ([strips][passes][8] words; *strips = 0 if none were recorded). */
+PHYX_B200_API int phyx_b200_strip_trace(phyx_b200_ctx* ctx, int passes, uint64_t* out, int64_t capacity, int32_t* strips);
 
 /* ---- resident collider stages: a whole World::Update without leaving HBM ------------------------ */
 /* The manifold cache (Collider::manifolds / contactPoints / manifoldMap, Collider.h:58-61) and the joint

@@ -58,6 +58,9 @@ EXPORTS = (
     "phyx_b200_download_contact_points",
     "phyx_b200_download_joints",
     "phyx_b200_upload_collider",
+    "phyx_b200_solve_tuning",
+    "phyx_b200_strip_plan",
+    "phyx_b200_strip_trace",
     "phyx_b200_partition_create",
     "phyx_b200_partition_attach",
     "phyx_b200_partition_destroy",
@@ -161,6 +164,9 @@ def load():
     l.phyx_b200_download_contact_points.argtypes = [vp, vp, i32]
     l.phyx_b200_download_joints.argtypes = [vp, vp, i32]
     l.phyx_b200_upload_collider.argtypes = [vp, vp, i32, vp, vp, i32]
+    l.phyx_b200_solve_tuning.argtypes = [vp, i32, i32]
+    l.phyx_b200_strip_plan.argtypes = [vp, C.POINTER(i32), vp, vp, i32, vp]
+    l.phyx_b200_strip_trace.argtypes = [vp, i32, vp, i64, C.POINTER(i32)]
     l.phyx_b200_partition_create.argtypes = [vp, i32, i32, i32, C.c_size_t, vp, C.POINTER(vp)]
     l.phyx_b200_partition_attach.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(i32)]
     l.phyx_b200_partition_destroy.argtypes = [vp]
@@ -338,6 +344,41 @@ class Context:
         levels = np.zeros(nl.value, dtype=LEVEL)
         self._check(self.l.phyx_b200_get_schedule(self.h, _p(slots), ns.value, _p(levels), nl.value, C.byref(ns), C.byref(nl)))
         return slots, levels
+
+    def solve_tuning(self, kernel_form=0, strips=0):
+        """kernel_form: 0 choose, 1 streaming, 2 record form, 3 strip-local (required); strips: 0 choose, -1 never, n strips."""
+        self._check(self.l.phyx_b200_solve_tuning(self.h, kernel_form, strips))
+
+    def strip_plan(self):
+        """Strip layout of the last solve: dict(strips, cuts, class_slot_start, info...) or None if it did not use strips."""
+        n = C.c_int32(0)
+        info = np.zeros(8, np.int32)
+        self._check(self.l.phyx_b200_strip_plan(self.h, C.byref(n), None, None, 0, _p(info)))
+        names = ("usable", "rejected", "max_strip_rows", "max_cut_rows", "max_bin", "statics", "colours", "cut_manifolds")
+        out = dict(zip(names, (int(v) for v in info)))
+        out["strips"] = n.value
+        if n.value == 0:
+            return out
+        cuts, cls = np.zeros(2 * n.value + 1, np.int32), np.zeros(2 * n.value + 1, np.int32)
+        self._check(self.l.phyx_b200_strip_plan(self.h, C.byref(n), _p(cuts), _p(cls), cuts.shape[0], _p(info)))
+        out["cuts"] = cuts[: n.value + 1].copy()
+        out["class_slot_start"] = cls
+        return out
+
+    def strip_trace(self, passes=-1, fetch=False):
+        """passes >= 0: record that many passes per CTA in the following solves; fetch: stamps [strips][passes][8] (ns) of the last solve."""
+        out = None
+        tp = getattr(self, "_trace_passes", 0)
+        if fetch and tp > 0:
+            n = C.c_int32(0)
+            buf = np.zeros(1024 * tp * 8, np.uint64)
+            self._check(self.l.phyx_b200_strip_trace(self.h, -1, _p(buf), buf.shape[0], C.byref(n)))
+            if n.value:
+                out = buf[: n.value * tp * 8].reshape(n.value, tp, 8)
+        if passes >= 0:
+            self._check(self.l.phyx_b200_strip_trace(self.h, passes, None, 0, None))
+            self._trace_passes = passes
+        return out
 
     # ---- one world over several devices (phyx_b200/partition.py drives these) ----
     def partition_create(self, rank, ranks, boundary_capacity, bulk_bytes):

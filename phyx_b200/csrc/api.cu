@@ -185,10 +185,11 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     part_destroy(c);
+    strip_release(c);
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
-        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->timeline, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->locKeysA, &c->locKeysB, &c->locOrder, &c->locRowOf, &c->locStats, &c->pairQ, &c->pairIdx };
+        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->pairQ, &c->pairIdx, &c->bodyActivity };
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -390,6 +391,76 @@ int phyx_b200_solve_staged(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, 
         stats->ms_schedule = elapsed_ms(t0, t1);
         stats->ms_total = elapsed_ms(t0, t2);
     }
+    return PHYX_B200_OK;
+}
+
+// ---- tuning and introspection of the solve ----------------------------------------------------------------
+
+int phyx_b200_solve_tuning(phyx_b200_ctx* c, int kernelForm, int strips)
+{
+    PHYX_TRY(check(c));
+    if (kernelForm < 0 || kernelForm > 3 || strips < -1)
+    {
+        set_error("solve_tuning: kernelForm must be 0 (choose), 1, 2 or 3; strips -1 (never), 0 (choose) or a count");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    c->forceKernelForm = kernelForm;
+    c->strip.want = strips;
+    // schedules built so far may have the other layout
+    c->scheduleMode = -1;
+    c->colourStateValid = false;
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_strip_plan(phyx_b200_ctx* c, int32_t* strips, int32_t* cuts, int32_t* classSlotStart, int32_t capacity, int32_t* info)
+{
+    PHYX_TRY(check(c));
+    const StripPlan& sp = c->strip;
+    if (strips) *strips = sp.valid ? sp.strips : 0;
+    if (info)
+    {
+        const int v[8] = { sp.valid ? 1 : 0, sp.rejected, sp.maxStripRows, sp.maxCutRows, sp.maxBin, sp.numStatics, sp.colours, sp.cutManifolds };
+        memcpy(info, v, sizeof(v));
+    }
+    if (!sp.valid || (!cuts && !classSlotStart)) return PHYX_B200_OK;
+    if (capacity < 2 * sp.strips + 1)
+    {
+        set_error("strip_plan: need room for %d entries", 2 * sp.strips + 1);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    if (cuts)
+    {
+        PHYX_CUDA(cudaMemcpyAsync(cuts, sp.cuts.ptr, size_t(sp.strips + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (classSlotStart)
+    {
+        std::vector<int> cs;
+        PHYX_TRY(strip_host_levels(c, &cs));
+        memcpy(classSlotStart, cs.data(), cs.size() * sizeof(int));
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_strip_trace(phyx_b200_ctx* c, int passes, uint64_t* out, int64_t capacity, int32_t* strips)
+{
+    PHYX_TRY(check(c));
+    StripPlan& sp = c->strip;
+    if (out && sp.trace.ptr && sp.tracePasses > 0 && sp.valid)
+    {
+        const int64_t n = int64_t(sp.strips) * sp.tracePasses * 8;
+        if (capacity < n)
+        {
+            set_error("strip_trace: need room for %lld words", (long long)n);
+            return PHYX_B200_ERR_CAPACITY;
+        }
+        PHYX_CUDA(cudaMemcpyAsync(out, sp.trace.ptr, size_t(n) * 8, cudaMemcpyDeviceToHost, c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+        if (strips) *strips = sp.strips;
+    }
+    else if (strips)
+        *strips = 0;
+    if (passes >= 0) sp.tracePasses = passes;
     return PHYX_B200_OK;
 }
 
@@ -761,6 +832,7 @@ int phyx_b200_get_schedule(phyx_b200_ctx* c, int32_t* slots, int32_t slotCapacit
     int32_t* levelCount)
 {
     PHYX_TRY(check(c));
+    if (c->hostLevelsStale) PHYX_TRY(strip_host_levels(c, nullptr));
     if (c->hostSlotsStale)
     {
         // device-built schedule: fetch the slot -> joint table on demand

@@ -134,7 +134,6 @@ int bodies_upload(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int n)
     c->bodyCount = n;
     c->broadphaseValid = false;
     c->rowOrderValid = false;
-    if (c->locBodies != n) c->locValid = false;
     c->hasSnapshot = false;
     if (n == 0) return PHYX_B200_OK;
     PHYX_CUDA(cudaMemcpyAsync(c->aos.ptr, bodies, size_t(n) * sizeof(phyx_rigid_body), cudaMemcpyHostToDevice, c->stream));

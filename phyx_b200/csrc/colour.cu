@@ -804,7 +804,53 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
 
     if (c->part.ranks > 1)
     {
+        c->strip.valid = false;
         return part_layout(c, jb, work, result, incremental, staticsChanged, &c->partColours);
+    }
+
+    // strip layout (strips.cu): class-major over S row ranges, run by the strip-local kernel; rejected layouts
+    // (a manifold across non-adjacent strips, a strip too large for shared memory) fall through to colour-major
+    c->strip.valid = false;
+    c->hostLevelsStale = false;
+    int S = c->forceKernelForm == 1 || c->forceKernelForm == 2 ? 0 : strip_choose(c, M, nb);
+    if (S > 0)
+    {
+        int res[4];
+        PHYX_CUDA(cudaMemcpyAsync(res, result, 16, cudaMemcpyDeviceToHost, c->stream));
+        bool usable = false;
+        for (;;)
+        {
+            PHYX_TRY(strip_layout(c, S, jb, work, &usable));   // synchronises the stream
+            // strips narrower than the bodies' reach (a manifold across non-adjacent strips, a row in two cut sets): try
+            // half as many, and remember what worked for the next steps of this world (one strip always works, if it fits)
+            if (usable || c->strip.want > 0 || S == 1 || !(c->strip.rejected & 3)) break;
+            S = std::max(1, S / 2);
+            c->strip.autoLimit = S;
+        }
+        if (res[1])
+        {
+            set_error("colouring needs more than %d colours", kMaxColours);
+            return PHYX_B200_ERR_CAPACITY;
+        }
+        if (usable)
+        {
+            c->slotCount = 2 * c->strip.manifolds;
+            c->levelCount = c->strip.colours;
+            c->colourRounds = res[0];
+            *staticsChanged = res[3] != 0;
+            c->colourStateValid = true;
+            c->colourStateBodies = nb;
+            if (!incremental) c->coloursAtFullBuild = c->levelCount;
+            c->hostSlotsStale = true;
+            c->hostLevelsStale = true;
+            return PHYX_B200_OK;
+        }
+        if (c->forceKernelForm == 3)
+        {
+            set_error("strip layout rejected (reason mask %d: 1 manifold across non-adjacent strips, 2 row in two cut sets, 4 shared memory, 8 static bodies, 16 no manifolds)",
+                c->strip.rejected);
+            return PHYX_B200_ERR_STATE;
+        }
     }
 
     // colour-major layout of the manifolds: stable counting sort on a 7-bit digit (bin 64 = skipped)

@@ -88,6 +88,22 @@ struct Partition
     int launchIndex = 0;
 };
 
+// Strip-local solve (strips.cu): the solver rows (sorted-x order) are cut into S contiguous ranges ("strips"), one per
+// CTA of a persistent kernel.  A manifold whose dynamic bodies lie in one strip is INTERIOR to it (class k); one whose
+// bodies lie in adjacent strips k, k+1 is CUT (class S + k).  Slots are laid out class-major, colour-minor.
+struct StripPlan
+{
+    bool valid = false;        // the schedule of the resident joints is a strip layout and k_solve_strips can run it
+    int want = 0;              // tuning (phyx_b200_solve_tuning): 0 = choose, -1 = never, > 0 = this many strips
+    int strips = 0;            // S of the current layout
+    int autoLimit = 0;         // largest S worth trying when choosing (halved whenever a layout is rejected as too narrow)
+    int maxStripRows = 0, maxCutRows = 0, maxBin = 0, numStatics = 0, colours = 0, cutManifolds = 0, manifolds = 0;
+    bool attributeSet = false;
+    int rejected = 0;          // why the last layout attempt was not usable (bit mask, see strips.cu), 0 = usable
+    DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, staticOrd, header, words, sync, hist, trace;
+    int tracePasses = 0;       // developer aid (phyx_b200_strip_trace): passes of the next solves to time-stamp per CTA
+};
+
 } // namespace phyx
 
 struct phyx_b200_ctx
@@ -157,17 +173,13 @@ struct phyx_b200_ctx
     phyx::DevBuf strictLevels, strictMap, staticMulti, rowsMulti;
     int strictLevelCount = 0, numMultiStatics = 0;
     phyx::DevBuf solveFlags;     // productive flags + result words
-    phyx::DevBuf timeline;       // developer aid (PHYX_SOLVE_TIMELINE)
     phyx::DevBuf solveRows;      // 2 x float4 per body: the solver's packed copy of the velocity / displacement rows
     phyx::DevBuf rowOf;          // int per body: its row in the sorted-x order of the last broadphase
     bool rowOrderValid = false;
     int rowOrderBodies = 0;
-    // strip order of the solver rows (locality.cu)
-    phyx::DevBuf locKeysA, locKeysB, locOrder, locRowOf, locStats;
-    bool locValid = false;
-    int locBodies = 0, locAge = 0;
     phyx::DevBuf colourTmp;      // colouring scratch
     phyx::DevBuf colourKeys, colourSorted;   // uint2 {colour, joint} before / after the counting sort
+    bool hostLevelsStale = false; // strip layout: the level list is rebuilt from the device's bin table on demand
     bool hostSlotsStale = false; // schedule lives on the device only; get_schedule fetches it on demand
     // persistent colouring state (incremental recolouring of the joint cache)
     phyx::DevBuf manColour;      // int per manifold, moves with it through PackManifolds; -1 = none (no contact points yet)
@@ -188,6 +200,12 @@ struct phyx_b200_ctx
     int solveBlocksPerSM = 0, colourBlocksPerSM = 0, colourRounds = 0;
     int lastKernelForm = 0;
     float lastActiveFraction = 1.0f;   // share of the impulse joint-iterations the previous solve relaxed (kernel choice, solve.cu)
+
+    phyx::StripPlan strip;
+    phyx::DevBuf bodyActivity;   // int per body: last impulse iteration with a productive joint on it, previous solve (strip balance)
+    bool activityValid = false;
+    int activityBodies = 0;
+    int forceKernelForm = 0;     // tuning: 0 = choose, 1 streaming, 2 record, 3 strips (error if the layout cannot be built)
 
     // ---- one world over several devices (partition.cu; SURVEY.md §8e: an island that spans devices) -----
     phyx::Partition part;
@@ -211,8 +229,12 @@ int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift,
 // colour.cu
 int colour_schedule_build(phyx_b200_ctx* c);
 
-// locality.cu
-int locality_order_update(phyx_b200_ctx* c);
+// strips.cu
+int strip_choose(const phyx_b200_ctx* c, int manifolds, int bodies);
+int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool* usable);
+int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, float4* rowsVel, float4* rowsDisp);
+int strip_host_levels(phyx_b200_ctx* c, std::vector<int>* classStart);
+void strip_release(phyx_b200_ctx* c);
 
 // schedule.cu
 int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int nj, int mode, int flags);

@@ -30,6 +30,7 @@
 // Compiled with --fmad=false: every float operation is the reference's, in the reference's order.
 #include "common.cuh"
 #include "barrier.cuh"
+#include "solve_math.cuh"
 
 #include <stdlib.h>
 
@@ -37,10 +38,6 @@ namespace phyx
 {
 
 constexpr int kBlock = 256;
-constexpr float kProductiveImpulse = 1e-4f;    // Solver.cpp:8
-constexpr float kFrictionCoefficient = 0.3f;   // Solver.cpp:9
-constexpr int kPairHasB = int(0x80000000u);    // pairIdx.y: the manifold has a second joint
-constexpr int kPairRecordWords = 6;            // float4 per manifold record (PairRecord below)
 
 struct SolveParams
 {
@@ -62,32 +59,17 @@ struct SolveParams
     unsigned long long* barrier;       // ring of 4 grid-barrier words
     int* result;                       // [0] impulse iterations run, [1] displacement iterations run, [2] extra wake passes
     unsigned long long* activeTotal;   // [2] joint-iterations relaxed (not skipped) per phase
-    unsigned long long* timeline;      // optional (PHYX_SOLVE_TIMELINE=1): globaltimer after every level barrier, CTA 0
     // strict companion schedule of a replay (schedule.cu StaticRule); numStrictLevels == 0: single schedule
     const Level* strictLevels;
     int numStrictLevels;
     // paired levels, record form (k_solve_pairs2): one 128-byte record and one index word pair per manifold
     const float4* pairQ;
     const int2* pairIdx;
-    int experiment;                    // developer aid (PHYX_SOLVE_EXPERIMENT, record form, tools/solve_experiments.py): 1 = no joint passes the
-                                       // skip test, 2 = no row gathers either (both: wrong results, early-out disabled), 5 = L2 prefetch on
     const int* strictMap;              // strict position -> slot (or -1)
     const unsigned char* rowsMulti;    // per body row: static body with at least two units
     int numMultiStatics;
     int* hotCount;                     // [2 phases][4]: multi-unit static bodies productive in iteration it, at [it % 3]
 };
-
-__device__ __forceinline__ void timeline_mark(const SolveParams& P, int tick)
-{
-    if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0 && tick < 4096)
-    {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        P.timeline[tick] = t;
-    }
-}
-
-__device__ __forceinline__ float vmax(float l, float r) { return l > r ? l : r; }   // SIMD max: l>r?l:r
 
 // ---- RefreshLimiter, Solver.cpp:549-590: angular projectors + compInvMass ------------------------
 __device__ __forceinline__ void refresh_limiter(float n1x, float n1y, float w1x, float w1y, float w2x, float w2y, float im1, float ii1,
@@ -126,11 +108,12 @@ __global__ void __launch_bounds__(kBlock) k_prepare_bodies(int n, const unsigned
 }
 
 __global__ void __launch_bounds__(kBlock) k_finish_bodies(int n, const unsigned* __restrict__ order, const float4* __restrict__ rowsVel,
-    const float4* __restrict__ rowsDisp, float4* __restrict__ vel, float4* __restrict__ disp)
+    const float4* __restrict__ rowsDisp, float4* __restrict__ vel, float4* __restrict__ disp, int* __restrict__ activity)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned b = order ? order[i] : unsigned(i);
+    if (activity) activity[b] = __float_as_int(rowsVel[i].w);   // last productive impulse iteration: next step's strip balance
     vel[b] = rowsVel[i];
     disp[b] = rowsDisp[i];
 }
@@ -139,7 +122,7 @@ __global__ void __launch_bounds__(kBlock) k_finish_bodies(int n, const unsigned*
 __global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __restrict__ slotJoint, const phyx_contact_joint* __restrict__ joints,
     const float4* __restrict__ contactPoints, const float4* __restrict__ params, const int* __restrict__ rowOf, float4* __restrict__ q0,
     float4* __restrict__ q1, float4* __restrict__ q2, float4* __restrict__ q3, float2* __restrict__ accNF, float* __restrict__ accD,
-    float4* __restrict__ pairQ, int2* __restrict__ pairIdx, int firstSlot)
+    float4* __restrict__ pairQ, int2* __restrict__ pairIdx, int firstSlot, bool writeIdx)
 {
     int s = firstSlot + blockIdx.x * blockDim.x + threadIdx.x;   // slots [firstSlot, numSlots)
     if (s >= numSlots) return;
@@ -148,7 +131,7 @@ __global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __r
     {
         if (!pairQ)
             q3[s] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
-        else if (!(s & 1))
+        else if (!(s & 1) && writeIdx)
             pairIdx[s >> 1] = make_int2(-1, -1);
         return;
     }
@@ -192,7 +175,7 @@ __global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __r
         if (!h)
         {
             rec[2] = make_float4(p1.x, p1.y, p2.x, p2.y);   // both joints of a manifold have the same two bodies
-            pairIdx[s >> 1] = make_int2(b1, b2 | (slotJoint[s + 1] >= 0 ? kPairHasB : 0));   // numSlots is a multiple of 64
+            if (writeIdx) pairIdx[s >> 1] = make_int2(b1, b2 | (slotJoint[s + 1] >= 0 ? kPairHasB : 0));   // numSlots is a multiple of 64
         }
     }
     else
@@ -219,65 +202,6 @@ __global__ void __launch_bounds__(kBlock) k_finish(int numSlots, const int* __re
     joints[j].frictionLimiter_accumulatedImpulse = a.y;
 }
 
-// ---- static bodies -----------------------------------------------------------------------------------
-// A static body (invMass = invInertia = 0) never changes velocity, so joints that share one do not
-// conflict and may sit in the same level; thousands of ground contacts would otherwise serialise.
-// What they DO share is the body's lastIteration, which the reference updates joint by joint
-// (Solver.cpp:903-910) and reads in the skip test (:790-798).  To reproduce the sequential
-// semantics exactly, each static body has one 64-bit word per phase:
-//     [63:48] latest iteration in which a joint on it was productive, +1 (0 = never)
-//     [47:32] the productive iteration before that, +1
-//     [31:0]  smallest sequential position among the productive joints of the latest iteration
-// A joint at position p in iteration it therefore sees lastIteration = it exactly when an EARLIER
-// joint (position < p) on that body was productive in this iteration, else the value carried over
-// from previous iterations.  Schedules keep the joints of one static body in non-decreasing level
-// order, so every earlier joint is in the same or an earlier level; if a joint of the same level
-// becomes productive on a body whose carried-over value is stale ("cold"), the level is re-scanned
-// for joints that this wakes up (k_solve, wake passes) until nothing changes.
-__device__ __forceinline__ int static_visible_last(const unsigned long long* p, int it, unsigned pos)
-{
-    unsigned long long w = __ldcg(p);
-    unsigned latest = unsigned(w >> 48), prev = unsigned(w >> 32) & 0xffffu, minPos = unsigned(w);
-    if (latest == unsigned(it + 1)) return (minPos < pos) ? it : int(prev) - 1;
-    return int(latest) - 1;
-}
-
-// Record "productive at (it, pos)".  Returns true if this changed the word while the body was cold
-// (its carried-over lastIteration <= it-2), i.e. if it can wake up later joints of the same level.
-__device__ __forceinline__ bool static_mark(unsigned long long* p, int it, unsigned pos, int* hotCounter)
-{
-    unsigned long long old = __ldcg(p);
-    for (;;)
-    {
-        unsigned latest = unsigned(old >> 48), prev = unsigned(old >> 32) & 0xffffu, minPos = unsigned(old);
-        unsigned long long nw;
-        int carried;
-        if (latest == unsigned(it + 1))
-        {
-            if (pos >= minPos) return false;
-            nw = (old & 0xffffffff00000000ull) | pos;
-            carried = int(prev) - 1;
-        }
-        else
-        {
-            nw = (static_cast<unsigned long long>(it + 1) << 48) | (static_cast<unsigned long long>(latest) << 32) | pos;
-            carried = int(latest) - 1;
-        }
-        unsigned long long seen = atomicCAS(p, old, nw);
-        if (seen == old)
-        {
-            // first productive joint on this body in this iteration: it will be "hot" in the next one
-            if (hotCounter && latest != unsigned(it + 1)) atomicAdd(hotCounter, 1);
-            return carried <= it - 2;
-        }
-        old = seen;
-    }
-}
-
-__device__ __forceinline__ float flipsign_bits(float x, float y)   // SIMD_AVX2.h:272-275
-{
-    return __int_as_float(__float_as_int(x) ^ (__float_as_int(y) & 0x80000000));
-}
 
 // ---- PreStepJoints, Solver.cpp:736-750 ---------------------------------------------------------------
 __device__ __forceinline__ void prestep_slot(const SolveParams& P, int s)
@@ -312,88 +236,6 @@ __device__ __forceinline__ void prestep_slot(const SolveParams& P, int s)
     if (!st2) __stcg(&P.vel[b2], v2);
 }
 
-// ---- the arithmetic of one joint --------------------------------------------------------------------
-// PHASE 0: SolveJointsImpulses (Solver.cpp:833-901): normal impulse clamped to >= -accumulated, then
-// friction clamped to the Coulomb cone of the updated normal impulse.  PHASE 1:
-// SolveJointsDisplacement (:971-1003).  v1 / v2 are the two body rows; acc = {accN, accF} resp. {accD, -}.
-// `wide` selects the SIMD (xor) form of flipsign over the scalar one (SIMD_AVX2.h:272 / SIMD_Scalar.h:265).
-template <int PHASE>
-__device__ __forceinline__ bool relax(const float4 c0, const float4 c1, const float4 c2, const float4 c3, float2& acc, float4& v1, float4& v2, bool wide)
-{
-    const float nx = c0.x, ny = c0.y, aN1 = c0.z, aN2 = c0.w;
-    const float im1 = c2.x, ii1 = c2.y, im2 = c2.z, ii2 = c2.w;
-    const float cinvN = c3.z;
-    // normal limiter: projectors (n, -n), compMass = projector * invMass
-    const float n2x = -nx, n2y = -ny;
-    const float cm1x = nx * im1, cm1y = ny * im1, cm1a = aN1 * ii1;
-    const float cm2x = n2x * im2, cm2y = n2y * im2, cm2a = aN2 * ii2;
-
-    if (PHASE == 0)
-    {
-        const float aF1 = c1.x, aF2 = c1.y, cinvF = c1.z, dstVel = c1.w;
-
-        float dV = dstVel;
-        dV -= nx * v1.x;
-        dV -= ny * v1.y;
-        dV -= aN1 * v1.z;
-        dV -= n2x * v2.x;
-        dV -= n2y * v2.y;
-        dV -= aN2 * v2.z;
-        float dN = dV * cinvN;
-        dN = vmax(dN, -acc.x);
-        v1.x += cm1x * dN;
-        v1.y += cm1y * dN;
-        v1.z += cm1a * dN;
-        v2.x += cm2x * dN;
-        v2.y += cm2y * dN;
-        v2.z += cm2a * dN;
-        acc.x += dN;
-
-        const float tx = -ny, ty = nx, t2x = -tx, t2y = -ty;
-        float fV = 0.0f;
-        fV -= tx * v1.x;
-        fV -= ty * v1.y;
-        fV -= aF1 * v1.z;
-        fV -= t2x * v2.x;
-        fV -= t2y * v2.y;
-        fV -= aF2 * v2.z;
-        float dF = fV * cinvF;
-        const float force = acc.y + dF;
-        const float limit = acc.x * kFrictionCoefficient;
-        const float limitSigned = wide ? flipsign_bits(limit, force) : (force < 0.0f ? -limit : limit);
-        const float adjusted = limitSigned - acc.y;
-        dF = (fabsf(force) > limit) ? adjusted : dF;
-        acc.y += dF;
-        v1.x += (tx * im1) * dF;
-        v1.y += (ty * im1) * dF;
-        v1.z += (aF1 * ii1) * dF;
-        v2.x += (t2x * im2) * dF;
-        v2.y += (t2y * im2) * dF;
-        v2.z += (aF2 * ii2) * dF;
-        return vmax(fabsf(dN), fabsf(dF)) > kProductiveImpulse;
-    }
-    else
-    {
-        float accD = acc.x;
-        float dV = c3.w;   // dstDisplacingVelocity
-        dV -= nx * v1.x;
-        dV -= ny * v1.y;
-        dV -= aN1 * v1.z;
-        dV -= n2x * v2.x;
-        dV -= n2y * v2.y;
-        dV -= aN2 * v2.z;
-        float d = dV * cinvN;
-        d = vmax(d, -accD);
-        v1.x += cm1x * d;
-        v1.y += cm1y * d;
-        v1.z += cm1a * d;
-        v2.x += cm2x * d;
-        v2.y += cm2y * d;
-        v2.z += cm2a * d;
-        acc.x = accD + d;
-        return fabsf(d) > kProductiveImpulse;
-    }
-}
 
 // ---- one pass over one level of one iteration -----------------------------------------------------------
 // The read-only joint streams of a slot (and its accumulators, which only this thread ever writes)
@@ -585,7 +427,6 @@ __device__ __forceinline__ int run_phase(const SolveParams& P, int iters, int ti
                 havePre = true;
             }
             BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
-            timeline_mark(P, tick);
             while (r.wake)
             {
                 SlotData<PHASE> scratch;
@@ -801,7 +642,6 @@ __device__ __forceinline__ int run_phase_pairs(const SolveParams& P, int iters, 
             havePre = sN < N.end;
             if (havePre) load_pair<PHASE>(P, sN, true, pre);
             BarrierResult r = grid_wait(P.barrier, epoch, ticket);
-            timeline_mark(P, tick);
             while (r.wake)
             {
                 PairData<PHASE> scratch;
@@ -868,16 +708,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve_pairs(SolveParams
 // flight), then the tests and the relaxations; no two manifolds of a level share a dynamic body, so
 // gathering the rows of a whole batch up front reads nothing stale.  The arithmetic and the order of
 // relaxations are those of solve_pairs, hence the same results bit for bit.
-struct PairRecord   // layout of pairQ: 6 float4 = 96 bytes per manifold; the displacement phase needs the first 64 bytes only
-{
-    float4 a0;   // joint a: {n.x, n.y, angN1, angN2}
-    float4 b0;   // joint b: the same
-    float4 m;    // {invMass1, invInertia1, invMass2, invInertia2}: shared, both joints have the same two bodies
-    float4 nd;   // {compInvMassN a, dstDisplacingVelocity a, compInvMassN b, dstDisplacingVelocity b}
-    float4 a1;   // joint a: {angF1, angF2, compInvMassF, dstVelocity}
-    float4 b1;   // joint b: the same
-};
-static_assert(sizeof(PairRecord) == kPairRecordWords * sizeof(float4), "record layout");
 
 // Records of the manifolds that pass the skip test are staged through shared memory with asynchronous copies
 // (LDGSTS): a thread issues the copies for ALL its active manifolds of a batch at once and waits once, instead
@@ -895,9 +725,6 @@ __device__ __forceinline__ void cp_async_wait_all()
 
 constexpr int kPairU = 4;   // manifolds a thread handles together (default; the 1024-threads-per-SM shape uses 2)
 
-__device__ __forceinline__ unsigned smem_u32(const void* p);
-
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 
 __device__ __forceinline__ void prestep_pair2(const SolveParams& P, int p)
@@ -989,7 +816,7 @@ __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L
             }
             if (!valid) idx[u].x = -1;
             v1[u] = v2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid && P.experiment != 2)
+            if (valid)
             {
                 v1[u] = __ldcg(&rows[idx[u].x & kBodyMask]);
                 v2[u] = __ldcg(&rows[idx[u].y & kBodyMask]);
@@ -1010,7 +837,7 @@ __device__ __forceinline__ bool solve_pairs2(const SolveParams& P, const Level L
             const unsigned pos = unsigned(2 * p);
             last1v[u] = (r1 & kStaticBit) ? static_visible_last(&statics[r1 & kBodyMask], it, pos) : __float_as_int(v1[u].w);
             last2v[u] = (r2 & kStaticBit) ? static_visible_last(&statics[r2 & kBodyMask], it, pos) : __float_as_int(v2[u].w);
-            const bool active = ((last1v[u] > it - 2) || (last2v[u] > it - 2)) && P.experiment != 1 && P.experiment != 2;
+            const bool active = ((last1v[u] > it - 2) || (last2v[u] > it - 2));
             if (!active)
             {
                 idx[u].x = -1;
@@ -1127,15 +954,11 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
             any |= solve_pairs2<PHASE, U>(P, L, it, tick, true, tid, nthreads, wake, activeCount, pre, havePre, bitCursor, activity, stage);
             unsigned long long ticket;
             grid_arrive(P.barrier, epoch, wake, any, ticket);
-            // While the grid drains into the barrier: index words of this thread's first batch of the level that
-            // follows, and an L2 prefetch of the records it is expected to need (this iteration's own activity
-            // bits when the next level is level 0 of the next iteration, else last iteration's).
+            // while the grid drains into the barrier: index words of this thread's first batch of the level that follows
             {
                 const bool wrap = l + 1 == P.numLevels;
                 const Level N = levels[wrap ? 0 : l + 1];
                 const int pairBaseN = N.start >> 1, numPairsN = (N.end - N.start) >> 1;
-                const unsigned cursorN = wrap ? 0u : bitCursor;
-                const unsigned long long hint = wrap ? activity : predicted;
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                 {
@@ -1145,23 +968,11 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
                     {
                         const int p = pairBaseN + int(pN);
                         pre[u] = __ldcs(&P.pairIdx[p]);
-                        // (an L2 prefetch of the records predicted active from the previous iteration's activity bits was
-                        // measured here: 10.08 us per level pass with it, 9.64 us without; PHYX_SOLVE_EXPERIMENT=5 turns it on)
-                        const unsigned bit = cursorN + u;
-                        if (P.experiment == 5 && (bit >= 64u || ((hint >> bit) & 1ull)))
-                        {
-                            prefetch_l2(P.pairQ + size_t(p) * kPairRecordWords);
-                            if (PHASE == 0)
-                                prefetch_l2(&P.accNF[2 * p]);
-                            else
-                                prefetch_l2(&P.accD[2 * p]);
-                        }
                     }
                 }
                 havePre = true;
             }
             BarrierResult r = grid_wait(P.barrier, epoch, ticket);
-            timeline_mark(P, tick);
             while (r.wake)
             {
                 int2 none[U];
@@ -1176,7 +987,6 @@ __device__ __forceinline__ int run_phase_pairs2(const SolveParams& P, const Leve
         }
         ++ran;
         predicted = activity;
-        if (P.experiment == 1 || P.experiment == 2) productiveAnywhere = true;
         if (!productiveAnywhere) break;   // Solver.cpp:189 / :210
     }
     return ran;
@@ -1227,316 +1037,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_solve_pairs2(SolveParam
     }
 }
 
-// =====================================================================================================
-// TMA-staged variant of the solve kernel
-// =====================================================================================================
-// Same algorithm, different data movement.  Each CTA owns every gridDim.x-th chunk of kU*256 slots of
-// every level.  The four read-only joint streams of a chunk (Q0..Q3, 64 B per slot) are brought into a
-// shared-memory ring by 1-D bulk TMA copies (cp.async.bulk, SASS UBLKCP) that complete on an mbarrier;
-// one elected thread issues them kStages-1 chunks ahead.  Because the streams never change during a
-// solve, the producer runs ahead of the grid barriers too: when a level opens, its first chunks are
-// already in shared memory, and what remains on the critical path of a slot is the gather of its two
-// body rows from L2, of which every thread keeps kU slots' worth in flight.
-
-template <int U, int T>
-struct PipeStage
-{
-    float4 q0[U * T], q1[U * T], q2[U * T], q3[U * T];
-};
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
-{
-    unsigned done;
-    do
-    {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done)
-                     : "r"(smem_u32(bar)), "r"(parity)
-                     : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
-                 "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// the chunks this CTA owns, in execution order
-struct ChunkCursor
-{
-    int it, l, k;
-};
-
-template <int U, int T>
-__device__ __forceinline__ bool cursor_next(const SolveParams& P, int iters, ChunkCursor& c, int& base, int& count)
-{
-    while (c.it < iters)
-    {
-        const Level L = P.levels[c.l];
-        const long long b = L.start + static_cast<long long>(blockIdx.x + c.k * gridDim.x) * (U * T);
-        if (b < L.end)
-        {
-            base = int(b);
-            count = min(U * T, L.end - int(b));
-            ++c.k;
-            return true;
-        }
-        c.k = 0;
-        if (++c.l == P.numLevels)
-        {
-            c.l = 0;
-            ++c.it;
-        }
-    }
-    return false;
-}
-
-struct SlotWork
-{
-    float4 c3, v1, v2;
-    float2 acc;
-    int s, b1, b2, last1, last2;
-    unsigned pos;
-    bool valid, wide, st1, st2, unitHasStatic, active;
-};
-
-template <int PHASE, int U, int S, int T>
-__device__ __forceinline__ int run_phase_pipe(const SolveParams& P, int iters, PipeStage<U, T>* stages, unsigned long long* full, int* sharedWord,
-    unsigned& consumed, unsigned& epoch, int& tick, int& wakePasses, unsigned& activeCount)
-{
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nthreads = gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const unsigned seg = 0xffu << (lane & ~7);
-    float4* rows = PHASE == 0 ? P.vel : P.disp;
-    unsigned long long* statics = PHASE == 0 ? P.staticImp : P.staticDisp;
-    const bool producer = threadIdx.x == 0;
-
-    ChunkCursor prod = { 0, 0, 0 };
-    unsigned issued = consumed;   // producer-only bookkeeping (thread 0)
-    auto produce = [&]() {
-        int base, count;
-        if (!cursor_next<U, T>(P, iters, prod, base, count)) return;
-        const unsigned st = issued % S;
-        PipeStage<U, T>& dst = stages[st];
-        const unsigned bytes = unsigned(count) * 16u;
-        mbar_expect_tx(&full[st], 4u * bytes);
-        bulk_g2s(dst.q0, P.q0 + base, bytes, &full[st]);
-        bulk_g2s(dst.q1, P.q1 + base, bytes, &full[st]);
-        bulk_g2s(dst.q2, P.q2 + base, bytes, &full[st]);
-        bulk_g2s(dst.q3, P.q3 + base, bytes, &full[st]);
-        ++issued;
-    };
-    if (producer)
-        for (int k = 0; k < S - 1; ++k) produce();
-
-    int ran = 0;
-    for (int it = 0; it < iters; ++it)
-    {
-        bool any = false, productiveAnywhere = false;
-        for (int l = 0; l < P.numLevels; ++l)
-        {
-            const Level L = P.levels[l];
-            ++tick;
-            bool wake = false;
-            for (int k = 0;; ++k)
-            {
-                const long long cb = L.start + static_cast<long long>(blockIdx.x + k * gridDim.x) * (U * T);
-                if (cb >= L.end) break;
-                const int base = int(cb);
-                const int count = min(U * T, L.end - base);
-                const unsigned st = consumed % S;
-                if (producer) produce();   // refills the stage released by the previous chunk's __syncthreads
-                mbar_wait(&full[st], (consumed / S) & 1u);
-                const PipeStage<U, T>& in = stages[st];
-
-                SlotWork w[U];
-                // 1. decode, issue every global load of the chunk's slots
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                {
-                    const int idx = u * T + threadIdx.x;
-                    SlotWork& x = w[u];
-                    x.s = base + idx;
-                    x.valid = idx < count;
-                    x.c3 = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
-                    if (x.valid) x.c3 = in.q3[idx];
-                    const int r1 = __float_as_int(x.c3.x), r2 = __float_as_int(x.c3.y);
-                    x.valid = x.valid && r1 >= 0;
-                    x.b1 = r1 & kBodyMask;
-                    x.b2 = r2 & kBodyMask;
-                    x.st1 = x.valid && (r1 & kStaticBit);
-                    x.st2 = x.valid && (r2 & kStaticBit);
-                    x.wide = x.s < L.grouped_end;
-                    x.v1 = x.v2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    x.acc = make_float2(0.f, 0.f);
-                    x.pos = 0;
-                    if (x.valid)
-                    {
-                        x.v1 = __ldcg(&rows[x.b1]);
-                        x.v2 = __ldcg(&rows[x.b2]);
-                        if (PHASE == 0)
-                            x.acc = __ldcs(&P.accNF[x.s]);
-                        else
-                            x.acc.x = __ldcs(&P.accD[x.s]);
-                        if (x.st1 || x.st2) x.pos = P.slotPos ? unsigned(P.slotPos[x.s]) : unsigned(x.s);
-                    }
-                }
-                // 2. skip test (Solver.cpp:790-798)
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                {
-                    SlotWork& x = w[u];
-                    const unsigned mStatic = __ballot_sync(0xffffffffu, x.st1 || x.st2);
-                    x.unitHasStatic = x.wide ? (mStatic & seg) != 0 : (x.st1 || x.st2);
-                    x.last1 = x.last2 = -1;
-                    x.active = false;
-                    if (x.valid)
-                    {
-                        x.last1 = x.st1 ? static_visible_last(&statics[x.b1], it, x.pos) : __float_as_int(x.v1.w);
-                        x.last2 = x.st2 ? static_visible_last(&statics[x.b2], it, x.pos) : __float_as_int(x.v2.w);
-                        x.active = (x.last1 > it - 2) || (x.last2 > it - 2);
-                    }
-                    const unsigned mActive = __ballot_sync(0xffffffffu, x.active);
-                    if (x.wide) x.active = x.valid && (mActive & seg) != 0;
-                }
-                // 3. relax, write back
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                {
-                    SlotWork& x = w[u];
-                    if (!x.active) continue;
-                    const int idx = u * T + threadIdx.x;
-                    ++activeCount;
-                    const bool productive = relax<PHASE>(in.q0[idx], in.q1[idx], in.q2[idx], x.c3, x.acc, x.v1, x.v2, x.wide);
-                    if (PHASE == 0)
-                        __stcs(&P.accNF[x.s], x.acc);
-                    else
-                        __stcs(&P.accD[x.s], x.acc.x);
-                    if (!x.st1)
-                    {
-                        x.v1.w = __int_as_float(productive ? it : x.last1);
-                        __stcg(&rows[x.b1], x.v1);
-                    }
-                    else if (productive)
-                        wake |= static_mark(&statics[x.b1], it, x.pos, nullptr);
-                    if (!x.st2)
-                    {
-                        x.v2.w = __int_as_float(productive ? it : x.last2);
-                        __stcg(&rows[x.b2], x.v2);
-                    }
-                    else if (productive)
-                        wake |= static_mark(&statics[x.b2], it, x.pos, nullptr);
-                    if (x.unitHasStatic) __stcg(&P.processed[x.s], tick);
-                    any |= productive;
-                }
-                __syncthreads();   // every thread is done with this stage: it may be refilled
-                ++consumed;
-            }
-            BarrierResult r = grid_barrier(P.barrier, epoch, wake, any);
-            timeline_mark(P, tick);
-            while (r.wake)
-            {
-                SlotData<PHASE> scratch;
-                wake = false;
-                any |= solve_level<PHASE, false>(P, L, nullptr, it, tick, false, tid, nthreads, wake, activeCount, scratch, false);
-                ++wakePasses;
-                r = grid_barrier(P.barrier, epoch, wake, any);
-            }
-            productiveAnywhere = r.productive;
-        }
-        ++ran;
-        if (!productiveAnywhere) break;   // Solver.cpp:189 / :210
-    }
-    // drain: chunks fetched speculatively for iterations that will not run must land before the ring
-    // is reused or the CTA exits
-    if (producer)
-    {
-        for (unsigned n = consumed; n != issued; ++n) mbar_wait(&full[n % S], (n / S) & 1u);
-        *sharedWord = int(issued);
-    }
-    __syncthreads();
-    consumed = unsigned(*sharedWord);
-    __syncthreads();
-    return ran;
-}
-
-template <int U, int S, int T, int MINB>
-__global__ void __launch_bounds__(T, MINB) k_solve_pipe(SolveParams P)
-{
-    extern __shared__ __align__(128) unsigned char pipeSmem[];
-    PipeStage<U, T>* stages = reinterpret_cast<PipeStage<U, T>*>(pipeSmem);
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(pipeSmem + sizeof(PipeStage<U, T>) * S);
-    int* sharedWord = reinterpret_cast<int*>(full + S);
-
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nthreads = gridDim.x * blockDim.x;
-    if (threadIdx.x == 0)
-    {
-        for (int k = 0; k < S; ++k) mbar_init(&full[k], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    unsigned epoch = 0, consumed = 0;
-    int wakePasses = 0, tick = 0;
-    unsigned active[2] = { 0u, 0u };
-
-    for (int l = 0; l < P.numLevels; ++l)
-    {
-        const Level L = P.levels[l];
-        for (int s = L.start + tid; s < L.end; s += nthreads) prestep_slot(P, s);
-        grid_barrier(P.barrier, epoch, false, false);
-    }
-    const int ranImpulse = run_phase_pipe<0, U, S, T>(P, P.contactIters, stages, full, sharedWord, consumed, epoch, tick, wakePasses, active[0]);
-    const int ranDisplacement = run_phase_pipe<1, U, S, T>(P, P.penetrationIters, stages, full, sharedWord, consumed, epoch, tick, wakePasses, active[1]);
-
-    for (int phase = 0; phase < 2; ++phase)
-    {
-        unsigned v = active[phase];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.activeTotal[phase], static_cast<unsigned long long>(v));
-    }
-    if (tid == 0)
-    {
-        P.result[0] = ranImpulse;
-        P.result[1] = ranDisplacement;
-        P.result[2] = wakePasses;
-    }
-}
-
-template <int U, int S, int T, int MINB>
-static int launch_solve_pipe(phyx_b200_ctx* c, SolveParams& P, int widestLevel)
-{
-    const size_t smem = sizeof(PipeStage<U, T>) * S + sizeof(unsigned long long) * S + 16;
-    static int perSM = 0;
-    if (perSM == 0)
-    {
-        PHYX_CUDA(cudaFuncSetAttribute(k_solve_pipe<U, S, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_solve_pipe<U, S, T, MINB>, T, smem));
-        if (perSM < 1)
-        {
-            set_error("pipelined solve kernel does not fit on an SM");
-            return PHYX_B200_ERR_CUDA;
-        }
-    }
-    const int want = (widestLevel + U * T - 1) / (U * T);
-    const int grid = max(1, min(want, c->numSMs * perSM));
-    void* args[] = { &P };
-    PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_pipe<U, S, T, MINB>, dim3(grid), dim3(T), args, smem, c->stream));
-    return PHYX_B200_OK;
-}
-
 // ---- host orchestration -----------------------------------------------------------------------------
 
 static float elapsed(cudaEvent_t a, cudaEvent_t b)
@@ -1547,27 +1047,39 @@ static float elapsed(cudaEvent_t a, cudaEvent_t b)
 }
 
 // joints + contact points are resident (c->joints, c->contactPoints), schedule is resident.
+// Iteration kernels (stats->kernelForm): 0 = k_solve (joint units: host-array API and replay schedules), 1 = k_solve_pairs
+// (manifold units, streaming), 2 = k_solve_pairs2 (manifold units, record form), 3 = k_solve_strips (strips.cu; the default
+// of the resident pipeline whenever the strip layout is usable).  1 and 2 give the same results bit for bit on the same
+// (colour-major) schedule; phyx_b200_solve_tuning forces a form.
 int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats)
 {
     const int ns = c->slotCount, nl = c->levelCount, nb = c->bodyCount;
     const int I = cfg->contactIterationsCount, D = cfg->penetrationIterationsCount;
-    if (I < 0 || D < 0)
+    if (I < 0 || D < 0 || I > 60000 || D > 60000)
     {
-        set_error("solve: negative iteration count");
+        set_error("solve: iteration counts must be in [0, 60000]");
         return PHYX_B200_ERR_ARGUMENT;
     }
+    const bool strips = c->strip.valid;
+    const bool paired = strips || (!c->hostLevels.empty() && c->hostLevels[0].grouped_end < 0);
+    // streaming against record form: 1.65 against 1.78 ms with 38 % of the joint-iterations active, 1.64 against 1.50 ms with
+    // 27 % (1 M pyramid, round 1): the choice follows the activity of the previous solve of this world
+    const bool records = strips || (paired && (c->forceKernelForm ? c->forceKernelForm == 2 : c->lastActiveFraction < 0.32f));
     size_t ns1 = size_t(ns > 0 ? ns : 1);
-    PHYX_TRY(c->q0.reserve(ns1 * sizeof(float4)));
-    PHYX_TRY(c->q1.reserve(ns1 * sizeof(float4)));
-    PHYX_TRY(c->q2.reserve(ns1 * sizeof(float4)));
-    PHYX_TRY(c->q3.reserve(ns1 * sizeof(float4)));
-    PHYX_TRY(c->accNF.reserve(ns1 * sizeof(float2)));
-    PHYX_TRY(c->accD.reserve(ns1 * sizeof(float)));
-    if (I > 60000 || D > 60000)
+    if (!records)
     {
-        set_error("solve: at most 60000 iterations per phase");
-        return PHYX_B200_ERR_ARGUMENT;
+        PHYX_TRY(c->q0.reserve(ns1 * sizeof(float4)));
+        PHYX_TRY(c->q1.reserve(ns1 * sizeof(float4)));
+        PHYX_TRY(c->q2.reserve(ns1 * sizeof(float4)));
+        PHYX_TRY(c->q3.reserve(ns1 * sizeof(float4)));
     }
+    else
+    {
+        PHYX_TRY(c->pairQ.reserve(ns1 / 2 * kPairRecordWords * sizeof(float4) + 128));
+        PHYX_TRY(c->pairIdx.reserve(ns1 / 2 * sizeof(int2) + 64));
+    }
+    PHYX_TRY(c->accNF.reserve(ns1 * sizeof(float2) + 64));
+    PHYX_TRY(c->accD.reserve(ns1 * sizeof(float) + 64));
     PHYX_TRY(c->stamps.reserve(size_t(nb > 0 ? nb : 1) * 2 * sizeof(unsigned long long)));
     PHYX_TRY(c->processed.reserve(ns1 * sizeof(int)));
     PHYX_TRY(c->solveFlags.reserve(128));
@@ -1577,19 +1089,14 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
     int ranI = I > 0 ? 1 : 0, ranD = D > 0 ? 1 : 0, wakePasses = 0;
     if (ns > 0 && nl > 0)
     {
-        PHYX_CUDA(cudaMemsetAsync(c->stamps.ptr, 0, size_t(nb) * 2 * sizeof(unsigned long long), c->stream));
+        if (!strips) PHYX_CUDA(cudaMemsetAsync(c->stamps.ptr, 0, size_t(nb) * 2 * sizeof(unsigned long long), c->stream));
         PHYX_CUDA(cudaMemsetAsync(c->solveFlags.ptr, 0, 128, c->stream));
-        PHYX_CUDA(cudaMemsetAsync(c->processed.ptr, 0, size_t(ns) * sizeof(int), c->stream));
-        // memory order of the solver rows: the broadphase's sorted-x order (default; measured best:
-        // k_solve 2.40 ms vs 2.71 ms for strips and 3.08 ms for body order on the 1 M pyramid), else body
-        // order.  PHYX_ROW_ORDER=strips|body overrides (for A/B measurements, see locality.cu).
-        static const char* orderEnv = getenv("PHYX_ROW_ORDER");
-        const bool wantStrips = orderEnv && !strcmp(orderEnv, "strips"), wantSweep = !orderEnv || !strcmp(orderEnv, "sweep");
-        if (wantStrips) PHYX_TRY(locality_order_update(c));
-        const bool strips = wantStrips && c->locValid && c->locBodies == nb;
-        const bool sorted = !strips && wantSweep && c->rowOrderValid && c->rowOrderBodies == nb;
-        const unsigned* order = strips ? c->locOrder.as<unsigned>() : sorted ? c->entryIndex.as<unsigned>() : nullptr;
-        const int* rowOf = strips ? c->locRowOf.as<int>() : sorted ? c->rowOf.as<int>() : nullptr;
+        PHYX_CUDA(cudaMemsetAsync(c->processed.ptr, 0, size_t(strips ? ns / 2 : ns) * sizeof(int), c->stream));
+        // memory order of the solver rows: the broadphase's sorted-x order when there is one (measured best: k_solve 2.40 ms
+        // vs 3.08 ms for body order on the 1 M pyramid), else body order
+        const bool sorted = c->rowOrderValid && c->rowOrderBodies == nb;
+        const unsigned* order = sorted ? c->entryIndex.as<unsigned>() : nullptr;
+        const int* rowOf = sorted ? c->rowOf.as<int>() : nullptr;
         PHYX_TRY(c->solveRows.reserve(size_t(nb) * 2 * sizeof(float4)));
         float4* rowsVel = c->solveRows.as<float4>();
         float4* rowsDisp = rowsVel + nb;
@@ -1599,91 +1106,54 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
             dual ? c->staticMulti.as<unsigned char>() : nullptr, dual ? c->rowsMulti.as<unsigned char>() : nullptr);
         c->launches++;
         int grid = (ns + kBlock - 1) / kBlock;
-        // manifold units (colour.cu): all levels are paired.  Two kernels, same results bit for bit: the streaming form
-        // (k_solve_pairs) fetches every manifold's streams whether or not it passes the skip test, the record form
-        // (k_solve_pairs2) fetches records of the manifolds that pass only, at the price of a longer dependent
-        // chain for those.  Measured on the 1 M pyramid: 1.65 against 1.78 ms with 38 % of the joint-iterations
-        // active, 1.64 against 1.50 ms with 27 %.  So the choice follows the activity of the previous solve of this
-        // world (the contact state changes slowly); PHYX_SOLVE_PAIRS=1 / 2 forces one form.
-        const bool paired = !c->hostLevels.empty() && c->hostLevels[0].grouped_end < 0;
-        static const char* pairsEnv = getenv("PHYX_SOLVE_PAIRS");
-        const bool records = paired && (pairsEnv ? !strcmp(pairsEnv, "2") : c->lastActiveFraction < 0.32f);
-        c->lastKernelForm = records ? 2 : paired ? 1 : 0;
-        if (records)
-        {
-            PHYX_TRY(c->pairQ.reserve(ns1 / 2 * kPairRecordWords * sizeof(float4) + 128));
-            PHYX_TRY(c->pairIdx.reserve(ns1 / 2 * sizeof(int2) + 64));
-        }
+        c->lastKernelForm = strips ? 3 : records ? 2 : paired ? 1 : 0;
+        // the strip layout writes its own index words (rows local to a strip's shared memory)
         k_refresh<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
             c->params.as<float4>(), rowOf, c->q0.as<float4>(), c->q1.as<float4>(), c->q2.as<float4>(), c->q3.as<float4>(), c->accNF.as<float2>(),
-            c->accD.as<float>(), records ? c->pairQ.as<float4>() : nullptr, records ? c->pairIdx.as<int2>() : nullptr, 0);
+            c->accD.as<float>(), records ? c->pairQ.as<float4>() : nullptr, records ? c->pairIdx.as<int2>() : nullptr, 0, !strips);
         c->launches++;
         PHYX_CUDA(cudaEventRecord(e1, c->stream));
 
         SolveParams P;
-        P.vel = rowsVel;
-        P.disp = rowsDisp;
-        P.q0 = c->q0.as<float4>();
-        P.q1 = c->q1.as<float4>();
-        P.q2 = c->q2.as<float4>();
-        P.q3 = c->q3.as<float4>();
-        P.accNF = c->accNF.as<float2>();
-        P.accD = c->accD.as<float>();
-        P.levels = c->levels.as<Level>();
-        P.numLevels = nl;
-        P.slotPos = c->slotPosValid ? c->slotPos.as<int>() : nullptr;
-        P.processed = c->processed.as<int>();
-        P.staticImp = c->stamps.as<unsigned long long>();
-        P.staticDisp = P.staticImp + nb;
-        P.contactIters = I;
-        P.penetrationIters = D;
-        P.barrier = c->solveFlags.as<unsigned long long>();          // 4 words
+        memset(&P, 0, sizeof(P));
         P.result = reinterpret_cast<int*>(c->solveFlags.as<char>() + 32);
-        P.activeTotal = reinterpret_cast<unsigned long long*>(c->solveFlags.as<char>() + 48);
-        const char* experimentEnv = getenv("PHYX_SOLVE_EXPERIMENT");   // read per call: tools/solve_experiments.py switches it between solves
-        P.experiment = experimentEnv ? atoi(experimentEnv) : 0;
-        P.pairQ = records ? c->pairQ.as<float4>() : nullptr;
-        P.pairIdx = records ? c->pairIdx.as<int2>() : nullptr;
-        P.strictLevels = dual ? c->strictLevels.as<Level>() : nullptr;
-        P.numStrictLevels = dual ? c->strictLevelCount : 0;
-        P.strictMap = dual ? c->strictMap.as<int>() : nullptr;
-        P.rowsMulti = dual ? c->rowsMulti.as<unsigned char>() : nullptr;
-        P.numMultiStatics = dual ? c->numMultiStatics : 0;
-        P.hotCount = dual ? reinterpret_cast<int*>(c->solveFlags.as<char>() + 64) : nullptr;
-        static const bool wantTimeline = getenv("PHYX_SOLVE_TIMELINE") != nullptr;
-        P.timeline = nullptr;
-        if (wantTimeline)
+        if (strips)
+            PHYX_TRY(strip_solve_launch(c, cfg, rowsVel, rowsDisp));
+        else
         {
-            PHYX_TRY(c->timeline.reserve(4096 * 8));
-            PHYX_CUDA(cudaMemsetAsync(c->timeline.ptr, 0, 4096 * 8, c->stream));
-            P.timeline = c->timeline.as<unsigned long long>();
-        }
-        // CTA shape of the direct kernel: PHYX_SOLVE_SHAPE = <threads><min CTAs per SM> (2564, 2563, 5122, 5121, 10241)
-        static const int shapeEnv = getenv("PHYX_SOLVE_SHAPE") ? atoi(getenv("PHYX_SOLVE_SHAPE")) : 5122;
-        int sblock = 512;
-        void* solveKernel = nullptr;
-#define PHYX_PICK(T, B) (records ? (void*)k_solve_pairs2<T, B, (T * B >= 1024 ? 2 : kPairU)> : paired ? (void*)k_solve_pairs<T, B> : dual ? (void*)k_solve<T, B, true> : (void*)k_solve<T, B, false>)
-        switch (paired && !getenv("PHYX_SOLVE_SHAPE") ? 2562 : shapeEnv)
-        {
-        case 2562: sblock = 256; solveKernel = PHYX_PICK(256, 2); break;
-        case 2564: sblock = 256; solveKernel = PHYX_PICK(256, 4); break;
-        case 2563: sblock = 256; solveKernel = PHYX_PICK(256, 3); break;
-        case 5121: sblock = 512; solveKernel = PHYX_PICK(512, 1); break;
-        case 10241: sblock = 1024; solveKernel = PHYX_PICK(1024, 1); break;
-        default: sblock = 512; solveKernel = PHYX_PICK(512, 2); break;
-        }
-#undef PHYX_PICK
-        // the record form stages the active records in dynamic shared memory: [U][6][threads] float4
-        size_t solveSmem = 0;
-        if (records)
-        {
-            const int shape = paired && !getenv("PHYX_SOLVE_SHAPE") ? 2562 : shapeEnv;
-            const int minBlocks = shape % 10 > 0 ? shape % 10 : 2;
-            const int batch = sblock * minBlocks >= 1024 ? 2 : kPairU;
-            solveSmem = size_t(batch) * kPairRecordWords * sblock * sizeof(float4);
-            PHYX_CUDA(cudaFuncSetAttribute(solveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(solveSmem)));
-        }
-        {
+            P.vel = rowsVel;
+            P.disp = rowsDisp;
+            P.q0 = c->q0.as<float4>();
+            P.q1 = c->q1.as<float4>();
+            P.q2 = c->q2.as<float4>();
+            P.q3 = c->q3.as<float4>();
+            P.accNF = c->accNF.as<float2>();
+            P.accD = c->accD.as<float>();
+            P.levels = c->levels.as<Level>();
+            P.numLevels = nl;
+            P.slotPos = c->slotPosValid ? c->slotPos.as<int>() : nullptr;
+            P.processed = c->processed.as<int>();
+            P.staticImp = c->stamps.as<unsigned long long>();
+            P.staticDisp = P.staticImp + nb;
+            P.contactIters = I;
+            P.penetrationIters = D;
+            P.barrier = c->solveFlags.as<unsigned long long>();          // 4 words
+            P.activeTotal = reinterpret_cast<unsigned long long*>(c->solveFlags.as<char>() + 48);
+            P.pairQ = records ? c->pairQ.as<float4>() : nullptr;
+            P.pairIdx = records ? c->pairIdx.as<int2>() : nullptr;
+            P.strictLevels = dual ? c->strictLevels.as<Level>() : nullptr;
+            P.numStrictLevels = dual ? c->strictLevelCount : 0;
+            P.strictMap = dual ? c->strictMap.as<int>() : nullptr;
+            P.rowsMulti = dual ? c->rowsMulti.as<unsigned char>() : nullptr;
+            P.numMultiStatics = dual ? c->numMultiStatics : 0;
+            P.hotCount = dual ? reinterpret_cast<int*>(c->solveFlags.as<char>() + 64) : nullptr;
+            // CTA shapes (measured, round 1): manifold units 256 threads x 2 CTAs per SM, joint units 512 x 2
+            const int sblock = paired ? 256 : 512;
+            void* solveKernel = records ? (void*)k_solve_pairs2<256, 2, kPairU> : paired ? (void*)k_solve_pairs<256, 2>
+                                        : dual  ? (void*)k_solve<512, 2, true> : (void*)k_solve<512, 2, false>;
+            // the record form stages the active records in dynamic shared memory: [U][6][threads] float4
+            const size_t solveSmem = records ? size_t(kPairU) * kPairRecordWords * sblock * sizeof(float4) : 0;
+            if (records) PHYX_CUDA(cudaFuncSetAttribute(solveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(solveSmem)));
             int per = 0;
             PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, solveKernel, sblock, solveSmem));
             if (per < 1)
@@ -1692,40 +1162,23 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
                 return PHYX_B200_ERR_CUDA;
             }
             c->solveBlocksPerSM = per;
-        }
-        // persistent grid: every SM full, but no more CTAs than the widest level can use
-        int maxLevel = 0;
-        for (const Level& L : c->hostLevels) maxLevel = max(maxLevel, L.end - L.start);
-        if (paired) maxLevel = (maxLevel + 1) / 2;   // one thread per pair
-        int want = (maxLevel + sblock - 1) / sblock;
-        int sgrid = max(1, min(want, c->numSMs * c->solveBlocksPerSM));
-        // Default: the register-prefetch kernel (fastest measured).  PHYX_SOLVE_KERNEL=pipe
-        // selects the TMA-staged one; PHYX_SOLVE_PIPE="<slots per thread><stages>" (e.g. 12, 23) its shape.
-        static const char* kernelEnv = getenv("PHYX_SOLVE_KERNEL");
-        static const char* pipeEnv = getenv("PHYX_SOLVE_PIPE");
-        if (dual || paired || !(kernelEnv && !strcmp(kernelEnv, "pipe")))   // strict companions and paired levels are direct-kernel features
-        {
+            // persistent grid: every SM full, but no more CTAs than the widest level can use
+            int maxLevel = 0;
+            for (const Level& L : c->hostLevels) maxLevel = max(maxLevel, L.end - L.start);
+            if (paired) maxLevel = (maxLevel + 1) / 2;   // one thread per pair
+            const int want = (maxLevel + sblock - 1) / sblock;
+            const int sgrid = max(1, min(want, c->numSMs * c->solveBlocksPerSM));
             void* args[] = { &P };
             PHYX_CUDA(cudaLaunchCooperativeKernel(solveKernel, dim3(sgrid), dim3(sblock), args, solveSmem, c->stream));
+            c->launches++;
         }
-        else
-        {
-            const int variant = pipeEnv ? atoi(pipeEnv) : 12;
-            switch (variant)   // <slots per thread, stages, threads, min CTAs per SM>
-            {
-            case 13: PHYX_TRY((launch_solve_pipe<1, 3, 256, 3>(c, P, maxLevel))); break;
-            case 22: PHYX_TRY((launch_solve_pipe<2, 2, 256, 2>(c, P, maxLevel))); break;
-            case 23: PHYX_TRY((launch_solve_pipe<2, 3, 256, 2>(c, P, maxLevel))); break;
-            case 124: PHYX_TRY((launch_solve_pipe<1, 2, 256, 4>(c, P, maxLevel))); break;
-            case 512: PHYX_TRY((launch_solve_pipe<1, 2, 512, 2>(c, P, maxLevel))); break;
-            case 1024: PHYX_TRY((launch_solve_pipe<1, 2, 1024, 1>(c, P, maxLevel))); break;
-            default: PHYX_TRY((launch_solve_pipe<1, 2, 256, 3>(c, P, maxLevel))); break;
-            }
-        }
-        c->launches++;
         PHYX_CUDA(cudaEventRecord(e2, c->stream));
         k_finish<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->accNF.as<float2>(), c->joints.as<phyx_contact_joint>());
-        k_finish_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, rowsVel, rowsDisp, c->vel.as<float4>(), c->disp.as<float4>());
+        PHYX_TRY(c->bodyActivity.reserve(size_t(nb) * sizeof(int)));
+        k_finish_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, rowsVel, rowsDisp, c->vel.as<float4>(), c->disp.as<float4>(),
+            c->bodyActivity.as<int>());
+        c->activityValid = true;
+        c->activityBodies = nb;
         c->launches += 2;
         PHYX_CUDA(cudaEventRecord(e3, c->stream));
         int host[8];   // result[0..2], pad, activeTotal[2] as two 64-bit words
@@ -1733,17 +1186,6 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         PHYX_CUDA(cudaStreamSynchronize(c->stream));
         ranI = host[0];
         ranD = host[1];
-        if (wantTimeline)
-        {
-            // developer aid: per-level durations of the last solve on stderr
-            std::vector<unsigned long long> t(4096);
-            cudaMemcpy(t.data(), c->timeline.ptr, 4096 * 8, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[timeline] levels=%d:", nl);
-            for (int l = 0; l < nl; ++l) fprintf(stderr, " %d", c->hostLevels[l].end - c->hostLevels[l].start);
-            fprintf(stderr, "\n");
-            for (int k = 2; k < 4096 && t[k]; ++k)
-                if (k <= 3 * nl + 1 || k % (nl * 5) < nl) fprintf(stderr, "[timeline] tick %d (level %d): %.2f us\n", k, (k - 1) % nl, (t[k] - t[k - 1]) * 1e-3);
-        }
         wakePasses = host[2];
         {
             long long act0 = 0;
@@ -1755,9 +1197,6 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         {
             memcpy(&stats->activeJointIterations[0], &host[4], 8);
             memcpy(&stats->activeJointIterations[1], &host[6], 8);
-        }
-        if (stats)
-        {
             stats->ms_refresh = elapsed(e0, e1);
             stats->ms_iterations = elapsed(e1, e2);
             stats->ms_finish = elapsed(e2, e3);
@@ -2210,7 +1649,7 @@ int part_begin(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg)
         if (n <= 0) continue;
         k_refresh<<<(n + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(rg[1], c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
             c->params.as<float4>(), rowOf, nullptr, nullptr, nullptr, nullptr, c->accNF.as<float2>(), c->accD.as<float>(), c->pairQ.as<float4>(),
-            c->pairIdx.as<int2>(), rg[0]);
+            c->pairIdx.as<int2>(), rg[0], true);
         c->launches++;
     }
     if (!pt.params) pt.params = new SolveParams;
@@ -2337,7 +1776,7 @@ int part_end(phyx_b200_ctx* c, phyx_b200_solve_stats* stats)
         const unsigned* order = sorted ? c->entryIndex.as<unsigned>() : nullptr;
         float4* rowsVel = c->solveRows.as<float4>();
         k_finish<<<(ns + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->accNF.as<float2>(), c->joints.as<phyx_contact_joint>());
-        k_finish_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, rowsVel, rowsVel + nb, c->vel.as<float4>(), c->disp.as<float4>());
+        k_finish_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, rowsVel, rowsVel + nb, c->vel.as<float4>(), c->disp.as<float4>(), nullptr);
         c->launches += 2;
         PHYX_CUDA(cudaMemcpyAsync(&host, pt.state.ptr, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
         PHYX_CUDA(cudaStreamSynchronize(c->stream));

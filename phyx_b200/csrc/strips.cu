@@ -1,0 +1,1118 @@
+// phyx_b200 — strip-local sequential-impulse solve: the iteration loops of Solver::SolveJointIsland
+// (reference src/Solver.cpp:130-215) with NO grid-wide barrier on the critical path.
+//
+// Reference stages replaced here (all src/Solver.cpp), same arithmetic as solve.cu (solve_math.cuh):
+//   PreStepJoints            :697-758   warm start pass
+//   SolveJointsImpulses      :760-914   impulse passes
+//   SolveJointsDisplacement  :916-1018  displacement passes
+//   SolveJointIsland loops   :159-211   iteration control incl. the productive early-out (:189, :210)
+//
+// Why: the grid-barrier forms (solve.cu) run one colour of the WHOLE world between two grid barriers; a pass over
+// one colour costs ~9 us whatever it holds (4-5 us barrier + skew, one DRAM latency chain), 7-8 colours x 22 passes
+// per solve (profiles/README.md, round 1).  Here the solver rows, which are stored in the broadphase's sorted-x
+// order, are cut into S contiguous ranges ("strips", S <= number of SMs), one per CTA of ONE persistent kernel:
+//   * the strip's body rows {v, w, lastIteration} live in SHARED MEMORY for the whole solve (a contiguous row range:
+//     one 1-D bulk TMA copy, cp.async.bulk + mbarrier, SASS UBLKCP, per phase);
+//   * a manifold whose dynamic bodies lie in one strip is INTERIOR to it: all colours of a strip's interior manifolds
+//     are relaxed by its CTA under __syncthreads;
+//   * a manifold whose bodies lie in adjacent strips k, k+1 is CUT (class S + k).  Cut sets of different boundaries
+//     touch disjoint rows (checked when the layout is built), so ALL cut sets are relaxed concurrently, set k by
+//     CTA k, on a shared-memory copy of the rows the set touches: the strip's own right-boundary rows and the
+//     neighbour's left-boundary rows, which travel through global memory (L2) under point-to-point flags:
+//         CTA k+1: interior -> store L(k+1) -> release flagA[k+1] .............. acquire flagB[k] -> load L(k+1)
+//         CTA k  : interior -> acquire flagA[k+1] -> load L(k+1) -> cut set k -> store L(k+1) -> release flagB[k]
+//     A CTA waits for its two neighbours only; skew does not accumulate across the grid;
+//   * the productive early-out needs an OR over all CTAs: every CTA adds its flag to a per-iteration counter and
+//     reads the counter of iteration it-2 before starting iteration it (complete by then without waiting, in
+//     practice).  Running one more iteration after a non-productive one changes nothing (every joint fails the
+//     lastIteration test, Solver.cpp:790-798), so results and the reported iteration counts equal the reference
+//     loop's.
+// Read as one order [strip 0 colours .. strip S-1 colours, cut set 0 .. cut set S-2] this is a valid sequential
+// Gauss-Seidel sweep over the slot order, which is what the oracle checks bit for bit; as in the partitioned solve
+// each class keeps its own lastIteration word per static body (tests: partition.sequential_equivalent).
+//
+// Inside a CTA a colour ("bin") is relaxed in two steps: every thread applies the skip test (Solver.cpp:790-798) to
+// its candidates, which needs the 8-byte index word (prefetched during the previous bin) and two shared-memory rows,
+// and pushes the ones that pass onto a shared-memory worklist; then the worklist is dealt round-robin over all
+// threads, and only those fetch their 96-byte record from HBM.  Work is
+// balanced however the active manifolds cluster, and no byte is fetched for a skipped manifold.
+//
+// Fallback: if a manifold spans non-adjacent strips, a row belongs to two cut sets, or a strip does not fit in shared
+// memory, the layout is rejected and the colour-major layout + grid-barrier kernels of solve.cu run instead.
+#include "common.cuh"
+#include "solve_math.cuh"
+#include "tma.cuh"
+
+#include <algorithm>
+#include <stdlib.h>
+
+namespace phyx
+{
+
+constexpr int kBlock = 256;
+constexpr int kStripU = 8;         // candidates per thread whose index words are prefetched one bin ahead
+constexpr int kStripBins = kMaxColours;   // bins (colours) per class
+
+// layout header (device ints)
+enum
+{
+    H_REJECT = 0,   // bit 0: a manifold spans non-adjacent strips, bit 1: a row is in two cut sets
+    H_MAXROWS,      // rows of the largest strip
+    H_MAXCUT,       // rows of the largest cut set (own right-boundary rows + the neighbour's left-boundary rows)
+    H_STATICS,      // static bodies
+    H_MANIFOLDS,    // manifolds with a colour (slots / 2)
+    H_MAXBIN,       // manifolds of the largest (class, colour) bin
+    H_COLOURS,      // colours in use
+    H_CUTM,         // cut manifolds
+    H_TOTAL_R,
+    H_TOTAL_L,
+    H_SCAN_TOTAL,
+    H_WORDS = 16
+};
+
+enum
+{
+    kRejectFar = 1,
+    kRejectBothSides = 2,
+    kRejectSmem = 4,
+    kRejectStatics = 8,
+    kRejectEmpty = 16
+};
+
+// ---- layout ----------------------------------------------------------------------------------------------------
+
+// hist[row] = predicted work of the manifolds whose lower dynamic row it is.  A manifold costs one skip test per pass
+// and, in the iterations in which it is relaxed, a record fetch + two relaxations (about 4x a test, measured).  How many
+// iterations that will be is predicted from the previous step: activity[b] = last iteration in which body b received a
+// productive impulse (FinishBodies keeps it), and a manifold is relaxed while either body is at most one iteration stale
+// (Solver.cpp:790-798).  Without a previous step every manifold counts the same.
+__global__ void __launch_bounds__(kBlock) k_strip_hist(int M, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
+    const int* __restrict__ activity, int* __restrict__ hist)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    if (work[m] >= kMaxColours) return;
+    const int2 b = jb[m];
+    const int r1 = b.x < 0 ? -1 : (rowOf ? rowOf[b.x] : b.x), r2 = b.y < 0 ? -1 : (rowOf ? rowOf[b.y] : b.y);
+    const int home = r1 < 0 ? r2 : (r2 < 0 ? r1 : min(r1, r2));
+    if (home < 0) return;
+    int weight = 8;
+    if (activity)
+    {
+        const int last = max(b.x >= 0 ? activity[b.x] : -1, b.y >= 0 ? activity[b.y] : -1);
+        weight = 5 + min(max(last + 2, 1), 24);
+    }
+    atomicAdd(&hist[home], weight);
+}
+
+// every dynamic row also counts (shared memory per strip is what limits its width)
+__global__ void __launch_bounds__(kBlock) k_strip_hist_rows(int nb, const unsigned* __restrict__ order, const unsigned char* __restrict__ bodyStatic, int* __restrict__ hist)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nb) return;
+    const unsigned body = order ? order[r] : unsigned(r);
+    if (!bodyStatic[body]) hist[r] += 12;
+}
+
+// cuts[q] = first row with at least q/S of the manifolds before it
+__global__ void __launch_bounds__(kBlock) k_strip_cuts(int nb, int S, const int* __restrict__ prefix, const int* __restrict__ total, int* __restrict__ cuts)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > S) return;
+    if (q == 0) { cuts[0] = 0; return; }
+    if (q == S) { cuts[q] = nb; return; }
+    const long long target = (static_cast<long long>(*total) * q + S - 1) / S;
+    int lo = 0, hi = nb;   // smallest row r in [0, nb] with prefix[r] >= target (prefix[nb] := total)
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    cuts[q] = lo;
+}
+
+// largest k in [0, S) with cuts[k] <= row: the strip that holds the row (empty strips are never returned)
+__device__ __forceinline__ int strip_of(const int* cuts, int S, int row)
+{
+    int lo = 0, hi = S - 1;
+    while (lo < hi)
+    {
+        const int mid = (lo + hi + 1) >> 1;
+        if (cuts[mid] <= row) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// classify, persist the colours, emit {class << 7 | colour, manifold} sort keys, flag the rows cut manifolds touch
+// (flags[row]: bit 0 = right-boundary row of its strip, bit 1 = left-boundary row)
+__global__ void __launch_bounds__(kBlock) k_strip_keys(int M, int S, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
+    const int* __restrict__ cutsG, int* __restrict__ manColour, uint2* __restrict__ keys, int* __restrict__ flags, int* __restrict__ header)
+{
+    extern __shared__ int s_cuts[];
+    for (int q = threadIdx.x; q <= S; q += blockDim.x) s_cuts[q] = cutsG[q];
+    __syncthreads();
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    bool coloured = false, cut = false;
+    int colour = 0;
+    if (m < M)
+    {
+        const int c = work[m];
+        manColour[m] = (c >= kMaxColours) ? -1 : c;
+        unsigned key = unsigned(2 * S) << 7;   // skipped: behind every class
+        if (c < kMaxColours)
+        {
+            coloured = true;
+            colour = c;
+            const int2 b = jb[m];
+            const int r1 = b.x < 0 ? -1 : (rowOf ? rowOf[b.x] : b.x), r2 = b.y < 0 ? -1 : (rowOf ? rowOf[b.y] : b.y);
+            int cls = 0;
+            if (r1 >= 0 && r2 >= 0)
+            {
+                const int k1 = strip_of(s_cuts, S, r1), k2 = strip_of(s_cuts, S, r2);
+                if (k1 == k2)
+                    cls = k1;
+                else
+                {
+                    const int lo = min(k1, k2), hi = max(k1, k2);
+                    if (hi - lo > 1) atomicOr(&header[H_REJECT], kRejectFar);
+                    cls = S + lo;
+                    cut = true;
+                    atomicOr(&flags[k1 < k2 ? r1 : r2], 1);
+                    atomicOr(&flags[k1 < k2 ? r2 : r1], 2);
+                }
+            }
+            else if (r1 >= 0 || r2 >= 0)
+                cls = strip_of(s_cuts, S, r1 >= 0 ? r1 : r2);
+            key = (unsigned(cls) << 7) | unsigned(c);
+        }
+        keys[m] = make_uint2(key, unsigned(m));
+    }
+    const int nCol = __syncthreads_count(coloured), nCut = __syncthreads_count(cut);
+    // colours in use: block maximum first
+    __shared__ int s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    if (coloured) atomicMax(&s_max, colour + 1);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        if (nCol) atomicAdd(&header[H_MANIFOLDS], nCol);
+        if (nCut) atomicAdd(&header[H_CUTM], nCut);
+        if (s_max) atomicMax(&header[H_COLOURS], s_max);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_strip_split_flags(int nb, const int* __restrict__ flags, int* __restrict__ flagR, int* __restrict__ flagL)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nb) return;
+    const int f = flags[r];
+    flagR[r] = f & 1;
+    flagL[r] = (f >> 1) & 1;
+}
+
+// boundary row lists in row order, static-body ordinals
+__global__ void __launch_bounds__(kBlock) k_strip_lists(int nb, const int* __restrict__ flags, const int* __restrict__ prefixR, const int* __restrict__ prefixL,
+    const unsigned* __restrict__ order, const unsigned char* __restrict__ bodyStatic, int* __restrict__ bR, int* __restrict__ bL, int* __restrict__ staticOrd,
+    int* __restrict__ header)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nb) return;
+    const int f = flags[r];
+    if (f & 1) bR[prefixR[r]] = r;
+    if (f & 2) bL[prefixL[r]] = r;
+    if (f == 3) atomicOr(&header[H_REJECT], kRejectBothSides);
+    const unsigned body = order ? order[r] : unsigned(r);
+    staticOrd[r] = bodyStatic[body] ? atomicAdd(&header[H_STATICS], 1) : -1;   // any bijection will do: it only addresses the words
+}
+
+// per strip: first boundary row of each kind, sizes for the kernel's shared memory
+// bStart: [0 .. S] right lists, [S+1 .. 2S+1] left lists
+__global__ void __launch_bounds__(kBlock) k_strip_starts(int nb, int S, const int* __restrict__ cuts, const int* __restrict__ prefixR, const int* __restrict__ prefixL,
+    int* __restrict__ bStart, int* __restrict__ header)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > S) return;
+    auto at = [&](const int* prefix, int total, int k) { const int row = cuts[k]; return row >= nb ? total : prefix[row]; };
+    const int totalR = header[H_TOTAL_R], totalL = header[H_TOTAL_L];
+    bStart[q] = at(prefixR, totalR, q);
+    bStart[S + 1 + q] = at(prefixL, totalL, q);
+    if (q < S)
+    {
+        atomicMax(&header[H_MAXROWS], cuts[q + 1] - cuts[q]);
+        const int nR = at(prefixR, totalR, q + 1) - at(prefixR, totalR, q);
+        const int nLn = q + 2 <= S ? at(prefixL, totalL, q + 2) - at(prefixL, totalL, q + 1) : 0;
+        atomicMax(&header[H_MAXCUT], nR + nLn);
+        const int nL = at(prefixL, totalL, q + 1) - at(prefixL, totalL, q);
+        atomicMax(&header[H_MAXCUT], nL);   // the own-left list is staged with the same capacity
+    }
+}
+
+// sorted position p = manifold slot p (joint slots 2p, 2p+1): joints, index words, bin table
+__global__ void __launch_bounds__(kBlock) k_strip_place(int M, int S, const uint2* __restrict__ sorted, const int2* __restrict__ manBody,
+    const int* __restrict__ manCount, const float4* __restrict__ contactPoints, const int* __restrict__ rowOf, const unsigned char* __restrict__ bodyStatic,
+    const int* __restrict__ cuts, const int* __restrict__ prefixR, const int* __restrict__ prefixL, const int* __restrict__ bStart,
+    int* __restrict__ slotJoint, int2* __restrict__ pairIdx, int2* __restrict__ binRange)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= M) return;
+    const uint2 e = sorted[p];
+    const int cls = int(e.x >> 7), colour = int(e.x & 127u);
+    if (cls >= 2 * S) return;   // manifold without contact points
+    const int m = int(e.y);
+    const int bin = cls * kStripBins + colour;
+    if (p == 0 || sorted[p - 1].x != e.x) binRange[bin].x = p;
+    if (p == M - 1 || sorted[p + 1].x != e.x) binRange[bin].y = p + 1;
+    // the joints of a manifold are the solverIndex of its contact points (World.cpp:100-103,140)
+    slotJoint[2 * p] = __float_as_int(contactPoints[size_t(2 * m) * 2 + 1].w);
+    const bool hasB = manCount[m] > 1;
+    slotJoint[2 * p + 1] = hasB ? __float_as_int(contactPoints[size_t(2 * m + 1) * 2 + 1].w) : -1;
+    const int2 b = manBody[m];
+    const int r1 = rowOf ? rowOf[b.x] : b.x, r2 = rowOf ? rowOf[b.y] : b.y;
+    const bool st1 = bodyStatic[b.x] != 0, st2 = bodyStatic[b.y] != 0;
+    int x, y;
+    if (cls < S)
+    {
+        const int row0 = cuts[cls];
+        x = st1 ? (r1 | kStaticBit) : r1 - row0;
+        y = st2 ? (r2 | kStaticBit) : r2 - row0;
+    }
+    else
+    {
+        // cut set k: buffer = [right-boundary rows of strip k][left-boundary rows of strip k+1]
+        const int k = cls - S;
+        const int nR = bStart[k + 1] - bStart[k];
+        const int split = cuts[k + 1];
+        x = r1 < split ? prefixR[r1] - bStart[k] : nR + prefixL[r1] - bStart[S + 1 + k + 1];
+        y = r2 < split ? prefixR[r2] - bStart[k] : nR + prefixL[r2] - bStart[S + 1 + k + 1];
+    }
+    pairIdx[p] = make_int2(x, y | (hasB ? kPairHasB : 0));
+}
+
+__global__ void __launch_bounds__(kBlock) k_strip_maxbin(int bins, const int2* __restrict__ binRange, int* __restrict__ header)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= bins) return;
+    const int2 r = binRange[b];
+    if (r.y > r.x) atomicMax(&header[H_MAXBIN], r.y - r.x);
+}
+
+// strips for a world of this size: enough manifolds per strip to keep a CTA busy, at most one strip per SM
+int strip_choose(const phyx_b200_ctx* c, int manifolds, int bodies)
+{
+    if (c->strip.want < 0) return 0;
+    if (c->strip.want > 0) return std::min(c->strip.want, 2 * c->numSMs);   // more than one strip per SM: 256-thread CTAs, two per SM
+    (void)bodies;
+    int S = std::max(1, std::min(c->numSMs, manifolds / 256));
+    if (c->strip.autoLimit > 0) S = std::min(S, c->strip.autoLimit);   // what the last rejected layouts of this world allowed
+    return S;
+}
+
+static size_t strip_smem_bytes(int rowCap, int cutCap, int workCap)
+{
+    return size_t(rowCap) * 20 + size_t(cutCap) * 16 + size_t(workCap) * 4 + size_t(cutCap) * 4 * 3;
+}
+constexpr size_t kStripSmemLimit = 227 * 1024 - 4096;   // dynamic part: the opt-in maximum minus the kernel's static tables
+constexpr size_t kStripSmemLimit2 = 113 * 1024 - 4096;  // two CTAs per SM
+
+// Class-major layout of the coloured manifolds over S strips; `work` holds the colours.  On success with *usable the
+// context's schedule (slotJoint, pairIdx, bin table) is the strip layout; otherwise the caller lays out colour-major.
+int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool* usable)
+{
+    StripPlan& sp = c->strip;
+    const int M = c->manifoldCount, nb = c->bodyCount;
+    *usable = false;
+    sp.valid = false;
+    sp.rejected = 0;
+    const int grid = (M + kBlock - 1) / kBlock, gridB = (nb + kBlock - 1) / kBlock, gridS = (S + 1 + kBlock - 1) / kBlock;
+    const bool sortedRows = c->rowOrderValid && c->rowOrderBodies == nb;
+    const int* rowOf = sortedRows ? c->rowOf.as<int>() : nullptr;
+    const unsigned* order = sortedRows ? c->entryIndex.as<unsigned>() : nullptr;
+    const int bins = 2 * S * kStripBins;
+
+    PHYX_TRY(sp.header.reserve(64 * sizeof(int)));
+    PHYX_TRY(sp.hist.reserve(size_t(nb + 1) * sizeof(int)));
+    PHYX_TRY(sp.flags.reserve(size_t(nb + 1) * 3 * sizeof(int)));
+    PHYX_TRY(sp.prefixR.reserve(size_t(nb + 1) * sizeof(int)));
+    PHYX_TRY(sp.prefixL.reserve(size_t(nb + 1) * sizeof(int)));
+    PHYX_TRY(sp.bR.reserve(size_t(nb + 1) * sizeof(int)));
+    PHYX_TRY(sp.bL.reserve(size_t(nb + 1) * sizeof(int)));
+    PHYX_TRY(sp.staticOrd.reserve(size_t(nb + 1) * sizeof(int)));
+    PHYX_TRY(sp.cuts.reserve(size_t(S + 2) * sizeof(int)));
+    PHYX_TRY(sp.bStart.reserve(size_t(2 * S + 4) * sizeof(int)));
+    PHYX_TRY(sp.binRange.reserve(size_t(bins) * sizeof(int2)));
+    int* header = sp.header.as<int>();
+    int* flags = sp.flags.as<int>();
+    int* flagR = flags + (nb + 1);
+    int* flagL = flags + 2 * (nb + 1);
+    PHYX_CUDA(cudaMemsetAsync(header, 0, 64 * sizeof(int), c->stream));
+    PHYX_CUDA(cudaMemsetAsync(sp.hist.ptr, 0, size_t(nb + 1) * sizeof(int), c->stream));
+    PHYX_CUDA(cudaMemsetAsync(flags, 0, size_t(nb + 1) * sizeof(int), c->stream));
+    PHYX_CUDA(cudaMemsetAsync(sp.binRange.ptr, 0, size_t(bins) * sizeof(int2), c->stream));
+
+    // cuts that balance the manifold count (a manifold counts for its lower dynamic row)
+    const int* activity = (c->activityValid && c->activityBodies == nb) ? c->bodyActivity.as<int>() : nullptr;
+    k_strip_hist<<<grid, kBlock, 0, c->stream>>>(M, jb, work, rowOf, activity, sp.hist.as<int>());
+    k_strip_hist_rows<<<gridB, kBlock, 0, c->stream>>>(nb, order, c->bodyStatic.as<unsigned char>(), sp.hist.as<int>());
+    c->launches++;
+    PHYX_TRY(exclusive_scan_i32(c, sp.hist.as<int>(), sp.prefixR.as<int>(), nb, header + H_SCAN_TOTAL));
+    k_strip_cuts<<<gridS, kBlock, 0, c->stream>>>(nb, S, sp.prefixR.as<int>(), header + H_SCAN_TOTAL, sp.cuts.as<int>());
+    c->launches += 2;
+
+    // classes, sort keys, boundary flags; two stable passes: colour (7 bits), then class
+    PHYX_TRY(c->colourKeys.reserve(size_t(M) * sizeof(uint2)));
+    PHYX_TRY(c->colourSorted.reserve(size_t(M) * sizeof(uint2)));
+    k_strip_keys<<<grid, kBlock, size_t(S + 1) * sizeof(int), c->stream>>>(M, S, jb, work, rowOf, sp.cuts.as<int>(), c->manColour.as<int>(), c->colourKeys.as<uint2>(),
+        flags, header);
+    c->launches++;
+    int digits = 1;
+    while (digits < 2 * S + 1) digits <<= 1;
+    PHYX_TRY(radix_pass(c, c->colourKeys.as<uint2>(), c->colourSorted.as<uint2>(), M, 0, 128));
+    PHYX_TRY(radix_pass(c, c->colourSorted.as<uint2>(), c->colourKeys.as<uint2>(), M, 7, digits));
+    const uint2* sorted = c->colourKeys.as<uint2>();
+
+    // boundary row lists
+    k_strip_split_flags<<<gridB, kBlock, 0, c->stream>>>(nb, flags, flagR, flagL);
+    c->launches++;
+    PHYX_TRY(exclusive_scan_i32(c, flagR, sp.prefixR.as<int>(), nb, header + H_TOTAL_R));
+    PHYX_TRY(exclusive_scan_i32(c, flagL, sp.prefixL.as<int>(), nb, header + H_TOTAL_L));
+    k_strip_lists<<<gridB, kBlock, 0, c->stream>>>(nb, flags, sp.prefixR.as<int>(), sp.prefixL.as<int>(), order, c->bodyStatic.as<unsigned char>(),
+        sp.bR.as<int>(), sp.bL.as<int>(), sp.staticOrd.as<int>(), header);
+    k_strip_starts<<<gridS, kBlock, 0, c->stream>>>(nb, S, sp.cuts.as<int>(), sp.prefixR.as<int>(), sp.prefixL.as<int>(), sp.bStart.as<int>(), header);
+    c->launches += 2;
+
+    // slots
+    const size_t maxSlots = 2 * size_t(M) + 64;
+    PHYX_TRY(c->slotJoint.reserve(maxSlots * sizeof(int)));
+    PHYX_TRY(c->pairIdx.reserve((size_t(M) + 64) * sizeof(int2)));
+    k_strip_place<<<grid, kBlock, 0, c->stream>>>(M, S, sorted, c->manBody.as<int2>(), c->manCount.as<int>(), c->contactPoints.as<float4>(), rowOf,
+        c->bodyStatic.as<unsigned char>(), sp.cuts.as<int>(), sp.prefixR.as<int>(), sp.prefixL.as<int>(), sp.bStart.as<int>(), c->slotJoint.as<int>(),
+        c->pairIdx.as<int2>(), sp.binRange.as<int2>());
+    k_strip_maxbin<<<(bins + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(bins, sp.binRange.as<int2>(), header);
+    c->launches += 2;
+    PHYX_CUDA(cudaGetLastError());
+
+    int host[16];
+    PHYX_CUDA(cudaMemcpyAsync(host, header, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+
+    sp.strips = S;
+    sp.maxStripRows = host[H_MAXROWS];
+    sp.maxCutRows = host[H_MAXCUT];
+    sp.numStatics = host[H_STATICS];
+    sp.manifolds = host[H_MANIFOLDS];
+    sp.maxBin = host[H_MAXBIN];
+    sp.colours = host[H_COLOURS];
+    sp.cutManifolds = host[H_CUTM];
+    int rejected = host[H_REJECT];
+    if (sp.manifolds == 0) rejected |= kRejectEmpty;
+    if (strip_smem_bytes(sp.maxStripRows + 9, sp.maxCutRows + 9, sp.maxBin + 9) > (S > c->numSMs ? kStripSmemLimit2 : kStripSmemLimit)) rejected |= kRejectSmem;
+    if (size_t(sp.numStatics) * size_t(S) * 16 > (size_t(256) << 20)) rejected |= kRejectStatics;
+    sp.rejected = rejected;
+    if (rejected) return PHYX_B200_OK;
+    sp.valid = true;
+    *usable = true;
+    return PHYX_B200_OK;
+}
+
+// host copy of the schedule for phyx_b200_get_schedule: one level per non-empty (class, colour) bin, in slot order;
+// classStart[cls] = first slot of class cls (2S + 1 entries)
+int strip_host_levels(phyx_b200_ctx* c, std::vector<int>* classStart)
+{
+    StripPlan& sp = c->strip;
+    c->hostLevels.clear();
+    if (classStart) classStart->clear();
+    if (!sp.valid) return PHYX_B200_OK;
+    const int bins = 2 * sp.strips * kStripBins;
+    std::vector<int2> r;
+    r.resize(size_t(bins));
+    PHYX_CUDA(cudaMemcpyAsync(r.data(), sp.binRange.ptr, size_t(bins) * sizeof(int2), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    int cursor = 0;
+    for (int b = 0; b < bins; ++b)
+    {
+        if (classStart && b % kStripBins == 0) classStart->push_back(cursor);
+        if (r[b].y > r[b].x)
+        {
+            c->hostLevels.push_back({ 2 * r[b].x, -1, 2 * r[b].y });
+            cursor = 2 * r[b].y;
+        }
+    }
+    if (classStart) classStart->push_back(cursor);
+    c->hostLevelsStale = false;
+    return PHYX_B200_OK;
+}
+
+void strip_release(phyx_b200_ctx* c)
+{
+    StripPlan& sp = c->strip;
+    DevBuf* bufs[] = { &sp.cuts, &sp.binRange, &sp.flags, &sp.prefixR, &sp.prefixL, &sp.bR, &sp.bL, &sp.bStart, &sp.staticOrd, &sp.header, &sp.words, &sp.sync, &sp.hist, &sp.trace };
+    for (DevBuf* b : bufs) b->release();
+    sp.valid = false;
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------------
+
+struct StripParams
+{
+    float4* rows[2];                 // solver rows: impulse (velocity) and displacement arrays
+    const float4* pairQ;             // PairRecord per manifold slot
+    const int2* pairIdx;             // {row1, row2 | hasB}: rows local to the class's shared-memory buffer, or global | static bit
+    float2* accNF;                   // per joint slot
+    float* accD;
+    const int2* binRange;            // [2S][kStripBins] manifold slot ranges
+    const int* cuts;                 // [S + 1]
+    const int* bR;                   // right-boundary rows (global row numbers), row order
+    const int* bL;                   // left-boundary rows
+    const int* bStart;               // [0..S] starts in bR, [S+1 .. 2S+1] starts in bL
+    const int* staticOrd;            // per row: ordinal of a static body, else -1
+    unsigned long long* staticWords; // [2 phases][S][numStatics]
+    int numStatics;
+    int* processed;                  // per manifold slot: tick of the bin pass that ran it (manifolds with a static body only)
+    unsigned long long* flagA;       // [S] "my interior pass `seq` is done and my left-boundary rows are in global memory"
+    unsigned long long* flagB;       // [S] "cut set k of pass `seq` is done and strip k+1's left-boundary rows are in global memory"
+    unsigned long long* done;        // [2][doneStride] per iteration: arrivals | productive CTAs << 32
+    int doneStride;
+    int S, contactIters, penetrationIters;
+    int rowCap, cutCap, workCap;
+    int* result;                     // [0] impulse iterations run, [1] displacement iterations run, [2] wake passes
+    unsigned long long* activeTotal; // [2]
+    unsigned long long* trace;       // developer aid (phyx_b200_strip_trace): [S][tracePasses][8] globaltimer stamps, or null
+    int tracePasses;
+    int variant;   // TEMPORARY timing experiments
+};
+
+__device__ __forceinline__ void flag_release(unsigned long long* flag, unsigned long long value)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long flag_peek(const unsigned long long* flag)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long flag_acquire(const unsigned long long* flag)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    return v;
+}
+
+// thread 0 spins until *flag >= want, then the CTA proceeds
+__device__ __forceinline__ void cta_wait_flag(const unsigned long long* flag, unsigned long long want)
+{
+    if (threadIdx.x == 0)
+    {
+        while (flag_peek(flag) < want) {}
+        flag_acquire(flag);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void trace_mark(const StripParams& P, int k, int passIndex, int what)
+{
+    if (P.trace && threadIdx.x == 0 && passIndex < P.tracePasses)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        P.trace[(size_t(k) * P.tracePasses + passIndex) * 8 + what] = t;
+    }
+}
+
+struct StripCta
+{
+    float4* s_rows;     // the strip's rows
+    int* s_last;        // mirror of s_rows[].w (lastIteration): the skip test reads it without the 8-way bank conflicts of a stride-16 access
+    float4* s_cut;      // rows of the cut set
+    int* s_work;        // worklist: positions in the bin
+    int* s_listL;       // own left-boundary rows (local)
+    int* s_listR;       // own right-boundary rows (local)
+    int* s_listN;       // the right neighbour's left-boundary rows (global row numbers)
+    int2* s_bins;       // [nInt interior bins][nCut cut bins]
+    int* s_count;       // [2] worklist lengths (alternating)
+    int k, row0, nRows, nL, nR, nLn, nInt, nCut;
+    int parity;         // which worklist counter the next bin pass uses
+    int wakePasses;
+    unsigned active[2];
+    long long clk[3];   // developer aid: SM clocks spent in step 1 / step 2 / (spare) of the bins of the current pass (thread 0)
+};
+
+// warm start (PreStepJoints, Solver.cpp:736-750) of one bin: every manifold, no test
+template <int T>
+__device__ __forceinline__ void prestep_bin(const StripParams& P, float4* rowsS, const float4* __restrict__ rowsG, int2 bin)
+{
+    const int n = bin.y - bin.x;
+    for (int i = threadIdx.x; i < n; i += T)
+    {
+        const int p = bin.x + i;
+        const int2 idx = __ldg(&P.pairIdx[p]);
+        const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
+        const float4 a0 = __ldcs(rec), b0 = __ldcs(rec + 1), c2 = __ldcs(rec + 2), a1 = __ldcs(rec + 4), b1 = __ldcs(rec + 5);
+        const float4 accs = __ldcs(reinterpret_cast<const float4*>(&P.accNF[2 * p]));
+        const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit, haveB = idx.y < 0;
+        const int r1 = idx.x & kBodyMask, r2 = idx.y & kBodyMask;
+        float4 v1 = st1 ? __ldcg(&rowsG[r1]) : rowsS[r1];
+        float4 v2 = st2 ? __ldcg(&rowsG[r2]) : rowsS[r2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+        {
+            if (h == 1 && !haveB) break;
+            const float4 c0 = h ? b0 : a0, c1 = h ? b1 : a1;
+            const float nx = c0.x, ny = c0.y;
+            const float accN = h ? accs.z : accs.x, accF = h ? accs.w : accs.y;
+            v1.x += (nx * c2.x) * accN;
+            v1.y += (ny * c2.x) * accN;
+            v1.z += (c0.z * c2.y) * accN;
+            v2.x += ((-nx) * c2.z) * accN;
+            v2.y += ((-ny) * c2.z) * accN;
+            v2.z += (c0.w * c2.w) * accN;
+            const float tx = -ny, ty = nx;
+            v1.x += (tx * c2.x) * accF;
+            v1.y += (ty * c2.x) * accF;
+            v1.z += (c1.x * c2.y) * accF;
+            v2.x += ((-tx) * c2.z) * accF;
+            v2.y += ((-ty) * c2.z) * accF;
+            v2.z += (c1.y * c2.w) * accF;
+        }
+        if (!st1) rowsS[r1] = v1;
+        if (!st2) rowsS[r2] = v2;
+    }
+    __syncthreads();
+}
+
+template <int T>
+__device__ __forceinline__ void prefetch_idx(const StripParams& P, int2 bin, int2 (&pre)[kStripU])
+{
+    const int n = bin.y - bin.x;
+#pragma unroll
+    for (int u = 0; u < kStripU; ++u)
+    {
+        const int i = int(threadIdx.x) + u * T;
+        pre[u] = i < n ? __ldg(&P.pairIdx[bin.x + i]) : make_int2(-1, -1);
+    }
+}
+
+// One bin (one colour of one class) of one iteration.  PHASE 0: SolveJointsImpulses (Solver.cpp:781-910), PHASE 1:
+// SolveJointsDisplacement (:937-1014).  `pre` holds the index words of this thread's first kStripU candidates; on
+// return it holds those of `next`.  words: the class's static-body words of this phase.  dummyRow: a shared-memory row
+// nobody owns (index words of static bodies are redirected there for the speculative lastIteration read).  Returns
+// "this thread saw a productive joint".
+template <int PHASE, int T>
+__device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, float4* rowsS, int* lastS, int dummyRow, const float4* __restrict__ rowsG, unsigned long long* words,
+    int2 bin, int2 next, int it, int tick, int2 (&pre)[kStripU])
+{
+    const int n = bin.y - bin.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    bool anyProductive = false;
+    bool firstPass = true;
+    const long long c0 = P.trace ? clock64() : 0;
+    for (;;)
+    {
+        int* count = &s.s_count[s.parity];
+        // ---- step 1: the skip test (Solver.cpp:790-792, for both joints of a manifold at once, see solve.cu paired levels).
+        // All shared-memory reads of a thread's candidates are issued together; the rare candidates with a static body
+        // (whose lastIteration lives in a global word) are fixed up afterwards.
+        if (firstPass)
+        {
+            bool active[kStripU];
+            bool anyStatic = false;
+            int la[kStripU], lb[kStripU];
+#pragma unroll
+            for (int u = 0; u < kStripU; ++u)
+            {
+                const int2 idx = pre[u];
+                const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit;
+                anyStatic |= (st1 || st2) && idx.x >= 0;
+                const int ra = st1 || idx.x < 0 ? dummyRow : (idx.x & kBodyMask), rb = st2 || idx.x < 0 ? dummyRow : (idx.y & kBodyMask);
+                la[u] = (P.variant & 2) ? -1 : lastS ? lastS[ra] : __float_as_int(rowsS[ra].w);
+                lb[u] = (P.variant & 2) ? -1 : lastS ? lastS[rb] : __float_as_int(rowsS[rb].w);
+            }
+            if (anyStatic && !(P.variant & 1))
+            {
+#pragma unroll
+                for (int u = 0; u < kStripU; ++u)
+                {
+                    const int2 idx = pre[u];
+                    if (idx.x < 0) continue;
+                    const unsigned pos = unsigned(2 * (bin.x + int(threadIdx.x) + u * T));
+                    if (idx.x & kStaticBit) la[u] = static_visible_last(&words[P.staticOrd[idx.x & kBodyMask]], it, pos);
+                    if (idx.y & kStaticBit) lb[u] = static_visible_last(&words[P.staticOrd[idx.y & kBodyMask]], it, pos);
+                }
+            }
+            unsigned m[kStripU];
+            int warpTotal = 0;
+#pragma unroll
+            for (int u = 0; u < kStripU; ++u) active[u] = pre[u].x >= 0 && ((la[u] > it - 2) || (lb[u] > it - 2));
+            // the index words are used up: fetch those of the next bin now, a whole bin pass ahead of their use
+            if (!(P.variant & 4)) prefetch_idx<T>(P, next, pre);
+#pragma unroll
+            for (int u = 0; u < kStripU; ++u)
+            {
+                m[u] = __ballot_sync(0xffffffffu, active[u]);
+                warpTotal += __popc(m[u]);
+            }
+            if (warpTotal)
+            {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(count, warpTotal);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                // candidates of this warp in (u, lane) order
+                int before = 0;
+#pragma unroll
+                for (int u = 0; u < kStripU; ++u)
+                {
+                    if (active[u]) s.s_work[base + before + __popc(m[u] & below)] = int(threadIdx.x) + u * T;
+                    before += __popc(m[u]);
+                }
+            }
+        }
+        // candidates beyond the prefetched ones (bins larger than kStripU * T), and wake passes (everything again)
+        for (int i0 = firstPass ? kStripU * T : 0; i0 < n; i0 += T)
+        {
+            const int i = i0 + int(threadIdx.x);
+            bool active = false;
+            if (i < n)
+            {
+                const int p = bin.x + i;
+                const int2 idx = __ldg(&P.pairIdx[p]);
+                const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit;
+                bool consider = true;
+                if (!firstPass) consider = (st1 || st2) && __ldcg(&P.processed[p]) != tick;   // wake pass: only what a static body can wake
+                if (consider)
+                {
+                    const int r1 = idx.x & kBodyMask, r2 = idx.y & kBodyMask;
+                    const unsigned pos = unsigned(2 * p);
+                    const int last1 = st1 ? static_visible_last(&words[P.staticOrd[r1]], it, pos) : __float_as_int(rowsS[r1].w);
+                    const int last2 = st2 ? static_visible_last(&words[P.staticOrd[r2]], it, pos) : __float_as_int(rowsS[r2].w);
+                    active = (last1 > it - 2) || (last2 > it - 2);
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, active);
+            if (m)
+            {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(count, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (active) s.s_work[base + __popc(m & below)] = i;
+            }
+        }
+        __syncthreads();
+        const long long c1 = P.trace ? clock64() : 0;
+        const int total = *count;
+        if (threadIdx.x == 0) s.s_count[s.parity ^ 1] = 0;  // the next bin pass counts there
+        s.parity ^= 1;
+
+        // ---- step 2: relax the worklist, one entry per thread and round
+        bool wake = false;
+        for (int w = threadIdx.x; w < total; w += T)
+        {
+            const int p = bin.x + s.s_work[w];
+            const int2 idx = __ldg(&P.pairIdx[p]);
+            const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
+            const float4 a0 = __ldcs(rec), b0 = __ldcs(rec + 1), c2 = __ldcs(rec + 2), nd = __ldcs(rec + 3);
+            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1, accv;
+            if (PHASE == 0)
+            {
+                a1 = __ldcs(rec + 4);
+                b1 = __ldcs(rec + 5);
+                accv = __ldcs(reinterpret_cast<const float4*>(&P.accNF[2 * p]));
+            }
+            else
+            {
+                const float2 a = __ldcs(reinterpret_cast<const float2*>(&P.accD[2 * p]));
+                accv = make_float4(a.x, a.y, 0.f, 0.f);
+            }
+            const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit, haveB = idx.y < 0;
+            const int r1 = idx.x & kBodyMask, r2 = idx.y & kBodyMask;
+            float4 w1 = st1 ? __ldcg(&rowsG[r1]) : rowsS[r1];
+            float4 w2 = st2 ? __ldcg(&rowsG[r2]) : rowsS[r2];
+            const int last1 = __float_as_int(w1.w), last2 = __float_as_int(w2.w);   // used for dynamic bodies only
+            const float4 a3 = make_float4(0.f, 0.f, nd.x, nd.y), b3 = make_float4(0.f, 0.f, nd.z, nd.w);
+            float2 accA, accB;
+            if (PHASE == 0)
+            {
+                accA = make_float2(accv.x, accv.y);
+                accB = make_float2(accv.z, accv.w);
+            }
+            else
+            {
+                accA = make_float2(accv.x, 0.f);
+                accB = make_float2(accv.y, 0.f);
+            }
+            s.active[PHASE] += haveB ? 2u : 1u;
+            const bool productiveA = relax<PHASE>(a0, a1, c2, a3, accA, w1, w2, false);
+            bool productiveB = false;
+            if (haveB) productiveB = relax<PHASE>(b0, b1, c2, b3, accB, w1, w2, false);
+            if (PHASE == 0)
+                __stcs(reinterpret_cast<float4*>(&P.accNF[2 * p]), make_float4(accA.x, accA.y, accB.x, accB.y));
+            else
+                __stcs(reinterpret_cast<float2*>(&P.accD[2 * p]), make_float2(accA.x, accB.x));
+            // lastIteration = it where productive (Solver.cpp:903-910); a static body is marked at the position of
+            // the first productive joint
+            const bool productive = productiveA || productiveB;
+            const unsigned pos = unsigned(2 * p), markPos = productiveA ? pos : pos + 1;
+            if (!st1)
+            {
+                w1.w = __int_as_float(productive ? it : last1);
+                rowsS[r1] = w1;
+                if (lastS) lastS[r1] = productive ? it : last1;
+            }
+            else if (productive)
+                wake |= static_mark(&words[P.staticOrd[r1]], it, markPos, nullptr);
+            if (!st2)
+            {
+                w2.w = __int_as_float(productive ? it : last2);
+                rowsS[r2] = w2;
+                if (lastS) lastS[r2] = productive ? it : last2;
+            }
+            else if (productive)
+                wake |= static_mark(&words[P.staticOrd[r2]], it, markPos, nullptr);
+            if (st1 || st2) __stcg(&P.processed[p], tick);
+            anyProductive |= productive;
+        }
+        // rows of this bin are written: the next bin (or a wake pass over this one) may read them
+        const int again = __syncthreads_or(wake ? 1 : 0);
+        if (P.trace && firstPass)
+        {
+            s.clk[0] += c1 - c0;
+            s.clk[1] += clock64() - c1;
+        }
+        if (!again) break;
+        firstPass = false;
+        if (threadIdx.x == 0) ++s.wakePasses;
+    }
+    return anyProductive;
+}
+
+// One pass over the strip's classes.  MODE -1: warm start, 0: impulse iteration `it`, 1: displacement iteration `it`.
+template <int MODE, int T>
+__device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int it, unsigned long long seq, int passIndex, int2 (&pre)[kStripU])
+{
+    constexpr int PHASE = MODE == 1 ? 1 : 0;
+    float4* rowsG = P.rows[PHASE];
+    unsigned long long* words = P.staticWords + (size_t(PHASE) * P.S + s.k) * P.numStatics;
+    const int k = s.k, nBins = s.nInt + s.nCut;
+    bool any = false;
+    trace_mark(P, k, passIndex, 0);
+    s.clk[0] = s.clk[1] = s.clk[2] = 0;
+    // interior
+    for (int b = 0; b < s.nInt; ++b)
+    {
+        if (MODE < 0)
+            prestep_bin<T>(P, s.s_rows, rowsG, s.s_bins[b]);
+        else
+            any |= solve_bin<PHASE, T>(P, s, s.s_rows, s.s_last, P.rowCap - 1, rowsG, words, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, passIndex * 256 + b + 1, pre);
+    }
+    trace_mark(P, k, passIndex, 1);
+    if (P.trace && threadIdx.x == 0 && passIndex < P.tracePasses)
+    {
+        P.trace[(size_t(k) * P.tracePasses + passIndex) * 8 + 5] = (unsigned long long)s.clk[0];
+        P.trace[(size_t(k) * P.tracePasses + passIndex) * 8 + 6] = (unsigned long long)s.clk[1];
+    }
+    if (P.S == 1) return any;
+    // my left-boundary rows -> global memory, for cut set k-1
+    if (k > 0)
+    {
+        for (int i = threadIdx.x; i < s.nL; i += T) __stcg(&rowsG[s.row0 + s.s_listL[i]], s.s_rows[s.s_listL[i]]);
+        __syncthreads();
+        if (threadIdx.x == 0) flag_release(&P.flagA[k], seq);
+    }
+    if (k + 1 < P.S)
+    {
+        if (s.nCut > 0)
+        {
+            cta_wait_flag(&P.flagA[k + 1], seq);
+            trace_mark(P, k, passIndex, 2);
+            for (int i = threadIdx.x; i < s.nR; i += T) s.s_cut[i] = s.s_rows[s.s_listR[i]];
+            for (int i = threadIdx.x; i < s.nLn; i += T) s.s_cut[s.nR + i] = __ldcg(&rowsG[s.s_listN[i]]);
+            __syncthreads();
+            for (int b = s.nInt; b < nBins; ++b)
+            {
+                if (MODE < 0)
+                    prestep_bin<T>(P, s.s_cut, rowsG, s.s_bins[b]);
+                else
+                    any |= solve_bin<PHASE, T>(P, s, s.s_cut, nullptr, P.cutCap - 1, rowsG, words, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, passIndex * 256 + b + 1, pre);
+            }
+            for (int i = threadIdx.x; i < s.nR; i += T)
+            {
+                const float4 v = s.s_cut[i];
+                s.s_rows[s.s_listR[i]] = v;
+                s.s_last[s.s_listR[i]] = __float_as_int(v.w);
+            }
+            for (int i = threadIdx.x; i < s.nLn; i += T) __stcg(&rowsG[s.s_listN[i]], s.s_cut[s.nR + i]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) flag_release(&P.flagB[k], seq);
+        trace_mark(P, k, passIndex, 3);
+    }
+    if (k > 0 && s.nL > 0)
+    {
+        cta_wait_flag(&P.flagB[k - 1], seq);
+        for (int i = threadIdx.x; i < s.nL; i += T)
+        {
+            const float4 v = __ldcg(&rowsG[s.row0 + s.s_listL[i]]);
+            s.s_rows[s.s_listL[i]] = v;
+            s.s_last[s.s_listL[i]] = __float_as_int(v.w);
+        }
+        __syncthreads();
+    }
+    trace_mark(P, k, passIndex, 4);
+    return any;
+}
+
+// all iterations of one phase; returns the number of passes executed (>= the reference's count: see the header)
+template <int PHASE, int T>
+__device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int iters, unsigned long long& seq, int& passIndex, int2 (&pre)[kStripU])
+{
+    __shared__ unsigned long long s_word;
+    unsigned long long* done = P.done + size_t(PHASE) * P.doneStride;
+    int it = 0;
+    for (; it < iters; ++it)
+    {
+        if (it >= 2)
+        {
+            // early-out (Solver.cpp:189 / :210), two iterations late: by now every CTA has reported iteration it-2
+            if (threadIdx.x == 0)
+            {
+                unsigned long long v;
+                while (((v = flag_peek(&done[it - 2])) & 0xffffffffull) != unsigned(P.S)) {}
+                s_word = v;
+            }
+            __syncthreads();
+            const bool productive = (s_word >> 32) != 0;
+            __syncthreads();
+            if (!productive) break;
+        }
+        ++seq;
+        ++passIndex;
+        const bool mine = run_pass<PHASE, T>(P, s, it, seq, passIndex, pre);
+        const int any = __syncthreads_or(mine ? 1 : 0);
+        if (threadIdx.x == 0) atomicAdd(&done[it], 1ull | (any ? (1ull << 32) : 0ull));
+    }
+    return it;
+}
+
+template <int T>
+__global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
+{
+    extern __shared__ __align__(128) unsigned char stripSmem[];
+    __shared__ int2 s_bins[2 * kStripBins];
+    __shared__ int2 s_tmp[2 * kStripBins];
+    __shared__ int s_count[2];
+    __shared__ int s_n[2];
+    __shared__ unsigned long long s_mbar;
+
+    StripCta s;
+    s.s_rows = reinterpret_cast<float4*>(stripSmem);
+    s.s_cut = s.s_rows + P.rowCap;
+    s.s_last = reinterpret_cast<int*>(s.s_cut + P.cutCap);
+    s.s_work = s.s_last + P.rowCap;
+    s.s_listL = s.s_work + P.workCap;
+    s.s_listR = s.s_listL + P.cutCap;
+    s.s_listN = s.s_listR + P.cutCap;
+    s.s_bins = s_bins;
+    s.s_count = s_count;
+    const int k = blockIdx.x, S = P.S;
+    s.k = k;
+    s.row0 = P.cuts[k];
+    s.nRows = P.cuts[k + 1] - s.row0;
+    const int* bRs = P.bStart;
+    const int* bLs = P.bStart + S + 1;
+    s.nR = bRs[k + 1] - bRs[k];
+    s.nL = bLs[k + 1] - bLs[k];
+    s.nLn = k + 1 < S ? bLs[k + 2] - bLs[k + 1] : 0;
+    s.parity = 0;
+    s.wakePasses = 0;
+    s.active[0] = s.active[1] = 0u;
+
+    // the strip's rows: one bulk copy
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&s_mbar, 1);
+        mbar_fence_init();
+        s_count[0] = s_count[1] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned bytes = unsigned(s.nRows) * 16u;
+        mbar_expect_tx(&s_mbar, bytes);
+        if (bytes) bulk_g2s(s.s_rows, P.rows[0] + s.row0, bytes, &s_mbar);
+    }
+    // bin tables of the strip's two classes, empty bins dropped
+    if (threadIdx.x < 2 * kStripBins)
+    {
+        const int cls = threadIdx.x < kStripBins ? k : S + k;
+        const int c = threadIdx.x & (kStripBins - 1);
+        s_tmp[threadIdx.x] = P.binRange[cls * kStripBins + c];   // the table has 2S classes; class 2S-1 is always empty
+    }
+    for (int i = threadIdx.x; i < s.nL; i += T) s.s_listL[i] = P.bL[bLs[k] + i] - s.row0;
+    for (int i = threadIdx.x; i < s.nR; i += T) s.s_listR[i] = P.bR[bRs[k] + i] - s.row0;
+    for (int i = threadIdx.x; i < s.nLn; i += T) s.s_listN[i] = P.bL[bLs[k + 1] + i];
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        int n = 0;
+        for (int c = 0; c < kStripBins; ++c)
+            if (s_tmp[c].y > s_tmp[c].x) s_bins[n++] = s_tmp[c];
+        s_n[0] = n;
+        if (k + 1 < S)
+            for (int c = 0; c < kStripBins; ++c)
+                if (s_tmp[kStripBins + c].y > s_tmp[kStripBins + c].x) s_bins[n++] = s_tmp[kStripBins + c];
+        s_n[1] = n - s_n[0];
+    }
+    __syncthreads();
+    s.nInt = s_n[0];
+    s.nCut = s_n[1];
+    mbar_wait(&s_mbar, 0);
+    for (int i = threadIdx.x; i < s.nRows; i += T) s.s_last[i] = __float_as_int(s.s_rows[i].w);
+    __syncthreads();
+
+    unsigned long long seq = 0;
+    int passIndex = 0;
+    int2 pre[kStripU];
+#pragma unroll
+    for (int u = 0; u < kStripU; ++u) pre[u] = make_int2(-1, -1);
+
+    // warm start
+    ++seq;
+    run_pass<-1, T>(P, s, 0, seq, passIndex, pre);
+    if (s.nInt + s.nCut > 0) prefetch_idx<T>(P, s_bins[0], pre);
+
+    const int ranI = run_phase<0, T>(P, s, P.contactIters, seq, passIndex, pre);
+
+    // velocity rows back, displacement rows in
+    __syncthreads();
+    if (threadIdx.x == 0 && s.nRows > 0)
+    {
+        bulk_s2g_fence();
+        bulk_s2g(P.rows[0] + s.row0, s.s_rows, unsigned(s.nRows) * 16u);
+        bulk_commit_wait_all();
+    }
+    int ranD = 0;
+    if (P.penetrationIters > 0)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const unsigned bytes = unsigned(s.nRows) * 16u;
+            mbar_expect_tx(&s_mbar, bytes);
+            if (bytes) bulk_g2s(s.s_rows, P.rows[1] + s.row0, bytes, &s_mbar);
+        }
+        mbar_wait(&s_mbar, 1);
+        for (int i = threadIdx.x; i < s.nRows; i += T) s.s_last[i] = __float_as_int(s.s_rows[i].w);
+        __syncthreads();
+        ranD = run_phase<1, T>(P, s, P.penetrationIters, seq, passIndex, pre);
+        __syncthreads();
+        if (threadIdx.x == 0 && s.nRows > 0)
+        {
+            bulk_s2g_fence();
+            bulk_s2g(P.rows[1] + s.row0, s.s_rows, unsigned(s.nRows) * 16u);
+            bulk_commit_wait_all();
+        }
+    }
+
+    for (int phase = 0; phase < 2; ++phase)
+    {
+        unsigned v = s.active[phase];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.activeTotal[phase], static_cast<unsigned long long>(v));
+    }
+    if (threadIdx.x == 0 && s.wakePasses) atomicAdd(&P.result[2], s.wakePasses);
+    // iteration counts as the reference loop reports them: up to and including the first non-productive iteration
+    if (k == 0 && threadIdx.x == 0)
+    {
+        const int executed[2] = { ranI, ranD };
+        for (int phase = 0; phase < 2; ++phase)
+        {
+            const unsigned long long* done = P.done + size_t(phase) * P.doneStride;
+            int ran = executed[phase];
+            for (int it = 0; it < executed[phase]; ++it)
+            {
+                unsigned long long v;
+                while (((v = flag_peek(&done[it])) & 0xffffffffull) != unsigned(S)) {}
+                if ((v >> 32) == 0)
+                {
+                    ran = it + 1;
+                    break;
+                }
+            }
+            P.result[phase] = ran;
+        }
+    }
+}
+
+// launch the strip kernel on the context's stream (rows are prepared, records refreshed)
+int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, float4* rowsVel, float4* rowsDisp)
+{
+    StripPlan& sp = c->strip;
+    const int S = sp.strips, I = cfg->contactIterationsCount, D = cfg->penetrationIterationsCount;
+    const int stride = std::max(I, D) + 2;
+    const size_t syncWords = size_t(2) * S + 2 * size_t(stride) + 8;
+    PHYX_TRY(sp.sync.reserve(syncWords * 8));
+    const size_t wordCount = std::max<size_t>(size_t(2) * S * sp.numStatics, 1);
+    PHYX_TRY(sp.words.reserve(wordCount * 8));
+    PHYX_CUDA(cudaMemsetAsync(sp.sync.ptr, 0, syncWords * 8, c->stream));
+    PHYX_CUDA(cudaMemsetAsync(sp.words.ptr, 0, wordCount * 8, c->stream));
+
+    StripParams P;
+    memset(&P, 0, sizeof(P));
+    P.rows[0] = rowsVel;
+    P.rows[1] = rowsDisp;
+    P.pairQ = c->pairQ.as<float4>();
+    P.pairIdx = c->pairIdx.as<int2>();
+    P.accNF = c->accNF.as<float2>();
+    P.accD = c->accD.as<float>();
+    P.binRange = sp.binRange.as<int2>();
+    P.cuts = sp.cuts.as<int>();
+    P.bR = sp.bR.as<int>();
+    P.bL = sp.bL.as<int>();
+    P.bStart = sp.bStart.as<int>();
+    P.staticOrd = sp.staticOrd.as<int>();
+    P.staticWords = sp.words.as<unsigned long long>();
+    P.numStatics = sp.numStatics;
+    P.processed = c->processed.as<int>();
+    unsigned long long* sync = sp.sync.as<unsigned long long>();
+    P.flagA = sync;
+    P.flagB = sync + S;
+    P.done = sync + 2 * S;
+    P.doneStride = stride;
+    P.S = S;
+    P.contactIters = I;
+    P.penetrationIters = D;
+    P.rowCap = (sp.maxStripRows + 8) & ~7;
+    P.cutCap = (sp.maxCutRows + 8) & ~7;
+    P.workCap = (sp.maxBin + 8) & ~7;
+    P.result = reinterpret_cast<int*>(c->solveFlags.as<char>() + 32);
+    P.activeTotal = reinterpret_cast<unsigned long long*>(c->solveFlags.as<char>() + 48);
+    P.variant = getenv("PHYX_STRIP_VARIANT") ? atoi(getenv("PHYX_STRIP_VARIANT")) : 0;
+    P.trace = nullptr;
+    if (sp.tracePasses > 0)
+    {
+        PHYX_TRY(sp.trace.reserve(size_t(S) * sp.tracePasses * 8 * 8));
+        PHYX_CUDA(cudaMemsetAsync(sp.trace.ptr, 0, size_t(S) * sp.tracePasses * 8 * 8, c->stream));
+        P.trace = sp.trace.as<unsigned long long>();
+        P.tracePasses = sp.tracePasses;
+    }
+    const size_t smem = strip_smem_bytes(P.rowCap, P.cutCap, P.workCap);
+    if (!sp.attributeSet)   // per device
+    {
+        PHYX_CUDA(cudaFuncSetAttribute(k_solve_strips<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStripSmemLimit)));
+        PHYX_CUDA(cudaFuncSetAttribute(k_solve_strips<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStripSmemLimit2)));
+        sp.attributeSet = true;
+    }
+    // every CTA waits for its neighbours: all S must be resident at once, which the cooperative launch guarantees (or refuses)
+    void* args[] = { &P };
+    if (S > c->numSMs)
+        PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_strips<256>, dim3(S), dim3(256), args, smem, c->stream));
+    else
+        PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_strips<512>, dim3(S), dim3(512), args, smem, c->stream));
+    c->launches++;
+    return PHYX_B200_OK;
+}
+
+} // namespace phyx

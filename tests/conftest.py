@@ -51,3 +51,24 @@ def ref():
     if not refpy.available("strict"):
         pytest.skip("oracle/_ref not built (make -C oracle ref needs /root/reference)")
     return refpy
+
+
+def oracle_on_device_schedule(ctx, oracle, bodies, joints, contact_points, iters=(20, 20)):
+    """The oracle's sequential sweep over the slot order the device used for its last colour-mode solve.  With the
+    strip layout every interior class keeps its own lastIteration word per static body (as the partitioned solve does
+    per rank): the sweep runs on the equivalent problem in which class k > 0 references its own copy of each static
+    body (phyx_b200.partition.sequential_equivalent).  Returns (bodies, joints, iterations run, slots, levels)."""
+    from phyx_b200 import partition
+
+    slots, levels = ctx.get_schedule()
+    plan = ctx.strip_plan()
+    n = bodies.shape[0]
+    if plan["strips"] > 1:
+        b2, j2 = partition.sequential_equivalent(bodies, joints, slots, plan["class_slot_start"], plan["strips"])
+        ob, oj, ran = oracle.solve_scheduled(b2, j2, contact_points, slots, levels, iters=iters)
+        oj = oj.copy()
+        oj["body1Index"], oj["body2Index"] = joints["body1Index"], joints["body2Index"]
+        ob = ob[:n]
+    else:
+        ob, oj, ran = oracle.solve_scheduled(bodies, joints, contact_points, slots, levels, iters=iters)
+    return ob, oj, ran, slots, levels

@@ -5,7 +5,7 @@ reference's own stage function leaves behind (order included)."""
 import numpy as np
 import pytest
 
-from conftest import assert_records_equal
+from conftest import assert_records_equal, oracle_on_device_schedule
 from phyx_b200 import capi, scenes, types as T, world
 
 pytestmark = pytest.mark.gpu
@@ -145,7 +145,7 @@ def test_incremental_colouring_stays_valid_and_exact(oracle, scene, steps):
         slots, levels = ctx.get_schedule()
         check_schedule(slots, levels, j0, b0)
         if step % 7 == 0 or step == steps - 1:
-            ob, oj, ran = oracle.solve_scheduled(b0, j0, cp, slots, levels)
+            ob, oj, ran, _, _ = oracle_on_device_schedule(ctx, oracle, b0, j0, cp)
             assert (st.contactIterationsRun, st.penetrationIterationsRun) == ran
             assert_records_equal(ctx.download_joints(), oj, what=f"step {step} joints")
             assert_records_equal(ctx.download_bodies(), ob, VEL_FIELDS, what=f"step {step} bodies")
@@ -161,6 +161,7 @@ def test_unit_colouring_is_priority_first_fit_over_manifolds():
 
     w = world.World(scenes.make("pyramid_1k"))
     ctx = w.context()
+    ctx.solve_tuning(strips=-1)   # colour-major layout: level index = colour
     ctx.upload_bodies(w.bodies())
     ctx.integrate_velocity(scenes.DT, scenes.GRAVITY)
     ctx.update_broadphase()
