@@ -278,6 +278,8 @@ int colour_schedule_build(phyx_b200_ctx* c)
 static int colour_joints_build(phyx_b200_ctx* c, bool* staticsChanged)
 {
     const bool incremental = false;
+    c->strip.valid = false;
+    c->hostLevelsStale = false;
 
     const int nj = c->jointCount, nb = c->bodyCount;
     c->hostSlots.clear();
@@ -829,6 +831,8 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
         }
         if (res[1])
         {
+            c->strip.valid = false;   // the layout was built on colours that do not exist
+            c->hostLevelsStale = false;
             set_error("colouring needs more than %d colours", kMaxColours);
             return PHYX_B200_ERR_CAPACITY;
         }

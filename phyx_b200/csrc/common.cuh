@@ -100,7 +100,7 @@ struct StripPlan
     int maxStripRows = 0, maxCutRows = 0, maxBin = 0, numStatics = 0, colours = 0, cutManifolds = 0, manifolds = 0;
     bool attributeSet = false;
     int rejected = 0;          // why the last layout attempt was not usable (bit mask, see strips.cu), 0 = usable
-    DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, staticOrd, header, words, sync, hist, trace;
+    DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, staticOrd, header, words, sync, hist, trace, pairTest;
     int tracePasses = 0;       // developer aid (phyx_b200_strip_trace): passes of the next solves to time-stamp per CTA
 };
 

@@ -264,6 +264,8 @@ int schedule_build(phyx_b200_ctx* c, const phyx_contact_joint* hostJoints, int n
         c->colourStateValid = false;
     }
     c->hostSlotsStale = false;
+    c->hostLevelsStale = false;
+    c->strip.valid = false;   // host-built schedules are colour-major / replay levels
     c->colourRounds = 0;
 
     // static flags from the resident body parameters

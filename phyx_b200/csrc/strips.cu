@@ -44,7 +44,6 @@
 #include "tma.cuh"
 
 #include <algorithm>
-#include <stdlib.h>
 
 namespace phyx
 {
@@ -111,7 +110,7 @@ __global__ void __launch_bounds__(kBlock) k_strip_hist_rows(int nb, const unsign
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
     const unsigned body = order ? order[r] : unsigned(r);
-    if (!bodyStatic[body]) hist[r] += 12;
+    if (!bodyStatic[body]) hist[r] += 3;
 }
 
 // cuts[q] = first row with at least q/S of the manifolds before it
@@ -252,7 +251,7 @@ __global__ void __launch_bounds__(kBlock) k_strip_starts(int nb, int S, const in
 __global__ void __launch_bounds__(kBlock) k_strip_place(int M, int S, const uint2* __restrict__ sorted, const int2* __restrict__ manBody,
     const int* __restrict__ manCount, const float4* __restrict__ contactPoints, const int* __restrict__ rowOf, const unsigned char* __restrict__ bodyStatic,
     const int* __restrict__ cuts, const int* __restrict__ prefixR, const int* __restrict__ prefixL, const int* __restrict__ bStart,
-    int* __restrict__ slotJoint, int2* __restrict__ pairIdx, int2* __restrict__ binRange)
+    int* __restrict__ slotJoint, int2* __restrict__ pairIdx, unsigned* __restrict__ pairTest, int2* __restrict__ binRange)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= M) return;
@@ -287,6 +286,187 @@ __global__ void __launch_bounds__(kBlock) k_strip_place(int M, int S, const uint
         y = r2 < split ? prefixR[r2] - bStart[k] : nR + prefixL[r2] - bStart[S + 1 + k + 1];
     }
     pairIdx[p] = make_int2(x, y | (hasB ? kPairHasB : 0));
+    // the skip test's view: two 16-bit local rows, 0xffff = static body (its lastIteration lives in a global word)
+    pairTest[p] = (st1 ? 0xffffu : unsigned(x)) | ((st2 ? 0xffffu : unsigned(y)) << 16);
+}
+
+// Cut sets get their own colouring.  The global colours (7-8 on a pile) leave a cut set of ~1000 manifolds in as many
+// bins, and every bin costs the strip kernel two block barriers and a latency chain whatever it holds; within a cut set
+// a body meets two or three manifolds, so first fit needs 3-4 colours.  One CTA per cut set: Jones-Plassmann rounds in
+// shared memory with the slot position as priority (= sequential first fit in slot order: deterministic), then a stable
+// counting sort of the set's slots by the new colour.  Sets too large for the shared-memory tables keep their bins.
+constexpr int kRecolourThreads = 256;
+constexpr int kRecolourItems = 16;                                  // manifolds per thread
+constexpr int kRecolourCap = kRecolourThreads * kRecolourItems;     // manifolds per cut set
+constexpr int kRecolourRows = 4096;                                 // rows per cut set
+
+__global__ void __launch_bounds__(kRecolourThreads) k_strip_recolour_cuts(int S, int* __restrict__ slotJoint, int2* __restrict__ pairIdx,
+    unsigned* __restrict__ pairTest, int2* __restrict__ binRange)
+{
+    __shared__ int s_claim[kRecolourRows];
+    __shared__ unsigned s_used[kRecolourRows];
+    __shared__ signed char s_col[kRecolourCap];
+    __shared__ int s_lo, s_hi, s_rows;
+    __shared__ int s_count[32], s_base[32], s_warp[kRecolourThreads / 32];
+    const int cls = S + blockIdx.x;
+    int2* bins = binRange + size_t(cls) * kStripBins;
+    if (threadIdx.x == 0)
+    {
+        int lo = 0x7fffffff, hi = 0;
+        for (int c = 0; c < kStripBins; ++c)
+            if (bins[c].y > bins[c].x)
+            {
+                lo = min(lo, bins[c].x);
+                hi = max(hi, bins[c].y);
+            }
+        s_lo = lo;
+        s_hi = hi;
+        s_rows = 0;
+    }
+    if (threadIdx.x < 32) s_count[threadIdx.x] = 0;
+    __syncthreads();
+    const int lo = s_lo, n = s_hi - s_lo;
+    if (n <= 0 || n > kRecolourCap) return;
+    unsigned t[kRecolourItems];
+    int maxRow = 0;
+#pragma unroll
+    for (int k = 0; k < kRecolourItems; ++k)
+    {
+        const int i = int(threadIdx.x) * kRecolourItems + k;   // a thread owns consecutive slots: the final ranking is a plain scan
+        t[k] = i < n ? pairTest[lo + i] : 0u;
+        if (i < n)
+        {
+            maxRow = max(maxRow, int(max(t[k] & 0xffffu, t[k] >> 16)));
+            s_col[i] = -1;
+        }
+    }
+    atomicMax(&s_rows, maxRow + 1);
+    __syncthreads();
+    const int rows = s_rows;
+    if (rows > kRecolourRows) return;   // (cut manifolds have two dynamic bodies: no 0xffff entries)
+    for (int r = threadIdx.x; r < rows; r += kRecolourThreads) s_used[r] = 0u;
+    for (;;)
+    {
+        for (int r = threadIdx.x; r < rows; r += kRecolourThreads) s_claim[r] = 0x7fffffff;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kRecolourItems; ++k)
+        {
+            const int i = int(threadIdx.x) * kRecolourItems + k;
+            if (i < n && s_col[i] < 0)
+            {
+                atomicMin(&s_claim[t[k] & 0xffffu], i);
+                atomicMin(&s_claim[t[k] >> 16], i);
+            }
+        }
+        __syncthreads();
+        bool left = false;
+#pragma unroll
+        for (int k = 0; k < kRecolourItems; ++k)
+        {
+            const int i = int(threadIdx.x) * kRecolourItems + k;
+            if (i < n && s_col[i] < 0)
+            {
+                const int ra = t[k] & 0xffffu, rb = t[k] >> 16;
+                if (s_claim[ra] == i && s_claim[rb] == i)
+                {
+                    const unsigned m = s_used[ra] | s_used[rb];
+                    const int c = m == 0xffffffffu ? 31 : __ffs(~m) - 1;   // (32 manifolds on one body of a cut set: give up on exactness of the colouring? no: see below)
+                    s_col[i] = (signed char)c;
+                    s_used[ra] |= 1u << c;
+                    s_used[rb] |= 1u << c;
+                    if (m == 0xffffffffu) s_lo = -1;   // more than 32 colours: keep the global bins
+                }
+                else
+                    left = true;
+            }
+        }
+        if (!__syncthreads_or(left ? 1 : 0)) break;
+    }
+    if (s_lo < 0) return;
+    // stable counting sort by colour: per colour an exclusive scan of "has this colour" in slot order
+#pragma unroll
+    for (int k = 0; k < kRecolourItems; ++k)
+    {
+        const int i = int(threadIdx.x) * kRecolourItems + k;
+        if (i < n) atomicAdd(&s_count[s_col[i]], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        int run = 0;
+        for (int c = 0; c < 32; ++c)
+        {
+            s_base[c] = run;
+            run += s_count[c];
+        }
+    }
+    __syncthreads();
+    int dest[kRecolourItems];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = 0; c < 32; ++c)
+    {
+        if (s_count[c] == 0) continue;   // uniform
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < kRecolourItems; ++k)
+        {
+            const int i = int(threadIdx.x) * kRecolourItems + k;
+            if (i < n && s_col[i] == c) ++mine;
+        }
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int before = inc - mine;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        __syncthreads();
+        int at = s_base[c] + before;
+#pragma unroll
+        for (int k = 0; k < kRecolourItems; ++k)
+        {
+            const int i = int(threadIdx.x) * kRecolourItems + k;
+            if (i < n && s_col[i] == c) dest[k] = at++;
+        }
+    }
+    // permute the set's slots
+    int ja[kRecolourItems], jb2[kRecolourItems];
+    int2 idx[kRecolourItems];
+#pragma unroll
+    for (int k = 0; k < kRecolourItems; ++k)
+    {
+        const int i = int(threadIdx.x) * kRecolourItems + k;
+        if (i < n)
+        {
+            ja[k] = slotJoint[2 * (lo + i)];
+            jb2[k] = slotJoint[2 * (lo + i) + 1];
+            idx[k] = pairIdx[lo + i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kRecolourItems; ++k)
+    {
+        const int i = int(threadIdx.x) * kRecolourItems + k;
+        if (i < n)
+        {
+            const int d = lo + dest[k];
+            slotJoint[2 * d] = ja[k];
+            slotJoint[2 * d + 1] = jb2[k];
+            pairIdx[d] = idx[k];
+            pairTest[d] = t[k];
+        }
+    }
+    if (threadIdx.x < kStripBins)
+    {
+        const int c = threadIdx.x;
+        bins[c] = (c < 32 && s_count[c] > 0) ? make_int2(lo + s_base[c], lo + s_base[c] + s_count[c]) : make_int2(0, 0);
+    }
 }
 
 __global__ void __launch_bounds__(kBlock) k_strip_maxbin(int bins, const int2* __restrict__ binRange, int* __restrict__ header)
@@ -310,7 +490,7 @@ int strip_choose(const phyx_b200_ctx* c, int manifolds, int bodies)
 
 static size_t strip_smem_bytes(int rowCap, int cutCap, int workCap)
 {
-    return size_t(rowCap) * 20 + size_t(cutCap) * 16 + size_t(workCap) * 4 + size_t(cutCap) * 4 * 3;
+    return size_t(rowCap) * 16 + size_t(cutCap) * 16 + size_t(workCap) * 2 + size_t(cutCap) * (2 + 2 + 4);
 }
 constexpr size_t kStripSmemLimit = 227 * 1024 - 4096;   // dynamic part: the opt-in maximum minus the kernel's static tables
 constexpr size_t kStripSmemLimit2 = 113 * 1024 - 4096;  // two CTAs per SM
@@ -385,9 +565,15 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
     const size_t maxSlots = 2 * size_t(M) + 64;
     PHYX_TRY(c->slotJoint.reserve(maxSlots * sizeof(int)));
     PHYX_TRY(c->pairIdx.reserve((size_t(M) + 64) * sizeof(int2)));
+    PHYX_TRY(sp.pairTest.reserve((size_t(M) + 64) * sizeof(unsigned)));
     k_strip_place<<<grid, kBlock, 0, c->stream>>>(M, S, sorted, c->manBody.as<int2>(), c->manCount.as<int>(), c->contactPoints.as<float4>(), rowOf,
         c->bodyStatic.as<unsigned char>(), sp.cuts.as<int>(), sp.prefixR.as<int>(), sp.prefixL.as<int>(), sp.bStart.as<int>(), c->slotJoint.as<int>(),
-        c->pairIdx.as<int2>(), sp.binRange.as<int2>());
+        c->pairIdx.as<int2>(), sp.pairTest.as<unsigned>(), sp.binRange.as<int2>());
+    if (S > 1)
+    {
+        k_strip_recolour_cuts<<<S - 1, kRecolourThreads, 0, c->stream>>>(S, c->slotJoint.as<int>(), c->pairIdx.as<int2>(), sp.pairTest.as<unsigned>(), sp.binRange.as<int2>());
+        c->launches++;
+    }
     k_strip_maxbin<<<(bins + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(bins, sp.binRange.as<int2>(), header);
     c->launches += 2;
     PHYX_CUDA(cudaGetLastError());
@@ -408,6 +594,7 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
     if (sp.manifolds == 0) rejected |= kRejectEmpty;
     if (strip_smem_bytes(sp.maxStripRows + 9, sp.maxCutRows + 9, sp.maxBin + 9) > (S > c->numSMs ? kStripSmemLimit2 : kStripSmemLimit)) rejected |= kRejectSmem;
     if (size_t(sp.numStatics) * size_t(S) * 16 > (size_t(256) << 20)) rejected |= kRejectStatics;
+    if (sp.maxStripRows > 65000 || sp.maxCutRows > 65000 || sp.maxBin > 65000) rejected |= kRejectSmem;
     sp.rejected = rejected;
     if (rejected) return PHYX_B200_OK;
     sp.valid = true;
@@ -446,7 +633,7 @@ int strip_host_levels(phyx_b200_ctx* c, std::vector<int>* classStart)
 void strip_release(phyx_b200_ctx* c)
 {
     StripPlan& sp = c->strip;
-    DevBuf* bufs[] = { &sp.cuts, &sp.binRange, &sp.flags, &sp.prefixR, &sp.prefixL, &sp.bR, &sp.bL, &sp.bStart, &sp.staticOrd, &sp.header, &sp.words, &sp.sync, &sp.hist, &sp.trace };
+    DevBuf* bufs[] = { &sp.cuts, &sp.binRange, &sp.flags, &sp.prefixR, &sp.prefixL, &sp.bR, &sp.bL, &sp.bStart, &sp.staticOrd, &sp.header, &sp.words, &sp.sync, &sp.hist, &sp.trace, &sp.pairTest };
     for (DevBuf* b : bufs) b->release();
     sp.valid = false;
 }
@@ -458,6 +645,7 @@ struct StripParams
     float4* rows[2];                 // solver rows: impulse (velocity) and displacement arrays
     const float4* pairQ;             // PairRecord per manifold slot
     const int2* pairIdx;             // {row1, row2 | hasB}: rows local to the class's shared-memory buffer, or global | static bit
+    const unsigned* pairTest;        // row1 | row2 << 16 (local; 0xffff = static body): all the skip test needs
     float2* accNF;                   // per joint slot
     float* accD;
     const int2* binRange;            // [2S][kStripBins] manifold slot ranges
@@ -479,7 +667,6 @@ struct StripParams
     unsigned long long* activeTotal; // [2]
     unsigned long long* trace;       // developer aid (phyx_b200_strip_trace): [S][tracePasses][8] globaltimer stamps, or null
     int tracePasses;
-    int variant;   // TEMPORARY timing experiments
 };
 
 __device__ __forceinline__ void flag_release(unsigned long long* flag, unsigned long long value)
@@ -525,12 +712,11 @@ __device__ __forceinline__ void trace_mark(const StripParams& P, int k, int pass
 struct StripCta
 {
     float4* s_rows;     // the strip's rows
-    int* s_last;        // mirror of s_rows[].w (lastIteration): the skip test reads it without the 8-way bank conflicts of a stride-16 access
     float4* s_cut;      // rows of the cut set
-    int* s_work;        // worklist: positions in the bin
-    int* s_listL;       // own left-boundary rows (local)
-    int* s_listR;       // own right-boundary rows (local)
-    int* s_listN;       // the right neighbour's left-boundary rows (global row numbers)
+    unsigned short* s_work;    // worklist: positions in the bin
+    unsigned short* s_listL;   // own left-boundary rows (local)
+    unsigned short* s_listR;   // own right-boundary rows (local)
+    int* s_listN;              // the right neighbour's left-boundary rows (global row numbers)
     int2* s_bins;       // [nInt interior bins][nCut cut bins]
     int* s_count;       // [2] worklist lengths (alternating)
     int k, row0, nRows, nL, nR, nLn, nInt, nCut;
@@ -584,14 +770,14 @@ __device__ __forceinline__ void prestep_bin(const StripParams& P, float4* rowsS,
 }
 
 template <int T>
-__device__ __forceinline__ void prefetch_idx(const StripParams& P, int2 bin, int2 (&pre)[kStripU])
+__device__ __forceinline__ void prefetch_idx(const StripParams& P, int2 bin, unsigned (&pre)[kStripU])
 {
     const int n = bin.y - bin.x;
 #pragma unroll
     for (int u = 0; u < kStripU; ++u)
     {
         const int i = int(threadIdx.x) + u * T;
-        pre[u] = i < n ? __ldg(&P.pairIdx[bin.x + i]) : make_int2(-1, -1);
+        pre[u] = i < n ? __ldg(&P.pairTest[bin.x + i]) : 0xffffffffu;
     }
 }
 
@@ -601,8 +787,8 @@ __device__ __forceinline__ void prefetch_idx(const StripParams& P, int2 bin, int
 // nobody owns (index words of static bodies are redirected there for the speculative lastIteration read).  Returns
 // "this thread saw a productive joint".
 template <int PHASE, int T>
-__device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, float4* rowsS, int* lastS, int dummyRow, const float4* __restrict__ rowsG, unsigned long long* words,
-    int2 bin, int2 next, int it, int tick, int2 (&pre)[kStripU])
+__device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, float4* rowsS, int dummyRow, const float4* __restrict__ rowsG, unsigned long long* words,
+    int2 bin, int2 next, int it, int tick, unsigned (&pre)[kStripU])
 {
     const int n = bin.y - bin.x;
     const int lane = threadIdx.x & 31;
@@ -618,55 +804,50 @@ __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, flo
         // (whose lastIteration lives in a global word) are fixed up afterwards.
         if (firstPass)
         {
+            // kStripU candidates per thread; slots beyond the bin are skipped as a block (n is uniform)
             bool active[kStripU];
-            bool anyStatic = false;
-            int la[kStripU], lb[kStripU];
-#pragma unroll
-            for (int u = 0; u < kStripU; ++u)
-            {
-                const int2 idx = pre[u];
-                const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit;
-                anyStatic |= (st1 || st2) && idx.x >= 0;
-                const int ra = st1 || idx.x < 0 ? dummyRow : (idx.x & kBodyMask), rb = st2 || idx.x < 0 ? dummyRow : (idx.y & kBodyMask);
-                la[u] = (P.variant & 2) ? -1 : lastS ? lastS[ra] : __float_as_int(rowsS[ra].w);
-                lb[u] = (P.variant & 2) ? -1 : lastS ? lastS[rb] : __float_as_int(rowsS[rb].w);
-            }
-            if (anyStatic && !(P.variant & 1))
-            {
-#pragma unroll
-                for (int u = 0; u < kStripU; ++u)
-                {
-                    const int2 idx = pre[u];
-                    if (idx.x < 0) continue;
-                    const unsigned pos = unsigned(2 * (bin.x + int(threadIdx.x) + u * T));
-                    if (idx.x & kStaticBit) la[u] = static_visible_last(&words[P.staticOrd[idx.x & kBodyMask]], it, pos);
-                    if (idx.y & kStaticBit) lb[u] = static_visible_last(&words[P.staticOrd[idx.y & kBodyMask]], it, pos);
-                }
-            }
             unsigned m[kStripU];
             int warpTotal = 0;
 #pragma unroll
-            for (int u = 0; u < kStripU; ++u) active[u] = pre[u].x >= 0 && ((la[u] > it - 2) || (lb[u] > it - 2));
-            // the index words are used up: fetch those of the next bin now, a whole bin pass ahead of their use
-            if (!(P.variant & 4)) prefetch_idx<T>(P, next, pre);
-#pragma unroll
             for (int u = 0; u < kStripU; ++u)
             {
-                m[u] = __ballot_sync(0xffffffffu, active[u]);
-                warpTotal += __popc(m[u]);
+                active[u] = false;
+                m[u] = 0u;
+                if (u * T < n)
+                {
+                    const unsigned t = pre[u];
+                    const int ra = min(int(t & 0xffffu), dummyRow), rb = min(int(t >> 16), dummyRow);
+                    int la = __float_as_int(rowsS[ra].w), lb = __float_as_int(rowsS[rb].w);
+                    if ((t & 0xffffu) == 0xffffu || (t >> 16) == 0xffffu)   // rare: a static body, or a slot beyond the bin
+                    {
+                        const int i = int(threadIdx.x) + u * T;
+                        la = lb = -(1 << 30);
+                        if (i < n)
+                        {
+                            const int2 idx = __ldg(&P.pairIdx[bin.x + i]);
+                            const unsigned pos = unsigned(2 * (bin.x + i));
+                            la = (idx.x & kStaticBit) ? static_visible_last(&words[P.staticOrd[idx.x & kBodyMask]], it, pos) : __float_as_int(rowsS[idx.x & kBodyMask].w);
+                            lb = (idx.y & kStaticBit) ? static_visible_last(&words[P.staticOrd[idx.y & kBodyMask]], it, pos) : __float_as_int(rowsS[idx.y & kBodyMask].w);
+                        }
+                    }
+                    active[u] = (la > it - 2) || (lb > it - 2);
+                    m[u] = __ballot_sync(0xffffffffu, active[u]);
+                    warpTotal += __popc(m[u]);
+                }
             }
+            // the index words are used up: fetch those of the next bin now, a whole bin pass ahead of their use
+            prefetch_idx<T>(P, next, pre);
             if (warpTotal)
             {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(count, warpTotal);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 // candidates of this warp in (u, lane) order
-                int before = 0;
 #pragma unroll
                 for (int u = 0; u < kStripU; ++u)
                 {
-                    if (active[u]) s.s_work[base + before + __popc(m[u] & below)] = int(threadIdx.x) + u * T;
-                    before += __popc(m[u]);
+                    if (active[u]) s.s_work[base + __popc(m[u] & below)] = (unsigned short)(int(threadIdx.x) + u * T);
+                    base += __popc(m[u]);
                 }
             }
         }
@@ -697,7 +878,7 @@ __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, flo
                 int base = 0;
                 if (lane == 0) base = atomicAdd(count, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (active) s.s_work[base + __popc(m & below)] = i;
+                if (active) s.s_work[base + __popc(m & below)] = (unsigned short)i;
             }
         }
         __syncthreads();
@@ -706,7 +887,8 @@ __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, flo
         if (threadIdx.x == 0) s.s_count[s.parity ^ 1] = 0;  // the next bin pass counts there
         s.parity ^= 1;
 
-        // ---- step 2: relax the worklist, one entry per thread and round
+        // ---- step 2: relax the worklist, one entry per thread and round.  Consecutive entries (neighbouring records) go to
+        // consecutive lanes: dealing them across the warps instead was measured 3x slower (DRAM locality of the record fetch)
         bool wake = false;
         for (int w = threadIdx.x; w < total; w += T)
         {
@@ -759,7 +941,6 @@ __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, flo
             {
                 w1.w = __int_as_float(productive ? it : last1);
                 rowsS[r1] = w1;
-                if (lastS) lastS[r1] = productive ? it : last1;
             }
             else if (productive)
                 wake |= static_mark(&words[P.staticOrd[r1]], it, markPos, nullptr);
@@ -767,7 +948,6 @@ __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, flo
             {
                 w2.w = __int_as_float(productive ? it : last2);
                 rowsS[r2] = w2;
-                if (lastS) lastS[r2] = productive ? it : last2;
             }
             else if (productive)
                 wake |= static_mark(&words[P.staticOrd[r2]], it, markPos, nullptr);
@@ -790,7 +970,7 @@ __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, flo
 
 // One pass over the strip's classes.  MODE -1: warm start, 0: impulse iteration `it`, 1: displacement iteration `it`.
 template <int MODE, int T>
-__device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int it, unsigned long long seq, int passIndex, int2 (&pre)[kStripU])
+__device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int it, unsigned long long seq, int passIndex, unsigned (&pre)[kStripU])
 {
     constexpr int PHASE = MODE == 1 ? 1 : 0;
     float4* rowsG = P.rows[PHASE];
@@ -805,7 +985,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
         if (MODE < 0)
             prestep_bin<T>(P, s.s_rows, rowsG, s.s_bins[b]);
         else
-            any |= solve_bin<PHASE, T>(P, s, s.s_rows, s.s_last, P.rowCap - 1, rowsG, words, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, passIndex * 256 + b + 1, pre);
+            any |= solve_bin<PHASE, T>(P, s, s.s_rows, P.rowCap - 1, rowsG, words, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, passIndex * 256 + b + 1, pre);
     }
     trace_mark(P, k, passIndex, 1);
     if (P.trace && threadIdx.x == 0 && passIndex < P.tracePasses)
@@ -835,14 +1015,9 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
                 if (MODE < 0)
                     prestep_bin<T>(P, s.s_cut, rowsG, s.s_bins[b]);
                 else
-                    any |= solve_bin<PHASE, T>(P, s, s.s_cut, nullptr, P.cutCap - 1, rowsG, words, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, passIndex * 256 + b + 1, pre);
+                    any |= solve_bin<PHASE, T>(P, s, s.s_cut, P.cutCap - 1, rowsG, words, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, passIndex * 256 + b + 1, pre);
             }
-            for (int i = threadIdx.x; i < s.nR; i += T)
-            {
-                const float4 v = s.s_cut[i];
-                s.s_rows[s.s_listR[i]] = v;
-                s.s_last[s.s_listR[i]] = __float_as_int(v.w);
-            }
+            for (int i = threadIdx.x; i < s.nR; i += T) s.s_rows[s.s_listR[i]] = s.s_cut[i];
             for (int i = threadIdx.x; i < s.nLn; i += T) __stcg(&rowsG[s.s_listN[i]], s.s_cut[s.nR + i]);
         }
         __syncthreads();
@@ -852,12 +1027,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
     if (k > 0 && s.nL > 0)
     {
         cta_wait_flag(&P.flagB[k - 1], seq);
-        for (int i = threadIdx.x; i < s.nL; i += T)
-        {
-            const float4 v = __ldcg(&rowsG[s.row0 + s.s_listL[i]]);
-            s.s_rows[s.s_listL[i]] = v;
-            s.s_last[s.s_listL[i]] = __float_as_int(v.w);
-        }
+        for (int i = threadIdx.x; i < s.nL; i += T) s.s_rows[s.s_listL[i]] = __ldcg(&rowsG[s.row0 + s.s_listL[i]]);
         __syncthreads();
     }
     trace_mark(P, k, passIndex, 4);
@@ -866,7 +1036,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
 
 // all iterations of one phase; returns the number of passes executed (>= the reference's count: see the header)
 template <int PHASE, int T>
-__device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int iters, unsigned long long& seq, int& passIndex, int2 (&pre)[kStripU])
+__device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int iters, unsigned long long& seq, int& passIndex, unsigned (&pre)[kStripU])
 {
     __shared__ unsigned long long s_word;
     unsigned long long* done = P.done + size_t(PHASE) * P.doneStride;
@@ -909,11 +1079,10 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
     StripCta s;
     s.s_rows = reinterpret_cast<float4*>(stripSmem);
     s.s_cut = s.s_rows + P.rowCap;
-    s.s_last = reinterpret_cast<int*>(s.s_cut + P.cutCap);
-    s.s_work = s.s_last + P.rowCap;
-    s.s_listL = s.s_work + P.workCap;
+    s.s_listN = reinterpret_cast<int*>(s.s_cut + P.cutCap);
+    s.s_listL = reinterpret_cast<unsigned short*>(s.s_listN + P.cutCap);
     s.s_listR = s.s_listL + P.cutCap;
-    s.s_listN = s.s_listR + P.cutCap;
+    s.s_work = s.s_listR + P.cutCap;
     s.s_bins = s_bins;
     s.s_count = s_count;
     const int k = blockIdx.x, S = P.S;
@@ -950,8 +1119,8 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
         const int c = threadIdx.x & (kStripBins - 1);
         s_tmp[threadIdx.x] = P.binRange[cls * kStripBins + c];   // the table has 2S classes; class 2S-1 is always empty
     }
-    for (int i = threadIdx.x; i < s.nL; i += T) s.s_listL[i] = P.bL[bLs[k] + i] - s.row0;
-    for (int i = threadIdx.x; i < s.nR; i += T) s.s_listR[i] = P.bR[bRs[k] + i] - s.row0;
+    for (int i = threadIdx.x; i < s.nL; i += T) s.s_listL[i] = (unsigned short)(P.bL[bLs[k] + i] - s.row0);
+    for (int i = threadIdx.x; i < s.nR; i += T) s.s_listR[i] = (unsigned short)(P.bR[bRs[k] + i] - s.row0);
     for (int i = threadIdx.x; i < s.nLn; i += T) s.s_listN[i] = P.bL[bLs[k + 1] + i];
     __syncthreads();
     if (threadIdx.x == 0)
@@ -969,14 +1138,12 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
     s.nInt = s_n[0];
     s.nCut = s_n[1];
     mbar_wait(&s_mbar, 0);
-    for (int i = threadIdx.x; i < s.nRows; i += T) s.s_last[i] = __float_as_int(s.s_rows[i].w);
-    __syncthreads();
 
     unsigned long long seq = 0;
     int passIndex = 0;
-    int2 pre[kStripU];
+    unsigned pre[kStripU];
 #pragma unroll
-    for (int u = 0; u < kStripU; ++u) pre[u] = make_int2(-1, -1);
+    for (int u = 0; u < kStripU; ++u) pre[u] = 0xffffffffu;
 
     // warm start
     ++seq;
@@ -1004,8 +1171,6 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
             if (bytes) bulk_g2s(s.s_rows, P.rows[1] + s.row0, bytes, &s_mbar);
         }
         mbar_wait(&s_mbar, 1);
-        for (int i = threadIdx.x; i < s.nRows; i += T) s.s_last[i] = __float_as_int(s.s_rows[i].w);
-        __syncthreads();
         ranD = run_phase<1, T>(P, s, P.penetrationIters, seq, passIndex, pre);
         __syncthreads();
         if (threadIdx.x == 0 && s.nRows > 0)
@@ -1065,6 +1230,7 @@ int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, floa
     P.rows[1] = rowsDisp;
     P.pairQ = c->pairQ.as<float4>();
     P.pairIdx = c->pairIdx.as<int2>();
+    P.pairTest = sp.pairTest.as<unsigned>();
     P.accNF = c->accNF.as<float2>();
     P.accD = c->accD.as<float>();
     P.binRange = sp.binRange.as<int2>();
@@ -1089,7 +1255,6 @@ int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, floa
     P.workCap = (sp.maxBin + 8) & ~7;
     P.result = reinterpret_cast<int*>(c->solveFlags.as<char>() + 32);
     P.activeTotal = reinterpret_cast<unsigned long long*>(c->solveFlags.as<char>() + 48);
-    P.variant = getenv("PHYX_STRIP_VARIANT") ? atoi(getenv("PHYX_STRIP_VARIANT")) : 0;
     P.trace = nullptr;
     if (sp.tracePasses > 0)
     {
