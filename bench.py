@@ -37,8 +37,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ITERS = (20, 20)
-# algorithmic bytes per joint-iteration of the reference's loops
+# algorithmic bytes per joint-iteration of the reference's loops (a10 / a11 / a9), per body of the radix
+# sort (a3: 8 histogram + 3 x 16 scatter), per sweep test (a4).  BYTES_SKIP (two indices + two body rows for a joint the
+# lastIteration test skips) is NOT part of §8(d): it only enters the separately reported "with_skips" figure.
 BYTES_IMPULSE, BYTES_DISPLACEMENT, BYTES_PRESTEP, BYTES_SKIP = 196, 136, 128, 40
+BYTES_RADIX_PER_BODY, BYTES_SWEEP_TEST = 56, 20
+KERNEL_FORMS = {0: "k_solve (joint units)", 1: "k_solve_pairs (manifold units, streaming)", 2: "k_solve_pairs2 (manifold units, record form)",
+                3: "k_solve_strips (strip-local: rows in shared memory via bulk TMA, neighbour flags)"}
 
 
 def parse():
@@ -50,6 +55,9 @@ def parse():
     ap.add_argument("--scene", default="pyramid_1m")
     ap.add_argument("--settle", type=int, default=30, help="untimed World::Update steps that build the contact state")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", dest="parity", action="store_false",
+                    help="skip the parity_mode section (replay mode timed on the workload; colour-mode deviation from the reference after 100 steps at 100 k bodies)")
+    ap.set_defaults(parity=True)
     ap.add_argument("--no-spanning", dest="spanning", action="store_false",
                     help="with --gpus N > 1 the bench additionally runs ONE world of the scene over all N GPUs (partitioned solve, boundary rows over NVLink "
                          "peer memory) after the timed weak-scaling run and reports it under \"spanning\"; this switches that off")
@@ -165,7 +173,7 @@ def measured_peak():
 
 
 # ---------------------------------------------------------------------------------------------------
-def reference_run(scene, settle, steps, warmup, workers=None):
+def reference_run(scene, settle, steps, warmup, workers=None, count_executed=False):
     """The reference's own World::Update stages (oracle/_ref fast build = the reference Makefile's
     flags), Solve_AVX2 + Island_SingleSloppy on all host cores: its "AVX2 multicore path"."""
     from oracle import refpy
@@ -186,7 +194,18 @@ def reference_run(scene, settle, steps, warmup, workers=None):
     wall = time.perf_counter() - t0
     ms = w.stage_ms()
     tests, pairs = w.count_sweep()
+    executed = None
+    if count_executed:
+        # Iteration counts the reference loop runs (Solver.cpp:175-211 breaks after the first non-productive iteration).  The
+        # reference exposes no counter, so they come from the oracle's bit-exact restatement of Solve_AVX2 / Island_Single on
+        # the state the timed steps ended in (stages 1-6 of one more step, then the restated SolveJoints).
+        from oracle import oraclepy
+
+        w.step_staged(solve=T.SOLVE_AVX2, island=T.ISLAND_SINGLE_SLOPPY, iters=ITERS, mask=0x3F | refpy.SAFE_PAIRS)
+        _, _, _, ran = oraclepy.solve_joints(w.bodies(), w.joints(), w.contact_points(), group=8, iters=ITERS)
+        executed = [int(ran[0]), int(ran[1])]
     return {
+        "executed_iterations": executed,
         "value": joint_iters / wall,
         "ms_per_step": wall * 1e3 / steps,
         "cores": workers + 1,
@@ -208,9 +227,9 @@ def run_reference(args, rank, world_size):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libphyx_ref_fast.so was not built (needs /root/reference at build time)"}))
         return
     scene = scenes.make(args.scene)
-    steps = min(args.steps, 4)  # bounded sample: the reference needs ~0.3 s per 1M-box step on 16 cores
-    warm = min(args.warmup, 1)
-    r = reference_run(scene, args.settle, steps, warm)
+    steps = min(max(args.steps, 10), 12)  # bounded sample (the reference needs ~0.3 s per 1M-box step on 16 cores), at least 10 timed steps
+    warm = min(max(args.warmup, 1), 3)
+    r = reference_run(scene, args.settle, steps, warm, count_executed=True)
     sample = f"{steps} World::Update steps of the same workload after {args.settle}+{warm} untimed steps"
     line = {
         "impl": "reference", "metric": "constraint_iterations_per_sec", "value": r["value"], "unit": "constraint-iterations/s",
@@ -222,8 +241,70 @@ def run_reference(args, rank, world_size):
         "e2e": {"value": r["value"], "unit": "constraint-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "stage_ms_per_step": r["stage_ms_per_step"], "steps_per_sec": r["steps_per_s"], "broadphase_pairs_per_sec": r["broadphase_pairs_per_s"],
         "solve_only_constraint_iterations_per_sec": r["solve_only"],
+        "executed_iterations": r["executed_iterations"],
+        "executed_constraint_iterations_per_sec": (r["joints"] * sum(r["executed_iterations"]) / (r["ms_per_step"] * 1e-3)) if r["executed_iterations"] else None,
+        "counting": "value = joints x configured iterations (20 + 20, nominal) / time, the same convention as the GPU arm; executed_* uses the iterations the "
+                    "loops actually run before the productive early-out",
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def rel_dev(a, b):
+    """max |delta pos| / scene size, max |delta velocity| / max |velocity| (the measure tests/test_gpu_world.py uses)"""
+    scale = max(float(np.abs(b["pos"]).max()), 1.0)
+    dpos = float(np.abs(a["pos"][1:] - b["pos"][1:]).max()) / scale
+    vscale = max(float(np.abs(b["velocity"]).max()), 1.0)
+    dvel = float(np.abs(a["velocity"] - b["velocity"]).max()) / vscale
+    return dpos, dvel
+
+
+def parity_section(args, w, local_rank):
+    """Which mode produced which number (hard part 1).  `value` / `e2e` are the throughput mode (Solve_B200:
+    device colouring, strip-local kernel): the same joints relaxed in another Gauss-Seidel order, bit-exact against the oracle
+    on that order (tests), not bit-comparable with the reference.  The parity mode (Solve_AVX2: replay of the reference's
+    order as dependency levels) IS bit-identical to the reference (tests) and is timed here on the bench workload; and the
+    throughput mode's distance from the reference after 100 steps is measured at BASELINE configs[1] size next to the
+    reference's own Scalar-vs-AVX2 spread."""
+    from oracle import refpy
+    from phyx_b200 import scenes, world
+    from phyx_b200 import types as T
+
+    out = {"benched_mode": "Solve_B200 (throughput): colour schedule, strip-local kernel; bit-exact vs the oracle on its own slot order, NOT bit-comparable with the reference",
+           "parity_mode": "Solve_AVX2 (replay): bit-identical to the reference's AVX2 / Island_Single path (tests/test_gpu_world.py)"}
+    # (1) the replay mode on the bench workload, continuing from the settled state
+    t0 = time.perf_counter()
+    w.step(solve=T.SOLVE_AVX2, iters=ITERS)   # builds the replay schedule for this joint graph
+    first = time.perf_counter() - t0
+    ms = []
+    while len(ms) < 2 and sum(ms) * 1e-3 + first < 60.0:
+        t0 = time.perf_counter()
+        w.step(solve=T.SOLVE_AVX2, iters=ITERS)
+        ms.append((time.perf_counter() - t0) * 1e3)
+    st = w.solve_stats()
+    out["replay_on_workload"] = {"scene": args.scene, "first_step_ms": first * 1e3, "ms_per_step": float(np.mean(ms)) if ms else None, "steps": len(ms),
+                                 "levels": int(st.levels), "joints": int(st.joints), "solve_ms": float(st.ms_total), "schedule_ms": float(st.ms_schedule),
+                                 "note": "World::Update through the host mirror (e2e path); the reference's greedy PrepareIndices order is restated on the host each step, "
+                                         "its dependency levels are deep because SIMD groups couple unrelated stacks: a parity mode, not a throughput mode"}
+    # (2) throughput mode vs the reference after 100 steps, 100 k bodies
+    if refpy.available("strict"):
+        name = "stack_100k"
+        sc = scenes.make(name)
+        t0 = time.perf_counter()
+        ra, rs = refpy.RefWorld(sc, "strict"), refpy.RefWorld(sc, "strict")
+        g = world.World(sc, device=local_rank, mirror_contents=False)
+        steps = 100
+        for _ in range(steps):
+            ra.step(solve=T.SOLVE_AVX2)
+            rs.step(solve=T.SOLVE_SCALAR)
+            g.step(solve=world.SOLVE_B200)
+        ours, spread = rel_dev(g.bodies(), ra.bodies()), rel_dev(rs.bodies(), ra.bodies())
+        out["throughput_mode_vs_reference"] = {"scene": name, "steps": steps, "ours_vs_ref_avx2": {"pos": ours[0], "vel": ours[1]},
+                                               "ref_scalar_vs_ref_avx2": {"pos": spread[0], "vel": spread[1]},
+                                               "measure": "max |delta pos| / scene size, max |delta velocity| / max |velocity|; reference = oracle/_ref strict build, Island_Single, 1 core",
+                                               "seconds": time.perf_counter() - t0}
+        g.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -326,6 +407,13 @@ def run_ours(args, rank, world_size, local_rank):
         w.step(solve=world.SOLVE_B200, iters=ITERS)
         stage_ms_e2e = {k: round(v, 3) for k, v in w.stage_ms().items()}
 
+    parity = None
+    if args.parity and world_size == 1:
+        try:
+            parity = parity_section(args, w, local_rank)
+        except Exception as e:  # noqa: BLE001 - the main line must still be printed
+            parity = {"error": str(e)}
+
     # ---- optional: ONE world over all ranks (an island that spans devices), strong scaling of the solve
     spanning = None
     if args.spanning and dist is not None:
@@ -341,23 +429,38 @@ def run_ours(args, rank, world_size, local_rank):
         dist.destroy_process_group()
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (k_solve: warm start + all iterations, one launch per step)
+    # ---- roofline of the dominant kernel (the iteration kernel: warm start + all iterations, one launch per step)
     ran_i = float(np.mean([st.contactIterationsRun for _, st in stats]))
     ran_d = float(np.mean([st.penetrationIterationsRun for _, st in stats]))
     act_i = float(np.mean([st.activeJointIterations[0] for _, st in stats]))
     act_d = float(np.mean([st.activeJointIterations[1] for _, st in stats]))
     jm = float(np.mean([st.joints for _, st in stats]))
-    # bytes the reference's algorithm moves for the same work: a relaxed joint-iteration streams its
-    # packed joint and both body rows, a skipped one only the two indices and body rows (Solver.cpp:781-798)
-    alg_bytes = (jm * BYTES_PRESTEP + act_i * BYTES_IMPULSE + (jm * ran_i - act_i) * BYTES_SKIP + act_d * BYTES_DISPLACEMENT + (jm * ran_d - act_d) * BYTES_SKIP)
+    # bytes the reference's algorithm moves for the joint-iterations that are relaxed (and the warm start)
+    alg_bytes = jm * BYTES_PRESTEP + act_i * BYTES_IMPULSE + act_d * BYTES_DISPLACEMENT
+    # not §8(d), reported separately: plus two indices and two body rows for every joint-iteration the lastIteration test skips
+    alg_bytes_with_skips = alg_bytes + (jm * ran_i - act_i) * BYTES_SKIP + (jm * ran_d - act_d) * BYTES_SKIP
     nominal_bytes = jm * (BYTES_PRESTEP + ran_i * BYTES_IMPULSE + ran_d * BYTES_DISPLACEMENT)
     k_ms = float(np.mean([st.ms_iterations for _, st in stats]))
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
+    forms = {}
+    for _, st in stats:
+        forms[int(st.kernelForm)] = forms.get(int(st.kernelForm), 0) + 1
+    # DRAM traffic (ncu dram__bytes_read + write of one launch on this workload), per kernel form that actually ran,
+    # weighted by how often each form ran; null when a form that ran has no capture
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "k_solve_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    if os.path.exists(tpath) and args.scene == "pyramid_1m":
+        by_form = json.load(open(tpath)).get("by_form", {})
+        if all(str(f) in by_form for f in forms):
+            traffic = sum(by_form[str(f)]["dram_bytes_per_launch"] * n for f, n in forms.items()) / sum(forms.values())
+            traffic_src = {str(f): by_form[str(f)]["source"] for f in forms}
+    # radix sort of the broadphase (north_star: "achieved HBM GB/s for the solve and radix kernels"): key build + 3 LSD passes
+    sort_ms = float(np.mean([bp.ms_sort for bp, _ in stats]))
+    sweep_ms = float(np.mean([bp.ms_sweep for bp, _ in stats]))
+    pairs_m = float(np.mean([bp.pairs for bp, _ in stats]))
+    tests_m = float(np.mean([bp.tests for bp, _ in stats]))
+    radix_achieved = nb * BYTES_RADIX_PER_BODY / (sort_ms * 1e-3) / 1e9 if sort_ms > 0 else None
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -365,7 +468,7 @@ def run_ours(args, rank, world_size, local_rank):
 
         if refpy.available("fast"):
             r = reference_run(scene, args.settle, 3, 1)
-            cpu = {"value": r["value"], "unit": "constraint-iterations/s", "cores": r["cores"], "kind": "reference",
+            cpu = {"value": r["value"], "unit": "constraint-iterations/s", "cores": r["cores"], "kind": "reference", "broadphase_pairs_per_sec": r["broadphase_pairs_per_s"],
                    "sample": f"3 World::Update steps of the same workload after {args.settle}+1 untimed steps (Solve_AVX2 / Island_SingleSloppy, reference Makefile flags)",
                    "ms_per_step": r["ms_per_step"], "stage_ms_per_step": r["stage_ms_per_step"], "solve_only": r["solve_only"]}
         else:
@@ -386,11 +489,24 @@ def run_ours(args, rank, world_size, local_rank):
                 "stage_wall_ms": stage_ms_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "kernel": "k_solve_pairs / k_solve_pairs2 (warm start + impulse + displacement iterations, persistent; form chosen per step from the previous step's activity: "
-                                                       + f"{sum(1 for _, st in stats if st.kernelForm == 1)} streaming, {sum(1 for _, st in stats if st.kernelForm == 2)} record launches)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "nominal_bytes_per_launch": nominal_bytes, "kernel_ms": k_ms,
-                     "iterations_run": [ran_i, ran_d], "active_joint_iterations": [act_i, act_d], "joints": jm},
+        "roofline": {"bound": "hbm", "kernel": "; ".join(f"{KERNEL_FORMS[f]} x{n}" for f, n in sorted(forms.items())) + " (warm start + impulse + displacement iterations, one persistent launch per step)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "formula": "SURVEY 8(d): joints x 128 B (warm start) + relaxed impulse joint-iterations x 196 B + relaxed displacement joint-iterations x 136 B, / kernel_ms",
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "iterations_run": [ran_i, ran_d], "active_joint_iterations": [act_i, act_d], "joints": jm,
+                     "kernel_forms_launched": {str(f): n for f, n in sorted(forms.items())},
+                     "with_skips": {"note": "NOT the 8(d) figure: adds 40 B (two indices, two body rows) per joint-iteration the lastIteration test skips",
+                                    "bytes_per_launch": alg_bytes_with_skips, "achieved": alg_bytes_with_skips / (k_ms * 1e-3) / 1e9, "frac": alg_bytes_with_skips / (k_ms * 1e-3) / 1e9 / peak},
+                     "nominal_bytes_per_launch": nominal_bytes},
+        "roofline_radix": {"bound": "hbm", "kernel": "k_make_keys + 3 x (k_radix_hist, scan, k_radix_scatter): radixFloat keys, 11/11/10-bit LSD passes", "achieved": radix_achieved,
+                           "peak": peak, "unit": "GB/s", "frac": (radix_achieved / peak) if radix_achieved else None, "ms": sort_ms,
+                           "formula": "SURVEY 8(d): 56 B per body (8 histogram + 3 x 16 scatter) x bodies / CUDA-event time of the sort",
+                           "note": f"{nb * 8 / 1e6:.0f} MB of keys: the passes run out of L2, the sort is launch- and latency-bound, not HBM-bound"},
+        "broadphase_pairs_per_sec": world_size * pairs_m / ((sort_ms + sweep_ms) * 1e-3) if sort_ms + sweep_ms > 0 else None,
+        "broadphase_tests_per_sec": world_size * tests_m / ((sort_ms + sweep_ms) * 1e-3) if sort_ms + sweep_ms > 0 else None,
+        "executed_constraint_iterations_per_sec": world_size * jm * (ran_i + ran_d) / (ms_step * 1e-3),
+        "relaxed_constraint_iterations_per_sec": world_size * (act_i + act_d) / (ms_step * 1e-3),
+        "counting": "value = joints x configured iterations (20 + 20, nominal) / time, the convention of both arms; executed_* = joints x iterations run before the "
+                    "productive early-out; relaxed_* = joint-iterations that pass the lastIteration test (counted on the device)",
         "cpu_baseline": cpu,
         "solve_ms_per_step": {"total": solve_ms, "schedule": float(np.mean([st.ms_schedule for _, st in stats])), "refresh": float(np.mean([st.ms_refresh for _, st in stats])),
                               "iterations_kernel": k_ms, "colour_rounds": int(stats[-1][1].colourRounds), "colours": int(stats[-1][1].levels)},
@@ -400,7 +516,8 @@ def run_ours(args, rank, world_size, local_rank):
         "resident_stage_wall_ms_max": {k: round(v, 3) for k, v in stage_max.items()},
         "device_allocations_in_timed_region": {"count": allocs1[0] - allocs0[0], "host_ms": round(allocs1[1] - allocs0[1], 3)},
         "steps_per_sec": world_size * 1e3 / ms_step,
-        "broadphase": {"pairs": int(bp_last.pairs), "tests": int(bp_last.tests)},
+        "broadphase": {"pairs": int(bp_last.pairs), "tests": int(bp_last.tests), "sort_ms": sort_ms, "sweep_and_cache_filter_ms": sweep_ms},
+        "parity_mode": parity,
     }
     print(json.dumps(line))
 

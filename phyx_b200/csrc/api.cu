@@ -175,6 +175,7 @@ int phyx_b200_create(int device, phyx_b200_ctx** out)
     c->numSMs = prop.multiProcessorCount;
     PHYX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) PHYX_CUDA(cudaEventCreate(&ev));
+    for (auto& ev : c->evBp) PHYX_CUDA(cudaEventCreate(&ev));
     *out = c;
     return PHYX_B200_OK;
 }
@@ -192,6 +193,8 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
         &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->pairQ, &c->pairIdx, &c->bodyActivity };
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->evBp)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -627,7 +630,18 @@ int phyx_b200_update_pairs(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
 {
     PHYX_TRY(check(c));
     c->hostJointsValid = false;
-    return collide_update_pairs(c, stats);
+    PHYX_CUDA(cudaEventRecord(c->evBp[2], c->stream));
+    PHYX_TRY(collide_update_pairs(c, stats));
+    if (stats)
+    {
+        // CUDA-event times of the radix sort (key build + 3 passes, run by the last update_broadphase) and of this sweep
+        PHYX_CUDA(cudaEventRecord(c->evBp[3], c->stream));
+        PHYX_CUDA(cudaEventSynchronize(c->evBp[3]));
+        stats->ms_sort = c->sortTimed ? elapsed_ms(c->evBp[0], c->evBp[1]) : 0.f;
+        stats->ms_sweep = elapsed_ms(c->evBp[2], c->evBp[3]);
+        stats->ms_total = stats->ms_sort + stats->ms_sweep;
+    }
+    return PHYX_B200_OK;
 }
 
 int phyx_b200_update_manifolds(phyx_b200_ctx* c)

@@ -197,6 +197,8 @@ struct phyx_b200_ctx
     bool hostJointsValid = false;
 
     cudaEvent_t ev[8] = {};
+    cudaEvent_t evBp[4] = {};    // broadphase timing: sort start / end (update_broadphase), sweep start / end (update_pairs)
+    bool sortTimed = false;
     int solveBlocksPerSM = 0, colourBlocksPerSM = 0, colourRounds = 0;
     int lastKernelForm = 0;
     float lastActiveFraction = 1.0f;   // share of the impulse joint-iterations the previous solve relaxed (kernel choice, solve.cu)
