@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scene", default="pyramid_1m")
+    ap.add_argument("--scene", default=None, help="default: pyramid_1m on one GPU (BASELINE configs[2]); islands_1m on several (configs[3])")
     ap.add_argument("--settle", type=int, default=30, help="untimed World::Update steps that build the contact state")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", dest="parity", action="store_false",
@@ -308,6 +308,141 @@ def parity_section(args, w, local_rank):
 
 
 # ---------------------------------------------------------------------------------------------------
+def run_island_parallel(args, rank, world_size, local_rank):
+    """--gpus N > 1: ONE world (default islands_1m, BASELINE configs[3]) stepped by all N ranks together, the solve split BY
+    ISLAND (phyx_b200/islands.py, csrc/islands.cu): strong scaling of one scene.  Every rank holds the whole world and runs the
+    collider stages redundantly; a rank relaxes only its own islands (no communication inside the solve) and one integer-sum
+    all-reduce over NCCL per step merges the results.  `value` = joints x (20 + 20) of that ONE world / max-over-ranks time."""
+    import hashlib
+
+    import torch
+    import torch.distributed as dist
+
+    from phyx_b200 import capi, islands, partition, scenes
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize(local_rank)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def digest(b):
+        h = hashlib.sha256()
+        for f in ("pos", "xVector", "velocity", "angularVelocity"):
+            h.update(np.ascontiguousarray(b[f]).tobytes())
+        return h.hexdigest()
+
+    scene = scenes.make(args.scene)
+    bodies = partition.body_records(scene, device=local_rank)
+    nb = bodies.shape[0]
+    ctx = capi.Context(local_rank)
+    ipw = islands.IslandParallelWorld(ctx, bodies, local_rank)
+    for _ in range(args.settle):
+        ipw.step(ITERS)
+    clocks = ClockSampler(local_rank)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        ipw.step(ITERS)
+    barrier()
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count()
+    with clocks:
+        e0.record(stream)
+        stats = [ipw.step(ITERS) for _ in range(args.steps)]
+        e1.record(stream)
+        barrier()
+    clocks.close()
+    launches = ctx.launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    joint_iters = sum(st.joints for _, st in stats) * sum(ITERS)
+    value = joint_iters / (ms_total * 1e-3)
+    state = digest(ctx.download_bodies())
+
+    # e2e: the same step with HOST buffers: every rank uploads World::bodies (pinned) and reads it back, every step
+    host = torch.from_numpy(ctx.download_bodies().view(np.uint8).reshape(-1)).pin_memory()
+    host_np = host.numpy().view(bodies.dtype)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_ji = 0
+    for _ in range(e2e_steps):
+        ctx.upload_bodies(host_np)
+        _, st = ipw.step(ITERS)
+        ctx.download_bodies(out=host_np)
+        e2e_ji += st.joints * sum(ITERS)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+
+    mine = {"rank": rank, "manifolds_relaxed": int(np.mean([st.slots for _, st in stats])) // 2, "kernel_ms": float(np.mean([st.ms_iterations for _, st in stats])),
+            "solve_ms": float(np.mean([st.ms_total for _, st in stats])), "kernel_form": int(stats[-1][1].kernelForm), "state": state,
+            "relaxed": [float(np.mean([st.activeJointIterations[0] for _, st in stats])), float(np.mean([st.activeJointIterations[1] for _, st in stats]))]}
+    per_rank = [None] * world_size
+    dist.all_gather_object(per_rank, mine)
+
+    # the same world on ONE device, same number of steps: the island-parallel result must be bit-identical (rank 0 checks)
+    matches = None
+    if rank == 0:
+        one = capi.Context(local_rank)
+        one.upload_bodies(bodies)
+        for _ in range(args.settle + warm + args.steps):
+            islands.stages_before_solve(one)
+            one.solve_resident(iters=ITERS, schedule=capi.SCHEDULE_COLOUR)
+            one.integrate_position(scenes.DT)
+        matches = digest(one.download_bodies()) == state
+        one.close()
+
+    spanning = None
+    if args.spanning:
+        try:
+            spanning = partition.run_spanning("pyramid_1m", args.settle, max(3, min(args.steps, 10)), local_rank, iters=ITERS)
+        except Exception as e:  # noqa: BLE001
+            spanning = {"error": str(e)}
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank != 0:
+        return
+    jm = float(np.mean([st.joints for _, st in stats]))
+    peak, peak_src = measured_peak()
+    k_ms = max(r["kernel_ms"] for r in per_rank)
+    act = [sum(r["relaxed"][0] for r in per_rank), sum(r["relaxed"][1] for r in per_rank)]
+    alg_bytes = jm * BYTES_PRESTEP + act[0] * BYTES_IMPULSE + act[1] * BYTES_DISPLACEMENT
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    words = nb * 8 + int(jm) * 2
+    line = {
+        "metric": "constraint_iterations_per_sec", "value": value, "unit": "constraint-iterations/s", "n_gpus": world_size, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.scene}: ONE world of {nb} bodies, {int(jm)} joints after {args.settle} settle steps, {ITERS[0]}+{ITERS[1]} iterations (nominal); step = World::Update "
+                               f"(8 stages, colour schedule), SolveJoints split by island over {world_size} GPUs",
+                   "inputs": "larger than L2; consecutive simulation steps (state evolves, nothing is replayed)",
+                   "parallelism": f"island-parallel x{world_size}: each rank relaxes a contiguous run of island groups with equal joint counts (device union-find, csrc/islands.cu); "
+                                  "collider stages replicated; one NCCL integer-sum all-reduce of the results per step"},
+        "e2e": {"value": e2e_ji / (e2e_ms * e2e_steps * 1e-3), "unit": "constraint-iterations/s", "h2d_bytes_per_step": int(nb * 128), "d2h_bytes_per_step": int(nb * 128),
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "call": "per rank: upload World::bodies (pinned), island-parallel World::Update, download World::bodies"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "roofline": {"bound": "hbm", "kernel": f"{KERNEL_FORMS[per_rank[0]['kernel_form']]}, one launch per rank and step over the rank's own islands", "achieved": achieved, "peak": peak * world_size,
+                     "unit": "GB/s", "frac": achieved / (peak * world_size), "traffic": None, "peak_source": peak_src + f" x {world_size} GPUs",
+                     "formula": "SURVEY 8(d) bytes of the relaxed joint-iterations of all ranks / the slowest rank's kernel time", "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms},
+        "cpu_baseline": None,
+        "island_parallel": {"per_rank": [{k: v for k, v in r.items() if k != "state"} for r in per_rank], "replicas_identical": len({r["state"] for r in per_rank}) == 1,
+                            "matches_one_device_run_bit_for_bit": matches, "exchange_bytes_per_step_per_rank": words * 4,
+                            "exchange": "NCCL all-reduce (int32 SUM, one non-zero term per word) of [velocity rows | displacement rows | cached impulses]"},
+        "spanning": spanning,
+        "executed_constraint_iterations_per_sec": jm * float(np.mean([st.contactIterationsRun + st.penetrationIterationsRun for _, st in stats])) / (ms_step * 1e-3),
+        "steps_per_sec": 1e3 / ms_step,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world_size, local_rank):
     import torch
 
@@ -527,8 +662,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.scene is None:
+        # one GPU: the configuration the metric is quoted on; several: ONE multi-island world split by island (configs[3]),
+        # for both arms, so that the driver's per-N ratio compares like with like
+        args.scene = "pyramid_1m" if max(world_size, args.gpus) == 1 else "islands_1m"
     if args.impl == "reference":
         run_reference(args, rank, world_size)
+    elif world_size > 1:
+        run_island_parallel(args, rank, world_size, local_rank)
     else:
         run_ours(args, rank, world_size, local_rank)
 

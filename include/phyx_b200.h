@@ -233,6 +233,28 @@ PHYX_B200_API int phyx_b200_download_joints(phyx_b200_ctx* ctx, phyx_contact_joi
 PHYX_B200_API int phyx_b200_upload_collider(phyx_b200_ctx* ctx, const phyx_manifold* manifolds, int manifoldCount,
     const phyx_contact_point* contactPoints, const phyx_contact_joint* joints, int jointCount);
 
+/* ---- islands: Solver::GatherIslands, reference src/Solver.cpp:285-454 ----------------------------------------------- */
+/* Union-find over the dynamic bodies joined by the resident contact joints (static bodies do not merge islands), islands
+ * numbered in order of their first body, consecutive islands coalesced into groups of >= 256 joints.  Call after
+ * refresh_contact_joints.  *islandCount / *islandMaxSize are Solver::islandCount / Solver::islandMaxSize (groups and the
+ * joints of the largest group, what the demo's HUD shows, src/main.cpp:358-360); *islands = islands before coalescing. */
+PHYX_B200_API int phyx_b200_build_islands(phyx_b200_ctx* ctx, int32_t* islandCount, int32_t* islandMaxSize, int32_t* islands);
+/* per body: its island (the reference's island_index[island_remap[body]]) and its group (island_indexremap of that), -1 for
+ * static bodies; either pointer may be NULL */
+PHYX_B200_API int phyx_b200_download_islands(phyx_b200_ctx* ctx, int32_t* islandOfBody, int32_t* groupOfBody, int32_t capacity);
+/* One world's Solver::SolveJoints split BY ISLAND over `ranks` devices (the reference's island dispatch, src/Solver.cpp:73-92,
+ * with devices in place of worker threads).  Every rank holds the whole world and runs the other stages redundantly; with
+ * ranks > 1 solve_resident (colour schedule) builds the islands, gives every rank a contiguous run of island groups with
+ * about equal joint counts, and relaxes only the manifolds of this rank's islands: islands exchange no impulses, so there is
+ * no communication inside the solve.  Afterwards island_pack writes this rank's results (velocity / displacement rows of its
+ * bodies, cached impulses of its joints; zero elsewhere) as island_exchange_words 32-bit words into a device buffer of the
+ * caller; an integer SUM all-reduce over the ranks (e.g. NCCL, one non-zero term per word: exact) followed by island_unpack
+ * on every rank leaves all replicas with the complete, identical state.  ranks = 1 switches the split off. */
+PHYX_B200_API int phyx_b200_island_partition(phyx_b200_ctx* ctx, int rank, int ranks);
+PHYX_B200_API int phyx_b200_island_exchange_words(phyx_b200_ctx* ctx, int64_t* words);
+PHYX_B200_API int phyx_b200_island_pack(phyx_b200_ctx* ctx, int32_t* deviceBuffer);
+PHYX_B200_API int phyx_b200_island_unpack(phyx_b200_ctx* ctx, const int32_t* deviceBuffer);
+
 /* ---- one world over several devices (an island that spans devices) ------------------------ */
 /* The reference has no counterpart (one process, one address space); in its terms this is Solver::SolveJoints
  * (src/Solver.cpp:68-215) of ONE island executed by `ranks` devices.  Every rank holds the whole world and

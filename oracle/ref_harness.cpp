@@ -240,6 +240,29 @@ int ref_prepare_indices(void* h, int groupSize, int* out_index)
     return groupOffset;
 }
 
+// Solver::GatherIslands (src/Solver.cpp:285-454) on the CURRENT joints: per body its island (island_index of its root,
+// -1 for static bodies) and its coalesced group (island_indexremap of that); out3 = {islands before coalescing,
+// islandCount, islandMaxSize}.
+void ref_gather_islands(void* h, int groupSize, int* out_island, int* out_group, int* out3)
+{
+    RefWorld* r = static_cast<RefWorld*>(h);
+    Solver& s = r->world.solver;
+    const int n = r->world.bodies.size;
+    s.GatherIslands(r->world.bodies.data, n, groupSize);
+    int islands = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        const int root = s.island_remap[i];
+        const int island = root < 0 ? -1 : s.island_index[root];
+        if (island + 1 > islands) islands = island + 1;
+        if (out_island) out_island[i] = island;
+        if (out_group) out_group[i] = island < 0 ? -1 : s.island_indexremap[island];
+    }
+    out3[0] = islands;
+    out3[1] = s.islandCount;
+    out3[2] = s.islandMaxSize;
+}
+
 // ---- function-level entry points on caller-provided arrays (captured-input parity) ----------
 
 // Solver::SolveJoints on caller arrays: bodies (RigidBody AoS, in/out), joints (ContactJoint AoS,

@@ -54,6 +54,7 @@ def lib(flavour="strict"):
     l.ref_count_sweep.argtypes = [vp, vp]
     l.ref_prepare_indices.argtypes = [vp, i32, vp]
     l.ref_prepare_indices.restype = i32
+    l.ref_gather_islands.argtypes = [vp, i32, vp, vp, vp]
     l.ref_solve_joints.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]
     l.ref_update_broadphase.argtypes = [vp, i32, vp]
     l.ref_all_pairs.argtypes = [vp, i32, vp, i32]
@@ -163,6 +164,13 @@ class RefWorld:
         out = np.zeros(n, dtype=np.int32)
         self.l.ref_get_joint_index(self.h, _p(out))
         return out
+
+    def gather_islands(self, group=8):
+        """Solver::GatherIslands on the current joints: (island per body, coalesced group per body, (islands, islandCount, islandMaxSize))."""
+        n = self.l.ref_body_count(self.h)
+        isl, grp, out3 = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(3, np.int32)
+        self.l.ref_gather_islands(self.h, group, _p(isl), _p(grp), _p(out3))
+        return isl, grp, tuple(int(v) for v in out3)
 
     def count_sweep(self):
         out = np.zeros(2, dtype=np.int64)

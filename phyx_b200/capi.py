@@ -61,6 +61,12 @@ EXPORTS = (
     "phyx_b200_solve_tuning",
     "phyx_b200_strip_plan",
     "phyx_b200_strip_trace",
+    "phyx_b200_build_islands",
+    "phyx_b200_download_islands",
+    "phyx_b200_island_partition",
+    "phyx_b200_island_exchange_words",
+    "phyx_b200_island_pack",
+    "phyx_b200_island_unpack",
     "phyx_b200_partition_create",
     "phyx_b200_partition_attach",
     "phyx_b200_partition_destroy",
@@ -167,6 +173,12 @@ def load():
     l.phyx_b200_solve_tuning.argtypes = [vp, i32, i32]
     l.phyx_b200_strip_plan.argtypes = [vp, C.POINTER(i32), vp, vp, i32, vp]
     l.phyx_b200_strip_trace.argtypes = [vp, i32, vp, i64, C.POINTER(i32)]
+    l.phyx_b200_build_islands.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    l.phyx_b200_download_islands.argtypes = [vp, vp, vp, i32]
+    l.phyx_b200_island_partition.argtypes = [vp, i32, i32]
+    l.phyx_b200_island_exchange_words.argtypes = [vp, C.POINTER(i64)]
+    l.phyx_b200_island_pack.argtypes = [vp, vp]
+    l.phyx_b200_island_unpack.argtypes = [vp, vp]
     l.phyx_b200_partition_create.argtypes = [vp, i32, i32, i32, C.c_size_t, vp, C.POINTER(vp)]
     l.phyx_b200_partition_attach.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(i32)]
     l.phyx_b200_partition_destroy.argtypes = [vp]
@@ -379,6 +391,34 @@ class Context:
             self._check(self.l.phyx_b200_strip_trace(self.h, passes, None, 0, None))
             self._trace_passes = passes
         return out
+
+    # ---- islands (Solver::GatherIslands) and the island-parallel solve over several devices (phyx_b200/islands.py) ----
+    def build_islands(self):
+        """Returns (islandCount, islandMaxSize, islands before coalescing)."""
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._check(self.l.phyx_b200_build_islands(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def download_islands(self):
+        """(island of every body, coalesced group of every body); -1 for static bodies."""
+        n = self.l.phyx_b200_body_count(self.h)
+        isl, grp = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._check(self.l.phyx_b200_download_islands(self.h, _p(isl), _p(grp), n))
+        return isl, grp
+
+    def island_partition(self, rank, ranks):
+        self._check(self.l.phyx_b200_island_partition(self.h, rank, ranks))
+
+    def island_exchange_words(self):
+        w = C.c_int64(0)
+        self._check(self.l.phyx_b200_island_exchange_words(self.h, C.byref(w)))
+        return int(w.value)
+
+    def island_pack(self, device_pointer):
+        self._check(self.l.phyx_b200_island_pack(self.h, C.c_void_p(device_pointer)))
+
+    def island_unpack(self, device_pointer):
+        self._check(self.l.phyx_b200_island_unpack(self.h, C.c_void_p(device_pointer)))
 
     # ---- one world over several devices (phyx_b200/partition.py drives these) ----
     def partition_create(self, rank, ranks, boundary_capacity, bulk_bytes):

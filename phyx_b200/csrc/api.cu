@@ -173,9 +173,24 @@ int phyx_b200_create(int device, phyx_b200_ctx** out)
     phyx_b200_ctx* c = new phyx_b200_ctx();
     c->device = device;
     c->numSMs = prop.multiProcessorCount;
-    PHYX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (auto& ev : c->ev) PHYX_CUDA(cudaEventCreate(&ev));
-    for (auto& ev : c->evBp) PHYX_CUDA(cudaEventCreate(&ev));
+    auto init = [&]() -> int {
+        PHYX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto& ev : c->ev) PHYX_CUDA(cudaEventCreate(&ev));
+        for (auto& ev : c->evBp) PHYX_CUDA(cudaEventCreate(&ev));
+        return PHYX_B200_OK;
+    };
+    const int st = init();
+    if (st != PHYX_B200_OK)
+    {
+        // do not leak the half-built context
+        for (auto& ev : c->ev)
+            if (ev) cudaEventDestroy(ev);
+        for (auto& ev : c->evBp)
+            if (ev) cudaEventDestroy(ev);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return st;
+    }
     *out = c;
     return PHYX_B200_OK;
 }
@@ -190,7 +205,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
-        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->pairQ, &c->pairIdx, &c->bodyActivity };
+        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->pairQ, &c->pairIdx, &c->bodyActivity, &c->islandTmp, &c->bodyOwner };
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -422,7 +437,7 @@ int phyx_b200_strip_plan(phyx_b200_ctx* c, int32_t* strips, int32_t* cuts, int32
     if (strips) *strips = sp.valid ? sp.strips : 0;
     if (info)
     {
-        const int v[8] = { sp.valid ? 1 : 0, sp.rejected, sp.maxStripRows, sp.maxCutRows, sp.maxBin, sp.numStatics, sp.colours, sp.cutManifolds };
+        const int v[8] = { sp.valid ? 1 : 0, sp.rejected, sp.maxStripRows, sp.maxCutRows, sp.maxBin, 0, sp.colours, sp.cutManifolds };
         memcpy(info, v, sizeof(v));
     }
     if (!sp.valid || (!cuts && !classSlotStart)) return PHYX_B200_OK;
@@ -465,6 +480,64 @@ int phyx_b200_strip_trace(phyx_b200_ctx* c, int passes, uint64_t* out, int64_t c
         *strips = 0;
     if (passes >= 0) sp.tracePasses = passes;
     return PHYX_B200_OK;
+}
+
+// ---- islands ------------------------------------------------------------------------------------------------
+
+int phyx_b200_build_islands(phyx_b200_ctx* c, int32_t* islandCount, int32_t* islandMaxSize, int32_t* islandsBeforeCoalescing)
+{
+    PHYX_TRY(check(c));
+    return islands_build(c, c->islandRanks, islandCount, islandMaxSize, islandsBeforeCoalescing);
+}
+
+int phyx_b200_download_islands(phyx_b200_ctx* c, int32_t* islandOfBody, int32_t* groupOfBody, int32_t capacity)
+{
+    PHYX_TRY(check(c));
+    if (capacity < c->bodyCount)
+    {
+        set_error("download_islands: capacity %d < %d bodies", capacity, c->bodyCount);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    return islands_download(c, islandOfBody, groupOfBody);
+}
+
+int phyx_b200_island_partition(phyx_b200_ctx* c, int rank, int ranks)
+{
+    PHYX_TRY(check(c));
+    if (ranks < 1 || ranks > 255 || rank < 0 || rank >= ranks)
+    {
+        set_error("island_partition: need 1 <= ranks <= 255 and 0 <= rank < ranks");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    if (c->part.ranks > 1)
+    {
+        set_error("island_partition: the context is partitioned by solver row (partition_create); the two are exclusive");
+        return PHYX_B200_ERR_STATE;
+    }
+    c->islandRank = rank;
+    c->islandRanks = ranks;
+    c->islandsValid = false;
+    c->scheduleMode = -1;   // schedules built so far cover other manifolds
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_island_exchange_words(phyx_b200_ctx* c, int64_t* words)
+{
+    PHYX_TRY(check(c));
+    if (words) *words = int64_t(islands_exchange_words(c));
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_island_pack(phyx_b200_ctx* c, int32_t* deviceBuffer)
+{
+    PHYX_TRY(check(c));
+    return islands_pack(c, deviceBuffer);
+}
+
+int phyx_b200_island_unpack(phyx_b200_ctx* c, const int32_t* deviceBuffer)
+{
+    PHYX_TRY(check(c));
+    return islands_unpack(c, deviceBuffer);
 }
 
 // ---- one world over several devices ---------------------------------------------------------------------
@@ -665,6 +738,18 @@ int phyx_b200_refresh_contact_joints(phyx_b200_ctx* c, int32_t* matched, int32_t
 
 int phyx_b200_solve_resident(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* stats)
 {
+    PHYX_TRY(check(c));
+    // island partition: which islands are this rank's is decided on the contact graph of this step
+    if (c->islandRanks > 1)
+    {
+        if (!cfg || cfg->schedule != PHYX_B200_SCHEDULE_COLOUR)
+        {
+            set_error("solve: an island partition needs schedule = PHYX_B200_SCHEDULE_COLOUR");
+            return PHYX_B200_ERR_ARGUMENT;
+        }
+        PHYX_TRY(islands_build(c, c->islandRanks, nullptr, nullptr, nullptr));
+        c->scheduleMode = -1;
+    }
     return phyx_b200_solve_staged(c, cfg, stats);
 }
 

@@ -385,8 +385,12 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(int n, const int* 
         const int numItems = (len + kChunk - 1) / kChunk;
         // candidates: the cells within reach of this body's y interval
         const float reach = yi.y + eymax;
-        const int cLo = min(kCells - 1, max(0, int((yi.x - reach - ymin) * invCellH) - 1));
-        const int cHi = min(kCells - 1, max(0, int((yi.x + reach - ymin) * invCellH) + 1));
+        // clamp in float BEFORE the conversion: a tall body (a wall, a thick slab) makes the quotient exceed the int range,
+        // and int(inf-ish) +/- 1 would be signed overflow
+        const float fLo = fminf(fmaxf((yi.x - reach - ymin) * invCellH, 0.0f), float(kCells - 1));
+        const float fHi = fminf(fmaxf((yi.x + reach - ymin) * invCellH, 0.0f), float(kCells - 1));
+        const int cLo = max(0, int(fLo) - 1);
+        const int cHi = min(kCells - 1, int(fHi) + 1);
         const int kBegin = cellStart[cLo], kEnd = cellStart[cHi + 1];
         // per work item (chunk of kChunk tests) counts; a tile-able body has at most kTileCap / kChunk items
         int counts[kTileCap / kChunk + 1];

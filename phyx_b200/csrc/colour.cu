@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kBlock) k_unit_init(int M, const int2* __restr
 
 // persist the colours, emit {colour, manifold} sort keys and the per-colour histogram (bin 64 = skipped)
 __global__ void __launch_bounds__(kBlock) k_unit_keys(int M, const int* __restrict__ work, int* __restrict__ manColour, uint2* __restrict__ keys,
-    int* __restrict__ counts)
+    int* __restrict__ counts, const int2* __restrict__ manBody, const unsigned char* __restrict__ bodyOwner, int rank)
 {
     __shared__ int h[kMaxColours + 1];
     if (threadIdx.x <= kMaxColours) h[threadIdx.x] = 0;
@@ -445,8 +445,10 @@ __global__ void __launch_bounds__(kBlock) k_unit_keys(int M, const int* __restri
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m < M)
     {
-        const int c = work[m];
+        int c = work[m];
         manColour[m] = (c == kSkipUnit) ? -1 : c;
+        // island partition (islands.cu): manifolds of another rank's islands keep their colour but are not laid out
+        if (bodyOwner && max(bodyOwner[manBody[m].x], bodyOwner[manBody[m].y]) != rank) c = kSkipUnit;
         keys[m] = make_uint2(unsigned(c), unsigned(m));
         atomicAdd(&h[c], 1);
     }
@@ -851,7 +853,7 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
         }
         if (c->forceKernelForm == 3)
         {
-            set_error("strip layout rejected (reason mask %d: 1 manifold across non-adjacent strips, 2 row in two cut sets, 4 shared memory, 8 static bodies, 16 no manifolds)",
+            set_error("strip layout rejected (reason mask %d: 1 manifold across non-adjacent strips, 2 row in two cut sets, 4 shared memory, 16 no manifolds)",
                 c->strip.rejected);
             return PHYX_B200_ERR_STATE;
         }
@@ -860,7 +862,9 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
     // colour-major layout of the manifolds: stable counting sort on a 7-bit digit (bin 64 = skipped)
     PHYX_TRY(c->colourKeys.reserve(size_t(M) * sizeof(uint2)));
     PHYX_TRY(c->colourSorted.reserve(size_t(M) * sizeof(uint2)));
-    k_unit_keys<<<grid, kBlock, 0, c->stream>>>(M, work, c->manColour.as<int>(), c->colourKeys.as<uint2>(), counts);
+    const bool split = c->islandRanks > 1 && c->islandsValid && c->islandBodies == nb;
+    k_unit_keys<<<grid, kBlock, 0, c->stream>>>(M, work, c->manColour.as<int>(), c->colourKeys.as<uint2>(), counts, c->manBody.as<int2>(),
+        split ? c->bodyOwner.as<unsigned char>() : nullptr, c->islandRank);
     c->launches++;
     PHYX_TRY(radix_pass(c, c->colourKeys.as<uint2>(), c->colourSorted.as<uint2>(), M, 0, 2 * kMaxColours));
     // per-colour table for the placement (a colour nobody uses is an empty entry); the solve gets a compact copy

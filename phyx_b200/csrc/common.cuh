@@ -81,6 +81,7 @@ struct Partition
     int classSlotStart[kMaxRanks + 2] = {};   // slots of class q (q = ranks: the cut class): [classSlotStart[q], classSlotStart[q+1])
     int numInterior = 0, numCut = 0;   // levels of this rank in partLevels: interior first, then cut
     bool planValid = false;
+    bool failed = false;               // a solve timed out waiting for a peer: the partition must be re-created
     DevBuf rowFlag, rowPrefix, bRows, planWords, binLevels, partLevels, state;
     int widestInterior = 0, widestCut = 0;   // slots of the widest level of each kind (grid sizing)
     void* params = nullptr;            // SolveParams of the solve in flight (solve.cu)
@@ -97,10 +98,10 @@ struct StripPlan
     int want = 0;              // tuning (phyx_b200_solve_tuning): 0 = choose, -1 = never, > 0 = this many strips
     int strips = 0;            // S of the current layout
     int autoLimit = 0;         // largest S worth trying when choosing (halved whenever a layout is rejected as too narrow)
-    int maxStripRows = 0, maxCutRows = 0, maxBin = 0, numStatics = 0, colours = 0, cutManifolds = 0, manifolds = 0;
+    int maxStripRows = 0, maxCutRows = 0, maxBin = 0, colours = 0, cutManifolds = 0, manifolds = 0;
     bool attributeSet = false;
     int rejected = 0;          // why the last layout attempt was not usable (bit mask, see strips.cu), 0 = usable
-    DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, staticOrd, header, words, sync, hist, trace, pairTest;
+    DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, header, sync, hist, trace, pairTest;
     int tracePasses = 0;       // developer aid (phyx_b200_strip_trace): passes of the next solves to time-stamp per CTA
 };
 
@@ -204,6 +205,11 @@ struct phyx_b200_ctx
     float lastActiveFraction = 1.0f;   // share of the impulse joint-iterations the previous solve relaxed (kernel choice, solve.cu)
 
     phyx::StripPlan strip;
+    // islands of the contact graph (islands.cu) and the split of one world's solve by island over several devices
+    phyx::DevBuf islandTmp, bodyOwner;
+    bool islandsValid = false;
+    int islandBodies = 0, islandCount = 0, islandMaxSize = 0;
+    int islandRank = 0, islandRanks = 1;
     phyx::DevBuf bodyActivity;   // int per body: last impulse iteration with a productive joint on it, previous solve (strip balance)
     bool activityValid = false;
     int activityBodies = 0;
@@ -230,6 +236,13 @@ int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift,
 
 // colour.cu
 int colour_schedule_build(phyx_b200_ctx* c);
+
+// islands.cu
+int islands_build(phyx_b200_ctx* c, int ranks, int* islandCount, int* islandMaxSize, int* islandsBeforeCoalescing);
+int islands_download(phyx_b200_ctx* c, int* islandOfBody, int* groupOfBody);
+size_t islands_exchange_words(const phyx_b200_ctx* c);
+int islands_pack(phyx_b200_ctx* c, int32_t* deviceBuffer);
+int islands_unpack(phyx_b200_ctx* c, const int32_t* deviceBuffer);
 
 // strips.cu
 int strip_choose(const phyx_b200_ctx* c, int manifolds, int bodies);

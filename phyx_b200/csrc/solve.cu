@@ -1091,7 +1091,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
     {
         if (!strips) PHYX_CUDA(cudaMemsetAsync(c->stamps.ptr, 0, size_t(nb) * 2 * sizeof(unsigned long long), c->stream));
         PHYX_CUDA(cudaMemsetAsync(c->solveFlags.ptr, 0, 128, c->stream));
-        PHYX_CUDA(cudaMemsetAsync(c->processed.ptr, 0, size_t(strips ? ns / 2 : ns) * sizeof(int), c->stream));
+        if (!strips) PHYX_CUDA(cudaMemsetAsync(c->processed.ptr, 0, size_t(ns) * sizeof(int), c->stream));
         // memory order of the solver rows: the broadphase's sorted-x order when there is one (measured best: k_solve 2.40 ms
         // vs 3.08 ms for body order on the 1 M pyramid), else body order
         const bool sorted = c->rowOrderValid && c->rowOrderBodies == nb;
@@ -1490,6 +1490,7 @@ int part_create(phyx_b200_ctx* c, int rank, int ranks, int boundaryCapacity, siz
     if (!pt.evReady) PHYX_CUDA(cudaEventCreateWithFlags(&pt.evReady, cudaEventDisableTiming));
     pt.bulkSeq = 0;
     pt.planValid = false;
+    pt.failed = false;
     for (int q = 0; q < kMaxRanks; ++q)
     {
         pt.peer[q] = nullptr;
@@ -1603,6 +1604,11 @@ int part_begin(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg)
         return PHYX_B200_ERR_ARGUMENT;
     }
     pt.launchIndex = 0;
+    if (pt.failed)
+    {
+        set_error("solve_partitioned: an earlier solve timed out waiting for a peer; partition_destroy / partition_create / partition_attach on all ranks first");
+        return PHYX_B200_ERR_STATE;
+    }
     if (c->jointCount == 0) return PHYX_B200_OK;
     if (!pt.planValid)
     {
@@ -1782,7 +1788,12 @@ int part_end(phyx_b200_ctx* c, phyx_b200_solve_stats* stats)
         PHYX_CUDA(cudaStreamSynchronize(c->stream));
         if (host.error)
         {
-            set_error("solve_partitioned: rank %d gave up waiting for a peer's boundary rows (a peer failed or did not call the solve)", pt.rank);
+            // the ranks' exchange counters and flags may have diverged for good: refuse further partitioned solves on this
+            // context until partition_destroy + partition_create + partition_attach have run again on ALL ranks
+            pt.failed = true;
+            pt.planValid = false;
+            set_error("solve_partitioned: rank %d gave up waiting for a peer's boundary rows (a peer failed or did not call the solve); "
+                      "re-create the partition on all ranks", pt.rank);
             return PHYX_B200_ERR_STATE;
         }
     }

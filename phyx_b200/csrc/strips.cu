@@ -58,7 +58,7 @@ enum
     H_REJECT = 0,   // bit 0: a manifold spans non-adjacent strips, bit 1: a row is in two cut sets
     H_MAXROWS,      // rows of the largest strip
     H_MAXCUT,       // rows of the largest cut set (own right-boundary rows + the neighbour's left-boundary rows)
-    H_STATICS,      // static bodies
+    H_UNUSED3,
     H_MANIFOLDS,    // manifolds with a colour (slots / 2)
     H_MAXBIN,       // manifolds of the largest (class, colour) bin
     H_COLOURS,      // colours in use
@@ -74,7 +74,6 @@ enum
     kRejectFar = 1,
     kRejectBothSides = 2,
     kRejectSmem = 4,
-    kRejectStatics = 8,
     kRejectEmpty = 16
 };
 
@@ -85,16 +84,31 @@ enum
 // iterations that will be is predicted from the previous step: activity[b] = last iteration in which body b received a
 // productive impulse (FinishBodies keeps it), and a manifold is relaxed while either body is at most one iteration stale
 // (Solver.cpp:790-798).  Without a previous step every manifold counts the same.
+// (cover: +1 at the lower row and -1 at the upper row of every manifold between two dynamic bodies; its exclusive prefix
+// sum at row r counts the manifolds a cut in front of row r would split.)
+// owner / rank: with an island partition (islands.cu) only the manifolds of this rank's islands are laid out.
+__device__ __forceinline__ bool manifold_is_mine(const unsigned char* __restrict__ bodyOwner, int rank, int2 bodies)
+{
+    return !bodyOwner || max(bodyOwner[bodies.x], bodyOwner[bodies.y]) == rank;
+}
+
 __global__ void __launch_bounds__(kBlock) k_strip_hist(int M, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
-    const int* __restrict__ activity, int* __restrict__ hist)
+    const int* __restrict__ activity, const int2* __restrict__ manBody, const unsigned char* __restrict__ bodyOwner, int rank, int* __restrict__ hist,
+    int* __restrict__ cover)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     if (work[m] >= kMaxColours) return;
+    if (!manifold_is_mine(bodyOwner, rank, manBody[m])) return;
     const int2 b = jb[m];
     const int r1 = b.x < 0 ? -1 : (rowOf ? rowOf[b.x] : b.x), r2 = b.y < 0 ? -1 : (rowOf ? rowOf[b.y] : b.y);
     const int home = r1 < 0 ? r2 : (r2 < 0 ? r1 : min(r1, r2));
     if (home < 0) return;
+    if (r1 >= 0 && r2 >= 0 && r1 != r2)
+    {
+        atomicAdd(&cover[min(r1, r2)], 1);
+        atomicAdd(&cover[max(r1, r2)], -1);
+    }
     int weight = 8;
     if (activity)
     {
@@ -130,6 +144,29 @@ __global__ void __launch_bounds__(kBlock) k_strip_cuts(int nb, int S, const int*
     cuts[q] = lo;
 }
 
+// Move every cut to the nearest row in front of which NO manifold would be split, if there is one within `reach` rows
+// (between separate piles there is: then whole islands lie inside a strip, the cut sets are empty, and the order in which
+// an island's manifolds are relaxed, colour-major, no longer depends on where the cuts are: the island-parallel solve over
+// several devices relies on that for bit-identical results).  covered[r] > 0: a cut in front of row r splits manifolds.
+__global__ void __launch_bounds__(kBlock) k_strip_snap(int nb, int S, int reach, const int* __restrict__ covered, int* __restrict__ cuts)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q <= 0 || q >= S) return;
+    const int r0 = cuts[q];
+    for (int d = 0; d <= reach; ++d)
+    {
+        const int lo = r0 - d, hi = r0 + d;
+        if (lo > 0 && lo < nb && covered[lo] == 0) { cuts[q] = lo; return; }
+        if (hi > 0 && hi < nb && covered[hi] == 0) { cuts[q] = hi; return; }
+    }
+}
+
+__global__ void k_strip_monotonic(int S, int* __restrict__ cuts)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int q = 1; q <= S; ++q) cuts[q] = max(cuts[q], cuts[q - 1]);
+}
+
 // largest k in [0, S) with cuts[k] <= row: the strip that holds the row (empty strips are never returned)
 __device__ __forceinline__ int strip_of(const int* cuts, int S, int row)
 {
@@ -145,7 +182,8 @@ __device__ __forceinline__ int strip_of(const int* cuts, int S, int row)
 // classify, persist the colours, emit {class << 7 | colour, manifold} sort keys, flag the rows cut manifolds touch
 // (flags[row]: bit 0 = right-boundary row of its strip, bit 1 = left-boundary row)
 __global__ void __launch_bounds__(kBlock) k_strip_keys(int M, int S, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
-    const int* __restrict__ cutsG, int* __restrict__ manColour, uint2* __restrict__ keys, int* __restrict__ flags, int* __restrict__ header)
+    const int* __restrict__ cutsG, const int2* __restrict__ manBody, const unsigned char* __restrict__ bodyOwner, int rank, int* __restrict__ manColour,
+    uint2* __restrict__ keys, int* __restrict__ flags, int* __restrict__ header)
 {
     extern __shared__ int s_cuts[];
     for (int q = threadIdx.x; q <= S; q += blockDim.x) s_cuts[q] = cutsG[q];
@@ -157,8 +195,8 @@ __global__ void __launch_bounds__(kBlock) k_strip_keys(int M, int S, const int2*
     {
         const int c = work[m];
         manColour[m] = (c >= kMaxColours) ? -1 : c;
-        unsigned key = unsigned(2 * S) << 7;   // skipped: behind every class
-        if (c < kMaxColours)
+        unsigned key = unsigned(2 * S) << 7;   // skipped (no contact points, or another rank's island): behind every class
+        if (c < kMaxColours && manifold_is_mine(bodyOwner, rank, manBody[m]))
         {
             coloured = true;
             colour = c;
@@ -210,10 +248,9 @@ __global__ void __launch_bounds__(kBlock) k_strip_split_flags(int nb, const int*
     flagL[r] = (f >> 1) & 1;
 }
 
-// boundary row lists in row order, static-body ordinals
+// boundary row lists in row order
 __global__ void __launch_bounds__(kBlock) k_strip_lists(int nb, const int* __restrict__ flags, const int* __restrict__ prefixR, const int* __restrict__ prefixL,
-    const unsigned* __restrict__ order, const unsigned char* __restrict__ bodyStatic, int* __restrict__ bR, int* __restrict__ bL, int* __restrict__ staticOrd,
-    int* __restrict__ header)
+    int* __restrict__ bR, int* __restrict__ bL, int* __restrict__ header)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
@@ -221,8 +258,6 @@ __global__ void __launch_bounds__(kBlock) k_strip_lists(int nb, const int* __res
     if (f & 1) bR[prefixR[r]] = r;
     if (f & 2) bL[prefixL[r]] = r;
     if (f == 3) atomicOr(&header[H_REJECT], kRejectBothSides);
-    const unsigned body = order ? order[r] : unsigned(r);
-    staticOrd[r] = bodyStatic[body] ? atomicAdd(&header[H_STATICS], 1) : -1;   // any bijection will do: it only addresses the words
 }
 
 // per strip: first boundary row of each kind, sizes for the kernel's shared memory
@@ -517,7 +552,6 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
     PHYX_TRY(sp.prefixL.reserve(size_t(nb + 1) * sizeof(int)));
     PHYX_TRY(sp.bR.reserve(size_t(nb + 1) * sizeof(int)));
     PHYX_TRY(sp.bL.reserve(size_t(nb + 1) * sizeof(int)));
-    PHYX_TRY(sp.staticOrd.reserve(size_t(nb + 1) * sizeof(int)));
     PHYX_TRY(sp.cuts.reserve(size_t(S + 2) * sizeof(int)));
     PHYX_TRY(sp.bStart.reserve(size_t(2 * S + 4) * sizeof(int)));
     PHYX_TRY(sp.binRange.reserve(size_t(bins) * sizeof(int2)));
@@ -527,23 +561,34 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
     int* flagL = flags + 2 * (nb + 1);
     PHYX_CUDA(cudaMemsetAsync(header, 0, 64 * sizeof(int), c->stream));
     PHYX_CUDA(cudaMemsetAsync(sp.hist.ptr, 0, size_t(nb + 1) * sizeof(int), c->stream));
+    PHYX_CUDA(cudaMemsetAsync(sp.prefixL.ptr, 0, size_t(nb + 1) * sizeof(int), c->stream));   // `cover` until the boundary lists need it
     PHYX_CUDA(cudaMemsetAsync(flags, 0, size_t(nb + 1) * sizeof(int), c->stream));
     PHYX_CUDA(cudaMemsetAsync(sp.binRange.ptr, 0, size_t(bins) * sizeof(int2), c->stream));
 
     // cuts that balance the manifold count (a manifold counts for its lower dynamic row)
     const int* activity = (c->activityValid && c->activityBodies == nb) ? c->bodyActivity.as<int>() : nullptr;
-    k_strip_hist<<<grid, kBlock, 0, c->stream>>>(M, jb, work, rowOf, activity, sp.hist.as<int>());
+    const bool split = c->islandRanks > 1 && c->islandsValid && c->islandBodies == nb;
+    const unsigned char* bodyOwner = split ? c->bodyOwner.as<unsigned char>() : nullptr;
+    int* cover = sp.prefixL.as<int>();
+    k_strip_hist<<<grid, kBlock, 0, c->stream>>>(M, jb, work, rowOf, activity, c->manBody.as<int2>(), bodyOwner, c->islandRank, sp.hist.as<int>(), cover);
     k_strip_hist_rows<<<gridB, kBlock, 0, c->stream>>>(nb, order, c->bodyStatic.as<unsigned char>(), sp.hist.as<int>());
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, sp.hist.as<int>(), sp.prefixR.as<int>(), nb, header + H_SCAN_TOTAL));
     k_strip_cuts<<<gridS, kBlock, 0, c->stream>>>(nb, S, sp.prefixR.as<int>(), header + H_SCAN_TOTAL, sp.cuts.as<int>());
     c->launches += 2;
+    if (S > 1)
+    {
+        PHYX_TRY(exclusive_scan_i32(c, cover, cover, nb, nullptr));
+        k_strip_snap<<<gridS, kBlock, 0, c->stream>>>(nb, S, std::max(1, nb / S / 2), cover, sp.cuts.as<int>());
+        k_strip_monotonic<<<1, 32, 0, c->stream>>>(S, sp.cuts.as<int>());
+        c->launches += 2;
+    }
 
     // classes, sort keys, boundary flags; two stable passes: colour (7 bits), then class
     PHYX_TRY(c->colourKeys.reserve(size_t(M) * sizeof(uint2)));
     PHYX_TRY(c->colourSorted.reserve(size_t(M) * sizeof(uint2)));
-    k_strip_keys<<<grid, kBlock, size_t(S + 1) * sizeof(int), c->stream>>>(M, S, jb, work, rowOf, sp.cuts.as<int>(), c->manColour.as<int>(), c->colourKeys.as<uint2>(),
-        flags, header);
+    k_strip_keys<<<grid, kBlock, size_t(S + 1) * sizeof(int), c->stream>>>(M, S, jb, work, rowOf, sp.cuts.as<int>(), c->manBody.as<int2>(), bodyOwner, c->islandRank,
+        c->manColour.as<int>(), c->colourKeys.as<uint2>(), flags, header);
     c->launches++;
     int digits = 1;
     while (digits < 2 * S + 1) digits <<= 1;
@@ -556,8 +601,8 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, flagR, sp.prefixR.as<int>(), nb, header + H_TOTAL_R));
     PHYX_TRY(exclusive_scan_i32(c, flagL, sp.prefixL.as<int>(), nb, header + H_TOTAL_L));
-    k_strip_lists<<<gridB, kBlock, 0, c->stream>>>(nb, flags, sp.prefixR.as<int>(), sp.prefixL.as<int>(), order, c->bodyStatic.as<unsigned char>(),
-        sp.bR.as<int>(), sp.bL.as<int>(), sp.staticOrd.as<int>(), header);
+    k_strip_lists<<<gridB, kBlock, 0, c->stream>>>(nb, flags, sp.prefixR.as<int>(), sp.prefixL.as<int>(),
+        sp.bR.as<int>(), sp.bL.as<int>(), header);
     k_strip_starts<<<gridS, kBlock, 0, c->stream>>>(nb, S, sp.cuts.as<int>(), sp.prefixR.as<int>(), sp.prefixL.as<int>(), sp.bStart.as<int>(), header);
     c->launches += 2;
 
@@ -585,7 +630,6 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
     sp.strips = S;
     sp.maxStripRows = host[H_MAXROWS];
     sp.maxCutRows = host[H_MAXCUT];
-    sp.numStatics = host[H_STATICS];
     sp.manifolds = host[H_MANIFOLDS];
     sp.maxBin = host[H_MAXBIN];
     sp.colours = host[H_COLOURS];
@@ -593,7 +637,6 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
     int rejected = host[H_REJECT];
     if (sp.manifolds == 0) rejected |= kRejectEmpty;
     if (strip_smem_bytes(sp.maxStripRows + 9, sp.maxCutRows + 9, sp.maxBin + 9) > (S > c->numSMs ? kStripSmemLimit2 : kStripSmemLimit)) rejected |= kRejectSmem;
-    if (size_t(sp.numStatics) * size_t(S) * 16 > (size_t(256) << 20)) rejected |= kRejectStatics;
     if (sp.maxStripRows > 65000 || sp.maxCutRows > 65000 || sp.maxBin > 65000) rejected |= kRejectSmem;
     sp.rejected = rejected;
     if (rejected) return PHYX_B200_OK;
@@ -633,7 +676,7 @@ int strip_host_levels(phyx_b200_ctx* c, std::vector<int>* classStart)
 void strip_release(phyx_b200_ctx* c)
 {
     StripPlan& sp = c->strip;
-    DevBuf* bufs[] = { &sp.cuts, &sp.binRange, &sp.flags, &sp.prefixR, &sp.prefixL, &sp.bR, &sp.bL, &sp.bStart, &sp.staticOrd, &sp.header, &sp.words, &sp.sync, &sp.hist, &sp.trace, &sp.pairTest };
+    DevBuf* bufs[] = { &sp.cuts, &sp.binRange, &sp.flags, &sp.prefixR, &sp.prefixL, &sp.bR, &sp.bL, &sp.bStart, &sp.header, &sp.sync, &sp.hist, &sp.trace, &sp.pairTest };
     for (DevBuf* b : bufs) b->release();
     sp.valid = false;
 }
@@ -653,10 +696,6 @@ struct StripParams
     const int* bR;                   // right-boundary rows (global row numbers), row order
     const int* bL;                   // left-boundary rows
     const int* bStart;               // [0..S] starts in bR, [S+1 .. 2S+1] starts in bL
-    const int* staticOrd;            // per row: ordinal of a static body, else -1
-    unsigned long long* staticWords; // [2 phases][S][numStatics]
-    int numStatics;
-    int* processed;                  // per manifold slot: tick of the bin pass that ran it (manifolds with a static body only)
     unsigned long long* flagA;       // [S] "my interior pass `seq` is done and my left-boundary rows are in global memory"
     unsigned long long* flagB;       // [S] "cut set k of pass `seq` is done and strip k+1's left-boundary rows are in global memory"
     unsigned long long* done;        // [2][doneStride] per iteration: arrivals | productive CTAs << 32
@@ -721,7 +760,6 @@ struct StripCta
     int* s_count;       // [2] worklist lengths (alternating)
     int k, row0, nRows, nL, nR, nLn, nInt, nCut;
     int parity;         // which worklist counter the next bin pass uses
-    int wakePasses;
     unsigned active[2];
     long long clk[3];   // developer aid: SM clocks spent in step 1 / step 2 / (spare) of the bins of the current pass (thread 0)
 };
@@ -782,188 +820,156 @@ __device__ __forceinline__ void prefetch_idx(const StripParams& P, int2 bin, uns
 }
 
 // One bin (one colour of one class) of one iteration.  PHASE 0: SolveJointsImpulses (Solver.cpp:781-910), PHASE 1:
-// SolveJointsDisplacement (:937-1014).  `pre` holds the index words of this thread's first kStripU candidates; on
-// return it holds those of `next`.  words: the class's static-body words of this phase.  dummyRow: a shared-memory row
-// nobody owns (index words of static bodies are redirected there for the speculative lastIteration read).  Returns
-// "this thread saw a productive joint".
+// SolveJointsDisplacement (:937-1014).  `pre` holds the test words of this thread's first kStripU candidates; on return
+// it holds those of `next`.  dummyRow: a shared-memory row nobody owns, whose lastIteration is "never" (the test words of
+// static bodies and of slots beyond the bin point there).  Returns "this thread saw a productive joint".
+//
+// Static bodies.  The reference keeps lastIteration on static bodies too and the skip test reads it (Solver.cpp:790-798,
+// 903-910): a productive ground contact of one pile keeps the ground contacts of every other pile awake.  That coupling is
+// an artefact of sharing one record, not physics, and it would make an island's result depend on which other islands
+// happen to be relaxed by the same CTA (or device).  The strip kernel therefore tracks a static body's lastIteration PER
+// DYNAMIC PARTNER; since a productive joint marks both of its bodies, the partner's own lastIteration already says
+// everything such a private copy would, and the static side of the test drops out.  The oracle reproduces this exactly
+// on the equivalent problem in which every (dynamic body, static body) pair has its own copy of the static body
+// (tests/conftest.py); the grid-barrier forms of solve.cu keep the reference's shared record.
 template <int PHASE, int T>
-__device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, float4* rowsS, int dummyRow, const float4* __restrict__ rowsG, unsigned long long* words,
-    int2 bin, int2 next, int it, int tick, unsigned (&pre)[kStripU])
+__device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, float4* rowsS, int dummyRow, const float4* __restrict__ rowsG, int2 bin, int2 next, int it,
+    unsigned (&pre)[kStripU])
 {
     const int n = bin.y - bin.x;
     const int lane = threadIdx.x & 31;
     const unsigned below = (1u << lane) - 1u;
     bool anyProductive = false;
-    bool firstPass = true;
     const long long c0 = P.trace ? clock64() : 0;
-    for (;;)
+    int* count = &s.s_count[s.parity];
+    // ---- step 1: the skip test (Solver.cpp:790-792, for both joints of a manifold at once, see solve.cu paired levels).
+    // kStripU candidates per thread from prefetched test words; slots beyond the bin are skipped as a block (n is uniform)
     {
-        int* count = &s.s_count[s.parity];
-        // ---- step 1: the skip test (Solver.cpp:790-792, for both joints of a manifold at once, see solve.cu paired levels).
-        // All shared-memory reads of a thread's candidates are issued together; the rare candidates with a static body
-        // (whose lastIteration lives in a global word) are fixed up afterwards.
-        if (firstPass)
+        bool active[kStripU];
+        unsigned m[kStripU];
+        int warpTotal = 0;
+#pragma unroll
+        for (int u = 0; u < kStripU; ++u)
         {
-            // kStripU candidates per thread; slots beyond the bin are skipped as a block (n is uniform)
-            bool active[kStripU];
-            unsigned m[kStripU];
-            int warpTotal = 0;
+            active[u] = false;
+            m[u] = 0u;
+            if (u * T < n)
+            {
+                const unsigned t = pre[u];
+                const int ra = min(int(t & 0xffffu), dummyRow), rb = min(int(t >> 16), dummyRow);
+                const int la = __float_as_int(rowsS[ra].w), lb = __float_as_int(rowsS[rb].w);
+                active[u] = (la > it - 2) || (lb > it - 2);
+                m[u] = __ballot_sync(0xffffffffu, active[u]);
+                warpTotal += __popc(m[u]);
+            }
+        }
+        // the test words are used up: fetch those of the next bin now, a whole bin pass ahead of their use
+        prefetch_idx<T>(P, next, pre);
+        if (warpTotal)
+        {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(count, warpTotal);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            // candidates of this warp in (u, lane) order
 #pragma unroll
             for (int u = 0; u < kStripU; ++u)
             {
-                active[u] = false;
-                m[u] = 0u;
-                if (u * T < n)
-                {
-                    const unsigned t = pre[u];
-                    const int ra = min(int(t & 0xffffu), dummyRow), rb = min(int(t >> 16), dummyRow);
-                    int la = __float_as_int(rowsS[ra].w), lb = __float_as_int(rowsS[rb].w);
-                    if ((t & 0xffffu) == 0xffffu || (t >> 16) == 0xffffu)   // rare: a static body, or a slot beyond the bin
-                    {
-                        const int i = int(threadIdx.x) + u * T;
-                        la = lb = -(1 << 30);
-                        if (i < n)
-                        {
-                            const int2 idx = __ldg(&P.pairIdx[bin.x + i]);
-                            const unsigned pos = unsigned(2 * (bin.x + i));
-                            la = (idx.x & kStaticBit) ? static_visible_last(&words[P.staticOrd[idx.x & kBodyMask]], it, pos) : __float_as_int(rowsS[idx.x & kBodyMask].w);
-                            lb = (idx.y & kStaticBit) ? static_visible_last(&words[P.staticOrd[idx.y & kBodyMask]], it, pos) : __float_as_int(rowsS[idx.y & kBodyMask].w);
-                        }
-                    }
-                    active[u] = (la > it - 2) || (lb > it - 2);
-                    m[u] = __ballot_sync(0xffffffffu, active[u]);
-                    warpTotal += __popc(m[u]);
-                }
-            }
-            // the index words are used up: fetch those of the next bin now, a whole bin pass ahead of their use
-            prefetch_idx<T>(P, next, pre);
-            if (warpTotal)
-            {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(count, warpTotal);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                // candidates of this warp in (u, lane) order
-#pragma unroll
-                for (int u = 0; u < kStripU; ++u)
-                {
-                    if (active[u]) s.s_work[base + __popc(m[u] & below)] = (unsigned short)(int(threadIdx.x) + u * T);
-                    base += __popc(m[u]);
-                }
+                if (active[u]) s.s_work[base + __popc(m[u] & below)] = (unsigned short)(int(threadIdx.x) + u * T);
+                base += __popc(m[u]);
             }
         }
-        // candidates beyond the prefetched ones (bins larger than kStripU * T), and wake passes (everything again)
-        for (int i0 = firstPass ? kStripU * T : 0; i0 < n; i0 += T)
+    }
+    // candidates beyond the prefetched ones (bins larger than kStripU * T)
+    for (int i0 = kStripU * T; i0 < n; i0 += T)
+    {
+        const int i = i0 + int(threadIdx.x);
+        bool active = false;
+        if (i < n)
         {
-            const int i = i0 + int(threadIdx.x);
-            bool active = false;
-            if (i < n)
-            {
-                const int p = bin.x + i;
-                const int2 idx = __ldg(&P.pairIdx[p]);
-                const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit;
-                bool consider = true;
-                if (!firstPass) consider = (st1 || st2) && __ldcg(&P.processed[p]) != tick;   // wake pass: only what a static body can wake
-                if (consider)
-                {
-                    const int r1 = idx.x & kBodyMask, r2 = idx.y & kBodyMask;
-                    const unsigned pos = unsigned(2 * p);
-                    const int last1 = st1 ? static_visible_last(&words[P.staticOrd[r1]], it, pos) : __float_as_int(rowsS[r1].w);
-                    const int last2 = st2 ? static_visible_last(&words[P.staticOrd[r2]], it, pos) : __float_as_int(rowsS[r2].w);
-                    active = (last1 > it - 2) || (last2 > it - 2);
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, active);
-            if (m)
-            {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(count, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (active) s.s_work[base + __popc(m & below)] = (unsigned short)i;
-            }
+            const unsigned t = __ldg(&P.pairTest[bin.x + i]);
+            const int ra = min(int(t & 0xffffu), dummyRow), rb = min(int(t >> 16), dummyRow);
+            active = (__float_as_int(rowsS[ra].w) > it - 2) || (__float_as_int(rowsS[rb].w) > it - 2);
         }
-        __syncthreads();
-        const long long c1 = P.trace ? clock64() : 0;
-        const int total = *count;
-        if (threadIdx.x == 0) s.s_count[s.parity ^ 1] = 0;  // the next bin pass counts there
-        s.parity ^= 1;
+        const unsigned m = __ballot_sync(0xffffffffu, active);
+        if (m)
+        {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (active) s.s_work[base + __popc(m & below)] = (unsigned short)i;
+        }
+    }
+    __syncthreads();
+    const long long c1 = P.trace ? clock64() : 0;
+    const int total = *count;
+    if (threadIdx.x == 0) s.s_count[s.parity ^ 1] = 0;  // the next bin pass counts there
+    s.parity ^= 1;
 
-        // ---- step 2: relax the worklist, one entry per thread and round.  Consecutive entries (neighbouring records) go to
-        // consecutive lanes: dealing them across the warps instead was measured 3x slower (DRAM locality of the record fetch)
-        bool wake = false;
-        for (int w = threadIdx.x; w < total; w += T)
+    // ---- step 2: relax the worklist, one entry per thread and round.  Consecutive entries (neighbouring records) go to
+    // consecutive lanes: dealing them across the warps instead was measured 3x slower (DRAM locality of the record fetch)
+    for (int w = threadIdx.x; w < total; w += T)
+    {
+        const int p = bin.x + s.s_work[w];
+        const int2 idx = __ldg(&P.pairIdx[p]);
+        const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
+        const float4 a0 = __ldcs(rec), b0 = __ldcs(rec + 1), c2 = __ldcs(rec + 2), nd = __ldcs(rec + 3);
+        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1, accv;
+        if (PHASE == 0)
         {
-            const int p = bin.x + s.s_work[w];
-            const int2 idx = __ldg(&P.pairIdx[p]);
-            const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
-            const float4 a0 = __ldcs(rec), b0 = __ldcs(rec + 1), c2 = __ldcs(rec + 2), nd = __ldcs(rec + 3);
-            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1, accv;
-            if (PHASE == 0)
-            {
-                a1 = __ldcs(rec + 4);
-                b1 = __ldcs(rec + 5);
-                accv = __ldcs(reinterpret_cast<const float4*>(&P.accNF[2 * p]));
-            }
-            else
-            {
-                const float2 a = __ldcs(reinterpret_cast<const float2*>(&P.accD[2 * p]));
-                accv = make_float4(a.x, a.y, 0.f, 0.f);
-            }
-            const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit, haveB = idx.y < 0;
-            const int r1 = idx.x & kBodyMask, r2 = idx.y & kBodyMask;
-            float4 w1 = st1 ? __ldcg(&rowsG[r1]) : rowsS[r1];
-            float4 w2 = st2 ? __ldcg(&rowsG[r2]) : rowsS[r2];
-            const int last1 = __float_as_int(w1.w), last2 = __float_as_int(w2.w);   // used for dynamic bodies only
-            const float4 a3 = make_float4(0.f, 0.f, nd.x, nd.y), b3 = make_float4(0.f, 0.f, nd.z, nd.w);
-            float2 accA, accB;
-            if (PHASE == 0)
-            {
-                accA = make_float2(accv.x, accv.y);
-                accB = make_float2(accv.z, accv.w);
-            }
-            else
-            {
-                accA = make_float2(accv.x, 0.f);
-                accB = make_float2(accv.y, 0.f);
-            }
-            s.active[PHASE] += haveB ? 2u : 1u;
-            const bool productiveA = relax<PHASE>(a0, a1, c2, a3, accA, w1, w2, false);
-            bool productiveB = false;
-            if (haveB) productiveB = relax<PHASE>(b0, b1, c2, b3, accB, w1, w2, false);
-            if (PHASE == 0)
-                __stcs(reinterpret_cast<float4*>(&P.accNF[2 * p]), make_float4(accA.x, accA.y, accB.x, accB.y));
-            else
-                __stcs(reinterpret_cast<float2*>(&P.accD[2 * p]), make_float2(accA.x, accB.x));
-            // lastIteration = it where productive (Solver.cpp:903-910); a static body is marked at the position of
-            // the first productive joint
-            const bool productive = productiveA || productiveB;
-            const unsigned pos = unsigned(2 * p), markPos = productiveA ? pos : pos + 1;
-            if (!st1)
-            {
-                w1.w = __int_as_float(productive ? it : last1);
-                rowsS[r1] = w1;
-            }
-            else if (productive)
-                wake |= static_mark(&words[P.staticOrd[r1]], it, markPos, nullptr);
-            if (!st2)
-            {
-                w2.w = __int_as_float(productive ? it : last2);
-                rowsS[r2] = w2;
-            }
-            else if (productive)
-                wake |= static_mark(&words[P.staticOrd[r2]], it, markPos, nullptr);
-            if (st1 || st2) __stcg(&P.processed[p], tick);
-            anyProductive |= productive;
+            a1 = __ldcs(rec + 4);
+            b1 = __ldcs(rec + 5);
+            accv = __ldcs(reinterpret_cast<const float4*>(&P.accNF[2 * p]));
         }
-        // rows of this bin are written: the next bin (or a wake pass over this one) may read them
-        const int again = __syncthreads_or(wake ? 1 : 0);
-        if (P.trace && firstPass)
+        else
         {
-            s.clk[0] += c1 - c0;
-            s.clk[1] += clock64() - c1;
+            const float2 a = __ldcs(reinterpret_cast<const float2*>(&P.accD[2 * p]));
+            accv = make_float4(a.x, a.y, 0.f, 0.f);
         }
-        if (!again) break;
-        firstPass = false;
-        if (threadIdx.x == 0) ++s.wakePasses;
+        const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit, haveB = idx.y < 0;
+        const int r1 = idx.x & kBodyMask, r2 = idx.y & kBodyMask;
+        float4 w1 = st1 ? __ldcg(&rowsG[r1]) : rowsS[r1];
+        float4 w2 = st2 ? __ldcg(&rowsG[r2]) : rowsS[r2];
+        const int last1 = __float_as_int(w1.w), last2 = __float_as_int(w2.w);   // used for dynamic bodies only
+        const float4 a3 = make_float4(0.f, 0.f, nd.x, nd.y), b3 = make_float4(0.f, 0.f, nd.z, nd.w);
+        float2 accA, accB;
+        if (PHASE == 0)
+        {
+            accA = make_float2(accv.x, accv.y);
+            accB = make_float2(accv.z, accv.w);
+        }
+        else
+        {
+            accA = make_float2(accv.x, 0.f);
+            accB = make_float2(accv.y, 0.f);
+        }
+        s.active[PHASE] += haveB ? 2u : 1u;
+        const bool productiveA = relax<PHASE>(a0, a1, c2, a3, accA, w1, w2, false);
+        bool productiveB = false;
+        if (haveB) productiveB = relax<PHASE>(b0, b1, c2, b3, accB, w1, w2, false);
+        if (PHASE == 0)
+            __stcs(reinterpret_cast<float4*>(&P.accNF[2 * p]), make_float4(accA.x, accA.y, accB.x, accB.y));
+        else
+            __stcs(reinterpret_cast<float2*>(&P.accD[2 * p]), make_float2(accA.x, accB.x));
+        // lastIteration = it where productive (Solver.cpp:903-910)
+        const bool productive = productiveA || productiveB;
+        if (!st1)
+        {
+            w1.w = __int_as_float(productive ? it : last1);
+            rowsS[r1] = w1;
+        }
+        if (!st2)
+        {
+            w2.w = __int_as_float(productive ? it : last2);
+            rowsS[r2] = w2;
+        }
+        anyProductive |= productive;
+    }
+    // rows of this bin are written: the next bin may read them
+    __syncthreads();
+    if (P.trace)
+    {
+        s.clk[0] += c1 - c0;
+        s.clk[1] += clock64() - c1;
     }
     return anyProductive;
 }
@@ -974,7 +980,6 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
 {
     constexpr int PHASE = MODE == 1 ? 1 : 0;
     float4* rowsG = P.rows[PHASE];
-    unsigned long long* words = P.staticWords + (size_t(PHASE) * P.S + s.k) * P.numStatics;
     const int k = s.k, nBins = s.nInt + s.nCut;
     bool any = false;
     trace_mark(P, k, passIndex, 0);
@@ -985,7 +990,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
         if (MODE < 0)
             prestep_bin<T>(P, s.s_rows, rowsG, s.s_bins[b]);
         else
-            any |= solve_bin<PHASE, T>(P, s, s.s_rows, P.rowCap - 1, rowsG, words, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, passIndex * 256 + b + 1, pre);
+            any |= solve_bin<PHASE, T>(P, s, s.s_rows, P.rowCap - 1, rowsG, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, pre);
     }
     trace_mark(P, k, passIndex, 1);
     if (P.trace && threadIdx.x == 0 && passIndex < P.tracePasses)
@@ -1015,7 +1020,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
                 if (MODE < 0)
                     prestep_bin<T>(P, s.s_cut, rowsG, s.s_bins[b]);
                 else
-                    any |= solve_bin<PHASE, T>(P, s, s.s_cut, P.cutCap - 1, rowsG, words, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, passIndex * 256 + b + 1, pre);
+                    any |= solve_bin<PHASE, T>(P, s, s.s_cut, P.cutCap - 1, rowsG, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, pre);
             }
             for (int i = threadIdx.x; i < s.nR; i += T) s.s_rows[s.s_listR[i]] = s.s_cut[i];
             for (int i = threadIdx.x; i < s.nLn; i += T) __stcg(&rowsG[s.s_listN[i]], s.s_cut[s.nR + i]);
@@ -1095,7 +1100,11 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
     s.nL = bLs[k + 1] - bLs[k];
     s.nLn = k + 1 < S ? bLs[k + 2] - bLs[k + 1] : 0;
     s.parity = 0;
-    s.wakePasses = 0;
+    if (threadIdx.x == 0)   // the rows that test words of static bodies and of empty slots point at: lastIteration = never
+    {
+        s.s_rows[P.rowCap - 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-(1 << 30)));
+        s.s_cut[P.cutCap - 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-(1 << 30)));
+    }
     s.active[0] = s.active[1] = 0u;
 
     // the strip's rows: one bulk copy
@@ -1187,7 +1196,6 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.activeTotal[phase], static_cast<unsigned long long>(v));
     }
-    if (threadIdx.x == 0 && s.wakePasses) atomicAdd(&P.result[2], s.wakePasses);
     // iteration counts as the reference loop reports them: up to and including the first non-productive iteration
     if (k == 0 && threadIdx.x == 0)
     {
@@ -1219,10 +1227,7 @@ int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, floa
     const int stride = std::max(I, D) + 2;
     const size_t syncWords = size_t(2) * S + 2 * size_t(stride) + 8;
     PHYX_TRY(sp.sync.reserve(syncWords * 8));
-    const size_t wordCount = std::max<size_t>(size_t(2) * S * sp.numStatics, 1);
-    PHYX_TRY(sp.words.reserve(wordCount * 8));
     PHYX_CUDA(cudaMemsetAsync(sp.sync.ptr, 0, syncWords * 8, c->stream));
-    PHYX_CUDA(cudaMemsetAsync(sp.words.ptr, 0, wordCount * 8, c->stream));
 
     StripParams P;
     memset(&P, 0, sizeof(P));
@@ -1238,10 +1243,6 @@ int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, floa
     P.bR = sp.bR.as<int>();
     P.bL = sp.bL.as<int>();
     P.bStart = sp.bStart.as<int>();
-    P.staticOrd = sp.staticOrd.as<int>();
-    P.staticWords = sp.words.as<unsigned long long>();
-    P.numStatics = sp.numStatics;
-    P.processed = c->processed.as<int>();
     unsigned long long* sync = sp.sync.as<unsigned long long>();
     P.flagA = sync;
     P.flagB = sync + S;

@@ -96,6 +96,16 @@ void Device::download(RigidBody* bodies, int count)
     hostStale = false;
 }
 
+void Device::unpin(void* buffer)
+{
+    if (buffer && buffer == pinnedPtr)
+    {
+        if (ctx) phyx_b200_host_unregister(ctx, pinnedPtr);
+        pinnedPtr = nullptr;
+        pinnedBytes = 0;
+    }
+}
+
 Device::~Device()
 {
     if (ctx && pinnedPtr) phyx_b200_host_unregister(ctx, pinnedPtr);
@@ -167,6 +177,7 @@ NOINLINE void Collider::UpdatePairs(WorkQueue&, RigidBody*, size_t)
 NOINLINE void Collider::UpdateManifolds(WorkQueue&, RigidBody*)
 {
     StageTimer t(&device->stageMs[3]);
+    device->ensure();
     PHYX_CALL(phyx_b200_update_manifolds(device->ctx));
     if (!device->inUpdate) device->mirror(*this, *solver, mirrorContents);
 }
@@ -174,6 +185,7 @@ NOINLINE void Collider::UpdateManifolds(WorkQueue&, RigidBody*)
 NOINLINE void Collider::PackManifolds(RigidBody*)
 {
     StageTimer t(&device->stageMs[4]);
+    device->ensure();
     PHYX_CALL(phyx_b200_pack_manifolds(device->ctx));
     if (!device->inUpdate) device->mirror(*this, *solver, mirrorContents);
 }
@@ -198,8 +210,20 @@ NOINLINE void Solver::SolveJoints(WorkQueue&, RigidBody* bodies, int bodiesCount
     }
     cfg.flags = solveFlags;
     PHYX_CALL(phyx_b200_solve_resident(device->ctx, &cfg, &device->lastSolve));
-    islandCount = 1;                       // Island_Single bookkeeping (reference src/Solver.cpp:108-109)
-    islandMaxSize = device->lastSolve.joints;
+    if (configuration.islandMode == Configuration::Island_Multiple || configuration.islandMode == Configuration::Island_MultipleSloppy)
+    {
+        // GatherIslands (reference src/Solver.cpp:285-454) on the device: the counters the demo's HUD reads.  The solve itself
+        // relaxes all islands at once whatever the island mode (a colour spans the world).
+        int32_t groups = 0, largest = 0;
+        PHYX_CALL(phyx_b200_build_islands(device->ctx, &groups, &largest, nullptr));
+        islandCount = groups;
+        islandMaxSize = largest;
+    }
+    else
+    {
+        islandCount = 1;                   // Island_Single bookkeeping (reference src/Solver.cpp:108-109)
+        islandMaxSize = device->lastSolve.joints;
+    }
     if (!device->inUpdate)
     {
         device->download(bodies, bodiesCount);
@@ -211,13 +235,21 @@ NOINLINE void Solver::SolveJoints(WorkQueue&, RigidBody* bodies, int bodiesCount
 
 World::World() : collisionTime(0), mergeTime(0), solveTime(0), gravity(0)
 {
+    // World::bodies is page-locked in place: whatever makes it reallocate must undo that first (AlignedArray::releaseHook)
+    bodies.releaseHook = [](void* buffer, void* user) { static_cast<phyx_host::Device*>(user)->unpin(buffer); };
+    bodies.releaseUser = &device;
     collider.device = &device;
     collider.solver = &solver;
     solver.device = &device;
     solver.collider = &collider;
 }
 
-World::~World() {}
+World::~World()
+{
+    // members are destroyed in reverse order (device before bodies): undo the page-lock while the context is still alive
+    device.unpin(bodies.data);
+    bodies.releaseHook = nullptr;
+}
 
 RigidBody* World::AddBody(Coords2f coords, Vector2f size)
 {

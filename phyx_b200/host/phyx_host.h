@@ -234,9 +234,14 @@ template <typename T> struct AlignedArray
     T* data;
     int size;
     int capacity;
+    // Called with (data, releaseUser) right before a buffer is given back to the allocator.  World::bodies is page-locked
+    // in place (cudaHostRegister) for full-rate PCIe copies: CUDA requires the range to be unregistered before it is freed,
+    // whichever call makes the array grow (AddBody, push_back, resize, move assignment, destruction).
+    void (*releaseHook)(void* buffer, void* user) = nullptr;
+    void* releaseUser = nullptr;
 
     AlignedArray() : data(nullptr), size(0), capacity(0) {}
-    ~AlignedArray() { std::free(data); }
+    ~AlignedArray() { release(); }
     AlignedArray(const AlignedArray&) = delete;
     AlignedArray& operator=(const AlignedArray&) = delete;
     AlignedArray(AlignedArray&& o) : data(o.data), size(o.size), capacity(o.capacity) { o.data = nullptr; o.size = o.capacity = 0; }
@@ -244,7 +249,7 @@ template <typename T> struct AlignedArray
     {
         if (this != &o)
         {
-            std::free(data);
+            release();
             data = o.data; size = o.size; capacity = o.capacity;
             o.data = nullptr; o.size = o.capacity = 0;
         }
@@ -273,6 +278,12 @@ template <typename T> struct AlignedArray
     void resize_copy(int n) { if (n > capacity) grow(n, true); size = n; }
 
   private:
+    void release()
+    {
+        if (data && releaseHook) releaseHook(data, releaseUser);
+        std::free(data);
+        data = nullptr;
+    }
     void grow(int need, bool keep)
     {
         int cap = capacity;
@@ -280,7 +291,7 @@ template <typename T> struct AlignedArray
         size_t bytes = (size_t(cap) * sizeof(T) + 32 + 31) & ~size_t(31);   // tail pad as in the reference
         T* fresh = static_cast<T*>(std::aligned_alloc(32, bytes));
         if (data && keep) std::memcpy(fresh, data, size_t(size) * sizeof(T));
-        std::free(data);
+        release();
         data = fresh;
         capacity = cap;
     }
@@ -354,6 +365,7 @@ struct Device
     void ensure();                                   // create the context (aborts with a message on failure)
     void upload(RigidBody* bodies, int count);       // AoS -> HBM
     void download(RigidBody* bodies, int count);     // HBM -> AoS
+    void unpin(void* buffer);                        // `buffer` is about to be freed: undo the page-lock if it is the pinned one
     void mirror(Collider& collider, Solver& solver, bool contents);   // device caches -> host arrays
     void followReset(Collider& collider, Solver& solver);             // host arrays cleared -> clear device caches
     ~Device();

@@ -134,6 +134,12 @@ API void phyxw_reset_stage_ms(void* h)
 }
 API void phyxw_get_solve_stats(void* h, phyx_b200_solve_stats* out) { *out = static_cast<Handle*>(h)->world.device.lastSolve; }
 API void phyxw_get_broadphase_stats(void* h, phyx_b200_broadphase_stats* out) { *out = static_cast<Handle*>(h)->world.device.lastBroadphase; }
+API void phyxw_get_island_counts(void* h, int* out2)
+{
+    const Solver& s = static_cast<Handle*>(h)->world.solver;
+    out2[0] = s.islandCount;
+    out2[1] = s.islandMaxSize;
+}
 API void* phyxw_context(void* h)
 {
     Handle* s = static_cast<Handle*>(h);

@@ -1,4 +1,15 @@
-"""Island partition of a scene across ranks (host logic of the multi-GPU path).
+"""Island-parallel execution of ONE world over several GPUs.
+
+Product path (device island builder, phyx_b200/csrc/islands.cu): every rank holds the whole world and runs the other stages
+redundantly; Solver::SolveJoints is split BY ISLAND (reference src/Solver.cpp:73-92, 285-454): each rank relaxes a
+contiguous run of island groups with about equal joint counts, with no communication inside the solve; afterwards the
+ranks' results (velocity rows of their bodies, cached impulses of their joints) are merged by ONE integer-sum all-reduce
+over NCCL per step (`IslandParallelWorld`, one process per GPU; `IslandGroup`, all ranks in one process, for tests).
+Results are bit-identical to the one-device run of the same world whenever no manifold straddles a strip cut, which is
+the case when the islands are separate piles (tests/test_gpu_islands.py).
+
+The functions at the end (`find_islands`, `partition`, `rank_scene`) are the older geometric estimate of the islands made
+from the scene description before any contact exists; they remain as host-side helpers (tests/test_islands_gloo.py).
 
 Bodies of different islands never exchange impulses (reference src/Solver.cpp:285-454: union-find
 over dynamic bodies joined by contact joints; static bodies do not merge islands), so each rank can
@@ -51,3 +62,88 @@ def rank_scene(scene, rank, world_size, margin=1.0):
     """The rows of `scene` that rank `rank` simulates (statics replicated) and their global indices."""
     idx = partition(scene, world_size, margin)[rank]
     return np.asarray(scene, dtype=np.float32)[idx], idx
+
+
+# ---------------------------------------------------------------------------------------------------
+# product path: islands from the contact graph (device), solve split by island, merged by an integer-sum all-reduce
+def stages_before_solve(ctx):
+    from . import scenes
+
+    ctx.integrate_velocity(scenes.DT, scenes.GRAVITY)
+    ctx.update_broadphase()
+    bp = ctx.update_pairs()
+    ctx.update_manifolds()
+    ctx.pack_manifolds()
+    ctx.refresh_contact_joints()
+    return bp
+
+
+class IslandGroup:
+    """`ranks` replicas of one world in ONE process (contexts may share a device): what the single-GPU tests drive.  The
+    merge is the same integer sum the multi-process path does with NCCL, here with torch on the device."""
+
+    def __init__(self, contexts, bodies, device=0):
+        import torch
+
+        self.torch = torch
+        self.ctx = list(contexts)
+        self.device = device
+        for k, c in enumerate(self.ctx):
+            c.upload_bodies(bodies)
+            c.island_partition(k, len(self.ctx))
+        self.buf = None
+
+    def step(self, iters=(20, 20), schedule=0):
+        from . import scenes
+
+        torch = self.torch
+        stats = []
+        for c in self.ctx:
+            stages_before_solve(c)
+            stats.append(c.solve_resident(iters=iters, schedule=schedule))
+        words = self.ctx[0].island_exchange_words()
+        if self.buf is None or self.buf.shape[1] < words:
+            self.buf = torch.zeros((len(self.ctx), max(words, 1)), dtype=torch.int32, device=f"cuda:{self.device}")
+        for k, c in enumerate(self.ctx):
+            c.island_pack(self.buf[k].data_ptr())
+            c.synchronize()
+        total = self.buf[:, :words].sum(dim=0, dtype=torch.int32).contiguous()
+        torch.cuda.synchronize(self.device)
+        for c in self.ctx:
+            c.island_unpack(total.data_ptr())
+            c.integrate_position(scenes.DT)
+            c.synchronize()
+        return stats
+
+
+class IslandParallelWorld:
+    """One process per GPU (torch.distributed, NCCL): this rank's replica of the world.  step() = World::Update with the
+    solve split by island and one all-reduce of the results."""
+
+    def __init__(self, ctx, bodies, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.ctx, self.device = ctx, device
+        self.rank, self.ranks = dist.get_rank(group), dist.get_world_size(group)
+        ctx.upload_bodies(bodies)
+        ctx.island_partition(self.rank, self.ranks)
+        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+        self.buf = None
+
+    def step(self, iters=(20, 20)):
+        from . import capi, scenes
+
+        torch, dist = self.torch, self.dist
+        bp = stages_before_solve(self.ctx)
+        st = self.ctx.solve_resident(iters=iters, schedule=capi.SCHEDULE_COLOUR)
+        words = self.ctx.island_exchange_words()
+        with torch.cuda.stream(self.stream):   # everything stays ordered on the context's own stream
+            if self.buf is None or self.buf.shape[0] < words:
+                self.buf = torch.zeros(max(words + words // 8, 1), dtype=torch.int32, device=f"cuda:{self.device}")
+            self.ctx.island_pack(self.buf.data_ptr())
+            dist.all_reduce(self.buf[:words], op=dist.ReduceOp.SUM, group=self.group)
+            self.ctx.island_unpack(self.buf.data_ptr())
+        self.ctx.integrate_position(scenes.DT)
+        return bp, st

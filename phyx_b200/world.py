@@ -54,6 +54,7 @@ def load():
     l.phyxw_get_sync_ms.restype = C.c_double
     l.phyxw_reset_world.argtypes = [vp]
     l.phyxw_context.argtypes = [vp]
+    l.phyxw_get_island_counts.argtypes = [vp, vp]
     l.phyxw_context.restype = vp
     _LIB = l
     return l
@@ -143,6 +144,12 @@ class World:
 
     def reset_stage_ms(self):
         self.l.phyxw_reset_stage_ms(self.h)
+
+    def island_counts(self):
+        """(Solver::islandCount, Solver::islandMaxSize) as left by the last SolveJoints"""
+        out = (C.c_int * 2)()
+        self.l.phyxw_get_island_counts(self.h, out)
+        return int(out[0]), int(out[1])
 
     def solve_stats(self):
         s = capi.SolveStats()

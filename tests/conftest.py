@@ -53,18 +53,38 @@ def ref():
     return refpy
 
 
-def oracle_on_device_schedule(ctx, oracle, bodies, joints, contact_points, iters=(20, 20)):
-    """The oracle's sequential sweep over the slot order the device used for its last colour-mode solve.  With the
-    strip layout every interior class keeps its own lastIteration word per static body (as the partitioned solve does
-    per rank): the sweep runs on the equivalent problem in which class k > 0 references its own copy of each static
-    body (phyx_b200.partition.sequential_equivalent).  Returns (bodies, joints, iterations run, slots, levels)."""
-    from phyx_b200 import partition
+def private_statics(bodies, joints):
+    """The equivalent problem the strip-local kernel solves: every (dynamic body, static body) pair gets its own copy of the
+    static body, so a static body's lastIteration (reference src/Solver.cpp:790-798, 903-910) no longer couples joints of
+    different dynamic bodies (phyx_b200/csrc/strips.cu, "Static bodies").  Returns (bodies', joints')."""
+    bodies = np.asarray(bodies)
+    joints = np.array(joints, copy=True)
+    static = (bodies["invMass"] == 0) & (bodies["invInertia"] == 0)
+    b1, b2 = joints["body1Index"].astype(np.int64), joints["body2Index"].astype(np.int64)
+    n = bodies.shape[0]
+    clones = []
+    seen = {}
+    for side, other in (("body1Index", b2), ("body2Index", b1)):
+        mine = joints[side].astype(np.int64)
+        for j in np.nonzero(static[mine] & ~static[other])[0]:
+            key = (int(other[j]), int(mine[j]))
+            if key not in seen:
+                seen[key] = n + len(clones)
+                clones.append(int(mine[j]))
+            joints[side][j] = seen[key]
+    out = np.concatenate([bodies, bodies[np.asarray(clones, dtype=np.int64)]]) if clones else bodies.copy()
+    return out, joints
 
+
+def oracle_on_device_schedule(ctx, oracle, bodies, joints, contact_points, iters=(20, 20)):
+    """The oracle's sequential sweep over the slot order the device used for its last colour-mode solve.  The strip-local
+    kernel tracks a static body's lastIteration per dynamic partner: there the sweep runs on the equivalent problem of
+    private_statics().  Returns (bodies, joints, iterations run, slots, levels)."""
     slots, levels = ctx.get_schedule()
     plan = ctx.strip_plan()
     n = bodies.shape[0]
-    if plan["strips"] > 1:
-        b2, j2 = partition.sequential_equivalent(bodies, joints, slots, plan["class_slot_start"], plan["strips"])
+    if plan["strips"] >= 1:
+        b2, j2 = private_statics(bodies, joints)
         ob, oj, ran = oracle.solve_scheduled(b2, j2, contact_points, slots, levels, iters=iters)
         oj = oj.copy()
         oj["body1Index"], oj["body2Index"] = joints["body1Index"], joints["body2Index"]

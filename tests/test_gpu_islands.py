@@ -1,0 +1,87 @@
+"""Islands on the device (phyx_b200/csrc/islands.cu) against the reference's Solver::GatherIslands
+(src/Solver.cpp:285-454), and ONE world's solve split by island over several ranks: the merged state must be
+bit-identical to the one-device run of the same scene."""
+import numpy as np
+import pytest
+
+from conftest import assert_records_equal
+from phyx_b200 import capi, islands, scenes, world
+from phyx_b200 import types as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("scene,steps", [("islands_64x20", (1, 6)), ("islands_8x10", (0, 3)), ("tumble_3k", (2, 25)), ("stack_1k", (1, 30)), ("pyramid_10", (0, 2))])
+def test_islands_equal_gather_islands_of_the_reference(ref, scene, steps):
+    """Same membership, same numbering (order of the first body), same coalesced groups, islandCount and islandMaxSize."""
+    sc = scenes.make(scene)
+    r = ref.RefWorld(sc, "strict")
+    w = world.World(sc)
+    ctx = w.context()
+    ctx.upload_bodies(w.bodies())
+    for step in range(max(steps) + 1):
+        islands.stages_before_solve(ctx)
+        r.step_staged(mask=0x3F | ref.SAFE_PAIRS)
+        if step in steps:
+            assert_records_equal(ctx.download_joints(), r.joints(), what=f"step {step}: joints before the solve")
+            count, largest, before = ctx.build_islands()
+            isl, grp = ctx.download_islands()
+            risl, rgrp, (rbefore, rcount, rlargest) = r.gather_islands(8)
+            assert (before, count, largest) == (rbefore, rcount, rlargest), f"step {step}"
+            assert np.array_equal(isl, risl), f"step {step}: island of every body"
+            assert np.array_equal(grp, rgrp), f"step {step}: coalesced group of every body"
+        ctx.solve_resident(schedule=capi.SCHEDULE_REPLAY_AVX2)
+        ctx.integrate_position(scenes.DT)
+        r.step_staged(mask=0xC0)
+    w.close()
+
+
+def test_host_mirror_reports_island_counts(ref):
+    """Solver::islandCount / islandMaxSize as the demo's HUD reads them (src/main.cpp:358-360) in Island_Multiple mode."""
+    sc = scenes.make("islands_8x10")
+    w, r = world.World(sc), ref.RefWorld(sc, "strict")
+    for _ in range(4):
+        w.step(solve=T.SOLVE_AVX2, island=T.ISLAND_MULTIPLE)
+        r.step_staged(mask=0x3F | ref.SAFE_PAIRS)
+        _, _, (_, rcount, rlargest) = r.gather_islands(8)
+        r.step_staged(mask=0xC0)
+        assert w.island_counts() == (rcount, rlargest)
+    w.step(solve=T.SOLVE_AVX2, island=T.ISLAND_SINGLE)
+    assert w.island_counts() == (1, len(w.joints()))
+    w.close()
+
+
+@pytest.mark.parametrize("scene,ranks,steps,form", [("islands_64x20", 2, 12, 0), ("islands_64x20", 4, 12, 0), ("islands_64x20", 3, 8, 2), ("islands_8x10", 8, 10, 0),
+                                                     ("pyramid_1k", 2, 6, 0)])
+def test_island_parallel_solve_is_bit_identical_to_one_device(scene, ranks, steps, form):
+    """`ranks` replicas (contexts of this device), each relaxing only its own islands, merged by the integer sum; against
+    ONE context stepping the same world.  form 0: the default kernel choice (strip-local; whole islands inside a strip);
+    form 2: the record form on the colour-major layout."""
+    sc = scenes.make(scene)
+    w = world.World(sc)
+    bodies = np.array(w.bodies(), copy=True)
+    one = w.context()
+    one.solve_tuning(kernel_form=form)
+    one.upload_bodies(bodies)
+    ctxs = [capi.Context(0) for _ in range(ranks)]
+    for c in ctxs:
+        c.solve_tuning(kernel_form=form)
+    grp = islands.IslandGroup(ctxs, bodies)
+    owned = np.zeros(ranks, dtype=np.int64)
+    for step in range(steps):
+        islands.stages_before_solve(one)
+        st1 = one.solve_resident(schedule=capi.SCHEDULE_COLOUR)
+        one.integrate_position(scenes.DT)
+        stats = grp.step()
+        if form == 0:
+            assert st1.kernelForm == 3 and all(s.kernelForm in (3, 0) for s in stats)
+            assert one.strip_plan()["cut_manifolds"] == 0, "separate piles: every island lies inside one strip"
+        owned += np.array([s.slots for s in stats])
+        for k, c in enumerate(ctxs):
+            assert_records_equal(c.download_bodies(), one.download_bodies(), ("pos", "xVector", "yVector", "velocity", "angularVelocity"), what=f"step {step} rank {k} bodies")
+            assert_records_equal(c.download_joints(), one.download_joints(), what=f"step {step} rank {k} joints")
+    if scene.startswith("islands") and ranks <= 4:
+        assert np.all(owned > 0), "every rank relaxed some islands"
+    for c in ctxs:
+        c.close()
+    w.close()
