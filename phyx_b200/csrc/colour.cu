@@ -265,7 +265,9 @@ int colour_schedule_build(phyx_b200_ctx* c)
     if (!c->jointUnitsValid || c->manifoldCount == 0) return colour_joints_build(c, &changed);
     bool incremental = c->colourStateValid && c->colourStateBodies == c->bodyCount && c->manColour.ptr && c->bodyUsed.ptr;
     int st = colour_units_build(c, incremental, &changed);
-    const int colours = c->part.ranks > 1 ? c->partColours : c->levelCount;   // partitioned layouts have one level per (class, colour)
+    // colours in use over ALL coloured manifolds (not only the ones this rank lays out: an island partition must take the same
+    // rebuild decisions as the one-device run, or the incremental colourings drift apart)
+    const int colours = c->part.ranks > 1 ? c->partColours : c->coloursInUse;
     // every colour is a level = a grid barrier and a latency chain per pass (~8-10 us x 22 passes on the bench scene),
     // a full rebuild costs about a millisecond once: rebuild as soon as the incremental colouring has drifted two
     // colours above the last full build (PHYX_COLOUR_DRIFT overrides the slack)
@@ -447,6 +449,7 @@ __global__ void __launch_bounds__(kBlock) k_unit_keys(int M, const int* __restri
     {
         int c = work[m];
         manColour[m] = (c == kSkipUnit) ? -1 : c;
+        if (c < kMaxColours) atomicMax(&counts[kMaxColours + 1], c + 1);   // colours in use, whoever owns the manifold
         // island partition (islands.cu): manifolds of another rank's islands keep their colour but are not laid out
         if (bodyOwner && max(bodyOwner[manBody[m].x], bodyOwner[manBody[m].y]) != rank) c = kSkipUnit;
         keys[m] = make_uint2(unsigned(c), unsigned(m));
@@ -760,7 +763,7 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
     const size_t oJb = take(size_t(M) * sizeof(int2)), oWork = take(size_t(M) * sizeof(int)), oHint = take(size_t(M) * sizeof(int)), oClaim = take(nb1 * 8),
                  oList0 = take(size_t(M) * sizeof(int)), oList1 = take(size_t(M) * sizeof(int)),
-                 oCounts = take((kMaxColours + 1) * sizeof(int)), oFirst = take(kMaxColours * sizeof(int)), oHeader = take(16), oResult = take(16),
+                 oCounts = take((kMaxColours + 2) * sizeof(int)), oFirst = take(kMaxColours * sizeof(int)), oHeader = take(16), oResult = take(16),
                  oBarrier = take(32), oListCount = take(16);
     PHYX_TRY(c->colourTmp.reserve(off));
     char* base = c->colourTmp.as<char>();
@@ -842,11 +845,12 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
         {
             c->slotCount = 2 * c->strip.manifolds;
             c->levelCount = c->strip.colours;
+            c->coloursInUse = c->strip.colours;
             c->colourRounds = res[0];
             *staticsChanged = res[3] != 0;
             c->colourStateValid = true;
             c->colourStateBodies = nb;
-            if (!incremental) c->coloursAtFullBuild = c->levelCount;
+            if (!incremental) c->coloursAtFullBuild = c->coloursInUse;
             c->hostSlotsStale = true;
             c->hostLevelsStale = true;
             return PHYX_B200_OK;
@@ -882,7 +886,7 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
     c->launches++;
     PHYX_CUDA(cudaGetLastError());
 
-    struct { int header[4]; int result[4]; int counts[kMaxColours + 1]; } host;
+    struct { int header[4]; int result[4]; int counts[kMaxColours + 2]; } host;
     PHYX_CUDA(cudaMemcpyAsync(host.header, header, 16, cudaMemcpyDeviceToHost, c->stream));
     PHYX_CUDA(cudaMemcpyAsync(host.result, result, 16, cudaMemcpyDeviceToHost, c->stream));
     PHYX_CUDA(cudaMemcpyAsync(host.counts, counts, sizeof(host.counts), cudaMemcpyDeviceToHost, c->stream));
@@ -904,7 +908,8 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
         cursor = (cursor + 2 * host.counts[k] + 63) & ~63;   // as k_unit_levels: an empty colour takes no slots
     }
     c->levelCount = int(c->hostLevels.size());
-    if (!incremental) c->coloursAtFullBuild = c->levelCount;
+    c->coloursInUse = host.counts[kMaxColours + 1];
+    if (!incremental) c->coloursAtFullBuild = c->coloursInUse;
     if (c->levelCount > 0)
         PHYX_CUDA(cudaMemcpyAsync(c->levels.ptr, c->hostLevels.data(), size_t(c->levelCount) * sizeof(Level), cudaMemcpyHostToDevice, c->stream));
     c->hostSlotsStale = true;

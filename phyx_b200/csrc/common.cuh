@@ -101,7 +101,8 @@ struct StripPlan
     int maxStripRows = 0, maxCutRows = 0, maxBin = 0, colours = 0, cutManifolds = 0, manifolds = 0;
     bool attributeSet = false;
     int rejected = 0;          // why the last layout attempt was not usable (bit mask, see strips.cu), 0 = usable
-    DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, header, sync, hist, trace, pairTest;
+    DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, header, sync, hist, trace, pairTest, cost, factor, prevCuts;
+    int feedbackStrips = 0, feedbackBodies = 0;   // the balance feedback (measured cost per strip) belongs to this layout shape
     int tracePasses = 0;       // developer aid (phyx_b200_strip_trace): passes of the next solves to time-stamp per CTA
 };
 
@@ -188,7 +189,7 @@ struct phyx_b200_ctx
     phyx::DevBuf bodyStatic;     // u8 per body: static flag the colouring was built with
     bool colourStateValid = false;
     bool jointUnitsValid = false;   // joints are exactly the contact points of the resident manifolds (set by RefreshContactJoints)
-    int colourStateBodies = 0, coloursAtFullBuild = 0, partColours = 0;
+    int colourStateBodies = 0, coloursAtFullBuild = 0, partColours = 0, coloursInUse = 0;
     std::vector<int> hostSlotPos;
     std::vector<int> hostSlots;  // last schedule (host copy, for get_schedule / KEEP_SCHEDULE)
     std::vector<phyx::Level> hostLevels;

@@ -94,7 +94,7 @@ __device__ __forceinline__ bool manifold_is_mine(const unsigned char* __restrict
 
 __global__ void __launch_bounds__(kBlock) k_strip_hist(int M, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
     const int* __restrict__ activity, const int2* __restrict__ manBody, const unsigned char* __restrict__ bodyOwner, int rank, int* __restrict__ hist,
-    int* __restrict__ cover)
+    int* __restrict__ cover, int prevS, const int* __restrict__ prevCuts, const float* __restrict__ factor)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
@@ -115,7 +115,55 @@ __global__ void __launch_bounds__(kBlock) k_strip_hist(int M, const int2* __rest
         const int last = max(b.x >= 0 ? activity[b.x] : -1, b.y >= 0 ? activity[b.y] : -1);
         weight = 5 + min(max(last + 2, 1), 24);
     }
+    weight *= 8;   // fixed point for the feedback factor
+    if (factor)
+    {
+        int lo = 0, hi = prevS - 1;   // the strip this row lived in last step
+        while (lo < hi)
+        {
+            const int mid = (lo + hi + 1) >> 1;
+            if (prevCuts[mid] <= home) lo = mid; else hi = mid - 1;
+        }
+        weight = max(1, int(float(weight) * factor[lo]));
+    }
     atomicAdd(&hist[home], weight);
+}
+
+// Balance feedback.  The predicted weights are only a model; the kernel measures what each strip really cost (SM clocks
+// its CTA spent working) and the next layout scales the weights of the manifolds that lived in strip k by factor[k], a
+// damped running product of (cost of strip k / mean cost).  Strips move from step to step, so factors are looked up by
+// row through the previous cuts and re-sampled onto the new cuts afterwards.
+__global__ void k_strip_feedback(int S, const long long* __restrict__ cost, float* __restrict__ factor)
+{
+    __shared__ float s_sum;
+    if (threadIdx.x == 0) s_sum = 0.f;
+    __syncthreads();
+    for (int k = threadIdx.x; k < S; k += blockDim.x) atomicAdd(&s_sum, float(cost[k]));
+    __syncthreads();
+    const float mean = s_sum / float(S);
+    if (mean <= 0.f) return;
+    for (int k = threadIdx.x; k < S; k += blockDim.x)
+    {
+        const float ratio = fminf(fmaxf(float(cost[k]) / mean, 0.5f), 2.0f);
+        factor[k] = fminf(fmaxf(factor[k] * sqrtf(ratio), 0.25f), 4.0f);
+    }
+}
+
+__global__ void k_strip_resample(int S, const int* __restrict__ cuts, const int* __restrict__ prevCuts, const float* __restrict__ factor, float* __restrict__ factorOut,
+    int* __restrict__ prevCutsOut)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > S) return;
+    prevCutsOut[k] = cuts[k];
+    if (k == S) return;
+    const int mid = (cuts[k] + cuts[k + 1]) >> 1;
+    int lo = 0, hi = S - 1;   // strip of `mid` under the previous cuts
+    while (lo < hi)
+    {
+        const int m = (lo + hi + 1) >> 1;
+        if (prevCuts[m] <= mid) lo = m; else hi = m - 1;
+    }
+    factorOut[k] = factor[lo];
 }
 
 // every dynamic row also counts (shared memory per strip is what limits its width)
@@ -124,7 +172,7 @@ __global__ void __launch_bounds__(kBlock) k_strip_hist_rows(int nb, const unsign
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
     const unsigned body = order ? order[r] : unsigned(r);
-    if (!bodyStatic[body]) hist[r] += 3;
+    if (!bodyStatic[body]) hist[r] += 24;
 }
 
 // cuts[q] = first row with at least q/S of the manifolds before it
@@ -196,10 +244,10 @@ __global__ void __launch_bounds__(kBlock) k_strip_keys(int M, int S, const int2*
         const int c = work[m];
         manColour[m] = (c >= kMaxColours) ? -1 : c;
         unsigned key = unsigned(2 * S) << 7;   // skipped (no contact points, or another rank's island): behind every class
+        if (c < kMaxColours) colour = c + 1;   // colours in use: counted whoever owns the manifold
         if (c < kMaxColours && manifold_is_mine(bodyOwner, rank, manBody[m]))
         {
             coloured = true;
-            colour = c;
             const int2 b = jb[m];
             const int r1 = b.x < 0 ? -1 : (rowOf ? rowOf[b.x] : b.x), r2 = b.y < 0 ? -1 : (rowOf ? rowOf[b.y] : b.y);
             int cls = 0;
@@ -229,7 +277,7 @@ __global__ void __launch_bounds__(kBlock) k_strip_keys(int M, int S, const int2*
     __shared__ int s_max;
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
-    if (coloured) atomicMax(&s_max, colour + 1);
+    if (colour) atomicMax(&s_max, colour);
     __syncthreads();
     if (threadIdx.x == 0)
     {
@@ -518,7 +566,7 @@ int strip_choose(const phyx_b200_ctx* c, int manifolds, int bodies)
     if (c->strip.want < 0) return 0;
     if (c->strip.want > 0) return std::min(c->strip.want, 2 * c->numSMs);   // more than one strip per SM: 256-thread CTAs, two per SM
     (void)bodies;
-    int S = std::max(1, std::min(c->numSMs, manifolds / 256));
+    int S = std::max(1, std::min(c->numSMs, manifolds / 1024));
     if (c->strip.autoLimit > 0) S = std::min(S, c->strip.autoLimit);   // what the last rejected layouts of this world allowed
     return S;
 }
@@ -570,7 +618,22 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
     const bool split = c->islandRanks > 1 && c->islandsValid && c->islandBodies == nb;
     const unsigned char* bodyOwner = split ? c->bodyOwner.as<unsigned char>() : nullptr;
     int* cover = sp.prefixL.as<int>();
-    k_strip_hist<<<grid, kBlock, 0, c->stream>>>(M, jb, work, rowOf, activity, c->manBody.as<int2>(), bodyOwner, c->islandRank, sp.hist.as<int>(), cover);
+    // balance feedback from the previous solve of this world (same strip count, same bodies)
+    PHYX_TRY(sp.cost.reserve(size_t(2 * S + 2) * sizeof(long long)));
+    PHYX_TRY(sp.factor.reserve(size_t(2 * S + 2) * sizeof(float)));
+    PHYX_TRY(sp.prevCuts.reserve(size_t(2 * S + 4) * sizeof(int)));
+    const bool feedback = sp.feedbackStrips == S && sp.feedbackBodies == nb && activity != nullptr;
+    float* factor = sp.factor.as<float>();
+    float* factorNext = factor + S + 1;
+    int* prevCuts = sp.prevCuts.as<int>();
+    int* prevCutsNext = prevCuts + S + 2;
+    if (feedback)
+    {
+        k_strip_feedback<<<1, 256, 0, c->stream>>>(S, sp.cost.as<long long>(), factor);
+        c->launches++;
+    }
+    k_strip_hist<<<grid, kBlock, 0, c->stream>>>(M, jb, work, rowOf, activity, c->manBody.as<int2>(), bodyOwner, c->islandRank, sp.hist.as<int>(), cover, S,
+        feedback ? prevCuts : nullptr, feedback ? factor : nullptr);
     k_strip_hist_rows<<<gridB, kBlock, 0, c->stream>>>(nb, order, c->bodyStatic.as<unsigned char>(), sp.hist.as<int>());
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, sp.hist.as<int>(), sp.prefixR.as<int>(), nb, header + H_SCAN_TOTAL));
@@ -583,6 +646,25 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
         k_strip_monotonic<<<1, 32, 0, c->stream>>>(S, sp.cuts.as<int>());
         c->launches += 2;
     }
+
+    // carry the balance factors over to the new cuts
+    if (feedback)
+    {
+        k_strip_resample<<<gridS, kBlock, 0, c->stream>>>(S, sp.cuts.as<int>(), prevCuts, factor, factorNext, prevCutsNext);
+        PHYX_CUDA(cudaMemcpyAsync(factor, factorNext, size_t(S) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        PHYX_CUDA(cudaMemcpyAsync(prevCuts, prevCutsNext, size_t(S + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+        c->launches++;
+    }
+    else
+    {
+        std::vector<float> ones(size_t(S), 1.0f);
+        PHYX_CUDA(cudaMemcpyAsync(factor, ones.data(), size_t(S) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        PHYX_CUDA(cudaMemcpyAsync(prevCuts, sp.cuts.ptr, size_t(S + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+        PHYX_CUDA(cudaMemsetAsync(sp.cost.ptr, 0, size_t(S) * sizeof(long long), c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));   // `ones` is pageable
+    }
+    sp.feedbackStrips = S;
+    sp.feedbackBodies = nb;
 
     // classes, sort keys, boundary flags; two stable passes: colour (7 bits), then class
     PHYX_TRY(c->colourKeys.reserve(size_t(M) * sizeof(uint2)));
@@ -676,7 +758,7 @@ int strip_host_levels(phyx_b200_ctx* c, std::vector<int>* classStart)
 void strip_release(phyx_b200_ctx* c)
 {
     StripPlan& sp = c->strip;
-    DevBuf* bufs[] = { &sp.cuts, &sp.binRange, &sp.flags, &sp.prefixR, &sp.prefixL, &sp.bR, &sp.bL, &sp.bStart, &sp.header, &sp.sync, &sp.hist, &sp.trace, &sp.pairTest };
+    DevBuf* bufs[] = { &sp.cuts, &sp.binRange, &sp.flags, &sp.prefixR, &sp.prefixL, &sp.bR, &sp.bL, &sp.bStart, &sp.header, &sp.sync, &sp.hist, &sp.trace, &sp.pairTest, &sp.cost, &sp.factor, &sp.prevCuts };
     for (DevBuf* b : bufs) b->release();
     sp.valid = false;
 }
@@ -704,6 +786,7 @@ struct StripParams
     int rowCap, cutCap, workCap;
     int* result;                     // [0] impulse iterations run, [1] displacement iterations run, [2] wake passes
     unsigned long long* activeTotal; // [2]
+    long long* cost;                 // [S] SM clocks this strip's CTA spent working (not waiting for neighbours) in this solve: next step's balance
     unsigned long long* trace;       // developer aid (phyx_b200_strip_trace): [S][tracePasses][8] globaltimer stamps, or null
     int tracePasses;
 };
@@ -762,49 +845,87 @@ struct StripCta
     int parity;         // which worklist counter the next bin pass uses
     unsigned active[2];
     long long clk[3];   // developer aid: SM clocks spent in step 1 / step 2 / (spare) of the bins of the current pass (thread 0)
+    long long busy;     // SM clocks spent working, all passes (thread 0)
 };
 
-// warm start (PreStepJoints, Solver.cpp:736-750) of one bin: every manifold, no test
+// warm start (PreStepJoints, Solver.cpp:736-750) of one bin: every manifold, no test; two manifolds per thread in flight
+// (the manifolds of a bin touch disjoint rows)
 template <int T>
 __device__ __forceinline__ void prestep_bin(const StripParams& P, float4* rowsS, const float4* __restrict__ rowsG, int2 bin)
 {
+    constexpr int K = 2;
     const int n = bin.y - bin.x;
-    for (int i = threadIdx.x; i < n; i += T)
+    for (int i0 = threadIdx.x; i0 < n; i0 += K * T)
     {
-        const int p = bin.x + i;
-        const int2 idx = __ldg(&P.pairIdx[p]);
-        const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
-        const float4 a0 = __ldcs(rec), b0 = __ldcs(rec + 1), c2 = __ldcs(rec + 2), a1 = __ldcs(rec + 4), b1 = __ldcs(rec + 5);
-        const float4 accs = __ldcs(reinterpret_cast<const float4*>(&P.accNF[2 * p]));
-        const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit, haveB = idx.y < 0;
-        const int r1 = idx.x & kBodyMask, r2 = idx.y & kBodyMask;
-        float4 v1 = st1 ? __ldcg(&rowsG[r1]) : rowsS[r1];
-        float4 v2 = st2 ? __ldcg(&rowsG[r2]) : rowsS[r2];
+        int2 idx[K];
+        float4 a0[K], b0[K], c2[K], a1[K], b1[K], accs[K];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int u = 0; u < K; ++u)
         {
-            if (h == 1 && !haveB) break;
-            const float4 c0 = h ? b0 : a0, c1 = h ? b1 : a1;
-            const float nx = c0.x, ny = c0.y;
-            const float accN = h ? accs.z : accs.x, accF = h ? accs.w : accs.y;
-            v1.x += (nx * c2.x) * accN;
-            v1.y += (ny * c2.x) * accN;
-            v1.z += (c0.z * c2.y) * accN;
-            v2.x += ((-nx) * c2.z) * accN;
-            v2.y += ((-ny) * c2.z) * accN;
-            v2.z += (c0.w * c2.w) * accN;
-            const float tx = -ny, ty = nx;
-            v1.x += (tx * c2.x) * accF;
-            v1.y += (ty * c2.x) * accF;
-            v1.z += (c1.x * c2.y) * accF;
-            v2.x += ((-tx) * c2.z) * accF;
-            v2.y += ((-ty) * c2.z) * accF;
-            v2.z += (c1.y * c2.w) * accF;
+            const int i = i0 + u * T;
+            idx[u] = make_int2(-1, -1);
+            if (i < n)
+            {
+                const int p = bin.x + i;
+                idx[u] = __ldg(&P.pairIdx[p]);
+                const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
+                a0[u] = __ldcs(rec);
+                b0[u] = __ldcs(rec + 1);
+                c2[u] = __ldcs(rec + 2);
+                a1[u] = __ldcs(rec + 4);
+                b1[u] = __ldcs(rec + 5);
+                accs[u] = __ldcs(reinterpret_cast<const float4*>(&P.accNF[2 * p]));
+            }
         }
-        if (!st1) rowsS[r1] = v1;
-        if (!st2) rowsS[r2] = v2;
+#pragma unroll
+        for (int u = 0; u < K; ++u)
+        {
+            if (i0 + u * T >= n) continue;
+            const bool st1 = idx[u].x & kStaticBit, st2 = idx[u].y & kStaticBit, haveB = idx[u].y < 0;
+            const int r1 = idx[u].x & kBodyMask, r2 = idx[u].y & kBodyMask;
+            float4 v1 = st1 ? __ldcg(&rowsG[r1]) : rowsS[r1];
+            float4 v2 = st2 ? __ldcg(&rowsG[r2]) : rowsS[r2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+            {
+                if (h == 1 && !haveB) break;
+                const float4 c0 = h ? b0[u] : a0[u], c1 = h ? b1[u] : a1[u];
+                const float nx = c0.x, ny = c0.y;
+                const float accN = h ? accs[u].z : accs[u].x, accF = h ? accs[u].w : accs[u].y;
+                v1.x += (nx * c2[u].x) * accN;
+                v1.y += (ny * c2[u].x) * accN;
+                v1.z += (c0.z * c2[u].y) * accN;
+                v2.x += ((-nx) * c2[u].z) * accN;
+                v2.y += ((-ny) * c2[u].z) * accN;
+                v2.z += (c0.w * c2[u].w) * accN;
+                const float tx = -ny, ty = nx;
+                v1.x += (tx * c2[u].x) * accF;
+                v1.y += (ty * c2[u].x) * accF;
+                v1.z += (c1.x * c2[u].y) * accF;
+                v2.x += ((-tx) * c2[u].z) * accF;
+                v2.y += ((-ty) * c2[u].z) * accF;
+                v2.z += (c1.y * c2[u].w) * accF;
+            }
+            if (!st1) rowsS[r1] = v1;
+            if (!st2) rowsS[r2] = v2;
+        }
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// the record and accumulators of manifold slot p are about to be read: start them towards L2
+template <int PHASE>
+__device__ __forceinline__ void prefetch_manifold(const StripParams& P, int p)
+{
+    const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
+    prefetch_l2(rec);
+    prefetch_l2(rec + (PHASE == 0 ? 5 : 3));   // a 96-byte record may straddle two 128-byte lines
+    if (PHASE == 0)
+        prefetch_l2(&P.accNF[2 * p]);
+    else
+        prefetch_l2(&P.accD[2 * p]);
 }
 
 template <int T>
@@ -859,6 +980,8 @@ __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, flo
                 const int ra = min(int(t & 0xffffu), dummyRow), rb = min(int(t >> 16), dummyRow);
                 const int la = __float_as_int(rowsS[ra].w), lb = __float_as_int(rowsS[rb].w);
                 active[u] = (la > it - 2) || (lb > it - 2);
+                // whoever relaxes it after the barrier finds its record on the way to L2 already
+                if (active[u] && it > 0) prefetch_manifold<PHASE>(P, bin.x + int(threadIdx.x) + u * T);   // (iteration 0 relaxes everything: nothing to get ahead of)
                 m[u] = __ballot_sync(0xffffffffu, active[u]);
                 warpTotal += __popc(m[u]);
             }
@@ -984,6 +1107,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
     bool any = false;
     trace_mark(P, k, passIndex, 0);
     s.clk[0] = s.clk[1] = s.clk[2] = 0;
+    const long long w0 = clock64();
     // interior
     for (int b = 0; b < s.nInt; ++b)
     {
@@ -993,6 +1117,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
             any |= solve_bin<PHASE, T>(P, s, s.s_rows, P.rowCap - 1, rowsG, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, pre);
     }
     trace_mark(P, k, passIndex, 1);
+    s.busy += clock64() - w0;
     if (P.trace && threadIdx.x == 0 && passIndex < P.tracePasses)
     {
         P.trace[(size_t(k) * P.tracePasses + passIndex) * 8 + 5] = (unsigned long long)s.clk[0];
@@ -1012,6 +1137,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
         {
             cta_wait_flag(&P.flagA[k + 1], seq);
             trace_mark(P, k, passIndex, 2);
+            const long long w1 = clock64();
             for (int i = threadIdx.x; i < s.nR; i += T) s.s_cut[i] = s.s_rows[s.s_listR[i]];
             for (int i = threadIdx.x; i < s.nLn; i += T) s.s_cut[s.nR + i] = __ldcg(&rowsG[s.s_listN[i]]);
             __syncthreads();
@@ -1024,6 +1150,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
             }
             for (int i = threadIdx.x; i < s.nR; i += T) s.s_rows[s.s_listR[i]] = s.s_cut[i];
             for (int i = threadIdx.x; i < s.nLn; i += T) __stcg(&rowsG[s.s_listN[i]], s.s_cut[s.nR + i]);
+            s.busy += clock64() - w1;
         }
         __syncthreads();
         if (threadIdx.x == 0) flag_release(&P.flagB[k], seq);
@@ -1106,6 +1233,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
         s.s_cut[P.cutCap - 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-(1 << 30)));
     }
     s.active[0] = s.active[1] = 0u;
+    s.busy = 0;
 
     // the strip's rows: one bulk copy
     if (threadIdx.x == 0)
@@ -1196,6 +1324,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.activeTotal[phase], static_cast<unsigned long long>(v));
     }
+    if (threadIdx.x == 0) P.cost[k] = s.busy;
     // iteration counts as the reference loop reports them: up to and including the first non-productive iteration
     if (k == 0 && threadIdx.x == 0)
     {
@@ -1256,6 +1385,7 @@ int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, floa
     P.workCap = (sp.maxBin + 8) & ~7;
     P.result = reinterpret_cast<int*>(c->solveFlags.as<char>() + 32);
     P.activeTotal = reinterpret_cast<unsigned long long*>(c->solveFlags.as<char>() + 48);
+    P.cost = sp.cost.as<long long>();
     P.trace = nullptr;
     if (sp.tracePasses > 0)
     {

@@ -78,6 +78,18 @@ def stages_before_solve(ctx):
     return bp
 
 
+def merge_model(words_per_rank, owner_of_word):
+    """numpy model of the merge the ranks do on the device (k_island_pack / all-reduce / k_island_unpack): every rank
+    contributes the 32-bit words it owns and zero elsewhere; the integer sum over the ranks is then the owned value of every
+    word, exactly, for any bit pattern (-0.0, NaN payloads, denormals included), because each sum has one non-zero term."""
+    words_per_rank = [np.asarray(w).view(np.int32) for w in words_per_rank]
+    owner_of_word = np.asarray(owner_of_word)
+    packed = [np.where(owner_of_word == r, w, 0).astype(np.int32) for r, w in enumerate(words_per_rank)]
+    with np.errstate(over="ignore"):
+        total = np.sum(np.stack(packed).astype(np.int64), axis=0).astype(np.int32)
+    return packed, total
+
+
 class IslandGroup:
     """`ranks` replicas of one world in ONE process (contexts may share a device): what the single-GPU tests drive.  The
     merge is the same integer sum the multi-process path does with NCCL, here with torch on the device."""
@@ -103,7 +115,8 @@ class IslandGroup:
             stats.append(c.solve_resident(iters=iters, schedule=schedule))
         words = self.ctx[0].island_exchange_words()
         if self.buf is None or self.buf.shape[1] < words:
-            self.buf = torch.zeros((len(self.ctx), max(words, 1)), dtype=torch.int32, device=f"cuda:{self.device}")
+            width = (max(words, 1) + 63) // 64 * 64   # every rank's row starts 16-byte aligned (the pack kernel writes int4)
+            self.buf = torch.zeros((len(self.ctx), width), dtype=torch.int32, device=f"cuda:{self.device}")
         for k, c in enumerate(self.ctx):
             c.island_pack(self.buf[k].data_ptr())
             c.synchronize()

@@ -51,12 +51,15 @@ def test_host_mirror_reports_island_counts(ref):
     w.close()
 
 
-@pytest.mark.parametrize("scene,ranks,steps,form", [("islands_64x20", 2, 12, 0), ("islands_64x20", 4, 12, 0), ("islands_64x20", 3, 8, 2), ("islands_8x10", 8, 10, 0),
+@pytest.mark.parametrize("scene,ranks,steps,form", [("islands_64x20", 2, 12, 0), ("islands_64x20", 4, 12, 0), ("islands_64x20", 3, 8, 0), ("islands_8x10", 8, 10, 0),
                                                      ("pyramid_1k", 2, 6, 0)])
 def test_island_parallel_solve_is_bit_identical_to_one_device(scene, ranks, steps, form):
     """`ranks` replicas (contexts of this device), each relaxing only its own islands, merged by the integer sum; against
-    ONE context stepping the same world.  form 0: the default kernel choice (strip-local; whole islands inside a strip);
-    form 2: the record form on the colour-major layout."""
+    ONE context stepping the same world, with the default kernel choice (strip-local; whole islands lie inside a strip, so
+    the order in which an island's manifolds are relaxed does not depend on the partition, and a static body's
+    lastIteration is private to each dynamic partner).  The grid-barrier forms keep the reference's shared lastIteration
+    record on static bodies, which couples the ground contacts of all islands: under them the split is still a valid
+    Gauss-Seidel sweep but not bit-identical to the one-device run."""
     sc = scenes.make(scene)
     w = world.World(sc)
     bodies = np.array(w.bodies(), copy=True)

@@ -73,3 +73,50 @@ def test_partition_agrees_across_ranks_gloo(tmp_path):
     dyn = np.nonzero(sc[:, 5] == 0)[0]
     assert total[0] == dyn.size and total[1] == int(dyn.sum())   # disjoint cover, agreed by both ranks
     assert total[2] == 2                                          # max-over-ranks reduction
+
+
+def _merge_worker(rank, world_size, port, out):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    rng = np.random.default_rng(7)                     # the same "replicated" state on every rank ...
+    n = 4096
+    truth = rng.integers(-2**31, 2**31 - 1, size=n, dtype=np.int64).astype(np.int32)
+    truth[:8] = np.array([-0.0, 0.0, np.nan, np.inf, -np.inf, 1e-45, -1e-45, 1.0], dtype=np.float32).view(np.int32)
+    owner = rng.integers(0, world_size, size=n)
+    mine = truth.copy()
+    mine[owner != rank] = rng.integers(-5, 5, size=int((owner != rank).sum()))   # ... except where another rank owns the result
+    packed = np.where(owner == rank, mine, 0).astype(np.int32)                   # k_island_pack
+    t = torch.from_numpy(packed.copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)                                     # the exchange
+    ok = np.array_equal(t.numpy(), truth)                                        # k_island_unpack would now write the full state
+    flags = [None] * world_size
+    dist.all_gather_object(flags, bool(ok))
+    dist.barrier()
+    if rank == 0:
+        np.save(out, np.array(flags))
+    dist.destroy_process_group()
+
+
+def test_integer_sum_merge_reassembles_the_state_on_every_rank_gloo(tmp_path):
+    """The island-parallel exchange (phyx_b200/islands.py IslandParallelWorld.step, csrc/islands.cu): each rank contributes
+    the words it owns, zero elsewhere; an int32 SUM all-reduce gives every rank the full state bit for bit."""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_merge_worker, args=(2, port, out), nprocs=2, join=True)
+    assert np.load(out).all()
+    # and the numpy model of the same algebra, three ranks
+    rng = np.random.default_rng(3)
+    truth = rng.standard_normal(1000).astype(np.float32)
+    truth[0] = -0.0
+    owner = rng.integers(0, 3, size=1000)
+    per_rank = [np.where(owner == r, truth, rng.standard_normal(1000).astype(np.float32)) for r in range(3)]
+    _, total = islands.merge_model(per_rank, owner)
+    assert np.array_equal(total, truth.view(np.int32))
