@@ -354,6 +354,7 @@ def run_island_parallel(args, rank, world_size, local_rank):
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.launch_count()
+    ipw.timing.update({"stages_before_solve_ms": 0.0, "solve_ms": 0.0, "exchange_ms": 0.0, "steps": 0})
     with clocks:
         e0.record(stream)
         stats = [ipw.step(ITERS) for _ in range(args.steps)]
@@ -382,8 +383,9 @@ def run_island_parallel(args, rank, world_size, local_rank):
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
 
-    mine = {"rank": rank, "manifolds_relaxed": int(np.mean([st.slots for _, st in stats])) // 2, "kernel_ms": float(np.mean([st.ms_iterations for _, st in stats])),
-            "solve_ms": float(np.mean([st.ms_total for _, st in stats])), "kernel_form": int(stats[-1][1].kernelForm), "state": state,
+    plan = ctx.strip_plan()
+    mine = {"rank": rank, "strips": int(plan["strips"]), "cut_manifolds": int(plan["cut_manifolds"]), "manifolds_relaxed": int(np.mean([st.slots for _, st in stats])) // 2, "kernel_ms": float(np.mean([st.ms_iterations for _, st in stats])),
+            "solve_ms": float(np.mean([st.ms_total for _, st in stats])), "phases_ms": ipw.mean_timing(), "schedule_ms": float(np.mean([st.ms_schedule for _, st in stats])), "kernel_form": int(stats[-1][1].kernelForm), "state": state,
             "relaxed": [float(np.mean([st.activeJointIterations[0] for _, st in stats])), float(np.mean([st.activeJointIterations[1] for _, st in stats]))]}
     per_rank = [None] * world_size
     dist.all_gather_object(per_rank, mine)
@@ -433,7 +435,9 @@ def run_island_parallel(args, rank, world_size, local_rank):
                      "formula": "SURVEY 8(d) bytes of the relaxed joint-iterations of all ranks / the slowest rank's kernel time", "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms},
         "cpu_baseline": None,
         "island_parallel": {"per_rank": [{k: v for k, v in r.items() if k != "state"} for r in per_rank], "replicas_identical": len({r["state"] for r in per_rank}) == 1,
-                            "matches_one_device_run_bit_for_bit": matches, "exchange_bytes_per_step_per_rank": words * 4,
+                            "matches_one_device_run_bit_for_bit": matches,
+                            "bit_identity_condition": "holds when every rank ran the strip-local kernel (kernel_form 3) with no manifold across a strip cut (cut_manifolds 0, also on the one-device "
+                                                      "run): then the order in which an island's manifolds are relaxed does not depend on the partition (tests/test_gpu_islands.py)", "exchange_bytes_per_step_per_rank": words * 4,
                             "exchange": "NCCL all-reduce (int32 SUM, one non-zero term per word) of [velocity rows | displacement rows | cached impulses]"},
         "spanning": spanning,
         "executed_constraint_iterations_per_sec": jm * float(np.mean([st.contactIterationsRun + st.penetrationIterationsRun for _, st in stats])) / (ms_step * 1e-3),

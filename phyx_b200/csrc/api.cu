@@ -487,7 +487,7 @@ int phyx_b200_strip_trace(phyx_b200_ctx* c, int passes, uint64_t* out, int64_t c
 int phyx_b200_build_islands(phyx_b200_ctx* c, int32_t* islandCount, int32_t* islandMaxSize, int32_t* islandsBeforeCoalescing)
 {
     PHYX_TRY(check(c));
-    return islands_build(c, c->islandRanks, islandCount, islandMaxSize, islandsBeforeCoalescing);
+    return islands_build(c, c->islandRanks, islandCount, islandMaxSize, islandsBeforeCoalescing, true);
 }
 
 int phyx_b200_download_islands(phyx_b200_ctx* c, int32_t* islandOfBody, int32_t* groupOfBody, int32_t capacity)
@@ -747,7 +747,7 @@ int phyx_b200_solve_resident(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg
             set_error("solve: an island partition needs schedule = PHYX_B200_SCHEDULE_COLOUR");
             return PHYX_B200_ERR_ARGUMENT;
         }
-        PHYX_TRY(islands_build(c, c->islandRanks, nullptr, nullptr, nullptr));
+        PHYX_TRY(islands_build(c, c->islandRanks, nullptr, nullptr, nullptr, false));
         c->scheduleMode = -1;
     }
     return phyx_b200_solve_staged(c, cfg, stats);

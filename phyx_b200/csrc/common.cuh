@@ -211,6 +211,7 @@ struct phyx_b200_ctx
     bool islandsValid = false;
     int islandBodies = 0, islandCount = 0, islandMaxSize = 0;
     int islandRank = 0, islandRanks = 1;
+    int islandForestBodies = -1, islandForestAge = 0;   // union-find forest kept between steps (partition path only)
     phyx::DevBuf bodyActivity;   // int per body: last impulse iteration with a productive joint on it, previous solve (strip balance)
     bool activityValid = false;
     int activityBodies = 0;
@@ -239,7 +240,7 @@ int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift,
 int colour_schedule_build(phyx_b200_ctx* c);
 
 // islands.cu
-int islands_build(phyx_b200_ctx* c, int ranks, int* islandCount, int* islandMaxSize, int* islandsBeforeCoalescing);
+int islands_build(phyx_b200_ctx* c, int ranks, int* islandCount, int* islandMaxSize, int* islandsBeforeCoalescing, bool exact);
 int islands_download(phyx_b200_ctx* c, int* islandOfBody, int* groupOfBody);
 size_t islands_exchange_words(const phyx_b200_ctx* c);
 int islands_pack(phyx_b200_ctx* c, int32_t* deviceBuffer);

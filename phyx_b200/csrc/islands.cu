@@ -39,12 +39,23 @@ __device__ __forceinline__ int island_find(int* parent, int x)
     return x;
 }
 
-__global__ void __launch_bounds__(kBlock) k_island_init(int nb, const float4* __restrict__ params, int* __restrict__ parent, int* __restrict__ counts)
+// keep = true: start from the (compressed) forest of the previous step instead of singletons: unions are only ever added,
+// so islands whose contacts have broken stay merged until the next full build (the island partition of the solve only
+// needs whole islands, not minimal ones; phyx_b200_build_islands always builds exactly).  result[4] = 1 if a body changed
+// between static and dynamic since the forest was built (the caller then rebuilds from singletons).
+__global__ void __launch_bounds__(kBlock) k_island_init(int nb, const float4* __restrict__ params, int* __restrict__ parent, int* __restrict__ counts, bool keep,
+    int* __restrict__ result)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     const float4 p = params[b];
-    parent[b] = (p.x == 0.0f && p.y == 0.0f) ? -1 : b;   // Solver.cpp:304
+    const bool isStatic = p.x == 0.0f && p.y == 0.0f;   // Solver.cpp:304
+    if (keep)
+    {
+        if (isStatic != (parent[b] < 0)) result[4] = 1;
+    }
+    else
+        parent[b] = isStatic ? -1 : b;
     counts[b] = 0;
 }
 
@@ -95,60 +106,105 @@ __global__ void __launch_bounds__(kBlock) k_island_count(int M, const int2* __re
     int* __restrict__ counts)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= M) return;
-    const int n = manCount[m];
-    if (n == 0) return;
-    const int2 b = manBody[m];
-    const int i1 = islandOf[b.x], i2 = islandOf[b.y];
-    if ((i1 & i2) < 0) return;   // both static
-    atomicAdd(&counts[i1 < 0 ? i2 : i1], n);
+    int island = -1, n = 0;
+    if (m < M)
+    {
+        n = manCount[m];
+        if (n > 0)
+        {
+            const int2 b = manBody[m];
+            const int i1 = islandOf[b.x], i2 = islandOf[b.y];
+            island = i1 < 0 ? i2 : i1;   // -1 if both are static
+        }
+    }
+    // neighbouring manifolds mostly belong to one island (a pile is thousands of manifolds): one atomic per island and warp
+    const unsigned peers = __match_any_sync(0xffffffffu, island);
+    int sum = 0;
+    for (unsigned rest = peers; rest; rest &= rest - 1) sum += __shfl_sync(peers, n, __ffs(rest) - 1);
+    if (island >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counts[island], sum);
 }
 
-// Solver.cpp:383-415: consecutive islands are merged until a group holds at least kIslandMinSize joints.  A running sum
-// with a reset is inherently sequential; one thread walks the islands (tens of thousands per millisecond), which is all
-// the bookkeeping needs.  result: [0] islands before coalescing, [1] groups = Solver::islandCount, [2] islandMaxSize,
-// [3] joints in islands
+// Solver.cpp:383-415: consecutive islands are merged until a group holds at least kIslandMinSize joints.  The running sum
+// with a reset is sequential in nature; ONE WARP walks the islands 32 at a time: an inclusive scan of the chunk's counts,
+// then for every group that closes inside the chunk one ballot finds where.  result: [0] islands before coalescing,
+// [1] groups = Solver::islandCount, [2] islandMaxSize, [3] joints in islands
 __global__ void k_island_coalesce(const int* __restrict__ islandsPtr, const int* __restrict__ counts, int* __restrict__ group, int* __restrict__ groupSize,
     int* __restrict__ result)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
     const int islands = *islandsPtr;
-    int runningIndex = 0, runningCount = 0, total = 0, largest = 0;
-    for (int i = 0; i < islands; ++i)
+    int running = 0, groups = 0, largest = 0, total = 0;
+    for (int base = 0; base < islands; base += 32)
     {
-        runningCount += counts[i];
-        group[i] = runningIndex;
-        if (runningCount >= kIslandMinSize || (runningCount > 0 && i == islands - 1))
+        const int i = base + lane;
+        const int cnt = i < islands ? counts[i] : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
         {
-            groupSize[runningIndex] = runningCount;
-            largest = max(largest, runningCount);
-            total += runningCount;
-            runningCount = 0;
-            runningIndex++;
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
+        int offset = 0, start = 0, closesBefore = 0, closed = 0;
+        // fast path: nothing carried in and every island of the chunk is a group of its own (separate piles)
+        if (running == 0 && __all_sync(0xffffffffu, i >= islands || cnt >= kIslandMinSize))
+        {
+            const int valid = min(32, islands - base);
+            if (i < islands)
+            {
+                group[i] = groups + lane;
+                groupSize[groups + lane] = cnt;
+            }
+            int mx = cnt;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            largest = max(largest, mx);
+            total += __shfl_sync(0xffffffffu, incl, 31);
+            groups += valid;
+            continue;
+        }
+        for (;;)
+        {
+            const int val = running + incl - offset;   // the running count including island i, for lanes from `start` on
+            const bool closes = lane >= start && i < islands && (val >= kIslandMinSize || (val > 0 && i == islands - 1));
+            const unsigned m = __ballot_sync(0xffffffffu, closes);
+            if (!m) break;
+            const int j = __ffs(m) - 1;
+            const int size = __shfl_sync(0xffffffffu, val, j);
+            if (lane == 0) groupSize[groups + closed] = size;
+            largest = max(largest, size);
+            total += size;
+            if (lane > j) ++closesBefore;
+            ++closed;
+            running = 0;
+            offset = __shfl_sync(0xffffffffu, incl, j);
+            start = j + 1;
+        }
+        if (i < islands) group[i] = groups + closesBefore;
+        groups += closed;
+        running += __shfl_sync(0xffffffffu, incl, 31) - offset;
     }
-    result[0] = islands;
-    result[1] = runningIndex;
-    result[2] = largest;
-    result[3] = total;
+    if (lane == 0)
+    {
+        result[0] = islands;
+        result[1] = groups;
+        result[2] = largest;
+        result[3] = total;
+    }
 }
 
-// owner rank of every island group: contiguous runs of groups with about equal joint counts, and from it
-// the owner of every body (static bodies and bodies of groups that were never closed: rank 0)
-__global__ void k_island_owner_cuts(int ranks, const int* __restrict__ result, const int* __restrict__ groupSize, int* __restrict__ groupOwner)
+// owner rank of every island group: contiguous runs of groups with about equal joint counts: a group goes to
+// the rank whose share of the joints its midpoint falls into.  before[g] = joints of the groups in front of g.
+__global__ void __launch_bounds__(kBlock) k_island_owner_cuts(int ranks, const int* __restrict__ result, const int* __restrict__ groupSize,
+    const int* __restrict__ before, int* __restrict__ groupOwner)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int groups = result[1];
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= result[1]) return;
     const long long total = result[3];
-    long long run = 0;
-    for (int g = 0; g < groups; ++g)
-    {
-        // the group goes to the rank whose share its midpoint falls into
-        const long long mid = 2 * run + groupSize[g];
-        int owner = total > 0 ? int((mid * ranks) / (2 * total)) : 0;
-        groupOwner[g] = min(max(owner, 0), ranks - 1);
-        run += groupSize[g];
-    }
+    const long long mid = 2ll * before[g] + groupSize[g];
+    const int owner = total > 0 ? int((mid * ranks) / (2 * total)) : 0;
+    groupOwner[g] = min(max(owner, 0), ranks - 1);
 }
 
 __global__ void __launch_bounds__(kBlock) k_island_body_owner(int nb, const int* __restrict__ islandOf, const int* __restrict__ group, const int* __restrict__ groupOwner,
@@ -163,7 +219,7 @@ __global__ void __launch_bounds__(kBlock) k_island_body_owner(int nb, const int*
 }
 
 // Islands of the resident manifolds.  Leaves islandOf / bodyGroup (per body) and, with ranks > 1, bodyOwner on the device.
-int islands_build(phyx_b200_ctx* c, int ranks, int* islandCount, int* islandMaxSize, int* islandsBeforeCoalescing)
+int islands_build(phyx_b200_ctx* c, int ranks, int* islandCount, int* islandMaxSize, int* islandsBeforeCoalescing, bool exact)
 {
     const int nb = c->bodyCount, M = c->manifoldCount;
     const size_t nb1 = size_t(nb > 0 ? nb : 1);
@@ -179,25 +235,38 @@ int islands_build(phyx_b200_ctx* c, int ranks, int* islandCount, int* islandMaxS
     int* groupSize = group + nb1;
     int* groupOwner = groupSize + nb1;
     int* bodyGroup = groupOwner + nb1;
-    int* result = bodyGroup + nb1;
-    int host[4] = { 0, 0, 0, 0 };
-    if (nb > 0)
+    int* result = bodyGroup + nb1;   // [0..3] counts, [4] statics changed, [8] islands before coalescing
+    int host[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    // the forest of the previous step can be reused (unions only added) a few steps in a row
+    bool keep = !exact && c->islandForestBodies == nb && c->islandForestAge < 8;
+    for (int attempt = 0; attempt < 2 && nb > 0; ++attempt)
     {
         const int gridB = (nb + kBlock - 1) / kBlock, gridM = (M + kBlock - 1) / kBlock;
-        k_island_init<<<gridB, kBlock, 0, c->stream>>>(nb, c->params.as<float4>(), parent, counts);
+        PHYX_CUDA(cudaMemsetAsync(result, 0, 8 * sizeof(int), c->stream));
+        k_island_init<<<gridB, kBlock, 0, c->stream>>>(nb, c->params.as<float4>(), parent, counts, keep, result);
         if (M > 0) k_island_hook<<<gridM, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(), parent);
         k_island_compress<<<gridB, kBlock, 0, c->stream>>>(nb, parent, isRoot);
         c->launches += 3;
         PHYX_TRY(exclusive_scan_i32(c, isRoot, rootRank, nb, result + 8));
         k_island_number<<<gridB, kBlock, 0, c->stream>>>(nb, parent, rootRank, islandOf);
         if (M > 0) k_island_count<<<gridM, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(), islandOf, counts);
+        PHYX_CUDA(cudaMemsetAsync(groupSize, 0, size_t(nb) * sizeof(int), c->stream));
         k_island_coalesce<<<1, 32, 0, c->stream>>>(result + 8, counts, group, groupSize, result);
-        if (ranks > 1) k_island_owner_cuts<<<1, 32, 0, c->stream>>>(ranks, result, groupSize, groupOwner);
+        if (ranks > 1)
+        {
+            // (at most one group per island, so nb bounds the grid; entries beyond the group count are never read)
+            PHYX_TRY(exclusive_scan_i32(c, groupSize, counts, nb, nullptr));   // `counts` is dead: reuse it for the prefix
+            k_island_owner_cuts<<<gridB, kBlock, 0, c->stream>>>(ranks, result, groupSize, counts, groupOwner);
+        }
         k_island_body_owner<<<gridB, kBlock, 0, c->stream>>>(nb, islandOf, group, groupOwner, result, bodyGroup, ranks > 1 ? c->bodyOwner.as<unsigned char>() : nullptr);
         c->launches += 5;
         PHYX_CUDA(cudaMemcpyAsync(host, result, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
         PHYX_CUDA(cudaStreamSynchronize(c->stream));
+        if (!(keep && host[4])) break;
+        keep = false;   // a body changed between static and dynamic: the old forest is void
     }
+    c->islandForestBodies = nb;
+    c->islandForestAge = keep ? c->islandForestAge + 1 : 0;
     c->islandsValid = true;
     c->islandBodies = nb;
     c->islandCount = host[1];

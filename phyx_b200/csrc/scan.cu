@@ -1,6 +1,6 @@
-// phyx_b200 — exclusive prefix sum over int32 (reduce / scan-of-partials / downsweep), used by the
-// radix sort offsets, the sweep's load-balanced emission and the colour-major joint layout.
-// Deterministic (no atomics, fixed association order).
+// phyx_b200 — exclusive prefix sum over int32 (single pass, decoupled look-back), used by the radix sort offsets, the
+// sweep's load-balanced emission, the swap-with-last compactions and the schedule layouts.
+// Deterministic: integer sums, so the result does not depend on the order tiles finish in.
 #include "common.cuh"
 
 namespace phyx
@@ -42,23 +42,20 @@ __device__ __forceinline__ int block_exclusive(int v, int* total)
     return res;
 }
 
-__global__ void k_scan_reduce(const int* __restrict__ in, int n, int* __restrict__ partial)
+// Single-pass scan with decoupled look-back: one launch instead of reduce / scan-of-partials / downsweep (a step makes
+// about fourteen scans, which used to be 40 launches).  Tiles are taken in ticket order, so a tile only ever waits for
+// tiles whose CTAs are already running.  status[t] = flag << 32 | value: flag 1 = the tile's own total is there,
+// 2 = the inclusive prefix up to and including the tile is.  Integer sums: the result does not depend on who adds what.
+__global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restrict__ in, int n, int* __restrict__ out, unsigned long long* __restrict__ status,
+    unsigned* __restrict__ ticket, int* __restrict__ totalOut)
 {
     __shared__ int total;
-    int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    int s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k)
-        if (base + k < n) s += in[base + k];
-    block_exclusive(s, &total);
-    if (threadIdx.x == 0) partial[blockIdx.x] = total;
-}
-
-__global__ void k_scan_down(const int* __restrict__ in, int n, const int* __restrict__ partialScanned, int* __restrict__ out,
-    int* __restrict__ totalOut)
-{
-    __shared__ int total;
-    int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    __shared__ unsigned s_tile;
+    __shared__ int s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = int(s_tile);
+    const int base = tile * kScanTile + threadIdx.x * kScanItems;
     int v[kScanItems];
     int s = 0;
 #pragma unroll
@@ -67,40 +64,53 @@ __global__ void k_scan_down(const int* __restrict__ in, int n, const int* __rest
         v[k] = (base + k < n) ? in[base + k] : 0;
         s += v[k];
     }
-    int ex = block_exclusive(s, &total) + (partialScanned ? partialScanned[blockIdx.x] : 0);
+    const int ex = block_exclusive(s, &total);
+    const unsigned mine = unsigned(total);
+    if (threadIdx.x == 0)
+    {
+        volatile unsigned long long* st = status;
+        st[tile] = ((tile == 0 ? 2ull : 1ull) << 32) | mine;
+    }
+    if (threadIdx.x < 32)
+    {
+        // look back, 32 predecessors at a time
+        volatile unsigned long long* st = status;
+        unsigned prefix = 0;
+        int t = tile - 1;
+        while (t >= 0)
+        {
+            const int idx = t - int(threadIdx.x);
+            unsigned long long w = 0;
+            if (idx >= 0)
+            {
+                do { w = st[idx]; } while ((w >> 32) == 0ull);
+            }
+            const unsigned flag = idx >= 0 ? unsigned(w >> 32) : 0u;
+            const unsigned full = __ballot_sync(0xffffffffu, flag == 2u);   // lanes that saw a complete prefix
+            // add everything up to and including the nearest complete prefix
+            const int stop = full ? __ffs(full) - 1 : 31;
+            unsigned part = (idx >= 0 && int(threadIdx.x) <= stop) ? unsigned(w) : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            prefix += part;
+            if (full) break;
+            t -= 32;
+        }
+        if (threadIdx.x == 0)
+        {
+            if (tile > 0) st[tile] = (2ull << 32) | unsigned(prefix + mine);
+            s_prefix = int(prefix);
+        }
+    }
+    __syncthreads();
+    int run = ex + s_prefix;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k)
     {
-        if (base + k < n) out[base + k] = ex;
-        ex += v[k];
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
     }
-    if (totalOut && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *totalOut = ex;
-}
-
-static int scan_rec(phyx_b200_ctx* c, const int* in, int* out, int n, int* totalDevice, int* scratch, size_t scratchInts)
-{
-    int blocks = (n + kScanTile - 1) / kScanTile;
-    if (blocks <= 1)
-    {
-        k_scan_down<<<1, kScanThreads, 0, c->stream>>>(in, n, nullptr, out, totalDevice);
-        c->launches++;
-        PHYX_CUDA(cudaGetLastError());
-        return PHYX_B200_OK;
-    }
-    if (size_t(blocks) * 2 > scratchInts)
-    {
-        set_error("scan scratch too small");
-        return PHYX_B200_ERR_STATE;
-    }
-    int* partial = scratch;
-    int* partialScanned = scratch + blocks;
-    k_scan_reduce<<<blocks, kScanThreads, 0, c->stream>>>(in, n, partial);
-    c->launches++;
-    PHYX_TRY(scan_rec(c, partial, partialScanned, blocks, nullptr, scratch + 2 * blocks, scratchInts - 2 * size_t(blocks)));
-    k_scan_down<<<blocks, kScanThreads, 0, c->stream>>>(in, n, partialScanned, out, totalDevice);
-    c->launches++;
-    PHYX_CUDA(cudaGetLastError());
-    return PHYX_B200_OK;
+    if (totalOut && base <= n - 1 && n - 1 < base + kScanItems) *totalOut = run;   // the thread that holds the last element
 }
 
 // in and out may alias.  If totalDevice is non-null it receives the grand total.
@@ -111,15 +121,16 @@ int exclusive_scan_i32(phyx_b200_ctx* c, const int* in, int* out, int n, int* to
         if (totalDevice) PHYX_CUDA(cudaMemsetAsync(totalDevice, 0, sizeof(int), c->stream));
         return PHYX_B200_OK;
     }
-    size_t need = 0;
-    for (int m = n; m > kScanTile;)
-    {
-        m = (m + kScanTile - 1) / kScanTile;
-        need += 2 * size_t(m);
-    }
-    need += 16;
-    PHYX_TRY(c->scanTmp.reserve(need * sizeof(int)));
-    return scan_rec(c, in, out, n, totalDevice, c->scanTmp.as<int>(), need);
+    const int tiles = (n + kScanTile - 1) / kScanTile;
+    const size_t bytes = (size_t(tiles) + 2) * sizeof(unsigned long long);
+    PHYX_TRY(c->scanTmp.reserve(bytes));
+    PHYX_CUDA(cudaMemsetAsync(c->scanTmp.ptr, 0, bytes, c->stream));
+    unsigned long long* status = c->scanTmp.as<unsigned long long>() + 1;
+    unsigned* ticket = c->scanTmp.as<unsigned>();
+    k_scan_single<<<tiles, kScanThreads, 0, c->stream>>>(in, n, out, status, ticket, totalDevice);
+    c->launches++;
+    PHYX_CUDA(cudaGetLastError());
+    return PHYX_B200_OK;
 }
 
 } // namespace phyx

@@ -58,7 +58,7 @@ enum
     H_REJECT = 0,   // bit 0: a manifold spans non-adjacent strips, bit 1: a row is in two cut sets
     H_MAXROWS,      // rows of the largest strip
     H_MAXCUT,       // rows of the largest cut set (own right-boundary rows + the neighbour's left-boundary rows)
-    H_UNUSED3,
+    H_ROW_LO,       // first / one past the last row the laid-out manifolds touch (an island partition owns a part of the world)
     H_MANIFOLDS,    // manifolds with a colour (slots / 2)
     H_MAXBIN,       // manifolds of the largest (class, colour) bin
     H_COLOURS,      // colours in use
@@ -66,6 +66,7 @@ enum
     H_TOTAL_R,
     H_TOTAL_L,
     H_SCAN_TOTAL,
+    H_ROW_HI,
     H_WORDS = 16
 };
 
@@ -94,15 +95,45 @@ __device__ __forceinline__ bool manifold_is_mine(const unsigned char* __restrict
 
 __global__ void __launch_bounds__(kBlock) k_strip_hist(int M, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
     const int* __restrict__ activity, const int2* __restrict__ manBody, const unsigned char* __restrict__ bodyOwner, int rank, int* __restrict__ hist,
-    int* __restrict__ cover, int prevS, const int* __restrict__ prevCuts, const float* __restrict__ factor)
+    int* __restrict__ cover, int prevS, const int* __restrict__ prevCuts, const float* __restrict__ factor, int* __restrict__ header)
 {
+    __shared__ int s_lo, s_hi;
+    if (threadIdx.x == 0)
+    {
+        s_lo = 0x7fffffff;
+        s_hi = 0;
+    }
+    __syncthreads();
     int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= M) return;
-    if (work[m] >= kMaxColours) return;
-    if (!manifold_is_mine(bodyOwner, rank, manBody[m])) return;
-    const int2 b = jb[m];
-    const int r1 = b.x < 0 ? -1 : (rowOf ? rowOf[b.x] : b.x), r2 = b.y < 0 ? -1 : (rowOf ? rowOf[b.y] : b.y);
-    const int home = r1 < 0 ? r2 : (r2 < 0 ? r1 : min(r1, r2));
+    int r1 = -1, r2 = -1, home = -1;
+    int2 b = make_int2(-1, -1);
+    if (m < M && work[m] < kMaxColours && manifold_is_mine(bodyOwner, rank, manBody[m]))
+    {
+        b = jb[m];
+        r1 = b.x < 0 ? -1 : (rowOf ? rowOf[b.x] : b.x);
+        r2 = b.y < 0 ? -1 : (rowOf ? rowOf[b.y] : b.y);
+        home = r1 < 0 ? r2 : (r2 < 0 ? r1 : min(r1, r2));
+    }
+    // the span of rows the laid-out manifolds touch: one atomic per block
+    {
+        int lo = home >= 0 ? home : 0x7fffffff, hi = home >= 0 ? max(r1, r2) + 1 : 0;
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0)
+        {
+            if (lo != 0x7fffffff) atomicMin(&s_lo, lo);
+            if (hi) atomicMax(&s_hi, hi);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            if (s_lo != 0x7fffffff) atomicMin(&header[H_ROW_LO], s_lo);
+            if (s_hi) atomicMax(&header[H_ROW_HI], s_hi);
+        }
+    }
     if (home < 0) return;
     if (r1 >= 0 && r2 >= 0 && r1 != r2)
     {
@@ -167,21 +198,25 @@ __global__ void k_strip_resample(int S, const int* __restrict__ cuts, const int*
 }
 
 // every dynamic row also counts (shared memory per strip is what limits its width)
-__global__ void __launch_bounds__(kBlock) k_strip_hist_rows(int nb, const unsigned* __restrict__ order, const unsigned char* __restrict__ bodyStatic, int* __restrict__ hist)
+__global__ void __launch_bounds__(kBlock) k_strip_hist_rows(int nb, const unsigned* __restrict__ order, const unsigned char* __restrict__ bodyStatic,
+    const unsigned char* __restrict__ bodyOwner, int rank, int* __restrict__ hist)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
     const unsigned body = order ? order[r] : unsigned(r);
-    if (!bodyStatic[body]) hist[r] += 24;
+    if (!bodyStatic[body] && (!bodyOwner || bodyOwner[body] == rank)) hist[r] += 24;
 }
 
 // cuts[q] = first row with at least q/S of the manifolds before it
-__global__ void __launch_bounds__(kBlock) k_strip_cuts(int nb, int S, const int* __restrict__ prefix, const int* __restrict__ total, int* __restrict__ cuts)
+__global__ void __launch_bounds__(kBlock) k_strip_cuts(int nb, int S, const int* __restrict__ prefix, const int* __restrict__ total, const int* __restrict__ header,
+    int* __restrict__ cuts)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q > S) return;
-    if (q == 0) { cuts[0] = 0; return; }
-    if (q == S) { cuts[q] = nb; return; }
+    // the strips cover the rows the laid-out manifolds touch; rows outside (other ranks' islands) belong to no strip
+    const int rowLo = min(header[H_ROW_LO], nb), rowHi = max(min(header[H_ROW_HI], nb), rowLo);
+    if (q == 0) { cuts[0] = rowLo; return; }
+    if (q == S) { cuts[q] = rowHi; return; }
     const long long target = (static_cast<long long>(*total) * q + S - 1) / S;
     int lo = 0, hi = nb;   // smallest row r in [0, nb] with prefix[r] >= target (prefix[nb] := total)
     while (lo < hi)
@@ -189,7 +224,7 @@ __global__ void __launch_bounds__(kBlock) k_strip_cuts(int nb, int S, const int*
         const int mid = (lo + hi) >> 1;
         if (prefix[mid] >= target) hi = mid; else lo = mid + 1;
     }
-    cuts[q] = lo;
+    cuts[q] = min(max(lo, rowLo), rowHi);
 }
 
 // Move every cut to the nearest row in front of which NO manifold would be split, if there is one within `reach` rows
@@ -198,21 +233,40 @@ __global__ void __launch_bounds__(kBlock) k_strip_cuts(int nb, int S, const int*
 // several devices relies on that for bit-identical results).  covered[r] > 0: a cut in front of row r splits manifolds.
 __global__ void __launch_bounds__(kBlock) k_strip_snap(int nb, int S, int reach, const int* __restrict__ covered, int* __restrict__ cuts)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q <= 0 || q >= S) return;
-    const int r0 = cuts[q];
-    for (int d = 0; d <= reach; ++d)
+    // one block per cut: the window [cut - reach, cut + reach] is searched by all threads, nearest clean row wins (the lower
+    // one on a tie)
+    __shared__ int s_best;
+    const int q = blockIdx.x + 1;
+    if (q >= S) return;
+    if (threadIdx.x == 0) s_best = 0x7fffffff;
+    __syncthreads();
+    const int r0 = cuts[q], first = cuts[0], last = cuts[S];
+    int best = 0x7fffffff;
+    for (int i = threadIdx.x; i <= 2 * reach; i += blockDim.x)
     {
-        const int lo = r0 - d, hi = r0 + d;
-        if (lo > 0 && lo < nb && covered[lo] == 0) { cuts[q] = lo; return; }
-        if (hi > 0 && hi < nb && covered[hi] == 0) { cuts[q] = hi; return; }
+        const int r = r0 - reach + i;
+        if (r < first || r > last || r >= nb || r < 0) continue;
+        if (covered[r] != 0) continue;
+        const int d = r < r0 ? r0 - r : r - r0;
+        best = min(best, 2 * d + (r > r0 ? 1 : 0));
+    }
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best != 0x7fffffff) atomicMin(&s_best, best);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_best != 0x7fffffff)
+    {
+        const int d = s_best >> 1;
+        cuts[q] = (s_best & 1) ? r0 + d : r0 - d;
     }
 }
 
-__global__ void k_strip_monotonic(int S, int* __restrict__ cuts)
+// cuts in order, and no strip wider than `limit` rows (its rows must fit in shared memory, with room left for the L1);
+// possible whenever bodies <= S * limit
+__global__ void k_strip_monotonic(int S, int limit, int* __restrict__ cuts)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    for (int q = 1; q <= S; ++q) cuts[q] = max(cuts[q], cuts[q - 1]);
+    for (int q = 1; q < S; ++q) cuts[q] = min(max(cuts[q], cuts[q - 1]), cuts[q - 1] + limit);
+    for (int q = S - 1; q >= 1; --q) cuts[q] = max(cuts[q], cuts[q + 1] - limit);
 }
 
 // largest k in [0, S) with cuts[k] <= row: the strip that holds the row (empty strips are never returned)
@@ -577,6 +631,7 @@ static size_t strip_smem_bytes(int rowCap, int cutCap, int workCap)
 }
 constexpr size_t kStripSmemLimit = 227 * 1024 - 4096;   // dynamic part: the opt-in maximum minus the kernel's static tables
 constexpr size_t kStripSmemLimit2 = 113 * 1024 - 4096;  // two CTAs per SM
+constexpr int kStripRowLimit = 10240;                   // rows per strip (160 KB of the SM's 228 KB: the record fetches of step 2 want the rest as L1)
 
 // Class-major layout of the coloured manifolds over S strips; `work` holds the colours.  On success with *usable the
 // context's schedule (slotJoint, pairIdx, bin table) is the strip layout; otherwise the caller lays out colour-major.
@@ -608,6 +663,7 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
     int* flagR = flags + (nb + 1);
     int* flagL = flags + 2 * (nb + 1);
     PHYX_CUDA(cudaMemsetAsync(header, 0, 64 * sizeof(int), c->stream));
+    PHYX_CUDA(cudaMemsetAsync(header + H_ROW_LO, 0x7f, sizeof(int), c->stream));   // 0x7f7f7f7f: larger than any row
     PHYX_CUDA(cudaMemsetAsync(sp.hist.ptr, 0, size_t(nb + 1) * sizeof(int), c->stream));
     PHYX_CUDA(cudaMemsetAsync(sp.prefixL.ptr, 0, size_t(nb + 1) * sizeof(int), c->stream));   // `cover` until the boundary lists need it
     PHYX_CUDA(cudaMemsetAsync(flags, 0, size_t(nb + 1) * sizeof(int), c->stream));
@@ -633,18 +689,21 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
         c->launches++;
     }
     k_strip_hist<<<grid, kBlock, 0, c->stream>>>(M, jb, work, rowOf, activity, c->manBody.as<int2>(), bodyOwner, c->islandRank, sp.hist.as<int>(), cover, S,
-        feedback ? prevCuts : nullptr, feedback ? factor : nullptr);
-    k_strip_hist_rows<<<gridB, kBlock, 0, c->stream>>>(nb, order, c->bodyStatic.as<unsigned char>(), sp.hist.as<int>());
+        feedback ? prevCuts : nullptr, feedback ? factor : nullptr, header);
+    k_strip_hist_rows<<<gridB, kBlock, 0, c->stream>>>(nb, order, c->bodyStatic.as<unsigned char>(), bodyOwner, c->islandRank, sp.hist.as<int>());
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, sp.hist.as<int>(), sp.prefixR.as<int>(), nb, header + H_SCAN_TOTAL));
-    k_strip_cuts<<<gridS, kBlock, 0, c->stream>>>(nb, S, sp.prefixR.as<int>(), header + H_SCAN_TOTAL, sp.cuts.as<int>());
+    k_strip_cuts<<<gridS, kBlock, 0, c->stream>>>(nb, S, sp.prefixR.as<int>(), header + H_SCAN_TOTAL, header, sp.cuts.as<int>());
     c->launches += 2;
     if (S > 1)
     {
         PHYX_TRY(exclusive_scan_i32(c, cover, cover, nb, nullptr));
-        k_strip_snap<<<gridS, kBlock, 0, c->stream>>>(nb, S, std::max(1, nb / S / 2), cover, sp.cuts.as<int>());
-        k_strip_monotonic<<<1, 32, 0, c->stream>>>(S, sp.cuts.as<int>());
-        c->launches += 2;
+        // width limit first, clean cuts last: a snapped cut is never moved again (a strip that ends up too wide for shared
+        // memory rejects the layout for this step)
+        k_strip_monotonic<<<1, 32, 0, c->stream>>>(S, S > c->numSMs ? kStripRowLimit / 2 : kStripRowLimit, sp.cuts.as<int>());
+        k_strip_snap<<<S - 1, kBlock, 0, c->stream>>>(nb, S, std::max(1, nb / S / 2), cover, sp.cuts.as<int>());
+        k_strip_monotonic<<<1, 32, 0, c->stream>>>(S, nb, sp.cuts.as<int>());
+        c->launches += 3;
     }
 
     // carry the balance factors over to the new cuts

@@ -144,13 +144,19 @@ class IslandParallelWorld:
         ctx.island_partition(self.rank, self.ranks)
         self.stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
         self.buf = None
+        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        self.timing = {"stages_before_solve_ms": 0.0, "solve_ms": 0.0, "exchange_ms": 0.0, "steps": 0}
 
     def step(self, iters=(20, 20)):
         from . import capi, scenes
 
         torch, dist = self.torch, self.dist
+        e = self.events
+        e[0].record(self.stream)
         bp = stages_before_solve(self.ctx)
-        st = self.ctx.solve_resident(iters=iters, schedule=capi.SCHEDULE_COLOUR)
+        e[1].record(self.stream)
+        st = self.ctx.solve_resident(iters=iters, schedule=capi.SCHEDULE_COLOUR)   # builds the islands, relaxes this rank's
+        e[2].record(self.stream)
         words = self.ctx.island_exchange_words()
         with torch.cuda.stream(self.stream):   # everything stays ordered on the context's own stream
             if self.buf is None or self.buf.shape[0] < words:
@@ -158,5 +164,16 @@ class IslandParallelWorld:
             self.ctx.island_pack(self.buf.data_ptr())
             dist.all_reduce(self.buf[:words], op=dist.ReduceOp.SUM, group=self.group)
             self.ctx.island_unpack(self.buf.data_ptr())
+        e[3].record(self.stream)
         self.ctx.integrate_position(scenes.DT)
+        if self.timing["steps"] >= 0:
+            e[3].synchronize()
+            self.timing["stages_before_solve_ms"] += e[0].elapsed_time(e[1])
+            self.timing["solve_ms"] += e[1].elapsed_time(e[2])
+            self.timing["exchange_ms"] += e[2].elapsed_time(e[3])
+            self.timing["steps"] += 1
         return bp, st
+
+    def mean_timing(self):
+        n = max(self.timing["steps"], 1)
+        return {k: v / n for k, v in self.timing.items() if k != "steps"}
