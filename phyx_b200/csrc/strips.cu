@@ -988,15 +988,75 @@ __device__ __forceinline__ void prefetch_manifold(const StripParams& P, int p)
 }
 
 template <int T>
-__device__ __forceinline__ void prefetch_idx(const StripParams& P, int2 bin, unsigned (&pre)[kStripU])
+__device__ __forceinline__ void prefetch_idx(const StripParams& P, int2 bin, unsigned (&pre)[kStripU], int2& preIdx)
 {
     const int n = bin.y - bin.x;
+    // a small bin is relaxed without a worklist, by the thread that tests the candidate: it will want the index words too
+    if (n <= T && int(threadIdx.x) < n) preIdx = __ldg(&P.pairIdx[bin.x + int(threadIdx.x)]);
 #pragma unroll
     for (int u = 0; u < kStripU; ++u)
     {
         const int i = int(threadIdx.x) + u * T;
         pre[u] = i < n ? __ldg(&P.pairTest[bin.x + i]) : 0xffffffffu;
     }
+}
+
+// relax the (up to two) joints of manifold slot p on the shared-memory rows; returns "productive"
+template <int PHASE>
+__device__ __forceinline__ bool relax_manifold(const StripParams& P, StripCta& s, float4* rowsS, const float4* __restrict__ rowsG, int p, int2 idx, int it)
+{
+    const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
+    const float4 a0 = __ldcs(rec), b0 = __ldcs(rec + 1), c2 = __ldcs(rec + 2), nd = __ldcs(rec + 3);
+    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1, accv;
+    if (PHASE == 0)
+    {
+        a1 = __ldcs(rec + 4);
+        b1 = __ldcs(rec + 5);
+        accv = __ldcs(reinterpret_cast<const float4*>(&P.accNF[2 * p]));
+    }
+    else
+    {
+        const float2 a = __ldcs(reinterpret_cast<const float2*>(&P.accD[2 * p]));
+        accv = make_float4(a.x, a.y, 0.f, 0.f);
+    }
+    const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit, haveB = idx.y < 0;
+    const int r1 = idx.x & kBodyMask, r2 = idx.y & kBodyMask;
+    float4 w1 = st1 ? __ldcg(&rowsG[r1]) : rowsS[r1];
+    float4 w2 = st2 ? __ldcg(&rowsG[r2]) : rowsS[r2];
+    const int last1 = __float_as_int(w1.w), last2 = __float_as_int(w2.w);   // used for dynamic bodies only
+    const float4 a3 = make_float4(0.f, 0.f, nd.x, nd.y), b3 = make_float4(0.f, 0.f, nd.z, nd.w);
+    float2 accA, accB;
+    if (PHASE == 0)
+    {
+        accA = make_float2(accv.x, accv.y);
+        accB = make_float2(accv.z, accv.w);
+    }
+    else
+    {
+        accA = make_float2(accv.x, 0.f);
+        accB = make_float2(accv.y, 0.f);
+    }
+    s.active[PHASE] += haveB ? 2u : 1u;
+    const bool productiveA = relax<PHASE>(a0, a1, c2, a3, accA, w1, w2, false);
+    bool productiveB = false;
+    if (haveB) productiveB = relax<PHASE>(b0, b1, c2, b3, accB, w1, w2, false);
+    if (PHASE == 0)
+        __stcs(reinterpret_cast<float4*>(&P.accNF[2 * p]), make_float4(accA.x, accA.y, accB.x, accB.y));
+    else
+        __stcs(reinterpret_cast<float2*>(&P.accD[2 * p]), make_float2(accA.x, accB.x));
+    // lastIteration = it where productive (Solver.cpp:903-910)
+    const bool productive = productiveA || productiveB;
+    if (!st1)
+    {
+        w1.w = __int_as_float(productive ? it : last1);
+        rowsS[r1] = w1;
+    }
+    if (!st2)
+    {
+        w2.w = __int_as_float(productive ? it : last2);
+        rowsS[r2] = w2;
+    }
+    return productive;
 }
 
 // One bin (one colour of one class) of one iteration.  PHASE 0: SolveJointsImpulses (Solver.cpp:781-910), PHASE 1:
@@ -1014,13 +1074,26 @@ __device__ __forceinline__ void prefetch_idx(const StripParams& P, int2 bin, uns
 // (tests/conftest.py); the grid-barrier forms of solve.cu keep the reference's shared record.
 template <int PHASE, int T>
 __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, float4* rowsS, int dummyRow, const float4* __restrict__ rowsG, int2 bin, int2 next, int it,
-    unsigned (&pre)[kStripU])
+    unsigned (&pre)[kStripU], int2& preIdx)
 {
     const int n = bin.y - bin.x;
     const int lane = threadIdx.x & 31;
     const unsigned below = (1u << lane) - 1u;
     bool anyProductive = false;
     const long long c0 = P.trace ? clock64() : 0;
+    if (n <= T)
+    {
+        // small bin: every thread owns at most one candidate; test it and relax it on the spot (no worklist, one barrier)
+        const unsigned t = pre[0];
+        const int2 idx = preIdx;
+        prefetch_idx<T>(P, next, pre, preIdx);
+        const int ra = min(int(t & 0xffffu), dummyRow), rb = min(int(t >> 16), dummyRow);
+        const bool active = (__float_as_int(rowsS[ra].w) > it - 2) || (__float_as_int(rowsS[rb].w) > it - 2);
+        if (active) anyProductive = relax_manifold<PHASE>(P, s, rowsS, rowsG, bin.x + int(threadIdx.x), idx, it);
+        __syncthreads();
+        if (P.trace) s.clk[1] += clock64() - c0;
+        return anyProductive;
+    }
     int* count = &s.s_count[s.parity];
     // ---- step 1: the skip test (Solver.cpp:790-792, for both joints of a manifold at once, see solve.cu paired levels).
     // kStripU candidates per thread from prefetched test words; slots beyond the bin are skipped as a block (n is uniform)
@@ -1046,7 +1119,7 @@ __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, flo
             }
         }
         // the test words are used up: fetch those of the next bin now, a whole bin pass ahead of their use
-        prefetch_idx<T>(P, next, pre);
+        prefetch_idx<T>(P, next, pre, preIdx);
         if (warpTotal)
         {
             int base = 0;
@@ -1089,62 +1162,9 @@ __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, flo
 
     // ---- step 2: relax the worklist, one entry per thread and round.  Consecutive entries (neighbouring records) go to
     // consecutive lanes: dealing them across the warps instead was measured 3x slower (DRAM locality of the record fetch)
-    for (int w = threadIdx.x; w < total; w += T)
-    {
+    for (int w = threadIdx.x; w < total; w += T) {
         const int p = bin.x + s.s_work[w];
-        const int2 idx = __ldg(&P.pairIdx[p]);
-        const float4* rec = P.pairQ + size_t(p) * kPairRecordWords;
-        const float4 a0 = __ldcs(rec), b0 = __ldcs(rec + 1), c2 = __ldcs(rec + 2), nd = __ldcs(rec + 3);
-        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1, accv;
-        if (PHASE == 0)
-        {
-            a1 = __ldcs(rec + 4);
-            b1 = __ldcs(rec + 5);
-            accv = __ldcs(reinterpret_cast<const float4*>(&P.accNF[2 * p]));
-        }
-        else
-        {
-            const float2 a = __ldcs(reinterpret_cast<const float2*>(&P.accD[2 * p]));
-            accv = make_float4(a.x, a.y, 0.f, 0.f);
-        }
-        const bool st1 = idx.x & kStaticBit, st2 = idx.y & kStaticBit, haveB = idx.y < 0;
-        const int r1 = idx.x & kBodyMask, r2 = idx.y & kBodyMask;
-        float4 w1 = st1 ? __ldcg(&rowsG[r1]) : rowsS[r1];
-        float4 w2 = st2 ? __ldcg(&rowsG[r2]) : rowsS[r2];
-        const int last1 = __float_as_int(w1.w), last2 = __float_as_int(w2.w);   // used for dynamic bodies only
-        const float4 a3 = make_float4(0.f, 0.f, nd.x, nd.y), b3 = make_float4(0.f, 0.f, nd.z, nd.w);
-        float2 accA, accB;
-        if (PHASE == 0)
-        {
-            accA = make_float2(accv.x, accv.y);
-            accB = make_float2(accv.z, accv.w);
-        }
-        else
-        {
-            accA = make_float2(accv.x, 0.f);
-            accB = make_float2(accv.y, 0.f);
-        }
-        s.active[PHASE] += haveB ? 2u : 1u;
-        const bool productiveA = relax<PHASE>(a0, a1, c2, a3, accA, w1, w2, false);
-        bool productiveB = false;
-        if (haveB) productiveB = relax<PHASE>(b0, b1, c2, b3, accB, w1, w2, false);
-        if (PHASE == 0)
-            __stcs(reinterpret_cast<float4*>(&P.accNF[2 * p]), make_float4(accA.x, accA.y, accB.x, accB.y));
-        else
-            __stcs(reinterpret_cast<float2*>(&P.accD[2 * p]), make_float2(accA.x, accB.x));
-        // lastIteration = it where productive (Solver.cpp:903-910)
-        const bool productive = productiveA || productiveB;
-        if (!st1)
-        {
-            w1.w = __int_as_float(productive ? it : last1);
-            rowsS[r1] = w1;
-        }
-        if (!st2)
-        {
-            w2.w = __int_as_float(productive ? it : last2);
-            rowsS[r2] = w2;
-        }
-        anyProductive |= productive;
+        anyProductive |= relax_manifold<PHASE>(P, s, rowsS, rowsG, p, __ldg(&P.pairIdx[p]), it);
     }
     // rows of this bin are written: the next bin may read them
     __syncthreads();
@@ -1158,7 +1178,7 @@ __device__ __forceinline__ bool solve_bin(const StripParams& P, StripCta& s, flo
 
 // One pass over the strip's classes.  MODE -1: warm start, 0: impulse iteration `it`, 1: displacement iteration `it`.
 template <int MODE, int T>
-__device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int it, unsigned long long seq, int passIndex, unsigned (&pre)[kStripU])
+__device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int it, unsigned long long seq, int passIndex, unsigned (&pre)[kStripU], int2& preIdx)
 {
     constexpr int PHASE = MODE == 1 ? 1 : 0;
     float4* rowsG = P.rows[PHASE];
@@ -1173,7 +1193,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
         if (MODE < 0)
             prestep_bin<T>(P, s.s_rows, rowsG, s.s_bins[b]);
         else
-            any |= solve_bin<PHASE, T>(P, s, s.s_rows, P.rowCap - 1, rowsG, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, pre);
+            any |= solve_bin<PHASE, T>(P, s, s.s_rows, P.rowCap - 1, rowsG, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, pre, preIdx);
     }
     trace_mark(P, k, passIndex, 1);
     s.busy += clock64() - w0;
@@ -1183,36 +1203,33 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
         P.trace[(size_t(k) * P.tracePasses + passIndex) * 8 + 6] = (unsigned long long)s.clk[1];
     }
     if (P.S == 1) return any;
-    // my left-boundary rows -> global memory, for cut set k-1
-    if (k > 0)
+    // my left-boundary rows -> global memory, for cut set k-1 (which exists exactly if I have left-boundary rows)
+    if (k > 0 && s.nL > 0)
     {
         for (int i = threadIdx.x; i < s.nL; i += T) __stcg(&rowsG[s.row0 + s.s_listL[i]], s.s_rows[s.s_listL[i]]);
         __syncthreads();
         if (threadIdx.x == 0) flag_release(&P.flagA[k], seq);
     }
-    if (k + 1 < P.S)
+    if (k + 1 < P.S && s.nCut > 0)
     {
-        if (s.nCut > 0)
-        {
-            cta_wait_flag(&P.flagA[k + 1], seq);
-            trace_mark(P, k, passIndex, 2);
-            const long long w1 = clock64();
-            for (int i = threadIdx.x; i < s.nR; i += T) s.s_cut[i] = s.s_rows[s.s_listR[i]];
-            for (int i = threadIdx.x; i < s.nLn; i += T) s.s_cut[s.nR + i] = __ldcg(&rowsG[s.s_listN[i]]);
-            __syncthreads();
-            for (int b = s.nInt; b < nBins; ++b)
-            {
-                if (MODE < 0)
-                    prestep_bin<T>(P, s.s_cut, rowsG, s.s_bins[b]);
-                else
-                    any |= solve_bin<PHASE, T>(P, s, s.s_cut, P.cutCap - 1, rowsG, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, pre);
-            }
-            for (int i = threadIdx.x; i < s.nR; i += T) s.s_rows[s.s_listR[i]] = s.s_cut[i];
-            for (int i = threadIdx.x; i < s.nLn; i += T) __stcg(&rowsG[s.s_listN[i]], s.s_cut[s.nR + i]);
-            s.busy += clock64() - w1;
-        }
+        cta_wait_flag(&P.flagA[k + 1], seq);
+        trace_mark(P, k, passIndex, 2);
+        const long long w1 = clock64();
+        for (int i = threadIdx.x; i < s.nR; i += T) s.s_cut[i] = s.s_rows[s.s_listR[i]];
+        for (int i = threadIdx.x; i < s.nLn; i += T) s.s_cut[s.nR + i] = __ldcg(&rowsG[s.s_listN[i]]);
         __syncthreads();
-        if (threadIdx.x == 0) flag_release(&P.flagB[k], seq);
+        for (int b = s.nInt; b < nBins; ++b)
+        {
+            if (MODE < 0)
+                prestep_bin<T>(P, s.s_cut, rowsG, s.s_bins[b]);
+            else
+                any |= solve_bin<PHASE, T>(P, s, s.s_cut, P.cutCap - 1, rowsG, s.s_bins[b], s.s_bins[b + 1 < nBins ? b + 1 : 0], it, pre, preIdx);
+        }
+        for (int i = threadIdx.x; i < s.nR; i += T) s.s_rows[s.s_listR[i]] = s.s_cut[i];
+        for (int i = threadIdx.x; i < s.nLn; i += T) __stcg(&rowsG[s.s_listN[i]], s.s_cut[s.nR + i]);
+        s.busy += clock64() - w1;
+        __syncthreads();
+        if (threadIdx.x == 0) flag_release(&P.flagB[k], seq);   // (strip k+1 waits for it exactly if it has left-boundary rows)
         trace_mark(P, k, passIndex, 3);
     }
     if (k > 0 && s.nL > 0)
@@ -1227,7 +1244,7 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
 
 // all iterations of one phase; returns the number of passes executed (>= the reference's count: see the header)
 template <int PHASE, int T>
-__device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int iters, unsigned long long& seq, int& passIndex, unsigned (&pre)[kStripU])
+__device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int iters, unsigned long long& seq, int& passIndex, unsigned (&pre)[kStripU], int2& preIdx)
 {
     __shared__ unsigned long long s_word;
     unsigned long long* done = P.done + size_t(PHASE) * P.doneStride;
@@ -1250,7 +1267,7 @@ __device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int 
         }
         ++seq;
         ++passIndex;
-        const bool mine = run_pass<PHASE, T>(P, s, it, seq, passIndex, pre);
+        const bool mine = run_pass<PHASE, T>(P, s, it, seq, passIndex, pre, preIdx);
         const int any = __syncthreads_or(mine ? 1 : 0);
         if (threadIdx.x == 0) atomicAdd(&done[it], 1ull | (any ? (1ull << 32) : 0ull));
     }
@@ -1343,10 +1360,11 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
 
     // warm start
     ++seq;
-    run_pass<-1, T>(P, s, 0, seq, passIndex, pre);
-    if (s.nInt + s.nCut > 0) prefetch_idx<T>(P, s_bins[0], pre);
+    int2 preIdx = make_int2(-1, -1);
+    run_pass<-1, T>(P, s, 0, seq, passIndex, pre, preIdx);
+    if (s.nInt + s.nCut > 0) prefetch_idx<T>(P, s_bins[0], pre, preIdx);
 
-    const int ranI = run_phase<0, T>(P, s, P.contactIters, seq, passIndex, pre);
+    const int ranI = run_phase<0, T>(P, s, P.contactIters, seq, passIndex, pre, preIdx);
 
     // velocity rows back, displacement rows in
     __syncthreads();
@@ -1367,7 +1385,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
             if (bytes) bulk_g2s(s.s_rows, P.rows[1] + s.row0, bytes, &s_mbar);
         }
         mbar_wait(&s_mbar, 1);
-        ranD = run_phase<1, T>(P, s, P.penetrationIters, seq, passIndex, pre);
+        ranD = run_phase<1, T>(P, s, P.penetrationIters, seq, passIndex, pre, preIdx);
         __syncthreads();
         if (threadIdx.x == 0 && s.nRows > 0)
         {

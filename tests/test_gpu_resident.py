@@ -223,3 +223,33 @@ def test_more_than_64_colours_falls_back_to_the_host_builder(oracle):
     ob, oj, ran = oracle.solve_scheduled(b0, j0, cp, slots, levels, iters=(4, 2))
     assert_records_equal(ctx.download_joints(), oj, what="joints")
     assert_records_equal(ctx.download_bodies(), ob, VEL_FIELDS, what="bodies")
+
+
+def test_tall_static_wall_and_thick_ground_do_not_lose_contacts(ctx, ref):
+    """A body whose y reach is thousands of cells high (a wall, a slab with half-height 2000) makes the sweep's cell index
+    exceed the int range before it is clamped (advisor finding, round 1): the pairs must still equal the reference's."""
+    rows = [(0.0, -1990.0, 0.0, 1e6, 2000.0, 1.0)]                      # thick ground, top at y = 10
+    rows += [(-500.0, 3000.0, 0.0, 10.0, 3000.0, 1.0)]                  # tall wall
+    rows += [(-479.0 + 21.0 * i, 15.0, 0.0, 10.0, 5.0, 0.0) for i in range(40)]
+    rows += [(-479.0 + 21.0 * i, 25.2, 0.0, 10.0, 5.0, 0.0) for i in range(40)]
+    sc = np.asarray(rows, dtype=np.float32)
+    r = ref.RefWorld(sc, "strict")
+    w = world.World(sc)
+    c2 = w.context()
+    c2.upload_bodies(w.bodies())
+    for step in range(6):
+        r.step_staged(mask=0x07 | ref.SAFE_PAIRS)
+        c2.integrate_velocity(scenes.DT, scenes.GRAVITY)
+        c2.update_broadphase()
+        bp = c2.update_pairs()
+        tests, pairs = r.count_sweep()
+        assert (bp.tests, bp.pairs) == (tests, pairs), f"step {step}"
+        assert_records_equal(c2.download_manifolds(), r.manifolds(), what=f"step {step} manifolds")
+        r.step_staged(mask=0xF8)
+        c2.update_manifolds()
+        c2.pack_manifolds()
+        c2.refresh_contact_joints()
+        c2.solve_resident(schedule=capi.SCHEDULE_REPLAY_AVX2)
+        c2.integrate_position(scenes.DT)
+    assert_records_equal(c2.download_bodies(), r.bodies(), ("pos", "velocity"), what="bodies")
+    w.close()

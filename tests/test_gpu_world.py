@@ -35,6 +35,7 @@ def rel_dev(a, b):
     ("tumble_300", 60, T.SOLVE_SCALAR, 0),
     ("tumble_3k", 80, T.SOLVE_AVX2, 0),
     ("platforms_400", 200, T.SOLVE_AVX2, 0),   # bodies with invMass = 0 only (not static): many joints on one dynamic body
+    ("pyramid_10k", 100, T.SOLVE_AVX2, 0),     # "after 100 steps" at 10 k bodies (1150 dependency levels per pass)
 ])
 def test_world_update_tracks_reference(ref, scene, steps, mode, flags):
     sc = scenes.make(scene)
