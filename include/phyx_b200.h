@@ -153,6 +153,10 @@ PHYX_B200_API int phyx_b200_body_count(const phyx_b200_ctx* ctx);
 PHYX_B200_API int phyx_b200_host_register(phyx_b200_ctx* ctx, void* ptr, size_t bytes);
 PHYX_B200_API int phyx_b200_host_unregister(phyx_b200_ctx* ctx, void* ptr);
 
+/* AABB of all dynamic bodies {min.x, min.y, max.x, max.y} ({+inf, +inf, -inf, -inf}-like extremes if there are none): what a
+ * caller that shards a scene by island over several devices exchanges to check that the shards stay apart */
+PHYX_B200_API int phyx_b200_dynamic_extent(phyx_b200_ctx* ctx, float* minMax4);
+
 /* ---- World::IntegrateVelocity / IntegratePosition, reference src/World.cpp:39-70 -------------- */
 PHYX_B200_API int phyx_b200_integrate_velocity(phyx_b200_ctx* ctx, float dt, float gravity);
 PHYX_B200_API int phyx_b200_integrate_position(phyx_b200_ctx* ctx, float dt);
@@ -251,6 +255,9 @@ PHYX_B200_API int phyx_b200_download_islands(phyx_b200_ctx* ctx, int32_t* island
  * caller; an integer SUM all-reduce over the ranks (e.g. NCCL, one non-zero term per word: exact) followed by island_unpack
  * on every rank leaves all replicas with the complete, identical state.  ranks = 1 switches the split off. */
 PHYX_B200_API int phyx_b200_island_partition(phyx_b200_ctx* ctx, int rank, int ranks);
+/* the rank that owns each body under the active island partition (static bodies: rank 0), as built by the last
+ * build_islands / solve_resident */
+PHYX_B200_API int phyx_b200_download_body_owners(phyx_b200_ctx* ctx, uint8_t* ownerOfBody, int32_t capacity);
 PHYX_B200_API int phyx_b200_island_exchange_words(phyx_b200_ctx* ctx, int64_t* words);
 PHYX_B200_API int phyx_b200_island_pack(phyx_b200_ctx* ctx, int32_t* deviceBuffer);
 PHYX_B200_API int phyx_b200_island_unpack(phyx_b200_ctx* ctx, const int32_t* deviceBuffer);

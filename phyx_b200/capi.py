@@ -34,6 +34,7 @@ EXPORTS = (
     "phyx_b200_body_count",
     "phyx_b200_host_register",
     "phyx_b200_host_unregister",
+    "phyx_b200_dynamic_extent",
     "phyx_b200_integrate_velocity",
     "phyx_b200_integrate_position",
     "phyx_b200_update_broadphase",
@@ -64,6 +65,7 @@ EXPORTS = (
     "phyx_b200_build_islands",
     "phyx_b200_download_islands",
     "phyx_b200_island_partition",
+    "phyx_b200_download_body_owners",
     "phyx_b200_island_exchange_words",
     "phyx_b200_island_pack",
     "phyx_b200_island_unpack",
@@ -146,6 +148,7 @@ def load():
     l.phyx_b200_body_count.argtypes = [vp]
     l.phyx_b200_host_register.argtypes = [vp, vp, C.c_size_t]
     l.phyx_b200_host_unregister.argtypes = [vp, vp]
+    l.phyx_b200_dynamic_extent.argtypes = [vp, vp]
     l.phyx_b200_integrate_velocity.argtypes = [vp, f32, f32]
     l.phyx_b200_integrate_position.argtypes = [vp, f32]
     l.phyx_b200_update_broadphase.argtypes = [vp]
@@ -176,6 +179,7 @@ def load():
     l.phyx_b200_build_islands.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     l.phyx_b200_download_islands.argtypes = [vp, vp, vp, i32]
     l.phyx_b200_island_partition.argtypes = [vp, i32, i32]
+    l.phyx_b200_download_body_owners.argtypes = [vp, vp, i32]
     l.phyx_b200_island_exchange_words.argtypes = [vp, C.POINTER(i64)]
     l.phyx_b200_island_pack.argtypes = [vp, vp]
     l.phyx_b200_island_unpack.argtypes = [vp, vp]
@@ -226,6 +230,12 @@ class Context:
         n = self.l.phyx_b200_body_count(self.h)
         out = np.zeros(n, dtype=T.RIGID_BODY) if out is None else out
         self._check(self.l.phyx_b200_download_bodies(self.h, _p(out), n))
+        return out
+
+    def dynamic_extent(self):
+        """(min.x, min.y, max.x, max.y) over the dynamic bodies' AABBs"""
+        out = np.zeros(4, np.float32)
+        self._check(self.l.phyx_b200_dynamic_extent(self.h, _p(out)))
         return out
 
     def integrate_velocity(self, dt, gravity):

@@ -297,6 +297,17 @@ int phyx_b200_integrate_position(phyx_b200_ctx* c, float dt)
     return bodies_integrate_position(c, dt);
 }
 
+int phyx_b200_dynamic_extent(phyx_b200_ctx* c, float* minMax4)
+{
+    PHYX_TRY(check(c));
+    if (!minMax4)
+    {
+        set_error("dynamic_extent: null output");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    return bodies_dynamic_extent(c, minMax4);
+}
+
 int phyx_b200_snapshot_bodies(phyx_b200_ctx* c)
 {
     PHYX_TRY(check(c));
@@ -518,6 +529,28 @@ int phyx_b200_island_partition(phyx_b200_ctx* c, int rank, int ranks)
     c->islandRanks = ranks;
     c->islandsValid = false;
     c->scheduleMode = -1;   // schedules built so far cover other manifolds
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_download_body_owners(phyx_b200_ctx* c, uint8_t* ownerOfBody, int32_t capacity)
+{
+    PHYX_TRY(check(c));
+    const int nb = c->bodyCount;
+    if (c->islandRanks < 2 || !c->islandsValid || c->islandBodies != nb)
+    {
+        set_error("download_body_owners: no island partition is active (island_partition with ranks > 1, then build_islands or a solve)");
+        return PHYX_B200_ERR_STATE;
+    }
+    if (capacity < nb)
+    {
+        set_error("download_body_owners: capacity %d < %d bodies", capacity, nb);
+        return PHYX_B200_ERR_CAPACITY;
+    }
+    if (nb > 0)
+    {
+        PHYX_CUDA(cudaMemcpyAsync(ownerOfBody, c->bodyOwner.ptr, size_t(nb), cudaMemcpyDeviceToHost, c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    }
     return PHYX_B200_OK;
 }
 

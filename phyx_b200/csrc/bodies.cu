@@ -114,6 +114,68 @@ __global__ void k_integrate_position(int n, float dt, const float4* __restrict__
     aabb[i] = make_float4(p.z - ex, p.w - ey, p.z + ex, p.w + ey);
 }
 
+// AABB of all dynamic bodies: {min.x, min.y, max.x, max.y} as order-preserving unsigned keys (atomicMin / atomicMax)
+__device__ __forceinline__ unsigned float_key(float v)
+{
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void k_dynamic_extent(int n, const float4* __restrict__ aabb, const float4* __restrict__ params, unsigned* __restrict__ out4)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned k[4] = { 0xffffffffu, 0xffffffffu, 0u, 0u };
+    if (i < n)
+    {
+        const float4 p = params[i];
+        if (!(p.x == 0.0f && p.y == 0.0f))
+        {
+            const float4 a = aabb[i];
+            k[0] = float_key(a.x);
+            k[1] = float_key(a.y);
+            k[2] = float_key(a.z);
+            k[3] = float_key(a.w);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        k[0] = min(k[0], __shfl_xor_sync(0xffffffffu, k[0], o));
+        k[1] = min(k[1], __shfl_xor_sync(0xffffffffu, k[1], o));
+        k[2] = max(k[2], __shfl_xor_sync(0xffffffffu, k[2], o));
+        k[3] = max(k[3], __shfl_xor_sync(0xffffffffu, k[3], o));
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicMin(&out4[0], k[0]);
+        atomicMin(&out4[1], k[1]);
+        atomicMax(&out4[2], k[2]);
+        atomicMax(&out4[3], k[3]);
+    }
+}
+
+int bodies_dynamic_extent(phyx_b200_ctx* c, float* out4)
+{
+    const int n = c->bodyCount;
+    PHYX_TRY(c->counters.reserve(64));
+    unsigned* d = c->counters.as<unsigned>() + 8;
+    const unsigned init[4] = { 0xffffffffu, 0xffffffffu, 0u, 0u };
+    PHYX_CUDA(cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    if (n > 0)
+    {
+        k_dynamic_extent<<<(n + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(n, c->aabb.as<float4>(), c->params.as<float4>(), d);
+        c->launches++;
+    }
+    unsigned host[4];
+    PHYX_CUDA(cudaMemcpyAsync(host, d, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
+    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; ++k)
+    {
+        const unsigned u = host[k];
+        const unsigned bits = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        memcpy(&out4[k], &bits, 4);
+    }
+    return PHYX_B200_OK;
+}
+
 static int reserve_bodies(phyx_b200_ctx* c, int n)
 {
     size_t n4 = size_t(n > 0 ? n : 1) * sizeof(float4);

@@ -229,6 +229,7 @@ int bodies_download(phyx_b200_ctx* c, phyx_rigid_body* bodies, int n);
 int bodies_integrate_velocity(phyx_b200_ctx* c, float dt, float gravity);
 int bodies_integrate_position(phyx_b200_ctx* c, float dt);
 int bodies_snapshot(phyx_b200_ctx* c, bool restore);
+int bodies_dynamic_extent(phyx_b200_ctx* c, float* out4);
 
 // broadphase.cu
 int broadphase_update(phyx_b200_ctx* c);

@@ -177,3 +177,89 @@ class IslandParallelWorld:
     def mean_timing(self):
         n = max(self.timing["steps"], 1)
         return {k: v / n for k, v in self.timing.items() if k != "steps"}
+
+
+class ShardedWorld:
+    """Island-parallel execution WITHOUT replication: every rank simulates only the bodies of its own islands (plus the static
+    bodies) as a world of its own, so all eight stages scale with the rank count and a step needs no exchange of state at
+    all.  This is the reference's island split (src/Solver.cpp:73-92: islands are solved independently) taken to the whole
+    step.  It is valid while the ranks' islands stay apart, which is checked every `check_every` steps by an all-gather of
+    each rank's x-extent (the only collective; a violation raises: re-partition with `IslandParallelWorld`, which handles any
+    contact graph).  Shards are cut on the contact graph: the full world is stepped `probe_steps` steps on every rank, the
+    device island builder assigns the island groups to the ranks, and each rank keeps its own bodies.  Results are NOT
+    bit-identical to the one-device run of the full scene (body and manifold indices differ per shard, and with them the
+    colouring priorities); use IslandParallelWorld where that is required."""
+
+    def __init__(self, ctx, bodies, device, group=None, probe_steps=10, check_every=8, margin=25.0):
+        import torch
+        import torch.distributed as dist
+
+        from . import capi, scenes
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.ctx, self.device = ctx, device
+        self.rank, self.ranks = dist.get_rank(group), dist.get_world_size(group)
+        self.check_every, self.margin, self.steps = check_every, margin, 0
+        # probe: the contact graph of the full scene after a few full steps, identical on every rank
+        import ctypes as C
+
+        ctx.upload_bodies(bodies)
+        for _ in range(probe_steps):
+            stages_before_solve(ctx)
+            ctx.solve_resident(iters=(20, 20), schedule=capi.SCHEDULE_COLOUR)
+            ctx.integrate_position(scenes.DT)
+        probed = ctx.download_bodies()   # the state the shards start from: after the last complete step
+        stages_before_solve(ctx)         # contacts of the next step: the graph the shards are cut on
+        ctx.island_partition(self.rank, self.ranks)
+        self.island_counts = ctx.build_islands()   # (groups, largest group, islands); also assigns the groups to the ranks
+        owner = np.zeros(bodies.shape[0], np.uint8)
+        ctx._check(ctx.l.phyx_b200_download_body_owners(ctx.h, owner.ctypes.data_as(C.c_void_p), owner.shape[0]))
+        ctx.island_partition(0, 1)
+        # this rank's world: the static bodies and the bodies of its own islands, in their original order
+        static = (bodies["invMass"] == 0) & (bodies["invInertia"] == 0)
+        self.global_index = np.nonzero(static | (owner == self.rank))[0]
+        self.dynamic_owned = int((~static & (owner == self.rank)).sum())
+        ctx.reset_collider()
+        mine = np.array(probed[self.global_index], copy=True)
+        mine["index"] = np.arange(mine.shape[0], dtype=np.uint32)
+        ctx.upload_bodies(mine)
+        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+        ctx.update_broadphase()   # (fills the AABBs' sorted order; the extent check below only needs the uploaded AABBs)
+        self.check_apart()        # a pile that was not one island yet when the shards were cut would straddle two ranks
+
+    def step(self, iters=(20, 20)):
+        from . import capi, scenes
+
+        bp = stages_before_solve(self.ctx)
+        st = self.ctx.solve_resident(iters=iters, schedule=capi.SCHEDULE_COLOUR)
+        self.ctx.integrate_position(scenes.DT)
+        self.steps += 1
+        if self.check_every and self.steps % self.check_every == 0:
+            self.check_apart()
+        return bp, st
+
+    def check_apart(self):
+        """all-gather of the ranks' dynamic x-extents; raises if two ranks' islands could touch"""
+        torch, dist = self.torch, self.dist
+        e = self.ctx.dynamic_extent()   # reduced on the device: 16 bytes come back
+        lo, hi = (float(e[0]), float(e[2])) if self.dynamic_owned else (float("inf"), float("-inf"))
+        t = torch.tensor([lo, hi], dtype=torch.float64, device=f"cuda:{self.device}" if dist.get_backend(self.group) == "nccl" else "cpu")
+        ext = [torch.zeros_like(t) for _ in range(self.ranks)]
+        dist.all_gather(ext, t, group=self.group)
+        spans = sorted((float(e[0]), float(e[1]), k) for k, e in enumerate(ext) if float(e[0]) <= float(e[1]))
+        for (lo1, hi1, k1), (lo2, hi2, k2) in zip(spans[:-1], spans[1:]):
+            if lo2 - hi1 < self.margin:
+                raise RuntimeError(f"islands of ranks {k1} and {k2} are within {self.margin} of each other: the shards are no longer independent")
+        return spans
+
+    def gather_bodies(self, total):
+        """the full scene's body records on every rank (each body from the rank that owns it; static bodies from rank 0)"""
+        dist = self.dist
+        mine = self.ctx.download_bodies()
+        parts = [None] * self.ranks
+        dist.all_gather_object(parts, (self.global_index, mine), group=self.group)
+        out = np.zeros(total, dtype=mine.dtype)
+        for idx, rec in reversed(parts):   # rank 0 last: its copy of the static bodies wins
+            out[idx] = rec
+        out["index"] = np.arange(total, dtype=np.uint32)
+        return out
