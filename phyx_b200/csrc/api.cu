@@ -90,6 +90,69 @@ void DevBuf::release()
     cap = 0;
 }
 
+constexpr size_t kMailboxBytes = 4096, kMailboxFlag = 4096 - 64;   // flag word at the start of the last cache line
+
+__global__ void k_mailbox_copy(const int* __restrict__ src, int words, int* __restrict__ dst)
+{
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void k_mailbox_flag(volatile int* flag, int seq)
+{
+    __threadfence_system();   // (kernels of one stream run in order: the staged copies are complete; make them visible first)
+    *flag = seq;
+}
+
+int mailbox_stage(phyx_b200_ctx* c, const void* dev, size_t bytes, size_t offset)
+{
+    if (bytes % 4 || offset % 4 || offset + bytes > kMailboxFlag)
+    {
+        set_error("mailbox: bad piece (%zu bytes at %zu)", bytes, offset);
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    k_mailbox_copy<<<1, 64, 0, c->stream>>>(static_cast<const int*>(dev), int(bytes / 4), c->mailboxDev + offset / 4);
+    return PHYX_B200_OK;
+}
+
+int mailbox_wait(phyx_b200_ctx* c)
+{
+    const int seq = int(++c->mailboxSeq & 0x7fffffffu);
+    k_mailbox_flag<<<1, 1, 0, c->stream>>>(c->mailboxDev + kMailboxFlag / 4, seq);
+    PHYX_CUDA(cudaGetLastError());
+    volatile int* flag = c->mailboxHost + kMailboxFlag / 4;
+    for (unsigned spins = 0;; ++spins)
+    {
+        if (*flag == seq) break;
+        if ((spins & 0xffffu) == 0xffffu)
+        {
+            // a faulted kernel never raises the flag: ask the driver now and then
+            const cudaError_t e = cudaStreamQuery(c->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+            {
+                set_error("device error while waiting for a result: %s", cudaGetErrorString(e));
+                return PHYX_B200_ERR_CUDA;
+            }
+            if (e == cudaSuccess && *flag != seq)
+            {
+                // the stream has drained without the flag (cannot happen unless the launch itself failed)
+                if (*flag == seq) break;
+                set_error("mailbox flag lost");
+                return PHYX_B200_ERR_CUDA;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return PHYX_B200_OK;
+}
+
+int fetch_small(phyx_b200_ctx* c, const void* dev, size_t bytes, void* out)
+{
+    PHYX_TRY(mailbox_stage(c, dev, bytes, 0));
+    PHYX_TRY(mailbox_wait(c));
+    memcpy(out, mailbox_at(c, 0), bytes);
+    return PHYX_B200_OK;
+}
+
 static int check(phyx_b200_ctx* c)
 {
     if (!c)
@@ -177,6 +240,13 @@ int phyx_b200_create(int device, phyx_b200_ctx** out)
         PHYX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& ev : c->ev) PHYX_CUDA(cudaEventCreate(&ev));
         for (auto& ev : c->evBp) PHYX_CUDA(cudaEventCreate(&ev));
+        void* host = nullptr;
+        PHYX_CUDA(cudaHostAlloc(&host, kMailboxBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(host, 0, kMailboxBytes);
+        c->mailboxHost = static_cast<int*>(host);
+        void* dev = nullptr;
+        PHYX_CUDA(cudaHostGetDevicePointer(&dev, host, 0));
+        c->mailboxDev = static_cast<int*>(dev);
         return PHYX_B200_OK;
     };
     const int st = init();
@@ -188,6 +258,7 @@ int phyx_b200_create(int device, phyx_b200_ctx** out)
         for (auto& ev : c->evBp)
             if (ev) cudaEventDestroy(ev);
         if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->mailboxHost) cudaFreeHost(c->mailboxHost);
         delete c;
         return st;
     }
@@ -212,6 +283,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     for (auto& ev : c->evBp)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
+    if (c->mailboxHost) cudaFreeHost(c->mailboxHost);
     delete c;
 }
 

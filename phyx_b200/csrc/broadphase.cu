@@ -528,8 +528,7 @@ int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats, bool f
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, c->itemStart.as<int>(), c->itemStart.as<int>(), n, d_numItems));
     int numItems = 0;
-    PHYX_CUDA(cudaMemcpyAsync(&numItems, d_numItems, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    PHYX_TRY(fetch_small(c, d_numItems, sizeof(int), &numItems));
     if (numItems == 0) return PHYX_B200_OK;
 
     PHYX_TRY(c->items.reserve(size_t(numItems) * sizeof(int2)));
@@ -562,8 +561,7 @@ int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats, bool f
     c->launches += 2;
     PHYX_TRY(exclusive_scan_i32(c, c->itemCount.as<int>(), c->itemCount.as<int>(), numItems, d_numPairs));
     struct { int items, pairs; long long pad; unsigned long long tests, hits; } host;
-    PHYX_CUDA(cudaMemcpyAsync(&host, c->counters.ptr, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
-    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    PHYX_TRY(fetch_small(c, c->counters.ptr, sizeof(host), &host));
     c->lastTests = (long long)host.tests;
     c->lastPairs = filter ? (long long)host.hits : host.pairs;
     c->lastNewPairs = filter ? host.pairs : 0;

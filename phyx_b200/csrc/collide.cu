@@ -442,8 +442,7 @@ int collide_pack_manifolds(phyx_b200_ctx* c)
         c->manColour.as<int>(), c->contactPoints.as<float4>());
     c->launches += 2;
     int K = 0;
-    PHYX_CUDA(cudaMemcpyAsync(&K, total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    PHYX_TRY(fetch_small(c, total, sizeof(int), &K));
     const bool removed = K != M;
     c->manifoldCount = K;
     c->contactPointCount = 2 * K;
@@ -542,8 +541,7 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         k_point_new_flags<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(P, c->manCount.as<int>(), c->contactPoints.as<float4>(), isNew);
         c->launches++;
         PHYX_TRY(exclusive_scan_i32(c, isNew, newRank, P, total));
-        PHYX_CUDA(cudaMemcpyAsync(&fresh, total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+        PHYX_TRY(fetch_small(c, total, sizeof(int), &fresh));
         PHYX_TRY(c->joints.reserve_keep(size_t(J0 + fresh > 0 ? J0 + fresh : 1) * sizeof(phyx_contact_joint), size_t(J0) * sizeof(phyx_contact_joint), c->stream));
         k_joint_match<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(P, J0, c->manBody.as<int2>(), c->manCount.as<int>(),
             c->contactPoints.as<float4>(), isNew, newRank, c->joints.as<phyx_contact_joint>());
@@ -566,8 +564,7 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         k_joint_fill<<<grid, kBlock, 0, c->stream>>>(J1, alive, prefix, total, movers, c->joints.as<phyx_contact_joint>());
         k_joint_backlink<<<grid, kBlock, 0, c->stream>>>(total, c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>());
         c->launches += 4;
-        PHYX_CUDA(cudaMemcpyAsync(&K, total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+        PHYX_TRY(fetch_small(c, total, sizeof(int), &K));
     }
     PHYX_CUDA(cudaGetLastError());
     c->jointCount = K;

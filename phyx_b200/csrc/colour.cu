@@ -822,12 +822,11 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
     int S = c->forceKernelForm == 1 || c->forceKernelForm == 2 ? 0 : strip_choose(c, M, nb);
     if (S > 0)
     {
-        int res[4];
-        PHYX_CUDA(cudaMemcpyAsync(res, result, 16, cudaMemcpyDeviceToHost, c->stream));
+        int res[4] = { 0, 0, 0, 0 };
         bool usable = false;
         for (;;)
         {
-            PHYX_TRY(strip_layout(c, S, jb, work, &usable));   // synchronises the stream
+            PHYX_TRY(strip_layout(c, S, jb, work, result, res, &usable));   // waits for the layout header and the colouring's result words
             // strips narrower than the bodies' reach (a manifold across non-adjacent strips, a row in two cut sets): try
             // half as many, and remember what worked for the next steps of this world (one strip always works, if it fits)
             if (usable || c->strip.want > 0 || S == 1 || !(c->strip.rejected & 3)) break;

@@ -198,6 +198,11 @@ struct phyx_b200_ctx
     std::vector<phyx_contact_joint> hostJoints; // host copy of the resident joints (host-built schedules need it)
     bool hostJointsValid = false;
 
+    // small results come back through page-locked, device-mapped host memory (a tiny kernel copies them and raises a sequence
+    // flag, the host spins on the flag): a fraction of the latency of cudaMemcpyAsync to pageable memory + cudaStreamSynchronize
+    int* mailboxHost = nullptr;
+    int* mailboxDev = nullptr;
+    unsigned mailboxSeq = 0;
     cudaEvent_t ev[8] = {};
     cudaEvent_t evBp[4] = {};    // broadphase timing: sort start / end (update_broadphase), sweep start / end (update_pairs)
     bool sortTimed = false;
@@ -249,7 +254,8 @@ int islands_unpack(phyx_b200_ctx* c, const int32_t* deviceBuffer);
 
 // strips.cu
 int strip_choose(const phyx_b200_ctx* c, int manifolds, int bodies);
-int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool* usable);
+// colourResult (device, 4 ints, may be null) is read back together with the layout header into colourResultHost
+int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const int* colourResult, int* colourResultHost, bool* usable);
 int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, float4* rowsVel, float4* rowsDisp);
 int strip_host_levels(phyx_b200_ctx* c, std::vector<int>* classStart);
 void strip_release(phyx_b200_ctx* c);
@@ -277,6 +283,15 @@ int collide_pack_manifolds(phyx_b200_ctx* c);
 int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* deleted);
 int collide_reset(phyx_b200_ctx* c);
 int collide_rebuild_pair_table(phyx_b200_ctx* c);
+
+// api.cu: small device -> host read-backs (see phyx_b200_ctx::mailboxHost).  stage() enqueues a copy of `bytes` (a multiple of 4, the
+// sum of all staged pieces <= 3.5 KB) to byte offset `offset` of the mailbox; wait() raises the flag and spins until it arrives;
+// at(offset) is the host view of what was staged.
+int mailbox_stage(phyx_b200_ctx* c, const void* dev, size_t bytes, size_t offset);
+int mailbox_wait(phyx_b200_ctx* c);
+inline const void* mailbox_at(const phyx_b200_ctx* c, size_t offset) { return reinterpret_cast<const char*>(c->mailboxHost) + offset; }
+// stage + wait + copy out
+int fetch_small(phyx_b200_ctx* c, const void* dev, size_t bytes, void* out);
 
 // scan.cu
 int exclusive_scan_i32(phyx_b200_ctx* c, const int* in, int* out, int n, int* totalDevice /* may be null */);

@@ -260,8 +260,7 @@ int islands_build(phyx_b200_ctx* c, int ranks, int* islandCount, int* islandMaxS
         }
         k_island_body_owner<<<gridB, kBlock, 0, c->stream>>>(nb, islandOf, group, groupOwner, result, bodyGroup, ranks > 1 ? c->bodyOwner.as<unsigned char>() : nullptr);
         c->launches += 5;
-        PHYX_CUDA(cudaMemcpyAsync(host, result, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
-        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+        PHYX_TRY(fetch_small(c, result, sizeof(host), host));
         if (!(keep && host[4])) break;
         keep = false;   // a body changed between static and dynamic: the old forest is void
     }

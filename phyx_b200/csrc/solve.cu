@@ -1182,8 +1182,8 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         c->launches += 2;
         PHYX_CUDA(cudaEventRecord(e3, c->stream));
         int host[8];   // result[0..2], pad, activeTotal[2] as two 64-bit words
-        PHYX_CUDA(cudaMemcpyAsync(host, P.result, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
-        PHYX_CUDA(cudaStreamSynchronize(c->stream));
+        PHYX_TRY(fetch_small(c, P.result, sizeof(host), host));
+        PHYX_CUDA(cudaEventSynchronize(e3));   // (complete by now: the read-back was enqueued behind it)
         ranI = host[0];
         ranD = host[1];
         wakePasses = host[2];

@@ -635,7 +635,7 @@ constexpr int kStripRowLimit = 10240;                   // rows per strip (160 K
 
 // Class-major layout of the coloured manifolds over S strips; `work` holds the colours.  On success with *usable the
 // context's schedule (slotJoint, pairIdx, bin table) is the strip layout; otherwise the caller lays out colour-major.
-int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool* usable)
+int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const int* colourResult, int* colourResultHost, bool* usable)
 {
     StripPlan& sp = c->strip;
     const int M = c->manifoldCount, nb = c->bodyCount;
@@ -765,8 +765,11 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, bool*
     PHYX_CUDA(cudaGetLastError());
 
     int host[16];
-    PHYX_CUDA(cudaMemcpyAsync(host, header, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
-    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    PHYX_TRY(mailbox_stage(c, header, sizeof(host), 0));
+    if (colourResult) PHYX_TRY(mailbox_stage(c, colourResult, 16, 64));
+    PHYX_TRY(mailbox_wait(c));
+    memcpy(host, mailbox_at(c, 0), sizeof(host));
+    if (colourResultHost) memcpy(colourResultHost, mailbox_at(c, 64), 16);
 
     sp.strips = S;
     sp.maxStripRows = host[H_MAXROWS];
