@@ -51,6 +51,8 @@ namespace phyx
 constexpr int kBlock = 256;
 constexpr int kStripU = 8;         // candidates per thread whose index words are prefetched one bin ahead
 constexpr int kStripBins = kMaxColours;   // bins (colours) per class
+constexpr int kStripMax = 1023;           // strips per layout (the class digit of the layout sort has 2048 bins)
+constexpr int kStripRowLimit = 10240;     // rows per strip (160 KB of the SM's 228 KB: the record fetches of step 2 want the rest as L1)
 
 // layout header (device ints)
 enum
@@ -618,10 +620,12 @@ __global__ void __launch_bounds__(kBlock) k_strip_maxbin(int bins, const int2* _
 int strip_choose(const phyx_b200_ctx* c, int manifolds, int bodies)
 {
     if (c->strip.want < 0) return 0;
-    if (c->strip.want > 0) return std::min(c->strip.want, 2 * c->numSMs);   // more than one strip per SM: 256-thread CTAs, two per SM
-    (void)bodies;
+    if (c->strip.want > 0) return std::min(c->strip.want, kStripMax);
     int S = std::max(1, std::min(c->numSMs, manifolds / 1024));
     if (c->strip.autoLimit > 0) S = std::min(S, c->strip.autoLimit);   // what the last rejected layouts of this world allowed
+    // a strip's rows must fit in shared memory: large worlds get more strips than SMs (several strips per CTA)
+    const int needed = (bodies + kStripRowLimit * 3 / 4 - 1) / (kStripRowLimit * 3 / 4);
+    if (needed > S) S = std::min(needed, kStripMax);
     return S;
 }
 
@@ -630,8 +634,6 @@ static size_t strip_smem_bytes(int rowCap, int cutCap, int workCap)
     return size_t(rowCap) * 16 + size_t(cutCap) * 16 + size_t(workCap) * 2 + size_t(cutCap) * (2 + 2 + 4);
 }
 constexpr size_t kStripSmemLimit = 227 * 1024 - 4096;   // dynamic part: the opt-in maximum minus the kernel's static tables
-constexpr size_t kStripSmemLimit2 = 113 * 1024 - 4096;  // two CTAs per SM
-constexpr int kStripRowLimit = 10240;                   // rows per strip (160 KB of the SM's 228 KB: the record fetches of step 2 want the rest as L1)
 
 // Class-major layout of the coloured manifolds over S strips; `work` holds the colours.  On success with *usable the
 // context's schedule (slotJoint, pairIdx, bin table) is the strip layout; otherwise the caller lays out colour-major.
@@ -700,7 +702,7 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
         PHYX_TRY(exclusive_scan_i32(c, cover, cover, nb, nullptr));
         // width limit first, clean cuts last: a snapped cut is never moved again (a strip that ends up too wide for shared
         // memory rejects the layout for this step)
-        k_strip_monotonic<<<1, 32, 0, c->stream>>>(S, S > c->numSMs ? kStripRowLimit / 2 : kStripRowLimit, sp.cuts.as<int>());
+        k_strip_monotonic<<<1, 32, 0, c->stream>>>(S, kStripRowLimit, sp.cuts.as<int>());
         k_strip_snap<<<S - 1, kBlock, 0, c->stream>>>(nb, S, std::max(1, nb / S / 2), cover, sp.cuts.as<int>());
         k_strip_monotonic<<<1, 32, 0, c->stream>>>(S, nb, sp.cuts.as<int>());
         c->launches += 3;
@@ -780,7 +782,7 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     sp.cutManifolds = host[H_CUTM];
     int rejected = host[H_REJECT];
     if (sp.manifolds == 0) rejected |= kRejectEmpty;
-    if (strip_smem_bytes(sp.maxStripRows + 9, sp.maxCutRows + 9, sp.maxBin + 9) > (S > c->numSMs ? kStripSmemLimit2 : kStripSmemLimit)) rejected |= kRejectSmem;
+    if (strip_smem_bytes(sp.maxStripRows + 9, sp.maxCutRows + 9, sp.maxBin + 9) > kStripSmemLimit) rejected |= kRejectSmem;
     if (sp.maxStripRows > 65000 || sp.maxCutRows > 65000 || sp.maxBin > 65000) rejected |= kRejectSmem;
     sp.rejected = rejected;
     if (rejected) return PHYX_B200_OK;
@@ -1245,9 +1247,114 @@ __device__ __forceinline__ bool run_pass(const StripParams& P, StripCta& s, int 
     return any;
 }
 
+// per-strip tables into shared memory: sizes, the bin lists of its two classes (empty bins dropped), its boundary row lists
+template <int T>
+__device__ __forceinline__ void setup_strip(const StripParams& P, StripCta& s, int k, int2* s_tmp, int* s_n)
+{
+    const int S = P.S;
+    s.k = k;
+    s.row0 = P.cuts[k];
+    s.nRows = P.cuts[k + 1] - s.row0;
+    const int* bRs = P.bStart;
+    const int* bLs = P.bStart + S + 1;
+    s.nR = bRs[k + 1] - bRs[k];
+    s.nL = bLs[k + 1] - bLs[k];
+    s.nLn = k + 1 < S ? bLs[k + 2] - bLs[k + 1] : 0;
+    __syncthreads();   // (whoever still reads the previous strip's tables is done)
+    if (threadIdx.x < 2 * kStripBins)
+    {
+        const int cls = threadIdx.x < kStripBins ? k : S + k;
+        const int c = threadIdx.x & (kStripBins - 1);
+        s_tmp[threadIdx.x] = P.binRange[cls * kStripBins + c];   // the table has 2S classes; class 2S-1 is always empty
+    }
+    for (int i = threadIdx.x; i < s.nL; i += T) s.s_listL[i] = (unsigned short)(P.bL[bLs[k] + i] - s.row0);
+    for (int i = threadIdx.x; i < s.nR; i += T) s.s_listR[i] = (unsigned short)(P.bR[bRs[k] + i] - s.row0);
+    for (int i = threadIdx.x; i < s.nLn; i += T) s.s_listN[i] = P.bL[bLs[k + 1] + i];
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        int n = 0;
+        for (int c = 0; c < kStripBins; ++c)
+            if (s_tmp[c].y > s_tmp[c].x) s.s_bins[n++] = s_tmp[c];
+        s_n[0] = n;
+        if (k + 1 < S)
+            for (int c = 0; c < kStripBins; ++c)
+                if (s_tmp[kStripBins + c].y > s_tmp[kStripBins + c].x) s.s_bins[n++] = s_tmp[kStripBins + c];
+        s_n[1] = n - s_n[0];
+    }
+    __syncthreads();
+    s.nInt = s_n[0];
+    s.nCut = s_n[1];
+}
+
+// One pass when there are MORE STRIPS THAN CTAs (worlds whose strips would not fit in shared memory otherwise: above ~1.5 M
+// bodies per device).  CTA c owns the strips c, c + G, c + 2G, ...; a strip's rows are staged into shared memory for each
+// visit and live in global memory in between.  Phase I: every owned strip's interior bins (its whole row range is written
+// back, which also publishes the left-boundary rows; flagA).  Phase C: every owned cut set (flagB).  A strip's interior
+// visit of pass p waits for the cut set on its left of pass p-1.  No wait can cycle: phase I of a pass waits only for
+// phase C of the previous pass, phase C only for phase I of the same pass.
+template <int MODE, int T>
+__device__ __forceinline__ bool run_pass_streaming(const StripParams& P, StripCta& s, int it, unsigned long long seq, int passIndex, unsigned (&pre)[kStripU], int2& preIdx,
+    int2* s_tmp, int* s_n)
+{
+    constexpr int PHASE = MODE == 1 ? 1 : 0;
+    float4* rowsG = P.rows[PHASE];
+    const int2 none = make_int2(0, 0);
+    bool any = false;
+    for (int k = blockIdx.x; k < P.S; k += gridDim.x)
+    {
+        setup_strip<T>(P, s, k, s_tmp, s_n);
+        // the cut set on my left of the previous pass has written my left-boundary rows (not across a phase change: the
+        // displacement rows are untouched until the first displacement pass)
+        if (k > 0 && s.nL > 0 && seq > 1 && !(MODE == 1 && it == 0)) cta_wait_flag(&P.flagB[k - 1], seq - 1);
+        const long long w0 = clock64();
+        for (int i = threadIdx.x; i < s.nRows; i += T) s.s_rows[i] = __ldcg(&rowsG[s.row0 + i]);
+        if (MODE >= 0 && s.nInt > 0) prefetch_idx<T>(P, s.s_bins[0], pre, preIdx);
+        __syncthreads();
+        for (int b = 0; b < s.nInt; ++b)
+        {
+            if (MODE < 0)
+                prestep_bin<T>(P, s.s_rows, rowsG, s.s_bins[b]);
+            else
+                any |= solve_bin<PHASE, T>(P, s, s.s_rows, P.rowCap - 1, rowsG, s.s_bins[b], b + 1 < s.nInt ? s.s_bins[b + 1] : none, it, pre, preIdx);
+        }
+        for (int i = threadIdx.x; i < s.nRows; i += T) __stcg(&rowsG[s.row0 + i], s.s_rows[i]);
+        if (threadIdx.x == 0) P.cost[k] += clock64() - w0;
+        __syncthreads();
+        if (threadIdx.x == 0 && k > 0 && s.nL > 0) flag_release(&P.flagA[k], seq);
+    }
+    for (int k = blockIdx.x; k + 1 < P.S; k += gridDim.x)
+    {
+        setup_strip<T>(P, s, k, s_tmp, s_n);
+        if (s.nCut == 0) continue;
+        cta_wait_flag(&P.flagA[k + 1], seq);
+        const long long w1 = clock64();
+        const int nBins = s.nInt + s.nCut;
+        for (int i = threadIdx.x; i < s.nR; i += T) s.s_cut[i] = __ldcg(&rowsG[s.row0 + s.s_listR[i]]);
+        for (int i = threadIdx.x; i < s.nLn; i += T) s.s_cut[s.nR + i] = __ldcg(&rowsG[s.s_listN[i]]);
+        if (MODE >= 0) prefetch_idx<T>(P, s.s_bins[s.nInt], pre, preIdx);
+        __syncthreads();
+        for (int b = s.nInt; b < nBins; ++b)
+        {
+            if (MODE < 0)
+                prestep_bin<T>(P, s.s_cut, rowsG, s.s_bins[b]);
+            else
+                any |= solve_bin<PHASE, T>(P, s, s.s_cut, P.cutCap - 1, rowsG, s.s_bins[b], b + 1 < nBins ? s.s_bins[b + 1] : none, it, pre, preIdx);
+        }
+        for (int i = threadIdx.x; i < s.nR; i += T) __stcg(&rowsG[s.row0 + s.s_listR[i]], s.s_cut[i]);
+        for (int i = threadIdx.x; i < s.nLn; i += T) __stcg(&rowsG[s.s_listN[i]], s.s_cut[s.nR + i]);
+        if (threadIdx.x == 0) P.cost[k] += clock64() - w1;
+        __syncthreads();
+        if (threadIdx.x == 0) flag_release(&P.flagB[k], seq);
+    }
+    (void)passIndex;
+    return any;
+}
+
 // all iterations of one phase; returns the number of passes executed (>= the reference's count: see the header)
-template <int PHASE, int T>
-__device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int iters, unsigned long long& seq, int& passIndex, unsigned (&pre)[kStripU], int2& preIdx)
+template <int PHASE, int T, bool STREAM>
+__device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int iters, unsigned long long& seq, int& passIndex, unsigned (&pre)[kStripU], int2& preIdx,
+    int2* s_tmp, int* s_n)
 {
     __shared__ unsigned long long s_word;
     unsigned long long* done = P.done + size_t(PHASE) * P.doneStride;
@@ -1260,7 +1367,7 @@ __device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int 
             if (threadIdx.x == 0)
             {
                 unsigned long long v;
-                while (((v = flag_peek(&done[it - 2])) & 0xffffffffull) != unsigned(P.S)) {}
+                while (((v = flag_peek(&done[it - 2])) & 0xffffffffull) != gridDim.x) {}
                 s_word = v;
             }
             __syncthreads();
@@ -1270,7 +1377,8 @@ __device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int 
         }
         ++seq;
         ++passIndex;
-        const bool mine = run_pass<PHASE, T>(P, s, it, seq, passIndex, pre, preIdx);
+        const bool mine = STREAM ? run_pass_streaming<PHASE, T>(P, s, it, seq, passIndex, pre, preIdx, s_tmp, s_n)
+                                 : run_pass<PHASE, T>(P, s, it, seq, passIndex, pre, preIdx);
         const int any = __syncthreads_or(mine ? 1 : 0);
         if (threadIdx.x == 0) atomicAdd(&done[it], 1ull | (any ? (1ull << 32) : 0ull));
     }
@@ -1278,7 +1386,7 @@ __device__ __forceinline__ int run_phase(const StripParams& P, StripCta& s, int 
 }
 
 template <int T>
-__global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
+__global__ void __launch_bounds__(T, 1) k_solve_strips(StripParams P)
 {
     extern __shared__ __align__(128) unsigned char stripSmem[];
     __shared__ int2 s_bins[2 * kStripBins];
@@ -1296,106 +1404,83 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
     s.s_work = s.s_listR + P.cutCap;
     s.s_bins = s_bins;
     s.s_count = s_count;
-    const int k = blockIdx.x, S = P.S;
-    s.k = k;
-    s.row0 = P.cuts[k];
-    s.nRows = P.cuts[k + 1] - s.row0;
-    const int* bRs = P.bStart;
-    const int* bLs = P.bStart + S + 1;
-    s.nR = bRs[k + 1] - bRs[k];
-    s.nL = bLs[k + 1] - bLs[k];
-    s.nLn = k + 1 < S ? bLs[k + 2] - bLs[k + 1] : 0;
+    const int S = P.S;
+    const bool streaming = S > int(gridDim.x);   // more strips than CTAs: rows are staged per visit (run_pass_streaming)
     s.parity = 0;
     if (threadIdx.x == 0)   // the rows that test words of static bodies and of empty slots point at: lastIteration = never
     {
         s.s_rows[P.rowCap - 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-(1 << 30)));
         s.s_cut[P.cutCap - 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-(1 << 30)));
-    }
-    s.active[0] = s.active[1] = 0u;
-    s.busy = 0;
-
-    // the strip's rows: one bulk copy
-    if (threadIdx.x == 0)
-    {
         mbar_init(&s_mbar, 1);
         mbar_fence_init();
         s_count[0] = s_count[1] = 0;
     }
+    s.active[0] = s.active[1] = 0u;
+    s.busy = 0;
     __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        const unsigned bytes = unsigned(s.nRows) * 16u;
-        mbar_expect_tx(&s_mbar, bytes);
-        if (bytes) bulk_g2s(s.s_rows, P.rows[0] + s.row0, bytes, &s_mbar);
-    }
-    // bin tables of the strip's two classes, empty bins dropped
-    if (threadIdx.x < 2 * kStripBins)
-    {
-        const int cls = threadIdx.x < kStripBins ? k : S + k;
-        const int c = threadIdx.x & (kStripBins - 1);
-        s_tmp[threadIdx.x] = P.binRange[cls * kStripBins + c];   // the table has 2S classes; class 2S-1 is always empty
-    }
-    for (int i = threadIdx.x; i < s.nL; i += T) s.s_listL[i] = (unsigned short)(P.bL[bLs[k] + i] - s.row0);
-    for (int i = threadIdx.x; i < s.nR; i += T) s.s_listR[i] = (unsigned short)(P.bR[bRs[k] + i] - s.row0);
-    for (int i = threadIdx.x; i < s.nLn; i += T) s.s_listN[i] = P.bL[bLs[k + 1] + i];
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        int n = 0;
-        for (int c = 0; c < kStripBins; ++c)
-            if (s_tmp[c].y > s_tmp[c].x) s_bins[n++] = s_tmp[c];
-        s_n[0] = n;
-        if (k + 1 < S)
-            for (int c = 0; c < kStripBins; ++c)
-                if (s_tmp[kStripBins + c].y > s_tmp[kStripBins + c].x) s_bins[n++] = s_tmp[kStripBins + c];
-        s_n[1] = n - s_n[0];
-    }
-    __syncthreads();
-    s.nInt = s_n[0];
-    s.nCut = s_n[1];
-    mbar_wait(&s_mbar, 0);
 
     unsigned long long seq = 0;
     int passIndex = 0;
     unsigned pre[kStripU];
 #pragma unroll
     for (int u = 0; u < kStripU; ++u) pre[u] = 0xffffffffu;
-
-    // warm start
-    ++seq;
     int2 preIdx = make_int2(-1, -1);
-    run_pass<-1, T>(P, s, 0, seq, passIndex, pre, preIdx);
-    if (s.nInt + s.nCut > 0) prefetch_idx<T>(P, s_bins[0], pre, preIdx);
+    int ranI = 0, ranD = 0;
 
-    const int ranI = run_phase<0, T>(P, s, P.contactIters, seq, passIndex, pre, preIdx);
-
-    // velocity rows back, displacement rows in
-    __syncthreads();
-    if (threadIdx.x == 0 && s.nRows > 0)
+    if (!streaming)
     {
-        bulk_s2g_fence();
-        bulk_s2g(P.rows[0] + s.row0, s.s_rows, unsigned(s.nRows) * 16u);
-        bulk_commit_wait_all();
-    }
-    int ranD = 0;
-    if (P.penetrationIters > 0)
-    {
-        __syncthreads();
+        const int k = blockIdx.x;
+        setup_strip<T>(P, s, k, s_tmp, s_n);
+        // the strip's rows: one bulk copy; they stay in shared memory for the whole phase
         if (threadIdx.x == 0)
         {
             const unsigned bytes = unsigned(s.nRows) * 16u;
             mbar_expect_tx(&s_mbar, bytes);
-            if (bytes) bulk_g2s(s.s_rows, P.rows[1] + s.row0, bytes, &s_mbar);
+            if (bytes) bulk_g2s(s.s_rows, P.rows[0] + s.row0, bytes, &s_mbar);
         }
-        mbar_wait(&s_mbar, 1);
-        ranD = run_phase<1, T>(P, s, P.penetrationIters, seq, passIndex, pre, preIdx);
+        mbar_wait(&s_mbar, 0);
+
+        // warm start
+        ++seq;
+        run_pass<-1, T>(P, s, 0, seq, passIndex, pre, preIdx);
+        if (s.nInt + s.nCut > 0) prefetch_idx<T>(P, s_bins[0], pre, preIdx);
+        ranI = run_phase<0, T, false>(P, s, P.contactIters, seq, passIndex, pre, preIdx, s_tmp, s_n);
+
+        // velocity rows back, displacement rows in
         __syncthreads();
         if (threadIdx.x == 0 && s.nRows > 0)
         {
             bulk_s2g_fence();
-            bulk_s2g(P.rows[1] + s.row0, s.s_rows, unsigned(s.nRows) * 16u);
+            bulk_s2g(P.rows[0] + s.row0, s.s_rows, unsigned(s.nRows) * 16u);
             bulk_commit_wait_all();
         }
+        if (P.penetrationIters > 0)
+        {
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                const unsigned bytes = unsigned(s.nRows) * 16u;
+                mbar_expect_tx(&s_mbar, bytes);
+                if (bytes) bulk_g2s(s.s_rows, P.rows[1] + s.row0, bytes, &s_mbar);
+            }
+            mbar_wait(&s_mbar, 1);
+            ranD = run_phase<1, T, false>(P, s, P.penetrationIters, seq, passIndex, pre, preIdx, s_tmp, s_n);
+            __syncthreads();
+            if (threadIdx.x == 0 && s.nRows > 0)
+            {
+                bulk_s2g_fence();
+                bulk_s2g(P.rows[1] + s.row0, s.s_rows, unsigned(s.nRows) * 16u);
+                bulk_commit_wait_all();
+            }
+        }
+        if (threadIdx.x == 0) P.cost[k] = s.busy;
+    }
+    else
+    {
+        ++seq;
+        run_pass_streaming<-1, T>(P, s, 0, seq, passIndex, pre, preIdx, s_tmp, s_n);
+        ranI = run_phase<0, T, true>(P, s, P.contactIters, seq, passIndex, pre, preIdx, s_tmp, s_n);
+        if (P.penetrationIters > 0) ranD = run_phase<1, T, true>(P, s, P.penetrationIters, seq, passIndex, pre, preIdx, s_tmp, s_n);
     }
 
     for (int phase = 0; phase < 2; ++phase)
@@ -1404,9 +1489,8 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.activeTotal[phase], static_cast<unsigned long long>(v));
     }
-    if (threadIdx.x == 0) P.cost[k] = s.busy;
     // iteration counts as the reference loop reports them: up to and including the first non-productive iteration
-    if (k == 0 && threadIdx.x == 0)
+    if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         const int executed[2] = { ranI, ranD };
         for (int phase = 0; phase < 2; ++phase)
@@ -1416,7 +1500,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_solve_strips(StripParams P)
             for (int it = 0; it < executed[phase]; ++it)
             {
                 unsigned long long v;
-                while (((v = flag_peek(&done[it])) & 0xffffffffull) != unsigned(S)) {}
+                while (((v = flag_peek(&done[it])) & 0xffffffffull) != gridDim.x) {}
                 if ((v >> 32) == 0)
                 {
                     ran = it + 1;
@@ -1478,15 +1562,13 @@ int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, floa
     if (!sp.attributeSet)   // per device
     {
         PHYX_CUDA(cudaFuncSetAttribute(k_solve_strips<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStripSmemLimit)));
-        PHYX_CUDA(cudaFuncSetAttribute(k_solve_strips<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStripSmemLimit2)));
         sp.attributeSet = true;
     }
     // every CTA waits for its neighbours: all S must be resident at once, which the cooperative launch guarantees (or refuses)
     void* args[] = { &P };
-    if (S > c->numSMs)
-        PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_strips<256>, dim3(S), dim3(256), args, smem, c->stream));
-    else
-        PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_strips<512>, dim3(S), dim3(512), args, smem, c->stream));
+    // one CTA per strip; a world with more strips than SMs is run by numSMs CTAs, each visiting several strips per pass
+    if (S > c->numSMs) PHYX_CUDA(cudaMemsetAsync(sp.cost.ptr, 0, size_t(S) * sizeof(long long), c->stream));   // (accumulated per visit there)
+    PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_strips<512>, dim3(std::min(S, c->numSMs)), dim3(512), args, smem, c->stream));
     c->launches++;
     return PHYX_B200_OK;
 }

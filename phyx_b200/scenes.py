@@ -58,6 +58,20 @@ def stack(columns, height, pitch=30.0, ground_half_width=1e7):
     return body
 
 
+def brick_wall(width, height, pitch=21.0, ground_half_width=1e7):
+    """A low, wide wall in running bond: `height` rows of `width` boxes, odd rows shifted by half a brick.  One island that
+    is thousands of columns wide and a few rows high: many strips, every strip boundary cuts manifolds."""
+    r = np.repeat(np.arange(height), width)
+    i = np.tile(np.arange(width), height)
+    body = np.zeros((width * height + 1, 6), dtype=np.float32)
+    body[0] = (0.0, 0.0, 0.0, ground_half_width, 10.0, 1.0)
+    body[1:, 0] = (i - width / 2) * pitch + (r % 2) * (pitch / 2)
+    body[1:, 1] = 15.0 + 10.0 * r
+    body[1:, 3] = BOX[0]
+    body[1:, 4] = BOX[1]
+    return body
+
+
 def multi_island(count, rows, pitch=21.0, ground_half_width=1e7):
     """`count` separate pyramids of `rows` rows side by side (independent islands: the ground is
     static and does not merge islands, reference src/Solver.cpp:304,316-317)."""
@@ -144,6 +158,7 @@ SCENES = {
     "platforms_400": lambda: platforms(400),
     "tumble_300": lambda: tumble(300),
     "tumble_3k": lambda: tumble(3000),
+    "wall_18k": lambda: brick_wall(3000, 6),
 }
 
 

@@ -57,6 +57,9 @@ def run_and_check(ctx, oracle, steps, check_at, form, iters=(20, 20), what=""):
     ("pyramid_10k", 0, 8, (0, 7)),
     ("pyramid_10k", 12, 6, (5,)),
     ("stack_10k", 0, 8, (7,)),
+    ("wall_18k", 60, 8, (0, 7)),       # one wide island: every strip boundary cuts manifolds
+    ("wall_18k", 200, 8, (0, 7)),      # more strips than SMs: several strips per CTA, rows staged per visit
+    ("stack_10k", 333, 6, (5,)),       # the same without cut sets
 ])
 def test_strip_solve_equals_oracle_on_its_slot_order(oracle, scene, strips, steps, check_at):
     w = world.World(scenes.make(scene))
