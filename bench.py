@@ -457,7 +457,7 @@ def run_island_parallel(args, rank, world_size, local_rank):
     spanning = None
     if args.spanning:
         try:
-            spanning = partition.run_spanning("pyramid_1m", args.settle, max(3, min(args.steps, 10)), local_rank, iters=ITERS)
+            spanning = partition.run_spanning("pyramid_1m", args.settle, max(3, min(args.steps, 10)), local_rank, iters=ITERS, check=True)
         except Exception as e:  # noqa: BLE001
             spanning = {"error": str(e)}
     dist.barrier()
