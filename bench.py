@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--scene", default=None, help="default: pyramid_1m on one GPU (BASELINE configs[2]); islands_1m on several (configs[3])")
     ap.add_argument("--settle", type=int, default=30, help="untimed World::Update steps that build the contact state")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-calls", action="store_true",
+                    help="time the eight stage functions of the C ABI instead of phyx_b200_world_step (same results, one read-back per stage)")
     ap.add_argument("--no-parity", dest="parity", action="store_false",
                     help="skip the parity_mode section (replay mode timed on the workload; colour-mode deviation from the reference after 100 steps at 100 k bodies)")
     ap.set_defaults(parity=True)
@@ -555,7 +557,18 @@ def run_ours(args, rank, world_size, local_rank):
         stage_max[name] = max(stage_max.get(name, 0.0), ms)
         return r
 
+    step_infos = []
+
     def resident_step():
+        # World::Update as ONE C-ABI call (phyx_b200_world_step): the eight stages with the counts kept on the device, one
+        # read-back per step.  --stage-calls times the eight stage functions instead (same results, a read-back per stage).
+        if not args.stage_calls:
+            st, bp, info = timed("WorldStep", ctx.world_step, scenes.DT, scenes.GRAVITY, iters=ITERS, schedule=capi.SCHEDULE_COLOUR)
+            step_infos.append((info.deferred, info.stopStage, info.stopReason))
+            return bp, st
+        return stage_calls_step()
+
+    def stage_calls_step():
         timed("IntegrateVelocity", ctx.integrate_velocity, scenes.DT, scenes.GRAVITY)
         timed("UpdateBroadphase", ctx.update_broadphase)
         bp = timed("UpdatePairs", ctx.update_pairs)
@@ -575,6 +588,7 @@ def run_ours(args, rank, world_size, local_rank):
     stats = []
     stage_wall.clear()
     stage_max.clear()
+    step_infos.clear()
     allocs0 = ctx.alloc_stats()
     with clocks:
         e0.record(stream)
@@ -591,6 +605,28 @@ def run_ours(args, rank, world_size, local_rank):
     value = world_size * joint_iters / (ms_total * 1e-3)
     nj = stats[-1][1].joints
     manifolds = ctx.collider_counts()[0]
+    # the same steps through the eight stage functions (a read-back per stage), for the per-stage host wall times
+    step_wall = dict(stage_wall)
+    step_infos_timed = list(step_infos)
+    stage_wall.clear()
+    stage_max.clear()
+    stage_steps = 0
+    stage_calls_ms = None
+    if not args.stage_calls:
+        stage_steps = max(3, min(args.steps, 10))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage_calls_step()
+        stage_wall.clear()
+        stage_max.clear()
+        torch.cuda.synchronize(local_rank)
+        s0.record(stream)
+        for _ in range(stage_steps):
+            stage_calls_step()
+        s1.record(stream)
+        torch.cuda.synchronize(local_rank)
+        stage_calls_ms = s0.elapsed_time(s1) / stage_steps
+    else:
+        stage_steps = args.steps
 
     # ---- e2e: World::Update through the host mirror, World::bodies uploaded and read back every step
     e2e_steps = max(3, min(args.steps, 10))
@@ -715,7 +751,15 @@ def run_ours(args, rank, world_size, local_rank):
                               "iterations_kernel": k_ms, "colour_rounds": int(stats[-1][1].colourRounds), "colours": int(stats[-1][1].levels)},
         "solve_only_constraint_iterations_per_sec": world_size * jm * sum(ITERS) / (solve_ms * 1e-3),
         "spanning": spanning,
-        "resident_stage_wall_ms": {k: round(v / args.steps, 3) for k, v in stage_wall.items()},
+        "step_call": {
+            "api": "eight stage functions" if args.stage_calls else "phyx_b200_world_step",
+            "deferred_steps": sum(1 for d, _, _ in step_infos_timed if d),
+            "stopped_steps": [[stg, why] for d, stg, why in step_infos_timed if stg],
+            "host_wall_ms_per_step": round(step_wall.get("WorldStep", 0.0) / args.steps, 3) if not args.stage_calls else None,
+            "stage_calls_ms_per_step": stage_calls_ms,
+            "note": "deferred = counts on the device, one read-back per step; a stopped step is finished by the stage functions (reasons: include/phyx_b200.h)",
+        },
+        "resident_stage_wall_ms": {k: round(v / max(stage_steps, 1), 3) for k, v in stage_wall.items()},
         "resident_stage_wall_ms_max": {k: round(v, 3) for k, v in stage_max.items()},
         "device_allocations_in_timed_region": {"count": allocs1[0] - allocs0[0], "host_ms": round(allocs1[1] - allocs0[1], 3)},
         "steps_per_sec": world_size * 1e3 / ms_step,

@@ -195,6 +195,13 @@ PHYX_B200_API int phyx_b200_get_schedule(phyx_b200_ctx* ctx, int32_t* slots, int
  * rejected).  strips: 0 = choose, -1 = never, n = cut the solver rows into n strips (<= number of SMs).  All forms
  * relax the same joints; 1 and 2 give identical results, 3 uses the slot order phyx_b200_get_schedule reports. */
 PHYX_B200_API int phyx_b200_solve_tuning(phyx_b200_ctx* ctx, int kernelForm, int strips);
+/* Balance feedback of the strip layout.  measured != 0 (default): the row cuts of a step are balanced with the SM clocks
+ * each strip's CTA spent in the previous solve, so on worlds whose strips share manifolds (one wide island) the slot order,
+ * and with it the last bits of the result, depend on timing: every run is a valid sweep (and is checked as such against
+ * the oracle), two runs are not bit-identical.  measured = 0: cuts follow the predicted work only; runs are reproducible
+ * bit for bit at a few percent of solve time.  (Reference counterpart: none; its multithreaded island modes are not
+ * reproducible either, SURVEY App. B.) */
+PHYX_B200_API int phyx_b200_strip_feedback(phyx_b200_ctx* ctx, int measured);
 /* The strip layout of the last solve: *strips = S (0: the last solve did not use strips), cuts[S+1] = row cuts,
  * classSlotStart[2S+1] = first slot of each class (class k < S: interior of strip k, class S+k: cut set between strips
  * k and k+1), info[8] = {usable, reject mask, rows of the largest strip, rows of the largest cut set, largest bin,
@@ -225,6 +232,34 @@ PHYX_B200_API int phyx_b200_pack_manifolds(phyx_b200_ctx* ctx);
 PHYX_B200_API int phyx_b200_refresh_contact_joints(phyx_b200_ctx* ctx, int32_t* matched, int32_t* created, int32_t* deleted);
 /* Solver::SolveJoints on the resident joint cache (same as solve_joints without the host arrays) */
 PHYX_B200_API int phyx_b200_solve_resident(phyx_b200_ctx* ctx, const phyx_b200_solve_config* config, phyx_b200_solve_stats* stats);
+/* ---- World::Update as ONE call: reference src/World.cpp:19-37 ------------------------------------------------------- */
+/* IntegrateVelocity, UpdateBroadphase, UpdatePairs, UpdateManifolds, PackManifolds, RefreshContactJoints, SolveJoints,
+ * IntegratePosition on the resident state, in that order, with the results of calling the eight stage functions above one
+ * after the other.  The difference is on the host side: the stage functions each return their counts, which costs a
+ * device read-back per stage; this call keeps the counts of the step in flight on the device (buffers and grids are sized
+ * by bounds predicted from the previous step) and reads everything back once, at the end.  A step whose counts outgrow the
+ * bounds, or in which the device takes a decision the stage path takes on the host (strip layout rejected, colouring
+ * rebuilt), stops on the device before the stage in question has changed anything and is finished by the stage functions
+ * (info->stopStage / stopReason say why).  The first steps of a world, replay schedules, forced kernel forms and
+ * partitioned worlds always take the stage path (info->deferred = 0). */
+typedef struct {
+    int32_t deferred;                    /* 1: the whole step ran with device-side counts and one read-back */
+    int32_t stopStage, stopReason;       /* deferred attempt stopped at stage (3 UpdatePairs, 6 RefreshContactJoints, 7 SolveJoints;
+                                            0 = not); reason: 1 sweep items, 2 new pairs, 3 new joints above their bound, 10 strip
+                                            layout rejected, 11 strip shape above the predicted one, 12 more than 64 colours,
+                                            13 a body changed between static and dynamic, 14 colouring drifted (rebuilt) */
+    int32_t manifolds, contactPoints, joints;   /* sizes of Collider::manifolds / contactPoints, Solver::contactJoints after the step */
+    int32_t newPairs, jointsCreated, jointsDeleted;
+    int32_t pad_;
+    int64_t pairs, tests;                /* overlapping pairs / sweep tests of this step's broadphase */
+    int64_t deferredSteps, deferredStops;       /* totals of this context */
+} phyx_b200_step_info;
+PHYX_B200_API int phyx_b200_world_step(phyx_b200_ctx* ctx, float dt, float gravity, const phyx_b200_solve_config* config,
+    phyx_b200_solve_stats* solveStats, phyx_b200_broadphase_stats* broadphaseStats, phyx_b200_step_info* info);
+/* deferred = 1 (default): world_step may run steps with device-side counts; 0: it always calls the stage functions;
+ * 2: as 1 with bounds that leave no headroom (test aid: every growing count exercises the stop-and-resume path) */
+PHYX_B200_API int phyx_b200_step_mode(phyx_b200_ctx* ctx, int deferred);
+
 /* resetWorld() clears manifolds, manifoldMap and contactJoints (reference src/main.cpp:86-89) */
 PHYX_B200_API int phyx_b200_reset_collider(phyx_b200_ctx* ctx);
 /* sizes of Collider::manifolds, Collider::contactPoints, Solver::contactJoints */

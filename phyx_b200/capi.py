@@ -53,6 +53,8 @@ EXPORTS = (
     "phyx_b200_pack_manifolds",
     "phyx_b200_refresh_contact_joints",
     "phyx_b200_solve_resident",
+    "phyx_b200_world_step",
+    "phyx_b200_step_mode",
     "phyx_b200_reset_collider",
     "phyx_b200_collider_counts",
     "phyx_b200_download_manifolds",
@@ -61,6 +63,7 @@ EXPORTS = (
     "phyx_b200_upload_collider",
     "phyx_b200_solve_tuning",
     "phyx_b200_strip_plan",
+    "phyx_b200_strip_feedback",
     "phyx_b200_strip_trace",
     "phyx_b200_build_islands",
     "phyx_b200_download_islands",
@@ -115,6 +118,28 @@ class BroadphaseStats(C.Structure):
     _fields_ = [("tests", C.c_int64), ("pairs", C.c_int64), ("ms_sort", C.c_float), ("ms_sweep", C.c_float), ("ms_total", C.c_float)]
 
 
+class StepInfo(C.Structure):
+    _fields_ = [
+        ("deferred", C.c_int32),
+        ("stopStage", C.c_int32),
+        ("stopReason", C.c_int32),
+        ("manifolds", C.c_int32),
+        ("contactPoints", C.c_int32),
+        ("joints", C.c_int32),
+        ("newPairs", C.c_int32),
+        ("jointsCreated", C.c_int32),
+        ("jointsDeleted", C.c_int32),
+        ("pad_", C.c_int32),
+        ("pairs", C.c_int64),
+        ("tests", C.c_int64),
+        ("deferredSteps", C.c_int64),
+        ("deferredStops", C.c_int64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad_"}
+
+
 class PhyxError(RuntimeError):
     pass
 
@@ -167,6 +192,9 @@ def load():
     l.phyx_b200_pack_manifolds.argtypes = [vp]
     l.phyx_b200_refresh_contact_joints.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     l.phyx_b200_solve_resident.argtypes = [vp, C.POINTER(SolveConfig), C.POINTER(SolveStats)]
+    l.phyx_b200_world_step.argtypes = [vp, f32, f32, C.POINTER(SolveConfig), C.POINTER(SolveStats), C.POINTER(BroadphaseStats), C.POINTER(StepInfo)]
+    l.phyx_b200_step_mode.argtypes = [vp, i32]
+    l.phyx_b200_strip_feedback.argtypes = [vp, i32]
     l.phyx_b200_reset_collider.argtypes = [vp]
     l.phyx_b200_collider_counts.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     l.phyx_b200_download_manifolds.argtypes = [vp, vp, i32]
@@ -329,6 +357,16 @@ class Context:
         self._check(self.l.phyx_b200_solve_resident(self.h, C.byref(cfg), C.byref(stats)))
         return stats
 
+    def world_step(self, dt, gravity=0.0, iters=(20, 20), schedule=SCHEDULE_COLOUR, flags=0):
+        """World::Update as one call (reference src/World.cpp:19-37); returns (solve stats, broadphase stats, step info)."""
+        cfg = SolveConfig(iters[0], iters[1], schedule, flags)
+        stats, bp, info = SolveStats(), BroadphaseStats(), StepInfo()
+        self._check(self.l.phyx_b200_world_step(self.h, dt, gravity, C.byref(cfg), C.byref(stats), C.byref(bp), C.byref(info)))
+        return stats, bp, info
+
+    def step_mode(self, deferred):
+        self._check(self.l.phyx_b200_step_mode(self.h, int(deferred)))
+
     def reset_collider(self):
         self._check(self.l.phyx_b200_reset_collider(self.h))
 
@@ -370,6 +408,10 @@ class Context:
     def solve_tuning(self, kernel_form=0, strips=0):
         """kernel_form: 0 choose, 1 streaming, 2 record form, 3 strip-local (required); strips: 0 choose, -1 never, n strips."""
         self._check(self.l.phyx_b200_solve_tuning(self.h, kernel_form, strips))
+
+    def strip_feedback(self, measured):
+        """measured=False: strip cuts from predicted work only (bit-reproducible runs); True (default): also from measured cost."""
+        self._check(self.l.phyx_b200_strip_feedback(self.h, int(bool(measured))))
 
     def strip_plan(self):
         """Strip layout of the last solve: dict(strips, cuts, class_slot_start, info...) or None if it did not use strips."""

@@ -114,11 +114,48 @@ int mailbox_stage(phyx_b200_ctx* c, const void* dev, size_t bytes, size_t offset
     return PHYX_B200_OK;
 }
 
+static int mailbox_spin(phyx_b200_ctx* c, int seq);
+
 int mailbox_wait(phyx_b200_ctx* c)
 {
     const int seq = int(++c->mailboxSeq & 0x7fffffffu);
     k_mailbox_flag<<<1, 1, 0, c->stream>>>(c->mailboxDev + kMailboxFlag / 4, seq);
     PHYX_CUDA(cudaGetLastError());
+    return mailbox_spin(c, seq);
+}
+
+// several pieces and the flag in ONE launch (the deferred step's only read-back)
+struct MailPieces
+{
+    const int* src[4];
+    int words[4], offset[4];   // offsets in words
+    int count;
+};
+
+__global__ void k_mailbox_post(MailPieces p, int* __restrict__ box, volatile int* flag, int seq)
+{
+    for (int k = 0; k < p.count; ++k)
+        for (int i = threadIdx.x; i < p.words[k]; i += blockDim.x) box[p.offset[k] + i] = p.src[k][i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence_system();
+        *flag = seq;
+    }
+}
+
+static int mailbox_post_and_wait(phyx_b200_ctx* c, const MailPieces& p)
+{
+    const int seq = int(++c->mailboxSeq & 0x7fffffffu);
+    k_mailbox_post<<<1, 128, 0, c->stream>>>(p, c->mailboxDev, c->mailboxDev + kMailboxFlag / 4, seq);
+    c->launches++;
+    PHYX_CUDA(cudaGetLastError());
+    return mailbox_spin(c, seq);
+}
+
+static int mailbox_spin(phyx_b200_ctx* c, int seq)
+{
     volatile int* flag = c->mailboxHost + kMailboxFlag / 4;
     for (unsigned spins = 0;; ++spins)
     {
@@ -276,7 +313,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
-        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->pairQ, &c->pairIdx, &c->bodyActivity, &c->islandTmp, &c->bodyOwner };
+        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->pairQ, &c->pairIdx, &c->bodyActivity, &c->islandTmp, &c->bodyOwner, &c->ctlBuf };
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -486,6 +523,7 @@ int phyx_b200_solve_staged(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, 
     PHYX_CUDA(cudaEventRecord(t1, c->stream));
     PHYX_TRY(solve_run(c, cfg, stats));
     PHYX_CUDA(cudaEventRecord(t2, c->stream));
+    if (c->def.active) return PHYX_B200_OK;   // deferred step: nothing waits here (deferred_finish fills the statistics)
     PHYX_CUDA(cudaEventSynchronize(t2));
     if (stats)
     {
@@ -510,6 +548,13 @@ int phyx_b200_solve_tuning(phyx_b200_ctx* c, int kernelForm, int strips)
     // schedules built so far may have the other layout
     c->scheduleMode = -1;
     c->colourStateValid = false;
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_strip_feedback(phyx_b200_ctx* c, int measured)
+{
+    PHYX_TRY(check(c));
+    c->strip.measuredFeedback = measured != 0;
     return PHYX_B200_OK;
 }
 
@@ -856,6 +901,267 @@ int phyx_b200_solve_resident(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg
         c->scheduleMode = -1;
     }
     return phyx_b200_solve_staged(c, cfg, stats);
+}
+
+// ---- World::Update as one call ------------------------------------------------------------------------------------
+// Reference src/World.cpp:19-37.  The eight stage functions above return their counts to the host, one read-back each;
+// here the step is issued without waiting: buffers and grids are sized by bounds predicted from the previous step, the
+// kernels read the true counts from a device block (common.cuh StepCtl) and ONE read-back at the end brings the counts,
+// the strip layout's header and the solve's results home.  When a bound does not hold, or the device takes a decision
+// the stage path takes on the host (rejected strip layout, colour rebuild), the step stops on the device before anything
+// was changed by the stage in question and the host finishes it with the stage functions: results are those of the
+// stage path either way.
+
+__global__ void k_ctl_begin(StepCtl* ctl, int bodies, int manifolds, int joints)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    StepCtl z;
+    memset(&z, 0, sizeof(z));
+    z.bodies = bodies;
+    z.manifolds = manifolds;
+    z.joints = joints;
+    z.jointsGrown = joints;
+    *ctl = z;
+}
+
+// stages of World::Update by number
+static int run_stages(phyx_b200_ctx* c, int first, float dt, float gravity, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* solveStats,
+    phyx_b200_broadphase_stats* bpStats)
+{
+    if (first <= 0) PHYX_TRY(phyx_b200_integrate_velocity(c, dt, gravity));
+    if (first <= 1) PHYX_TRY(phyx_b200_update_broadphase(c));
+    if (first <= 2) PHYX_TRY(phyx_b200_update_pairs(c, bpStats));
+    if (first <= 3) PHYX_TRY(phyx_b200_update_manifolds(c));
+    if (first <= 4) PHYX_TRY(phyx_b200_pack_manifolds(c));
+    if (first <= 5) PHYX_TRY(phyx_b200_refresh_contact_joints(c, nullptr, nullptr, nullptr));
+    if (first <= 6) PHYX_TRY(phyx_b200_solve_resident(c, cfg, solveStats));
+    return phyx_b200_integrate_position(c, dt);
+}
+
+static int bound_of(int last, int floorValue)
+{
+    const long long v = std::max<long long>(floorValue, (long long)last + last / 2 + 1024);
+    return int(std::min<long long>((v + 1023) & ~1023ll, 1ll << 30));
+}
+
+// can this step run deferred?  Only the steady state of the default pipeline does: colour schedule on the strip layout of
+// the previous step, one device, nothing forced
+static bool deferred_eligible(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg)
+{
+    const int nb = c->bodyCount;
+    if (!c->def.enabled || !cfg || cfg->schedule != PHYX_B200_SCHEDULE_COLOUR || cfg->flags != 0) return false;
+    if (cfg->contactIterationsCount < 0 || cfg->penetrationIterationsCount < 0 || cfg->contactIterationsCount > 60000 || cfg->penetrationIterationsCount > 60000) return false;
+    if (c->part.ranks > 1 || c->islandRanks > 1) return false;
+    if (c->forceKernelForm == 1 || c->forceKernelForm == 2 || c->strip.want != 0 || c->strip.tracePasses > 0) return false;
+    if (nb < 2 || c->manifoldCount <= 0 || c->jointCount <= 0) return false;
+    if (!c->jointUnitsValid || !c->colourStateValid || c->colourStateBodies != nb || !c->manColour.ptr || !c->bodyUsed.ptr) return false;
+    if (c->scheduleMode != PHYX_B200_SCHEDULE_COLOUR || c->scheduleFlags != 0) return false;
+    const StripPlan& sp = c->strip;
+    if (!sp.valid || sp.strips <= 0 || sp.feedbackStrips != sp.strips || sp.feedbackBodies != nb) return false;
+    if (!c->activityValid || c->activityBodies != nb) return false;
+    if (c->pairTableSlots == 0) return false;
+    // the strip count follows the world's size: leave the choice to the stage path when it would change by much
+    const int S = strip_choose(c, c->manifoldCount, nb);
+    if (S <= 0 || S * 8 > sp.strips * 9 || S * 9 < sp.strips * 8) return false;
+    return strip_predict_caps(c, &c->def.rowCap, &c->def.cutCap, &c->def.workCap);
+}
+
+static int deferred_issue(phyx_b200_ctx* c, float dt, float gravity, const phyx_b200_solve_config* cfg)
+{
+    Deferred& d = c->def;
+    PHYX_TRY(c->ctlBuf.reserve(sizeof(StepCtl)));
+    d.capItems = bound_of(std::max(d.lastItems, c->bodyCount), 8192);
+    d.capNewPairs = bound_of(std::max(d.lastNewPairs, c->manifoldCount / 64), 4096);
+    d.capFresh = bound_of(std::max(d.lastFresh, c->jointCount / 64), 4096);
+    if (d.tight)
+    {
+        // test mode: no headroom at all, so that any growth exercises the stop-and-resume path
+        d.capItems = std::max(d.lastItems, 1);
+        d.capNewPairs = std::max(d.lastNewPairs, 1);
+        d.capFresh = std::max(d.lastFresh, 1);
+    }
+    // the cache must take the new pairs without a rebuild in the middle of the step
+    if (size_t(c->manifoldCount + d.capNewPairs) * 2 > c->pairTableSlots) PHYX_TRY(collide_rebuild_pair_table_for(c, c->manifoldCount + d.capNewPairs));
+    k_ctl_begin<<<1, 32, 0, c->stream>>>(c->ctl(), c->bodyCount, c->manifoldCount, c->jointCount);
+    c->launches++;
+    d.colourResult = nullptr;
+    d.active = true;
+    c->hostJointsValid = false;
+    PHYX_TRY(bodies_integrate_velocity(c, dt, gravity));
+    PHYX_TRY(broadphase_update(c));
+    PHYX_CUDA(cudaEventRecord(c->evBp[2], c->stream));
+    PHYX_TRY(collide_update_pairs(c, nullptr));
+    PHYX_CUDA(cudaEventRecord(c->evBp[3], c->stream));
+    PHYX_TRY(collide_update_manifolds(c));
+    PHYX_TRY(collide_pack_manifolds(c));
+    PHYX_TRY(collide_refresh_joints(c, nullptr, nullptr, nullptr));
+    PHYX_TRY(phyx_b200_solve_staged(c, cfg, nullptr));
+    PHYX_TRY(bodies_integrate_position(c, dt));
+    if (!d.colourResult || !c->strip.header.ptr)
+    {
+        set_error("deferred step: the solve did not take the strip path (internal)");
+        return PHYX_B200_ERR_STATE;
+    }
+    // one read-back: counts | layout header | colouring result | solve result
+    MailPieces p;
+    p.count = 4;
+    p.src[0] = reinterpret_cast<const int*>(c->ctl());
+    p.words[0] = int(sizeof(StepCtl) / 4);
+    p.offset[0] = 0;
+    p.src[1] = c->strip.header.as<int>();
+    p.words[1] = 16;
+    p.offset[1] = 128 / 4;
+    p.src[2] = d.colourResult;
+    p.words[2] = 4;
+    p.offset[2] = 192 / 4;
+    p.src[3] = reinterpret_cast<const int*>(c->solveFlags.as<char>() + 32);
+    p.words[3] = 8;
+    p.offset[3] = 208 / 4;
+    return mailbox_post_and_wait(c, p);
+}
+
+int phyx_b200_world_step(phyx_b200_ctx* c, float dt, float gravity, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* solveStats,
+    phyx_b200_broadphase_stats* bpStats, phyx_b200_step_info* info)
+{
+    PHYX_TRY(check(c));
+    if (!cfg)
+    {
+        set_error("world_step: null config");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    if (info) memset(info, 0, sizeof(*info));
+    if (solveStats) memset(solveStats, 0, sizeof(*solveStats));
+    Deferred& d = c->def;
+    int resumeFrom = 0;
+    bool ranDeferred = false;
+    if (deferred_eligible(c, cfg))
+    {
+        const int st = deferred_issue(c, dt, gravity, cfg);
+        d.active = false;
+        if (st != PHYX_B200_OK)
+        {
+            // the context's counts may be bounds: nothing sensible can continue from here
+            c->jointUnitsValid = false;
+            c->colourStateValid = false;
+            c->strip.valid = false;
+            return st;
+        }
+        d.steps++;
+        StepCtl ctl;
+        int header[16], colourResult[4], result[8];
+        memcpy(&ctl, mailbox_at(c, 0), sizeof(ctl));
+        memcpy(header, mailbox_at(c, 128), sizeof(header));
+        memcpy(colourResult, mailbox_at(c, 192), sizeof(colourResult));
+        memcpy(result, mailbox_at(c, 208), sizeof(result));
+        if (ctl.stop)
+        {
+            // the device stopped before stage ctl.stop changed anything: exact counts, then the stage path from there
+            d.stops++;
+            d.lastStopStage = ctl.stop;
+            d.lastStopReason = ctl.stopReason;
+            c->manifoldCount = ctl.saved[1];
+            c->contactPointCount = 2 * c->manifoldCount;
+            c->jointCount = ctl.saved[2];
+            c->broadphaseValid = true;            // (IntegratePosition did not run)
+            c->jointUnitsValid = ctl.stop == kStageSolve;
+            c->strip.valid = false;
+            c->scheduleMode = -1;
+            if (ctl.stop == kStageSolve && ctl.stopReason == 12) c->colourStateValid = false;   // colour overflow: the stage path rebuilds (and falls back)
+            if (ctl.stop == kStagePairs)
+            {
+                d.lastItems = std::max(d.lastItems, ctl.stopReason == 1 ? ctl.stopNeed : d.lastItems);
+                d.lastNewPairs = std::max(d.lastNewPairs, ctl.stopReason == 2 ? ctl.stopNeed : d.lastNewPairs);
+            }
+            if (ctl.stop == kStageRefresh) d.lastFresh = std::max(d.lastFresh, ctl.stopNeed);
+            resumeFrom = ctl.stop == kStagePairs ? 2 : ctl.stop == kStageRefresh ? 5 : 6;
+            // (the stopped step's PackManifolds rebuilt the cache from zero manifolds)
+            if (ctl.stop == kStagePairs) PHYX_TRY(collide_rebuild_pair_table(c));
+        }
+        else
+        {
+            ranDeferred = true;
+            c->manifoldCount = ctl.manifolds;
+            c->contactPointCount = 2 * ctl.manifolds;
+            c->jointCount = ctl.joints;
+            c->lastTests = (long long)ctl.tests;
+            c->lastPairs = (long long)ctl.hits;
+            c->lastNewPairs = ctl.newPairs;
+            d.lastItems = ctl.items;
+            d.lastNewPairs = ctl.newPairs;
+            d.lastFresh = ctl.fresh;
+            strip_apply_header(c, header);        // (usable: the device has checked it)
+            c->slotCount = 2 * c->strip.manifolds;
+            c->levelCount = c->strip.colours;
+            c->coloursInUse = c->strip.colours;
+            c->colourRounds = colourResult[0];
+            c->lastKernelForm = 3;
+            long long act0 = 0, act1 = 0;
+            memcpy(&act0, &result[4], 8);
+            memcpy(&act1, &result[6], 8);
+            const double nominal = double(c->jointCount) * double(result[0] > 0 ? result[0] : 1);
+            c->lastActiveFraction = nominal > 0.0 ? float(double(act0) / nominal) : 1.0f;
+            if (solveStats)
+            {
+                solveStats->joints = c->jointCount;
+                solveStats->slots = c->slotCount;
+                solveStats->levels = c->levelCount;
+                solveStats->contactIterationsRun = result[0];
+                solveStats->penetrationIterationsRun = result[1];
+                solveStats->wakePasses = result[2];
+                solveStats->colourRounds = c->colourRounds;
+                solveStats->kernelForm = 3;
+                solveStats->activeJointIterations[0] = act0;
+                solveStats->activeJointIterations[1] = act1;
+                solveStats->ms_schedule = elapsed_ms(c->ev[4], c->ev[5]);
+                solveStats->ms_refresh = elapsed_ms(c->ev[0], c->ev[1]);
+                solveStats->ms_iterations = elapsed_ms(c->ev[1], c->ev[2]);
+                solveStats->ms_finish = elapsed_ms(c->ev[2], c->ev[3]);
+                solveStats->ms_total = elapsed_ms(c->ev[4], c->ev[6]);
+            }
+            if (bpStats)
+            {
+                bpStats->tests = c->lastTests;
+                bpStats->pairs = c->lastPairs;
+                bpStats->ms_sort = c->sortTimed ? elapsed_ms(c->evBp[0], c->evBp[1]) : 0.f;
+                bpStats->ms_sweep = elapsed_ms(c->evBp[2], c->evBp[3]);
+                bpStats->ms_total = bpStats->ms_sort + bpStats->ms_sweep;
+            }
+            if (info)
+            {
+                info->newPairs = ctl.newPairs;
+                info->jointsCreated = ctl.created;
+                info->jointsDeleted = ctl.deleted;
+            }
+        }
+        if (info)
+        {
+            info->stopStage = ctl.stop;
+            info->stopReason = ctl.stopReason;
+        }
+    }
+    else
+        d.ineligible++;
+    if (!ranDeferred) PHYX_TRY(run_stages(c, resumeFrom, dt, gravity, cfg, solveStats, bpStats));
+    if (info)
+    {
+        info->deferred = ranDeferred ? 1 : 0;
+        info->manifolds = c->manifoldCount;
+        info->contactPoints = c->contactPointCount;
+        info->joints = c->jointCount;
+        info->pairs = c->lastPairs;
+        info->tests = c->lastTests;
+        info->deferredSteps = d.steps;
+        info->deferredStops = d.stops;
+    }
+    return PHYX_B200_OK;
+}
+
+int phyx_b200_step_mode(phyx_b200_ctx* c, int deferred)
+{
+    PHYX_TRY(check(c));
+    c->def.enabled = deferred != 0;
+    c->def.tight = deferred == 2;
+    return PHYX_B200_OK;
 }
 
 int phyx_b200_reset_collider(phyx_b200_ctx* c)

@@ -89,11 +89,11 @@ __device__ __forceinline__ void rotate_vec(float& x, float& y, float c, float s)
 }
 
 // World::IntegratePosition, src/World.cpp:61-69
-__global__ void k_integrate_position(int n, float dt, const float4* __restrict__ vel, float4* __restrict__ disp,
+__global__ void k_integrate_position(Count nc, float dt, const float4* __restrict__ vel, float4* __restrict__ disp,
     float4* __restrict__ params, float4* __restrict__ rot, float4* __restrict__ aabb, const float2* __restrict__ size)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= count_of(nc)) return;   // (a stopped deferred step must not move the bodies: the host finishes it first)
     float4 v = vel[i], d = disp[i], p = params[i], r = rot[i];
     float2 sz = size[i];
     float mx = d.x + v.x * dt;
@@ -235,7 +235,7 @@ int bodies_integrate_position(phyx_b200_ctx* c, float dt)
 {
     int n = c->bodyCount;
     if (n == 0) return PHYX_B200_OK;
-    k_integrate_position<<<(n + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(n, dt, c->vel.as<float4>(), c->disp.as<float4>(),
+    k_integrate_position<<<(n + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->count(n, &StepCtl::bodies), dt, c->vel.as<float4>(), c->disp.as<float4>(),
         c->params.as<float4>(), c->rot.as<float4>(), c->aabb.as<float4>(), c->size.as<float2>());
     c->launches++;
     c->broadphaseValid = false;

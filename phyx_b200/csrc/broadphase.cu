@@ -50,10 +50,11 @@ constexpr int kSortWarps = kBlock / 32;
 constexpr int kSortTile = kBlock * kSortItems;
 constexpr int kMaxDigits = 2048;
 
-__global__ void __launch_bounds__(kBlock) k_radix_hist(const uint2* __restrict__ src, int n, int shift, int digits, int numBlocks,
+__global__ void __launch_bounds__(kBlock) k_radix_hist(const uint2* __restrict__ src, Count nc, int shift, int digits, int numBlocks,
     int* __restrict__ table)
 {
     __shared__ int h[kMaxDigits];
+    const int n = count_of(nc);
     for (int d = threadIdx.x; d < digits; d += kBlock) h[d] = 0;
     __syncthreads();
     int base = blockIdx.x * kSortTile;
@@ -68,9 +69,11 @@ __global__ void __launch_bounds__(kBlock) k_radix_hist(const uint2* __restrict__
     for (int d = threadIdx.x; d < digits; d += kBlock) table[size_t(d) * numBlocks + blockIdx.x] = h[d];
 }
 
-__global__ void __launch_bounds__(kBlock) k_radix_scatter(const uint2* __restrict__ src, uint2* __restrict__ dst, int n, int shift,
+__global__ void __launch_bounds__(kBlock) k_radix_scatter(const uint2* __restrict__ src, uint2* __restrict__ dst, Count nc, int shift,
     int digits, int numBlocks, const int* __restrict__ tableScanned)
 {
+    const int n = count_of(nc);
+    if (blockIdx.x * kSortTile >= n) return;   // (a count read from the device may be shorter than the grid)
     __shared__ unsigned short cnt[kSortWarps][kMaxDigits];   // per-warp digit counts, then prefixes
     __shared__ int gOff[kMaxDigits];                         // global offset of (digit, this block)
 
@@ -169,10 +172,10 @@ __global__ void k_sweep_end(int n, const float2* __restrict__ entryX, int* __res
     itemsOf[i] = (lo - i - 1 + kChunk - 1) / kChunk;
 }
 
-__global__ void k_sweep_items(int n, const int* __restrict__ itemStart, const int* __restrict__ end, int2* __restrict__ items)
+__global__ void k_sweep_items(Count nc, const int* __restrict__ itemStart, const int* __restrict__ end, int2* __restrict__ items)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= count_of(nc)) return;
     int cnt = (end[i] - i - 1 + kChunk - 1) / kChunk;
     int s = itemStart[i];
     for (int k = 0; k < cnt; ++k) items[s + k] = make_int2(i, k);
@@ -278,10 +281,12 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numIte
 // not fit (the ground body's scan covers every entry) are flagged and left to the item kernel.
 
 template <bool FILTER>
-__global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(int n, const int* __restrict__ end, const int* __restrict__ itemStart,
+__global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(Count nc, const int* __restrict__ end, const int* __restrict__ itemStart,
     const float2* __restrict__ entryY, const unsigned* __restrict__ entryIndex, int* __restrict__ itemCount, unsigned char* __restrict__ tileLong,
     unsigned long long* __restrict__ totals, const unsigned long long* __restrict__ table, size_t tableMask)
 {
+    const int n = count_of(nc);
+    if (n == 0) return;   // (a stopped deferred step)
     __shared__ float2 tileY[kTileCap];
     __shared__ unsigned short byCell[kTileCap];     // tile entries (relative index) bucketed by y cell
     __shared__ int cellStart[kCells + 1], cellFill[kCells];
@@ -447,17 +452,64 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(int n, const int* 
     }
 }
 
+// ---- deferred step: the sweep's counts stay on the device (common.cuh StepCtl) ---------------------
+// counters: [0] work items, [1] emitted pairs, then two 64-bit totals (tests, unfiltered hits) at byte 16
+
+__global__ void k_gate_items(StepCtl* ctl, int* __restrict__ counters, int capItems)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int items = counters[0];
+    if (!ctl->stop)
+    {
+        ctl->items = items;
+        if (items > capItems) ctl_stop(ctl, kStagePairs, items, 1);
+    }
+    if (ctl->stop) counters[0] = 0;
+}
+
+__global__ void k_gate_pairs(StepCtl* ctl, int* __restrict__ counters, int capPairs)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (!ctl->stop)
+    {
+        const int pairs = counters[1];
+        const unsigned long long* totals = reinterpret_cast<const unsigned long long*>(counters + 4);
+        ctl->newPairs = pairs;
+        ctl->tests = totals[0];
+        ctl->hits = totals[1];
+        if (pairs > capPairs)
+            ctl_stop(ctl, kStagePairs, pairs, 2);
+        else
+        {
+            ctl->appendFirst = ctl->manifolds;   // Collider.cpp:358-362: new manifolds are appended in sweep order
+            ctl->manifolds += pairs;
+        }
+    }
+    if (ctl->stop) counters[0] = counters[1] = 0;
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 
 int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift, int digits)
 {
+    Count nc;
+    nc.v = n;
+    nc.p = nullptr;
+    nc.mul = 1;
+    return radix_pass_count(c, src, dst, nc, shift, digits);
+}
+
+int radix_pass_count(phyx_b200_ctx* c, const uint2* src, uint2* dst, Count nc, int shift, int digits)
+{
+    const int n = nc.v;
+    if (n <= 0) return PHYX_B200_OK;
     int blocks = (n + kSortTile - 1) / kSortTile;
     size_t tableInts = size_t(digits) * blocks;
     PHYX_TRY(c->hist.reserve(tableInts * sizeof(int)));
-    k_radix_hist<<<blocks, kBlock, 0, c->stream>>>(src, n, shift, digits, blocks, c->hist.as<int>());
+    k_radix_hist<<<blocks, kBlock, 0, c->stream>>>(src, nc, shift, digits, blocks, c->hist.as<int>());
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, c->hist.as<int>(), c->hist.as<int>(), int(tableInts), nullptr));
-    k_radix_scatter<<<blocks, kBlock, 0, c->stream>>>(src, dst, n, shift, digits, blocks, c->hist.as<int>());
+    k_radix_scatter<<<blocks, kBlock, 0, c->stream>>>(src, dst, nc, shift, digits, blocks, c->hist.as<int>());
     c->launches++;
     PHYX_CUDA(cudaGetLastError());
     return PHYX_B200_OK;
@@ -527,13 +579,22 @@ int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats, bool f
     k_sweep_end<<<grid, kBlock, 0, c->stream>>>(n, entryX, c->sweepEnd.as<int>(), c->itemStart.as<int>());
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, c->itemStart.as<int>(), c->itemStart.as<int>(), n, d_numItems));
+    const bool deferred = c->def.active;   // (only the cache-filtered sweep of a whole step is ever deferred)
     int numItems = 0;
-    PHYX_TRY(fetch_small(c, d_numItems, sizeof(int), &numItems));
+    if (deferred)
+    {
+        numItems = c->def.capItems;
+        k_gate_items<<<1, 32, 0, c->stream>>>(c->ctl(), d_numItems, numItems);
+        c->launches++;
+    }
+    else
+        PHYX_TRY(fetch_small(c, d_numItems, sizeof(int), &numItems));
     if (numItems == 0) return PHYX_B200_OK;
 
     PHYX_TRY(c->items.reserve(size_t(numItems) * sizeof(int2)));
     PHYX_TRY(c->itemCount.reserve(size_t(numItems) * sizeof(int)));
-    k_sweep_items<<<grid, kBlock, 0, c->stream>>>(n, c->itemStart.as<int>(), c->sweepEnd.as<int>(), c->items.as<int2>());
+    const Count nLive = c->count(n, &StepCtl::bodies);
+    k_sweep_items<<<grid, kBlock, 0, c->stream>>>(nLive, c->itemStart.as<int>(), c->sweepEnd.as<int>(), c->items.as<int2>());
     c->launches++;
 
     const unsigned long long* table = c->pairTable.as<unsigned long long>();
@@ -546,22 +607,38 @@ int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats, bool f
     unsigned char* tileLong = c->tileLong.as<unsigned char>();
     if (filter)
     {
-        k_sweep_count_tiled<true><<<tiles, kBlock, 0, c->stream>>>(n, c->sweepEnd.as<int>(), c->itemStart.as<int>(), entryY, c->entryIndex.as<unsigned>(),
+        k_sweep_count_tiled<true><<<tiles, kBlock, 0, c->stream>>>(nLive, c->sweepEnd.as<int>(), c->itemStart.as<int>(), entryY, c->entryIndex.as<unsigned>(),
             c->itemCount.as<int>(), tileLong, d_totals, table, mask);
         k_sweep<false, true><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
             c->entryIndex.as<unsigned>(), c->itemCount.as<int>(), nullptr, nullptr, d_totals, table, mask, nullptr, tileLong);
     }
     else
     {
-        k_sweep_count_tiled<false><<<tiles, kBlock, 0, c->stream>>>(n, c->sweepEnd.as<int>(), c->itemStart.as<int>(), entryY, c->entryIndex.as<unsigned>(),
+        k_sweep_count_tiled<false><<<tiles, kBlock, 0, c->stream>>>(nLive, c->sweepEnd.as<int>(), c->itemStart.as<int>(), entryY, c->entryIndex.as<unsigned>(),
             c->itemCount.as<int>(), tileLong, d_totals, nullptr, 0);
         k_sweep<false, false><<<sweepGrid, kBlock, 0, c->stream>>>(d_numItems, c->items.as<int2>(), c->sweepEnd.as<int>(), entryY,
             c->entryIndex.as<unsigned>(), c->itemCount.as<int>(), nullptr, nullptr, d_totals, nullptr, 0, nullptr, tileLong);
     }
     c->launches += 2;
-    PHYX_TRY(exclusive_scan_i32(c, c->itemCount.as<int>(), c->itemCount.as<int>(), numItems, d_numPairs));
     struct { int items, pairs; long long pad; unsigned long long tests, hits; } host;
-    PHYX_TRY(fetch_small(c, c->counters.ptr, sizeof(host), &host));
+    if (deferred)
+    {
+        Count ni;
+        ni.v = numItems;
+        ni.p = d_numItems;
+        ni.mul = 1;
+        PHYX_TRY(exclusive_scan_count(c, c->itemCount.as<int>(), c->itemCount.as<int>(), ni, d_numPairs));
+        k_gate_pairs<<<1, 32, 0, c->stream>>>(c->ctl(), d_numItems, c->def.capNewPairs);
+        c->launches++;
+        host.items = numItems;
+        host.pairs = c->def.capNewPairs;   // bound; the true totals come home with the step (StepCtl)
+        host.tests = host.hits = 0;
+    }
+    else
+    {
+        PHYX_TRY(exclusive_scan_i32(c, c->itemCount.as<int>(), c->itemCount.as<int>(), numItems, d_numPairs));
+        PHYX_TRY(fetch_small(c, c->counters.ptr, sizeof(host), &host));
+    }
     c->lastTests = (long long)host.tests;
     c->lastPairs = filter ? (long long)host.hits : host.pairs;
     c->lastNewPairs = filter ? host.pairs : 0;

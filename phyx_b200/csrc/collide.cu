@@ -29,11 +29,12 @@ constexpr int kBlock = 256;
 // UpdatePairs: append the sweep's new pairs as manifolds
 // ================================================================================================
 
-__global__ void __launch_bounds__(kBlock) k_append_manifolds(int count, const int2* __restrict__ pairs, int first, int2* __restrict__ manBody,
-    int* __restrict__ manCount, int* __restrict__ manColour, unsigned long long* __restrict__ table, size_t mask)
+__global__ void __launch_bounds__(kBlock) k_append_manifolds(Count count, const int2* __restrict__ pairs, int first, const int* __restrict__ firstPtr,
+    int2* __restrict__ manBody, int* __restrict__ manCount, int* __restrict__ manColour, unsigned long long* __restrict__ table, size_t mask)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
+    if (k >= count_of(count)) return;
+    if (firstPtr) first = __ldcg(firstPtr);   // (deferred step: the manifold count lives on the device)
     int2 p = pairs[k];
     manBody[first + k] = p;        // Manifold(index_i, index_j, size*2): pointIndex is implicit (2*m)
     manCount[first + k] = 0;
@@ -41,10 +42,10 @@ __global__ void __launch_bounds__(kBlock) k_append_manifolds(int count, const in
     if (table) pair_insert(table, mask, pair_key(unsigned(p.x), unsigned(p.y)));
 }
 
-__global__ void __launch_bounds__(kBlock) k_table_insert(int count, const int2* __restrict__ manBody, unsigned long long* __restrict__ table, size_t mask)
+__global__ void __launch_bounds__(kBlock) k_table_insert(Count count, const int2* __restrict__ manBody, unsigned long long* __restrict__ table, size_t mask)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= count) return;
+    if (m >= count_of(count)) return;
     int2 p = manBody[m];
     pair_insert(table, mask, pair_key(unsigned(p.x), unsigned(p.y)));
 }
@@ -61,10 +62,12 @@ static int reserve_manifolds(phyx_b200_ctx* c, int count)
 }
 
 // (re)build the pair table from the live manifolds; sized for a load factor <= 1/4 with headroom
-int collide_rebuild_pair_table(phyx_b200_ctx* c)
+int collide_rebuild_pair_table(phyx_b200_ctx* c) { return collide_rebuild_pair_table_for(c, c->manifoldCount); }
+
+int collide_rebuild_pair_table_for(phyx_b200_ctx* c, int manifolds)
 {
     size_t want = 1024;
-    while (want < size_t(c->manifoldCount + c->bodyCount) * 4) want <<= 1;
+    while (want < size_t(manifolds + c->bodyCount) * 4) want <<= 1;
     if (want > c->pairTableSlots)
     {
         PHYX_TRY(c->pairTable.reserve(want * sizeof(unsigned long long)));
@@ -73,7 +76,7 @@ int collide_rebuild_pair_table(phyx_b200_ctx* c)
     PHYX_CUDA(cudaMemsetAsync(c->pairTable.ptr, 0xff, c->pairTableSlots * sizeof(unsigned long long), c->stream));
     if (c->manifoldCount > 0)
     {
-        k_table_insert<<<(c->manifoldCount + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->manifoldCount, c->manBody.as<int2>(),
+        k_table_insert<<<(c->manifoldCount + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->count(c->manifoldCount, &StepCtl::manifolds), c->manBody.as<int2>(),
             c->pairTable.as<unsigned long long>(), c->pairTableSlots - 1);
         c->launches++;
     }
@@ -90,7 +93,9 @@ int collide_update_pairs(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats)
     // the table must stay sparse (linear probing never terminates on a full table): if the additions
     // would push it past half full, append without inserting and rebuild it at the right size
     const bool rebuild = size_t(c->manifoldCount + fresh) * 2 > c->pairTableSlots;
-    k_append_manifolds<<<(fresh + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(fresh, c->pairs.as<int2>(), c->manifoldCount, c->manBody.as<int2>(),
+    // (deferred step: `fresh` and manifoldCount are bounds, the kernel reads the counts the sweep left on the device)
+    k_append_manifolds<<<(fresh + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->count(fresh, &StepCtl::newPairs), c->pairs.as<int2>(), c->manifoldCount,
+        c->def.active ? &c->ctl()->appendFirst : nullptr, c->manBody.as<int2>(),
         c->manCount.as<int>(), c->manColour.as<int>(), rebuild ? nullptr : c->pairTable.as<unsigned long long>(), c->pairTableSlots - 1);
     c->launches++;
     c->manifoldCount += fresh;
@@ -313,11 +318,11 @@ __device__ void generate_contacts(const Box& A, const Box& B, Point* pts, int& c
 }
 
 // UpdateManifold, src/Collider.cpp:213-245: one thread per manifold; contact point = 2 x float4
-__global__ void __launch_bounds__(kBlock) k_update_manifolds(int count, const int2* __restrict__ manBody, int* __restrict__ manCount,
+__global__ void __launch_bounds__(kBlock) k_update_manifolds(Count count, const int2* __restrict__ manBody, int* __restrict__ manCount,
     float4* __restrict__ contactPoints, const float4* __restrict__ params, const float4* __restrict__ rot, const float2* __restrict__ size)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= count) return;
+    if (m >= count_of(count)) return;
     const int2 bodies = manBody[m];
     const int had = manCount[m];
     Point pts[4];
@@ -355,7 +360,7 @@ int collide_update_manifolds(phyx_b200_ctx* c)
     int M = c->manifoldCount;
     c->jointUnitsValid = false;   // new contact points have no joint until RefreshContactJoints
     if (M == 0) return PHYX_B200_OK;
-    k_update_manifolds<<<(M + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(),
+    k_update_manifolds<<<(M + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->count(M, &StepCtl::manifolds), c->manBody.as<int2>(), c->manCount.as<int>(),
         c->contactPoints.as<float4>(), c->params.as<float4>(), c->rot.as<float4>(), c->size.as<float2>());
     c->launches++;
     PHYX_CUDA(cudaGetLastError());
@@ -368,11 +373,11 @@ int collide_update_manifolds(phyx_b200_ctx* c)
 // alive[i] (0/1) -> prefix (exclusive scan).  K = number alive.  Movers = alive elements at index
 // >= K, numbered from the END; holes = dead elements at index < K, numbered from the FRONT.
 
-__global__ void __launch_bounds__(kBlock) k_list_movers(int n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
+__global__ void __launch_bounds__(kBlock) k_list_movers(Count n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
     int* __restrict__ moverIndex)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= count_of(n)) return;
     const int K = *totalPtr;
     if (i >= K && alive[i]) moverIndex[K - prefix[i] - 1] = i;   // alive elements after i: K - prefix[i] - 1
 }
@@ -381,11 +386,11 @@ __global__ void __launch_bounds__(kBlock) k_list_movers(int n, const int* __rest
 // PackManifolds
 // ================================================================================================
 
-__global__ void __launch_bounds__(kBlock) k_manifold_alive(int count, const int2* __restrict__ manBody, const int* __restrict__ manCount,
+__global__ void __launch_bounds__(kBlock) k_manifold_alive(Count count, const int2* __restrict__ manBody, const int* __restrict__ manCount,
     const float4* __restrict__ aabb, int* __restrict__ alive, const int* __restrict__ manColour, unsigned long long* __restrict__ bodyUsed)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= count) return;
+    if (m >= count_of(count)) return;
     int2 b = manBody[m];
     float4 a1 = aabb[b.x], a2 = aabb[b.y];
     // AABB2::Intersects, src/AABB2.h:18-23
@@ -401,13 +406,13 @@ __global__ void __launch_bounds__(kBlock) k_manifold_alive(int count, const int2
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_manifold_fill(int n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
+__global__ void __launch_bounds__(kBlock) k_manifold_fill(Count n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
     const int* __restrict__ moverIndex, int2* __restrict__ manBody, int* __restrict__ manCount, int* __restrict__ manColour,
     float4* __restrict__ contactPoints)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     const int K = *totalPtr;
-    if (m >= n || m >= K || alive[m]) return;
+    if (m >= count_of(n) || m >= K || alive[m]) return;
     const int src = moverIndex[m - prefix[m]];   // holes before m: m - prefix[m]
     const int cnt = manCount[src];
     manBody[m] = manBody[src];
@@ -418,6 +423,35 @@ __global__ void __launch_bounds__(kBlock) k_manifold_fill(int n, const int* __re
         contactPoints[size_t(2 * m + k) * 2] = contactPoints[size_t(2 * src + k) * 2];
         contactPoints[size_t(2 * m + k) * 2 + 1] = contactPoints[size_t(2 * src + k) * 2 + 1];
     }
+}
+
+// deferred step: small single-thread kernels move the counts along on the device
+__global__ void k_ctl_packed(StepCtl* ctl, const int* __restrict__ total)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || ctl->stop) return;
+    ctl->packed = *total;
+    ctl->manifolds = *total;
+}
+
+// new joints are known: check the bound, fix the joint count the cleanup starts from
+__global__ void k_gate_fresh(StepCtl* ctl, const int* __restrict__ total, int capFresh)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || ctl->stop) return;
+    const int fresh = *total;
+    ctl->fresh = fresh;
+    if (fresh > capFresh)
+        ctl_stop(ctl, kStageRefresh, fresh, 3);
+    else
+        ctl->jointsGrown = ctl->joints + fresh;
+}
+
+__global__ void k_ctl_joints(StepCtl* ctl, const int* __restrict__ total)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || ctl->stop) return;
+    ctl->jointsKept = *total;
+    ctl->created = ctl->fresh;
+    ctl->deleted = ctl->jointsGrown - *total;
+    ctl->joints = *total;
 }
 
 int collide_pack_manifolds(phyx_b200_ctx* c)
@@ -433,14 +467,23 @@ int collide_pack_manifolds(phyx_b200_ctx* c)
     int* total = movers + M;
     const int grid = (M + kBlock - 1) / kBlock;
     const bool track = c->colourStateValid && c->colourStateBodies == c->bodyCount && c->bodyUsed.ptr;
-    k_manifold_alive<<<grid, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(), c->aabb.as<float4>(), alive, c->manColour.as<int>(),
+    const Count Mc = c->count(M, &StepCtl::manifolds);
+    k_manifold_alive<<<grid, kBlock, 0, c->stream>>>(Mc, c->manBody.as<int2>(), c->manCount.as<int>(), c->aabb.as<float4>(), alive, c->manColour.as<int>(),
         track ? c->bodyUsed.as<unsigned long long>() : nullptr);
     c->launches++;
-    PHYX_TRY(exclusive_scan_i32(c, alive, prefix, M, total));
-    k_list_movers<<<grid, kBlock, 0, c->stream>>>(M, alive, prefix, total, movers);
-    k_manifold_fill<<<grid, kBlock, 0, c->stream>>>(M, alive, prefix, total, movers, c->manBody.as<int2>(), c->manCount.as<int>(),
+    PHYX_TRY(exclusive_scan_count(c, alive, prefix, Mc, total));
+    k_list_movers<<<grid, kBlock, 0, c->stream>>>(Mc, alive, prefix, total, movers);
+    k_manifold_fill<<<grid, kBlock, 0, c->stream>>>(Mc, alive, prefix, total, movers, c->manBody.as<int2>(), c->manCount.as<int>(),
         c->manColour.as<int>(), c->contactPoints.as<float4>());
     c->launches += 2;
+    if (c->def.active)
+    {
+        // deferred step: the survivor count stays on the device (M remains the host's bound); the cache is rebuilt from the
+        // survivors whether or not anything was removed (in a moving world something always is)
+        k_ctl_packed<<<1, 32, 0, c->stream>>>(c->ctl(), total);
+        c->launches++;
+        return collide_rebuild_pair_table(c);
+    }
     int K = 0;
     PHYX_TRY(fetch_small(c, total, sizeof(int), &K));
     const bool removed = K != M;
@@ -455,28 +498,29 @@ int collide_pack_manifolds(phyx_b200_ctx* c)
 // RefreshContactJoints
 // ================================================================================================
 
-__global__ void __launch_bounds__(kBlock) k_joint_reset(int nj, phyx_contact_joint* __restrict__ joints)
+__global__ void __launch_bounds__(kBlock) k_joint_reset(Count nj, phyx_contact_joint* __restrict__ joints)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nj) joints[j].contactPointIndex = -1;   // World.cpp:83-86
+    if (j < count_of(nj)) joints[j].contactPointIndex = -1;   // World.cpp:83-86
 }
 
 // flag[p] = 1 for live contact points without a joint yet (solverIndex < 0)
-__global__ void __launch_bounds__(kBlock) k_point_new_flags(int numPoints, const int* __restrict__ manCount, const float4* __restrict__ contactPoints,
+__global__ void __launch_bounds__(kBlock) k_point_new_flags(Count numPoints, const int* __restrict__ manCount, const float4* __restrict__ contactPoints,
     int* __restrict__ isNew)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= numPoints) return;
+    if (p >= count_of(numPoints)) return;
     bool live = (p & 1) < manCount[p >> 1];
     isNew[p] = live && __float_as_int(contactPoints[size_t(p) * 2 + 1].w) < 0;
 }
 
 // World.cpp:91-124: new points get a joint appended in (manifold, point) order, known points re-attach
-__global__ void __launch_bounds__(kBlock) k_joint_match(int numPoints, int oldJoints, const int2* __restrict__ manBody, const int* __restrict__ manCount,
+__global__ void __launch_bounds__(kBlock) k_joint_match(Count numPoints, Count oldJointsC, const int2* __restrict__ manBody, const int* __restrict__ manCount,
     float4* __restrict__ contactPoints, const int* __restrict__ isNew, const int* __restrict__ newRank, phyx_contact_joint* __restrict__ joints)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= numPoints) return;
+    if (p >= count_of(numPoints)) return;
+    const int oldJoints = count_of(oldJointsC);
     if ((p & 1) >= manCount[p >> 1]) return;
     if (isNew[p])
     {
@@ -498,18 +542,18 @@ __global__ void __launch_bounds__(kBlock) k_joint_match(int numPoints, int oldJo
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_joint_alive(int nj, const phyx_contact_joint* __restrict__ joints, int* __restrict__ alive)
+__global__ void __launch_bounds__(kBlock) k_joint_alive(Count nj, const phyx_contact_joint* __restrict__ joints, int* __restrict__ alive)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nj) alive[j] = joints[j].contactPointIndex >= 0;
+    if (j < count_of(nj)) alive[j] = joints[j].contactPointIndex >= 0;
 }
 
-__global__ void __launch_bounds__(kBlock) k_joint_fill(int n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
+__global__ void __launch_bounds__(kBlock) k_joint_fill(Count n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
     const int* __restrict__ moverIndex, phyx_contact_joint* __restrict__ joints)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int K = *totalPtr;
-    if (j >= n || j >= K || alive[j]) return;
+    if (j >= count_of(n) || j >= K || alive[j]) return;
     joints[j] = joints[moverIndex[j - prefix[j]]];   // World.cpp:131-134
 }
 
@@ -523,11 +567,15 @@ __global__ void __launch_bounds__(kBlock) k_joint_backlink(const int* __restrict
 
 int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* deleted)
 {
+    // deferred step: J0 is exact (nothing before this stage changes the joints), P, `fresh`, J1 are bounds; the true counts
+    // are StepCtl::joints / manifolds x 2 / fresh / jointsGrown / jointsKept
+    const bool deferred = c->def.active;
     const int J0 = c->jointCount, P = 2 * c->manifoldCount;
     int fresh = 0;
+    const Count J0c = c->count(J0, &StepCtl::joints);
     if (J0 > 0)
     {
-        k_joint_reset<<<(J0 + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(J0, c->joints.as<phyx_contact_joint>());
+        k_joint_reset<<<(J0 + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(J0c, c->joints.as<phyx_contact_joint>());
         c->launches++;
     }
     // scratch A (points): isNew[P] | newRank[P] | total
@@ -538,12 +586,20 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         int* isNew = c->collideTmp.as<int>();
         int* newRank = isNew + P;
         int* total = newRank + P;
-        k_point_new_flags<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(P, c->manCount.as<int>(), c->contactPoints.as<float4>(), isNew);
+        const Count Pc = c->count(P, &StepCtl::manifolds, 2);
+        k_point_new_flags<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(Pc, c->manCount.as<int>(), c->contactPoints.as<float4>(), isNew);
         c->launches++;
-        PHYX_TRY(exclusive_scan_i32(c, isNew, newRank, P, total));
-        PHYX_TRY(fetch_small(c, total, sizeof(int), &fresh));
+        PHYX_TRY(exclusive_scan_count(c, isNew, newRank, Pc, total));
+        if (deferred)
+        {
+            fresh = c->def.capFresh;
+            k_gate_fresh<<<1, 32, 0, c->stream>>>(c->ctl(), total, fresh);
+            c->launches++;
+        }
+        else
+            PHYX_TRY(fetch_small(c, total, sizeof(int), &fresh));
         PHYX_TRY(c->joints.reserve_keep(size_t(J0 + fresh > 0 ? J0 + fresh : 1) * sizeof(phyx_contact_joint), size_t(J0) * sizeof(phyx_contact_joint), c->stream));
-        k_joint_match<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(P, J0, c->manBody.as<int2>(), c->manCount.as<int>(),
+        k_joint_match<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(Pc, J0c, c->manBody.as<int2>(), c->manCount.as<int>(),
             c->contactPoints.as<float4>(), isNew, newRank, c->joints.as<phyx_contact_joint>());
         c->launches++;
     }
@@ -558,13 +614,21 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         int* movers = prefix + J1;
         int* total = movers + J1;
         const int grid = (J1 + kBlock - 1) / kBlock;
-        k_joint_alive<<<grid, kBlock, 0, c->stream>>>(J1, c->joints.as<phyx_contact_joint>(), alive);
-        PHYX_TRY(exclusive_scan_i32(c, alive, prefix, J1, total));
-        k_list_movers<<<grid, kBlock, 0, c->stream>>>(J1, alive, prefix, total, movers);
-        k_joint_fill<<<grid, kBlock, 0, c->stream>>>(J1, alive, prefix, total, movers, c->joints.as<phyx_contact_joint>());
+        const Count J1c = c->count(J1, &StepCtl::jointsGrown);
+        k_joint_alive<<<grid, kBlock, 0, c->stream>>>(J1c, c->joints.as<phyx_contact_joint>(), alive);
+        PHYX_TRY(exclusive_scan_count(c, alive, prefix, J1c, total));
+        k_list_movers<<<grid, kBlock, 0, c->stream>>>(J1c, alive, prefix, total, movers);
+        k_joint_fill<<<grid, kBlock, 0, c->stream>>>(J1c, alive, prefix, total, movers, c->joints.as<phyx_contact_joint>());
         k_joint_backlink<<<grid, kBlock, 0, c->stream>>>(total, c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>());
         c->launches += 4;
-        PHYX_TRY(fetch_small(c, total, sizeof(int), &K));
+        if (deferred)
+        {
+            k_ctl_joints<<<1, 32, 0, c->stream>>>(c->ctl(), total);
+            c->launches++;
+            K = J1;   // bound
+        }
+        else
+            PHYX_TRY(fetch_small(c, total, sizeof(int), &K));
     }
     PHYX_CUDA(cudaGetLastError());
     c->jointCount = K;

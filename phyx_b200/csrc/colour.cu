@@ -66,11 +66,11 @@ __global__ void __launch_bounds__(kBlock) k_colour_init(int nj, int nb, int ncp,
 }
 
 // static flags the colouring is built with; mismatch = 1 if a body changed class since the last full build
-__global__ void __launch_bounds__(kBlock) k_colour_body_flags(int nb, const float4* __restrict__ params, unsigned char* __restrict__ bodyStatic, bool compare,
+__global__ void __launch_bounds__(kBlock) k_colour_body_flags(Count nb, const float4* __restrict__ params, unsigned char* __restrict__ bodyStatic, bool compare,
     int* __restrict__ result)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
+    if (b >= count_of(nb)) return;
     float4 p = params[b];
     unsigned char st = (p.x == 0.0f && p.y == 0.0f) ? 1 : 0;
     if (compare)
@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kBlock) k_colour_body_flags(int nb, const floa
 struct ColourParams
 {
     int nj;
+    const int* njPtr;            // deferred step: the unit count lives on the device (nj is the bound)
     const int2* jb;
     int* colour;
     unsigned long long* claim;   // per body: smallest (priority, joint) among its uncoloured joints
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kBlock) k_colour_rounds(ColourParams P)
     bool overflow = false;
     for (;;)
     {
-        const int n = rounds == 0 ? P.nj : __ldcg(&P.listCount[rounds & 3]);
+        const int n = rounds == 0 ? (P.njPtr ? min(__ldcg(P.njPtr), P.nj) : P.nj) : __ldcg(&P.listCount[rounds & 3]);
         const int* cur = P.list[rounds & 1];
         int* next = P.list[(rounds + 1) & 1];
         int* nextCount = &P.listCount[(rounds + 1) & 3];
@@ -270,9 +271,9 @@ int colour_schedule_build(phyx_b200_ctx* c)
     const int colours = c->part.ranks > 1 ? c->partColours : c->coloursInUse;
     // every colour is a level = a grid barrier and a latency chain per pass (~8-10 us x 22 passes on the bench scene),
     // a full rebuild costs about a millisecond once: rebuild as soon as the incremental colouring has drifted two
-    // colours above the last full build (PHYX_COLOUR_DRIFT overrides the slack)
-    static const int drift = getenv("PHYX_COLOUR_DRIFT") ? atoi(getenv("PHYX_COLOUR_DRIFT")) : 1;
-    if (st == PHYX_B200_OK && incremental && (changed || colours > c->coloursAtFullBuild + drift))
+    // colours above the last full build (kColourDrift; a deferred step takes the same decision on the device and stops)
+    if (c->def.active) return st;
+    if (st == PHYX_B200_OK && incremental && (changed || colours > c->coloursAtFullBuild + kColourDrift))
         st = colour_units_build(c, false, &changed);
     return st;
 }
@@ -321,7 +322,8 @@ static int colour_joints_build(phyx_b200_ctx* c, bool* staticsChanged)
     const int grid = (nj + kBlock - 1) / kBlock;
     if (nb > 0)
     {
-        k_colour_body_flags<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, c->params.as<float4>(), c->bodyStatic.as<unsigned char>(), incremental, result);
+        k_colour_body_flags<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->count(nb, &StepCtl::bodies), c->params.as<float4>(),
+            c->bodyStatic.as<unsigned char>(), incremental, result);
         c->launches++;
     }
     k_colour_init<<<grid, kBlock, 0, c->stream>>>(nj, nb, c->contactPointCount, c->joints.as<phyx_contact_joint>(), c->params.as<float4>(), jb, colour,
@@ -334,7 +336,7 @@ static int colour_joints_build(phyx_b200_ctx* c, bool* staticsChanged)
         PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_colour_rounds, kBlock, 0));
         c->colourBlocksPerSM = per > 0 ? per : 1;
     }
-    ColourParams P = { nj, jb, colour, claim, used, { reinterpret_cast<int*>(base + oList0), reinterpret_cast<int*>(base + oList1) },
+    ColourParams P = { nj, nullptr, jb, colour, claim, used, { reinterpret_cast<int*>(base + oList0), reinterpret_cast<int*>(base + oList1) },
         reinterpret_cast<int*>(base + oListCount), barrier, result, nullptr };
     int cgrid = std::max(1, std::min(grid, c->numSMs * c->colourBlocksPerSM));
     void* args[] = { &P };
@@ -406,12 +408,12 @@ __device__ __forceinline__ int unit_hint(float4 p1, float2 s1, float4 p2, float2
     return 2 * layer + (hi.z > lo.z ? 1 : 0);
 }
 
-__global__ void __launch_bounds__(kBlock) k_unit_init(int M, const int2* __restrict__ manBody, const int* __restrict__ manCount,
+__global__ void __launch_bounds__(kBlock) k_unit_init(Count Mc, const int2* __restrict__ manBody, const int* __restrict__ manCount,
     const float4* __restrict__ params, const float2* __restrict__ size, int* __restrict__ manColour, int2* __restrict__ jb, int* __restrict__ work,
     int* __restrict__ hint, unsigned long long* __restrict__ bodyUsed, bool keepColours)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= M) return;
+    if (m >= count_of(Mc)) return;
     int2 b = manBody[m];
     const float4 p1 = params[b.x], p2 = params[b.y];
     if (hint) hint[m] = unit_hint(p1, size[b.x], p2, size[b.y]);
@@ -787,12 +789,13 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
     const int grid = (M + kBlock - 1) / kBlock;
     if (nb > 0)
     {
-        k_colour_body_flags<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, c->params.as<float4>(), c->bodyStatic.as<unsigned char>(), incremental, result);
+        k_colour_body_flags<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->count(nb, &StepCtl::bodies), c->params.as<float4>(),
+            c->bodyStatic.as<unsigned char>(), incremental, result);
         c->launches++;
     }
-    static const bool useHints = getenv("PHYX_COLOUR_HINTS") && !strcmp(getenv("PHYX_COLOUR_HINTS"), "1");
-    int* hint = useHints ? reinterpret_cast<int*>(base + oHint) : nullptr;
-    k_unit_init<<<grid, kBlock, 0, c->stream>>>(M, c->manBody.as<int2>(), c->manCount.as<int>(), c->params.as<float4>(), c->size.as<float2>(),
+    int* hint = nullptr;   // (geometric colour hints: a measured round-1 experiment, not used)
+    (void)oHint;
+    k_unit_init<<<grid, kBlock, 0, c->stream>>>(c->count(M, &StepCtl::manifolds), c->manBody.as<int2>(), c->manCount.as<int>(), c->params.as<float4>(), c->size.as<float2>(),
         c->manColour.as<int>(), jb, work, hint, used, incremental);
     c->launches++;
 
@@ -802,7 +805,7 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
         PHYX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_colour_rounds, kBlock, 0));
         c->colourBlocksPerSM = per > 0 ? per : 1;
     }
-    ColourParams P = { M, jb, work, claim, used, { reinterpret_cast<int*>(base + oList0), reinterpret_cast<int*>(base + oList1) },
+    ColourParams P = { M, c->def.active ? &c->ctl()->manifolds : nullptr, jb, work, claim, used, { reinterpret_cast<int*>(base + oList0), reinterpret_cast<int*>(base + oList1) },
         reinterpret_cast<int*>(base + oListCount), barrier, result, hint };
     int cgrid = std::max(1, std::min(grid, c->numSMs * c->colourBlocksPerSM));
     void* args[] = { &P };
@@ -819,7 +822,8 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
     // (a manifold across non-adjacent strips, a strip too large for shared memory) fall through to colour-major
     c->strip.valid = false;
     c->hostLevelsStale = false;
-    int S = c->forceKernelForm == 1 || c->forceKernelForm == 2 ? 0 : strip_choose(c, M, nb);
+    // (deferred step: the strip count of the previous layout; the verdict on the layout is taken on the device, strips.cu)
+    int S = c->def.active ? c->strip.strips : c->forceKernelForm == 1 || c->forceKernelForm == 2 ? 0 : strip_choose(c, M, nb);
     if (S > 0)
     {
         int res[4] = { 0, 0, 0, 0 };
@@ -827,6 +831,18 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
         for (;;)
         {
             PHYX_TRY(strip_layout(c, S, jb, work, result, res, &usable));   // waits for the layout header and the colouring's result words
+            if (c->def.active)
+            {
+                // bounds until the step's counts come home (deferred_finish, api.cu)
+                c->def.colourResult = result;
+                c->slotCount = 2 * M;
+                c->levelCount = std::max(1, c->strip.colours);   // (the previous layout's; the solve only asks whether there are any)
+                c->colourStateValid = true;
+                c->colourStateBodies = nb;
+                c->hostSlotsStale = true;
+                c->hostLevelsStale = true;
+                return PHYX_B200_OK;
+            }
             // strips narrower than the bodies' reach (a manifold across non-adjacent strips, a row in two cut sets): try
             // half as many, and remember what worked for the next steps of this world (one strip always works, if it fits)
             if (usable || c->strip.want > 0 || S == 1 || !(c->strip.rejected & 3)) break;

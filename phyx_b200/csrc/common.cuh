@@ -59,6 +59,7 @@ constexpr int kBodyMask = kStaticBit - 1;
 
 constexpr int kMaxRanks = 8;              // devices one world can be partitioned over
 constexpr int kMaxColours = 64;           // colours per class of the schedule
+constexpr int kColourDrift = 1;           // the incremental colouring is rebuilt when it uses this many colours more than the last full build
 
 // Partition of one world's solve over `ranks` devices (partition.cu).  Every rank holds the whole world and runs
 // the collider stages redundantly (they are deterministic, so the replicas stay bit-identical); the solve is
@@ -103,7 +104,72 @@ struct StripPlan
     int rejected = 0;          // why the last layout attempt was not usable (bit mask, see strips.cu), 0 = usable
     DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, header, sync, hist, trace, pairTest, cost, factor, prevCuts;
     int feedbackStrips = 0, feedbackBodies = 0;   // the balance feedback (measured cost per strip) belongs to this layout shape
+    bool measuredFeedback = true;   // phyx_b200_strip_feedback: balance the cuts by the measured cost of the previous solve's strips
     int tracePasses = 0;       // developer aid (phyx_b200_strip_trace): passes of the next solves to time-stamp per CTA
+};
+
+// ---- deferred step (phyx_b200_world_step): the counts of a step in flight live on the device -----------------------
+// The stage functions of the C ABI return their counts (pairs, manifolds, joints) to the host, which costs a read-back
+// per stage.  A whole World::Update issued through phyx_b200_world_step keeps them in this block instead: the host
+// sizes buffers and grids by UPPER BOUNDS predicted from the previous step, every kernel reads the true count from
+// here, and ONE read-back at the end of the step brings all of them home.  A count that outgrows its bound stops the
+// step on the device (every later kernel sees zero counts); the host then finishes it with the stage functions.
+struct StepCtl
+{
+    int bodies, manifolds, joints, slots;      // live counts (zeroed by a stop; `saved` keeps them)
+    int items, newPairs, appendFirst, packed;  // sweep work items, new pairs, first manifold slot of the append, survivors of the pack
+    int fresh, jointsGrown, jointsKept, stop;  // new joints, joints before the cleanup, after it; stage that stopped the step (0 = none)
+    int stopNeed, stopReason, pad0, pad1;
+    int saved[4];                              // bodies, manifolds, joints, slots at the moment of the stop
+    unsigned long long tests, hits;            // sweep totals
+    int created, deleted, pad2, pad3;
+};
+static_assert(sizeof(StepCtl) == 112, "StepCtl layout");
+
+enum StepStage { kStageNone = 0, kStagePairs = 3, kStageRefresh = 6, kStageSolve = 7 };   // numbered as in World::Update
+
+// a count a kernel receives: the host's value (stage functions) or a device word times `mul` (deferred step; v is then the bound
+// the grid was sized by)
+struct Count
+{
+    int v;
+    const int* p;
+    int mul;
+    __host__ __device__ Count(int value = 0) : v(value), p(nullptr), mul(1) {}   // a plain host count converts silently
+    __host__ __device__ Count(int bound, const int* word, int times) : v(bound), p(word), mul(times) {}
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ int count_of(const Count& c) { return c.p ? min(__ldcg(c.p) * c.mul, c.v) : c.v; }
+// stop the step in flight: later kernels see zero counts
+__device__ __forceinline__ void ctl_stop(StepCtl* ctl, int stage, int need, int reason)
+{
+    if (ctl->stop) return;
+    ctl->stop = stage;
+    ctl->stopNeed = need;
+    ctl->stopReason = reason;
+    ctl->saved[0] = ctl->bodies;
+    ctl->saved[1] = ctl->manifolds;
+    ctl->saved[2] = ctl->joints;
+    ctl->saved[3] = ctl->slots;
+    ctl->bodies = ctl->manifolds = ctl->joints = ctl->slots = 0;
+    ctl->items = ctl->newPairs = ctl->packed = ctl->fresh = ctl->jointsGrown = ctl->jointsKept = 0;
+}
+#endif
+
+// host side of the deferred step
+struct Deferred
+{
+    bool enabled = true;       // phyx_b200_step_mode
+    bool tight = false;        // test mode (step_mode 2): bounds without headroom
+    bool active = false;       // a deferred step is being issued: the context's counts are upper bounds
+    bool ctlStale = true;      // the device block does not hold the host's counts (a stage function changed them)
+    int capItems = 0, capNewPairs = 0, capFresh = 0;   // bounds of this step
+    int rowCap = 0, cutCap = 0, workCap = 0;           // shared-memory shape of the strip kernel, from the previous layouts
+    float baseRows = 0.f, baseCut = 0.f, baseBin = 0.f; // ... their running maxima (strips.cu strip_predict_caps)
+    int lastItems = 0, lastNewPairs = 0, lastFresh = 0;
+    int64_t steps = 0, stops = 0, ineligible = 0;      // statistics
+    int lastStopStage = 0, lastStopReason = 0;
+    const int* colourResult = nullptr;                 // device words of the colouring's result (colour.cu), read back with the step
 };
 
 } // namespace phyx
@@ -134,6 +200,8 @@ struct phyx_b200_ctx
     phyx::DevBuf sortA, sortB;   // uint2 {key, index}
     phyx::DevBuf hist;           // per-block digit counts / offsets
     phyx::DevBuf scanTmp;
+    unsigned scanEpoch = 0;      // scan.cu: tag of the current scan's status words
+    void* scanTmpCleared = nullptr;
     phyx::DevBuf entry;          // float4 {minx, maxx, centery, extenty}, sorted order
     phyx::DevBuf entryIndex;     // uint32 body index, sorted order
     phyx::DevBuf sweepEnd;       // int: end_i
@@ -224,6 +292,16 @@ struct phyx_b200_ctx
 
     // ---- one world over several devices (partition.cu; SURVEY.md §8e: an island that spans devices) -----
     phyx::Partition part;
+
+    // ---- deferred step -------------------------------------------------------------------------------------
+    phyx::DevBuf ctlBuf;         // StepCtl
+    phyx::Deferred def;
+    phyx::StepCtl* ctl() const { return ctlBuf.as<phyx::StepCtl>(); }
+    // a count for a kernel launch: the host value, or (deferred step) the device word with the host value as the bound
+    phyx::Count count(int hostValue, int phyx::StepCtl::*field, int mul = 1) const
+    {
+        return def.active ? phyx::Count(hostValue, &(ctl()->*field), mul) : phyx::Count(hostValue);
+    }
 };
 
 namespace phyx
@@ -241,6 +319,7 @@ int broadphase_update(phyx_b200_ctx* c);
 int broadphase_sweep(phyx_b200_ctx* c, phyx_b200_broadphase_stats* stats, bool filter);
 // one stable LSD pass over {key, value} pairs on `digits` (power of two <= 2048) bins of key >> shift
 int radix_pass(phyx_b200_ctx* c, const uint2* src, uint2* dst, int n, int shift, int digits);
+int radix_pass_count(phyx_b200_ctx* c, const uint2* src, uint2* dst, Count n, int shift, int digits);
 
 // colour.cu
 int colour_schedule_build(phyx_b200_ctx* c);
@@ -258,6 +337,8 @@ int strip_choose(const phyx_b200_ctx* c, int manifolds, int bodies);
 int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const int* colourResult, int* colourResultHost, bool* usable);
 int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, float4* rowsVel, float4* rowsDisp);
 int strip_host_levels(phyx_b200_ctx* c, std::vector<int>* classStart);
+bool strip_apply_header(phyx_b200_ctx* c, const int* host16);
+bool strip_predict_caps(phyx_b200_ctx* c, int* rowCap, int* cutCap, int* workCap);
 void strip_release(phyx_b200_ctx* c);
 
 // schedule.cu
@@ -283,6 +364,7 @@ int collide_pack_manifolds(phyx_b200_ctx* c);
 int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* deleted);
 int collide_reset(phyx_b200_ctx* c);
 int collide_rebuild_pair_table(phyx_b200_ctx* c);
+int collide_rebuild_pair_table_for(phyx_b200_ctx* c, int manifolds);   // sized for this many manifolds
 
 // api.cu: small device -> host read-backs (see phyx_b200_ctx::mailboxHost).  stage() enqueues a copy of `bytes` (a multiple of 4, the
 // sum of all staged pieces <= 3.5 KB) to byte offset `offset` of the mailbox; wait() raises the flag and spins until it arrives;
@@ -295,4 +377,5 @@ int fetch_small(phyx_b200_ctx* c, const void* dev, size_t bytes, void* out);
 
 // scan.cu
 int exclusive_scan_i32(phyx_b200_ctx* c, const int* in, int* out, int n, int* totalDevice /* may be null */);
+int exclusive_scan_count(phyx_b200_ctx* c, const int* in, int* out, Count n, int* totalDevice /* may be null */);
 } // namespace phyx

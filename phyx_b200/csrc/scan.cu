@@ -46,15 +46,37 @@ __device__ __forceinline__ int block_exclusive(int v, int* total)
 // about fourteen scans, which used to be 40 launches).  Tiles are taken in ticket order, so a tile only ever waits for
 // tiles whose CTAs are already running.  status[t] = flag << 32 | value: flag 1 = the tile's own total is there,
 // 2 = the inclusive prefix up to and including the tile is.  Integer sums: the result does not depend on who adds what.
-__global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restrict__ in, int n, int* __restrict__ out, unsigned long long* __restrict__ status,
-    unsigned* __restrict__ ticket, int* __restrict__ totalOut)
+// The status words carry the scan's EPOCH (a per-context call counter) in their upper 30 bits, so words left by earlier
+// scans read as "not there yet" and nothing has to be cleared between scans; the CTA that finishes last puts the ticket
+// counter back to zero.  (A memset per scan was a quarter of a small world's step: fourteen scans, each a few microseconds.)
+__device__ __forceinline__ void scan_leave(unsigned* ticket)
+{
+    // ticket[0] = next tile, ticket[1] = CTAs done
+    if (threadIdx.x == 0 && atomicAdd(&ticket[1], 1u) == gridDim.x - 1)
+    {
+        ticket[0] = 0u;
+        ticket[1] = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restrict__ in, Count nc, int* __restrict__ out, unsigned long long* __restrict__ status,
+    unsigned* __restrict__ ticket, int* __restrict__ totalOut, unsigned epoch)
 {
     __shared__ int total;
     __shared__ unsigned s_tile;
     __shared__ int s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    const int n = count_of(nc);
+    const unsigned long long tag = static_cast<unsigned long long>(epoch) << 34;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ticket[0], 1u);
     __syncthreads();
     const int tile = int(s_tile);
+    // (a length read from the device may be shorter than the grid was sized for: tiles past the end have no successors that matter)
+    if (tile * kScanTile >= n)
+    {
+        if (tile == 0 && threadIdx.x == 0 && totalOut) *totalOut = 0;
+        scan_leave(ticket);
+        return;
+    }
     const int base = tile * kScanTile + threadIdx.x * kScanItems;
     int v[kScanItems];
     int s = 0;
@@ -69,7 +91,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restr
     if (threadIdx.x == 0)
     {
         volatile unsigned long long* st = status;
-        st[tile] = ((tile == 0 ? 2ull : 1ull) << 32) | mine;
+        st[tile] = tag | ((tile == 0 ? 2ull : 1ull) << 32) | mine;
     }
     if (threadIdx.x < 32)
     {
@@ -83,9 +105,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restr
             unsigned long long w = 0;
             if (idx >= 0)
             {
-                do { w = st[idx]; } while ((w >> 32) == 0ull);
+                do { w = st[idx]; } while ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0ull);
             }
-            const unsigned flag = idx >= 0 ? unsigned(w >> 32) : 0u;
+            const unsigned flag = idx >= 0 ? unsigned(w >> 32) & 3u : 0u;
             const unsigned full = __ballot_sync(0xffffffffu, flag == 2u);   // lanes that saw a complete prefix
             // add everything up to and including the nearest complete prefix
             const int stop = full ? __ffs(full) - 1 : 31;
@@ -98,7 +120,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restr
         }
         if (threadIdx.x == 0)
         {
-            if (tile > 0) st[tile] = (2ull << 32) | unsigned(prefix + mine);
+            if (tile > 0) st[tile] = tag | (2ull << 32) | unsigned(prefix + mine);
             s_prefix = int(prefix);
         }
     }
@@ -111,11 +133,23 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restr
         run += v[k];
     }
     if (totalOut && base <= n - 1 && n - 1 < base + kScanItems) *totalOut = run;   // the thread that holds the last element
+    scan_leave(ticket);
 }
 
 // in and out may alias.  If totalDevice is non-null it receives the grand total.
 int exclusive_scan_i32(phyx_b200_ctx* c, const int* in, int* out, int n, int* totalDevice)
 {
+    Count nc;
+    nc.v = n;
+    nc.p = nullptr;
+    nc.mul = 1;
+    return exclusive_scan_count(c, in, out, nc, totalDevice);
+}
+
+// the same with the length as a Count (deferred step: n.v is the bound, the device word the length)
+int exclusive_scan_count(phyx_b200_ctx* c, const int* in, int* out, Count nc, int* totalDevice)
+{
+    const int n = nc.v;
     if (n <= 0)
     {
         if (totalDevice) PHYX_CUDA(cudaMemsetAsync(totalDevice, 0, sizeof(int), c->stream));
@@ -124,10 +158,17 @@ int exclusive_scan_i32(phyx_b200_ctx* c, const int* in, int* out, int n, int* to
     const int tiles = (n + kScanTile - 1) / kScanTile;
     const size_t bytes = (size_t(tiles) + 2) * sizeof(unsigned long long);
     PHYX_TRY(c->scanTmp.reserve(bytes));
-    PHYX_CUDA(cudaMemsetAsync(c->scanTmp.ptr, 0, bytes, c->stream));
+    c->scanEpoch = (c->scanEpoch + 1u) & 0x3fffffffu;
+    if (c->scanTmp.ptr != c->scanTmpCleared || c->scanEpoch == 0u)
+    {
+        // a new buffer, or the epoch counter has wrapped: start from clean words (epoch 0 is never used for a scan)
+        PHYX_CUDA(cudaMemsetAsync(c->scanTmp.ptr, 0, c->scanTmp.cap, c->stream));
+        c->scanTmpCleared = c->scanTmp.ptr;
+        if (c->scanEpoch == 0u) c->scanEpoch = 1u;
+    }
     unsigned long long* status = c->scanTmp.as<unsigned long long>() + 1;
     unsigned* ticket = c->scanTmp.as<unsigned>();
-    k_scan_single<<<tiles, kScanThreads, 0, c->stream>>>(in, n, out, status, ticket, totalDevice);
+    k_scan_single<<<tiles, kScanThreads, 0, c->stream>>>(in, nc, out, status, ticket, totalDevice, c->scanEpoch);
     c->launches++;
     PHYX_CUDA(cudaGetLastError());
     return PHYX_B200_OK;

@@ -92,12 +92,12 @@ __device__ __forceinline__ void refresh_limiter(float n1x, float n1y, float w1x,
 // sorted-x order (order[i] = body at sorted position i), so joints that are neighbours in the slot
 // order (sweep order) gather neighbouring rows: the gather / scatter of body rows through L1 is what
 // bounds the iterations (one 32-byte sector per lane when the rows are scattered).
-__global__ void __launch_bounds__(kBlock) k_prepare_bodies(int n, const unsigned* __restrict__ order, const float4* __restrict__ vel,
+__global__ void __launch_bounds__(kBlock) k_prepare_bodies(Count nc, const unsigned* __restrict__ order, const float4* __restrict__ vel,
     const float4* __restrict__ disp, float4* __restrict__ rowsVel, float4* __restrict__ rowsDisp, const unsigned char* __restrict__ multi,
     unsigned char* __restrict__ rowsMulti)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= count_of(nc)) return;
     const unsigned b = order ? order[i] : unsigned(i);
     if (multi) rowsMulti[i] = multi[b];
     float4 v = vel[b], d = disp[b];
@@ -107,11 +107,11 @@ __global__ void __launch_bounds__(kBlock) k_prepare_bodies(int n, const unsigned
     rowsDisp[i] = d;
 }
 
-__global__ void __launch_bounds__(kBlock) k_finish_bodies(int n, const unsigned* __restrict__ order, const float4* __restrict__ rowsVel,
+__global__ void __launch_bounds__(kBlock) k_finish_bodies(Count nc, const unsigned* __restrict__ order, const float4* __restrict__ rowsVel,
     const float4* __restrict__ rowsDisp, float4* __restrict__ vel, float4* __restrict__ disp, int* __restrict__ activity)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= count_of(nc)) return;
     const unsigned b = order ? order[i] : unsigned(i);
     if (activity) activity[b] = __float_as_int(rowsVel[i].w);   // last productive impulse iteration: next step's strip balance
     vel[b] = rowsVel[i];
@@ -119,13 +119,13 @@ __global__ void __launch_bounds__(kBlock) k_finish_bodies(int n, const unsigned*
 }
 
 // ---- PrepareJoints copy + RefreshJoints ----------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __restrict__ slotJoint, const phyx_contact_joint* __restrict__ joints,
+__global__ void __launch_bounds__(kBlock) k_refresh(Count numSlotsC, const int* __restrict__ slotJoint, const phyx_contact_joint* __restrict__ joints,
     const float4* __restrict__ contactPoints, const float4* __restrict__ params, const int* __restrict__ rowOf, float4* __restrict__ q0,
     float4* __restrict__ q1, float4* __restrict__ q2, float4* __restrict__ q3, float2* __restrict__ accNF, float* __restrict__ accD,
     float4* __restrict__ pairQ, int2* __restrict__ pairIdx, int firstSlot, bool writeIdx)
 {
     int s = firstSlot + blockIdx.x * blockDim.x + threadIdx.x;   // slots [firstSlot, numSlots)
-    if (s >= numSlots) return;
+    if (s >= count_of(numSlotsC)) return;
     int j = slotJoint[s];
     if (j < 0)
     {
@@ -190,11 +190,11 @@ __global__ void __launch_bounds__(kBlock) k_refresh(int numSlots, const int* __r
 }
 
 // ---- FinishJoints ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_finish(int numSlots, const int* __restrict__ slotJoint, const float2* __restrict__ accNF,
+__global__ void __launch_bounds__(kBlock) k_finish(Count numSlotsC, const int* __restrict__ slotJoint, const float2* __restrict__ accNF,
     phyx_contact_joint* __restrict__ joints)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= numSlots) return;
+    if (s >= count_of(numSlotsC)) return;
     int j = slotJoint[s];
     if (j < 0) return;
     float2 a = accNF[s];
@@ -1102,13 +1102,15 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         float4* rowsDisp = rowsVel + nb;
         const bool dual = c->strictLevelCount > 0 && c->slotPosValid;
         if (dual) PHYX_TRY(c->rowsMulti.reserve(size_t(nb)));
-        k_prepare_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, c->vel.as<float4>(), c->disp.as<float4>(), rowsVel, rowsDisp,
+        // (deferred step: ns is a bound, the true slot count is StepCtl::slots; a stopped step has zero counts everywhere)
+        const Count nbc = c->count(nb, &StepCtl::bodies), nsc = c->count(ns, &StepCtl::slots);
+        k_prepare_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nbc, order, c->vel.as<float4>(), c->disp.as<float4>(), rowsVel, rowsDisp,
             dual ? c->staticMulti.as<unsigned char>() : nullptr, dual ? c->rowsMulti.as<unsigned char>() : nullptr);
         c->launches++;
         int grid = (ns + kBlock - 1) / kBlock;
         c->lastKernelForm = strips ? 3 : records ? 2 : paired ? 1 : 0;
         // the strip layout writes its own index words (rows local to a strip's shared memory)
-        k_refresh<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
+        k_refresh<<<grid, kBlock, 0, c->stream>>>(nsc, c->slotJoint.as<int>(), c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>(),
             c->params.as<float4>(), rowOf, c->q0.as<float4>(), c->q1.as<float4>(), c->q2.as<float4>(), c->q3.as<float4>(), c->accNF.as<float2>(),
             c->accD.as<float>(), records ? c->pairQ.as<float4>() : nullptr, records ? c->pairIdx.as<int2>() : nullptr, 0, !strips);
         c->launches++;
@@ -1173,14 +1175,15 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
             c->launches++;
         }
         PHYX_CUDA(cudaEventRecord(e2, c->stream));
-        k_finish<<<grid, kBlock, 0, c->stream>>>(ns, c->slotJoint.as<int>(), c->accNF.as<float2>(), c->joints.as<phyx_contact_joint>());
+        k_finish<<<grid, kBlock, 0, c->stream>>>(nsc, c->slotJoint.as<int>(), c->accNF.as<float2>(), c->joints.as<phyx_contact_joint>());
         PHYX_TRY(c->bodyActivity.reserve(size_t(nb) * sizeof(int)));
-        k_finish_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nb, order, rowsVel, rowsDisp, c->vel.as<float4>(), c->disp.as<float4>(),
+        k_finish_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nbc, order, rowsVel, rowsDisp, c->vel.as<float4>(), c->disp.as<float4>(),
             c->bodyActivity.as<int>());
         c->activityValid = true;
         c->activityBodies = nb;
         c->launches += 2;
         PHYX_CUDA(cudaEventRecord(e3, c->stream));
+        if (c->def.active) return PHYX_B200_OK;   // the results come home with the step's counts (deferred_finish, api.cu)
         int host[8];   // result[0..2], pad, activeTotal[2] as two 64-bit words
         PHYX_TRY(fetch_small(c, P.result, sizeof(host), host));
         PHYX_CUDA(cudaEventSynchronize(e3));   // (complete by now: the read-back was enqueued behind it)

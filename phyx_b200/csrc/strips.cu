@@ -95,7 +95,7 @@ __device__ __forceinline__ bool manifold_is_mine(const unsigned char* __restrict
     return !bodyOwner || max(bodyOwner[bodies.x], bodyOwner[bodies.y]) == rank;
 }
 
-__global__ void __launch_bounds__(kBlock) k_strip_hist(int M, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
+__global__ void __launch_bounds__(kBlock) k_strip_hist(Count Mc, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
     const int* __restrict__ activity, const int2* __restrict__ manBody, const unsigned char* __restrict__ bodyOwner, int rank, int* __restrict__ hist,
     int* __restrict__ cover, int prevS, const int* __restrict__ prevCuts, const float* __restrict__ factor, int* __restrict__ header)
 {
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(kBlock) k_strip_hist(int M, const int2* __rest
         s_hi = 0;
     }
     __syncthreads();
+    const int M = count_of(Mc);
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     int r1 = -1, r2 = -1, home = -1;
     int2 b = make_int2(-1, -1);
@@ -166,19 +167,37 @@ __global__ void __launch_bounds__(kBlock) k_strip_hist(int M, const int2* __rest
 // its CTA spent working) and the next layout scales the weights of the manifolds that lived in strip k by factor[k], a
 // damped running product of (cost of strip k / mean cost).  Strips move from step to step, so factors are looked up by
 // row through the previous cuts and re-sampled onto the new cuts afterwards.
-__global__ void k_strip_feedback(int S, const long long* __restrict__ cost, float* __restrict__ factor)
+// (out of place: the factors of the last layout stay untouched until k_strip_commit, so a deferred step that stops after
+// the layout can be laid out again by the stage path from the same state)
+__global__ void k_strip_feedback(int S, const long long* __restrict__ cost, const float* __restrict__ factor, float* __restrict__ factorOut, bool useCost)
 {
     __shared__ float s_sum;
     if (threadIdx.x == 0) s_sum = 0.f;
     __syncthreads();
     for (int k = threadIdx.x; k < S; k += blockDim.x) atomicAdd(&s_sum, float(cost[k]));
     __syncthreads();
-    const float mean = s_sum / float(S);
-    if (mean <= 0.f) return;
+    const float mean = useCost ? s_sum / float(S) : 0.f;   // (measured feedback switched off: the factors stay what they are)
     for (int k = threadIdx.x; k < S; k += blockDim.x)
     {
-        const float ratio = fminf(fmaxf(float(cost[k]) / mean, 0.5f), 2.0f);
-        factor[k] = fminf(fmaxf(factor[k] * sqrtf(ratio), 0.25f), 4.0f);
+        float f = factor[k];
+        if (mean > 0.f)
+        {
+            const float ratio = fminf(fmaxf(float(cost[k]) / mean, 0.5f), 2.0f);
+            f = fminf(fmaxf(f * sqrtf(ratio), 0.25f), 4.0f);
+        }
+        factorOut[k] = f;
+    }
+}
+
+// the new layout's balance state becomes the current one (not for a deferred step that has stopped)
+__global__ void k_strip_commit(const StepCtl* ctl, int S, const float* __restrict__ factorNext, const int* __restrict__ cutsNext, float* __restrict__ factor,
+    int* __restrict__ prevCuts)
+{
+    if (ctl && ctl->stop) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= S; k += gridDim.x * blockDim.x)
+    {
+        prevCuts[k] = cutsNext[k];
+        if (k < S) factor[k] = factorNext[k];
     }
 }
 
@@ -285,13 +304,14 @@ __device__ __forceinline__ int strip_of(const int* cuts, int S, int row)
 
 // classify, persist the colours, emit {class << 7 | colour, manifold} sort keys, flag the rows cut manifolds touch
 // (flags[row]: bit 0 = right-boundary row of its strip, bit 1 = left-boundary row)
-__global__ void __launch_bounds__(kBlock) k_strip_keys(int M, int S, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
+__global__ void __launch_bounds__(kBlock) k_strip_keys(Count Mc, int S, const int2* __restrict__ jb, const int* __restrict__ work, const int* __restrict__ rowOf,
     const int* __restrict__ cutsG, const int2* __restrict__ manBody, const unsigned char* __restrict__ bodyOwner, int rank, int* __restrict__ manColour,
     uint2* __restrict__ keys, int* __restrict__ flags, int* __restrict__ header)
 {
     extern __shared__ int s_cuts[];
     for (int q = threadIdx.x; q <= S; q += blockDim.x) s_cuts[q] = cutsG[q];
     __syncthreads();
+    const int M = count_of(Mc);
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     bool coloured = false, cut = false;
     int colour = 0;
@@ -387,11 +407,12 @@ __global__ void __launch_bounds__(kBlock) k_strip_starts(int nb, int S, const in
 }
 
 // sorted position p = manifold slot p (joint slots 2p, 2p+1): joints, index words, bin table
-__global__ void __launch_bounds__(kBlock) k_strip_place(int M, int S, const uint2* __restrict__ sorted, const int2* __restrict__ manBody,
+__global__ void __launch_bounds__(kBlock) k_strip_place(Count Mc, int S, const uint2* __restrict__ sorted, const int2* __restrict__ manBody,
     const int* __restrict__ manCount, const float4* __restrict__ contactPoints, const int* __restrict__ rowOf, const unsigned char* __restrict__ bodyStatic,
     const int* __restrict__ cuts, const int* __restrict__ prefixR, const int* __restrict__ prefixL, const int* __restrict__ bStart,
     int* __restrict__ slotJoint, int2* __restrict__ pairIdx, unsigned* __restrict__ pairTest, int2* __restrict__ binRange)
 {
+    const int M = count_of(Mc);
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= M) return;
     const uint2 e = sorted[p];
@@ -616,17 +637,44 @@ __global__ void __launch_bounds__(kBlock) k_strip_maxbin(int bins, const int2* _
     if (r.y > r.x) atomicMax(&header[H_MAXBIN], r.y - r.x);
 }
 
+// Deferred step (common.cuh StepCtl): the decisions strip_layout's caller takes on the host after reading the header are
+// taken here, and the step stops when any of them says "not this layout": rejected layout, shared-memory shape above the
+// predicted one, colour overflow, a body that changed between static and dynamic, colour drift (colour.cu).
+__host__ __device__ inline int strip_count_for(int manifolds, int bodies, int numSMs, int autoLimit)
+{
+    int S = manifolds / 1024;
+    S = S < numSMs ? S : numSMs;
+    S = S > 1 ? S : 1;
+    if (autoLimit > 0 && S > autoLimit) S = autoLimit;   // what the last rejected layouts of this world allowed
+    // a strip's rows must fit in shared memory: large worlds get more strips than SMs (several strips per CTA)
+    const int needed = (bodies + kStripRowLimit * 3 / 4 - 1) / (kStripRowLimit * 3 / 4);
+    if (needed > S) S = needed < kStripMax ? needed : kStripMax;
+    return S;
+}
+
+__global__ void k_strip_verdict(StepCtl* ctl, const int* __restrict__ header, const int* __restrict__ colourResult, int rowCap, int cutCap, int workCap,
+    int coloursAtFullBuild, int S, int numSMs, int autoLimit, int bodies)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || ctl->stop) return;
+    int reason = 0;
+    if (strip_count_for(ctl->manifolds, bodies, numSMs, autoLimit) != S) reason = 15;   // the stage path would choose another strip count
+    else if (header[H_REJECT] || header[H_MANIFOLDS] == 0) reason = 10;
+    else if (((header[H_MAXROWS] + 8) & ~7) > rowCap || ((header[H_MAXCUT] + 8) & ~7) > cutCap || ((header[H_MAXBIN] + 8) & ~7) > workCap) reason = 11;
+    else if (colourResult[1]) reason = 12;
+    else if (colourResult[3]) reason = 13;
+    else if (header[H_COLOURS] > coloursAtFullBuild + kColourDrift) reason = 14;
+    if (reason)
+        ctl_stop(ctl, kStageSolve, header[H_MAXROWS], reason);
+    else
+        ctl->slots = 2 * header[H_MANIFOLDS];
+}
+
 // strips for a world of this size: enough manifolds per strip to keep a CTA busy, at most one strip per SM
 int strip_choose(const phyx_b200_ctx* c, int manifolds, int bodies)
 {
     if (c->strip.want < 0) return 0;
     if (c->strip.want > 0) return std::min(c->strip.want, kStripMax);
-    int S = std::max(1, std::min(c->numSMs, manifolds / 1024));
-    if (c->strip.autoLimit > 0) S = std::min(S, c->strip.autoLimit);   // what the last rejected layouts of this world allowed
-    // a strip's rows must fit in shared memory: large worlds get more strips than SMs (several strips per CTA)
-    const int needed = (bodies + kStripRowLimit * 3 / 4 - 1) / (kStripRowLimit * 3 / 4);
-    if (needed > S) S = std::min(needed, kStripMax);
-    return S;
+    return strip_count_for(manifolds, bodies, c->numSMs, c->strip.autoLimit);
 }
 
 static size_t strip_smem_bytes(int rowCap, int cutCap, int workCap)
@@ -678,20 +726,22 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     int* cover = sp.prefixL.as<int>();
     // balance feedback from the previous solve of this world (same strip count, same bodies)
     PHYX_TRY(sp.cost.reserve(size_t(2 * S + 2) * sizeof(long long)));
-    PHYX_TRY(sp.factor.reserve(size_t(2 * S + 2) * sizeof(float)));
+    PHYX_TRY(sp.factor.reserve(size_t(3 * S + 3) * sizeof(float)));
     PHYX_TRY(sp.prevCuts.reserve(size_t(2 * S + 4) * sizeof(int)));
     const bool feedback = sp.feedbackStrips == S && sp.feedbackBodies == nb && activity != nullptr;
     float* factor = sp.factor.as<float>();
     float* factorNext = factor + S + 1;
+    float* factorFb = factor + 2 * (S + 1);   // this step's factors: last layout's x the measured cost of its strips
     int* prevCuts = sp.prevCuts.as<int>();
     int* prevCutsNext = prevCuts + S + 2;
     if (feedback)
     {
-        k_strip_feedback<<<1, 256, 0, c->stream>>>(S, sp.cost.as<long long>(), factor);
+        k_strip_feedback<<<1, 256, 0, c->stream>>>(S, sp.cost.as<long long>(), factor, factorFb, sp.measuredFeedback);
         c->launches++;
     }
-    k_strip_hist<<<grid, kBlock, 0, c->stream>>>(M, jb, work, rowOf, activity, c->manBody.as<int2>(), bodyOwner, c->islandRank, sp.hist.as<int>(), cover, S,
-        feedback ? prevCuts : nullptr, feedback ? factor : nullptr, header);
+    const Count Mc = c->count(M, &StepCtl::manifolds);
+    k_strip_hist<<<grid, kBlock, 0, c->stream>>>(Mc, jb, work, rowOf, activity, c->manBody.as<int2>(), bodyOwner, c->islandRank, sp.hist.as<int>(), cover, S,
+        feedback ? prevCuts : nullptr, feedback ? factorFb : nullptr, header);
     k_strip_hist_rows<<<gridB, kBlock, 0, c->stream>>>(nb, order, c->bodyStatic.as<unsigned char>(), bodyOwner, c->islandRank, sp.hist.as<int>());
     c->launches++;
     PHYX_TRY(exclusive_scan_i32(c, sp.hist.as<int>(), sp.prefixR.as<int>(), nb, header + H_SCAN_TOTAL));
@@ -711,13 +761,21 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     // carry the balance factors over to the new cuts
     if (feedback)
     {
-        k_strip_resample<<<gridS, kBlock, 0, c->stream>>>(S, sp.cuts.as<int>(), prevCuts, factor, factorNext, prevCutsNext);
-        PHYX_CUDA(cudaMemcpyAsync(factor, factorNext, size_t(S) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-        PHYX_CUDA(cudaMemcpyAsync(prevCuts, prevCutsNext, size_t(S + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+        k_strip_resample<<<gridS, kBlock, 0, c->stream>>>(S, sp.cuts.as<int>(), prevCuts, factorFb, factorNext, prevCutsNext);
         c->launches++;
+        if (!c->def.active)
+        {
+            k_strip_commit<<<gridS, kBlock, 0, c->stream>>>(nullptr, S, factorNext, prevCutsNext, factor, prevCuts);
+            c->launches++;
+        }
     }
     else
     {
+        if (c->def.active)
+        {
+            set_error("deferred step without balance feedback (internal: the step was not eligible)");
+            return PHYX_B200_ERR_STATE;
+        }
         std::vector<float> ones(size_t(S), 1.0f);
         PHYX_CUDA(cudaMemcpyAsync(factor, ones.data(), size_t(S) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         PHYX_CUDA(cudaMemcpyAsync(prevCuts, sp.cuts.ptr, size_t(S + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
@@ -730,13 +788,13 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     // classes, sort keys, boundary flags; two stable passes: colour (7 bits), then class
     PHYX_TRY(c->colourKeys.reserve(size_t(M) * sizeof(uint2)));
     PHYX_TRY(c->colourSorted.reserve(size_t(M) * sizeof(uint2)));
-    k_strip_keys<<<grid, kBlock, size_t(S + 1) * sizeof(int), c->stream>>>(M, S, jb, work, rowOf, sp.cuts.as<int>(), c->manBody.as<int2>(), bodyOwner, c->islandRank,
+    k_strip_keys<<<grid, kBlock, size_t(S + 1) * sizeof(int), c->stream>>>(Mc, S, jb, work, rowOf, sp.cuts.as<int>(), c->manBody.as<int2>(), bodyOwner, c->islandRank,
         c->manColour.as<int>(), c->colourKeys.as<uint2>(), flags, header);
     c->launches++;
     int digits = 1;
     while (digits < 2 * S + 1) digits <<= 1;
-    PHYX_TRY(radix_pass(c, c->colourKeys.as<uint2>(), c->colourSorted.as<uint2>(), M, 0, 128));
-    PHYX_TRY(radix_pass(c, c->colourSorted.as<uint2>(), c->colourKeys.as<uint2>(), M, 7, digits));
+    PHYX_TRY(radix_pass_count(c, c->colourKeys.as<uint2>(), c->colourSorted.as<uint2>(), Mc, 0, 128));
+    PHYX_TRY(radix_pass_count(c, c->colourSorted.as<uint2>(), c->colourKeys.as<uint2>(), Mc, 7, digits));
     const uint2* sorted = c->colourKeys.as<uint2>();
 
     // boundary row lists
@@ -754,7 +812,7 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     PHYX_TRY(c->slotJoint.reserve(maxSlots * sizeof(int)));
     PHYX_TRY(c->pairIdx.reserve((size_t(M) + 64) * sizeof(int2)));
     PHYX_TRY(sp.pairTest.reserve((size_t(M) + 64) * sizeof(unsigned)));
-    k_strip_place<<<grid, kBlock, 0, c->stream>>>(M, S, sorted, c->manBody.as<int2>(), c->manCount.as<int>(), c->contactPoints.as<float4>(), rowOf,
+    k_strip_place<<<grid, kBlock, 0, c->stream>>>(Mc, S, sorted, c->manBody.as<int2>(), c->manCount.as<int>(), c->contactPoints.as<float4>(), rowOf,
         c->bodyStatic.as<unsigned char>(), sp.cuts.as<int>(), sp.prefixR.as<int>(), sp.prefixL.as<int>(), sp.bStart.as<int>(), c->slotJoint.as<int>(),
         c->pairIdx.as<int2>(), sp.pairTest.as<unsigned>(), sp.binRange.as<int2>());
     if (S > 1)
@@ -766,6 +824,19 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     c->launches += 2;
     PHYX_CUDA(cudaGetLastError());
 
+    if (c->def.active)
+    {
+        // the verdict is taken on the device; the header comes home with the step's counts (deferred_finish, api.cu)
+        k_strip_verdict<<<1, 32, 0, c->stream>>>(c->ctl(), header, colourResult, c->def.rowCap, c->def.cutCap, c->def.workCap, c->coloursAtFullBuild,
+            S, c->numSMs, sp.autoLimit, nb);
+        k_strip_commit<<<gridS, kBlock, 0, c->stream>>>(c->ctl(), S, factorNext, prevCutsNext, factor, prevCuts);
+        c->launches += 2;
+        PHYX_CUDA(cudaGetLastError());
+        sp.strips = S;
+        sp.valid = true;
+        *usable = true;
+        return PHYX_B200_OK;
+    }
     int host[16];
     PHYX_TRY(mailbox_stage(c, header, sizeof(host), 0));
     if (colourResult) PHYX_TRY(mailbox_stage(c, colourResult, 16, 64));
@@ -774,6 +845,14 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     if (colourResultHost) memcpy(colourResultHost, mailbox_at(c, 64), 16);
 
     sp.strips = S;
+    *usable = strip_apply_header(c, host);
+    return PHYX_B200_OK;
+}
+
+// the layout header (16 words, read back from the device) -> the plan's host fields; true if the layout is usable
+bool strip_apply_header(phyx_b200_ctx* c, const int* host)
+{
+    StripPlan& sp = c->strip;
     sp.maxStripRows = host[H_MAXROWS];
     sp.maxCutRows = host[H_MAXCUT];
     sp.manifolds = host[H_MANIFOLDS];
@@ -785,10 +864,68 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     if (strip_smem_bytes(sp.maxStripRows + 9, sp.maxCutRows + 9, sp.maxBin + 9) > kStripSmemLimit) rejected |= kRejectSmem;
     if (sp.maxStripRows > 65000 || sp.maxCutRows > 65000 || sp.maxBin > 65000) rejected |= kRejectSmem;
     sp.rejected = rejected;
-    if (rejected) return PHYX_B200_OK;
-    sp.valid = true;
-    *usable = true;
-    return PHYX_B200_OK;
+    sp.valid = rejected == 0;
+    return sp.valid;
+}
+
+// Deferred step: the shared-memory shape the strip kernel will be launched with, predicted from the previous layouts
+// (strips move a little from step to step; k_strip_verdict stops the step if the new layout does not fit).  Headroom is
+// free only up to the next shared-memory carve-out of the SM: past it the kernel loses L1 (measured: +20 % kernel time on
+// the 1 M pyramid for 10 KB too much), so the bound grows into the slack of the bucket the exact shape falls into and
+// crosses into the next bucket only for a minimal margin.  False if the previous layout leaves no usable prediction.
+bool strip_predict_caps(phyx_b200_ctx* c, int* rowCap, int* cutCap, int* workCap)
+{
+    const StripPlan& sp = c->strip;
+    if (!sp.valid || sp.strips <= 0) return false;
+    Deferred& d = c->def;
+    // base shape: the largest of the last few layouts (islands hop between strips: the maxima oscillate), slowly forgotten
+    d.baseRows = std::max(float(sp.maxStripRows), d.baseRows * 0.985f);
+    d.baseCut = std::max(float(sp.maxCutRows), d.baseCut * 0.97f);
+    d.baseBin = std::max(float(sp.maxBin), d.baseBin * 0.97f);
+    auto round8 = [](float v) { return (int(v) + 8) & ~7; };
+    const int r0 = std::min(round8(d.baseRows), (kStripRowLimit + 8) & ~7), k0 = round8(d.baseCut), w0 = round8(d.baseBin);
+    if (r0 <= sp.maxStripRows || k0 <= sp.maxCutRows || w0 <= sp.maxBin) return false;
+    auto fits = [](int r, int k, int w) { return strip_smem_bytes(r + 1, k + 1, w + 1) <= kStripSmemLimit && r < 65000 && k < 65000 && w < 65000; };
+    if (!fits(r0, k0, w0)) return false;
+    int r = r0, k = k0, w = w0;
+    if (!d.tight)
+    {
+        // carve-outs of an sm_100 SM (KB); the kernel's static tables and the system's 1 KB come on top of the dynamic part
+        static const int buckets[] = { 8, 16, 32, 64, 100, 132, 164, 196, 228 };
+        const size_t overhead = 5 * 1024, exact = strip_smem_bytes(r0, k0, w0) + overhead;
+        size_t limit = 228 * 1024;
+        for (int b : buckets)
+            if (size_t(b) * 1024 >= exact) { limit = size_t(b) * 1024; break; }
+        // wanted: rows + 6 % + 64, cut rows and bin + 12 % + 128; at least rows + 1 % + 16, the others + 3 % + 32
+        const int rWant = r0 + r0 / 16 + 64, kWant = k0 + k0 / 8 + 128, wWant = w0 + w0 / 8 + 128;
+        const int rMin = r0 + r0 / 100 + 16, kMin = k0 + k0 / 32 + 32, wMin = w0 + w0 / 32 + 32;
+        auto total = [&](int rr, int kk, int ww) { return strip_smem_bytes(rr, kk, ww) + overhead; };
+        // binary search on the share t of (want - min) that still stays inside the bucket
+        r = rMin; k = kMin; w = wMin;
+        int lo = 0, hi = 64;
+        while (lo < hi)
+        {
+            const int mid = (lo + hi + 1) / 2;
+            const int rr = rMin + (rWant - rMin) * mid / 64, kk = kMin + (kWant - kMin) * mid / 64, ww = wMin + (wWant - wMin) * mid / 64;
+            if (total(rr, kk, ww) <= limit) lo = mid; else hi = mid - 1;
+        }
+        r = rMin + (rWant - rMin) * lo / 64;
+        k = kMin + (kWant - kMin) * lo / 64;
+        w = wMin + (wWant - wMin) * lo / 64;
+        r = std::min((r + 7) & ~7, (kStripRowLimit + 8) & ~7);
+        k = (k + 7) & ~7;
+        w = (w + 7) & ~7;
+        while (!fits(r, k, w) && (r > r0 || k > k0 || w > w0))
+        {
+            r = std::max(r0, r - 8);
+            k = std::max(k0, k - 8);
+            w = std::max(w0, w - 8);
+        }
+    }
+    *rowCap = r;
+    *cutCap = k;
+    *workCap = w;
+    return true;
 }
 
 // host copy of the schedule for phyx_b200_get_schedule: one level per non-empty (class, colour) bin, in slot order;
@@ -853,6 +990,7 @@ struct StripParams
     long long* cost;                 // [S] SM clocks this strip's CTA spent working (not waiting for neighbours) in this solve: next step's balance
     unsigned long long* trace;       // developer aid (phyx_b200_strip_trace): [S][tracePasses][8] globaltimer stamps, or null
     int tracePasses;
+    const StepCtl* ctl;              // deferred step: a stopped step (ctl->stop) must not be solved; null otherwise
 };
 
 __device__ __forceinline__ void flag_release(unsigned long long* flag, unsigned long long value)
@@ -1395,6 +1533,7 @@ __global__ void __launch_bounds__(T, 1) k_solve_strips(StripParams P)
     __shared__ int s_n[2];
     __shared__ unsigned long long s_mbar;
 
+    if (P.ctl && P.ctl->stop) return;   // (every CTA reads the same word: the whole grid leaves)
     StripCta s;
     s.s_rows = reinterpret_cast<float4*>(stripSmem);
     s.s_cut = s.s_rows + P.rowCap;
@@ -1406,6 +1545,8 @@ __global__ void __launch_bounds__(T, 1) k_solve_strips(StripParams P)
     s.s_count = s_count;
     const int S = P.S;
     const bool streaming = S > int(gridDim.x);   // more strips than CTAs: rows are staged per visit (run_pass_streaming)
+    if (streaming && threadIdx.x == 0)
+        for (int k = blockIdx.x; k < S; k += gridDim.x) P.cost[k] = 0;   // accumulated per visit (only this CTA touches them)
     s.parity = 0;
     if (threadIdx.x == 0)   // the rows that test words of static bodies and of empty slots point at: lastIteration = never
     {
@@ -1544,9 +1685,11 @@ int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, floa
     P.S = S;
     P.contactIters = I;
     P.penetrationIters = D;
-    P.rowCap = (sp.maxStripRows + 8) & ~7;
-    P.cutCap = (sp.maxCutRows + 8) & ~7;
-    P.workCap = (sp.maxBin + 8) & ~7;
+    // (deferred step: the shape predicted from the previous layout; k_strip_verdict has checked that this layout fits)
+    P.rowCap = c->def.active ? c->def.rowCap : (sp.maxStripRows + 8) & ~7;
+    P.cutCap = c->def.active ? c->def.cutCap : (sp.maxCutRows + 8) & ~7;
+    P.workCap = c->def.active ? c->def.workCap : (sp.maxBin + 8) & ~7;
+    P.ctl = c->def.active ? c->ctl() : nullptr;
     P.result = reinterpret_cast<int*>(c->solveFlags.as<char>() + 32);
     P.activeTotal = reinterpret_cast<unsigned long long*>(c->solveFlags.as<char>() + 48);
     P.cost = sp.cost.as<long long>();
@@ -1567,7 +1710,6 @@ int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, floa
     // every CTA waits for its neighbours: all S must be resident at once, which the cooperative launch guarantees (or refuses)
     void* args[] = { &P };
     // one CTA per strip; a world with more strips than SMs is run by numSMs CTAs, each visiting several strips per pass
-    if (S > c->numSMs) PHYX_CUDA(cudaMemsetAsync(sp.cost.ptr, 0, size_t(S) * sizeof(long long), c->stream));   // (accumulated per visit there)
     PHYX_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_strips<512>, dim3(std::min(S, c->numSMs)), dim3(512), args, smem, c->stream));
     c->launches++;
     return PHYX_B200_OK;

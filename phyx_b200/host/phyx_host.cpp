@@ -198,6 +198,18 @@ NOINLINE void Solver::SolveJoints(WorkQueue&, RigidBody* bodies, int bodiesCount
 {
     StageTimer t(&device->stageMs[6]);
     if (!device->inUpdate) device->upload(bodies, bodiesCount);
+    phyx_b200_solve_config cfg = MakeConfig(configuration);
+    PHYX_CALL(phyx_b200_solve_resident(device->ctx, &cfg, &device->lastSolve));
+    FillIslandCounters(configuration);
+    if (!device->inUpdate)
+    {
+        device->download(bodies, bodiesCount);
+        device->mirror(*collider, *this, collider->mirrorContents);
+    }
+}
+
+phyx_b200_solve_config Solver::MakeConfig(const Configuration& configuration) const
+{
     phyx_b200_solve_config cfg;
     cfg.contactIterationsCount = configuration.contactIterationsCount;
     cfg.penetrationIterationsCount = configuration.penetrationIterationsCount;
@@ -209,7 +221,11 @@ NOINLINE void Solver::SolveJoints(WorkQueue&, RigidBody* bodies, int bodiesCount
     default: cfg.schedule = PHYX_B200_SCHEDULE_COLOUR; break;
     }
     cfg.flags = solveFlags;
-    PHYX_CALL(phyx_b200_solve_resident(device->ctx, &cfg, &device->lastSolve));
+    return cfg;
+}
+
+void Solver::FillIslandCounters(const Configuration& configuration)
+{
     if (configuration.islandMode == Configuration::Island_Multiple || configuration.islandMode == Configuration::Island_MultipleSloppy)
     {
         // GatherIslands (reference src/Solver.cpp:285-454) on the device: the counters the demo's HUD reads.  The solve itself
@@ -223,11 +239,6 @@ NOINLINE void Solver::SolveJoints(WorkQueue&, RigidBody* bodies, int bodiesCount
     {
         islandCount = 1;                   // Island_Single bookkeeping (reference src/Solver.cpp:108-109)
         islandMaxSize = device->lastSolve.joints;
-    }
-    if (!device->inUpdate)
-    {
-        device->download(bodies, bodiesCount);
-        device->mirror(*collider, *this, collider->mirrorContents);
     }
 }
 
@@ -286,18 +297,34 @@ void World::Update(WorkQueue& queue, float dt, const Configuration& configuratio
     device.hostEdited = false;
     device.inUpdate = true;
 
-    IntegrateVelocity(queue, dt);
+    if (device.fusedUpdate && !collider.mirrorBroadphase)
+    {
+        // the eight stages as ONE call into the C ABI (phyx_b200_world_step): same results, no read-back per stage
+        StageTimer t(&device.stepMs);
+        phyx_b200_solve_config cfg = solver.MakeConfig(configuration);
+        phyx_b200_step_info info;
+        PHYX_CALL(phyx_b200_world_step(device.ctx, dt, gravity, &cfg, &device.lastSolve, &device.lastBroadphase, &info));
+        createdJoints = info.deferred ? info.jointsCreated : createdJoints;
+        deletedJoints = info.deferred ? info.jointsDeleted : deletedJoints;
+        matchedJoints = info.deferred ? info.joints - info.jointsCreated : matchedJoints;
+        device.lastStepDeferred = info.deferred != 0;
+        solver.FillIslandCounters(configuration);
+    }
+    else
+    {
+        IntegrateVelocity(queue, dt);
 
-    collider.UpdateBroadphase(bodies.data, bodies.size);
-    collider.UpdatePairs(queue, bodies.data, bodies.size);
-    collider.UpdateManifolds(queue, bodies.data);
-    collider.PackManifolds(bodies.data);
+        collider.UpdateBroadphase(bodies.data, bodies.size);
+        collider.UpdatePairs(queue, bodies.data, bodies.size);
+        collider.UpdateManifolds(queue, bodies.data);
+        collider.PackManifolds(bodies.data);
 
-    RefreshContactJoints();
+        RefreshContactJoints();
 
-    solver.SolveJoints(queue, bodies.data, bodies.size, collider.contactPoints.data, configuration);
+        solver.SolveJoints(queue, bodies.data, bodies.size, collider.contactPoints.data, configuration);
 
-    IntegratePosition(queue, dt);
+        IntegratePosition(queue, dt);
+    }
 
     device.inUpdate = false;
     {

@@ -348,6 +348,9 @@ struct Device
     int residentCount = 0;
     double stageMs[8] = {};    // wall time per stage (reference scope taxonomy)
     double syncMs = 0;         // wall time of the end-of-Update download + mirrors
+    double stepMs = 0;         // wall time of the fused step (phyx_b200_world_step) when World::Update takes it
+    bool fusedUpdate = true;   // World::Update = one phyx_b200_world_step call (false: the eight stage calls, same results)
+    bool lastStepDeferred = false;
     bool pinBodies = true;     // page-lock World::bodies in place for full-rate PCIe copies
     void* pinnedPtr = nullptr;
     size_t pinnedBytes = 0;
@@ -433,6 +436,10 @@ struct Solver
     int islandCount;
     int islandMaxSize;
     AlignedArray<ContactJoint> contactJoints;
+
+    // (not in the reference) Configuration -> the C ABI's solve config; islandCount / islandMaxSize after a solve
+    phyx_b200_solve_config MakeConfig(const Configuration& configuration) const;
+    void FillIslandCounters(const Configuration& configuration);
 
     phyx_host::Device* device = nullptr;
     Collider* collider = nullptr;

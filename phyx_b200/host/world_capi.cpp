@@ -131,7 +131,11 @@ API void phyxw_reset_stage_ms(void* h)
 {
     memset(static_cast<Handle*>(h)->world.device.stageMs, 0, sizeof(double) * 8);
     static_cast<Handle*>(h)->world.device.syncMs = 0;
+    static_cast<Handle*>(h)->world.device.stepMs = 0;
 }
+API double phyxw_get_step_ms(void* h) { return static_cast<Handle*>(h)->world.device.stepMs; }
+API void phyxw_set_fused_update(void* h, int on) { static_cast<Handle*>(h)->world.device.fusedUpdate = on != 0; }
+API int phyxw_last_step_deferred(void* h) { return static_cast<Handle*>(h)->world.device.lastStepDeferred ? 1 : 0; }
 API void phyxw_get_solve_stats(void* h, phyx_b200_solve_stats* out) { *out = static_cast<Handle*>(h)->world.device.lastSolve; }
 API void phyxw_get_broadphase_stats(void* h, phyx_b200_broadphase_stats* out) { *out = static_cast<Handle*>(h)->world.device.lastBroadphase; }
 API void phyxw_get_island_counts(void* h, int* out2)

@@ -200,6 +200,7 @@ class ShardedWorld:
         self.ctx, self.device = ctx, device
         self.rank, self.ranks = dist.get_rank(group), dist.get_world_size(group)
         self.check_every, self.margin, self.steps = check_every, margin, 0
+        self.deferred_steps = 0
         # probe: the contact graph of the full scene after a few full steps, identical on every rank
         import ctypes as C
 
@@ -230,9 +231,9 @@ class ShardedWorld:
     def step(self, iters=(20, 20)):
         from . import capi, scenes
 
-        bp = stages_before_solve(self.ctx)
-        st = self.ctx.solve_resident(iters=iters, schedule=capi.SCHEDULE_COLOUR)
-        self.ctx.integrate_position(scenes.DT)
+        # World::Update of this rank's shard as one C-ABI call (counts stay on the device, one read-back per step)
+        st, bp, info = self.ctx.world_step(scenes.DT, scenes.GRAVITY, iters=iters, schedule=capi.SCHEDULE_COLOUR)
+        self.deferred_steps += int(info.deferred)
         self.steps += 1
         if self.check_every and self.steps % self.check_every == 0:
             self.check_apart()

@@ -52,6 +52,11 @@ def load():
     l.phyxw_sync_bodies.argtypes = [vp]
     l.phyxw_get_sync_ms.argtypes = [vp]
     l.phyxw_get_sync_ms.restype = C.c_double
+    l.phyxw_get_step_ms.argtypes = [vp]
+    l.phyxw_get_step_ms.restype = C.c_double
+    l.phyxw_set_fused_update.argtypes = [vp, i32]
+    l.phyxw_last_step_deferred.argtypes = [vp]
+    l.phyxw_last_step_deferred.restype = i32
     l.phyxw_reset_world.argtypes = [vp]
     l.phyxw_context.argtypes = [vp]
     l.phyxw_get_island_counts.argtypes = [vp, vp]
@@ -129,7 +134,17 @@ class World:
         self.l.phyxw_get_stage_ms(self.h, _p(out))
         d = dict(zip(STAGES, out.tolist()))
         d["sync"] = float(self.l.phyxw_get_sync_ms(self.h))
+        step = float(self.l.phyxw_get_step_ms(self.h))
+        if step > 0.0:
+            d["WorldStep"] = step   # World::Update took the fused path (one C-ABI call for the eight stages)
         return d
+
+    def set_fused_update(self, on):
+        """World::Update through phyx_b200_world_step (default) or through the eight stage calls: same results."""
+        self.l.phyxw_set_fused_update(self.h, int(on))
+
+    def last_step_deferred(self):
+        return bool(self.l.phyxw_last_step_deferred(self.h))
 
     def reset_world(self):
         self.l.phyxw_reset_world(self.h)
