@@ -564,7 +564,7 @@ def run_ours(args, rank, world_size, local_rank):
         # read-back per step.  --stage-calls times the eight stage functions instead (same results, a read-back per stage).
         if not args.stage_calls:
             st, bp, info = timed("WorldStep", ctx.world_step, scenes.DT, scenes.GRAVITY, iters=ITERS, schedule=capi.SCHEDULE_COLOUR)
-            step_infos.append((info.deferred, info.stopStage, info.stopReason))
+            step_infos.append((info.deferred, info.stopStage, info.stopReason, info.graphReplay))
             return bp, st
         return stage_calls_step()
 
@@ -753,11 +753,12 @@ def run_ours(args, rank, world_size, local_rank):
         "spanning": spanning,
         "step_call": {
             "api": "eight stage functions" if args.stage_calls else "phyx_b200_world_step",
-            "deferred_steps": sum(1 for d, _, _ in step_infos_timed if d),
-            "stopped_steps": [[stg, why] for d, stg, why in step_infos_timed if stg],
+            "deferred_steps": sum(1 for d, _, _, _ in step_infos_timed if d),
+            "graph_replays": sum(1 for _, _, _, g in step_infos_timed if g),
+            "stopped_steps": [[stg, why] for d, stg, why, _ in step_infos_timed if stg],
             "host_wall_ms_per_step": round(step_wall.get("WorldStep", 0.0) / args.steps, 3) if not args.stage_calls else None,
             "stage_calls_ms_per_step": stage_calls_ms,
-            "note": "deferred = counts on the device, one read-back per step; a stopped step is finished by the stage functions (reasons: include/phyx_b200.h)",
+            "note": "deferred = counts on the device, one read-back per step; graph replay = the whole step is one CUDA-graph launch (same bounds and buffers as the step before); a stopped step is finished by the stage functions (reasons: include/phyx_b200.h)",
         },
         "resident_stage_wall_ms": {k: round(v / max(stage_steps, 1), 3) for k, v in stage_wall.items()},
         "resident_stage_wall_ms_max": {k: round(v, 3) for k, v in stage_max.items()},

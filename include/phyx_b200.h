@@ -250,6 +250,9 @@ typedef struct {
                                             13 a body changed between static and dynamic, 14 colouring drifted (rebuilt) */
     int32_t manifolds, contactPoints, joints;   /* sizes of Collider::manifolds / contactPoints, Solver::contactJoints after the step */
     int32_t newPairs, jointsCreated, jointsDeleted;
+    int32_t graphReplay;                 /* 1: the step was one CUDA-graph launch (steady state: same bounds and buffers as the step before) */
+    int32_t graphStatus;                 /* why not, when it was not: 0 first step with these launches, 2 captured and launched now,
+                                            3 launches differ from the previous step's (bounds or buffers changed), -1 capture failed */
     int32_t pad_;
     int64_t pairs, tests;                /* overlapping pairs / sweep tests of this step's broadphase */
     int64_t deferredSteps, deferredStops;       /* totals of this context */
@@ -257,7 +260,8 @@ typedef struct {
 PHYX_B200_API int phyx_b200_world_step(phyx_b200_ctx* ctx, float dt, float gravity, const phyx_b200_solve_config* config,
     phyx_b200_solve_stats* solveStats, phyx_b200_broadphase_stats* broadphaseStats, phyx_b200_step_info* info);
 /* deferred = 1 (default): world_step may run steps with device-side counts; 0: it always calls the stage functions;
- * 2: as 1 with bounds that leave no headroom (test aid: every growing count exercises the stop-and-resume path) */
+ * 2: as 1 with bounds that leave no headroom (test aid: every growing count exercises the stop-and-resume path);
+ * 3: as 1 without CUDA-graph replay of the steady-state step */
 PHYX_B200_API int phyx_b200_step_mode(phyx_b200_ctx* ctx, int deferred);
 
 /* resetWorld() clears manifolds, manifoldMap and contactJoints (reference src/main.cpp:86-89) */

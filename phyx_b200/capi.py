@@ -129,6 +129,8 @@ class StepInfo(C.Structure):
         ("newPairs", C.c_int32),
         ("jointsCreated", C.c_int32),
         ("jointsDeleted", C.c_int32),
+        ("graphReplay", C.c_int32),
+        ("graphStatus", C.c_int32),
         ("pad_", C.c_int32),
         ("pairs", C.c_int64),
         ("tests", C.c_int64),
@@ -137,7 +139,7 @@ class StepInfo(C.Structure):
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad_"}
+        return {k: getattr(self, k) for k, _ in self._fields_ }
 
 
 class PhyxError(RuntimeError):

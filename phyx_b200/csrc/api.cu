@@ -41,6 +41,10 @@ static size_t grow_to(size_t bytes, size_t cap)
     return (want + 255) & ~size_t(255);
 }
 
+// allocations of the context the calling thread is working on (set at every API entry): a buffer that moved invalidates the
+// context's captured step graph
+static thread_local long long* t_ctxAllocs = nullptr;
+
 struct AllocTimer
 {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -48,6 +52,7 @@ struct AllocTimer
     {
         g_allocNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         g_allocCount++;
+        if (t_ctxAllocs) ++*t_ctxAllocs;
     }
 };
 
@@ -97,9 +102,12 @@ __global__ void k_mailbox_copy(const int* __restrict__ src, int words, int* __re
     for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
 }
 
-__global__ void k_mailbox_flag(volatile int* flag, int seq)
+// (the sequence number of the last post is also kept in device memory: k_mailbox_post counts on from it, so that its launch
+// parameters do not change from step to step and the deferred step can be replayed as a CUDA graph)
+__global__ void k_mailbox_flag(volatile int* flag, int seq, int* __restrict__ seqDev)
 {
     __threadfence_system();   // (kernels of one stream run in order: the staged copies are complete; make them visible first)
+    *seqDev = seq;
     *flag = seq;
 }
 
@@ -119,7 +127,7 @@ static int mailbox_spin(phyx_b200_ctx* c, int seq);
 int mailbox_wait(phyx_b200_ctx* c)
 {
     const int seq = int(++c->mailboxSeq & 0x7fffffffu);
-    k_mailbox_flag<<<1, 1, 0, c->stream>>>(c->mailboxDev + kMailboxFlag / 4, seq);
+    k_mailbox_flag<<<1, 1, 0, c->stream>>>(c->mailboxDev + kMailboxFlag / 4, seq, c->mailboxSeqDev);
     PHYX_CUDA(cudaGetLastError());
     return mailbox_spin(c, seq);
 }
@@ -132,7 +140,7 @@ struct MailPieces
     int count;
 };
 
-__global__ void k_mailbox_post(MailPieces p, int* __restrict__ box, volatile int* flag, int seq)
+__global__ void k_mailbox_post(MailPieces p, int* __restrict__ box, volatile int* flag, int* __restrict__ seqDev)
 {
     for (int k = 0; k < p.count; ++k)
         for (int i = threadIdx.x; i < p.words[k]; i += blockDim.x) box[p.offset[k] + i] = p.src[k][i];
@@ -141,16 +149,23 @@ __global__ void k_mailbox_post(MailPieces p, int* __restrict__ box, volatile int
     if (threadIdx.x == 0)
     {
         __threadfence_system();
+        const int seq = (*seqDev + 1) & 0x7fffffff;
+        *seqDev = seq;
         *flag = seq;
     }
 }
 
-static int mailbox_post_and_wait(phyx_b200_ctx* c, const MailPieces& p)
+static int mailbox_post(phyx_b200_ctx* c, const MailPieces& p)
 {
-    const int seq = int(++c->mailboxSeq & 0x7fffffffu);
-    k_mailbox_post<<<1, 128, 0, c->stream>>>(p, c->mailboxDev, c->mailboxDev + kMailboxFlag / 4, seq);
+    k_mailbox_post<<<1, 128, 0, c->stream>>>(p, c->mailboxDev, c->mailboxDev + kMailboxFlag / 4, c->mailboxSeqDev);
     c->launches++;
     PHYX_CUDA(cudaGetLastError());
+    return PHYX_B200_OK;
+}
+// the host side of a post: wait for the next sequence number
+static int mailbox_await_post(phyx_b200_ctx* c)
+{
+    const int seq = int(++c->mailboxSeq & 0x7fffffffu);
     return mailbox_spin(c, seq);
 }
 
@@ -198,6 +213,7 @@ static int check(phyx_b200_ctx* c)
         return PHYX_B200_ERR_ARGUMENT;
     }
     PHYX_CUDA(cudaSetDevice(c->device));
+    t_ctxAllocs = &c->allocCount;
     return PHYX_B200_OK;
 }
 
@@ -284,6 +300,9 @@ int phyx_b200_create(int device, phyx_b200_ctx** out)
         void* dev = nullptr;
         PHYX_CUDA(cudaHostGetDevicePointer(&dev, host, 0));
         c->mailboxDev = static_cast<int*>(dev);
+        PHYX_CUDA(cudaMalloc(&dev, 64));
+        PHYX_CUDA(cudaMemset(dev, 0, 64));
+        c->mailboxSeqDev = static_cast<int*>(dev);
         return PHYX_B200_OK;
     };
     const int st = init();
@@ -296,6 +315,7 @@ int phyx_b200_create(int device, phyx_b200_ctx** out)
             if (ev) cudaEventDestroy(ev);
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->mailboxHost) cudaFreeHost(c->mailboxHost);
+        if (c->mailboxSeqDev) cudaFree(c->mailboxSeqDev);
         delete c;
         return st;
     }
@@ -310,6 +330,8 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     cudaStreamSynchronize(c->stream);
     part_destroy(c);
     strip_release(c);
+    if (c->def.graphExec) cudaGraphExecDestroy(c->def.graphExec);
+    c->def.graphExec = nullptr;
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
@@ -321,6 +343,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     if (c->mailboxHost) cudaFreeHost(c->mailboxHost);
+    if (c->mailboxSeqDev) cudaFree(c->mailboxSeqDev);
     delete c;
 }
 
@@ -518,11 +541,11 @@ int phyx_b200_solve_staged(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, 
     }
     if (stats) memset(stats, 0, sizeof(*stats));
     cudaEvent_t t0 = c->ev[4], t1 = c->ev[5], t2 = c->ev[6];
-    PHYX_CUDA(cudaEventRecord(t0, c->stream));
+    PHYX_CUDA(record_event(c, t0));
     PHYX_TRY(schedule_build(c, c->hostJointsValid ? c->hostJoints.data() : nullptr, c->jointCount, cfg->schedule, cfg->flags));
-    PHYX_CUDA(cudaEventRecord(t1, c->stream));
+    PHYX_CUDA(record_event(c, t1));
     PHYX_TRY(solve_run(c, cfg, stats));
-    PHYX_CUDA(cudaEventRecord(t2, c->stream));
+    PHYX_CUDA(record_event(c, t2));
     if (c->def.active) return PHYX_B200_OK;   // deferred step: nothing waits here (deferred_finish fills the statistics)
     PHYX_CUDA(cudaEventSynchronize(t2));
     if (stats)
@@ -912,15 +935,26 @@ int phyx_b200_solve_resident(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg
 // was changed by the stage in question and the host finishes it with the stage functions: results are those of the
 // stage path either way.
 
-__global__ void k_ctl_begin(StepCtl* ctl, int bodies, int manifolds, int joints)
+// the counts the device block starts a step from: written from the host only when they are not what the previous deferred
+// step left there (first deferred step, or stage functions ran in between) ...
+__global__ void k_ctl_set(StepCtl* ctl, int manifolds, int joints)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->manifolds = manifolds;
+    ctl->joints = joints;
+}
+
+// ... and the per-step part: manifolds / joints carry over from the previous step on the device, so this launch has the same
+// parameters every step (the step is replayed as a CUDA graph)
+__global__ void k_ctl_reset(StepCtl* ctl, int bodies)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     StepCtl z;
     memset(&z, 0, sizeof(z));
     z.bodies = bodies;
-    z.manifolds = manifolds;
-    z.joints = joints;
-    z.jointsGrown = joints;
+    z.manifolds = ctl->manifolds;
+    z.joints = ctl->joints;
+    z.jointsGrown = z.joints;
     *ctl = z;
 }
 
@@ -966,32 +1000,85 @@ static bool deferred_eligible(phyx_b200_ctx* c, const phyx_b200_solve_config* cf
     return strip_predict_caps(c, &c->def.rowCap, &c->def.cutCap, &c->def.workCap);
 }
 
-static int deferred_issue(phyx_b200_ctx* c, float dt, float gravity, const phyx_b200_solve_config* cfg)
+// keep `cap` while it is neither too tight nor wasteful for `need`: the bounds are launch parameters, and launch parameters
+// that do not change let the step be replayed as a graph
+static void sticky_bound(int* cap, int need, int floorValue)
+{
+    if (*cap < need + need / 8 + 256 || *cap > 4 * need + 4 * floorValue) *cap = bound_of(need, floorValue);
+}
+
+// bounds of this step, the device block's starting counts; returns the key of everything the issued launches depend on
+static int deferred_prepare(phyx_b200_ctx* c, float dt, float gravity, const phyx_b200_solve_config* cfg, unsigned long long* keyOut)
 {
     Deferred& d = c->def;
     PHYX_TRY(c->ctlBuf.reserve(sizeof(StepCtl)));
-    d.capItems = bound_of(std::max(d.lastItems, c->bodyCount), 8192);
-    d.capNewPairs = bound_of(std::max(d.lastNewPairs, c->manifoldCount / 64), 4096);
-    d.capFresh = bound_of(std::max(d.lastFresh, c->jointCount / 64), 4096);
     if (d.tight)
     {
         // test mode: no headroom at all, so that any growth exercises the stop-and-resume path
         d.capItems = std::max(d.lastItems, 1);
         d.capNewPairs = std::max(d.lastNewPairs, 1);
         d.capFresh = std::max(d.lastFresh, 1);
+        d.ubManifolds = c->manifoldCount + d.capNewPairs;
+        d.ubJoints = c->jointCount + d.capFresh;
+    }
+    else
+    {
+        sticky_bound(&d.capItems, std::max(d.lastItems, c->bodyCount), 8192);
+        sticky_bound(&d.capNewPairs, std::max(d.lastNewPairs, c->manifoldCount / 64), 4096);
+        sticky_bound(&d.capFresh, std::max(d.lastFresh, c->jointCount / 64), 4096);
+        // bounds on the arrays themselves (what grids and scratch are sized by)
+        auto sticky_array = [](int* ub, int need) {
+            if (*ub < need || *ub > need + need / 3 + 65536) *ub = int(std::min<long long>(((long long)need + need / 8 + 16383) & ~16383ll, 1ll << 30));
+        };
+        sticky_array(&d.ubManifolds, c->manifoldCount + d.capNewPairs);
+        sticky_array(&d.ubJoints, c->jointCount + d.capFresh);
     }
     // the cache must take the new pairs without a rebuild in the middle of the step
-    if (size_t(c->manifoldCount + d.capNewPairs) * 2 > c->pairTableSlots) PHYX_TRY(collide_rebuild_pair_table_for(c, c->manifoldCount + d.capNewPairs));
-    k_ctl_begin<<<1, 32, 0, c->stream>>>(c->ctl(), c->bodyCount, c->manifoldCount, c->jointCount);
+    if (size_t(d.ubManifolds) * 2 > c->pairTableSlots) PHYX_TRY(collide_rebuild_pair_table_for(c, d.ubManifolds));
+    if (d.ctlManifolds != c->manifoldCount || d.ctlJoints != c->jointCount)
+    {
+        k_ctl_set<<<1, 32, 0, c->stream>>>(c->ctl(), c->manifoldCount, c->jointCount);
+        c->launches++;
+        d.ctlManifolds = c->manifoldCount;
+        d.ctlJoints = c->jointCount;
+    }
+    // everything the launches of deferred_enqueue depend on besides the buffers' addresses (covered by the allocation count)
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&h](unsigned long long v) { h = (h ^ v) * 1099511628211ull; };
+    unsigned dtBits, gBits;
+    memcpy(&dtBits, &dt, 4);
+    memcpy(&gBits, &gravity, 4);
+    mix(unsigned(c->bodyCount)); mix(unsigned(d.capItems)); mix(unsigned(d.capNewPairs)); mix(unsigned(d.capFresh));
+    mix(unsigned(d.ubManifolds)); mix(unsigned(d.ubJoints)); mix(unsigned(d.rowCap)); mix(unsigned(d.cutCap)); mix(unsigned(d.workCap));
+    mix(unsigned(c->strip.strips)); mix(unsigned(c->strip.autoLimit)); mix(unsigned(c->coloursAtFullBuild)); mix(c->strip.measuredFeedback ? 1u : 0u);
+    mix(unsigned(cfg->contactIterationsCount)); mix(unsigned(cfg->penetrationIterationsCount)); mix(dtBits); mix(gBits);
+    mix((unsigned long long)c->pairTableSlots); mix((unsigned long long)c->allocCount);
+    // (belt and braces: the addresses of the buffers that grow with the world)
+    const DevBuf* watched[] = { &c->manBody, &c->manCount, &c->manColour, &c->contactPoints, &c->joints, &c->collideTmp, &c->colourTmp, &c->colourKeys,
+        &c->colourSorted, &c->slotJoint, &c->pairQ, &c->pairIdx, &c->accNF, &c->accD, &c->solveRows, &c->items, &c->itemCount, &c->pairs, &c->pairTable,
+        &c->hist, &c->scanTmp, &c->strip.pairTest, &c->strip.sync, &c->bodyActivity };
+    for (const DevBuf* b : watched) mix((unsigned long long)(uintptr_t)b->ptr);
+    *keyOut = h;
+    return PHYX_B200_OK;
+}
+
+// the launches of one step, in stream order (capturable: nothing in here waits for the device)
+static int deferred_enqueue(phyx_b200_ctx* c, float dt, float gravity, const phyx_b200_solve_config* cfg)
+{
+    Deferred& d = c->def;
+    k_ctl_reset<<<1, 32, 0, c->stream>>>(c->ctl(), c->bodyCount);
     c->launches++;
     d.colourResult = nullptr;
-    d.active = true;
     c->hostJointsValid = false;
+    // the context's counts are BOUNDS from here on (the true counts are in the device block)
+    c->manifoldCount = d.ubManifolds - d.capNewPairs;
+    c->contactPointCount = 2 * c->manifoldCount;
+    c->jointCount = d.ubJoints - d.capFresh;
     PHYX_TRY(bodies_integrate_velocity(c, dt, gravity));
     PHYX_TRY(broadphase_update(c));
-    PHYX_CUDA(cudaEventRecord(c->evBp[2], c->stream));
+    PHYX_CUDA(record_event(c, c->evBp[2]));
     PHYX_TRY(collide_update_pairs(c, nullptr));
-    PHYX_CUDA(cudaEventRecord(c->evBp[3], c->stream));
+    PHYX_CUDA(record_event(c, c->evBp[3]));
     PHYX_TRY(collide_update_manifolds(c));
     PHYX_TRY(collide_pack_manifolds(c));
     PHYX_TRY(collide_refresh_joints(c, nullptr, nullptr, nullptr));
@@ -1017,7 +1104,86 @@ static int deferred_issue(phyx_b200_ctx* c, float dt, float gravity, const phyx_
     p.src[3] = reinterpret_cast<const int*>(c->solveFlags.as<char>() + 32);
     p.words[3] = 8;
     p.offset[3] = 208 / 4;
-    return mailbox_post_and_wait(c, p);
+    return mailbox_post(c, p);
+}
+
+static void graph_drop(phyx_b200_ctx* c)
+{
+    if (c->def.graphExec) cudaGraphExecDestroy(c->def.graphExec);
+    c->def.graphExec = nullptr;
+    c->def.graphKey = 0;
+}
+
+// Issue one deferred step and wait for its read-back.  Steps whose launches are the same as the previous step's (same
+// bounds, same buffers: the steady state) are captured into a CUDA graph once and replayed: ~110 stream operations become
+// one launch.
+static int deferred_issue(phyx_b200_ctx* c, float dt, float gravity, const phyx_b200_solve_config* cfg, bool* replayed)
+{
+    Deferred& d = c->def;
+    *replayed = false;
+    d.graphStatus = 0;
+    unsigned long long key = 0;
+    PHYX_TRY(deferred_prepare(c, dt, gravity, cfg, &key));
+    d.active = true;
+    if (d.useGraph && d.graphExec && d.graphKey == key)
+    {
+        PHYX_CUDA(cudaGraphLaunch(d.graphExec, c->stream));
+        c->launches += d.graphLaunches;
+        *replayed = true;
+        d.graphStatus = 1;
+        d.graphReplays++;
+        // (the host-side bookkeeping of deferred_enqueue is the same every step: it still stands from the captured one,
+        // except the bounds-as-counts, which deferred_finish replaces by the true counts anyway)
+        return mailbox_await_post(c);
+    }
+    if (d.useGraph && !d.graphBroken && d.lastKey == key && key != 0)
+    {
+        // second step in a row with the same launches: capture it
+        graph_drop(c);
+        const int64_t launches0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        d.capturing = true;
+        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
+        int st = PHYX_B200_OK;
+        if (e == cudaSuccess)
+        {
+            st = deferred_enqueue(c, dt, gravity, cfg);
+            e = cudaStreamEndCapture(c->stream, &graph);
+        }
+        d.capturing = false;
+        if (st == PHYX_B200_OK && e == cudaSuccess && graph)
+        {
+            e = cudaGraphInstantiate(&d.graphExec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e == cudaSuccess && c->allocCount == d.lastAllocCount)
+            {
+                d.graphKey = key;
+                d.graphLaunches = c->launches - launches0;
+                PHYX_CUDA(cudaGraphLaunch(d.graphExec, c->stream));
+                *replayed = true;
+                d.graphStatus = 2;
+                d.graphReplays++;
+                return mailbox_await_post(c);
+            }
+            graph_drop(c);
+        }
+        else if (graph)
+            cudaGraphDestroy(graph);
+        // the capture did not work out (nothing of it has run): issue the step on the stream, and do not try again
+        set_error("graph capture of the deferred step failed: %s (status %d)", cudaGetErrorString(e), st);
+        cudaGetLastError();
+        c->launches = launches0;
+        d.graphStatus = -1;
+        if (c->allocCount == d.lastAllocCount) d.graphBroken = true;
+    }
+    else if (d.lastKey != key)
+        d.graphStatus = 3;
+    d.lastKey = key;
+    d.lastAllocCount = c->allocCount;
+    PHYX_TRY(deferred_enqueue(c, dt, gravity, cfg));
+    // (an allocation during the enqueue moves a buffer: the next step's launches differ, whatever the key says)
+    if (c->allocCount != d.lastAllocCount) d.lastKey = 0;
+    return mailbox_await_post(c);
 }
 
 int phyx_b200_world_step(phyx_b200_ctx* c, float dt, float gravity, const phyx_b200_solve_config* cfg, phyx_b200_solve_stats* solveStats,
@@ -1036,14 +1202,20 @@ int phyx_b200_world_step(phyx_b200_ctx* c, float dt, float gravity, const phyx_b
     bool ranDeferred = false;
     if (deferred_eligible(c, cfg))
     {
-        const int st = deferred_issue(c, dt, gravity, cfg);
+        bool replayed = false;
+        const int st = deferred_issue(c, dt, gravity, cfg, &replayed);
         d.active = false;
+        d.capturing = false;
+        if (info) info->graphReplay = replayed ? 1 : 0;
+        if (info) info->graphStatus = d.graphStatus;
         if (st != PHYX_B200_OK)
         {
             // the context's counts may be bounds: nothing sensible can continue from here
             c->jointUnitsValid = false;
             c->colourStateValid = false;
             c->strip.valid = false;
+            d.ctlManifolds = d.ctlJoints = -1;
+            graph_drop(c);
             return st;
         }
         d.steps++;
@@ -1059,6 +1231,7 @@ int phyx_b200_world_step(phyx_b200_ctx* c, float dt, float gravity, const phyx_b
             d.stops++;
             d.lastStopStage = ctl.stop;
             d.lastStopReason = ctl.stopReason;
+            d.ctlManifolds = d.ctlJoints = -1;    // (the device block was zeroed by the stop)
             c->manifoldCount = ctl.saved[1];
             c->contactPointCount = 2 * c->manifoldCount;
             c->jointCount = ctl.saved[2];
@@ -1080,6 +1253,8 @@ int phyx_b200_world_step(phyx_b200_ctx* c, float dt, float gravity, const phyx_b
         else
         {
             ranDeferred = true;
+            d.ctlManifolds = ctl.manifolds;
+            d.ctlJoints = ctl.joints;
             c->manifoldCount = ctl.manifolds;
             c->contactPointCount = 2 * ctl.manifolds;
             c->jointCount = ctl.joints;
@@ -1161,6 +1336,7 @@ int phyx_b200_step_mode(phyx_b200_ctx* c, int deferred)
     PHYX_TRY(check(c));
     c->def.enabled = deferred != 0;
     c->def.tight = deferred == 2;
+    c->def.useGraph = deferred != 3;
     return PHYX_B200_OK;
 }
 

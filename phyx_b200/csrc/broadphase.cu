@@ -526,14 +526,14 @@ int broadphase_update(phyx_b200_ctx* c)
     c->broadphaseValid = true;
     if (n == 0) return PHYX_B200_OK;
     int grid = (n + kBlock - 1) / kBlock;
-    PHYX_CUDA(cudaEventRecord(c->evBp[0], c->stream));
+    PHYX_CUDA(record_event(c, c->evBp[0]));
     k_make_keys<<<grid, kBlock, 0, c->stream>>>(n, c->aabb.as<float4>(), c->sortA.as<uint2>());
     c->launches++;
     // radixSort3: digits 0-10, 11-21, 22-31; A -> B -> A -> B (RadixSort.h:74-88)
     PHYX_TRY(radix_pass(c, c->sortA.as<uint2>(), c->sortB.as<uint2>(), n, 0, 2048));
     PHYX_TRY(radix_pass(c, c->sortB.as<uint2>(), c->sortA.as<uint2>(), n, 11, 2048));
     PHYX_TRY(radix_pass(c, c->sortA.as<uint2>(), c->sortB.as<uint2>(), n, 22, 1024));
-    PHYX_CUDA(cudaEventRecord(c->evBp[1], c->stream));
+    PHYX_CUDA(record_event(c, c->evBp[1]));
     c->sortTimed = true;
     float2* entryX = c->entry.as<float2>();
     float2* entryY = entryX + n1;

@@ -170,6 +170,15 @@ struct Deferred
     int64_t steps = 0, stops = 0, ineligible = 0;      // statistics
     int lastStopStage = 0, lastStopReason = 0;
     const int* colourResult = nullptr;                 // device words of the colouring's result (colour.cu), read back with the step
+    int ubManifolds = 0, ubJoints = 0;                 // bounds on the manifold / joint arrays (grids and scratch are sized by them)
+    int ctlManifolds = -1, ctlJoints = -1;             // what the device block holds as the starting counts (-1: unknown)
+    // the steady-state step as a CUDA graph
+    bool useGraph = true, graphBroken = false, capturing = false;
+    cudaGraphExec_t graphExec = nullptr;
+    unsigned long long graphKey = 0, lastKey = 0;
+    long long lastAllocCount = -1;
+    int64_t graphLaunches = 0, graphReplays = 0;
+    int graphStatus = 0;
 };
 
 } // namespace phyx
@@ -180,6 +189,7 @@ struct phyx_b200_ctx
     int numSMs = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    long long allocCount = 0;    // device (re)allocations made for this context (api.cu AllocTimer)
 
     // ---- bodies (SoA in HBM) --------------------------------------------------------------
     int bodyCount = 0;
@@ -200,7 +210,6 @@ struct phyx_b200_ctx
     phyx::DevBuf sortA, sortB;   // uint2 {key, index}
     phyx::DevBuf hist;           // per-block digit counts / offsets
     phyx::DevBuf scanTmp;
-    unsigned scanEpoch = 0;      // scan.cu: tag of the current scan's status words
     void* scanTmpCleared = nullptr;
     phyx::DevBuf entry;          // float4 {minx, maxx, centery, extenty}, sorted order
     phyx::DevBuf entryIndex;     // uint32 body index, sorted order
@@ -270,6 +279,7 @@ struct phyx_b200_ctx
     // flag, the host spins on the flag): a fraction of the latency of cudaMemcpyAsync to pageable memory + cudaStreamSynchronize
     int* mailboxHost = nullptr;
     int* mailboxDev = nullptr;
+    int* mailboxSeqDev = nullptr;   // device copy of the last sequence number posted
     unsigned mailboxSeq = 0;
     cudaEvent_t ev[8] = {};
     cudaEvent_t evBp[4] = {};    // broadphase timing: sort start / end (update_broadphase), sweep start / end (update_pairs)
@@ -306,6 +316,12 @@ struct phyx_b200_ctx
 
 namespace phyx
 {
+// cudaEventRecord that also works while the deferred step is being captured into a graph (an external event node)
+inline cudaError_t record_event(phyx_b200_ctx* c, cudaEvent_t ev)
+{
+    return cudaEventRecordWithFlags(ev, c->stream, c->def.capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
 // bodies.cu
 int bodies_upload(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int n);
 int bodies_download(phyx_b200_ctx* c, phyx_rigid_body* bodies, int n);

@@ -46,26 +46,33 @@ __device__ __forceinline__ int block_exclusive(int v, int* total)
 // about fourteen scans, which used to be 40 launches).  Tiles are taken in ticket order, so a tile only ever waits for
 // tiles whose CTAs are already running.  status[t] = flag << 32 | value: flag 1 = the tile's own total is there,
 // 2 = the inclusive prefix up to and including the tile is.  Integer sums: the result does not depend on who adds what.
-// The status words carry the scan's EPOCH (a per-context call counter) in their upper 30 bits, so words left by earlier
-// scans read as "not there yet" and nothing has to be cleared between scans; the CTA that finishes last puts the ticket
-// counter back to zero.  (A memset per scan was a quarter of a small world's step: fourteen scans, each a few microseconds.)
-__device__ __forceinline__ void scan_leave(unsigned* ticket)
+// The status words carry the scan's EPOCH (a counter in device memory, advanced by every scan) in their upper 30 bits, so
+// words left by earlier scans read as "not there yet" and nothing has to be cleared between scans; the CTA that finishes
+// last puts the ticket counter back to zero and advances the epoch.  (A memset per scan was a quarter of a small world's
+// step: fourteen scans, each a few microseconds.  The epoch lives on the device so that a scan's launch parameters do not
+// change from step to step: the deferred step is replayed as a CUDA graph.)
+__device__ __forceinline__ void scan_leave(unsigned* ticket, unsigned epoch)
 {
-    // ticket[0] = next tile, ticket[1] = CTAs done
+    // ticket[0] = next tile, ticket[1] = CTAs done, ticket[2] = epoch
     if (threadIdx.x == 0 && atomicAdd(&ticket[1], 1u) == gridDim.x - 1)
     {
         ticket[0] = 0u;
         ticket[1] = 0u;
+        const unsigned next = (epoch + 1u) & 0x3fffffffu;
+        ticket[2] = next ? next : 1u;   // (0 = "never written"; a word 2^30 scans old could be mistaken for a fresh one: the
+                                        // status area of one scan is rewritten entirely by the next scan of the same size or larger,
+                                        // and a step makes the same scans in the same order)
     }
 }
 
 __global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restrict__ in, Count nc, int* __restrict__ out, unsigned long long* __restrict__ status,
-    unsigned* __restrict__ ticket, int* __restrict__ totalOut, unsigned epoch)
+    unsigned* __restrict__ ticket, int* __restrict__ totalOut)
 {
     __shared__ int total;
     __shared__ unsigned s_tile;
     __shared__ int s_prefix;
     const int n = count_of(nc);
+    const unsigned epoch = __ldcg(&ticket[2]);   // (only the last CTA of a scan changes it, after every CTA has read it... see scan_leave)
     const unsigned long long tag = static_cast<unsigned long long>(epoch) << 34;
     if (threadIdx.x == 0) s_tile = atomicAdd(&ticket[0], 1u);
     __syncthreads();
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restr
     if (tile * kScanTile >= n)
     {
         if (tile == 0 && threadIdx.x == 0 && totalOut) *totalOut = 0;
-        scan_leave(ticket);
+        scan_leave(ticket, epoch);
         return;
     }
     const int base = tile * kScanTile + threadIdx.x * kScanItems;
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restr
         run += v[k];
     }
     if (totalOut && base <= n - 1 && n - 1 < base + kScanItems) *totalOut = run;   // the thread that holds the last element
-    scan_leave(ticket);
+    scan_leave(ticket, epoch);
 }
 
 // in and out may alias.  If totalDevice is non-null it receives the grand total.
@@ -156,19 +163,20 @@ int exclusive_scan_count(phyx_b200_ctx* c, const int* in, int* out, Count nc, in
         return PHYX_B200_OK;
     }
     const int tiles = (n + kScanTile - 1) / kScanTile;
-    const size_t bytes = (size_t(tiles) + 2) * sizeof(unsigned long long);
+    const size_t bytes = (size_t(tiles) + 4) * sizeof(unsigned long long);
     PHYX_TRY(c->scanTmp.reserve(bytes));
-    c->scanEpoch = (c->scanEpoch + 1u) & 0x3fffffffu;
-    if (c->scanTmp.ptr != c->scanTmpCleared || c->scanEpoch == 0u)
+    if (c->scanTmp.ptr != c->scanTmpCleared)
     {
-        // a new buffer, or the epoch counter has wrapped: start from clean words (epoch 0 is never used for a scan)
+        // a new buffer: clean words, epoch 1 (0 is what cleared words carry)
         PHYX_CUDA(cudaMemsetAsync(c->scanTmp.ptr, 0, c->scanTmp.cap, c->stream));
+        const unsigned one = 1u;
+        PHYX_CUDA(cudaMemcpyAsync(c->scanTmp.as<unsigned>() + 2, &one, sizeof(one), cudaMemcpyHostToDevice, c->stream));
+        PHYX_CUDA(cudaStreamSynchronize(c->stream));   // (`one` is on the stack; once per buffer)
         c->scanTmpCleared = c->scanTmp.ptr;
-        if (c->scanEpoch == 0u) c->scanEpoch = 1u;
     }
-    unsigned long long* status = c->scanTmp.as<unsigned long long>() + 1;
+    unsigned long long* status = c->scanTmp.as<unsigned long long>() + 2;
     unsigned* ticket = c->scanTmp.as<unsigned>();
-    k_scan_single<<<tiles, kScanThreads, 0, c->stream>>>(in, nc, out, status, ticket, totalDevice, c->scanEpoch);
+    k_scan_single<<<tiles, kScanThreads, 0, c->stream>>>(in, nc, out, status, ticket, totalDevice);
     c->launches++;
     PHYX_CUDA(cudaGetLastError());
     return PHYX_B200_OK;

@@ -1085,7 +1085,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
     PHYX_TRY(c->solveFlags.reserve(128));
 
     cudaEvent_t e0 = c->ev[0], e1 = c->ev[1], e2 = c->ev[2], e3 = c->ev[3];
-    PHYX_CUDA(cudaEventRecord(e0, c->stream));
+    PHYX_CUDA(record_event(c, e0));
     int ranI = I > 0 ? 1 : 0, ranD = D > 0 ? 1 : 0, wakePasses = 0;
     if (ns > 0 && nl > 0)
     {
@@ -1114,7 +1114,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
             c->params.as<float4>(), rowOf, c->q0.as<float4>(), c->q1.as<float4>(), c->q2.as<float4>(), c->q3.as<float4>(), c->accNF.as<float2>(),
             c->accD.as<float>(), records ? c->pairQ.as<float4>() : nullptr, records ? c->pairIdx.as<int2>() : nullptr, 0, !strips);
         c->launches++;
-        PHYX_CUDA(cudaEventRecord(e1, c->stream));
+        PHYX_CUDA(record_event(c, e1));
 
         SolveParams P;
         memset(&P, 0, sizeof(P));
@@ -1174,7 +1174,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
             PHYX_CUDA(cudaLaunchCooperativeKernel(solveKernel, dim3(sgrid), dim3(sblock), args, solveSmem, c->stream));
             c->launches++;
         }
-        PHYX_CUDA(cudaEventRecord(e2, c->stream));
+        PHYX_CUDA(record_event(c, e2));
         k_finish<<<grid, kBlock, 0, c->stream>>>(nsc, c->slotJoint.as<int>(), c->accNF.as<float2>(), c->joints.as<phyx_contact_joint>());
         PHYX_TRY(c->bodyActivity.reserve(size_t(nb) * sizeof(int)));
         k_finish_bodies<<<(nb + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(nbc, order, rowsVel, rowsDisp, c->vel.as<float4>(), c->disp.as<float4>(),
@@ -1182,7 +1182,7 @@ int solve_run(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, phyx_b200_sol
         c->activityValid = true;
         c->activityBodies = nb;
         c->launches += 2;
-        PHYX_CUDA(cudaEventRecord(e3, c->stream));
+        PHYX_CUDA(record_event(c, e3));
         if (c->def.active) return PHYX_B200_OK;   // the results come home with the step's counts (deferred_finish, api.cu)
         int host[8];   // result[0..2], pad, activeTotal[2] as two 64-bit words
         PHYX_TRY(fetch_small(c, P.result, sizeof(host), host));

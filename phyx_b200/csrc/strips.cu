@@ -900,6 +900,10 @@ bool strip_predict_caps(phyx_b200_ctx* c, int* rowCap, int* cutCap, int* workCap
         const int rWant = r0 + r0 / 16 + 64, kWant = k0 + k0 / 8 + 128, wWant = w0 + w0 / 8 + 128;
         const int rMin = r0 + r0 / 100 + 16, kMin = k0 + k0 / 32 + 32, wMin = w0 + w0 / 32 + 32;
         auto total = [&](int rr, int kk, int ww) { return strip_smem_bytes(rr, kk, ww) + overhead; };
+        // the shape of the previous step still does (roomy enough, same carve-out): keep it, launch parameters that do not
+        // change let the step be replayed as a graph
+        if (*rowCap >= rMin && *cutCap >= kMin && *workCap >= wMin && total(*rowCap, *cutCap, *workCap) <= limit && fits(*rowCap, *cutCap, *workCap))
+            return true;
         // binary search on the share t of (want - min) that still stays inside the bucket
         r = rMin; k = kMin; w = wMin;
         int lo = 0, hi = 64;

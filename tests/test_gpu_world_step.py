@@ -77,6 +77,16 @@ def test_stopped_steps_are_finished_by_the_stage_functions(scene, steps):
     assert any(i["deferred"] for i in infos)
 
 
+def test_steady_state_steps_are_replayed_as_a_graph():
+    """Same bounds and buffers as the step before: the ~110 stream operations of a step become one graph launch; results
+    stay those of the stage path."""
+    infos = run_pair("stack_10k", 40, 1, check_every=8)
+    replays = sum(i["graphReplay"] for i in infos)
+    assert replays >= 10, [(i["deferred"], i["graphReplay"], i["stopStage"], i["stopReason"]) for i in infos]
+    infos = run_pair("stack_10k", 12, 3)
+    assert not any(i["graphReplay"] for i in infos) and any(i["deferred"] for i in infos)
+
+
 def test_step_mode_zero_is_the_stage_path():
     infos = run_pair("pyramid_1k", 8, 0)
     assert not any(i["deferred"] for i in infos)
