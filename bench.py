@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--scene", default=None, help="default: pyramid_1m on one GPU (BASELINE configs[2]); islands_1m on several (configs[3])")
     ap.add_argument("--settle", type=int, default=30, help="untimed World::Update steps that build the contact state")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--step-mode", type=int, default=1, choices=[0, 1, 3],
+                    help="phyx_b200_step_mode: 1 deferred steps with CUDA-graph replay (default), 3 deferred without graphs, 0 stage path")
     ap.add_argument("--stage-calls", action="store_true",
                     help="time the eight stage functions of the C ABI instead of phyx_b200_world_step (same results, one read-back per stage)")
     ap.add_argument("--no-parity", dest="parity", action="store_false",
@@ -543,6 +545,7 @@ def run_ours(args, rank, world_size, local_rank):
     for _ in range(args.settle):
         w.step(solve=world.SOLVE_B200, iters=ITERS)
     ctx = w.context()
+    ctx.step_mode(args.step_mode)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
     nb = scene.shape[0]
 
@@ -605,6 +608,7 @@ def run_ours(args, rank, world_size, local_rank):
     value = world_size * joint_iters / (ms_total * 1e-3)
     nj = stats[-1][1].joints
     manifolds = ctx.collider_counts()[0]
+    plan = ctx.strip_plan()
     # the same steps through the eight stage functions (a read-back per stage), for the per-stage host wall times
     step_wall = dict(stage_wall)
     step_infos_timed = list(step_infos)
@@ -760,6 +764,7 @@ def run_ours(args, rank, world_size, local_rank):
             "stage_calls_ms_per_step": stage_calls_ms,
             "note": "deferred = counts on the device, one read-back per step; graph replay = the whole step is one CUDA-graph launch (same bounds and buffers as the step before); a stopped step is finished by the stage functions (reasons: include/phyx_b200.h)",
         },
+        "strip_plan": {k: v for k, v in plan.items() if k in ("strips", "usable", "rejected", "max_strip_rows", "max_cut_rows", "max_bin", "colours", "cut_manifolds")},
         "resident_stage_wall_ms": {k: round(v / max(stage_steps, 1), 3) for k, v in stage_wall.items()},
         "resident_stage_wall_ms_max": {k: round(v, 3) for k, v in stage_max.items()},
         "device_allocations_in_timed_region": {"count": allocs1[0] - allocs0[0], "host_ms": round(allocs1[1] - allocs0[1], 3)},

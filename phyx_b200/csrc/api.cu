@@ -1265,6 +1265,7 @@ int phyx_b200_world_step(phyx_b200_ctx* c, float dt, float gravity, const phyx_b
             d.lastNewPairs = ctl.newPairs;
             d.lastFresh = ctl.fresh;
             strip_apply_header(c, header);        // (usable: the device has checked it)
+            strip_limit_recover(c);
             c->slotCount = 2 * c->strip.manifolds;
             c->levelCount = c->strip.colours;
             c->coloursInUse = c->strip.colours;

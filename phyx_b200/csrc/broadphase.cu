@@ -229,35 +229,72 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numIte
             unsigned bi = (EMIT || FILTER) ? entryIndex[i] : 0u;
             int out = EMIT ? itemOffset[it] : 0;
             int count = 0;
-            for (int jb = j0; jb < j1; jb += 32)
+            // four rounds of 32 tests per trip, their loads issued together: a round is a chain of dependent accesses
+            // (entry, body index, cache probe), and the ground body's scan is a thousand items of 32 rounds each
+            constexpr int U = 4;
+            for (int jb = j0; jb < j1; jb += 32 * U)
             {
-                int j = jb + lane;
-                bool hit = false;
-                unsigned bj = 0;
-                if (j < j1)
+                float2 yj[U];
+                bool hit[U];
+                unsigned bj[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
                 {
-                    float2 yj = entryY[j];
-                    hit = fabsf(yj.x - yi.x) <= yi.y + yj.y;   // Collider.cpp:309
+                    const int j = jb + u * 32 + lane;
+                    yj[u] = j < j1 ? entryY[j] : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    const int j = jb + u * 32 + lane;
+                    hit[u] = j < j1 && fabsf(yj[u].x - yi.x) <= yi.y + yj[u].y;   // Collider.cpp:309
+                    bj[u] = 0;
                 }
                 if (FILTER)
                 {
-                    if (!EMIT) localHits += __popc(__ballot_sync(0xffffffffu, hit));
-                    if (hit)
+                    unsigned long long key[U], firstWord[U];
+                    size_t slot[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
                     {
-                        bj = entryIndex[j];
-                        hit = !pair_contains(table, tableMask, pair_key(bi, bj));
+                        if (!EMIT) localHits += __popc(__ballot_sync(0xffffffffu, hit[u]));
+                        if (hit[u]) bj[u] = entryIndex[jb + u * 32 + lane];
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                    {
+                        key[u] = pair_key(bi, bj[u]);
+                        slot[u] = pair_slot(key[u], tableMask);
+                        firstWord[u] = hit[u] ? table[slot[u]] : kEmptyPair;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                    {
+                        if (!hit[u]) continue;
+                        if (firstWord[u] == key[u])
+                            hit[u] = false;
+                        else if (firstWord[u] != kEmptyPair)
+                            hit[u] = !pair_contains_from(table, tableMask, key[u], (slot[u] + 1) & tableMask);
                     }
                 }
-                else if (EMIT && hit)
-                    bj = entryIndex[j];
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (EMIT)
+                else if (EMIT)
                 {
-                    if (hit) pairs[out + __popc(m & ((1u << lane) - 1u))] = make_int2(int(bi), int(bj));
-                    out += __popc(m);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (hit[u]) bj[u] = entryIndex[jb + u * 32 + lane];
                 }
-                else
-                    count += __popc(m);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    const unsigned m = __ballot_sync(0xffffffffu, hit[u]);
+                    if (EMIT)
+                    {
+                        if (hit[u]) pairs[out + __popc(m & ((1u << lane) - 1u))] = make_int2(int(bi), int(bj[u]));
+                        out += __popc(m);
+                    }
+                    else
+                        count += __popc(m);
+                }
             }
             if (!EMIT && lane == 0)
             {

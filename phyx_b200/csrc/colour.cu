@@ -848,6 +848,7 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
             if (usable || c->strip.want > 0 || S == 1 || !(c->strip.rejected & 3)) break;
             S = std::max(1, S / 2);
             c->strip.autoLimit = S;
+            c->strip.limitAge = 0;
         }
         if (res[1])
         {
@@ -858,6 +859,7 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
         }
         if (usable)
         {
+            strip_limit_recover(c);
             c->slotCount = 2 * c->strip.manifolds;
             c->levelCount = c->strip.colours;
             c->coloursInUse = c->strip.colours;

@@ -33,6 +33,17 @@ __device__ __forceinline__ bool pair_contains(const unsigned long long* __restri
     }
 }
 
+// the same, continuing a probe sequence at slot i (the caller has looked at the slots before it)
+__device__ __forceinline__ bool pair_contains_from(const unsigned long long* __restrict__ table, size_t mask, unsigned long long key, size_t i)
+{
+    for (;; i = (i + 1) & mask)
+    {
+        unsigned long long v = table[i];
+        if (v == key) return true;
+        if (v == kEmptyPair) return false;
+    }
+}
+
 __device__ __forceinline__ void pair_insert(unsigned long long* table, size_t mask, unsigned long long key)
 {
     for (size_t i = pair_slot(key, mask);; i = (i + 1) & mask)

@@ -171,10 +171,19 @@ __global__ void __launch_bounds__(kBlock) k_strip_hist(Count Mc, const int2* __r
 // the layout can be laid out again by the stage path from the same state)
 __global__ void k_strip_feedback(int S, const long long* __restrict__ cost, const float* __restrict__ factor, float* __restrict__ factorOut, bool useCost)
 {
+    // (sum in a fixed order: thread t adds its strips, then the 256 partial sums are added in index order by thread 0)
+    __shared__ float s_part[256];
     __shared__ float s_sum;
-    if (threadIdx.x == 0) s_sum = 0.f;
+    float part = 0.f;
+    for (int k = threadIdx.x; k < S; k += blockDim.x) part += float(cost[k]);
+    s_part[threadIdx.x] = part;
     __syncthreads();
-    for (int k = threadIdx.x; k < S; k += blockDim.x) atomicAdd(&s_sum, float(cost[k]));
+    if (threadIdx.x == 0)
+    {
+        float sum = 0.f;
+        for (int t = 0; t < int(blockDim.x); ++t) sum += s_part[t];
+        s_sum = sum;
+    }
     __syncthreads();
     const float mean = useCost ? s_sum / float(S) : 0.f;   // (measured feedback switched off: the factors stay what they are)
     for (int k = threadIdx.x; k < S; k += blockDim.x)
@@ -285,9 +294,18 @@ __global__ void __launch_bounds__(kBlock) k_strip_snap(int nb, int S, int reach,
 // possible whenever bodies <= S * limit
 __global__ void k_strip_monotonic(int S, int limit, int* __restrict__ cuts)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    for (int q = 1; q < S; ++q) cuts[q] = min(max(cuts[q], cuts[q - 1]), cuts[q - 1] + limit);
-    for (int q = S - 1; q >= 1; --q) cuts[q] = max(cuts[q], cuts[q + 1] - limit);
+    // the two sweeps are serial; run them on a shared-memory copy (in global memory every step of the chain is an L2 round trip)
+    __shared__ int s_cuts[kStripMax + 2];
+    if (blockIdx.x != 0) return;
+    for (int q = threadIdx.x; q <= S; q += blockDim.x) s_cuts[q] = cuts[q];
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int q = 1; q < S; ++q) s_cuts[q] = min(max(s_cuts[q], s_cuts[q - 1]), s_cuts[q - 1] + limit);
+        for (int q = S - 1; q >= 1; --q) s_cuts[q] = max(s_cuts[q], s_cuts[q + 1] - limit);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q <= S; q += blockDim.x) cuts[q] = s_cuts[q];
 }
 
 // largest k in [0, S) with cuts[k] <= row: the strip that holds the row (empty strips are never returned)
@@ -752,9 +770,9 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
         PHYX_TRY(exclusive_scan_i32(c, cover, cover, nb, nullptr));
         // width limit first, clean cuts last: a snapped cut is never moved again (a strip that ends up too wide for shared
         // memory rejects the layout for this step)
-        k_strip_monotonic<<<1, 32, 0, c->stream>>>(S, kStripRowLimit, sp.cuts.as<int>());
+        k_strip_monotonic<<<1, 128, 0, c->stream>>>(S, kStripRowLimit, sp.cuts.as<int>());
         k_strip_snap<<<S - 1, kBlock, 0, c->stream>>>(nb, S, std::max(1, nb / S / 2), cover, sp.cuts.as<int>());
-        k_strip_monotonic<<<1, 32, 0, c->stream>>>(S, nb, sp.cuts.as<int>());
+        k_strip_monotonic<<<1, 128, 0, c->stream>>>(S, nb, sp.cuts.as<int>());
         c->launches += 3;
     }
 
@@ -847,6 +865,23 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     sp.strips = S;
     *usable = strip_apply_header(c, host);
     return PHYX_B200_OK;
+}
+
+// A rejected layout halves the strip count and the world remembers the limit (autoLimit).  Rejections are often transient
+// (a pile that is still collapsing, a strip squeezed narrow by the balance feedback), and a limit that stays for good
+// leaves SMs idle: after 32 usable layouts under a limit the limit is doubled (dropped once it reaches the SM count); if
+// the wider layout is rejected again, the halving comes back at the price of one extra layout build.
+void strip_limit_recover(phyx_b200_ctx* c)
+{
+    StripPlan& sp = c->strip;
+    if (sp.autoLimit <= 0)
+    {
+        sp.limitAge = 0;
+        return;
+    }
+    if (++sp.limitAge < 32) return;
+    sp.limitAge = 0;
+    sp.autoLimit = sp.autoLimit * 2 >= c->numSMs ? 0 : sp.autoLimit * 2;
 }
 
 // the layout header (16 words, read back from the device) -> the plan's host fields; true if the layout is usable

@@ -154,6 +154,7 @@ SCENES = {
     "stack_10k": lambda: stack(1000, 10),
     "islands_8x10": lambda: multi_island(8, 10),
     "islands_64x20": lambda: multi_island(64, 20),
+    "islands_128k": lambda: multi_island(128, 44),   # one rank's share of islands_1m on 8 devices
     "clump_300": lambda: clump(300),
     "platforms_400": lambda: platforms(400),
     "tumble_300": lambda: tumble(300),
