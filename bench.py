@@ -71,6 +71,39 @@ def parse():
 
 
 # ---------------------------------------------------------------------------------------------------
+class NearGpu:
+    """Run this process on the cores of the GPU's NUMA node while the GPU arm is measured: World::bodies is first touched (and
+    page-locked) there, so the 2 x 128 MB per step of the end-to-end path cross ONE socket's PCIe root instead of the
+    inter-socket link (seen as 2.3 against 3.0 ms per copy between boxes).  restore() gives all cores back for the CPU legs
+    (cpu_baseline, parity), which use every core."""
+
+    def __init__(self, index):
+        self.all = None
+        self.info = "not bound"
+        try:
+            import pynvml
+
+            self.all = os.sched_getaffinity(0)
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(ClockSampler._physical_index(index))
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            near = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1} & self.all
+            if near and near != self.all:
+                os.sched_setaffinity(0, near)
+                self.info = f"{len(near)} of {len(self.all)} cores (NVML cpu affinity of the device)"
+            elif near:
+                self.info = "device is near every core"
+        except Exception as e:  # noqa: BLE001 - a missing NVML or a container that forbids it must not stop the bench
+            self.info = f"not bound ({type(e).__name__})"
+
+    def restore(self):
+        try:
+            if self.all:
+                os.sched_setaffinity(0, self.all)
+        except Exception:  # noqa: BLE001
+            pass
+
+
 class ClockSampler:
     """SM clocks / throttle reasons DURING the timed region: the counters of the B200_PROFILING.md
     `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.*` line, read through
@@ -324,6 +357,7 @@ def run_island_parallel(args, rank, world_size, local_rank):
 
     from phyx_b200 import capi, islands, partition, scenes
 
+    NearGpu(local_rank)   # every rank on the cores next to its own GPU (host buffers of the end-to-end leg are first touched there)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
@@ -540,6 +574,7 @@ def run_ours(args, rank, world_size, local_rank):
         return float(t.item())
 
     # ---- workload: the scene advanced `settle` steps by full World::Update calls (untimed)
+    near = NearGpu(local_rank)
     scene = scenes.make(args.scene)
     w = world.World(scene, device=local_rank, mirror_contents=False)
     for _ in range(args.settle):
@@ -650,6 +685,7 @@ def run_ours(args, rank, world_size, local_rank):
         w.step(solve=world.SOLVE_B200, iters=ITERS)
         stage_ms_e2e = {k: round(v, 3) for k, v in w.stage_ms().items()}
 
+    near.restore()
     parity = None
     if args.parity and world_size == 1:
         try:
@@ -729,7 +765,7 @@ def run_ours(args, rank, world_size, local_rank):
                    "parallelism": f"island-parallel x{world_size} (no data-path collective)"},
         "e2e": {"value": e2e_value, "unit": "constraint-iterations/s", "h2d_bytes_per_step": int(nb * 128), "d2h_bytes_per_step": int(nb * 128),
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "call": "World::Update (host mirror), bodies page-locked in place, collider mirrors: sizes only",
-                "stage_wall_ms": stage_ms_e2e},
+                "stage_wall_ms": stage_ms_e2e, "host_cores": near.info},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "kernel": "; ".join(f"{KERNEL_FORMS[f]} x{n}" for f, n in sorted(forms.items())) + " (warm start + impulse + displacement iterations, one persistent launch per step)",

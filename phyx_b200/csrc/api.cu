@@ -1050,7 +1050,7 @@ static int deferred_prepare(phyx_b200_ctx* c, float dt, float gravity, const phy
     memcpy(&gBits, &gravity, 4);
     mix(unsigned(c->bodyCount)); mix(unsigned(d.capItems)); mix(unsigned(d.capNewPairs)); mix(unsigned(d.capFresh));
     mix(unsigned(d.ubManifolds)); mix(unsigned(d.ubJoints)); mix(unsigned(d.rowCap)); mix(unsigned(d.cutCap)); mix(unsigned(d.workCap));
-    mix(unsigned(c->strip.strips)); mix(unsigned(c->strip.autoLimit)); mix(unsigned(c->coloursAtFullBuild)); mix(c->strip.measuredFeedback ? 1u : 0u);
+    mix(unsigned(c->strip.strips)); mix(unsigned(c->strip.autoLimit)); mix(unsigned(strip_row_limit(c, c->strip.strips))); mix(unsigned(c->coloursAtFullBuild)); mix(c->strip.measuredFeedback ? 1u : 0u);
     mix(unsigned(cfg->contactIterationsCount)); mix(unsigned(cfg->penetrationIterationsCount)); mix(dtBits); mix(gBits);
     mix((unsigned long long)c->pairTableSlots); mix((unsigned long long)c->allocCount);
     // (belt and braces: the addresses of the buffers that grow with the world)

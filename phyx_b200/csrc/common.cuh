@@ -100,6 +100,7 @@ struct StripPlan
     int strips = 0;            // S of the current layout
     int autoLimit = 0;         // largest S worth trying when choosing (halved whenever a layout is rejected as too narrow)
     int limitAge = 0;          // usable layouts since autoLimit last changed (strip_limit_recover)
+    int rowLimit = 0;          // rows a strip of the current layout may have (strips.cu strip_row_limit)
     int maxStripRows = 0, maxCutRows = 0, maxBin = 0, colours = 0, cutManifolds = 0, manifolds = 0;
     bool attributeSet = false;
     int rejected = 0;          // why the last layout attempt was not usable (bit mask, see strips.cu), 0 = usable
@@ -356,6 +357,7 @@ int strip_solve_launch(phyx_b200_ctx* c, const phyx_b200_solve_config* cfg, floa
 int strip_host_levels(phyx_b200_ctx* c, std::vector<int>* classStart);
 bool strip_apply_header(phyx_b200_ctx* c, const int* host16);
 void strip_limit_recover(phyx_b200_ctx* c);
+int strip_row_limit(const phyx_b200_ctx* c, int S);
 bool strip_predict_caps(phyx_b200_ctx* c, int* rowCap, int* cutCap, int* workCap);
 void strip_release(phyx_b200_ctx* c);
 

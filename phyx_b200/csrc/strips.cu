@@ -687,6 +687,22 @@ __global__ void k_strip_verdict(StepCtl* ctl, const int* __restrict__ header, co
         ctl->slots = 2 * header[H_MANIFOLDS];
 }
 
+// Rows a strip may have.  kStripRowLimit bounds what fits at all; within it, a layout whose shared memory (rows + cut-set
+// buffers + worklist) stays inside the SM's 196 KB carve-out keeps 32 KB of L1 for the record fetches, one that spills into
+// the 228 KB carve-out keeps none (0.95 against 1.15 ms on the 1 M pyramid, whose balanced strips sit right on that edge).
+// So when the previous layout of this shape says the side buffers leave room for strips a seventh wider than average, the
+// limit is what keeps the total inside 196 KB.  In steps of 256 rows: the limit is a launch parameter of the deferred step.
+int strip_row_limit(const phyx_b200_ctx* c, int S)
+{
+    const StripPlan& sp = c->strip;
+    if (S <= 1 || sp.feedbackStrips != S || sp.feedbackBodies != c->bodyCount || sp.maxStripRows <= 0) return kStripRowLimit;
+    const long long side = (long long)(sp.maxCutRows + sp.maxCutRows / 8 + 72) * 24 + (long long)(sp.maxBin + sp.maxBin / 8 + 72) * 2 + 5 * 1024;
+    long long rows = ((196 * 1024 - side) / 16 - 16) & ~255ll;
+    const int avg = (c->bodyCount + S - 1) / S;
+    if (rows < avg + avg / 7 || rows < 2048) return kStripRowLimit;   // these strips do not fit that carve-out anyway
+    return int(std::min<long long>(rows, kStripRowLimit));
+}
+
 // strips for a world of this size: enough manifolds per strip to keep a CTA busy, at most one strip per SM
 int strip_choose(const phyx_b200_ctx* c, int manifolds, int bodies)
 {
@@ -715,6 +731,8 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     const int* rowOf = sortedRows ? c->rowOf.as<int>() : nullptr;
     const unsigned* order = sortedRows ? c->entryIndex.as<unsigned>() : nullptr;
     const int bins = 2 * S * kStripBins;
+    const int rowLimit = strip_row_limit(c, S);
+    sp.rowLimit = rowLimit;
 
     PHYX_TRY(sp.header.reserve(64 * sizeof(int)));
     PHYX_TRY(sp.hist.reserve(size_t(nb + 1) * sizeof(int)));
@@ -770,7 +788,7 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
         PHYX_TRY(exclusive_scan_i32(c, cover, cover, nb, nullptr));
         // width limit first, clean cuts last: a snapped cut is never moved again (a strip that ends up too wide for shared
         // memory rejects the layout for this step)
-        k_strip_monotonic<<<1, 128, 0, c->stream>>>(S, kStripRowLimit, sp.cuts.as<int>());
+        k_strip_monotonic<<<1, 128, 0, c->stream>>>(S, rowLimit, sp.cuts.as<int>());
         k_strip_snap<<<S - 1, kBlock, 0, c->stream>>>(nb, S, std::max(1, nb / S / 2), cover, sp.cuts.as<int>());
         k_strip_monotonic<<<1, 128, 0, c->stream>>>(S, nb, sp.cuts.as<int>());
         c->launches += 3;
@@ -918,7 +936,10 @@ bool strip_predict_caps(phyx_b200_ctx* c, int* rowCap, int* cutCap, int* workCap
     d.baseCut = std::max(float(sp.maxCutRows), d.baseCut * 0.97f);
     d.baseBin = std::max(float(sp.maxBin), d.baseBin * 0.97f);
     auto round8 = [](float v) { return (int(v) + 8) & ~7; };
-    const int r0 = std::min(round8(d.baseRows), (kStripRowLimit + 8) & ~7), k0 = round8(d.baseCut), w0 = round8(d.baseBin);
+    // (rows: when the layout holds the strips inside the 196 KB carve-out, the limit itself is the bound: it never changes)
+    const int limitRows = strip_row_limit(c, sp.strips);
+    const bool fixedRows = limitRows < kStripRowLimit && round8(float(limitRows)) > sp.maxStripRows;
+    const int r0 = fixedRows ? round8(float(limitRows)) : std::min(round8(d.baseRows), (kStripRowLimit + 8) & ~7), k0 = round8(d.baseCut), w0 = round8(d.baseBin);
     if (r0 <= sp.maxStripRows || k0 <= sp.maxCutRows || w0 <= sp.maxBin) return false;
     auto fits = [](int r, int k, int w) { return strip_smem_bytes(r + 1, k + 1, w + 1) <= kStripSmemLimit && r < 65000 && k < 65000 && w < 65000; };
     if (!fits(r0, k0, w0)) return false;
@@ -931,9 +952,10 @@ bool strip_predict_caps(phyx_b200_ctx* c, int* rowCap, int* cutCap, int* workCap
         size_t limit = 228 * 1024;
         for (int b : buckets)
             if (size_t(b) * 1024 >= exact) { limit = size_t(b) * 1024; break; }
-        // wanted: rows + 6 % + 64, cut rows and bin + 12 % + 128; at least rows + 1 % + 16, the others + 3 % + 32
-        const int rWant = r0 + r0 / 16 + 64, kWant = k0 + k0 / 8 + 128, wWant = w0 + w0 / 8 + 128;
-        const int rMin = r0 + r0 / 100 + 16, kMin = k0 + k0 / 32 + 32, wMin = w0 + w0 / 32 + 32;
+        // wanted: rows + 25 % + 64, cut rows and bin + 50 % + 128; at least rows + 1 % + 16, the others + 3 % + 32
+        // (room inside the bucket is free: take a lot of it, the shape then also stays valid for many steps)
+        const int rWant = fixedRows ? r0 : r0 + r0 / 4 + 64, kWant = k0 + k0 / 2 + 128, wWant = w0 + w0 / 2 + 128;
+        const int rMin = fixedRows ? r0 : r0 + r0 / 100 + 16, kMin = k0 + k0 / 32 + 32, wMin = w0 + w0 / 32 + 32;
         auto total = [&](int rr, int kk, int ww) { return strip_smem_bytes(rr, kk, ww) + overhead; };
         // the shape of the previous step still does (roomy enough, same carve-out): keep it, launch parameters that do not
         // change let the step be replayed as a graph
