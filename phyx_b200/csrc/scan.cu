@@ -22,26 +22,6 @@ __device__ __forceinline__ int warp_inclusive(int v)
     return v;
 }
 
-// exclusive scan of one value per thread across the block; returns exclusive prefix, total in *total
-__device__ __forceinline__ int block_exclusive(int v, int* total)
-{
-    __shared__ int warpSums[kScanThreads / 32];
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = warp_inclusive(v);
-    if (lane == 31) warpSums[warp] = inc;
-    __syncthreads();
-    if (warp == 0)
-    {
-        int w = lane < kScanThreads / 32 ? warpSums[lane] : 0;
-        int winc = warp_inclusive(w);
-        if (lane < kScanThreads / 32) warpSums[lane] = winc - w;
-        if (lane == kScanThreads / 32 - 1) *total = winc;
-    }
-    __syncthreads();
-    int res = inc - v + warpSums[warp];
-    return res;
-}
-
 // Single-pass scan with decoupled look-back: one launch instead of reduce / scan-of-partials / downsweep (a step makes
 // about fourteen scans, which used to be 40 launches).  Tiles are taken in ticket order, so a tile only ever waits for
 // tiles whose CTAs are already running.  status[t] = flag << 32 | value: flag 1 = the tile's own total is there,
@@ -68,7 +48,6 @@ __device__ __forceinline__ void scan_leave(unsigned* ticket, unsigned epoch)
 __global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restrict__ in, Count nc, int* __restrict__ out, unsigned long long* __restrict__ status,
     unsigned* __restrict__ ticket, int* __restrict__ totalOut)
 {
-    __shared__ int total;
     __shared__ unsigned s_tile;
     __shared__ int s_prefix;
     const int n = count_of(nc);
@@ -84,17 +63,53 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restr
         scan_leave(ticket, epoch);
         return;
     }
-    const int base = tile * kScanTile + threadIdx.x * kScanItems;
-    int v[kScanItems];
-    int s = 0;
+    // Warp-striped tile: warp w owns the 512 ints [w * 512, (w + 1) * 512) of the tile as 4 rows of 128; lane l holds the 4
+    // consecutive ints at 4 * l of every row (one 16-byte load per row when the arrays are 16-byte aligned: every load and
+    // store of the warp is a full 512-byte line set; the blocked layout it replaces read 64-byte pieces per thread).
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warpBase = tile * kScanTile + warp * (32 * kScanItems);
+    const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0 && tile * kScanTile + kScanTile <= n;
+    int v[4][4];
+    int rowSum[4];
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k)
+    for (int r = 0; r < 4; ++r)
     {
-        v[k] = (base + k < n) ? in[base + k] : 0;
-        s += v[k];
+        const int at = warpBase + r * 128 + 4 * lane;
+        if (vec)
+        {
+            const int4 q = *reinterpret_cast<const int4*>(in + at);
+            v[r][0] = q.x; v[r][1] = q.y; v[r][2] = q.z; v[r][3] = q.w;
+        }
+        else
+        {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[r][e] = (at + e < n) ? in[at + e] : 0;
+        }
+        rowSum[r] = v[r][0] + v[r][1] + v[r][2] + v[r][3];
     }
-    const int ex = block_exclusive(s, &total);
-    const unsigned mine = unsigned(total);
+    // exclusive prefix of each lane's 4-int group inside the warp's 512 ints
+    int groupEx[4];
+    int warpTotal = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+        const int inc = warp_inclusive(rowSum[r]);
+        groupEx[r] = warpTotal + inc - rowSum[r];
+        warpTotal += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    // across the 8 warps of the block
+    __shared__ int s_warp[kScanThreads / 32];
+    if (lane == 0) s_warp[warp] = warpTotal;
+    __syncthreads();
+    int warpEx = 0, blockTotal = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w)
+    {
+        const int t = s_warp[w];
+        if (w < warp) warpEx += t;
+        blockTotal += t;
+    }
+    const unsigned mine = unsigned(blockTotal);
     if (threadIdx.x == 0)
     {
         volatile unsigned long long* st = status;
@@ -132,14 +147,35 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_single(const int* __restr
         }
     }
     __syncthreads();
-    int run = ex + s_prefix;
+    const int blockEx = s_prefix + warpEx;
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k)
+    for (int r = 0; r < 4; ++r)
     {
-        if (base + k < n) out[base + k] = run;
-        run += v[k];
+        const int at = warpBase + r * 128 + 4 * lane;
+        int run = blockEx + groupEx[r];
+        int o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+        {
+            o[e] = run;
+            run += v[r][e];
+        }
+        if (vec)
+            *reinterpret_cast<int4*>(out + at) = make_int4(o[0], o[1], o[2], o[3]);
+        else
+        {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (at + e < n) out[at + e] = o[e];
+        }
+        // the thread that holds the last element
+        if (totalOut && at <= n - 1 && n - 1 < at + 4)
+        {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (at + e == n - 1) *totalOut = o[e] + v[r][e];
+        }
     }
-    if (totalOut && base <= n - 1 && n - 1 < base + kScanItems) *totalOut = run;   // the thread that holds the last element
     scan_leave(ticket, epoch);
 }
 
