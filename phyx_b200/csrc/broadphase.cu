@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(kBlock) k_radix_scatter(const uint2* __restric
     __shared__ unsigned short cnt[kSortWarps][kMaxDigits];   // per-warp digit counts, then prefixes
     __shared__ int gOff[kMaxDigits];                         // global offset of (digit, this block)
 
-    unsigned short* flat = &cnt[0][0];
-    for (int k = threadIdx.x; k < kSortWarps * kMaxDigits; k += kBlock) flat[k] = 0;
+    // (only the bins this pass uses: the layout sorts of the solve schedule have 128 and <= 1024 of them)
+    for (int k = threadIdx.x; k < kSortWarps * digits; k += kBlock) cnt[k / digits][k % digits] = 0;
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -317,6 +317,23 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const int* __restrict__ numIte
 // scan is ~R/2 long), so this replaces ~R/2 global reads per entry by one.  Tiles whose union does
 // not fit (the ground body's scan covers every entry) are flagged and left to the item kernel.
 
+// Up to 32 queued hits, one per lane: {rel (12 bits) | body - i0 (8) | chunk (3)}; a pair that is not in the manifold cache
+// counts for its (body, chunk).  Returns the new queue length.
+__device__ __forceinline__ int drain_queue(const unsigned* queue, int qn, int lane, int i0, int first, const unsigned* __restrict__ entryIndex,
+    const unsigned long long* __restrict__ table, size_t tableMask, unsigned* counts, int countWords)
+{
+    const int take = min(qn, 32);
+    if (lane < take)
+    {
+        const unsigned e = queue[qn - 1 - lane];
+        const int rel = int(e & 0xfffu), local = int((e >> 12) & 0xffu), chunk = int(e >> 20);
+        const unsigned bi = entryIndex[i0 + local], bj = entryIndex[first + rel];
+        if (!pair_contains(table, tableMask, pair_key(bi, bj))) atomicAdd(&counts[local * countWords + (chunk >> 1)], 1u << ((chunk & 1) * 16));
+    }
+    __syncwarp();
+    return qn - take;
+}
+
 template <bool FILTER>
 __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(Count nc, const int* __restrict__ end, const int* __restrict__ itemStart,
     const float2* __restrict__ entryY, const unsigned* __restrict__ entryIndex, int* __restrict__ itemCount, unsigned char* __restrict__ tileLong,
@@ -329,6 +346,11 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(Count nc, const in
     __shared__ int cellStart[kCells + 1], cellFill[kCells];
     __shared__ int sMaxEnd;
     __shared__ unsigned sYmin, sYmax, sEymax;        // order-preserving float bits
+    // FILTER: hits wait in a per-warp queue and are looked up in the cache 32 at a time (one per lane); what survives is
+    // counted per (body, chunk) in shared memory, two 16-bit counters to a word
+    constexpr int kQueue = 56, kDrainAbove = kQueue - 32, kCountWords = (kTileCap / kChunk + 2) / 2;
+    __shared__ unsigned sQueue[FILTER ? kBlock / 32 : 1][FILTER ? kQueue : 1];
+    __shared__ unsigned sCount[FILTER ? kTile : 1][FILTER ? kCountWords : 1];
     const int i0 = blockIdx.x * kTile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0)
@@ -339,6 +361,8 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(Count nc, const in
         sEymax = 0u;
     }
     for (int k = threadIdx.x; k < kCells; k += kBlock) cellFill[k] = 0;
+    if (FILTER)
+        for (int k = threadIdx.x; k < kTile * kCountWords; k += kBlock) (&sCount[0][0])[k] = 0u;
     __syncthreads();
     {
         const int i = i0 + threadIdx.x;
@@ -416,6 +440,7 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(Count nc, const in
     __syncthreads();
 
     unsigned long long localTests = 0, localHits = 0;
+    int qn = 0;   // entries in this warp's queue (warp-uniform)
     for (int i = i0 + warp; i < min(i0 + kTile, n); i += kBlock / 32)
     {
         const int e = end[i];
@@ -453,15 +478,37 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(Count nc, const in
                     if (j > i && j < e && fabsf(yj.x - yi.x) <= yi.y + yj.y) hits |= 1u << t;   // Collider.cpp:306,309
                 }
             }
-            // ... then the cache lookups of the hits, all lanes' probes in flight together
-            if (FILTER) localHits += __popc(hits);
-            while (hits)
+            if (FILTER)
             {
-                const int t = __ffs(hits) - 1;
-                hits &= hits - 1;
-                const int j = first + byCell[kb + t * 32 + lane];
-                if (!FILTER || !pair_contains(table, tableMask, pair_key(bi, entryIndex[j])))
+                // ... then the hits go to the warp's queue (the cache lookup is two dependent global loads: done one body at
+                // a time it was the whole kernel, 2-4 probes in flight per warp)
+                localHits += __popc(hits);
+                while (__any_sync(0xffffffffu, hits != 0u))
                 {
+                    unsigned entry = 0u;
+                    const bool have = hits != 0u;
+                    if (have)
+                    {
+                        const int t = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const int rel = byCell[kb + t * 32 + lane];
+                        const int chunk = (first + rel - i - 1) / kChunk;
+                        entry = unsigned(rel) | (unsigned(i - i0) << 12) | (unsigned(chunk) << 20);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, have);
+                    if (have) sQueue[warp][qn + __popc(m & ((1u << lane) - 1u))] = entry;
+                    qn += __popc(m);
+                    __syncwarp();
+                    while (qn > kDrainAbove) qn = drain_queue(sQueue[warp], qn, lane, i0, first, entryIndex, table, tableMask, &sCount[0][0], kCountWords);
+                }
+            }
+            else
+            {
+                while (hits)
+                {
+                    const int t = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const int j = first + byCell[kb + t * 32 + lane];
                     const int chunk = (j - i - 1) / kChunk;
 #pragma unroll
                     for (int c = 0; c <= kTileCap / kChunk; ++c)
@@ -469,17 +516,36 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(Count nc, const in
                 }
             }
         }
-#pragma unroll
-        for (int c = 0; c <= kTileCap / kChunk; ++c)
+        if (!FILTER)
         {
-            if (c < numItems)
+#pragma unroll
+            for (int c = 0; c <= kTileCap / kChunk; ++c)
             {
-                int v = counts[c];
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) itemCount[item + c] = v;
+                if (c < numItems)
+                {
+                    int v = counts[c];
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) itemCount[item + c] = v;
+                }
             }
         }
         localTests += (unsigned long long)len;   // what the reference's scan would have tested
+    }
+    if (FILTER)
+    {
+        while (qn > 0) qn = drain_queue(sQueue[warp], qn, lane, i0, first, entryIndex, table, tableMask, &sCount[0][0], kCountWords);
+        __syncwarp();
+        // the counts of this warp's bodies (only this warp touched them): lane = body, one item per chunk
+        const int i = i0 + warp + lane * (kBlock / 32);
+        if (i < min(i0 + kTile, n))
+        {
+            const int len = end[i] - i - 1;
+            if (len > 0)
+            {
+                const int item = itemStart[i], numItems = (len + kChunk - 1) / kChunk;
+                for (int c = 0; c < numItems; ++c) itemCount[item + c] = int((sCount[i - i0][c >> 1] >> ((c & 1) * 16)) & 0xffffu);
+            }
+        }
     }
     for (int o = 16; o > 0; o >>= 1) localHits += __shfl_xor_sync(0xffffffffu, localHits, o);
     if (lane == 0)
