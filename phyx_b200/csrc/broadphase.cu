@@ -447,7 +447,6 @@ __global__ void __launch_bounds__(kBlock) k_sweep_count_tiled(Count nc, const in
         const int len = e - i - 1;
         if (len <= 0) continue;
         const float2 yi = (i == i0) ? entryY[i] : tileY[i - first];
-        const unsigned bi = FILTER ? entryIndex[i] : 0u;
         const int item = itemStart[i];
         const int numItems = (len + kChunk - 1) / kChunk;
         // candidates: the cells within reach of this body's y interval

@@ -19,6 +19,7 @@
 // All float arithmetic mirrors the reference operation by operation (--fmad=false).
 #include "common.cuh"
 #include "pairset.cuh"
+#include "scan.cuh"
 
 namespace phyx
 {
@@ -373,46 +374,57 @@ int collide_update_manifolds(phyx_b200_ctx* c)
 // alive[i] (0/1) -> prefix (exclusive scan).  K = number alive.  Movers = alive elements at index
 // >= K, numbered from the END; holes = dead elements at index < K, numbered from the FRONT.
 
-__global__ void __launch_bounds__(kBlock) k_list_movers(Count n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
-    int* __restrict__ moverIndex)
+// (the flags themselves are never stored: element i is alive iff the exclusive prefix steps up after it)
+__device__ __forceinline__ bool alive_at(const int* __restrict__ prefix, int i, int n, int total) { return (i + 1 < n ? prefix[i + 1] : total) != prefix[i]; }
+
+__global__ void __launch_bounds__(kBlock) k_list_movers(Count nc, const int* __restrict__ prefix, const int* __restrict__ totalPtr, int* __restrict__ moverIndex)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count_of(n)) return;
+    const int n = count_of(nc);
+    if (i >= n) return;
     const int K = *totalPtr;
-    if (i >= K && alive[i]) moverIndex[K - prefix[i] - 1] = i;   // alive elements after i: K - prefix[i] - 1
+    if (i >= K && alive_at(prefix, i, n, K)) moverIndex[K - prefix[i] - 1] = i;   // alive elements after i: K - prefix[i] - 1
 }
 
 // ================================================================================================
 // PackManifolds
 // ================================================================================================
 
-__global__ void __launch_bounds__(kBlock) k_manifold_alive(Count count, const int2* __restrict__ manBody, const int* __restrict__ manCount,
-    const float4* __restrict__ aabb, int* __restrict__ alive, const int* __restrict__ manColour, unsigned long long* __restrict__ bodyUsed)
+// alive flag of a manifold, computed inside the scan that ranks the survivors (scan.cuh): Collider.cpp:390
+struct ManifoldAlive
 {
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= count_of(count)) return;
-    int2 b = manBody[m];
-    float4 a1 = aabb[b.x], a2 = aabb[b.y];
-    // AABB2::Intersects, src/AABB2.h:18-23
-    bool apart = (a1.x > a2.z) || (a2.x > a1.z) || (a1.y > a2.w) || (a2.y > a1.w);
-    const bool keep = !(manCount[m] == 0 && apart);   // Collider.cpp:390
-    alive[m] = keep;
-    // a removed manifold hands its solver colour back to its bodies (colour.cu; the masks of static bodies are never read)
-    if (!keep && bodyUsed && manColour[m] >= 0)
+    const int2* manBody;
+    const int* manCount;
+    const float4* aabb;
+    const int* manColour;
+    unsigned long long* bodyUsed;
+    __device__ __forceinline__ bool vector_ok(const int*) const { return false; }
+    __device__ __forceinline__ void load4(int, int (&)[4]) const {}
+    __device__ __forceinline__ int load(int m) const
     {
-        const unsigned long long mask = ~(1ull << manColour[m]);
-        atomicAnd(&bodyUsed[b.x], mask);
-        atomicAnd(&bodyUsed[b.y], mask);
+        int2 b = manBody[m];
+        float4 a1 = aabb[b.x], a2 = aabb[b.y];
+        // AABB2::Intersects, src/AABB2.h:18-23
+        bool apart = (a1.x > a2.z) || (a2.x > a1.z) || (a1.y > a2.w) || (a2.y > a1.w);
+        const bool keep = !(manCount[m] == 0 && apart);   // Collider.cpp:390
+        // a removed manifold hands its solver colour back to its bodies (colour.cu; the masks of static bodies are never read)
+        if (!keep && bodyUsed && manColour[m] >= 0)
+        {
+            const unsigned long long mask = ~(1ull << manColour[m]);
+            atomicAnd(&bodyUsed[b.x], mask);
+            atomicAnd(&bodyUsed[b.y], mask);
+        }
+        return keep ? 1 : 0;
     }
-}
+};
 
-__global__ void __launch_bounds__(kBlock) k_manifold_fill(Count n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
+__global__ void __launch_bounds__(kBlock) k_manifold_fill(Count nc, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
     const int* __restrict__ moverIndex, int2* __restrict__ manBody, int* __restrict__ manCount, int* __restrict__ manColour,
     float4* __restrict__ contactPoints)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
-    const int K = *totalPtr;
-    if (m >= count_of(n) || m >= K || alive[m]) return;
+    const int K = *totalPtr, n = count_of(nc);
+    if (m >= n || m >= K || alive_at(prefix, m, n, K)) return;
     const int src = moverIndex[m - prefix[m]];   // holes before m: m - prefix[m]
     const int cnt = manCount[src];
     manBody[m] = manBody[src];
@@ -468,12 +480,12 @@ int collide_pack_manifolds(phyx_b200_ctx* c)
     const int grid = (M + kBlock - 1) / kBlock;
     const bool track = c->colourStateValid && c->colourStateBodies == c->bodyCount && c->bodyUsed.ptr;
     const Count Mc = c->count(M, &StepCtl::manifolds);
-    k_manifold_alive<<<grid, kBlock, 0, c->stream>>>(Mc, c->manBody.as<int2>(), c->manCount.as<int>(), c->aabb.as<float4>(), alive, c->manColour.as<int>(),
-        track ? c->bodyUsed.as<unsigned long long>() : nullptr);
-    c->launches++;
-    PHYX_TRY(exclusive_scan_count(c, alive, prefix, Mc, total));
-    k_list_movers<<<grid, kBlock, 0, c->stream>>>(Mc, alive, prefix, total, movers);
-    k_manifold_fill<<<grid, kBlock, 0, c->stream>>>(Mc, alive, prefix, total, movers, c->manBody.as<int2>(), c->manCount.as<int>(),
+    ManifoldAlive aliveOf = { c->manBody.as<int2>(), c->manCount.as<int>(), c->aabb.as<float4>(), c->manColour.as<int>(),
+        track ? c->bodyUsed.as<unsigned long long>() : nullptr };
+    (void)alive;
+    PHYX_TRY(exclusive_scan_with(c, aliveOf, prefix, Mc, total));
+    k_list_movers<<<grid, kBlock, 0, c->stream>>>(Mc, prefix, total, movers);
+    k_manifold_fill<<<grid, kBlock, 0, c->stream>>>(Mc, prefix, total, movers, c->manBody.as<int2>(), c->manCount.as<int>(),
         c->manColour.as<int>(), c->contactPoints.as<float4>());
     c->launches += 2;
     if (c->def.active)
@@ -504,25 +516,38 @@ __global__ void __launch_bounds__(kBlock) k_joint_reset(Count nj, phyx_contact_j
     if (j < count_of(nj)) joints[j].contactPointIndex = -1;   // World.cpp:83-86
 }
 
-// flag[p] = 1 for live contact points without a joint yet (solverIndex < 0)
-__global__ void __launch_bounds__(kBlock) k_point_new_flags(Count numPoints, const int* __restrict__ manCount, const float4* __restrict__ contactPoints,
-    int* __restrict__ isNew)
+// 1 for live contact points without a joint yet (solverIndex < 0), computed inside the scan that ranks them
+struct PointIsNew
 {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= count_of(numPoints)) return;
-    bool live = (p & 1) < manCount[p >> 1];
-    isNew[p] = live && __float_as_int(contactPoints[size_t(p) * 2 + 1].w) < 0;
-}
+    const int* manCount;
+    const float4* contactPoints;
+    __device__ __forceinline__ bool vector_ok(const int*) const { return false; }
+    __device__ __forceinline__ void load4(int, int (&)[4]) const {}
+    __device__ __forceinline__ int load(int p) const
+    {
+        const bool live = (p & 1) < manCount[p >> 1];
+        return (live && __float_as_int(contactPoints[size_t(p) * 2 + 1].w) < 0) ? 1 : 0;
+    }
+};
+
+struct JointAlive
+{
+    const phyx_contact_joint* joints;
+    __device__ __forceinline__ bool vector_ok(const int*) const { return false; }
+    __device__ __forceinline__ void load4(int, int (&)[4]) const {}
+    __device__ __forceinline__ int load(int j) const { return joints[j].contactPointIndex >= 0 ? 1 : 0; }
+};
 
 // World.cpp:91-124: new points get a joint appended in (manifold, point) order, known points re-attach
 __global__ void __launch_bounds__(kBlock) k_joint_match(Count numPoints, Count oldJointsC, const int2* __restrict__ manBody, const int* __restrict__ manCount,
-    float4* __restrict__ contactPoints, const int* __restrict__ isNew, const int* __restrict__ newRank, phyx_contact_joint* __restrict__ joints)
+    float4* __restrict__ contactPoints, const int* __restrict__ newRank, const int* __restrict__ newTotal, phyx_contact_joint* __restrict__ joints)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= count_of(numPoints)) return;
+    const int nP = count_of(numPoints);
+    if (p >= nP) return;
     const int oldJoints = count_of(oldJointsC);
     if ((p & 1) >= manCount[p >> 1]) return;
-    if (isNew[p])
+    if (alive_at(newRank, p, nP, *newTotal))
     {
         int j = oldJoints + newRank[p];
         int2 b = manBody[p >> 1];
@@ -542,18 +567,12 @@ __global__ void __launch_bounds__(kBlock) k_joint_match(Count numPoints, Count o
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_joint_alive(Count nj, const phyx_contact_joint* __restrict__ joints, int* __restrict__ alive)
-{
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < count_of(nj)) alive[j] = joints[j].contactPointIndex >= 0;
-}
-
-__global__ void __launch_bounds__(kBlock) k_joint_fill(Count n, const int* __restrict__ alive, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
+__global__ void __launch_bounds__(kBlock) k_joint_fill(Count nc, const int* __restrict__ prefix, const int* __restrict__ totalPtr,
     const int* __restrict__ moverIndex, phyx_contact_joint* __restrict__ joints)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int K = *totalPtr;
-    if (j >= count_of(n) || j >= K || alive[j]) return;
+    const int K = *totalPtr, n = count_of(nc);
+    if (j >= n || j >= K || alive_at(prefix, j, n, K)) return;
     joints[j] = joints[moverIndex[j - prefix[j]]];   // World.cpp:131-134
 }
 
@@ -587,9 +606,9 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         int* newRank = isNew + P;
         int* total = newRank + P;
         const Count Pc = c->count(P, &StepCtl::manifolds, 2);
-        k_point_new_flags<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(Pc, c->manCount.as<int>(), c->contactPoints.as<float4>(), isNew);
-        c->launches++;
-        PHYX_TRY(exclusive_scan_count(c, isNew, newRank, Pc, total));
+        PointIsNew isNewOf = { c->manCount.as<int>(), c->contactPoints.as<float4>() };
+        (void)isNew;
+        PHYX_TRY(exclusive_scan_with(c, isNewOf, newRank, Pc, total));
         if (deferred)
         {
             fresh = c->def.capFresh;
@@ -600,7 +619,7 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
             PHYX_TRY(fetch_small(c, total, sizeof(int), &fresh));
         PHYX_TRY(c->joints.reserve_keep(size_t(J0 + fresh > 0 ? J0 + fresh : 1) * sizeof(phyx_contact_joint), size_t(J0) * sizeof(phyx_contact_joint), c->stream));
         k_joint_match<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(Pc, J0c, c->manBody.as<int2>(), c->manCount.as<int>(),
-            c->contactPoints.as<float4>(), isNew, newRank, c->joints.as<phyx_contact_joint>());
+            c->contactPoints.as<float4>(), newRank, total, c->joints.as<phyx_contact_joint>());
         c->launches++;
     }
     const int J1 = J0 + fresh;
@@ -615,12 +634,13 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         int* total = movers + J1;
         const int grid = (J1 + kBlock - 1) / kBlock;
         const Count J1c = c->count(J1, &StepCtl::jointsGrown);
-        k_joint_alive<<<grid, kBlock, 0, c->stream>>>(J1c, c->joints.as<phyx_contact_joint>(), alive);
-        PHYX_TRY(exclusive_scan_count(c, alive, prefix, J1c, total));
-        k_list_movers<<<grid, kBlock, 0, c->stream>>>(J1c, alive, prefix, total, movers);
-        k_joint_fill<<<grid, kBlock, 0, c->stream>>>(J1c, alive, prefix, total, movers, c->joints.as<phyx_contact_joint>());
+        JointAlive aliveOf = { c->joints.as<phyx_contact_joint>() };
+        (void)alive;
+        PHYX_TRY(exclusive_scan_with(c, aliveOf, prefix, J1c, total));
+        k_list_movers<<<grid, kBlock, 0, c->stream>>>(J1c, prefix, total, movers);
+        k_joint_fill<<<grid, kBlock, 0, c->stream>>>(J1c, prefix, total, movers, c->joints.as<phyx_contact_joint>());
         k_joint_backlink<<<grid, kBlock, 0, c->stream>>>(total, c->joints.as<phyx_contact_joint>(), c->contactPoints.as<float4>());
-        c->launches += 4;
+        c->launches += 3;
         if (deferred)
         {
             k_ctl_joints<<<1, 32, 0, c->stream>>>(c->ctl(), total);
