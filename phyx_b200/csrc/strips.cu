@@ -40,6 +40,7 @@
 // Fallback: if a manifold spans non-adjacent strips, a row belongs to two cut sets, or a strip does not fit in shared
 // memory, the layout is rejected and the colour-major layout + grid-barrier kernels of solve.cu run instead.
 #include "common.cuh"
+#include "scan.cuh"
 #include "solve_math.cuh"
 #include "tma.cuh"
 
@@ -227,15 +228,23 @@ __global__ void k_strip_resample(int S, const int* __restrict__ cuts, const int*
     factorOut[k] = factor[lo];
 }
 
-// every dynamic row also counts (shared memory per strip is what limits its width)
-__global__ void __launch_bounds__(kBlock) k_strip_hist_rows(int nb, const unsigned* __restrict__ order, const unsigned char* __restrict__ bodyStatic,
-    const unsigned char* __restrict__ bodyOwner, int rank, int* __restrict__ hist)
+// the work of a row as the cut scan sees it: its manifolds' weights, plus a constant for every dynamic row (shared memory per
+// strip is what limits its width); added on the fly by the scan's loader (scan.cuh)
+struct RowWork
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nb) return;
-    const unsigned body = order ? order[r] : unsigned(r);
-    if (!bodyStatic[body] && (!bodyOwner || bodyOwner[body] == rank)) hist[r] += 24;
-}
+    const int* hist;
+    const unsigned* order;
+    const unsigned char* bodyStatic;
+    const unsigned char* bodyOwner;
+    int rank;
+    __device__ __forceinline__ bool vector_ok(const int*) const { return false; }
+    __device__ __forceinline__ void load4(int, int (&)[4]) const {}
+    __device__ __forceinline__ int load(int r) const
+    {
+        const unsigned body = order ? order[r] : unsigned(r);
+        return hist[r] + ((!bodyStatic[body] && (!bodyOwner || bodyOwner[body] == rank)) ? 24 : 0);
+    }
+};
 
 // cuts[q] = first row with at least q/S of the manifolds before it
 __global__ void __launch_bounds__(kBlock) k_strip_cuts(int nb, int S, const int* __restrict__ prefix, const int* __restrict__ total, const int* __restrict__ header,
@@ -381,14 +390,23 @@ __global__ void __launch_bounds__(kBlock) k_strip_keys(Count Mc, int S, const in
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_strip_split_flags(int nb, const int* __restrict__ flags, int* __restrict__ flagR, int* __restrict__ flagL)
+// header and bin table of a new layout
+__global__ void __launch_bounds__(kBlock) k_strip_init(int* __restrict__ header, int2* __restrict__ binRange, int bins)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nb) return;
-    const int f = flags[r];
-    flagR[r] = f & 1;
-    flagL[r] = (f >> 1) & 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 64) header[i] = i == H_ROW_LO ? 0x7f7f7f7f : 0;   // (larger than any row)
+    if (i < bins) binRange[i] = make_int2(0, 0);
 }
+
+// one bit of the boundary flags as the value the boundary-list scans rank (scan.cuh loader)
+struct FlagBit
+{
+    const int* flags;
+    int shift;
+    __device__ __forceinline__ bool vector_ok(const int*) const { return false; }
+    __device__ __forceinline__ void load4(int, int (&)[4]) const {}
+    __device__ __forceinline__ int load(int r) const { return (flags[r] >> shift) & 1; }
+};
 
 // boundary row lists in row order
 __global__ void __launch_bounds__(kBlock) k_strip_lists(int nb, const int* __restrict__ flags, const int* __restrict__ prefixR, const int* __restrict__ prefixL,
@@ -735,7 +753,6 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     sp.rowLimit = rowLimit;
 
     PHYX_TRY(sp.header.reserve(64 * sizeof(int)));
-    PHYX_TRY(sp.hist.reserve(size_t(nb + 1) * sizeof(int)));
     PHYX_TRY(sp.flags.reserve(size_t(nb + 1) * 3 * sizeof(int)));
     PHYX_TRY(sp.prefixR.reserve(size_t(nb + 1) * sizeof(int)));
     PHYX_TRY(sp.prefixL.reserve(size_t(nb + 1) * sizeof(int)));
@@ -745,21 +762,18 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     PHYX_TRY(sp.bStart.reserve(size_t(2 * S + 4) * sizeof(int)));
     PHYX_TRY(sp.binRange.reserve(size_t(bins) * sizeof(int2)));
     int* header = sp.header.as<int>();
+    // the three per-row arrays that start from zero share one buffer and one memset: boundary flags | work histogram | cover
     int* flags = sp.flags.as<int>();
-    int* flagR = flags + (nb + 1);
-    int* flagL = flags + 2 * (nb + 1);
-    PHYX_CUDA(cudaMemsetAsync(header, 0, 64 * sizeof(int), c->stream));
-    PHYX_CUDA(cudaMemsetAsync(header + H_ROW_LO, 0x7f, sizeof(int), c->stream));   // 0x7f7f7f7f: larger than any row
-    PHYX_CUDA(cudaMemsetAsync(sp.hist.ptr, 0, size_t(nb + 1) * sizeof(int), c->stream));
-    PHYX_CUDA(cudaMemsetAsync(sp.prefixL.ptr, 0, size_t(nb + 1) * sizeof(int), c->stream));   // `cover` until the boundary lists need it
-    PHYX_CUDA(cudaMemsetAsync(flags, 0, size_t(nb + 1) * sizeof(int), c->stream));
-    PHYX_CUDA(cudaMemsetAsync(sp.binRange.ptr, 0, size_t(bins) * sizeof(int2), c->stream));
+    int* hist = flags + (nb + 1);
+    int* cover = flags + 2 * (nb + 1);
+    PHYX_CUDA(cudaMemsetAsync(flags, 0, size_t(nb + 1) * 3 * sizeof(int), c->stream));
+    k_strip_init<<<(bins + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(header, sp.binRange.as<int2>(), bins);
+    c->launches++;
 
     // cuts that balance the manifold count (a manifold counts for its lower dynamic row)
     const int* activity = (c->activityValid && c->activityBodies == nb) ? c->bodyActivity.as<int>() : nullptr;
     const bool split = c->islandRanks > 1 && c->islandsValid && c->islandBodies == nb;
     const unsigned char* bodyOwner = split ? c->bodyOwner.as<unsigned char>() : nullptr;
-    int* cover = sp.prefixL.as<int>();
     // balance feedback from the previous solve of this world (same strip count, same bodies)
     PHYX_TRY(sp.cost.reserve(size_t(2 * S + 2) * sizeof(long long)));
     PHYX_TRY(sp.factor.reserve(size_t(3 * S + 3) * sizeof(float)));
@@ -776,11 +790,10 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
         c->launches++;
     }
     const Count Mc = c->count(M, &StepCtl::manifolds);
-    k_strip_hist<<<grid, kBlock, 0, c->stream>>>(Mc, jb, work, rowOf, activity, c->manBody.as<int2>(), bodyOwner, c->islandRank, sp.hist.as<int>(), cover, S,
+    k_strip_hist<<<grid, kBlock, 0, c->stream>>>(Mc, jb, work, rowOf, activity, c->manBody.as<int2>(), bodyOwner, c->islandRank, hist, cover, S,
         feedback ? prevCuts : nullptr, feedback ? factorFb : nullptr, header);
-    k_strip_hist_rows<<<gridB, kBlock, 0, c->stream>>>(nb, order, c->bodyStatic.as<unsigned char>(), bodyOwner, c->islandRank, sp.hist.as<int>());
-    c->launches++;
-    PHYX_TRY(exclusive_scan_i32(c, sp.hist.as<int>(), sp.prefixR.as<int>(), nb, header + H_SCAN_TOTAL));
+    PHYX_TRY(exclusive_scan_with(c, RowWork{ hist, order, c->bodyStatic.as<unsigned char>(), bodyOwner, c->islandRank }, sp.prefixR.as<int>(),
+        Count(nb), header + H_SCAN_TOTAL));
     k_strip_cuts<<<gridS, kBlock, 0, c->stream>>>(nb, S, sp.prefixR.as<int>(), header + H_SCAN_TOTAL, header, sp.cuts.as<int>());
     c->launches += 2;
     if (S > 1)
@@ -834,10 +847,8 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     const uint2* sorted = c->colourKeys.as<uint2>();
 
     // boundary row lists
-    k_strip_split_flags<<<gridB, kBlock, 0, c->stream>>>(nb, flags, flagR, flagL);
-    c->launches++;
-    PHYX_TRY(exclusive_scan_i32(c, flagR, sp.prefixR.as<int>(), nb, header + H_TOTAL_R));
-    PHYX_TRY(exclusive_scan_i32(c, flagL, sp.prefixL.as<int>(), nb, header + H_TOTAL_L));
+    PHYX_TRY(exclusive_scan_with(c, FlagBit{ flags, 0 }, sp.prefixR.as<int>(), Count(nb), header + H_TOTAL_R));
+    PHYX_TRY(exclusive_scan_with(c, FlagBit{ flags, 1 }, sp.prefixL.as<int>(), Count(nb), header + H_TOTAL_L));
     k_strip_lists<<<gridB, kBlock, 0, c->stream>>>(nb, flags, sp.prefixR.as<int>(), sp.prefixL.as<int>(),
         sp.bR.as<int>(), sp.bL.as<int>(), header);
     k_strip_starts<<<gridS, kBlock, 0, c->stream>>>(nb, S, sp.cuts.as<int>(), sp.prefixR.as<int>(), sp.prefixL.as<int>(), sp.bStart.as<int>(), header);
