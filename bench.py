@@ -461,7 +461,8 @@ def run_island_parallel(args, rank, world_size, local_rank):
         dist.all_reduce(sj, op=dist.ReduceOp.SUM)
         shard_info = [None] * world_size
         dist.all_gather_object(shard_info, {"rank": rank, "bodies": int(sw.global_index.shape[0]), "dynamic_bodies_owned": sw.dynamic_owned,
-                                            "joints": int(sstats[-1][1].joints), "ms_per_step": s0.elapsed_time(s1) / args.steps})
+                                            "joints": int(sstats[-1][1].joints), "ms_per_step": s0.elapsed_time(s1) / args.steps,
+                                            "steps_total": sw.steps, "deferred_steps_total": sw.deferred_steps, "graph_replays_total": sw.graph_replays})
         # e2e of the sharded run: this rank's bodies up and down every step
         shost = torch.from_numpy(sctx.download_bodies().view(np.uint8).reshape(-1)).pin_memory()
         shost_np = shost.numpy().view(bodies.dtype)

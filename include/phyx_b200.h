@@ -146,6 +146,10 @@ PHYX_B200_API int phyx_b200_synchronize(phyx_b200_ctx* ctx);
  * the drop-in.  upload converts the AoS records to the device SoA, download converts back and
  * fills every field the reference's stages write (velocity .. coords, geom.coords, geom.aabb). */
 PHYX_B200_API int phyx_b200_upload_bodies(phyx_b200_ctx* ctx, const phyx_rigid_body* bodies, int count);
+/* upload without waiting for the copy: `bodies` must be page-locked (phyx_b200_host_register) and stay untouched until the
+ * next call that waits for the device (world_step, download_bodies, synchronize).  What World::Update of the host mirror
+ * uses: the copy engine and the launch of the step then overlap the host's bookkeeping */
+PHYX_B200_API int phyx_b200_upload_bodies_async(phyx_b200_ctx* ctx, const phyx_rigid_body* bodies, int count);
 PHYX_B200_API int phyx_b200_download_bodies(phyx_b200_ctx* ctx, phyx_rigid_body* bodies, int count);
 PHYX_B200_API int phyx_b200_body_count(const phyx_b200_ctx* ctx);
 /* page-lock / release a caller buffer in place (e.g. World::bodies.data) so the copies above run at

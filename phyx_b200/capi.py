@@ -30,6 +30,7 @@ EXPORTS = (
     "phyx_b200_stream",
     "phyx_b200_synchronize",
     "phyx_b200_upload_bodies",
+    "phyx_b200_upload_bodies_async",
     "phyx_b200_download_bodies",
     "phyx_b200_body_count",
     "phyx_b200_host_register",
@@ -171,6 +172,7 @@ def load():
     l.phyx_b200_stream.restype = vp
     l.phyx_b200_synchronize.argtypes = [vp]
     l.phyx_b200_upload_bodies.argtypes = [vp, vp, i32]
+    l.phyx_b200_upload_bodies_async.argtypes = [vp, vp, i32]
     l.phyx_b200_download_bodies.argtypes = [vp, vp, i32]
     l.phyx_b200_body_count.argtypes = [vp]
     l.phyx_b200_host_register.argtypes = [vp, vp, C.c_size_t]

@@ -406,6 +406,17 @@ int phyx_b200_upload_bodies(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int
     return bodies_upload(c, bodies, count);
 }
 
+int phyx_b200_upload_bodies_async(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int count)
+{
+    PHYX_TRY(check(c));
+    if (count < 0 || (count > 0 && !bodies))
+    {
+        set_error("upload_bodies_async: bad arguments");
+        return PHYX_B200_ERR_ARGUMENT;
+    }
+    return bodies_upload(c, bodies, count, false);
+}
+
 int phyx_b200_download_bodies(phyx_b200_ctx* c, phyx_rigid_body* bodies, int count)
 {
     PHYX_TRY(check(c));

@@ -190,7 +190,7 @@ static int reserve_bodies(phyx_b200_ctx* c, int n)
     return PHYX_B200_OK;
 }
 
-int bodies_upload(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int n)
+int bodies_upload(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int n, bool wait)
 {
     PHYX_TRY(reserve_bodies(c, n));
     c->bodyCount = n;
@@ -203,8 +203,9 @@ int bodies_upload(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int n)
         c->acc.as<float4>(), c->params.as<float4>(), c->rot.as<float4>(), c->aabb.as<float4>(), c->size.as<float2>());
     c->launches++;
     PHYX_CUDA(cudaGetLastError());
-    // the source may be pageable memory that the caller mutates right after: finish the copy now
-    PHYX_CUDA(cudaStreamSynchronize(c->stream));
+    // the source may be pageable memory that the caller mutates right after: finish the copy now (unless the caller has
+    // promised to leave the array alone until its next synchronising call: phyx_b200_upload_bodies_async)
+    if (wait) PHYX_CUDA(cudaStreamSynchronize(c->stream));
     return PHYX_B200_OK;
 }
 

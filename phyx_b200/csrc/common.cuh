@@ -325,7 +325,7 @@ inline cudaError_t record_event(phyx_b200_ctx* c, cudaEvent_t ev)
 }
 
 // bodies.cu
-int bodies_upload(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int n);
+int bodies_upload(phyx_b200_ctx* c, const phyx_rigid_body* bodies, int n, bool wait = true);
 int bodies_download(phyx_b200_ctx* c, phyx_rigid_body* bodies, int n);
 int bodies_integrate_velocity(phyx_b200_ctx* c, float dt, float gravity);
 int bodies_integrate_position(phyx_b200_ctx* c, float dt);

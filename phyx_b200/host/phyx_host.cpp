@@ -85,7 +85,11 @@ void Device::upload(RigidBody* bodies, int count)
             pinnedBytes = size_t(count) * sizeof(RigidBody);
         }
     }
-    PHYX_CALL(phyx_b200_upload_bodies(ctx, reinterpret_cast<const phyx_rigid_body*>(bodies), count));
+    // inside World::Update with the array page-locked, nobody touches it before the step's own read-back: no need to wait
+    if (inUpdateUpload && pinnedPtr == bodies)
+        PHYX_CALL(phyx_b200_upload_bodies_async(ctx, reinterpret_cast<const phyx_rigid_body*>(bodies), count));
+    else
+        PHYX_CALL(phyx_b200_upload_bodies(ctx, reinterpret_cast<const phyx_rigid_body*>(bodies), count));
     resident = true;
     residentCount = count;
 }
@@ -293,7 +297,11 @@ void World::Update(WorkQueue& queue, float dt, const Configuration& configuratio
     // the reference's semantics: World::bodies is the source of truth at entry.  With the opt-in lazyBodies contract
     // it only is when the caller said so.
     if (!device.lazyBodies || device.hostEdited || !device.resident || device.residentCount != int(bodies.size))
+    {
+        device.inUpdateUpload = device.fusedUpdate && !collider.mirrorBroadphase;   // (the fused step ends with a wait)
         device.upload(bodies.data, bodies.size);
+        device.inUpdateUpload = false;
+    }
     device.hostEdited = false;
     device.inUpdate = true;
 

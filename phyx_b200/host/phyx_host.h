@@ -351,6 +351,7 @@ struct Device
     double stepMs = 0;         // wall time of the fused step (phyx_b200_world_step) when World::Update takes it
     bool fusedUpdate = true;   // World::Update = one phyx_b200_world_step call (false: the eight stage calls, same results)
     bool lastStepDeferred = false;
+    bool inUpdateUpload = false;   // this upload is World::Update's own (may skip the wait: phyx_b200_upload_bodies_async)
     bool pinBodies = true;     // page-lock World::bodies in place for full-rate PCIe copies
     void* pinnedPtr = nullptr;
     size_t pinnedBytes = 0;

@@ -201,6 +201,7 @@ class ShardedWorld:
         self.rank, self.ranks = dist.get_rank(group), dist.get_world_size(group)
         self.check_every, self.margin, self.steps = check_every, margin, 0
         self.deferred_steps = 0
+        self.graph_replays = 0
         # probe: the contact graph of the full scene after a few full steps, identical on every rank
         import ctypes as C
 
@@ -234,6 +235,7 @@ class ShardedWorld:
         # World::Update of this rank's shard as one C-ABI call (counts stay on the device, one read-back per step)
         st, bp, info = self.ctx.world_step(scenes.DT, scenes.GRAVITY, iters=iters, schedule=capi.SCHEDULE_COLOUR)
         self.deferred_steps += int(info.deferred)
+        self.graph_replays += int(info.graphReplay)
         self.steps += 1
         if self.check_every and self.steps % self.check_every == 0:
             self.check_apart()
