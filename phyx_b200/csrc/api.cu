@@ -335,7 +335,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     DevBuf* bufs[] = { &c->vel, &c->disp, &c->acc, &c->params, &c->rot, &c->aabb, &c->size, &c->aos, &c->snap, &c->snapJoints, &c->sortA, &c->sortB, &c->hist,
         &c->scanTmp, &c->entry, &c->entryIndex, &c->sweepEnd, &c->itemStart, &c->items, &c->itemCount, &c->pairs, &c->counters, &c->joints,
         &c->contactPoints, &c->slotJoint, &c->levels, &c->q0, &c->q1, &c->q2, &c->q3, &c->accNF, &c->accD, &c->stamps, &c->solveFlags, &c->slotPos, &c->processed,
-        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->pairQ, &c->pairIdx, &c->bodyActivity, &c->islandTmp, &c->bodyOwner, &c->ctlBuf };
+        &c->colourTmp, &c->colourKeys, &c->colourSorted, &c->manBody, &c->manCount, &c->pairTable, &c->collideTmp, &c->manColour, &c->bodyUsed, &c->bodyStatic, &c->solveRows, &c->rowOf, &c->tileLong, &c->strictLevels, &c->strictMap, &c->staticMulti, &c->rowsMulti, &c->pairQ, &c->pairIdx, &c->bodyActivity, &c->islandTmp, &c->bodyOwner, &c->ctlBuf, &c->jointStamp };
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -1067,7 +1067,7 @@ static int deferred_prepare(phyx_b200_ctx* c, float dt, float gravity, const phy
     // (belt and braces: the addresses of the buffers that grow with the world)
     const DevBuf* watched[] = { &c->manBody, &c->manCount, &c->manColour, &c->contactPoints, &c->joints, &c->collideTmp, &c->colourTmp, &c->colourKeys,
         &c->colourSorted, &c->slotJoint, &c->pairQ, &c->pairIdx, &c->accNF, &c->accD, &c->solveRows, &c->items, &c->itemCount, &c->pairs, &c->pairTable,
-        &c->hist, &c->scanTmp, &c->strip.pairTest, &c->strip.sync, &c->bodyActivity };
+        &c->hist, &c->scanTmp, &c->strip.pairTest, &c->strip.sync, &c->bodyActivity, &c->jointStamp };
     for (const DevBuf* b : watched) mix((unsigned long long)(uintptr_t)b->ptr);
     *keyOut = h;
     return PHYX_B200_OK;

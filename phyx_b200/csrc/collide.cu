@@ -471,10 +471,9 @@ int collide_pack_manifolds(phyx_b200_ctx* c)
     const int M = c->manifoldCount;
     c->jointUnitsValid = false;   // contact points move; RefreshContactJoints re-links the joints
     if (M == 0) return PHYX_B200_OK;
-    // scratch: alive[M] | prefix[M] | movers[M] | total
-    PHYX_TRY(c->collideTmp.reserve((size_t(M) * 3 + 4) * sizeof(int)));
-    int* alive = c->collideTmp.as<int>();
-    int* prefix = alive + M;
+    // scratch: prefix[M] | movers[M] | total  (the alive flags are computed inside the scan and never stored)
+    PHYX_TRY(c->collideTmp.reserve((size_t(M) * 2 + 4) * sizeof(int)));
+    int* prefix = c->collideTmp.as<int>();
     int* movers = prefix + M;
     int* total = movers + M;
     const int grid = (M + kBlock - 1) / kBlock;
@@ -482,7 +481,6 @@ int collide_pack_manifolds(phyx_b200_ctx* c)
     const Count Mc = c->count(M, &StepCtl::manifolds);
     ManifoldAlive aliveOf = { c->manBody.as<int2>(), c->manCount.as<int>(), c->aabb.as<float4>(), c->manColour.as<int>(),
         track ? c->bodyUsed.as<unsigned long long>() : nullptr };
-    (void)alive;
     PHYX_TRY(exclusive_scan_with(c, aliveOf, prefix, Mc, total));
     k_list_movers<<<grid, kBlock, 0, c->stream>>>(Mc, prefix, total, movers);
     k_manifold_fill<<<grid, kBlock, 0, c->stream>>>(Mc, prefix, total, movers, c->manBody.as<int2>(), c->manCount.as<int>(),
@@ -510,10 +508,13 @@ int collide_pack_manifolds(phyx_b200_ctx* c)
 // RefreshContactJoints
 // ================================================================================================
 
-__global__ void __launch_bounds__(kBlock) k_joint_reset(Count nj, phyx_contact_joint* __restrict__ joints)
+// World.cpp:83-86 marks every joint dead (contactPointIndex = -1) before the contact points claim theirs.  Here a joint is
+// alive iff its STAMP is this refresh's epoch: the match kernel stamps the joints it touches, nothing has to be reset (a
+// pass over the 20-byte joint records just to clear one word), and the survivor scan reads 4 contiguous bytes per joint.
+// The epoch lives in device memory (its launch parameter must not change from step to step: graph replay).
+__global__ void k_joint_epoch(int* __restrict__ epoch)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < count_of(nj)) joints[j].contactPointIndex = -1;   // World.cpp:83-86
+    if (threadIdx.x == 0 && blockIdx.x == 0) *epoch += 1;
 }
 
 // 1 for live contact points without a joint yet (solverIndex < 0), computed inside the scan that ranks them
@@ -532,20 +533,23 @@ struct PointIsNew
 
 struct JointAlive
 {
-    const phyx_contact_joint* joints;
+    const int* stamp;
+    const int* epoch;
     __device__ __forceinline__ bool vector_ok(const int*) const { return false; }
     __device__ __forceinline__ void load4(int, int (&)[4]) const {}
-    __device__ __forceinline__ int load(int j) const { return joints[j].contactPointIndex >= 0 ? 1 : 0; }
+    __device__ __forceinline__ int load(int j) const { return stamp[j] == __ldg(epoch) ? 1 : 0; }
 };
 
 // World.cpp:91-124: new points get a joint appended in (manifold, point) order, known points re-attach
 __global__ void __launch_bounds__(kBlock) k_joint_match(Count numPoints, Count oldJointsC, const int2* __restrict__ manBody, const int* __restrict__ manCount,
-    float4* __restrict__ contactPoints, const int* __restrict__ newRank, const int* __restrict__ newTotal, phyx_contact_joint* __restrict__ joints)
+    float4* __restrict__ contactPoints, const int* __restrict__ newRank, const int* __restrict__ newTotal, phyx_contact_joint* __restrict__ joints,
+    int* __restrict__ stamp, const int* __restrict__ epochPtr)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int nP = count_of(numPoints);
     if (p >= nP) return;
     const int oldJoints = count_of(oldJointsC);
+    const int epoch = __ldg(epochPtr);
     if ((p & 1) >= manCount[p >> 1]) return;
     if (alive_at(newRank, p, nP, *newTotal))
     {
@@ -558,12 +562,14 @@ __global__ void __launch_bounds__(kBlock) k_joint_match(Count numPoints, Count o
         jt.normalLimiter_accumulatedImpulse = 0.f;
         jt.frictionLimiter_accumulatedImpulse = 0.f;
         joints[j] = jt;
+        stamp[j] = epoch;
         reinterpret_cast<int*>(contactPoints + size_t(p) * 2 + 1)[3] = j;
     }
     else
     {
         int j = __float_as_int(contactPoints[size_t(p) * 2 + 1].w);
         joints[j].contactPointIndex = p;
+        stamp[j] = epoch;
     }
 }
 
@@ -584,6 +590,15 @@ __global__ void __launch_bounds__(kBlock) k_joint_backlink(const int* __restrict
     reinterpret_cast<int*>(contactPoints + size_t(joints[j].contactPointIndex) * 2 + 1)[3] = j;   // World.cpp:140
 }
 
+// stamps of the joints (see k_joint_epoch); a new buffer starts from zeros (epochs start at 1)
+static int reserve_stamps(phyx_b200_ctx* c, int joints)
+{
+    const void* before = c->jointStamp.ptr;
+    PHYX_TRY(c->jointStamp.reserve(size_t(joints > 0 ? joints : 1) * sizeof(int)));
+    if (c->jointStamp.ptr != before) PHYX_CUDA(cudaMemsetAsync(c->jointStamp.ptr, 0, c->jointStamp.cap, c->stream));
+    return PHYX_B200_OK;
+}
+
 int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* deleted)
 {
     // deferred step: J0 is exact (nothing before this stage changes the joints), P, `fresh`, J1 are bounds; the true counts
@@ -592,22 +607,18 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
     const int J0 = c->jointCount, P = 2 * c->manifoldCount;
     int fresh = 0;
     const Count J0c = c->count(J0, &StepCtl::joints);
-    if (J0 > 0)
-    {
-        k_joint_reset<<<(J0 + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(J0c, c->joints.as<phyx_contact_joint>());
-        c->launches++;
-    }
-    // scratch A (points): isNew[P] | newRank[P] | total
-    size_t needA = size_t(P) * 2 + 4;
+    int* epoch = c->mailboxSeqDev + 1;   // (a spare word of that small device block)
+    k_joint_epoch<<<1, 32, 0, c->stream>>>(epoch);
+    c->launches++;
+    // scratch A (points): newRank[P] | total
+    size_t needA = size_t(P) + 4;
     PHYX_TRY(c->collideTmp.reserve(needA * sizeof(int)));
     if (P > 0)
     {
-        int* isNew = c->collideTmp.as<int>();
-        int* newRank = isNew + P;
+        int* newRank = c->collideTmp.as<int>();
         int* total = newRank + P;
         const Count Pc = c->count(P, &StepCtl::manifolds, 2);
         PointIsNew isNewOf = { c->manCount.as<int>(), c->contactPoints.as<float4>() };
-        (void)isNew;
         PHYX_TRY(exclusive_scan_with(c, isNewOf, newRank, Pc, total));
         if (deferred)
         {
@@ -618,24 +629,24 @@ int collide_refresh_joints(phyx_b200_ctx* c, int* matched, int* created, int* de
         else
             PHYX_TRY(fetch_small(c, total, sizeof(int), &fresh));
         PHYX_TRY(c->joints.reserve_keep(size_t(J0 + fresh > 0 ? J0 + fresh : 1) * sizeof(phyx_contact_joint), size_t(J0) * sizeof(phyx_contact_joint), c->stream));
+        PHYX_TRY(reserve_stamps(c, J0 + fresh));
         k_joint_match<<<(P + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(Pc, J0c, c->manBody.as<int2>(), c->manCount.as<int>(),
-            c->contactPoints.as<float4>(), newRank, total, c->joints.as<phyx_contact_joint>());
+            c->contactPoints.as<float4>(), newRank, total, c->joints.as<phyx_contact_joint>(), c->jointStamp.as<int>(), epoch);
         c->launches++;
     }
     const int J1 = J0 + fresh;
     int K = 0;
     if (J1 > 0)
     {
-        // scratch B (joints): alive[J1] | prefix[J1] | movers[J1] | total  (scratch A is dead by now)
-        PHYX_TRY(c->collideTmp.reserve((size_t(J1) * 3 + 4) * sizeof(int)));
-        int* alive = c->collideTmp.as<int>();
-        int* prefix = alive + J1;
+        // scratch B (joints): prefix[J1] | movers[J1] | total  (scratch A is dead by now)
+        PHYX_TRY(c->collideTmp.reserve((size_t(J1) * 2 + 4) * sizeof(int)));
+        int* prefix = c->collideTmp.as<int>();
         int* movers = prefix + J1;
         int* total = movers + J1;
         const int grid = (J1 + kBlock - 1) / kBlock;
         const Count J1c = c->count(J1, &StepCtl::jointsGrown);
-        JointAlive aliveOf = { c->joints.as<phyx_contact_joint>() };
-        (void)alive;
+        PHYX_TRY(reserve_stamps(c, J1));   // (P == 0: no match ran, every stamp is older than the epoch: all joints go)
+        JointAlive aliveOf = { c->jointStamp.as<int>(), epoch };
         PHYX_TRY(exclusive_scan_with(c, aliveOf, prefix, J1c, total));
         k_list_movers<<<grid, kBlock, 0, c->stream>>>(J1c, prefix, total, movers);
         k_joint_fill<<<grid, kBlock, 0, c->stream>>>(J1c, prefix, total, movers, c->joints.as<phyx_contact_joint>());

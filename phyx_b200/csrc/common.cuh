@@ -104,7 +104,7 @@ struct StripPlan
     int maxStripRows = 0, maxCutRows = 0, maxBin = 0, colours = 0, cutManifolds = 0, manifolds = 0;
     bool attributeSet = false;
     int rejected = 0;          // why the last layout attempt was not usable (bit mask, see strips.cu), 0 = usable
-    DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, header, sync, hist, trace, pairTest, cost, factor, prevCuts;
+    DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, header, sync, trace, pairTest, cost, factor, prevCuts;
     int feedbackStrips = 0, feedbackBodies = 0;   // the balance feedback (measured cost per strip) belongs to this layout shape
     bool measuredFeedback = true;   // phyx_b200_strip_feedback: balance the cuts by the measured cost of the previous solve's strips
     int tracePasses = 0;       // developer aid (phyx_b200_strip_trace): passes of the next solves to time-stamp per CTA
@@ -237,6 +237,7 @@ struct phyx_b200_ctx
     // ---- solve ----------------------------------------------------------------------------
     int jointCount = 0, contactPointCount = 0;
     phyx::DevBuf joints;         // phyx_contact_joint AoS (device copy)
+    phyx::DevBuf jointStamp;     // int per joint: refresh epoch in which a contact point last claimed it (collide.cu)
     phyx::DevBuf contactPoints;  // phyx_contact_point AoS (device copy)
     int slotCount = 0, levelCount = 0;
     phyx::DevBuf slotJoint;      // int: joint index of slot (or -1)

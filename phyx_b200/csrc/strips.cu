@@ -1031,7 +1031,7 @@ int strip_host_levels(phyx_b200_ctx* c, std::vector<int>* classStart)
 void strip_release(phyx_b200_ctx* c)
 {
     StripPlan& sp = c->strip;
-    DevBuf* bufs[] = { &sp.cuts, &sp.binRange, &sp.flags, &sp.prefixR, &sp.prefixL, &sp.bR, &sp.bL, &sp.bStart, &sp.header, &sp.sync, &sp.hist, &sp.trace, &sp.pairTest, &sp.cost, &sp.factor, &sp.prevCuts };
+    DevBuf* bufs[] = { &sp.cuts, &sp.binRange, &sp.flags, &sp.prefixR, &sp.prefixL, &sp.bR, &sp.bL, &sp.bStart, &sp.header, &sp.sync, &sp.trace, &sp.pairTest, &sp.cost, &sp.factor, &sp.prevCuts };
     for (DevBuf* b : bufs) b->release();
     sp.valid = false;
 }

@@ -41,6 +41,28 @@ def test_struct_sizes_match_header():
     assert C.sizeof(capi.BroadphaseStats) == 8 + 8 + 12 + 4  # 3 floats + tail padding
 
 
+def test_struct_layouts_match_the_compiled_header(tmp_path):
+    """sizeof / offsetof of every struct that crosses the ABI, from the header itself (gcc), against the ctypes mirrors and the
+    host mirror's use of them: a field added on one side only would smash a caller's stack."""
+    structs = {"phyx_b200_solve_config": capi.SolveConfig, "phyx_b200_solve_stats": capi.SolveStats,
+               "phyx_b200_broadphase_stats": capi.BroadphaseStats, "phyx_b200_step_info": capi.StepInfo}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "phyx_b200.h"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for field, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{field} %zu\\n", offsetof({cname}, {field}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for field, _ in ct._fields_:
+            assert int(got[f"{cname}.{field}"]) == getattr(ct, field).offset, f"{cname}.{field}"
+
+
 def test_header_cites_reference_interfaces():
     text = open(os.path.join(ROOT, "include", "phyx_b200.h")).read()
     for cite in ("src/World.cpp:39-70", "src/Collider.cpp:251-284", "src/Collider.cpp:296-366", "src/Solver.cpp:17-119", "src/RigidBody.h:12-58"):
