@@ -801,7 +801,7 @@ def run_ours(args, rank, world_size, local_rank):
             "stage_calls_ms_per_step": stage_calls_ms,
             "note": "deferred = counts on the device, one read-back per step; graph replay = the whole step is one CUDA-graph launch (same bounds and buffers as the step before); a stopped step is finished by the stage functions (reasons: include/phyx_b200.h)",
         },
-        "strip_plan": {k: v for k, v in plan.items() if k in ("strips", "usable", "rejected", "max_strip_rows", "max_cut_rows", "max_bin", "colours", "cut_manifolds")},
+        "strip_plan": {k: v for k, v in plan.items() if k in ("strips", "usable", "rejected", "last_reject", "max_strip_rows", "max_cut_rows", "max_bin", "colours", "cut_manifolds")},
         "resident_stage_wall_ms": {k: round(v / max(stage_steps, 1), 3) for k, v in stage_wall.items()},
         "resident_stage_wall_ms_max": {k: round(v, 3) for k, v in stage_max.items()},
         "device_allocations_in_timed_region": {"count": allocs1[0] - allocs0[0], "host_ms": round(allocs1[1] - allocs0[1], 3)},

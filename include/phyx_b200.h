@@ -209,7 +209,7 @@ PHYX_B200_API int phyx_b200_strip_feedback(phyx_b200_ctx* ctx, int measured);
 /* The strip layout of the last solve: *strips = S (0: the last solve did not use strips), cuts[S+1] = row cuts,
  * classSlotStart[2S+1] = first slot of each class (class k < S: interior of strip k, class S+k: cut set between strips
  * k and k+1), info[8] = {usable, reject mask, rows of the largest strip, rows of the largest cut set, largest bin,
- * static bodies, colours, cut manifolds}.  capacity = entries available in cuts / classSlotStart; any pointer may be NULL. */
+ * last rejection (sticky: mask | strips << 8 | widest strip rows / 64 << 20), colours, cut manifolds}.  capacity = entries available in cuts / classSlotStart; any pointer may be NULL. */
 PHYX_B200_API int phyx_b200_strip_plan(phyx_b200_ctx* ctx, int32_t* strips, int32_t* cuts, int32_t* classSlotStart, int32_t capacity, int32_t* info);
 
 /* Developer aid (no reference counterpart; the reference instruments its solve with microprofile scopes, Solver.cpp:132):

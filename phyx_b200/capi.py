@@ -422,7 +422,7 @@ class Context:
         n = C.c_int32(0)
         info = np.zeros(8, np.int32)
         self._check(self.l.phyx_b200_strip_plan(self.h, C.byref(n), None, None, 0, _p(info)))
-        names = ("usable", "rejected", "max_strip_rows", "max_cut_rows", "max_bin", "statics", "colours", "cut_manifolds")
+        names = ("usable", "rejected", "max_strip_rows", "max_cut_rows", "max_bin", "last_reject", "colours", "cut_manifolds")
         out = dict(zip(names, (int(v) for v in info)))
         out["strips"] = n.value
         if n.value == 0:

@@ -599,7 +599,8 @@ int phyx_b200_strip_plan(phyx_b200_ctx* c, int32_t* strips, int32_t* cuts, int32
     if (strips) *strips = sp.valid ? sp.strips : 0;
     if (info)
     {
-        const int v[8] = { sp.valid ? 1 : 0, sp.rejected, sp.maxStripRows, sp.maxCutRows, sp.maxBin, 0, sp.colours, sp.cutManifolds };
+        // [5]: the last rejection of this context, sticky: reason mask | strips << 8 | (rows of the widest strip / 64) << 20
+        const int v[8] = { sp.valid ? 1 : 0, sp.rejected, sp.maxStripRows, sp.maxCutRows, sp.maxBin, sp.lastReject, sp.colours, sp.cutManifolds };
         memcpy(info, v, sizeof(v));
     }
     if (!sp.valid || (!cuts && !classSlotStart)) return PHYX_B200_OK;

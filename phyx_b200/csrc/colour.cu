@@ -845,11 +845,24 @@ static int colour_units_build(phyx_b200_ctx* c, bool incremental, bool* staticsC
             }
             // strips narrower than the bodies' reach (a manifold across non-adjacent strips, a row in two cut sets): try
             // half as many, and remember what worked for the next steps of this world (one strip always works, if it fits)
+            // too large for shared memory only (the side buffers grew, e.g. larger bins after a full recolouring): once
+            // more with the rows that the side buffers just measured leave room for, instead of a step on the fallback forms
+            if (!usable && c->strip.rejected == 4 && c->strip.rowLimitForce == 0 && c->strip.maxStripRows > 0)
+            {
+                const long long side = (long long)(c->strip.maxCutRows + 64) * 24 + (long long)(c->strip.maxBin + 64) * 2;
+                const long long rows = ((227ll * 1024 - 4096 - side) / 16 - 32) & ~63ll;
+                if (rows >= (nb + S - 1) / S + 64 && rows < c->strip.maxStripRows)
+                {
+                    c->strip.rowLimitForce = int(rows);
+                    continue;
+                }
+            }
             if (usable || c->strip.want > 0 || S == 1 || !(c->strip.rejected & 3)) break;
             S = std::max(1, S / 2);
             c->strip.autoLimit = S;
             c->strip.limitAge = 0;
         }
+        c->strip.rowLimitForce = 0;
         if (res[1])
         {
             c->strip.valid = false;   // the layout was built on colours that do not exist

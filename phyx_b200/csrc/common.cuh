@@ -101,9 +101,11 @@ struct StripPlan
     int autoLimit = 0;         // largest S worth trying when choosing (halved whenever a layout is rejected as too narrow)
     int limitAge = 0;          // usable layouts since autoLimit last changed (strip_limit_recover)
     int rowLimit = 0;          // rows a strip of the current layout may have (strips.cu strip_row_limit)
+    int rowLimitForce = 0;     // > 0: a tighter limit for the retry of a layout that was rejected for its shared-memory size
     int maxStripRows = 0, maxCutRows = 0, maxBin = 0, colours = 0, cutManifolds = 0, manifolds = 0;
     bool attributeSet = false;
     int rejected = 0;          // why the last layout attempt was not usable (bit mask, see strips.cu), 0 = usable
+    int lastReject = 0;        // the last rejection, sticky: mask | strips << 8 | (widest strip's rows / 64) << 20 (diagnostics)
     DevBuf cuts, binRange, flags, prefixR, prefixL, bR, bL, bStart, header, sync, trace, pairTest, cost, factor, prevCuts;
     int feedbackStrips = 0, feedbackBodies = 0;   // the balance feedback (measured cost per strip) belongs to this layout shape
     bool measuredFeedback = true;   // phyx_b200_strip_feedback: balance the cuts by the measured cost of the previous solve's strips

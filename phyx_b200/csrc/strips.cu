@@ -53,6 +53,7 @@ constexpr int kBlock = 256;
 constexpr int kStripU = 8;         // candidates per thread whose index words are prefetched one bin ahead
 constexpr int kStripBins = kMaxColours;   // bins (colours) per class
 constexpr int kStripMax = 1023;           // strips per layout (the class digit of the layout sort has 2048 bins)
+constexpr size_t kStripSmemLimit = 227 * 1024 - 4096;   // dynamic shared memory of the strip kernel: the opt-in maximum minus its static tables
 constexpr int kStripRowLimit = 10240;     // rows per strip (160 KB of the SM's 228 KB: the record fetches of step 2 want the rest as L1)
 
 // layout header (device ints)
@@ -713,11 +714,20 @@ __global__ void k_strip_verdict(StepCtl* ctl, const int* __restrict__ header, co
 int strip_row_limit(const phyx_b200_ctx* c, int S)
 {
     const StripPlan& sp = c->strip;
-    if (S <= 1 || sp.feedbackStrips != S || sp.feedbackBodies != c->bodyCount || sp.maxStripRows <= 0) return kStripRowLimit;
+    if (S <= 1 || sp.feedbackStrips != S || sp.feedbackBodies != c->bodyCount || sp.maxStripRows <= 0)
+        return sp.rowLimitForce > 0 ? std::min(sp.rowLimitForce, kStripRowLimit) : kStripRowLimit;
     const long long side = (long long)(sp.maxCutRows + sp.maxCutRows / 8 + 72) * 24 + (long long)(sp.maxBin + sp.maxBin / 8 + 72) * 2 + 5 * 1024;
     long long rows = ((196 * 1024 - side) / 16 - 16) & ~255ll;
     const int avg = (c->bodyCount + S - 1) / S;
-    if (rows < avg + avg / 7 || rows < 2048) return kStripRowLimit;   // these strips do not fit that carve-out anyway
+    if (rows < avg + avg / 7 || rows < 2048)
+    {
+        // these strips do not fit that carve-out anyway: what the whole shared memory leaves for rows beside the side
+        // buffers (kStripRowLimit assumes ~60 KB of them; a layout with more must keep its strips narrower or it is rejected)
+        rows = ((long long)kStripSmemLimit + 5 * 1024 - side) / 16 - 32;
+        rows &= ~63ll;
+        if (rows < avg + 64) return kStripRowLimit;
+    }
+    if (sp.rowLimitForce > 0) rows = std::min<long long>(rows, sp.rowLimitForce);
     return int(std::min<long long>(rows, kStripRowLimit));
 }
 
@@ -733,7 +743,6 @@ static size_t strip_smem_bytes(int rowCap, int cutCap, int workCap)
 {
     return size_t(rowCap) * 16 + size_t(cutCap) * 16 + size_t(workCap) * 2 + size_t(cutCap) * (2 + 2 + 4);
 }
-constexpr size_t kStripSmemLimit = 227 * 1024 - 4096;   // dynamic part: the opt-in maximum minus the kernel's static tables
 
 // Class-major layout of the coloured manifolds over S strips; `work` holds the colours.  On success with *usable the
 // context's schedule (slotJoint, pairIdx, bin table) is the strip layout; otherwise the caller lays out colour-major.
@@ -788,6 +797,12 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     {
         k_strip_feedback<<<1, 256, 0, c->stream>>>(S, sp.cost.as<long long>(), factor, factorFb, sp.measuredFeedback);
         c->launches++;
+        // A step that rebuilds its colouring lays out twice (colour.cu), and the second layout must not apply the same
+        // measured cost again on top of the first one's committed factors: squared factors squeeze strips until the layout
+        // is rejected and the step falls back to the grid-barrier forms (seen as one form-1 solve, and the first-time
+        // allocation of its streams, in the step of every rebuild).  The cost is consumed here; the strip kernel writes
+        // the next.  (Not in a deferred step: if it stops, the stage path lays out again from the same state.)
+        if (!c->def.active) PHYX_CUDA(cudaMemsetAsync(sp.cost.ptr, 0, size_t(S) * sizeof(long long), c->stream));
     }
     const Count Mc = c->count(M, &StepCtl::manifolds);
     k_strip_hist<<<grid, kBlock, 0, c->stream>>>(Mc, jb, work, rowOf, activity, c->manBody.as<int2>(), bodyOwner, c->islandRank, hist, cover, S,
@@ -799,11 +814,14 @@ int strip_layout(phyx_b200_ctx* c, int S, const int2* jb, const int* work, const
     if (S > 1)
     {
         PHYX_TRY(exclusive_scan_i32(c, cover, cover, nb, nullptr));
-        // width limit first, clean cuts last: a snapped cut is never moved again (a strip that ends up too wide for shared
-        // memory rejects the layout for this step)
+        // width limit first, then clean cuts, then the width limit again for the strips a snap made too wide
         k_strip_monotonic<<<1, 128, 0, c->stream>>>(S, rowLimit, sp.cuts.as<int>());
         k_strip_snap<<<S - 1, kBlock, 0, c->stream>>>(nb, S, std::max(1, nb / S / 2), cover, sp.cuts.as<int>());
-        k_strip_monotonic<<<1, 128, 0, c->stream>>>(S, nb, sp.cuts.as<int>());
+        // (the snap may have pulled a cut up to half a strip away: a strip that became wider than the limit gets its cut
+        // pulled back, which costs that cut its cleanness; leaving it rejected the whole layout for the step, and the
+        // step then ran on the grid-barrier forms, with the first-time allocation of their streams: seen at 1 M bodies
+        // as one form-1 solve and 2-140 ms of cudaMalloc in the step of a colour rebuild)
+        k_strip_monotonic<<<1, 128, 0, c->stream>>>(S, rowLimit, sp.cuts.as<int>());
         c->launches += 3;
     }
 
@@ -928,6 +946,7 @@ bool strip_apply_header(phyx_b200_ctx* c, const int* host)
     if (strip_smem_bytes(sp.maxStripRows + 9, sp.maxCutRows + 9, sp.maxBin + 9) > kStripSmemLimit) rejected |= kRejectSmem;
     if (sp.maxStripRows > 65000 || sp.maxCutRows > 65000 || sp.maxBin > 65000) rejected |= kRejectSmem;
     sp.rejected = rejected;
+    if (rejected) sp.lastReject = (rejected & 0xff) | (sp.strips << 8) | ((sp.maxStripRows / 64) << 20);
     sp.valid = rejected == 0;
     return sp.valid;
 }
