@@ -344,6 +344,7 @@ void phyx_b200_destroy(phyx_b200_ctx* c)
     cudaStreamDestroy(c->stream);
     if (c->mailboxHost) cudaFreeHost(c->mailboxHost);
     if (c->mailboxSeqDev) cudaFree(c->mailboxSeqDev);
+    if (t_ctxAllocs == &c->allocCount) t_ctxAllocs = nullptr;   // (this thread's allocation counter pointed into the context)
     delete c;
 }
 
